@@ -1,0 +1,125 @@
+"""ctypes binding of the C ABI in include/az_engine.h (libaz_engine.so, built in-tree by nvcc).
+
+There is no fallback: if the library is missing or fails to load, `load()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libaz_engine.so")
+SOURCES = ["az_engine.cu"]
+HEADERS = ["az_eval.cuh", "c4_bitboard.cuh", os.path.join("..", "..", "include", "az_engine.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",  # fp64 PUCT must round every operation separately, like CPython
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> alphazero-implementation_b200/libaz_engine.so"""
+    if not force and not _stale():
+        return LIB_PATH
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed ({' '.join(cmd)}):\n{proc.stdout}\n{proc.stderr}")
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+def library_available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+class AzConfig(C.Structure):
+    _fields_ = [
+        ("height", C.c_int32), ("width", C.c_int32), ("count", C.c_int32), ("num_games", C.c_int32),
+        ("num_simulations", C.c_int32), ("device", C.c_int32), ("lanes_per_tree", C.c_int32), ("reserved", C.c_int32),
+        ("c_puct", C.c_double),
+    ]
+
+
+class AzStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("simulations", "evaluations", "levels", "children_created", "backup_nodes",
+                                           "moves", "episodes", "reserved")]
+
+
+P = C.c_void_p  # device pointers and streams cross the boundary as plain addresses
+I32, I64 = C.c_int32, C.c_int64
+
+# name -> (restype, argtypes); the single source of truth for tests/test_abi.py as well
+SIGNATURES = {
+    "az_abi_version": (I32, []),
+    "az_last_error": (C.c_char_p, [P]),
+    "az_create": (I32, [C.POINTER(AzConfig), C.POINTER(P)]),
+    "az_destroy": (I32, [P]),
+    "az_device_bytes": (I64, [P]),
+    "az_env_step": (I32, [P, P, P, P, P, I64, P, P, P, P, P, P, P, P]),
+    "az_state_info": (I32, [P, P, P, P, I64, P, P, P, P]),
+    "az_masked_softmax": (I32, [P, P, P, I64, P, P]),
+    "az_encode_states": (I32, [P, P, P, P, I64, P, I32, P]),
+    "az_reset_games": (I32, [P, C.c_uint64, C.c_uint64, I32, P]),
+    "az_set_roots": (I32, [P, P, P, P, I32, P]),
+    "az_run_simulations": (I32, [P, I32, I32, P]),
+    "az_select_leaves": (I32, [P, P]),
+    "az_gather_leaves": (I32, [P, P, I32, P]),
+    "az_expand_backup": (I32, [P, P, P, I32, P]),
+    "az_leaf_info": (I32, [P, P, P, P, P, P, P]),
+    "az_root_stats": (I32, [P, P, P, P, P, P, P, P, P]),
+    "az_tree_capacity": (I32, [P]),
+    "az_export_tree": (I32, [P, I32, P, P, P, P, C.POINTER(I32)]),
+    "az_sample_moves": (I32, [P, P, P, P]),
+    "az_episode_counts": (I32, [P, C.POINTER(I64), C.POINTER(I64), P]),
+    "az_drain_episodes": (I32, [P, I64, I64, P, P, P, P, P, P, P, P, P, C.POINTER(I64), C.POINTER(I64), P]),
+    "az_get_stats": (I32, [P, C.POINTER(AzStats), P]),
+    "az_reset_stats": (I32, [P, P]),
+    "az_launch_count": (I64, [P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libaz_engine.so.  Raises if it has not been built: there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if lib.az_abi_version() != 1:
+        raise RuntimeError(f"libaz_engine.so ABI version {lib.az_abi_version()} != 1; rebuild")
+    _lib = lib
+    return lib

@@ -1,0 +1,1112 @@
+// B200-native AlphaZero self-play engine: MCTS tree arena + Connect4 rules + leaf gather.
+// C ABI in include/az_engine.h.  Built for sm_100a only; there is no CPU path.
+//
+// Data layout in HBM (structure of arrays, tree-major, `cap` = roundup8(1 + 7*S) nodes per tree):
+//   W [E][cap] f64   value_sum      (node.py:14)      fp64 because Python sums doubles
+//   N [E][cap] u32   visit_count    (node.py:13)
+//   P [E][cap] f32   prior          (node.py:15; fp32 softmax output widened to double when scored)
+//   CB[E][cap] u32   index of the first child (children of a node are contiguous, ascending column
+//                    = dict insertion order of node.children, search.py:88-90); 0 = not expanded
+// Node 0 is the root.  Positions are NOT stored per node: the descent replays the chosen columns on
+// the root bitboards held in registers (a drop + win test is ~20 integer ops, a node-sized load is not).
+//
+// Work decomposition: a group of G lanes (G = 32: one warp per tree; G = 8: four trees per warp) owns
+// one tree for the whole launch.  Lane c (< 7) of every 8-lane subgroup handles column c of the current
+// node: it loads that child's N/W/P/CB (coalesced, neighbouring lanes read neighbouring words), scores
+// it in fp64 with the reference's operation order and rounding, and the best child is found with a
+// __shfl_xor butterfly on (score, column) — strict '>' with the lowest column winning ties, which is
+// the reference's first-maximum rule.  The tree is owned by one group, so its updates need no atomics;
+// __syncwarp orders them between lanes.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <cuda_bf16.h>
+
+#include "../../include/az_engine.h"
+#include "az_eval.cuh"
+#include "c4_bitboard.cuh"
+
+namespace {
+
+constexpr int PATH_STRIDE = 44;  // root + at most 42 plies (+1 pad)
+constexpr int MAX_PLIES = 42;
+constexpr int NSTAT = 6;  // per-tree counters: sims, evals, levels, children, moves, episodes
+
+struct Arena {
+    double *W;
+    uint32_t *N;
+    float *P;
+    uint32_t *CB;
+    uint64_t *root_bb0, *root_bb1;
+    uint8_t *root_player;
+    uint32_t *used;
+    int32_t *tree_err;
+    // leaves of the split (external evaluator) path
+    uint32_t *leaf_node;
+    uint64_t *leaf_bb0, *leaf_bb1;
+    uint8_t *leaf_player, *leaf_status, *leaf_depth;
+    uint32_t *path;  // [E][PATH_STRIDE]
+    uint32_t *tstats;  // [E][NSTAT]
+    // game in progress per slot
+    uint64_t *g_bb0, *g_bb1;  // [E][42]
+    uint8_t *g_player;        // [E][42]
+    int32_t *g_counts;        // [E][42][7]
+    int32_t *g_len;           // [E]
+    // finished-episode ring
+    unsigned long long *ring;  // [0] episodes, [1] samples, [2] dropped
+    int32_t *ep_slot, *ep_step, *ep_len;
+    int64_t *ep_offset;
+    int8_t *ep_outcome;  // [cap][2]
+    uint64_t *s_bb0, *s_bb1;
+    uint8_t *s_player;
+    int32_t *s_counts;  // [cap][7]
+    int64_t ep_cap, s_cap;
+    int cap;  // nodes per tree
+    int E;
+};
+
+// ------------------------------------------------------------------------------------------------
+// group helpers
+template <int G>
+__device__ __forceinline__ unsigned group_mask() {
+    if (G == 32) return 0xFFFFFFFFu;
+    return 0xFFu << (threadIdx.x & 24);
+}
+
+struct Leaf {
+    uint64_t b0, b1;
+    uint32_t node;
+    int pl;     // side to move at the leaf
+    int depth;  // number of moves below the root
+    bool win;   // the move into the leaf made 4-in-line (mover = pl ^ 1)
+    bool term;  // win or board full
+};
+
+// AlphaZeroSearch.select_child repeated until an unexpanded node (search.py:72-73, 27-46).
+// `path[d]` receives the node index at depth d.  Every lane of the group returns the same Leaf.
+template <int G>
+__device__ __forceinline__ Leaf descend(const double *__restrict__ Wt, const uint32_t *__restrict__ Nt,
+                                        const float *__restrict__ Pt, const uint32_t *__restrict__ CBt,
+                                        uint64_t rb0, uint64_t rb1, int rpl, double c_puct, uint32_t *path,
+                                        unsigned gmask, uint32_t &levels) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & 24;  // first lane of my 8-lane subgroup
+    const int c = lane & 7;     // the column this lane scores (7 = none)
+    const bool writer = (threadIdx.x & (G - 1)) == 0;
+    Leaf L;
+    L.b0 = rb0;
+    L.b1 = rb1;
+    L.pl = rpl;
+    L.node = 0;
+    L.depth = 0;
+    uint32_t cb = CBt[0];
+    uint32_t n_parent = Nt[0];
+    if (writer) path[0] = 0;
+    while (cb != 0) {
+        const uint64_t occ = L.b0 | L.b1;
+        const bool my_legal = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);
+        const unsigned legal = (__ballot_sync(gmask, my_legal) >> sub) & 0x7Fu;
+        const int j = __popc(legal & ((1u << c) - 1u));
+        double score = -INFINITY;
+        uint32_t n = 0, ccb = 0;
+        if (my_legal) {
+            const uint32_t idx = cb + j;
+            n = Nt[idx];
+            const double w = Wt[idx];
+            const float p = Pt[idx];
+            ccb = CBt[idx];
+            // score = child.value + c * child.prior * sqrt(node.visit_count) / (1 + child.visit_count)
+            // evaluated left to right in fp64, one rounding per operation (search.py:33-40).
+            const double q = n ? __ddiv_rn(w, (double)n) : 0.0;
+            const double sq = __dsqrt_rn((double)n_parent);
+            const double u = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, (double)p), sq), (double)(1u + n));
+            score = __dadd_rn(q, u);
+        }
+        int bc = c;
+#pragma unroll
+        for (int off = 4; off >= 1; off >>= 1) {
+            const double os = __shfl_xor_sync(gmask, score, off);
+            const int oc = __shfl_xor_sync(gmask, bc, off);
+            if (os > score || (os == score && oc < bc)) {
+                score = os;
+                bc = oc;
+            }
+        }
+        n_parent = __shfl_sync(gmask, n, sub + bc);
+        const uint32_t next_cb = __shfl_sync(gmask, ccb, sub + bc);
+        // Action.sample_next_state(): drop in column bc, flip the side to move
+        const uint64_t bit = c4::drop_bit(occ, bc);
+        if (L.pl == 0) L.b0 |= bit; else L.b1 |= bit;
+        L.pl ^= 1;
+        L.node = cb + __popc(legal & ((1u << bc) - 1u));
+        cb = next_cb;
+        L.depth++;
+        if (writer) path[L.depth] = L.node;
+        levels++;
+    }
+    // Node.is_terminal of the leaf (node.py:61-63).  Interior nodes are never terminal (a terminal
+    // node is never expanded), so only the last mover's stones need the line test.
+    L.win = false;
+    L.term = false;
+    if (L.depth > 0) {
+        L.win = c4::has4_nb(L.pl ? L.b0 : L.b1);  // mover = pl ^ 1
+        L.term = L.win || c4::is_full(L.b0 | L.b1);
+    }
+    return L;
+}
+
+// AlphaZeroSearch.backpropagate (search.py:48-57) along the recorded path: the leaf gets +v, the sign
+// flips going up except across a terminal leaf.  Stops at the current root (older ancestors are never
+// read again).
+template <int G>
+__device__ __forceinline__ void backup(double *Wt, uint32_t *Nt, const uint32_t *path, int depth, double v,
+                                       bool leaf_terminal) {
+    for (int i = threadIdx.x & (G - 1); i <= depth; i += G) {
+        const uint32_t nd = path[i];
+        const int d = depth - i;
+        const bool neg = leaf_terminal ? (d >= 1 && ((d - 1) & 1)) : (d & 1);
+        Wt[nd] = __dadd_rn(Wt[nd], neg ? -v : v);
+        Nt[nd] += 1u;
+    }
+}
+
+// node.add_child for every legal column (search.py:88-90): children contiguous at `first`, zeroed statistics.
+__device__ __forceinline__ void write_child(double *Wt, uint32_t *Nt, float *Pt, uint32_t *CBt, uint32_t idx,
+                                            float prior) {
+    Wt[idx] = 0.0;
+    Nt[idx] = 0u;
+    Pt[idx] = prior;
+    CBt[idx] = 0u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused search: all S simulations of a tree in one launch, built-in evaluator
+template <int G, int EVAL>
+__global__ void __launch_bounds__(G == 32 ? 128 : 64)
+k_run_sims(Arena a, int n_active, int S, double c_puct) {
+    constexpr int THREADS = (G == 32) ? 128 : 64;
+    constexpr int TREES = THREADS / G;
+    __shared__ uint32_t s_path[TREES][PATH_STRIDE];
+    const int tib = threadIdx.x / G;
+    const int t = blockIdx.x * TREES + tib;
+    if (t >= n_active) return;
+    if (a.tree_err[t]) return;
+    const unsigned gmask = group_mask<G>();
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & 24;
+    const int c = lane & 7;
+    const bool writer = (threadIdx.x & (G - 1)) == 0;
+    const bool first_sub = (threadIdx.x & (G - 1)) < 8;
+
+    const size_t base = (size_t)t * a.cap;
+    double *Wt = a.W + base;
+    uint32_t *Nt = a.N + base;
+    float *Pt = a.P + base;
+    uint32_t *CBt = a.CB + base;
+    uint32_t *path = s_path[tib];
+    const uint64_t rb0 = a.root_bb0[t], rb1 = a.root_bb1[t];
+    const int rpl = a.root_player[t];
+    uint32_t used = a.used[t];
+    uint32_t levels = 0, evals = 0, children = 0;
+
+    for (int s = 0; s < S; ++s) {
+        Leaf L = descend<G>(Wt, Nt, Pt, CBt, rb0, rb1, rpl, c_puct, path, gmask, levels);
+        double v;
+        if (L.term) {
+            // value = reward[parent.state.player]: the mover's own reward, +1 on a win, 0 on a draw (search.py:76)
+            v = L.win ? 1.0 : 0.0;
+        } else {
+            const uint64_t occ = L.b0 | L.b1;
+            const bool my_legal = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);
+            const unsigned legal = (__ballot_sync(gmask, my_legal) >> sub) & 0x7Fu;
+            const int k = __popc(legal);
+            const int j = __popc(legal & ((1u << c) - 1u));
+            float prior, val;
+            if (EVAL == AZ_EVAL_UNIFORM) {
+                prior = __fdiv_rn(1.0f, (float)k);
+                val = 0.0f;
+            } else {
+                const uint64_t h = azeval::board_hash(L.b0, L.b1, L.pl);
+                prior = __fdiv_rn((float)azeval::hash_weight(h, c), (float)azeval::hash_weight_total(h, legal));
+                const float v0 = azeval::hash_value0(h);
+                val = L.pl == 0 ? v0 : -v0;
+            }
+            if (my_legal && first_sub) write_child(Wt, Nt, Pt, CBt, used + j, prior);
+            if (writer) CBt[L.node] = used;
+            used += k;
+            children += k;
+            evals++;
+            v = (double)val;  // value[node.state.player] (search.py:91)
+        }
+        __syncwarp(gmask);
+        backup<G>(Wt, Nt, path, L.depth, v, L.term);
+        __syncwarp(gmask);
+    }
+    if (writer) {
+        a.used[t] = used;
+        uint32_t *st = a.tstats + (size_t)t * NSTAT;
+        st[0] += (uint32_t)S;
+        st[1] += evals;
+        st[2] += levels;
+        st[3] += children;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// split path, step 1: search.py:69-79
+template <int G>
+__global__ void __launch_bounds__(G == 32 ? 128 : 64) k_select(Arena a, int n_active, double c_puct) {
+    constexpr int THREADS = (G == 32) ? 128 : 64;
+    constexpr int TREES = THREADS / G;
+    const int t = blockIdx.x * TREES + threadIdx.x / G;
+    if (t >= n_active) return;
+    const bool writer = (threadIdx.x & (G - 1)) == 0;
+    if (a.tree_err[t]) {
+        if (writer) a.leaf_status[t] = AZ_LEAF_IDLE;
+        return;
+    }
+    const unsigned gmask = group_mask<G>();
+    const size_t base = (size_t)t * a.cap;
+    double *Wt = a.W + base;
+    uint32_t *Nt = a.N + base;
+    uint32_t *path = a.path + (size_t)t * PATH_STRIDE;
+    uint32_t levels = 0;
+    Leaf L = descend<G>(Wt, Nt, a.P + base, a.CB + base, a.root_bb0[t], a.root_bb1[t], a.root_player[t], c_puct,
+                        path, gmask, levels);
+    if (writer) {
+        a.leaf_node[t] = L.node;
+        a.leaf_bb0[t] = L.b0;
+        a.leaf_bb1[t] = L.b1;
+        a.leaf_player[t] = (uint8_t)L.pl;
+        a.leaf_depth[t] = (uint8_t)L.depth;
+        a.leaf_status[t] = L.term ? AZ_LEAF_TERMINAL : AZ_LEAF_EVAL;
+        uint32_t *st = a.tstats + (size_t)t * NSTAT;
+        st[0] += 1u;
+        st[2] += levels;
+    }
+    if (L.term) {
+        __syncwarp(gmask);
+        backup<G>(Wt, Nt, path, L.depth, L.win ? 1.0 : 0.0, true);
+    }
+}
+
+// split path, step 3: search.py:87-91 with the evaluator's outputs
+template <int G>
+__global__ void __launch_bounds__(G == 32 ? 128 : 64)
+k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const float *__restrict__ values,
+                int policy_kind) {
+    constexpr int THREADS = (G == 32) ? 128 : 64;
+    constexpr int TREES = THREADS / G;
+    const int t = blockIdx.x * TREES + threadIdx.x / G;
+    if (t >= n_active) return;
+    if (a.leaf_status[t] != AZ_LEAF_EVAL) return;
+    const unsigned gmask = group_mask<G>();
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & 24;
+    const int c = lane & 7;
+    const bool writer = (threadIdx.x & (G - 1)) == 0;
+    const bool first_sub = (threadIdx.x & (G - 1)) < 8;
+    const size_t base = (size_t)t * a.cap;
+    double *Wt = a.W + base;
+    uint32_t *Nt = a.N + base;
+    const uint64_t occ = a.leaf_bb0[t] | a.leaf_bb1[t];
+    const int pl = a.leaf_player[t];
+    const uint32_t node = a.leaf_node[t];
+    const int depth = a.leaf_depth[t];
+    const uint32_t used = a.used[t];
+    const bool my_legal = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);
+    const unsigned legal = (__ballot_sync(gmask, my_legal) >> sub) & 0x7Fu;
+    const int k = __popc(legal);
+    const int j = __popc(legal & ((1u << c) - 1u));
+    float x = my_legal ? policy[(size_t)t * 7 + c] : -INFINITY;
+    float prior;
+    if (policy_kind == AZ_POLICY_PRIORS) {
+        prior = x;
+    } else {
+        // F.softmax over the logits of the legal columns only, fp32 (model.py:29-35)
+        float m = x;
+#pragma unroll
+        for (int off = 4; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, off));
+        const float e = my_legal ? expf(x - m) : 0.0f;
+        float sum = e;
+#pragma unroll
+        for (int off = 4; off >= 1; off >>= 1) sum += __shfl_xor_sync(gmask, sum, off);
+        prior = __fdiv_rn(e, sum);
+    }
+    if (my_legal && first_sub) write_child(Wt, Nt, a.P + base, a.CB + base, used + j, prior);
+    const double v = (double)values[(size_t)t * 2 + pl];
+    if (writer) {
+        a.CB[base + node] = used;
+        a.used[t] = used + k;
+        a.leaf_status[t] = AZ_LEAF_IDLE;  // consumed: a second az_expand_backup without a select is a no-op
+        uint32_t *st = a.tstats + (size_t)t * NSTAT;
+        st[1] += 1u;
+        st[3] += (uint32_t)k;
+    }
+    __syncwarp(gmask);
+    backup<G>(Wt, Nt, a.path + (size_t)t * PATH_STRIDE, depth, v, false);
+}
+
+// ------------------------------------------------------------------------------------------------
+// plane encoders.  One thread produces 4 consecutive output elements (16-byte / 8-byte stores).
+__device__ __forceinline__ float plane_value(uint64_t b0, uint64_t b1, int pl, bool live, int layout, int e) {
+    // e = element index inside one position's block
+    if (!live) return 0.0f;
+    if (layout == AZ_LAYOUT_GRID_F32) {
+        const int r = e / 7, col = e % 7;  // [6][7], row 0 = bottom
+        const int bit = col * 7 + r;
+        return ((b0 >> bit) & 1ull) ? 0.0f : (((b1 >> bit) & 1ull) ? 1.0f : -1.0f);
+    }
+    int ch, r, col;
+    if (layout == AZ_LAYOUT_PLANES_BF16_NHWC) {  // [6][7][8]
+        ch = e & 7;
+        col = (e >> 3) % 7;
+        r = (e >> 3) / 7;
+        if (ch > 2) return 0.0f;
+    } else {  // [3][6][7]
+        ch = e / 42;
+        r = (e % 42) / 7;
+        col = e % 7;
+    }
+    const int bit = col * 7 + r;
+    const uint64_t mine = pl ? b1 : b0, theirs = pl ? b0 : b1;
+    const uint64_t src = ch == 0 ? ~(b0 | b1) : (ch == 1 ? mine : theirs);  // empty, side to move, opponent (cnn.py:93-95)
+    return (float)((src >> bit) & 1ull);
+}
+
+__host__ __device__ inline int layout_elems(int layout) {
+    return layout == AZ_LAYOUT_GRID_F32 ? 42 : (layout == AZ_LAYOUT_PLANES_BF16_NHWC ? 336 : 126);
+}
+
+__global__ void __launch_bounds__(256)
+k_encode(const uint64_t *__restrict__ bb0, const uint64_t *__restrict__ bb1, const uint8_t *__restrict__ player,
+         const uint8_t *__restrict__ status, long long n, void *out, int layout) {
+    const int elems = layout_elems(layout);
+    const long long total = n * elems;
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= total) return;
+    float v[4];
+    long long t = i0 / elems;
+    int e = (int)(i0 - t * elems);
+    uint64_t b0 = bb0[t], b1 = bb1[t];
+    int pl = player[t];
+    bool live = status ? (status[t] == AZ_LEAF_EVAL) : true;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (i0 + q < total) {
+            if (e == elems) {
+                e = 0;
+                ++t;
+                b0 = bb0[t];
+                b1 = bb1[t];
+                pl = player[t];
+                live = status ? (status[t] == AZ_LEAF_EVAL) : true;
+            }
+            v[q] = plane_value(b0, b1, pl, live, layout, e);
+            ++e;
+        } else {
+            v[q] = 0.0f;
+        }
+    }
+    const bool is_bf16 = (layout == AZ_LAYOUT_PLANES_BF16 || layout == AZ_LAYOUT_PLANES_BF16_NHWC);
+    if (i0 + 3 < total) {
+        if (is_bf16) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t *>(&lo);
+            pk.y = *reinterpret_cast<uint32_t *>(&hi);
+            reinterpret_cast<uint2 *>(out)[i0 >> 2] = pk;
+        } else {
+            reinterpret_cast<float4 *>(out)[i0 >> 2] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    } else {
+        for (int q = 0; q < 4 && i0 + q < total; ++q) {
+            if (is_bf16) reinterpret_cast<__nv_bfloat16 *>(out)[i0 + q] = __float2bfloat16_rn(v[q]);
+            else reinterpret_cast<float *>(out)[i0 + q] = v[q];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rules kernels (one thread per position)
+__global__ void __launch_bounds__(256)
+k_env_step(const uint64_t *__restrict__ bb0, const uint64_t *__restrict__ bb1, const uint8_t *__restrict__ player,
+           const uint8_t *__restrict__ col, long long n, uint64_t *o0, uint64_t *o1, uint8_t *opl, uint8_t *olegal,
+           uint8_t *oended, int8_t *oreward, uint8_t *ostatus) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t b0 = bb0[i], b1 = bb1[i];
+    int pl = player[i] & 1;
+    const int cc = col[i];
+    c4::Terminal T = c4::terminal_of(b0, b1);
+    uint8_t status = 1;
+    if (!T.ended && cc < c4::W && !(((b0 | b1) >> (c4::STRIDE * cc + 5)) & 1ull)) {
+        const uint64_t bit = c4::drop_bit(b0 | b1, cc);
+        if (pl == 0) b0 |= bit; else b1 |= bit;
+        const bool win = c4::has4(pl ? b1 : b0);
+        T.ended = win || c4::is_full(b0 | b1);
+        T.reward0 = win ? (pl == 0 ? 1 : -1) : 0;
+        pl ^= 1;
+        status = 0;
+    }
+    if (o0) o0[i] = b0;
+    if (o1) o1[i] = b1;
+    if (opl) opl[i] = (uint8_t)pl;
+    if (olegal) olegal[i] = T.ended ? 0 : (uint8_t)c4::legal_mask(b0 | b1);
+    if (oended) oended[i] = T.ended ? 1 : 0;
+    if (oreward) {
+        oreward[2 * i] = T.reward0;
+        oreward[2 * i + 1] = (int8_t)-T.reward0;
+    }
+    if (ostatus) ostatus[i] = status;
+}
+
+__global__ void __launch_bounds__(256)
+k_state_info(const uint64_t *__restrict__ bb0, const uint64_t *__restrict__ bb1, long long n, uint8_t *olegal,
+             uint8_t *oended, int8_t *oreward) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t b0 = bb0[i], b1 = bb1[i];
+    const c4::Terminal T = c4::terminal_of(b0, b1);
+    if (olegal) olegal[i] = T.ended ? 0 : (uint8_t)c4::legal_mask(b0 | b1);
+    if (oended) oended[i] = T.ended ? 1 : 0;
+    if (oreward) {
+        oreward[2 * i] = T.reward0;
+        oreward[2 * i + 1] = (int8_t)-T.reward0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_masked_softmax(const float *__restrict__ logits, const uint8_t *__restrict__ legal, long long n, float *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t lg = legal[i] & 0x7Fu;
+    float x[7], m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        x[c] = logits[i * 7 + c];
+        if ((lg >> c) & 1u) m = fmaxf(m, x[c]);
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        x[c] = ((lg >> c) & 1u) ? expf(x[c] - m) : 0.0f;
+        sum += x[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 7; ++c) out[i * 7 + c] = ((lg >> c) & 1u) ? __fdiv_rn(x[c], sum) : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// roots / results
+__device__ __forceinline__ void reset_tree(const Arena &a, int t) {
+    const size_t base = (size_t)t * a.cap;
+    a.W[base] = 0.0;
+    a.N[base] = 0u;
+    a.P[base] = 0.0f;
+    a.CB[base] = 0u;
+    a.used[t] = 1u;
+}
+
+__global__ void __launch_bounds__(256)
+k_set_roots(Arena a, const uint64_t *bb0, const uint64_t *bb1, const uint8_t *player, uint64_t c0, uint64_t c1,
+            int cpl, int n, int clear_logs) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint64_t b0 = bb0 ? bb0[t] : c0, b1 = bb1 ? bb1[t] : c1;
+    const int pl = player ? (player[t] & 1) : cpl;
+    a.root_bb0[t] = b0;
+    a.root_bb1[t] = b1;
+    a.root_player[t] = (uint8_t)pl;
+    a.tree_err[t] = c4::terminal_of(b0, b1).ended ? AZ_TREE_ROOT_ENDED : AZ_TREE_OK;
+    a.leaf_status[t] = AZ_LEAF_IDLE;
+    reset_tree(a, t);
+    if (clear_logs) a.g_len[t] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_root_stats(Arena a, int n, int32_t *child_N, double *child_W, float *child_P, double *root_W, int32_t *root_N,
+             uint8_t *legal_out, int32_t *err) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const size_t base = (size_t)t * a.cap;
+    const uint32_t cb = a.CB[base];
+    const int terr = a.tree_err[t];
+    const uint32_t legal = terr ? 0u : c4::legal_mask(a.root_bb0[t] | a.root_bb1[t]);
+    int j = 0;
+    for (int c = 0; c < 7; ++c) {
+        const bool has = cb != 0 && ((legal >> c) & 1u);
+        const size_t idx = base + cb + j;
+        if (child_N) child_N[(size_t)t * 7 + c] = has ? (int32_t)a.N[idx] : 0;
+        if (child_W) child_W[(size_t)t * 7 + c] = has ? a.W[idx] : 0.0;
+        if (child_P) child_P[(size_t)t * 7 + c] = has ? a.P[idx] : 0.0f;
+        if (has) ++j;
+    }
+    if (root_W) root_W[t] = a.W[base];
+    if (root_N) root_N[t] = (int32_t)a.N[base];
+    if (legal_out) legal_out[t] = (uint8_t)legal;
+    if (err) err[t] = terr;
+}
+
+__global__ void __launch_bounds__(256)
+k_leaf_info(Arena a, int n, uint64_t *o0, uint64_t *o1, uint8_t *opl, uint8_t *olegal, uint8_t *ostatus) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint8_t st = a.leaf_status[t];
+    if (o0) o0[t] = a.leaf_bb0[t];
+    if (o1) o1[t] = a.leaf_bb1[t];
+    if (opl) opl[t] = a.leaf_player[t];
+    if (olegal) olegal[t] = st == AZ_LEAF_EVAL ? (uint8_t)c4::legal_mask(a.leaf_bb0[t] | a.leaf_bb1[t]) : 0;
+    if (ostatus) ostatus[t] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// self-play move step (episode_generator.py:53-78, node.py:23-42), one thread per slot
+__global__ void __launch_bounds__(128)
+k_sample_moves(Arena a, int n, const double *__restrict__ uniforms, uint8_t *finished, int step, uint64_t init0,
+               uint64_t init1, int initpl) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    if (finished) finished[t] = 0;
+    if (a.tree_err[t]) return;
+    const size_t base = (size_t)t * a.cap;
+    const uint32_t cb = a.CB[base];
+    if (cb == 0) return;  // no search ran on this root
+    uint64_t b0 = a.root_bb0[t], b1 = a.root_bb1[t];
+    int pl = a.root_player[t];
+    const uint32_t legal = c4::legal_mask(b0 | b1);
+    const int k = __popc(legal);
+    const double denom = (double)((int)a.N[base] - 1);  // improved_policy denominator (node.py:27)
+    // sample = (state, improved_policy) recorded before the move (episode_generator.py:56-62)
+    const int len = a.g_len[t];
+    int32_t cnt[7];
+    double cdf[7];  // indexed by column (static indexing only: stays in registers)
+    double acc = 0.0;
+    {
+        int j = 0;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            cnt[c] = 0;
+            cdf[c] = 0.0;
+            if ((legal >> c) & 1u) {
+                const int32_t nc = (int32_t)a.N[base + cb + j];
+                cnt[c] = nc;
+                const double p = __ddiv_rn((double)nc, denom);
+                acc = (j == 0) ? p : __dadd_rn(acc, p);  // p.cumsum()
+                cdf[c] = acc;
+                ++j;
+            }
+        }
+    }
+    if (len < MAX_PLIES) {
+        const size_t o = (size_t)t * MAX_PLIES + len;
+        a.g_bb0[o] = b0;
+        a.g_bb1[o] = b1;
+        a.g_player[o] = (uint8_t)pl;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) a.g_counts[o * 7 + c] = cnt[c];
+    }
+    const int new_len = len + 1;
+    // np.random.choice(k, p): cdf /= cdf[-1]; idx = searchsorted(cdf, u, side='right') = #{cdf <= u}
+    const double u = uniforms[t];
+    const double last = acc;
+    int idx = 0;
+#pragma unroll
+    for (int c = 0; c < 7; ++c)
+        if (((legal >> c) & 1u) && __ddiv_rn(cdf[c], last) <= u) ++idx;
+    if (idx >= k) idx = k - 1;
+    const int col = c4::nth_legal_column(legal, idx);
+    const uint64_t bit = c4::drop_bit(b0 | b1, col);
+    if (pl == 0) b0 |= bit; else b1 |= bit;
+    const bool win = c4::has4(pl ? b1 : b0);
+    const bool ended = win || c4::is_full(b0 | b1);
+    uint32_t *st = a.tstats + (size_t)t * NSTAT;
+    st[4] += 1u;
+    if (!ended) {
+        a.root_bb0[t] = b0;
+        a.root_bb1[t] = b1;
+        a.root_player[t] = (uint8_t)(pl ^ 1);
+        a.g_len[t] = new_len;
+    } else {
+        // outcome to every sample (episode.py:52-54); emit; recycle the slot (episode_generator.py:71-78)
+        const int8_t r0 = win ? (pl == 0 ? 1 : -1) : 0;
+        const unsigned long long e = atomicAdd(&a.ring[0], 1ull);
+        const unsigned long long o = atomicAdd(&a.ring[1], (unsigned long long)new_len);
+        if ((long long)e < a.ep_cap && (long long)(o + new_len) <= a.s_cap) {
+            a.ep_slot[e] = t;
+            a.ep_step[e] = step;
+            a.ep_len[e] = new_len;
+            a.ep_offset[e] = (int64_t)o;
+            a.ep_outcome[2 * e] = r0;
+            a.ep_outcome[2 * e + 1] = (int8_t)-r0;
+            for (int q = 0; q < new_len; ++q) {
+                const size_t src = (size_t)t * MAX_PLIES + q;
+                a.s_bb0[o + q] = a.g_bb0[src];
+                a.s_bb1[o + q] = a.g_bb1[src];
+                a.s_player[o + q] = a.g_player[src];
+                for (int c = 0; c < 7; ++c) a.s_counts[(o + q) * 7 + c] = a.g_counts[src * 7 + c];
+            }
+        } else {
+            atomicAdd(&a.ring[2], 1ull);
+        }
+        st[5] += 1u;
+        a.root_bb0[t] = init0;
+        a.root_bb1[t] = init1;
+        a.root_player[t] = (uint8_t)initpl;
+        a.g_len[t] = 0;
+        if (finished) finished[t] = 1;
+    }
+    reset_tree(a, t);  // no subtree reuse: the new root has no children (node.py:37-41)
+}
+
+__global__ void __launch_bounds__(256) k_sum_stats(const uint32_t *__restrict__ tstats, int E, unsigned long long *tot) {
+    unsigned long long loc[NSTAT] = {0, 0, 0, 0, 0, 0};
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < E; t += gridDim.x * blockDim.x)
+        for (int q = 0; q < NSTAT; ++q) loc[q] += tstats[(size_t)t * NSTAT + q];
+    for (int q = 0; q < NSTAT; ++q) {
+        unsigned long long x = loc[q];
+        for (int off = 16; off >= 1; off >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, off);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&tot[q], x);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_zero_u32(uint32_t *p, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = 0u;
+}
+
+char g_create_error[512] = "";
+
+}  // namespace
+
+// ==================================================================================================
+struct az_engine {
+    az_config cfg;
+    Arena a;
+    int G;
+    int n_active;
+    int step;
+    uint64_t init0, init1;
+    int initpl;
+    bool have_init;
+    int64_t bytes;
+    int64_t launches;
+    unsigned long long *d_tot;   // [8] stats totals (device)
+    unsigned long long acc_tot[NSTAT];  // totals folded on the host across resets
+    void *allocs[64];
+    int n_allocs;
+    char err[512];
+};
+
+namespace {
+
+int fail(az_engine *h, int code, const char *fmt, const char *detail) {
+    if (h) snprintf(h->err, sizeof h->err, fmt, detail);
+    else snprintf(g_create_error, sizeof g_create_error, fmt, detail);
+    return code;
+}
+
+#define AZ_CUDA(h, call)                                                            \
+    do {                                                                            \
+        cudaError_t e_ = (call);                                                    \
+        if (e_ != cudaSuccess) return fail((h), AZ_E_CUDA, #call ": %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+#define AZ_LAUNCH_CHECK(h, name)                                                    \
+    do {                                                                            \
+        cudaError_t e_ = cudaGetLastError();                                        \
+        if (e_ != cudaSuccess) return fail((h), AZ_E_CUDA, name " launch: %s", cudaGetErrorString(e_)); \
+        (h)->launches++;                                                            \
+    } while (0)
+
+template <typename T>
+int dev_alloc(az_engine *h, T **p, size_t count) {
+    void *q = nullptr;
+    const size_t bytes = (count ? count : 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(h, AZ_E_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    if (h->n_allocs >= 64) return fail(h, AZ_E_INVALID, "%s", "allocation table full");
+    h->allocs[h->n_allocs++] = q;
+    h->bytes += (int64_t)bytes;
+    *p = (T *)q;
+    return AZ_OK;
+}
+
+inline cudaStream_t S(void *s) { return (cudaStream_t)s; }
+inline int blocks_for(long long n, int per_block) { return (int)((n + per_block - 1) / per_block); }
+
+int set_device(az_engine *h) {
+    AZ_CUDA(h, cudaSetDevice(h->cfg.device));
+    return AZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t az_abi_version(void) { return AZ_ABI_VERSION; }
+
+const char *az_last_error(const az_engine *h) { return h ? h->err : g_create_error; }
+
+int32_t az_create(const az_config *cfg, az_engine **out) {
+    if (!cfg || !out) return fail(nullptr, AZ_E_INVALID, "%s", "az_create: null argument");
+    *out = nullptr;
+    if (cfg->height != 6 || cfg->width != 7 || cfg->count != 4)
+        return fail(nullptr, AZ_E_INVALID, "%s", "az_create: only Config(6,7,4) is supported (scripts/train.py:12)");
+    if (cfg->num_games < 1 || cfg->num_simulations < 1 || cfg->num_simulations > 1000000)
+        return fail(nullptr, AZ_E_INVALID, "%s", "az_create: num_games >= 1 and 1 <= num_simulations <= 1e6 required");
+    int G = cfg->lanes_per_tree == 0 ? 8 : cfg->lanes_per_tree;
+    if (G != 8 && G != 32) return fail(nullptr, AZ_E_INVALID, "%s", "az_create: lanes_per_tree must be 8 or 32");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, AZ_E_CUDA, "az_create: no CUDA device (%s); this engine has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, AZ_E_INVALID, "%s", "az_create: bad device ordinal");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, AZ_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, AZ_E_CUDA, "az_create: device is not sm_100 (%s); kernels are built for sm_100a only", prop.name);
+
+    az_engine *h = (az_engine *)calloc(1, sizeof(az_engine));
+    if (!h) return fail(nullptr, AZ_E_NOMEM, "%s", "az_create: host allocation failed");
+    h->cfg = *cfg;
+    h->G = G;
+    h->n_active = cfg->num_games;
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) {
+        free(h);
+        return fail(nullptr, AZ_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    }
+    Arena &a = h->a;
+    const int E = cfg->num_games;
+    a.E = E;
+    a.cap = ((1 + 7 * cfg->num_simulations) + 7) & ~7;
+    a.ep_cap = 2ll * E + 64;
+    a.s_cap = a.ep_cap * MAX_PLIES;
+    const size_t nodes = (size_t)E * a.cap;
+    int rc = AZ_OK;
+#define AL(ptr, count) if (rc == AZ_OK) rc = dev_alloc(h, &(ptr), (size_t)(count))
+    AL(a.W, nodes); AL(a.N, nodes); AL(a.P, nodes); AL(a.CB, nodes);
+    AL(a.root_bb0, E); AL(a.root_bb1, E); AL(a.root_player, E); AL(a.used, E); AL(a.tree_err, E);
+    AL(a.leaf_node, E); AL(a.leaf_bb0, E); AL(a.leaf_bb1, E); AL(a.leaf_player, E); AL(a.leaf_status, E);
+    AL(a.leaf_depth, E); AL(a.path, (size_t)E * PATH_STRIDE); AL(a.tstats, (size_t)E * NSTAT);
+    AL(a.g_bb0, (size_t)E * MAX_PLIES); AL(a.g_bb1, (size_t)E * MAX_PLIES); AL(a.g_player, (size_t)E * MAX_PLIES);
+    AL(a.g_counts, (size_t)E * MAX_PLIES * 7); AL(a.g_len, E);
+    AL(a.ring, 4);
+    AL(a.ep_slot, a.ep_cap); AL(a.ep_step, a.ep_cap); AL(a.ep_len, a.ep_cap); AL(a.ep_offset, a.ep_cap);
+    AL(a.ep_outcome, a.ep_cap * 2);
+    AL(a.s_bb0, a.s_cap); AL(a.s_bb1, a.s_cap); AL(a.s_player, a.s_cap); AL(a.s_counts, a.s_cap * 7);
+    AL(h->d_tot, 8);
+#undef AL
+    if (rc != AZ_OK) {
+        snprintf(g_create_error, sizeof g_create_error, "az_create: %s", h->err);
+        for (int i = 0; i < h->n_allocs; ++i) cudaFree(h->allocs[i]);
+        free(h);
+        return rc;
+    }
+    cudaMemset(a.tstats, 0, (size_t)E * NSTAT * sizeof(uint32_t));
+    cudaMemset(a.ring, 0, 4 * sizeof(unsigned long long));
+    cudaMemset(h->d_tot, 0, 8 * sizeof(unsigned long long));
+    cudaMemset(a.g_len, 0, (size_t)E * sizeof(int32_t));
+    // every slot starts at the empty board, player 0 (Config.sample_initial_state())
+    k_set_roots<<<blocks_for(E, 256), 256>>>(a, nullptr, nullptr, nullptr, 0ull, 0ull, 0, E, 1);
+    h->launches++;
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        snprintf(g_create_error, sizeof g_create_error, "az_create: init failed: %s", cudaGetErrorString(e));
+        for (int i = 0; i < h->n_allocs; ++i) cudaFree(h->allocs[i]);
+        free(h);
+        return AZ_E_CUDA;
+    }
+    h->init0 = 0;
+    h->init1 = 0;
+    h->initpl = 0;
+    h->have_init = true;
+    *out = h;
+    return AZ_OK;
+}
+
+int32_t az_destroy(az_engine *h) {
+    if (!h) return AZ_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < h->n_allocs; ++i) cudaFree(h->allocs[i]);
+    free(h);
+    return AZ_OK;
+}
+
+int64_t az_device_bytes(const az_engine *h) { return h ? h->bytes : 0; }
+int64_t az_launch_count(const az_engine *h) { return h ? h->launches : 0; }
+int32_t az_tree_capacity(const az_engine *h) { return h ? h->a.cap : 0; }
+
+int32_t az_env_step(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, const uint8_t *player, const uint8_t *col,
+                    int64_t n, uint64_t *o0, uint64_t *o1, uint8_t *opl, uint8_t *olegal, uint8_t *oended,
+                    int8_t *oreward, uint8_t *ostatus, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (n < 0 || (n > 0 && (!bb0 || !bb1 || !player || !col))) return fail(h, AZ_E_INVALID, "%s", "az_env_step: null input");
+    if (n == 0) return AZ_OK;
+    if (int rc = set_device(h)) return rc;
+    k_env_step<<<blocks_for(n, 256), 256, 0, S(stream)>>>(bb0, bb1, player, col, n, o0, o1, opl, olegal, oended, oreward,
+                                                         ostatus);
+    AZ_LAUNCH_CHECK(h, "k_env_step");
+    return AZ_OK;
+}
+
+int32_t az_state_info(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, const uint8_t *player, int64_t n,
+                      uint8_t *olegal, uint8_t *oended, int8_t *oreward, void *stream) {
+    (void)player;
+    if (!h) return AZ_E_INVALID;
+    if (n < 0 || (n > 0 && (!bb0 || !bb1))) return fail(h, AZ_E_INVALID, "%s", "az_state_info: null input");
+    if (n == 0) return AZ_OK;
+    if (int rc = set_device(h)) return rc;
+    k_state_info<<<blocks_for(n, 256), 256, 0, S(stream)>>>(bb0, bb1, n, olegal, oended, oreward);
+    AZ_LAUNCH_CHECK(h, "k_state_info");
+    return AZ_OK;
+}
+
+int32_t az_masked_softmax(az_engine *h, const float *logits, const uint8_t *legal, int64_t n, float *out, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (n < 0 || (n > 0 && (!logits || !legal || !out))) return fail(h, AZ_E_INVALID, "%s", "az_masked_softmax: null argument");
+    if (n == 0) return AZ_OK;
+    if (int rc = set_device(h)) return rc;
+    k_masked_softmax<<<blocks_for(n, 256), 256, 0, S(stream)>>>(logits, legal, n, out);
+    AZ_LAUNCH_CHECK(h, "k_masked_softmax");
+    return AZ_OK;
+}
+
+static int check_layout(az_engine *h, int layout) {
+    if (layout < AZ_LAYOUT_GRID_F32 || layout > AZ_LAYOUT_PLANES_BF16_NHWC) return fail(h, AZ_E_INVALID, "%s", "unknown plane layout");
+    return AZ_OK;
+}
+
+int32_t az_encode_states(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, const uint8_t *player, int64_t n,
+                         void *out, int32_t layout, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (n < 0 || (n > 0 && (!bb0 || !bb1 || !player || !out))) return fail(h, AZ_E_INVALID, "%s", "az_encode_states: null argument");
+    if (int rc = check_layout(h, layout)) return rc;
+    if (n == 0) return AZ_OK;
+    if (int rc = set_device(h)) return rc;
+    const long long quads = (n * layout_elems(layout) + 3) / 4;
+    k_encode<<<blocks_for(quads, 256), 256, 0, S(stream)>>>(bb0, bb1, player, nullptr, n, out, layout);
+    AZ_LAUNCH_CHECK(h, "k_encode");
+    return AZ_OK;
+}
+
+int32_t az_reset_games(az_engine *h, uint64_t init_bb0, uint64_t init_bb1, int32_t init_player, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if ((init_bb0 & init_bb1) || ((init_bb0 | init_bb1) & ~c4::BOARD) || (init_player != 0 && init_player != 1))
+        return fail(h, AZ_E_INVALID, "%s", "az_reset_games: invalid initial position");
+    if (int rc = set_device(h)) return rc;
+    const int E = h->a.E;
+    k_set_roots<<<blocks_for(E, 256), 256, 0, S(stream)>>>(h->a, nullptr, nullptr, nullptr, init_bb0, init_bb1, init_player,
+                                                          E, 1);
+    AZ_LAUNCH_CHECK(h, "k_set_roots");
+    AZ_CUDA(h, cudaMemsetAsync(h->a.ring, 0, 4 * sizeof(unsigned long long), S(stream)));
+    h->init0 = init_bb0;
+    h->init1 = init_bb1;
+    h->initpl = init_player;
+    h->have_init = true;
+    h->n_active = E;
+    h->step = 0;
+    return AZ_OK;
+}
+
+int32_t az_set_roots(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, const uint8_t *player, int32_t n,
+                     void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (n < 1 || n > h->a.E || !bb0 || !bb1 || !player) return fail(h, AZ_E_INVALID, "%s", "az_set_roots: need 1 <= n <= num_games and non-null positions");
+    if (int rc = set_device(h)) return rc;
+    k_set_roots<<<blocks_for(n, 256), 256, 0, S(stream)>>>(h->a, bb0, bb1, player, 0ull, 0ull, 0, n, 0);
+    AZ_LAUNCH_CHECK(h, "k_set_roots");
+    h->n_active = n;
+    return AZ_OK;
+}
+
+int32_t az_run_simulations(az_engine *h, int32_t num_sims, int32_t eval_kind, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (num_sims < 0) return fail(h, AZ_E_INVALID, "%s", "az_run_simulations: num_sims < 0");
+    if (num_sims > h->cfg.num_simulations)
+        return fail(h, AZ_E_INVALID, "%s", "az_run_simulations: num_sims exceeds the arena (1 + 7*num_simulations nodes per tree)");
+    if (eval_kind != AZ_EVAL_UNIFORM && eval_kind != AZ_EVAL_HASH) return fail(h, AZ_E_INVALID, "%s", "az_run_simulations: unknown evaluator");
+    if (num_sims == 0) return AZ_OK;
+    if (int rc = set_device(h)) return rc;
+    const int n = h->n_active;
+    const double c = h->cfg.c_puct;
+    if (h->G == 32) {
+        const int blocks = blocks_for(n, 4);
+        if (eval_kind == AZ_EVAL_UNIFORM) k_run_sims<32, AZ_EVAL_UNIFORM><<<blocks, 128, 0, S(stream)>>>(h->a, n, num_sims, c);
+        else k_run_sims<32, AZ_EVAL_HASH><<<blocks, 128, 0, S(stream)>>>(h->a, n, num_sims, c);
+    } else {
+        const int blocks = blocks_for(n, 8);
+        if (eval_kind == AZ_EVAL_UNIFORM) k_run_sims<8, AZ_EVAL_UNIFORM><<<blocks, 64, 0, S(stream)>>>(h->a, n, num_sims, c);
+        else k_run_sims<8, AZ_EVAL_HASH><<<blocks, 64, 0, S(stream)>>>(h->a, n, num_sims, c);
+    }
+    AZ_LAUNCH_CHECK(h, "k_run_sims");
+    return AZ_OK;
+}
+
+int32_t az_select_leaves(az_engine *h, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (int rc = set_device(h)) return rc;
+    const int n = h->n_active;
+    if (h->G == 32) k_select<32><<<blocks_for(n, 4), 128, 0, S(stream)>>>(h->a, n, h->cfg.c_puct);
+    else k_select<8><<<blocks_for(n, 8), 64, 0, S(stream)>>>(h->a, n, h->cfg.c_puct);
+    AZ_LAUNCH_CHECK(h, "k_select");
+    return AZ_OK;
+}
+
+int32_t az_gather_leaves(az_engine *h, void *out, int32_t layout, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (!out) return fail(h, AZ_E_INVALID, "%s", "az_gather_leaves: null output");
+    if (int rc = check_layout(h, layout)) return rc;
+    if (int rc = set_device(h)) return rc;
+    const long long n = h->n_active;
+    const long long quads = (n * layout_elems(layout) + 3) / 4;
+    k_encode<<<blocks_for(quads, 256), 256, 0, S(stream)>>>(h->a.leaf_bb0, h->a.leaf_bb1, h->a.leaf_player, h->a.leaf_status,
+                                                           n, out, layout);
+    AZ_LAUNCH_CHECK(h, "k_encode");
+    return AZ_OK;
+}
+
+int32_t az_expand_backup(az_engine *h, const float *policy, const float *values, int32_t policy_kind, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (!policy || !values) return fail(h, AZ_E_INVALID, "%s", "az_expand_backup: null evaluator output");
+    if (policy_kind != AZ_POLICY_LOGITS && policy_kind != AZ_POLICY_PRIORS) return fail(h, AZ_E_INVALID, "%s", "az_expand_backup: bad policy_kind");
+    if (int rc = set_device(h)) return rc;
+    const int n = h->n_active;
+    if (h->G == 32) k_expand_backup<32><<<blocks_for(n, 4), 128, 0, S(stream)>>>(h->a, n, policy, values, policy_kind);
+    else k_expand_backup<8><<<blocks_for(n, 8), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind);
+    AZ_LAUNCH_CHECK(h, "k_expand_backup");
+    return AZ_OK;
+}
+
+int32_t az_leaf_info(az_engine *h, uint64_t *o0, uint64_t *o1, uint8_t *opl, uint8_t *olegal, uint8_t *ostatus,
+                     void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (int rc = set_device(h)) return rc;
+    const int n = h->n_active;
+    k_leaf_info<<<blocks_for(n, 256), 256, 0, S(stream)>>>(h->a, n, o0, o1, opl, olegal, ostatus);
+    AZ_LAUNCH_CHECK(h, "k_leaf_info");
+    return AZ_OK;
+}
+
+int32_t az_root_stats(az_engine *h, int32_t *child_N, double *child_W, float *child_P, double *root_W, int32_t *root_N,
+                      uint8_t *legal, int32_t *err, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (int rc = set_device(h)) return rc;
+    const int n = h->n_active;
+    k_root_stats<<<blocks_for(n, 256), 256, 0, S(stream)>>>(h->a, n, child_N, child_W, child_P, root_W, root_N, legal, err);
+    AZ_LAUNCH_CHECK(h, "k_root_stats");
+    return AZ_OK;
+}
+
+int32_t az_export_tree(az_engine *h, int32_t slot, double *W, uint32_t *N, float *P, uint32_t *first_child,
+                       int32_t *used_host) {
+    if (!h) return AZ_E_INVALID;
+    if (slot < 0 || slot >= h->a.E) return fail(h, AZ_E_INVALID, "%s", "az_export_tree: bad slot");
+    if (int rc = set_device(h)) return rc;
+    AZ_CUDA(h, cudaDeviceSynchronize());
+    const size_t base = (size_t)slot * h->a.cap, cap = (size_t)h->a.cap;
+    if (W) AZ_CUDA(h, cudaMemcpy(W, h->a.W + base, cap * sizeof(double), cudaMemcpyDeviceToDevice));
+    if (N) AZ_CUDA(h, cudaMemcpy(N, h->a.N + base, cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+    if (P) AZ_CUDA(h, cudaMemcpy(P, h->a.P + base, cap * sizeof(float), cudaMemcpyDeviceToDevice));
+    if (first_child) AZ_CUDA(h, cudaMemcpy(first_child, h->a.CB + base, cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+    if (used_host) {
+        uint32_t u = 0;
+        AZ_CUDA(h, cudaMemcpy(&u, h->a.used + slot, sizeof u, cudaMemcpyDeviceToHost));
+        *used_host = (int32_t)u;
+    }
+    AZ_CUDA(h, cudaDeviceSynchronize());
+    return AZ_OK;
+}
+
+int32_t az_sample_moves(az_engine *h, const double *uniforms, uint8_t *finished, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (!uniforms) return fail(h, AZ_E_INVALID, "%s", "az_sample_moves: null uniforms");
+    if (!h->have_init) return fail(h, AZ_E_STATE, "%s", "az_sample_moves: call az_reset_games first");
+    if (int rc = set_device(h)) return rc;
+    const int n = h->n_active;
+    k_sample_moves<<<blocks_for(n, 128), 128, 0, S(stream)>>>(h->a, n, uniforms, finished, h->step, h->init0, h->init1,
+                                                             h->initpl);
+    AZ_LAUNCH_CHECK(h, "k_sample_moves");
+    h->step++;
+    return AZ_OK;
+}
+
+int32_t az_episode_counts(az_engine *h, int64_t *n_episodes_host, int64_t *n_samples_host, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (int rc = set_device(h)) return rc;
+    unsigned long long r[4];
+    AZ_CUDA(h, cudaMemcpyAsync(r, h->a.ring, sizeof r, cudaMemcpyDeviceToHost, S(stream)));
+    AZ_CUDA(h, cudaStreamSynchronize(S(stream)));
+    if (n_episodes_host) *n_episodes_host = (int64_t)r[0];
+    if (n_samples_host) *n_samples_host = (int64_t)r[1];
+    if (r[2]) return fail(h, AZ_E_OVERFLOW, "%s", "episode ring overflowed: drain more often (capacity 2*num_games + 64 episodes)");
+    return AZ_OK;
+}
+
+int32_t az_drain_episodes(az_engine *h, int64_t ep_cap, int64_t s_cap, int32_t *ep_slot, int32_t *ep_step,
+                          int32_t *ep_len, int64_t *ep_offset, int8_t *ep_outcome, uint64_t *s_bb0, uint64_t *s_bb1,
+                          uint8_t *s_player, int32_t *s_counts, int64_t *n_episodes_host, int64_t *n_samples_host,
+                          void *stream) {
+    if (!h) return AZ_E_INVALID;
+    int64_t ne = 0, ns = 0;
+    int rc = az_episode_counts(h, &ne, &ns, stream);
+    if (rc != AZ_OK) return rc;
+    if (ne > ep_cap || ns > s_cap) return fail(h, AZ_E_OVERFLOW, "%s", "az_drain_episodes: caller buffers too small");
+    cudaStream_t st = S(stream);
+    const Arena &a = h->a;
+#define CP(dst, src, count, T) if ((dst) && (count) > 0) AZ_CUDA(h, cudaMemcpyAsync((dst), (src), (size_t)(count) * sizeof(T), cudaMemcpyDeviceToDevice, st))
+    CP(ep_slot, a.ep_slot, ne, int32_t); CP(ep_step, a.ep_step, ne, int32_t); CP(ep_len, a.ep_len, ne, int32_t);
+    CP(ep_offset, a.ep_offset, ne, int64_t); CP(ep_outcome, a.ep_outcome, ne * 2, int8_t);
+    CP(s_bb0, a.s_bb0, ns, uint64_t); CP(s_bb1, a.s_bb1, ns, uint64_t); CP(s_player, a.s_player, ns, uint8_t);
+    CP(s_counts, a.s_counts, ns * 7, int32_t);
+#undef CP
+    AZ_CUDA(h, cudaMemsetAsync(a.ring, 0, 4 * sizeof(unsigned long long), st));
+    AZ_CUDA(h, cudaStreamSynchronize(st));
+    if (n_episodes_host) *n_episodes_host = ne;
+    if (n_samples_host) *n_samples_host = ns;
+    return AZ_OK;
+}
+
+int32_t az_get_stats(az_engine *h, az_stats *out, void *stream) {
+    if (!h || !out) return AZ_E_INVALID;
+    if (int rc = set_device(h)) return rc;
+    cudaStream_t st = S(stream);
+    AZ_CUDA(h, cudaMemsetAsync(h->d_tot, 0, 8 * sizeof(unsigned long long), st));
+    k_sum_stats<<<148, 256, 0, st>>>(h->a.tstats, h->a.E, h->d_tot);
+    AZ_LAUNCH_CHECK(h, "k_sum_stats");
+    unsigned long long r[8];
+    AZ_CUDA(h, cudaMemcpyAsync(r, h->d_tot, sizeof r, cudaMemcpyDeviceToHost, st));
+    AZ_CUDA(h, cudaStreamSynchronize(st));
+    for (int q = 0; q < NSTAT; ++q) r[q] += h->acc_tot[q];
+    out->simulations = r[0];
+    out->evaluations = r[1];
+    out->levels = r[2];
+    out->children_created = r[3];
+    out->backup_nodes = r[2] + r[0];
+    out->moves = r[4];
+    out->episodes = r[5];
+    out->reserved = 0;
+    return AZ_OK;
+}
+
+int32_t az_reset_stats(az_engine *h, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (int rc = set_device(h)) return rc;
+    k_zero_u32<<<148, 256, 0, S(stream)>>>(h->a.tstats, (long long)h->a.E * NSTAT);
+    AZ_LAUNCH_CHECK(h, "k_zero_u32");
+    memset(h->acc_tot, 0, sizeof h->acc_tot);
+    return AZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+"""Python handle on the CUDA engine (include/az_engine.h).  PyTorch is used only for device
+memory, streams and host<->device copies; every computation on the path is a kernel of
+libaz_engine.so.  No fallback exists: constructing an `Engine` without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AzConfig, AzStats
+
+EVAL_UNIFORM = 1
+EVAL_HASH = 2
+LAYOUT_GRID_F32 = 0
+LAYOUT_PLANES_F32 = 1
+LAYOUT_PLANES_BF16 = 2
+LAYOUT_PLANES_BF16_NHWC = 3
+POLICY_LOGITS = 0
+POLICY_PRIORS = 1
+LEAF_EVAL, LEAF_TERMINAL, LEAF_IDLE = 0, 1, 2
+TREE_ROOT_ENDED = 3
+
+_LAYOUT_SHAPE = {
+    LAYOUT_GRID_F32: ((6, 7), torch.float32),
+    LAYOUT_PLANES_F32: ((3, 6, 7), torch.float32),
+    LAYOUT_PLANES_BF16: ((3, 6, 7), torch.bfloat16),
+    LAYOUT_PLANES_BF16_NHWC: ((6, 7, 8), torch.bfloat16),
+}
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "engine buffers must be contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+@dataclass
+class EpisodeBatch:
+    """Finished games as flat host arrays (the device ring drained once).
+
+    Episode i owns samples [ep_offset[i], ep_offset[i] + ep_len[i]).  Policy target of a sample =
+    s_counts / (S - 1) (`Node.improved_policy`, node.py:23-29); value target = ep_outcome of its episode
+    (`Episode.backpropagate_outcome`, episode.py:52-54).  Sorted in the reference's yield order (step, slot).
+    """
+
+    ep_slot: np.ndarray
+    ep_step: np.ndarray
+    ep_len: np.ndarray
+    ep_offset: np.ndarray
+    ep_outcome: np.ndarray  # [n,2] int8
+    s_bb0: np.ndarray
+    s_bb1: np.ndarray
+    s_player: np.ndarray
+    s_counts: np.ndarray  # [m,7] int32
+
+    def __len__(self) -> int:
+        return int(self.ep_slot.shape[0])
+
+    @property
+    def num_samples(self) -> int:
+        return int(self.ep_len.sum())
+
+
+class Engine:
+    """E game slots, each with a tree arena sized for S simulations per move."""
+
+    def __init__(self, num_games: int, num_simulations: int, c_puct: float = 1.0, device: int | None = None,
+                 lanes_per_tree: int = 0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("alphazero_implementation_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.num_games = int(num_games)
+        self.num_simulations = int(num_simulations)
+        self.c_puct = float(c_puct)
+        cfg = AzConfig(6, 7, 4, self.num_games, self.num_simulations, self.device_index, int(lanes_per_tree), 0, self.c_puct)
+        h = C.c_void_p()
+        rc = self.lib.az_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"az_create failed ({rc}): {self.lib.az_last_error(None).decode()}")
+        self.h = h
+        self.n_active = self.num_games
+        self.tree_capacity = self.lib.az_tree_capacity(self.h)
+
+    # -- plumbing --------------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.az_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.az_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _dev(self, x, dtype) -> torch.Tensor:
+        if isinstance(x, torch.Tensor):
+            return x.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
+        a = np.ascontiguousarray(x)
+        if a.dtype == np.uint64:
+            a = a.view(np.int64)
+        return torch.from_numpy(a).to(device=self.device, dtype=dtype, non_blocking=True)
+
+    def empty(self, shape, dtype) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.az_device_bytes(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.az_launch_count(self.h))
+
+    # -- rules -----------------------------------------------------------------------------------
+    def env_step(self, bb0, bb1, player, col):
+        """`Action.sample_next_state()` on a batch -> dict of device tensors."""
+        bb0 = self._dev(bb0, torch.int64); bb1 = self._dev(bb1, torch.int64)
+        player = self._dev(player, torch.uint8); col = self._dev(col, torch.uint8)
+        n = bb0.numel()
+        out = dict(bb0=self.empty(n, torch.int64), bb1=self.empty(n, torch.int64), player=self.empty(n, torch.uint8),
+                   legal=self.empty(n, torch.uint8), ended=self.empty(n, torch.uint8), reward=self.empty((n, 2), torch.int8),
+                   status=self.empty(n, torch.uint8))
+        self._check(self.lib.az_env_step(self.h, _ptr(bb0), _ptr(bb1), _ptr(player), _ptr(col), n, _ptr(out["bb0"]),
+                                         _ptr(out["bb1"]), _ptr(out["player"]), _ptr(out["legal"]), _ptr(out["ended"]),
+                                         _ptr(out["reward"]), _ptr(out["status"]), _stream()), "az_env_step")
+        return out
+
+    def state_info(self, bb0, bb1, player=None):
+        bb0 = self._dev(bb0, torch.int64); bb1 = self._dev(bb1, torch.int64)
+        n = bb0.numel()
+        out = dict(legal=self.empty(n, torch.uint8), ended=self.empty(n, torch.uint8), reward=self.empty((n, 2), torch.int8))
+        self._check(self.lib.az_state_info(self.h, _ptr(bb0), _ptr(bb1), None, n, _ptr(out["legal"]), _ptr(out["ended"]),
+                                           _ptr(out["reward"]), _stream()), "az_state_info")
+        return out
+
+    def masked_softmax(self, logits: torch.Tensor, legal) -> torch.Tensor:
+        logits = self._dev(logits, torch.float32).reshape(-1, 7)
+        legal = self._dev(legal, torch.uint8)
+        out = self.empty(logits.shape, torch.float32)
+        self._check(self.lib.az_masked_softmax(self.h, _ptr(logits), _ptr(legal), logits.shape[0], _ptr(out), _stream()),
+                    "az_masked_softmax")
+        return out
+
+    def encode_states(self, bb0, bb1, player, layout: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        bb0 = self._dev(bb0, torch.int64); bb1 = self._dev(bb1, torch.int64); player = self._dev(player, torch.uint8)
+        n = bb0.numel()
+        shape, dtype = _LAYOUT_SHAPE[layout]
+        if out is None:
+            out = self.empty((n, *shape), dtype)
+        self._check(self.lib.az_encode_states(self.h, _ptr(bb0), _ptr(bb1), _ptr(player), n, _ptr(out), layout, _stream()),
+                    "az_encode_states")
+        return out
+
+    # -- roots -----------------------------------------------------------------------------------
+    def reset_games(self, init_bb0: int = 0, init_bb1: int = 0, init_player: int = 0):
+        self._check(self.lib.az_reset_games(self.h, int(init_bb0), int(init_bb1), int(init_player), _stream()), "az_reset_games")
+        self.n_active = self.num_games
+
+    def set_roots(self, bb0, bb1, player):
+        bb0 = self._dev(bb0, torch.int64); bb1 = self._dev(bb1, torch.int64); player = self._dev(player, torch.uint8)
+        n = bb0.numel()
+        self._check(self.lib.az_set_roots(self.h, _ptr(bb0), _ptr(bb1), _ptr(player), n, _stream()), "az_set_roots")
+        self.n_active = n
+
+    # -- search ----------------------------------------------------------------------------------
+    def run_simulations(self, num_sims: int, eval_kind: int):
+        self._check(self.lib.az_run_simulations(self.h, int(num_sims), int(eval_kind), _stream()), "az_run_simulations")
+
+    def select_leaves(self):
+        self._check(self.lib.az_select_leaves(self.h, _stream()), "az_select_leaves")
+
+    def gather_leaves(self, layout: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        shape, dtype = _LAYOUT_SHAPE[layout]
+        if out is None:
+            out = self.empty((self.n_active, *shape), dtype)
+        self._check(self.lib.az_gather_leaves(self.h, _ptr(out), layout, _stream()), "az_gather_leaves")
+        return out
+
+    def expand_backup(self, policy: torch.Tensor, values: torch.Tensor, policy_kind: int = POLICY_LOGITS):
+        assert policy.dtype == torch.float32 and values.dtype == torch.float32
+        assert policy.shape[0] >= self.n_active and policy.shape[-1] == 7 and values.shape[-1] == 2
+        self._check(self.lib.az_expand_backup(self.h, _ptr(policy), _ptr(values), policy_kind, _stream()), "az_expand_backup")
+
+    def leaf_info(self):
+        n = self.n_active
+        out = dict(bb0=self.empty(n, torch.int64), bb1=self.empty(n, torch.int64), player=self.empty(n, torch.uint8),
+                   legal=self.empty(n, torch.uint8), status=self.empty(n, torch.uint8))
+        self._check(self.lib.az_leaf_info(self.h, _ptr(out["bb0"]), _ptr(out["bb1"]), _ptr(out["player"]), _ptr(out["legal"]),
+                                          _ptr(out["status"]), _stream()), "az_leaf_info")
+        return out
+
+    # -- results ---------------------------------------------------------------------------------
+    def root_stats(self, out: dict | None = None):
+        n = self.n_active
+        if out is None:
+            out = dict(child_N=self.empty((n, 7), torch.int32), child_W=self.empty((n, 7), torch.float64),
+                       child_P=self.empty((n, 7), torch.float32), root_W=self.empty(n, torch.float64),
+                       root_N=self.empty(n, torch.int32), legal=self.empty(n, torch.uint8), err=self.empty(n, torch.int32))
+        self._check(self.lib.az_root_stats(self.h, _ptr(out.get("child_N")), _ptr(out.get("child_W")), _ptr(out.get("child_P")),
+                                           _ptr(out.get("root_W")), _ptr(out.get("root_N")), _ptr(out.get("legal")),
+                                           _ptr(out.get("err")), _stream()), "az_root_stats")
+        return out
+
+    def export_tree(self, slot: int):
+        cap = self.tree_capacity
+        W = self.empty(cap, torch.float64); N = self.empty(cap, torch.int32); P = self.empty(cap, torch.float32)
+        CB = self.empty(cap, torch.int32)
+        used = C.c_int32(0)
+        self._check(self.lib.az_export_tree(self.h, int(slot), _ptr(W), _ptr(N), _ptr(P), _ptr(CB), C.byref(used)), "az_export_tree")
+        u = used.value
+        return dict(W=W[:u].cpu().numpy(), N=N[:u].cpu().numpy(), P=P[:u].cpu().numpy(), first_child=CB[:u].cpu().numpy(), used=u)
+
+    # -- self-play -------------------------------------------------------------------------------
+    def sample_moves(self, uniforms: torch.Tensor, finished: torch.Tensor | None = None):
+        assert uniforms.dtype == torch.float64 and uniforms.numel() >= self.n_active
+        self._check(self.lib.az_sample_moves(self.h, _ptr(uniforms), _ptr(finished), _stream()), "az_sample_moves")
+
+    def episode_counts(self) -> tuple[int, int]:
+        ne, ns = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.az_episode_counts(self.h, C.byref(ne), C.byref(ns), _stream()), "az_episode_counts")
+        return ne.value, ns.value
+
+    def drain_episodes_device(self):
+        """Ring -> fresh device tensors (ring order, unsorted).  Used by the NCCL all-gather."""
+        ne, ns = self.episode_counts()
+        d = dict(ep_slot=self.empty(ne, torch.int32), ep_step=self.empty(ne, torch.int32), ep_len=self.empty(ne, torch.int32),
+                 ep_offset=self.empty(ne, torch.int64), ep_outcome=self.empty((ne, 2), torch.int8),
+                 s_bb0=self.empty(ns, torch.int64), s_bb1=self.empty(ns, torch.int64), s_player=self.empty(ns, torch.uint8),
+                 s_counts=self.empty((ns, 7), torch.int32))
+        one, ons = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.az_drain_episodes(self.h, ne, ns, _ptr(d["ep_slot"]), _ptr(d["ep_step"]), _ptr(d["ep_len"]),
+                                               _ptr(d["ep_offset"]), _ptr(d["ep_outcome"]), _ptr(d["s_bb0"]), _ptr(d["s_bb1"]),
+                                               _ptr(d["s_player"]), _ptr(d["s_counts"]), C.byref(one), C.byref(ons), _stream()),
+                    "az_drain_episodes")
+        assert one.value == ne and ons.value == ns
+        return d
+
+    def drain_episodes(self) -> EpisodeBatch:
+        """Ring -> host, sorted into the reference's yield order (move step, then slot)."""
+        d = {k: v.cpu().numpy() for k, v in self.drain_episodes_device().items()}
+        return sort_episode_batch(d)
+
+    # -- instrumentation -------------------------------------------------------------------------
+    def stats(self) -> dict:
+        st = AzStats()
+        self._check(self.lib.az_get_stats(self.h, C.byref(st), _stream()), "az_get_stats")
+        return {n: int(getattr(st, n)) for n, _ in AzStats._fields_ if n != "reserved"}
+
+    def reset_stats(self):
+        self._check(self.lib.az_reset_stats(self.h, _stream()), "az_reset_stats")
+
+
+def sort_episode_batch(d: dict) -> EpisodeBatch:
+    """Order episodes by (step, slot) and make their samples contiguous in that order."""
+    order = np.lexsort((d["ep_slot"], d["ep_step"]))
+    ep_len = d["ep_len"][order].astype(np.int32)
+    old_off = d["ep_offset"][order]
+    new_off = np.zeros(len(order), np.int64)
+    if len(order):
+        new_off[1:] = np.cumsum(ep_len[:-1])
+    idx = np.concatenate([np.arange(o, o + l) for o, l in zip(old_off, ep_len)]) if len(order) else np.zeros(0, np.int64)
+    return EpisodeBatch(
+        ep_slot=d["ep_slot"][order], ep_step=d["ep_step"][order], ep_len=ep_len, ep_offset=new_off,
+        ep_outcome=d["ep_outcome"][order], s_bb0=d["s_bb0"][idx].view(np.uint64), s_bb1=d["s_bb1"][idx].view(np.uint64),
+        s_player=d["s_player"][idx], s_counts=d["s_counts"][idx],
+    )

@@ -1,0 +1,292 @@
+"""Policy/value network API of the reference, kept verbatim at the call surface:
+
+  Model.predict(states) -> (list[dict[Action, float]], list[list[float]])   models/base/model.py:54-74
+  Model.forward(x)      -> (logits[B,7], value[B,2])                        models/base/model.py:51
+  Model.get_inference_clone(), state_dict()/load_state_dict()               models/base/model.py:92-96
+  Model.training_step / configure_optimizers / format_dataset               models/base/model.py:27-48,76-82
+
+`lightning` is not required: `Model` is a plain `nn.Module` exposing the hooks a Lightning trainer calls.
+Parameter names match the reference classes, so their checkpoints' `state_dict`s load unchanged.
+
+What runs where: plane encoding (`_states_to_tensor`) and the legal-only softmax of `predict` are CUDA
+kernels of libaz_engine.so (`az_encode_states`, `az_masked_softmax`); the conv / linear layers are
+library GEMMs (cuBLAS / cuDNN through torch).  For the search hot path `InferenceNet` folds BatchNorm
+into the convolutions and runs them in bf16 channels-last so that only the conv/GEMM layers touch the
+tensor cores; softmax / tanh epilogues stay in fp32.
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from .engine import LAYOUT_GRID_F32, LAYOUT_PLANES_BF16, LAYOUT_PLANES_F32
+from .game import Action, State, rules_engine
+
+ActionPolicy = dict
+Value = list
+
+
+class Model(nn.Module):
+    """Abstract policy/value model (reference: `Model(ABC, L.LightningModule)`, models/base/model.py:15)."""
+
+    input_layout: int = LAYOUT_PLANES_F32  # which az_gather_leaves layout `forward` consumes
+
+    def __init__(self, learning_rate: float = 1e-3):
+        super().__init__()
+        self.learning_rate = learning_rate
+        self.model_name = self.__class__.__name__
+        self.hparams = {"learning_rate": learning_rate, "model_name": self.model_name}
+
+    # Lightning hooks (no-ops without a trainer)
+    def save_hyperparameters(self, *args, **kwargs):
+        return None
+
+    def log(self, *args, **kwargs):
+        return None
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.parameters()).device
+
+    def training_step(self, batch: tuple[Tensor, Tensor, Tensor], batch_idx: int = 0) -> Tensor:
+        x, policy_target, value_target = batch
+        policy_logits, value_logits = self(x)
+        policy_loss = F.cross_entropy(policy_logits, policy_target)  # soft targets (visit distribution)
+        value_loss = F.mse_loss(value_logits, value_target)
+        total = policy_loss + value_loss
+        self.log("train_loss", total)
+        self.log("policy_loss", policy_loss)
+        self.log("value_loss", value_loss)
+        return total
+
+    def configure_optimizers(self):
+        return torch.optim.Adam(self.parameters(), lr=self.learning_rate, weight_decay=1e-4)
+
+    def forward(self, x: Tensor) -> tuple[Tensor, Tensor]:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def predict(self, states: list[State]) -> tuple[list[ActionPolicy], list[Value]]:  # pragma: no cover
+        raise NotImplementedError
+
+    def format_dataset(self, states, policies, values):
+        from torch.utils.data import TensorDataset
+
+        return TensorDataset(self._states_to_tensor(states).cpu(), self._policies_to_tensor(policies),
+                             torch.tensor(values, dtype=torch.float32))
+
+    def get_inference_clone(self):
+        clone = copy.deepcopy(self)
+        clone.eval()
+        return clone
+
+
+def _state_arrays(states: list[State]):
+    return (np.array([s.bb0 for s in states], np.uint64), np.array([s.bb1 for s in states], np.uint64),
+            np.array([s.player for s in states], np.uint8))
+
+
+class Connect4Model(Model):
+    """`predict` generalised for all Connect4 nets (models/games/connect4/model.py:8-51)."""
+
+    def __init__(self):
+        super().__init__()
+        self.board_height = 6
+        self.board_width = 7
+
+    def _states_to_tensor(self, states: list[State]) -> Tensor:
+        bb0, bb1, pl = _state_arrays(states)
+        return rules_engine().encode_states(bb0, bb1, pl, self.input_layout)
+
+    @torch.no_grad()
+    def predict(self, states: list[State]) -> tuple[list[ActionPolicy], list[Value]]:
+        eng = rules_engine()
+        x = self._states_to_tensor(states)
+        policy_logits, values_tensor = self.forward(x)
+        legal = np.array([s.legal_mask for s in states], np.uint8)
+        priors = eng.masked_softmax(policy_logits.float(), legal).cpu().numpy()  # legal-only softmax, fp32
+        policies: list[ActionPolicy] = []
+        for i, state in enumerate(states):
+            policies.append({a: float(priors[i, a.column]) for a in state.actions})
+        values: list[Value] = values_tensor.detach().float().cpu().tolist()
+        return policies, values
+
+    def _policies_to_tensor(self, policies: list[ActionPolicy]) -> Tensor:
+        t = torch.zeros((len(policies), self.board_width))
+        for i, policy in enumerate(policies):
+            for action, prob in policy.items():
+                t[i, action.column] = prob
+        return t
+
+
+class BasicNN(Connect4Model):
+    """42 -> 512 -> 512 -> {7, 2 (tanh)} on the raw grid (-1 / 0 / 1, absolute) (basic.py:8-47)."""
+
+    input_layout = LAYOUT_GRID_F32
+
+    def __init__(self):
+        super().__init__()
+        self.flatten = nn.Flatten()
+        self.shared_layers = nn.Sequential(
+            nn.Linear(self.board_height * self.board_width, 512), nn.ReLU(), nn.Linear(512, 512), nn.ReLU())
+        self.policy_head = nn.Linear(512, self.board_width)
+        self.value_head = nn.Sequential(nn.Linear(512, 2), nn.Tanh())
+
+    def forward(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        x = x.to(self.shared_layers[0].weight.device)
+        h = self.shared_layers(self.flatten(x))
+        return self.policy_head(h), self.value_head(h)
+
+
+class CNNModel(Connect4Model):
+    """3 x (conv3x3 + BN + ReLU) 3->64->128->256, FC 10752->512, heads 7 / tanh(1) -> [v, -v] (cnn.py:8-100)."""
+
+    input_layout = LAYOUT_PLANES_F32
+
+    def __init__(self):
+        super().__init__()
+        self.channels = [3, 64, 128, 256]
+        self.conv_layers = nn.Sequential(
+            nn.Conv2d(3, 64, kernel_size=3, padding=1), nn.BatchNorm2d(64), nn.ReLU(),
+            nn.Conv2d(64, 128, kernel_size=3, padding=1), nn.BatchNorm2d(128), nn.ReLU(),
+            nn.Conv2d(128, 256, kernel_size=3, padding=1), nn.BatchNorm2d(256), nn.ReLU(),
+        )
+        self.conv_output_size = 256 * self.board_height * self.board_width
+        self.shared_layers = nn.Sequential(nn.Linear(self.conv_output_size, 512), nn.ReLU(), nn.Dropout(0.3))
+        self.policy_head = nn.Linear(512, self.board_width)
+        self.value_head = nn.Sequential(nn.Linear(512, 1), nn.Tanh())
+        self.learning_rate = 1e-3
+
+    def forward(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        x = x.to(next(self.parameters()).device)
+        x = self.conv_layers(x)
+        h = self.shared_layers(x.reshape(x.size(0), -1))
+        value = self.value_head(h)
+        return self.policy_head(h), torch.cat([value, -value], dim=1)
+
+
+class ResBlock(nn.Module):
+    def __init__(self, num_channels: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(num_channels, num_channels, kernel_size=3, padding=1)
+        self.bn1 = nn.BatchNorm2d(num_channels)
+        self.conv2 = nn.Conv2d(num_channels, num_channels, kernel_size=3, padding=1)
+        self.bn2 = nn.BatchNorm2d(num_channels)
+
+    def forward(self, x):
+        r = x
+        x = F.relu(self.bn1(self.conv1(x)))
+        x = self.bn2(self.conv2(x))
+        return F.relu(x + r)
+
+
+class ResNet(Connect4Model):
+    """The reference's own ResNet-style net (src/alphazero_simple/resnet.py:30-72: stem conv3x3+BN+ReLU,
+    n x ResBlock, policy head conv1x1->32+BN+ReLU+FC, value head conv3x3->3+BN+ReLU+FC->1) behind the main
+    package's `Model` API: side-relative planes (cnn.py:93-95), tanh value returned as [v, -v] (cnn.py:73)."""
+
+    input_layout = LAYOUT_PLANES_F32
+
+    def __init__(self, num_res_blocks: int = 9, num_channels: int = 128):
+        super().__init__()
+        self.num_res_blocks, self.num_channels = num_res_blocks, num_channels
+        rows, cols = self.board_height, self.board_width
+        self.input_conv = nn.Sequential(nn.Conv2d(3, num_channels, kernel_size=3, padding=1), nn.BatchNorm2d(num_channels), nn.ReLU())
+        self.residual_blocks = nn.ModuleList([ResBlock(num_channels) for _ in range(num_res_blocks)])
+        self.policy_head = nn.Sequential(nn.Conv2d(num_channels, 32, kernel_size=1), nn.BatchNorm2d(32), nn.ReLU(), nn.Flatten(),
+                                         nn.Linear(32 * rows * cols, self.board_width))
+        self.value_head = nn.Sequential(nn.Conv2d(num_channels, 3, kernel_size=3, padding=1), nn.BatchNorm2d(3), nn.ReLU(),
+                                        nn.Flatten(), nn.Linear(3 * rows * cols, 1))
+
+    def forward(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        x = x.to(next(self.parameters()).device)
+        x = self.input_conv(x)
+        for block in self.residual_blocks:
+            x = block(x)
+        v = torch.tanh(self.value_head(x))
+        return self.policy_head(x), torch.cat([v, -v], dim=1)
+
+    def flops_per_position(self) -> int:
+        """2 x MACs of the conv / linear layers for one 6x7 position."""
+        c, hw = self.num_channels, 42
+        f = 2 * hw * 9 * 3 * c + self.num_res_blocks * 2 * (2 * hw * 9 * c * c)
+        f += 2 * hw * c * 32 + 2 * 32 * hw * 7 + 2 * hw * 9 * c * 3 + 2 * 3 * hw
+        return f
+
+
+# ------------------------------------------------------------------------------------------------
+def _fold_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+    """eval-mode BatchNorm folded into the preceding convolution (fp32 arithmetic)."""
+    w = conv.weight.detach().float()
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    return w * scale.view(-1, 1, 1, 1), (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+
+
+class InferenceNet(nn.Module):
+    """Search-time form of a `Model` (the role of `get_inference_clone()`, models/base/model.py:92-96):
+    eval-mode, BatchNorm folded, conv/linear weights in `dtype` (bf16 on the hot path), activations
+    channels-last.  `forward(planes) -> (logits f32 [B,7], values f32 [B,2])`, consumed directly by
+    `az_expand_backup`.  BasicNN stays fp32 (config 1 parity is quoted in fp32)."""
+
+    def __init__(self, model: Model, dtype: torch.dtype = torch.bfloat16, device: torch.device | str = "cuda"):
+        super().__init__()
+        m = copy.deepcopy(model).eval().to(device)
+        self.kind = type(model).__name__
+        self.dtype = dtype
+        self.layers: list[tuple[str, Tensor, Tensor]] = []
+        if isinstance(m, BasicNN):
+            self.dtype = torch.float32
+            self.input_layout = LAYOUT_GRID_F32
+            self.net = m
+        elif isinstance(m, (CNNModel, ResNet)):
+            self.input_layout = LAYOUT_PLANES_BF16 if dtype == torch.bfloat16 else LAYOUT_PLANES_F32
+            self.net = self._fold(m).to(dtype).to(memory_format=torch.channels_last)
+        else:
+            self.input_layout = getattr(model, "input_layout", LAYOUT_PLANES_F32)
+            self.net = m
+            self.dtype = torch.float32
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    @staticmethod
+    def _fold(m: nn.Module) -> nn.Module:
+        def fold_seq(seq: nn.Sequential) -> nn.Sequential:
+            out, mods, i = [], list(seq), 0
+            while i < len(mods):
+                if isinstance(mods[i], nn.Conv2d) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm2d):
+                    w, b = _fold_bn(mods[i], mods[i + 1])
+                    conv = nn.Conv2d(mods[i].in_channels, mods[i].out_channels, mods[i].kernel_size, padding=mods[i].padding)
+                    conv.weight.data, conv.bias.data = w, b
+                    out.append(conv)
+                    i += 2
+                elif isinstance(mods[i], nn.Dropout):
+                    i += 1
+                else:
+                    out.append(mods[i])
+                    i += 1
+            return nn.Sequential(*out)
+
+        if isinstance(m, CNNModel):
+            m.conv_layers = fold_seq(m.conv_layers)
+            m.shared_layers = fold_seq(m.shared_layers)
+        else:
+            m.input_conv = fold_seq(m.input_conv)
+            for blk in m.residual_blocks:
+                for cn, bn in (("conv1", "bn1"), ("conv2", "bn2")):
+                    w, b = _fold_bn(getattr(blk, cn), getattr(blk, bn))
+                    getattr(blk, cn).weight.data, getattr(blk, cn).bias.data = w, b
+                    setattr(blk, bn, nn.Identity())
+            m.policy_head = fold_seq(m.policy_head)
+            m.value_head = fold_seq(m.value_head)
+        return m
+
+    @torch.no_grad()
+    def forward(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        if x.dim() == 4:
+            x = x.contiguous(memory_format=torch.channels_last)
+        logits, values = self.net(x.to(self.dtype))
+        return logits.float().contiguous(), values.float().contiguous()

@@ -1,0 +1,271 @@
+"""`AlphaZeroSearch` / `Node` with the reference's call surface (core/search/mcts/search.py:10-91,
+core/search/mcts/node.py:7-73), executed by the CUDA tree arena.
+
+`run_simulations(nodes)` uploads the roots' positions, runs `num_simulations` simulations per tree on
+the GPU (fused kernel for the built-in deterministic evaluators; select -> gather -> net -> expand/backup
+for a network; select -> `predict(states)` -> expand/backup for any other object with a `predict`), and
+writes the result back into the caller's `Node`s in place: visit_count, value_sum and one level of
+children with their statistics (what `improved_policy`, `value` and `select_next_node` read).
+`materialize="full"` rebuilds the entire tree as `Node`s.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .engine import (EVAL_HASH, EVAL_UNIFORM, LEAF_EVAL, POLICY_LOGITS, POLICY_PRIORS, TREE_ROOT_ENDED, Engine)
+from .game import DEFAULT_CONFIG, Action, State, states_from_arrays
+
+
+class Node:
+    """Host-side view of a tree node; same attributes and properties as the reference (node.py:7-73)."""
+
+    __slots__ = ("state", "parent", "children", "visit_count", "value_sum", "prior")
+
+    def __init__(self, state: State, parent: "Node | None" = None, prior: float = 0.0):
+        self.state = state
+        self.parent = parent
+        self.children: dict[Action, Node] = {}
+        self.visit_count = 0
+        self.value_sum = 0.0
+        self.prior = prior
+
+    @property
+    def raw_policy(self) -> dict[Action, float]:
+        return {a: ch.prior for a, ch in self.children.items()}
+
+    @property
+    def improved_policy(self) -> dict[Action, float]:
+        return {a: ch.visit_count / (self.visit_count - 1) for a, ch in self.children.items()}
+
+    def select_next_node(self) -> "Node":
+        """Sample the move from the visit distribution with the global NumPy stream (node.py:31-42)."""
+        pol = self.improved_policy
+        index = np.random.choice(len(pol), p=list(pol.values()))
+        action = list(pol.keys())[index]
+        child = self.children[action]
+        return Node(state=child.state if child.state is not None else action.sample_next_state(), parent=self,
+                    prior=pol[action])
+
+    def add_child(self, action: Action, child_state: State, prior: float) -> "Node":
+        child = Node(state=child_state, parent=self, prior=prior)
+        self.children[action] = child
+        return child
+
+    @property
+    def value(self) -> float:
+        if self.visit_count == 0:
+            return 0
+        return self.value_sum / self.visit_count
+
+    @property
+    def is_expanded(self) -> bool:
+        return len(self.children) > 0
+
+    @property
+    def is_terminal(self) -> bool:
+        return self.state.has_ended
+
+    @property
+    def utility_values(self) -> list[float]:
+        return self.state.reward.tolist()
+
+    @property
+    def is_root(self) -> bool:
+        return self.parent is None
+
+
+class _GraphedStep:
+    """One simulation step (select -> gather -> net -> expand/backup), optionally replayed as a CUDA graph.
+
+    The step has fixed shapes (row i of the packed batch = slot i), so one capture serves every
+    simulation of every move.  Capture only records; the two warm-up steps that precede it are real
+    simulations and the caller counts them.
+    """
+
+    def __init__(self, engine: Engine, net, layout: int):
+        self.engine, self.net, self.layout = engine, net, layout
+        self.graph = None
+        self.n = -1
+        self.x = None
+
+    def step(self):
+        e = self.engine
+        e.select_leaves()
+        e.gather_leaves(self.layout, self.x)
+        logits, values = self.net(self.x)
+        e.expand_backup(logits, values, POLICY_LOGITS)
+
+    def run(self, num_steps: int, use_graph: bool):
+        e = self.engine
+        if self.n != e.n_active:
+            self.n = e.n_active
+            self.x = e.gather_leaves(self.layout)  # allocates the packed batch once per batch size
+            self.graph = None
+        done = 0
+        if use_graph and self.graph is None and num_steps > 2:
+            for _ in range(2):  # cuDNN / cuBLAS pick algorithms and allocate workspaces outside capture
+                self.step()
+            done = 2
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=e.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    self.step()
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = g
+        for _ in range(num_steps - done):
+            if use_graph and self.graph is not None:
+                self.graph.replay()
+            else:
+                self.step()
+
+
+class AlphaZeroSearch:
+    def __init__(self, *, model, num_simulations: int, exploration_weight: float = 1.0, device: int | None = None,
+                 lanes_per_tree: int = 0, inference_dtype: torch.dtype | None = None, use_cuda_graph: bool = True):
+        self.inference_model = model.get_inference_clone()
+        self.num_simulations = int(num_simulations)
+        self.exploration_weight = exploration_weight
+        self.device_index = device
+        self.lanes_per_tree = lanes_per_tree
+        self.inference_dtype = inference_dtype
+        self.use_cuda_graph = use_cuda_graph
+        self._engine: Engine | None = None
+        self._net = None
+        self._graphed: _GraphedStep | None = None
+        self._refresh_net()
+
+    # -- weights ---------------------------------------------------------------------------------
+    def update_inference_model(self, model):
+        """Copy the training model's weights into the inference clone (search.py:22-25)."""
+        self.inference_model.load_state_dict(model.state_dict())
+        self.inference_model.eval()
+        self._refresh_net()
+
+    def _refresh_net(self):
+        from .models import BasicNN, InferenceNet, Model
+
+        m = self.inference_model
+        self._graphed = None
+        if getattr(m, "az_builtin_eval_kind", 0) in (EVAL_UNIFORM, EVAL_HASH):
+            self._mode, self._net = "builtin", None
+        elif isinstance(m, Model):
+            dtype = self.inference_dtype or (torch.float32 if isinstance(m, BasicNN) else torch.bfloat16)
+            dev = torch.device("cuda", torch.cuda.current_device() if self.device_index is None else self.device_index)
+            self._mode, self._net = "net", InferenceNet(m, dtype=dtype, device=dev)
+        else:
+            self._mode, self._net = "predict", None
+
+    # -- engine ----------------------------------------------------------------------------------
+    def engine_for(self, n: int) -> Engine:
+        if self._engine is None or self._engine.num_games < n:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = Engine(num_games=n, num_simulations=self.num_simulations, c_puct=float(self.exploration_weight),
+                                  device=self.device_index, lanes_per_tree=self.lanes_per_tree)
+            self._graphed = None
+        return self._engine
+
+    def simulate(self, engine: Engine, num_simulations: int | None = None):
+        """`num_simulations` simulations on every active tree of `engine` (roots already set)."""
+        S = self.num_simulations if num_simulations is None else num_simulations
+        if self._mode == "builtin":
+            engine.run_simulations(S, self.inference_model.az_builtin_eval_kind)
+        elif self._mode == "net":
+            if self._graphed is None or self._graphed.engine is not engine:
+                self._graphed = _GraphedStep(engine, self._net, self._net.input_layout)
+            self._graphed.run(S, self.use_cuda_graph)
+        else:
+            self._simulate_predict(engine, S)
+
+    def _simulate_predict(self, engine: Engine, S: int):
+        """Generic evaluator: any object with the reference's `predict(states)`."""
+        n = engine.n_active
+        for _ in range(S):
+            engine.select_leaves()
+            info = {k: v.cpu().numpy() for k, v in engine.leaf_info().items()}
+            rows = np.nonzero(info["status"] == LEAF_EVAL)[0]
+            pri = np.zeros((n, 7), np.float32)
+            val = np.zeros((n, 2), np.float32)
+            if len(rows):
+                states = states_from_arrays(info["bb0"][rows], info["bb1"][rows], info["player"][rows], legal=info["legal"][rows],
+                                            ended=np.zeros(len(rows), bool), reward=np.zeros((len(rows), 2), np.int8))
+                policies, values = self.inference_model.predict(states)
+                for r, pol, v in zip(rows, policies, values):
+                    for a, p in pol.items():
+                        pri[r, a.column] = p
+                    val[r] = v
+            engine.expand_backup(torch.from_numpy(pri).to(engine.device), torch.from_numpy(val).to(engine.device), POLICY_PRIORS)
+
+    # -- reference surface -----------------------------------------------------------------------
+    def run(self, root: Node) -> tuple[dict[Action, float], float]:
+        self.run_simulations([root])
+        return root.improved_policy, root.value
+
+    def run_simulations(self, current_nodes: list[Node], materialize: str = "root") -> None:
+        if not current_nodes:
+            return
+        for nd in current_nodes:
+            if nd.children or nd.visit_count:
+                raise ValueError("run_simulations expects fresh roots (the reference always passes Node(state)); "
+                                 "continuing a search on an already expanded Node is not supported")
+        n = len(current_nodes)
+        eng = self.engine_for(n)
+        bb0 = np.array([nd.state.bb0 for nd in current_nodes], np.uint64)
+        bb1 = np.array([nd.state.bb1 for nd in current_nodes], np.uint64)
+        pl = np.array([nd.state.player for nd in current_nodes], np.uint8)
+        eng.set_roots(bb0, bb1, pl)
+        self.simulate(eng)
+        st = {k: v.cpu().numpy() for k, v in eng.root_stats().items()}
+        if (st["err"] == TREE_ROOT_ENDED).any():
+            # the reference dereferences node.parent (None) for a terminal root (search.py:76)
+            raise AttributeError("'NoneType' object has no attribute 'state'")
+        # successor states of every legal root move, one rules-kernel call
+        cols = np.tile(np.arange(7, dtype=np.uint8), n)
+        nxt = {k: v.cpu().numpy() for k, v in eng.env_step(np.repeat(bb0, 7), np.repeat(bb1, 7), np.repeat(pl, 7), cols).items()}
+        for i, nd in enumerate(current_nodes):
+            nd.visit_count = int(st["root_N"][i])
+            nd.value_sum = float(st["root_W"][i])
+            nd.state._legal, nd.state._ended, nd.state._reward = int(st["legal"][i]), False, (0, 0)
+            for c in range(7):
+                if not (st["legal"][i] >> c) & 1:
+                    continue
+                k = 7 * i + c
+                child_state = State(nd.state.config, int(nxt["bb0"][k]), int(nxt["bb1"][k]), int(nxt["player"][k]),
+                                    legal=int(nxt["legal"][k]), ended=bool(nxt["ended"][k]),
+                                    reward=(int(nxt["reward"][k][0]), int(nxt["reward"][k][1])))
+                ch = nd.add_child(Action(nd.state, c), child_state, float(st["child_P"][i, c]))
+                ch.visit_count = int(st["child_N"][i, c])
+                ch.value_sum = float(st["child_W"][i, c])
+        if materialize == "full":
+            for i, nd in enumerate(current_nodes):
+                _materialize_subtree(eng, i, nd)
+
+
+def _materialize_subtree(eng: Engine, slot: int, root: Node):
+    """Rebuild every expanded node of tree `slot` below `root` as `Node`s (children in column order)."""
+    t = eng.export_tree(slot)
+    W, N, P, CB = t["W"], t["N"], t["P"], t["first_child"]
+    rules = eng
+
+    def expand(node: Node, idx: int):
+        cb = int(CB[idx])
+        if cb == 0:
+            return
+        s = node.state
+        legal = [c for c in range(7) if (s.legal_mask >> c) & 1]
+        n = len(legal)
+        nxt = {k: v.cpu().numpy() for k, v in rules.env_step(np.full(n, s.bb0, np.uint64), np.full(n, s.bb1, np.uint64),
+                                                             np.full(n, s.player, np.uint8), np.array(legal, np.uint8)).items()}
+        node.children = {}
+        for j, c in enumerate(legal):
+            cs = State(s.config, int(nxt["bb0"][j]), int(nxt["bb1"][j]), int(nxt["player"][j]), legal=int(nxt["legal"][j]),
+                       ended=bool(nxt["ended"][j]), reward=(int(nxt["reward"][j][0]), int(nxt["reward"][j][1])))
+            ch = node.add_child(Action(s, c), cs, float(P[cb + j]))
+            ch.visit_count, ch.value_sum = int(N[cb + j]), float(W[cb + j])
+            expand(ch, cb + j)
+
+    expand(root, 0)

@@ -1,0 +1,193 @@
+/*
+ * az_engine.h — C ABI of the B200-native AlphaZero self-play engine (Connect4).
+ *
+ * This is the drop-in boundary for the self-play / episode-generation path of
+ * pierreveron/alphazero-implementation.  The reference has no FFI layer of its
+ * own (it is pure Python); each entry point below names the reference code it
+ * replaces (paths relative to src/alphazero_implementation/ of the reference).
+ * The Python adapters in alphazero-implementation_b200/ bind these with ctypes
+ * and present the reference's class surfaces (EpisodeGenerator, AlphaZeroSearch,
+ * Node, Model.predict, Config/State/Action).  See INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative AZ_E_* code on failure;
+ *     az_last_error() gives the message.  Nothing throws across the boundary.
+ *   - all buffer arguments are DEVICE pointers on the engine's GPU unless the
+ *     name ends in _host; sizes are in elements.  The engine owns its arenas;
+ *     caller buffers are borrowed for the duration of the call's stream work.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Calls only enqueue work unless documented as synchronising.
+ *   - boards are two u64 bitboards (stones of player 0 / player 1), bit index =
+ *     column*7 + row, row 0 = bottom (the reference's `State.grid[row][col]`,
+ *     notebooks/policy_comparison.ipynb#cell6 "Row 0 (bottom)").
+ *   - children of a node are ordered by ascending column (`state.actions` order,
+ *     models/games/connect4/model.py:29); per-column outputs use column index.
+ *   - there is no CPU fallback: az_create fails if no sm_100 device is usable.
+ */
+#ifndef AZ_ENGINE_H
+#define AZ_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZ_ABI_VERSION 1
+
+/* status codes */
+#define AZ_OK 0
+#define AZ_E_INVALID (-1)   /* bad argument / configuration */
+#define AZ_E_CUDA (-2)      /* CUDA runtime error (message has the detail) */
+#define AZ_E_NOMEM (-3)     /* device allocation failed */
+#define AZ_E_STATE (-4)     /* call not valid in the engine's current state */
+#define AZ_E_OVERFLOW (-5)  /* an output buffer / episode ring was too small */
+
+/* built-in deterministic evaluators for az_run_simulations (normative definition:
+ * oracle/evaluators.py; restated in csrc/az_eval.cuh) */
+#define AZ_EVAL_UNIFORM 1 /* prior = fp32(1)/fp32(k) on the k legal columns, value [0,0] */
+#define AZ_EVAL_HASH 2    /* priors / value from a 64-bit hash of the position */
+
+/* layouts for az_gather_leaves */
+#define AZ_LAYOUT_GRID_F32 0        /* [E,6,7] f32, -1 empty / 0 / 1 owner  (BasicNN._states_to_tensor, basic.py:41-47) */
+#define AZ_LAYOUT_PLANES_F32 1      /* [E,3,6,7] f32: empty, side-to-move, opponent (CNNModel._states_to_tensor, cnn.py:77-100) */
+#define AZ_LAYOUT_PLANES_BF16 2     /* same planes, bf16 NCHW */
+#define AZ_LAYOUT_PLANES_BF16_NHWC 3 /* [E,6,7,8] bf16 channels-last, channels 3..7 zero (tensor-core conv input) */
+
+/* policy_kind for az_expand_backup */
+#define AZ_POLICY_LOGITS 0 /* raw logits[E,7]; legal-only fp32 softmax applied (model.py:29-38) */
+#define AZ_POLICY_PRIORS 1 /* priors[E,7] already normalised over the legal columns */
+
+/* leaf status written by az_select_leaves */
+#define AZ_LEAF_EVAL 0     /* non-terminal leaf waiting for the evaluator */
+#define AZ_LEAF_TERMINAL 1 /* terminal leaf, already backed up (search.py:75-77) */
+#define AZ_LEAF_IDLE 2     /* slot inactive or in error */
+
+/* per-tree error flags (az_root_stats `err`) */
+#define AZ_TREE_OK 0
+#define AZ_TREE_ROOT_ENDED 3 /* search asked on a finished position: the reference raises AttributeError (search.py:76, parent is None) */
+
+typedef struct az_config {
+    int32_t height;          /* 6 */
+    int32_t width;           /* 7 */
+    int32_t count;           /* 4  (Config(6,7,4), scripts/train.py:12) */
+    int32_t num_games;       /* E: concurrent game slots / trees (EpisodeGenerator num_episodes) */
+    int32_t num_simulations; /* S: arena is sized for 1 + 7*S nodes per tree (search.py:15) */
+    int32_t device;          /* CUDA device ordinal */
+    int32_t lanes_per_tree;  /* 32 = one warp per tree, 8 = four trees per warp; 0 = default */
+    int32_t reserved;
+    double c_puct;           /* exploration_weight (search.py:16) */
+} az_config;
+
+typedef struct az_engine az_engine;
+
+/* counters returned by az_get_stats (totals since az_create / az_reset_stats) */
+typedef struct az_stats {
+    uint64_t simulations;      /* iterations of search.py:66 summed over trees */
+    uint64_t evaluations;      /* non-terminal leaves (one evaluator row each) */
+    uint64_t levels;           /* select_child calls (search.py:27) */
+    uint64_t children_created; /* add_child calls (node.py:44) */
+    uint64_t backup_nodes;     /* nodes touched by backpropagate (search.py:48) */
+    uint64_t moves;            /* select_next_node calls (node.py:31) */
+    uint64_t episodes;         /* finished games */
+    uint64_t reserved;
+} az_stats;
+
+int32_t az_abi_version(void);
+/* message of the last failure on `h` (or of the last failed az_create when h == NULL) */
+const char *az_last_error(const az_engine *h);
+
+/* lifetime.  Replaces: AlphaZeroSearch.__init__ (search.py:11-20) + the Python object heap of Nodes. */
+int32_t az_create(const az_config *cfg, az_engine **out);
+int32_t az_destroy(az_engine *h);
+/* bytes of device memory the engine allocated */
+int64_t az_device_bytes(const az_engine *h);
+
+/* ---- game rules (stand-alone; replaces third-party simulator.game.connect) ---- */
+/* Action.sample_next_state() (search.py:89, node.py:38) on n boards, plus the successor's
+ * State.actions mask / has_ended / reward.  status[i] = 0 ok, 1 illegal (column full, >= width, or game over). */
+int32_t az_env_step(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, const uint8_t *player,
+                    const uint8_t *col, int64_t n, uint64_t *out_bb0, uint64_t *out_bb1, uint8_t *out_player,
+                    uint8_t *out_legal, uint8_t *out_ended, int8_t *out_reward /*[n][2]*/, uint8_t *out_status,
+                    void *stream);
+/* State.actions (7-bit mask) / State.has_ended / State.reward of arbitrary positions */
+int32_t az_state_info(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, const uint8_t *player, int64_t n,
+                      uint8_t *out_legal, uint8_t *out_ended, int8_t *out_reward /*[n][2]*/, void *stream);
+/* legal-only softmax epilogue of Connect4Model.predict (model.py:26-39): priors[n,7] (0 on illegal columns) */
+int32_t az_masked_softmax(az_engine *h, const float *logits /*[n][7]*/, const uint8_t *legal, int64_t n,
+                          float *out_priors /*[n][7]*/, void *stream);
+/* plane encoders on arbitrary positions (basic.py:41-47, cnn.py:77-100); layout = AZ_LAYOUT_* */
+int32_t az_encode_states(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, const uint8_t *player, int64_t n,
+                         void *out, int32_t layout, void *stream);
+
+/* ---- roots ---- */
+/* all E slots to the given initial state with empty trees and empty episode logs
+ * (episode_generator.py:42-45).  Resets the move-step counter and the episode ring. */
+int32_t az_reset_games(az_engine *h, uint64_t init_bb0, uint64_t init_bb1, int32_t init_player, void *stream);
+/* slots 0..n-1 take the given root positions (Node(state), node.py:8), n <= num_games becomes the
+ * active tree count for the search calls below.  Does not touch the episode logs. */
+int32_t az_set_roots(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, const uint8_t *player, int32_t n,
+                     void *stream);
+
+/* ---- search ---- */
+/* AlphaZeroSearch.run_simulations (search.py:65-91) with a built-in evaluator, all `num_sims`
+ * simulations of every active tree in ONE launch (select -> evaluate -> expand -> backup). */
+int32_t az_run_simulations(az_engine *h, int32_t num_sims, int32_t eval_kind, void *stream);
+/* one simulation step with an external evaluator (the policy/value net), split at the
+ * device boundary of search.py:82-84:
+ *   az_select_leaves : search.py:69-79  (PUCT descent; terminal leaves are backed up here)
+ *   az_gather_leaves : Model._states_to_tensor of the leaves into one packed batch, row i = slot i
+ *                      (rows of AZ_LEAF_TERMINAL / AZ_LEAF_IDLE slots are zero-filled)
+ *   az_expand_backup : search.py:87-91  (legal-only softmax, add_child x k, backpropagate value[leaf.player]) */
+int32_t az_select_leaves(az_engine *h, void *stream);
+int32_t az_gather_leaves(az_engine *h, void *out, int32_t layout, void *stream);
+int32_t az_expand_backup(az_engine *h, const float *policy /*[E][7]*/, const float *values /*[E][2]*/,
+                         int32_t policy_kind, void *stream);
+/* the leaves chosen by the last az_select_leaves (for evaluators that want positions, not planes) */
+int32_t az_leaf_info(az_engine *h, uint64_t *out_bb0, uint64_t *out_bb1, uint8_t *out_player, uint8_t *out_legal,
+                     uint8_t *out_status, void *stream);
+
+/* ---- results ---- */
+/* root statistics of every active tree, per column (0 on illegal columns):
+ * child visit counts (Node.improved_policy = child_N / (root_N - 1), node.py:23-29), child value sums,
+ * child priors, root value_sum / visit_count (Node.value, node.py:50-55), legal mask, AZ_TREE_* flag.
+ * Any output pointer may be NULL. */
+int32_t az_root_stats(az_engine *h, int32_t *child_N /*[n][7]*/, double *child_W /*[n][7]*/,
+                      float *child_P /*[n][7]*/, double *root_W, int32_t *root_N, uint8_t *legal, int32_t *err,
+                      void *stream);
+/* the whole SoA tree of one slot (value_sum f64, visit_count u32, prior f32, first-child index u32;
+ * node 0 = root, 0 = no children).  Buffers hold az_tree_capacity() entries.  Synchronises. */
+int32_t az_tree_capacity(const az_engine *h);
+int32_t az_export_tree(az_engine *h, int32_t slot, double *W, uint32_t *N, float *P, uint32_t *first_child,
+                       int32_t *used_host);
+
+/* ---- self-play (episode_generator.py:53-78) ---- */
+/* For every slot in slot order semantics: record the sample (root position, child visit counts),
+ * draw the move with the supplied uniform exactly as np.random.choice(k, p=N_c/(N-1)) would
+ * (node.py:31-35), advance the root (no subtree reuse, node.py:37-41); if the successor is terminal,
+ * finish the episode (outcome = successor reward, episode.py:52-54), move it to the episode ring and
+ * recycle the slot to the initial state.  finished[slot] (may be NULL) = 1 where an episode finished.
+ * Increments the move-step counter. */
+int32_t az_sample_moves(az_engine *h, const double *uniforms /*[E]*/, uint8_t *finished, void *stream);
+/* number of finished episodes / samples waiting in the ring.  Synchronises on `stream`. */
+int32_t az_episode_counts(az_engine *h, int64_t *n_episodes_host, int64_t *n_samples_host, void *stream);
+/* copy the ring out (device buffers sized from az_episode_counts) and empty it.  Episodes appear in
+ * ring order; sort by (ep_step, ep_slot) for the reference's yield order.  Synchronises.
+ *   ep_*: per episode  — slot, move-step at which it finished, length, first sample index, outcome
+ *         (reward of player 0 / player 1: +1 / -1 / 0)
+ *   s_* : per sample   — position, side to move, root child visit counts by column */
+int32_t az_drain_episodes(az_engine *h, int64_t ep_cap, int64_t s_cap, int32_t *ep_slot, int32_t *ep_step,
+                          int32_t *ep_len, int64_t *ep_offset, int8_t *ep_outcome /*[n][2]*/, uint64_t *s_bb0,
+                          uint64_t *s_bb1, uint8_t *s_player, int32_t *s_counts /*[n][7]*/,
+                          int64_t *n_episodes_host, int64_t *n_samples_host, void *stream);
+
+/* ---- instrumentation ---- */
+int32_t az_get_stats(az_engine *h, az_stats *out_host, void *stream); /* synchronises */
+int32_t az_reset_stats(az_engine *h, void *stream);
+/* number of kernels this engine has launched since az_create */
+int64_t az_launch_count(const az_engine *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AZ_ENGINE_H */

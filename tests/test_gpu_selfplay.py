@@ -1,0 +1,84 @@
+"""GPU parity: the self-play loop (sample recording, np.random.choice-equivalent move sampling, slot recycling,
+episode order) vs transcripts of the reference's EpisodeGenerator and vs the C oracle at config-2 size."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import golden_uniforms  # noqa: E402
+
+
+def _run_engine(E, S, kind, uniforms_2d, init=(0, 0, 0), lanes=0, quota=None):
+    from alphazero_implementation_b200.engine import Engine, sort_episode_batch
+
+    quota = E if quota is None else quota
+    eng = Engine(num_games=E, num_simulations=S, lanes_per_tree=lanes)
+    eng.reset_games(*init)
+    parts, count = [], 0
+    for step in range(uniforms_2d.shape[0]):
+        eng.run_simulations(S, kind)
+        eng.sample_moves(torch.from_numpy(uniforms_2d[step]).cuda())
+        ne, _ = eng.episode_counts()
+        if ne:
+            parts.append(eng.drain_episodes())
+            count += ne
+            if count >= quota:
+                break
+    stats = eng.stats()
+    eng.close()
+    return parts, stats, step + 1
+
+
+def _flatten(parts, quota):
+    eps = []
+    for b in parts:
+        for e in range(len(b)):
+            o, n = int(b.ep_offset[e]), int(b.ep_len[e])
+            eps.append(dict(slot=int(b.ep_slot[e]), step=int(b.ep_step[e]), outcome=b.ep_outcome[e].tolist(),
+                            bb0=b.s_bb0[o:o + n].tolist(), bb1=b.s_bb1[o:o + n].tolist(), player=b.s_player[o:o + n].tolist(),
+                            counts=b.s_counts[o:o + n].tolist()))
+    return eps[:quota]
+
+
+@pytest.mark.parametrize("lanes", [8, 32])
+def test_selfplay_goldens(selfplay_goldens, lanes):
+    for run in selfplay_goldens:
+        E, S = run["E"], run["S"]
+        u = golden_uniforms(run)
+        steps = (run["n_draws"] + E - 1) // E + 1
+        u2 = u[: steps * E].reshape(steps, E)
+        parts, stats, _ = _run_engine(E, S, run["eval_kind"], u2, init=(run["init_bb0"], run["init_bb1"], run["init_player"]), lanes=lanes)
+        got = _flatten(parts, E)
+        assert len(got) == len(run["episodes"]) == E
+        for g, ep in zip(got, run["episodes"]):
+            assert g["outcome"] == [int(v) for v in ep["outcome"]]
+            assert g["bb0"] == [s["bb0"] for s in ep["samples"]] and g["bb1"] == [s["bb1"] for s in ep["samples"]]
+            assert g["player"] == [s["player"] for s in ep["samples"]]
+            assert g["counts"] == [s["counts"] for s in ep["samples"]]
+            assert [[c / (S - 1) for c in row] for row in g["counts"]] == [s["policy"] for s in ep["samples"]]
+        # draws consumed up to the quota slot of the last step == the reference's np.random.choice calls
+        last = got[-1]
+        assert last["step"] * E + last["slot"] + 1 == run["n_draws"]
+
+
+@pytest.mark.parametrize("E,S,kind,lanes", [(4096, 200, 1, 8), (4096, 200, 2, 32), (1024, 64, 2, 8)])
+def test_selfplay_vs_oracle_config2(oracle, E, S, kind, lanes):
+    """BASELINE config 2 (4096 games x 200 sims): a whole self-play round until E episodes, all per-move visit
+    counts, positions, outcomes and the episode order bit-exact against the C oracle."""
+    rng = np.random.RandomState(E + S)
+    u2 = rng.random_sample((60, E))
+    ref = oracle.selfplay(E, S, u2, eval_kind=kind)
+    parts, stats, steps = _run_engine(E, S, kind, u2, lanes=lanes)
+    got = _flatten(parts, E)
+    assert len(got) == E == len(ref.ep_slot) and steps == ref.n_steps
+    assert [g["slot"] for g in got] == ref.ep_slot.tolist() and [g["step"] for g in got] == ref.ep_step.tolist()
+    assert [g["outcome"] for g in got] == ref.ep_outcome.tolist()
+    assert np.array([len(g["bb0"]) for g in got]).tolist() == ref.ep_len.tolist()
+    assert (np.concatenate([np.array(g["bb0"], np.uint64) for g in got]) == ref.s_bb0).all()
+    assert (np.concatenate([np.array(g["bb1"], np.uint64) for g in got]) == ref.s_bb1).all()
+    assert (np.concatenate([np.array(g["counts"], np.int32) for g in got]) == ref.s_counts).all()
+    assert (np.concatenate([np.array(g["player"], np.uint8) for g in got]) == ref.s_player).all()
+    assert stats["simulations"] == ref.n_sims and stats["evaluations"] == ref.n_evals
+    outcomes = np.array([g["outcome"][0] for g in got])
+    assert (outcomes == 1).sum() > 0 and (outcomes == -1).sum() > 0

@@ -1,0 +1,53 @@
+"""Host-side logic that needs no GPU: episode ordering, JSON shapes, grid <-> bitboard formatting."""
+import json
+
+import numpy as np
+
+from alphazero_implementation_b200.engine import sort_episode_batch
+from alphazero_implementation_b200.episode import Episode, Sample
+from alphazero_implementation_b200.game import Action, Config, State, bitboards_to_grid, grid_to_bitboards
+
+
+def test_grid_bitboard_round_trip(rules_goldens):
+    for plies in rules_goldens["games"][:50]:
+        for p in plies:
+            g = bitboards_to_grid(p["bb0"], p["bb1"])
+            assert grid_to_bitboards(g) == (p["bb0"], p["bb1"])
+            assert (g >= 0).sum() == bin(p["bb0"] | p["bb1"]).count("1")
+
+
+def test_state_json_shape_matches_reference_fixture():
+    # notebooks/episode_generation_testing.ipynb#cell2
+    d = {"config": {"count": 4, "height": 6, "width": 7},
+         "grid": [[0, 0, 0, -1, -1, 1, -1], [-1] * 7, [-1] * 7, [-1] * 7, [-1] * 7, [-1] * 7], "player": 0}
+    s = State.from_json(d)
+    assert s.to_json() == d
+    assert s.bb0 == (1 << 0) | (1 << 7) | (1 << 14) and s.bb1 == 1 << 35
+
+
+def test_episode_json_round_trip():
+    cfg = Config(6, 7, 4)
+    s = State(cfg, 1, 1 << 7, 0, legal=0x7F, ended=False, reward=(0, 0))
+    pol = {Action(s, c): (c + 1) / 28 for c in range(7)}
+    ep = Episode()
+    ep.add_sample(Sample(s, pol, [0.0, 0.0]))
+    ep.backpropagate_outcome([1.0, -1.0])
+    d = json.loads(json.dumps(ep.to_dict()))
+    assert list(d["samples"][0]["policy"].keys())[0] == "{'column': 0}"  # str(action.to_json()), episode.py:22
+    back = Episode.from_dict(d)
+    assert back.samples[0].state == s and back.samples[0].value == [1.0, -1.0]
+    assert [a.column for a in back.samples[0].policy] == list(range(7))
+    assert list(back.samples[0].policy.values()) == list(pol.values())
+
+
+def test_sort_episode_batch_orders_by_step_then_slot():
+    d = dict(ep_slot=np.array([5, 1, 3], np.int32), ep_step=np.array([2, 2, 1], np.int32), ep_len=np.array([2, 1, 3], np.int32),
+             ep_offset=np.array([0, 2, 3], np.int64), ep_outcome=np.array([[1, -1], [0, 0], [-1, 1]], np.int8),
+             s_bb0=np.arange(6, dtype=np.int64), s_bb1=np.arange(6, dtype=np.int64) * 10, s_player=np.arange(6, dtype=np.uint8),
+             s_counts=np.arange(42, dtype=np.int32).reshape(6, 7))
+    b = sort_episode_batch(d)
+    assert b.ep_slot.tolist() == [3, 1, 5] and b.ep_step.tolist() == [1, 2, 2]
+    assert b.ep_offset.tolist() == [0, 3, 4] and b.ep_len.tolist() == [3, 1, 2]
+    assert b.s_bb0.tolist() == [3, 4, 5, 2, 0, 1]
+    assert b.ep_outcome.tolist() == [[-1, 1], [0, 0], [1, -1]]
+    assert b.num_samples == 6 and len(b) == 3
