@@ -66,7 +66,7 @@ class AzConfig(C.Structure):
 
 class AzStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("simulations", "evaluations", "levels", "children_created", "backup_nodes",
-                                           "moves", "episodes", "reserved")]
+                                           "moves", "episodes", "children_scanned")]
 
 
 P = C.c_void_p  # device pointers and streams cross the boundary as plain addresses

@@ -32,7 +32,7 @@ namespace {
 
 constexpr int PATH_STRIDE = 44;  // root + at most 42 plies (+1 pad)
 constexpr int MAX_PLIES = 42;
-constexpr int NSTAT = 6;  // per-tree counters: sims, evals, levels, children, moves, episodes
+constexpr int NSTAT = 7;  // per-tree counters: sims, evals, levels, children, moves, episodes, children scanned
 
 struct Arena {
     double *W;
@@ -90,7 +90,7 @@ template <int G>
 __device__ __forceinline__ Leaf descend(const double *__restrict__ Wt, const uint32_t *__restrict__ Nt,
                                         const float *__restrict__ Pt, const uint32_t *__restrict__ CBt,
                                         uint64_t rb0, uint64_t rb1, int rpl, double c_puct, uint32_t *path,
-                                        unsigned gmask, uint32_t &levels) {
+                                        unsigned gmask, uint32_t &levels, uint32_t &scanned) {
     const int lane = threadIdx.x & 31;
     const int sub = lane & 24;  // first lane of my 8-lane subgroup
     const int c = lane & 7;     // the column this lane scores (7 = none)
@@ -145,6 +145,7 @@ __device__ __forceinline__ Leaf descend(const double *__restrict__ Wt, const uin
         L.depth++;
         if (writer) path[L.depth] = L.node;
         levels++;
+        scanned += (uint32_t)__popc(legal);
     }
     // Node.is_terminal of the leaf (node.py:61-63).  Interior nodes are never terminal (a terminal
     // node is never expanded), so only the last mover's stones need the line test.
@@ -209,10 +210,10 @@ k_run_sims(Arena a, int n_active, int S, double c_puct) {
     const uint64_t rb0 = a.root_bb0[t], rb1 = a.root_bb1[t];
     const int rpl = a.root_player[t];
     uint32_t used = a.used[t];
-    uint32_t levels = 0, evals = 0, children = 0;
+    uint32_t levels = 0, evals = 0, children = 0, scanned = 0;
 
     for (int s = 0; s < S; ++s) {
-        Leaf L = descend<G>(Wt, Nt, Pt, CBt, rb0, rb1, rpl, c_puct, path, gmask, levels);
+        Leaf L = descend<G>(Wt, Nt, Pt, CBt, rb0, rb1, rpl, c_puct, path, gmask, levels, scanned);
         double v;
         if (L.term) {
             // value = reward[parent.state.player]: the mover's own reward, +1 on a win, 0 on a draw (search.py:76)
@@ -251,6 +252,7 @@ k_run_sims(Arena a, int n_active, int S, double c_puct) {
         st[1] += evals;
         st[2] += levels;
         st[3] += children;
+        st[6] += scanned;
     }
 }
 
@@ -272,9 +274,9 @@ __global__ void __launch_bounds__(G == 32 ? 128 : 64) k_select(Arena a, int n_ac
     double *Wt = a.W + base;
     uint32_t *Nt = a.N + base;
     uint32_t *path = a.path + (size_t)t * PATH_STRIDE;
-    uint32_t levels = 0;
+    uint32_t levels = 0, scanned = 0;
     Leaf L = descend<G>(Wt, Nt, a.P + base, a.CB + base, a.root_bb0[t], a.root_bb1[t], a.root_player[t], c_puct,
-                        path, gmask, levels);
+                        path, gmask, levels, scanned);
     if (writer) {
         a.leaf_node[t] = L.node;
         a.leaf_bb0[t] = L.b0;
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(G == 32 ? 128 : 64) k_select(Arena a, int n_ac
         uint32_t *st = a.tstats + (size_t)t * NSTAT;
         st[0] += 1u;
         st[2] += levels;
+        st[6] += scanned;
     }
     if (L.term) {
         __syncwarp(gmask);
@@ -662,7 +665,7 @@ k_sample_moves(Arena a, int n, const double *__restrict__ uniforms, uint8_t *fin
 }
 
 __global__ void __launch_bounds__(256) k_sum_stats(const uint32_t *__restrict__ tstats, int E, unsigned long long *tot) {
-    unsigned long long loc[NSTAT] = {0, 0, 0, 0, 0, 0};
+    unsigned long long loc[NSTAT] = {0, 0, 0, 0, 0, 0, 0};
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < E; t += gridDim.x * blockDim.x)
         for (int q = 0; q < NSTAT; ++q) loc[q] += tstats[(size_t)t * NSTAT + q];
     for (int q = 0; q < NSTAT; ++q) {
@@ -1096,7 +1099,7 @@ int32_t az_get_stats(az_engine *h, az_stats *out, void *stream) {
     out->backup_nodes = r[2] + r[0];
     out->moves = r[4];
     out->episodes = r[5];
-    out->reserved = 0;
+    out->children_scanned = r[6];
     return AZ_OK;
 }
 

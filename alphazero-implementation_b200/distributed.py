@@ -1,0 +1,89 @@
+"""Multi-GPU plumbing: one process per GPU, games sharded, NCCL used for exactly two things
+(SURVEY.md §8e): broadcasting new network weights and all-gathering finished episodes.
+
+  broadcast_weights   <- `inference_model.load_state_dict(model.state_dict())`  search.py:22-25 / datamodule.py:100
+  all_gather_episodes <- `buffer.append(episode)` into the shared replay deque    datamodule.py:29-30,57
+
+Games never interact inside the search, so there is no collective on the per-simulation path.
+Works on any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+_EP_FIELDS = ("ep_slot", "ep_step", "ep_len", "ep_offset", "ep_outcome")
+_S_FIELDS = ("s_bb0", "s_bb1", "s_player", "s_counts")
+
+
+def shard_range(total_games: int, rank: int, world: int) -> tuple[int, int]:
+    """Static partition of game slots: rank r owns [lo, hi); sizes differ by at most one."""
+    base, rem = divmod(total_games, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+@torch.no_grad()
+def broadcast_weights(model: torch.nn.Module, src: int = 0, group=None) -> int:
+    """One flat broadcast of every parameter and buffer from `src`; returns the bytes sent."""
+    tensors = [t for t in list(model.parameters()) + list(model.buffers()) if t.numel()]
+    if not tensors or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    nbytes = 0
+    by_dtype: dict[torch.dtype, list[torch.Tensor]] = {}
+    for t in tensors:
+        by_dtype.setdefault(t.dtype, []).append(t)
+    for dtype, ts in by_dtype.items():
+        flat = torch.cat([t.detach().reshape(-1) for t in ts])
+        dist.broadcast(flat, src=src, group=group)
+        nbytes += flat.numel() * flat.element_size()
+        o = 0
+        for t in ts:
+            t.copy_(flat[o:o + t.numel()].view_as(t))
+            o += t.numel()
+    return nbytes
+
+
+def all_gather_episodes(local: dict, group=None, slot_offset: int | None = None) -> dict:
+    """Merge every rank's drained episodes (dict of tensors as returned by `Engine.drain_episodes_device`)
+    into one dict present on all ranks.  Two phases: all-gather the (episodes, samples) counts, then one padded
+    all-gather per field.  Episode slots are made global by adding the rank's slot offset; sample offsets are
+    rebased.  Merge order: rank, then the rank's own order."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = local["ep_len"].device
+    counts = torch.tensor([local["ep_len"].numel(), local["s_bb0"].numel()], dtype=torch.int64, device=dev)
+    all_counts = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    ne = [int(c[0]) for c in all_counts]
+    ns = [int(c[1]) for c in all_counts]
+    max_e, max_s = max(ne + [1]), max(ns + [1])
+    out = {}
+    for fields, cnt, mx in ((_EP_FIELDS, ne, max_e), (_S_FIELDS, ns, max_s)):
+        for f in fields:
+            x = local[f]
+            pad = torch.zeros((mx, *x.shape[1:]), dtype=x.dtype, device=dev)
+            pad[: x.shape[0]] = x
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad, group=group)
+            out[f] = torch.cat([p[:c] for p, c in zip(parts, cnt)])
+    # rebase sample offsets and slots
+    s_base, e_pos = 0, 0
+    for r in range(world):
+        sl = slice(e_pos, e_pos + ne[r])
+        out["ep_offset"][sl] += s_base
+        if slot_offset is not None:
+            pass
+        s_base += ns[r]
+        e_pos += ne[r]
+    if slot_offset is not None:
+        offs = torch.tensor([slot_offset], dtype=torch.int64, device=dev)
+        all_offs = [torch.zeros_like(offs) for _ in range(world)]
+        dist.all_gather(all_offs, offs, group=group)
+        e_pos = 0
+        for r in range(world):
+            out["ep_slot"][e_pos:e_pos + ne[r]] += int(all_offs[r])
+            e_pos += ne[r]
+    out["ep_rank"] = torch.cat([torch.full((c,), r, dtype=torch.int32, device=dev) for r, c in enumerate(ne)])
+    return out

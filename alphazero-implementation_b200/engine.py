@@ -260,7 +260,7 @@ class Engine:
     def stats(self) -> dict:
         st = AzStats()
         self._check(self.lib.az_get_stats(self.h, C.byref(st), _stream()), "az_get_stats")
-        return {n: int(getattr(st, n)) for n, _ in AzStats._fields_ if n != "reserved"}
+        return {n: int(getattr(st, n)) for n, _ in AzStats._fields_}
 
     def reset_stats(self):
         self._check(self.lib.az_reset_stats(self.h, _stream()), "az_reset_stats")

@@ -34,8 +34,10 @@ class EpisodeGenerator:
         self.search.update_inference_model(model)
 
     # ------------------------------------------------------------------------------------------
-    def _steps(self, initial_state: State | None, quota: int | None, max_steps: int | None = None):
-        """Yield (step, EpisodeBatch-or-None, rng_state_before_draw) after every move step."""
+    def iter_steps(self, initial_state: State | None = None, max_steps: int | None = None):
+        """Run the self-play loop; after every move step yield (step, EpisodeBatch-or-None, rng_state_before_draw).
+        Host buffers in, host buffers out: the step's uniforms are copied from pinned host memory and the
+        finished episodes (if any) plus the ring counters are read back."""
         if initial_state is None:
             initial_state = self.game_initial_state
         E = self.num_episodes
@@ -63,7 +65,7 @@ class EpisodeGenerator:
         abandoning games in flight (episode_generator.py:48-81)."""
         count = 0
         S = self.search.num_simulations
-        for step, batch, rng_state in self._steps(initial_state, self.num_episodes):
+        for step, batch, rng_state in self.iter_steps(initial_state):
             if batch is None:
                 continue
             episodes = episodes_from_batch(batch, S)
@@ -84,7 +86,7 @@ class EpisodeGenerator:
         """Array-level variant for large E: yields `EpisodeBatch`es (flat host arrays) as games finish.
         With `quota`, truncates at the reference's stopping point."""
         count = 0
-        for step, batch, _ in self._steps(initial_state, quota, max_steps):
+        for step, batch, _ in self.iter_steps(initial_state, max_steps):
             if batch is None:
                 continue
             if quota is not None and count + len(batch) >= quota:

@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Headline benchmark: MCTS simulations/s (and self-play games/s) for Connect4 self-play on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (N=1): BASELINE.json configs[1] — 4096 concurrent games x 200 simulations/move with the
+deterministic uniform-prior evaluator (the bit-exact parity configuration).  One STEP = one move step of
+the self-play loop for every game: `az_run_simulations` (200 simulations per tree, one launch) followed by
+`az_sample_moves` (record samples, draw moves, recycle finished games).  With N > 1 every rank runs its own
+4096 games (weak scaling, no collective on the data path); finished episodes are all-gathered over NCCL
+after the timed region and that time is reported separately.
+
+`value`   device-resident: uniforms already in HBM, CUDA events around each step, L2 flushed between steps.
+`e2e`     the public API (`EpisodeGenerator.generate_batches`): per step the uniforms come from pinned host
+          memory and finished episodes + counters are read back to the host.
+`--impl reference`  the CPU arm: the reference algorithm (oracle/c4_oracle.c, the C restatement pinned against
+          the reference's own outputs; the reference itself is pure Python that cannot travel to the GPU box)
+          on all host cores via OpenMP, same workload, bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NODE_BYTES = 20  # W f64 + N u32 + P f32 + CB u32
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games", type=int, default=4096)
+    ap.add_argument("--sims", type=int, default=200)
+    ap.add_argument("--evaluator", default="uniform", choices=["uniform", "hash"])
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per tree: 8, 32 or 0 = engine default")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--net", default="resnet4x64", help="network-in-the-loop side measurement: resnetBxC | basic | none")
+    ap.add_argument("--net-games", type=int, default=16384)
+    ap.add_argument("--net-sims", type=int, default=800)
+    ap.add_argument("--net-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [ln.strip().split(", ") for ln in open(self.f.name) if ln.strip()]
+        os.unlink(self.f.name)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.strip() == "Active":
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(st: dict) -> int:
+    """Bytes the tree kernels must move for the work counted in `st` ('algorithmic bytes'):
+    select reads one 20-byte record per child scanned plus the root's N and CB (8 B) per simulation;
+    expansion writes one 20-byte record per child created plus the leaf's CB (4 B);
+    backup reads and writes W (f64) and N (u32) of every node on the path (24 B)."""
+    return (st["children_scanned"] * NODE_BYTES + st["simulations"] * 8 + st["children_created"] * NODE_BYTES
+            + st["evaluations"] * 4 + st["backup_nodes"] * 24)
+
+
+def diff(a: dict, b: dict) -> dict:
+    return {k: b[k] - a[k] for k in a}
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_arm(E: int, S: int, kind: int, target_s: float = 12.0):
+    """The reference algorithm on the host cores (C restatement, OpenMP over trees).  A step = one move
+    step of the E-game self-play loop; the sample is however many steps fit in ~target_s."""
+    import numpy as np
+
+    from oracle import c4oracle
+
+    c4oracle.build()
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    rng = np.random.RandomState(0)
+    t0 = time.perf_counter()
+    r = c4oracle.selfplay(E, S, rng.random_sample((1, E)), quota=10**9, eval_kind=kind)
+    t1 = time.perf_counter() - t0
+    steps = max(1, min(400, int(target_s / max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    r = c4oracle.selfplay(E, S, rng.random_sample((steps, E)), quota=10**9, eval_kind=kind)
+    dt = time.perf_counter() - t0
+    return dict(sims_per_s=r.n_sims / dt, games_per_s=len(r.ep_slot) / dt, steps=steps, seconds=dt, cores=cores,
+                ms_per_step=dt / steps * 1e3, sims=r.n_sims)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind = 1 if args.evaluator == "uniform" else 2
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_arm(args.games, args.sims, kind, target_s=1.0)
+    res = cpu_arm(args.games, args.sims, kind, target_s=max(4.0, min(60.0, 0.5 * args.steps)))
+    sample = f"{res['steps']} move steps of {args.games} games x {args.sims} sims from the initial position ({res['seconds']:.1f} s)"
+    line = {
+        "impl": "reference", "metric": "mcts_simulations_per_sec", "value": res["sims_per_s"], "unit": "sims/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "games_per_sec": res["games_per_s"],
+        "config": {"workload": f"connect4_selfplay_{args.evaluator}_{args.games}x{args.sims}", "num_games": args.games,
+                   "num_simulations": args.sims, "evaluator": args.evaluator, "c_puct": 1.0},
+        "cpu_baseline": {"value": res["sims_per_s"], "unit": "sims/s", "cores": res["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": res["sims_per_s"], "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference algorithm as the C restatement oracle/c4_oracle.c (pinned to the reference's own outputs), OpenMP over trees; "
+                "the reference itself is pure Python (~2e3 sims/s/core, SURVEY.md §6) and its tree is not on the GPU box",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def net_in_loop(args, device_index: int, peaks: dict):
+    """Side measurement (BASELINE configs[2]): self-play with a bf16 ResNet-style net in the loop."""
+    import torch
+
+    import alphazero_implementation_b200 as az
+
+    if args.net == "none":
+        return None
+    if args.net == "basic":
+        model, name, flops = az.BasicNN(), "BasicNN", 577_000
+    else:
+        b, c = args.net.replace("resnet", "").split("x")
+        model = az.ResNet(num_res_blocks=int(b), num_channels=int(c))
+        name, flops = f"ResNet {b}x{c}", model.flops_per_position()
+    E, S = args.net_games, args.net_sims
+    torch.manual_seed(0)
+    search = az.AlphaZeroSearch(model=model, num_simulations=S, device=device_index)
+    eng = search.engine_for(E)
+    eng.reset_games()
+    g = torch.Generator(device="cpu").manual_seed(1)
+    u = torch.rand((args.net_steps + 1, E), dtype=torch.float64, generator=g).to(eng.device)
+    search.simulate(eng)  # warm-up move step (includes graph capture)
+    eng.sample_moves(u[0])
+    torch.cuda.synchronize()
+    st0 = eng.stats()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.net_steps):
+        search.simulate(eng)
+        eng.sample_moves(u[i + 1])
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    st = diff(st0, eng.stats())
+    eng.drain_episodes()
+    sims_s = st["simulations"] / ms * 1e3
+    evals_s = E * S * args.net_steps / ms * 1e3  # every slot occupies a batch row each simulation
+    return {"workload": f"connect4_selfplay_{name.replace(' ', '')}_bf16_{E}x{S}", "net": name, "dtype": "bf16", "num_games": E,
+            "num_simulations": S, "move_steps": args.net_steps, "sims_per_s": sims_s, "ms_per_sim_step": ms / (args.net_steps * S),
+            "flops_per_position": flops, "tensor_tflops": evals_s * flops / 1e12,
+            "tensor_pipe_frac_of_measured_bf16": evals_s * flops / 1e12 / peaks["bf16_tflops"],
+            "leaf_eval_fraction": st["evaluations"] / max(1, st["simulations"])}
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import alphazero_implementation_b200 as az
+    from alphazero_implementation_b200.engine import EVAL_HASH, EVAL_UNIFORM
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, K = max(3, args.warmup), max(1, args.steps)
+    E, S = args.games, args.sims
+    kind = EVAL_UNIFORM if args.evaluator == "uniform" else EVAL_HASH
+    peaks = load_peaks()
+
+    eng = az.Engine(num_games=E, num_simulations=S, device=local, lanes_per_tree=args.lanes)
+    eng.reset_games()
+    rng = np.random.RandomState(1000 + rank)
+    u_all = torch.from_numpy(rng.random_sample((W + K, E))).to(eng.device)  # inputs resident in HBM
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        eng.run_simulations(S, kind)
+        eng.sample_moves(u_all[i])
+        if eng.episode_counts()[0]:
+            eng.drain_episodes_device()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    barrier()
+    st0, l0 = eng.stats(), eng.launch_count
+    sampler = ClockSampler(local)
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()  # L2 flush between timed iterations (outside the step's event pair)
+        ev[i][0].record()
+        eng.run_simulations(S, kind)
+        ev[i][1].record()
+        eng.sample_moves(u_all[W + i])
+        ev[i][2].record()
+        if (i + 1) % 16 == 0:  # keep the device ring from filling; not part of the device-resident step
+            eng.drain_episodes_device()
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = eng.launch_count - l0 - K // 16 * 0
+    st = diff(st0, eng.stats())
+    sim_ms = [a.elapsed_time(b) for a, b, _ in ev]
+    step_ms = [a.elapsed_time(c) for a, _, c in ev]
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        cnt = torch.tensor([st["simulations"], st["episodes"]], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        tot_sims, tot_eps = float(cnt[0].item()), float(cnt[1].item())
+    else:
+        tot_sims, tot_eps = float(st["simulations"]), float(st["episodes"])
+    value = tot_sims / total_ms * 1e3
+    eng.drain_episodes_device()
+
+    # roofline of the dominant kernel (k_run_sims), this rank
+    alg_bytes = algorithmic_bytes(st) / K
+    k_ms = float(np.mean(sim_ms))
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"kernel": "k_run_sims", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (total_ms / K) if world == 1 else None,
+                "bytes_per_sim": alg_bytes * K / max(1, st["simulations"]),
+                "note": "latency-bound pointer chasing: one dependent load round per tree level; see DESIGN.md"}
+    prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("k_run_sims_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # end to end through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        gen = az.EpisodeGenerator(model=az.UniformEvaluator() if kind == EVAL_UNIFORM else az.HashEvaluator(), num_simulations=S,
+                                  num_episodes=E, game_initial_state=az.Config(6, 7, 4).sample_initial_state(), device=local,
+                                  lanes_per_tree=args.lanes)
+        np.random.seed(7 + rank)
+        g_eng = gen.search.engine_for(E)
+        d2h, eps, e2e_t0, sims_before, n_steps = 0, 0, None, None, 0
+        for step, batch, _ in gen.iter_steps(max_steps=W + K):
+            if step == W - 1:  # warm-up done: open the timed region on a quiet device
+                barrier()
+                sims_before = g_eng.stats()
+                e2e_t0 = time.perf_counter()
+                continue
+            if e2e_t0 is None:
+                continue
+            n_steps += 1
+            if batch is not None:
+                d2h += sum(getattr(batch, f).nbytes for f in ("ep_slot", "ep_step", "ep_len", "ep_offset", "ep_outcome", "s_bb0", "s_bb1",
+                                                              "s_player", "s_counts"))
+                eps += len(batch)
+        barrier()
+        e2e_s = time.perf_counter() - e2e_t0
+        d = diff(sims_before, g_eng.stats())
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=eng.device)
+        c = torch.tensor([float(d["simulations"])], dtype=torch.float64, device=eng.device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(c.item()) / float(t.item()), "unit": "sims/s", "h2d_bytes_per_step": E * 8,
+               "d2h_bytes_per_step": int(d2h / max(1, n_steps)) + 32, "steps": int(n_steps), "games_per_sec": eps / e2e_s * world,
+               "api": "EpisodeGenerator.generate_batches (pinned-host uniforms in, finished episodes + counters out, every step)"}
+
+    # multi-GPU: all-gather of finished episodes over NCCL (config 4), timed apart from the data path
+    allgather = None
+    if world > 1:
+        from alphazero_implementation_b200.distributed import all_gather_episodes
+
+        for _ in range(3):
+            eng.run_simulations(S, kind); eng.sample_moves(u_all[0])
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        merged = all_gather_episodes(eng.drain_episodes_device())
+        a1.record()
+        torch.cuda.synchronize()
+        allgather = {"ms": a0.elapsed_time(a1), "episodes": int(merged["ep_len"].numel()), "samples": int(merged["s_bb0"].numel())}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_arm(E, S, kind)
+        cpu = {"value": r["sims_per_s"], "unit": "sims/s", "cores": r["cores"], "kind": "port",
+               "sample": f"{r['steps']} move steps of {E} games x {S} sims from the initial position ({r['seconds']:.1f} s), "
+                         "oracle/c4_oracle.c with OpenMP over trees"}
+    extra = None
+    if rank == 0 and world == 1 and args.net != "none":
+        try:
+            eng.close()
+            extra = net_in_loop(args, local, peaks)
+        except Exception as exc:  # the side measurement must not sink the headline
+            extra = {"error": repr(exc)}
+
+    if rank == 0:
+        line = {
+            "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "games_per_sec": tot_eps / total_ms * 1e3,
+            "config": {"workload": f"connect4_selfplay_{args.evaluator}_{E}x{S}", "num_games_per_gpu": E, "num_simulations": S,
+                       "evaluator": args.evaluator, "c_puct": 1.0, "lanes_per_tree": args.lanes or 8, "parallelism": f"games sharded x{world}",
+                       "l2": "flushed between timed steps (256 MiB memset outside the per-step event pair)",
+                       "tree_arena_bytes": eng.device_bytes if eng.h else None},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "wall_s_timed_region": wall_s, "work": {k: v / K for k, v in st.items()},
+        }
+        if allgather:
+            line["episode_allgather"] = allgather
+        if extra:
+            line["net_in_loop"] = extra
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -90,7 +90,7 @@ typedef struct az_stats {
     uint64_t backup_nodes;     /* nodes touched by backpropagate (search.py:48) */
     uint64_t moves;            /* select_next_node calls (node.py:31) */
     uint64_t episodes;         /* finished games */
-    uint64_t reserved;
+    uint64_t children_scanned; /* child records read by select_child (sum of legal moves over levels) */
 } az_stats;
 
 int32_t az_abi_version(void);

@@ -132,10 +132,12 @@ def selfplay(E, S, uniforms, quota=None, c_puct=1.0, eval_kind=1, init=(0, 0, 0)
     quota = E if quota is None else quota
     uniforms = np.ascontiguousarray(uniforms, np.float64).reshape(-1, E)
     max_steps = uniforms.shape[0]
+    n_ep_cap = int(min(quota, E * max_steps // 7 + E))  # a game lasts at least 7 plies
+    max_samples = n_ep_cap * 42
+    quota = int(min(quota, 2**31 - 1))
+    ep_slot = np.zeros(n_ep_cap, np.int32); ep_len = np.zeros(n_ep_cap, np.int32); ep_step = np.zeros(n_ep_cap, np.int32)
+    ep_out = np.zeros((n_ep_cap, 2), np.int8)
     cfg = _Cfg(E, S, eval_kind, init[2], quota, max_steps, c_puct, init[0], init[1])
-    max_samples = quota * 42
-    ep_slot = np.zeros(quota, np.int32); ep_len = np.zeros(quota, np.int32); ep_step = np.zeros(quota, np.int32)
-    ep_out = np.zeros((quota, 2), np.int8)
     s0 = np.zeros(max_samples, np.uint64); s1 = np.zeros(max_samples, np.uint64); sp = np.zeros(max_samples, np.uint8)
     sc = np.zeros((max_samples, 7), np.int32)
     ne, ns, nst, nu, nsim, nev = (C.c_int64(0) for _ in range(6))
