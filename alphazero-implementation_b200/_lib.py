@@ -98,6 +98,7 @@ SIGNATURES = {
     "az_drain_episodes": (I32, [P, I64, I64, P, P, P, P, P, P, P, P, P, C.POINTER(I64), C.POINTER(I64), P]),
     "az_get_stats": (I32, [P, C.POINTER(AzStats), P]),
     "az_reset_stats": (I32, [P, P]),
+    "az_selftest_division": (I32, [P, I64, C.c_uint64, C.POINTER(I64)]),
     "az_launch_count": (I64, [P]),
 }
 

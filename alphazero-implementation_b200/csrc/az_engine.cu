@@ -2,21 +2,27 @@
 // C ABI in include/az_engine.h.  Built for sm_100a only; there is no CPU path.
 //
 // Data layout in HBM (structure of arrays, tree-major, `cap` = roundup8(1 + 7*S) nodes per tree):
-//   W [E][cap] f64   value_sum      (node.py:14)      fp64 because Python sums doubles
-//   N [E][cap] u32   visit_count    (node.py:13)
-//   P [E][cap] f32   prior          (node.py:15; fp32 softmax output widened to double when scored)
-//   CB[E][cap] u32   index of the first child (children of a node are contiguous, ascending column
-//                    = dict insertion order of node.children, search.py:88-90); 0 = not expanded
-// Node 0 is the root.  Positions are NOT stored per node: the descent replays the chosen columns on
-// the root bitboards held in registers (a drop + win test is ~20 integer ops, a node-sized load is not).
+//   W[E][cap] f64     value_sum (node.py:14); fp64 because the reference sums Python floats
+//   M[E][cap] uint4   {visit_count u32 (node.py:13), prior f32 bits (node.py:15), first-child index u32, 0}
+//                     one 16-byte vector load per child; children of a node are contiguous in ascending
+//                     column order (= dict insertion order of node.children, search.py:88-90); 0 = not expanded
+// Node 0 is the root.  Positions are NOT stored per node: the descent replays the chosen columns on the
+// root bitboards held in registers (a drop + line test is ~20 integer ops; a node-sized load is not).
 //
-// Work decomposition: a group of G lanes (G = 32: one warp per tree; G = 8: four trees per warp) owns
-// one tree for the whole launch.  Lane c (< 7) of every 8-lane subgroup handles column c of the current
-// node: it loads that child's N/W/P/CB (coalesced, neighbouring lanes read neighbouring words), scores
-// it in fp64 with the reference's operation order and rounding, and the best child is found with a
-// __shfl_xor butterfly on (score, column) — strict '>' with the lowest column winning ties, which is
-// the reference's first-maximum rule.  The tree is owned by one group, so its updates need no atomics;
-// __syncwarp orders them between lanes.
+// Work decomposition: eight lanes own one tree for the whole launch (TPW = 4 trees per warp), or a whole
+// warp owns one (TPW = 1; its four 8-lane quarters then compute the same thing).  Lane c (< 7) of each
+// quarter handles column c of the current node: it loads that child's record (coalesced: neighbouring
+// lanes read neighbouring records), scores it in fp64 with the reference's operation order and
+// rounding, and the best child is found with a __shfl_xor butterfly (max) + ballot (lowest column among
+// the maxima = the reference's strict '>' first-maximum rule).  The warp stays converged — quarters
+// whose tree has reached its leaf idle with their loads predicated off — so every shuffle / ballot
+// uses the full mask and no divergence bookkeeping is generated.  A tree is owned by one quarter, so
+// updates need no atomics; __syncwarp orders them between lanes.
+//
+// fp64 without the division subroutine: the divisors of PUCT are small integers (visit counts <= S),
+// so 1/d and sqrt(n) come from tables of correctly rounded values (built once per engine with
+// __drcp_rn / __dsqrt_rn) and x/d is finished with two FMA residual corrections, which yields the
+// correctly rounded quotient (Markstein); tests/test_gpu_search.py checks it against __ddiv_rn.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -33,12 +39,13 @@ namespace {
 constexpr int PATH_STRIDE = 44;  // root + at most 42 plies (+1 pad)
 constexpr int MAX_PLIES = 42;
 constexpr int NSTAT = 7;  // per-tree counters: sims, evals, levels, children, moves, episodes, children scanned
+constexpr unsigned FULL = 0xFFFFFFFFu;
 
 struct Arena {
     double *W;
-    uint32_t *N;
-    float *P;
-    uint32_t *CB;
+    uint4 *M;  // x = N, y = prior bits, z = first child, w = 0
+    const double *rcp;  // rcp[d] = RN(1/d), d = 0 .. S+1 (rcp[0] unused)
+    const double *sqt;  // sqt[n] = RN(sqrt(n))
     uint64_t *root_bb0, *root_bb1;
     uint8_t *root_player;
     uint32_t *used;
@@ -47,7 +54,7 @@ struct Arena {
     uint32_t *leaf_node;
     uint64_t *leaf_bb0, *leaf_bb1;
     uint8_t *leaf_player, *leaf_status, *leaf_depth;
-    uint32_t *path;  // [E][PATH_STRIDE]
+    uint32_t *path;    // [E][PATH_STRIDE]
     uint32_t *tstats;  // [E][NSTAT]
     // game in progress per slot
     uint64_t *g_bb0, *g_bb1;  // [E][42]
@@ -65,87 +72,129 @@ struct Arena {
     int64_t ep_cap, s_cap;
     int cap;  // nodes per tree
     int E;
+    int tab_n;  // entries in rcp / sqt
 };
 
 // ------------------------------------------------------------------------------------------------
-// group helpers
-template <int G>
-__device__ __forceinline__ unsigned group_mask() {
-    if (G == 32) return 0xFFFFFFFFu;
-    return 0xFFu << (threadIdx.x & 24);
+// exact fp64 helpers
+// x / d for an integer 1 <= d < tab_n, correctly rounded: r = RN(1/d) from the table, then two
+// residual corrections (q += (x - d*q) * r).  The first makes q faithful, the second exact-rounded.
+__device__ __forceinline__ double div_tab(double x, uint32_t d, const double *__restrict__ rcp) {
+    const double r = __ldg(rcp + d);
+    const double nd = -(double)d;
+    double q = __dmul_rn(x, r);
+    q = __fma_rn(__fma_rn(nd, q, x), r, q);
+    return __fma_rn(__fma_rn(nd, q, x), r, q);
 }
+
+// score = child.value + c * child.prior * sqrt(node.visit_count) / (1 + child.visit_count), evaluated
+// left to right in fp64 with one rounding per operation (search.py:33-40).  child.value = W/N, 0 if N == 0
+// (node.py:50-55); W == 0 gives q = 0 without dividing (N == 0 implies W == 0).
+__device__ __forceinline__ double puct_score(uint32_t n, double w, float p, double sq, double c_puct,
+                                             const double *__restrict__ rcp) {
+    const double u = div_tab(__dmul_rn(__dmul_rn(c_puct, (double)p), sq), 1u + n, rcp);
+    const double q = (w == 0.0) ? 0.0 : div_tab(w, n, rcp);
+    return __dadd_rn(q, u);
+}
+
+// first maximum over the 7 columns of an 8-lane quarter: butterfly max, then the lowest lane holding it
+__device__ __forceinline__ int argmax_first(double score, int sub) {
+    double m = score;
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) {
+        const double o = __shfl_xor_sync(FULL, m, off);
+        m = (o > m) ? o : m;
+    }
+    const unsigned eq = __ballot_sync(FULL, score == m);
+    return __ffs((eq >> sub) & 0xFFu) - 1;
+}
+
+struct Child {  // the record of "my" column's child at the current node
+    double w;
+    uint32_t n, cb;
+    float p;
+};
+
+__device__ __forceinline__ Child load_child(const double *__restrict__ Wt, const uint4 *__restrict__ Mt, uint32_t idx) {
+    Child ch;
+    const uint4 m = Mt[idx];
+    ch.w = Wt[idx];
+    ch.n = m.x;
+    ch.p = __uint_as_float(m.y);
+    ch.cb = m.z;
+    return ch;
+}
+
+__device__ __forceinline__ void store_new_child(double *Wt, uint4 *Mt, uint32_t idx, float prior) {
+    Wt[idx] = 0.0;
+    Mt[idx] = make_uint4(0u, __float_as_uint(prior), 0u, 0u);
+}
+
+__device__ __forceinline__ uint32_t *node_N(uint4 *Mt, uint32_t idx) { return reinterpret_cast<uint32_t *>(Mt + idx); }
+__device__ __forceinline__ uint32_t *node_CB(uint4 *Mt, uint32_t idx) { return reinterpret_cast<uint32_t *>(Mt + idx) + 2; }
 
 struct Leaf {
     uint64_t b0, b1;
     uint32_t node;
     int pl;     // side to move at the leaf
     int depth;  // number of moves below the root
+    int first_col;  // column chosen at the root (valid when depth >= 1)
     bool win;   // the move into the leaf made 4-in-line (mover = pl ^ 1)
     bool term;  // win or board full
 };
 
 // AlphaZeroSearch.select_child repeated until an unexpanded node (search.py:72-73, 27-46).
-// `path[d]` receives the node index at depth d.  Every lane of the group returns the same Leaf.
-template <int G>
-__device__ __forceinline__ Leaf descend(const double *__restrict__ Wt, const uint32_t *__restrict__ Nt,
-                                        const float *__restrict__ Pt, const uint32_t *__restrict__ CBt,
-                                        uint64_t rb0, uint64_t rb1, int rpl, double c_puct, uint32_t *path,
-                                        unsigned gmask, uint32_t &levels, uint32_t &scanned) {
+// Warp-converged: every lane of the warp calls this; `alive` is uniform per quarter.  On entry
+// (cb, n_parent) describe the root and (root_legal, ch) hold the root's legal mask and this lane's
+// root child record (valid when alive && cb != 0) — the fused kernel keeps them in registers across
+// simulations.  `path[d]` receives the node index at depth d (written by lane 0 of the tree's lanes).
+__device__ __forceinline__ Leaf descend(const double *__restrict__ Wt, const uint4 *__restrict__ Mt,
+                                        const double *__restrict__ rcp, const double *__restrict__ sqt,
+                                        uint64_t rb0, uint64_t rb1, int rpl, double c_puct, uint32_t cb,
+                                        uint32_t n_parent, unsigned legal, Child ch, bool alive, bool writer,
+                                        uint32_t *path, uint32_t &levels, uint32_t &scanned) {
     const int lane = threadIdx.x & 31;
-    const int sub = lane & 24;  // first lane of my 8-lane subgroup
-    const int c = lane & 7;     // the column this lane scores (7 = none)
-    const bool writer = (threadIdx.x & (G - 1)) == 0;
+    const int sub = lane & 24;
+    const int c = lane & 7;
     Leaf L;
     L.b0 = rb0;
     L.b1 = rb1;
     L.pl = rpl;
     L.node = 0;
     L.depth = 0;
-    uint32_t cb = CBt[0];
-    uint32_t n_parent = Nt[0];
-    if (writer) path[0] = 0;
-    while (cb != 0) {
-        const uint64_t occ = L.b0 | L.b1;
-        const bool my_legal = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);
-        const unsigned legal = (__ballot_sync(gmask, my_legal) >> sub) & 0x7Fu;
-        const int j = __popc(legal & ((1u << c) - 1u));
+    L.first_col = 0;
+    bool go = alive && cb != 0;
+    bool my_legal = (legal >> c) & 1u;
+    while (__any_sync(FULL, go)) {
         double score = -INFINITY;
-        uint32_t n = 0, ccb = 0;
-        if (my_legal) {
-            const uint32_t idx = cb + j;
-            n = Nt[idx];
-            const double w = Wt[idx];
-            const float p = Pt[idx];
-            ccb = CBt[idx];
-            // score = child.value + c * child.prior * sqrt(node.visit_count) / (1 + child.visit_count)
-            // evaluated left to right in fp64, one rounding per operation (search.py:33-40).
-            const double q = n ? __ddiv_rn(w, (double)n) : 0.0;
-            const double sq = __dsqrt_rn((double)n_parent);
-            const double u = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, (double)p), sq), (double)(1u + n));
-            score = __dadd_rn(q, u);
+        if (go && my_legal) score = puct_score(ch.n, ch.w, ch.p, __ldg(sqt + n_parent), c_puct, rcp);
+        const int bc = argmax_first(score, sub);
+        const uint32_t n_sel = __shfl_sync(FULL, ch.n, sub + bc);
+        const uint32_t cb_sel = __shfl_sync(FULL, ch.cb, sub + bc);
+        if (go) {
+            // Action.sample_next_state(): drop in column bc, flip the side to move
+            const uint64_t bit = c4::drop_bit(L.b0 | L.b1, bc);
+            if (L.pl == 0) L.b0 |= bit; else L.b1 |= bit;
+            L.pl ^= 1;
+            L.node = cb + __popc(legal & ((1u << bc) - 1u));
+            if (L.depth == 0) L.first_col = bc;
+            L.depth++;
+            if (writer) path[L.depth] = L.node;
+            levels++;
+            scanned += (uint32_t)__popc(legal);
+            n_parent = n_sel;
+            cb = cb_sel;
+            go = cb != 0;
         }
-        int bc = c;
-#pragma unroll
-        for (int off = 4; off >= 1; off >>= 1) {
-            const double os = __shfl_xor_sync(gmask, score, off);
-            const int oc = __shfl_xor_sync(gmask, bc, off);
-            if (os > score || (os == score && oc < bc)) {
-                score = os;
-                bc = oc;
-            }
+        // the children of the node just entered
+        const uint64_t occ = L.b0 | L.b1;
+        const bool can = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);
+        const unsigned lg = (__ballot_sync(FULL, can) >> sub) & 0x7Fu;
+        if (go) {
+            legal = lg;
+            my_legal = can;
+            if (can) ch = load_child(Wt, Mt, cb + __popc(lg & ((1u << c) - 1u)));
         }
-        n_parent = __shfl_sync(gmask, n, sub + bc);
-        const uint32_t next_cb = __shfl_sync(gmask, ccb, sub + bc);
-        // Action.sample_next_state(): drop in column bc, flip the side to move
-        const uint64_t bit = c4::drop_bit(occ, bc);
-        if (L.pl == 0) L.b0 |= bit; else L.b1 |= bit;
-        L.pl ^= 1;
-        L.node = cb + __popc(legal & ((1u << bc) - 1u));
-        cb = next_cb;
-        L.depth++;
-        if (writer) path[L.depth] = L.node;
-        levels++;
-        scanned += (uint32_t)__popc(legal);
     }
     // Node.is_terminal of the leaf (node.py:61-63).  Interior nodes are never terminal (a terminal
     // node is never expanded), so only the last mover's stones need the line test.
@@ -160,68 +209,79 @@ __device__ __forceinline__ Leaf descend(const double *__restrict__ Wt, const uin
 
 // AlphaZeroSearch.backpropagate (search.py:48-57) along the recorded path: the leaf gets +v, the sign
 // flips going up except across a terminal leaf.  Stops at the current root (older ancestors are never
-// read again).
-template <int G>
-__device__ __forceinline__ void backup(double *Wt, uint32_t *Nt, const uint32_t *path, int depth, double v,
-                                       bool leaf_terminal) {
-    for (int i = threadIdx.x & (G - 1); i <= depth; i += G) {
+// read again).  `lit` = lane index within the tree's lanes, `nl` = lanes per tree.
+__device__ __forceinline__ void backup(double *Wt, uint4 *Mt, const uint32_t *path, int depth, double v,
+                                       bool leaf_terminal, int lit, int nl, int first) {
+    for (int i = first + lit; i <= depth; i += nl) {
         const uint32_t nd = path[i];
         const int d = depth - i;
         const bool neg = leaf_terminal ? (d >= 1 && ((d - 1) & 1)) : (d & 1);
         Wt[nd] = __dadd_rn(Wt[nd], neg ? -v : v);
-        Nt[nd] += 1u;
+        *node_N(Mt, nd) += 1u;
     }
 }
 
-// node.add_child for every legal column (search.py:88-90): children contiguous at `first`, zeroed statistics.
-__device__ __forceinline__ void write_child(double *Wt, uint32_t *Nt, float *Pt, uint32_t *CBt, uint32_t idx,
-                                            float prior) {
-    Wt[idx] = 0.0;
-    Nt[idx] = 0u;
-    Pt[idx] = prior;
-    CBt[idx] = 0u;
+__device__ __forceinline__ double backup_sign(double v, int depth, int i, bool leaf_terminal) {
+    const int d = depth - i;
+    const bool neg = leaf_terminal ? (d >= 1 && ((d - 1) & 1)) : (d & 1);
+    return neg ? -v : v;
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused search: all S simulations of a tree in one launch, built-in evaluator
-template <int G, int EVAL>
-__global__ void __launch_bounds__(G == 32 ? 128 : 64)
-k_run_sims(Arena a, int n_active, int S, double c_puct) {
-    constexpr int THREADS = (G == 32) ? 128 : 64;
-    constexpr int TREES = THREADS / G;
+// fused search: all S simulations of a tree in one launch, built-in evaluator.
+// The root's scalars (N, first child, legal mask) and each lane's root-child record live in registers
+// for the whole launch; memory is kept in step so that every other kernel sees a complete tree.
+template <int TPW, int EVAL>
+__global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, double c_puct) {
+    constexpr int TREES = 2 * TPW;  // per 64-thread block
+    constexpr int NL = 32 / TPW;    // lanes per tree
     __shared__ uint32_t s_path[TREES][PATH_STRIDE];
-    const int tib = threadIdx.x / G;
-    const int t = blockIdx.x * TREES + tib;
-    if (t >= n_active) return;
-    if (a.tree_err[t]) return;
-    const unsigned gmask = group_mask<G>();
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int sub = lane & 24;
     const int c = lane & 7;
-    const bool writer = (threadIdx.x & (G - 1)) == 0;
-    const bool first_sub = (threadIdx.x & (G - 1)) < 8;
+    const int q = (TPW == 4) ? (lane >> 3) : 0;
+    const int tib = warp * TPW + q;
+    const int t = blockIdx.x * TREES + tib;
+    const bool alive = (t < n_active) && (a.tree_err[t < n_active ? t : 0] == 0);
+    if (!__any_sync(FULL, alive)) return;
+    const int tt = alive ? t : 0;
+    const int lit = lane & (NL - 1);
+    const bool writer = alive && lit == 0;
+    const bool first_q = lit < 8;
 
-    const size_t base = (size_t)t * a.cap;
+    const size_t base = (size_t)tt * a.cap;
     double *Wt = a.W + base;
-    uint32_t *Nt = a.N + base;
-    float *Pt = a.P + base;
-    uint32_t *CBt = a.CB + base;
+    uint4 *Mt = a.M + base;
     uint32_t *path = s_path[tib];
-    const uint64_t rb0 = a.root_bb0[t], rb1 = a.root_bb1[t];
-    const int rpl = a.root_player[t];
-    uint32_t used = a.used[t];
+    const uint64_t rb0 = a.root_bb0[tt], rb1 = a.root_bb1[tt];
+    const int rpl = a.root_player[tt];
+    uint32_t used = a.used[tt];
     uint32_t levels = 0, evals = 0, children = 0, scanned = 0;
 
+    // root registers
+    const uint4 rm = Mt[0];
+    uint32_t root_n = rm.x, root_cb = rm.z;
+    const bool r_can = (c < c4::W) && !(((rb0 | rb1) >> (c4::STRIDE * c + 5)) & 1ull);
+    const unsigned r_legal = (__ballot_sync(FULL, r_can) >> sub) & 0x7Fu;
+    const int r_j = __popc(r_legal & ((1u << c) - 1u));
+    Child rch;
+    rch.w = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
+    if (alive && root_cb != 0 && r_can) rch = load_child(Wt, Mt, root_cb + r_j);
+    if (writer) path[0] = 0;
+
     for (int s = 0; s < S; ++s) {
-        Leaf L = descend<G>(Wt, Nt, Pt, CBt, rb0, rb1, rpl, c_puct, path, gmask, levels, scanned);
+        Leaf L = descend(Wt, Mt, a.rcp, a.sqt, rb0, rb1, rpl, c_puct, root_cb, root_n, r_legal, rch, alive, writer, path,
+                         levels, scanned);
+        // leaf: evaluate + expand, or terminal value
+        const uint64_t occ = L.b0 | L.b1;
+        const bool can = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);
+        const unsigned legal = (__ballot_sync(FULL, can) >> sub) & 0x7Fu;
         double v;
         if (L.term) {
             // value = reward[parent.state.player]: the mover's own reward, +1 on a win, 0 on a draw (search.py:76)
             v = L.win ? 1.0 : 0.0;
         } else {
-            const uint64_t occ = L.b0 | L.b1;
-            const bool my_legal = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);
-            const unsigned legal = (__ballot_sync(gmask, my_legal) >> sub) & 0x7Fu;
             const int k = __popc(legal);
             const int j = __popc(legal & ((1u << c) - 1u));
             float prior, val;
@@ -234,16 +294,32 @@ k_run_sims(Arena a, int n_active, int S, double c_puct) {
                 const float v0 = azeval::hash_value0(h);
                 val = L.pl == 0 ? v0 : -v0;
             }
-            if (my_legal && first_sub) write_child(Wt, Nt, Pt, CBt, used + j, prior);
-            if (writer) CBt[L.node] = used;
-            used += k;
-            children += k;
-            evals++;
+            if (alive) {
+                if (can && first_q) store_new_child(Wt, Mt, used + j, prior);
+                if (writer) *node_CB(Mt, L.node) = used;
+                if (L.depth == 0) {  // the root itself was expanded: its children enter the registers
+                    root_cb = used;
+                    rch.w = 0.0; rch.n = 0; rch.cb = 0; rch.p = prior;
+                } else if (L.depth == 1 && c == L.first_col) {
+                    rch.cb = used;
+                }
+                used += k;
+                children += k;
+                evals++;
+            }
             v = (double)val;  // value[node.state.player] (search.py:91)
         }
-        __syncwarp(gmask);
-        backup<G>(Wt, Nt, path, L.depth, v, L.term);
-        __syncwarp(gmask);
+        __syncwarp();
+        if (alive) {
+            // registers: root and the chosen root child; memory: every node on the path
+            root_n += 1u;
+            if (L.depth >= 1 && c == L.first_col) {
+                rch.n += 1u;
+                rch.w = __dadd_rn(rch.w, backup_sign(v, L.depth, 1, L.term));
+            }
+            backup(Wt, Mt, path, L.depth, v, L.term, lit, NL, 0);
+        }
+        __syncwarp();
     }
     if (writer) {
         a.used[t] = used;
@@ -258,25 +334,38 @@ k_run_sims(Arena a, int n_active, int S, double c_puct) {
 
 // ------------------------------------------------------------------------------------------------
 // split path, step 1: search.py:69-79
-template <int G>
-__global__ void __launch_bounds__(G == 32 ? 128 : 64) k_select(Arena a, int n_active, double c_puct) {
-    constexpr int THREADS = (G == 32) ? 128 : 64;
-    constexpr int TREES = THREADS / G;
-    const int t = blockIdx.x * TREES + threadIdx.x / G;
-    if (t >= n_active) return;
-    const bool writer = (threadIdx.x & (G - 1)) == 0;
-    if (a.tree_err[t]) {
-        if (writer) a.leaf_status[t] = AZ_LEAF_IDLE;
-        return;
-    }
-    const unsigned gmask = group_mask<G>();
-    const size_t base = (size_t)t * a.cap;
+template <int TPW>
+__global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_puct) {
+    constexpr int TREES = 2 * TPW;
+    constexpr int NL = 32 / TPW;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int sub = lane & 24;
+    const int c = lane & 7;
+    const int q = (TPW == 4) ? (lane >> 3) : 0;
+    const int t = blockIdx.x * TREES + warp * TPW + q;
+    const bool in_range = t < n_active;
+    const bool alive = in_range && (a.tree_err[in_range ? t : 0] == 0);
+    const int lit = lane & (NL - 1);
+    if (in_range && !alive && lit == 0) a.leaf_status[t] = AZ_LEAF_IDLE;
+    if (!__any_sync(FULL, alive)) return;
+    const int tt = alive ? t : 0;
+    const bool writer = alive && lit == 0;
+    const size_t base = (size_t)tt * a.cap;
     double *Wt = a.W + base;
-    uint32_t *Nt = a.N + base;
-    uint32_t *path = a.path + (size_t)t * PATH_STRIDE;
+    uint4 *Mt = a.M + base;
+    uint32_t *path = a.path + (size_t)tt * PATH_STRIDE;
+    const uint64_t rb0 = a.root_bb0[tt], rb1 = a.root_bb1[tt];
+    const uint4 rm = Mt[0];
+    const bool r_can = (c < c4::W) && !(((rb0 | rb1) >> (c4::STRIDE * c + 5)) & 1ull);
+    const unsigned r_legal = (__ballot_sync(FULL, r_can) >> sub) & 0x7Fu;
+    Child rch;
+    rch.w = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
+    if (alive && rm.z != 0 && r_can) rch = load_child(Wt, Mt, rm.z + __popc(r_legal & ((1u << c) - 1u)));
+    if (writer) path[0] = 0;
     uint32_t levels = 0, scanned = 0;
-    Leaf L = descend<G>(Wt, Nt, a.P + base, a.CB + base, a.root_bb0[t], a.root_bb1[t], a.root_player[t], c_puct,
-                        path, gmask, levels, scanned);
+    Leaf L = descend(Wt, Mt, a.rcp, a.sqt, rb0, rb1, a.root_player[tt], c_puct, rm.z, rm.x, r_legal, rch, alive, writer, path,
+                     levels, scanned);
     if (writer) {
         a.leaf_node[t] = L.node;
         a.leaf_bb0[t] = L.b0;
@@ -289,41 +378,42 @@ __global__ void __launch_bounds__(G == 32 ? 128 : 64) k_select(Arena a, int n_ac
         st[2] += levels;
         st[6] += scanned;
     }
-    if (L.term) {
-        __syncwarp(gmask);
-        backup<G>(Wt, Nt, path, L.depth, L.win ? 1.0 : 0.0, true);
-    }
+    __syncwarp();
+    if (alive && L.term) backup(Wt, Mt, path, L.depth, L.win ? 1.0 : 0.0, true, lit, NL, 0);
 }
 
 // split path, step 3: search.py:87-91 with the evaluator's outputs
-template <int G>
-__global__ void __launch_bounds__(G == 32 ? 128 : 64)
+template <int TPW>
+__global__ void __launch_bounds__(64)
 k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const float *__restrict__ values,
                 int policy_kind) {
-    constexpr int THREADS = (G == 32) ? 128 : 64;
-    constexpr int TREES = THREADS / G;
-    const int t = blockIdx.x * TREES + threadIdx.x / G;
-    if (t >= n_active) return;
-    if (a.leaf_status[t] != AZ_LEAF_EVAL) return;
-    const unsigned gmask = group_mask<G>();
+    constexpr int TREES = 2 * TPW;
+    constexpr int NL = 32 / TPW;
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int sub = lane & 24;
     const int c = lane & 7;
-    const bool writer = (threadIdx.x & (G - 1)) == 0;
-    const bool first_sub = (threadIdx.x & (G - 1)) < 8;
-    const size_t base = (size_t)t * a.cap;
+    const int q = (TPW == 4) ? (lane >> 3) : 0;
+    const int t = blockIdx.x * TREES + warp * TPW + q;
+    const bool alive = (t < n_active) && (a.leaf_status[t < n_active ? t : 0] == AZ_LEAF_EVAL);
+    if (!__any_sync(FULL, alive)) return;
+    const int tt = alive ? t : 0;
+    const int lit = lane & (NL - 1);
+    const bool writer = alive && lit == 0;
+    const bool first_q = lit < 8;
+    const size_t base = (size_t)tt * a.cap;
     double *Wt = a.W + base;
-    uint32_t *Nt = a.N + base;
-    const uint64_t occ = a.leaf_bb0[t] | a.leaf_bb1[t];
-    const int pl = a.leaf_player[t];
-    const uint32_t node = a.leaf_node[t];
-    const int depth = a.leaf_depth[t];
-    const uint32_t used = a.used[t];
-    const bool my_legal = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);
-    const unsigned legal = (__ballot_sync(gmask, my_legal) >> sub) & 0x7Fu;
+    uint4 *Mt = a.M + base;
+    const uint64_t occ = a.leaf_bb0[tt] | a.leaf_bb1[tt];
+    const int pl = a.leaf_player[tt];
+    const uint32_t node = a.leaf_node[tt];
+    const int depth = a.leaf_depth[tt];
+    const uint32_t used = a.used[tt];
+    const bool can = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);
+    const unsigned legal = (__ballot_sync(FULL, can) >> sub) & 0x7Fu;
     const int k = __popc(legal);
     const int j = __popc(legal & ((1u << c) - 1u));
-    float x = my_legal ? policy[(size_t)t * 7 + c] : -INFINITY;
+    const float x = (alive && can) ? policy[(size_t)tt * 7 + c] : -INFINITY;
     float prior;
     if (policy_kind == AZ_POLICY_PRIORS) {
         prior = x;
@@ -331,25 +421,27 @@ k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const f
         // F.softmax over the logits of the legal columns only, fp32 (model.py:29-35)
         float m = x;
 #pragma unroll
-        for (int off = 4; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, off));
-        const float e = my_legal ? expf(x - m) : 0.0f;
+        for (int off = 4; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, off));
+        const float e = (alive && can) ? expf(x - m) : 0.0f;
         float sum = e;
 #pragma unroll
-        for (int off = 4; off >= 1; off >>= 1) sum += __shfl_xor_sync(gmask, sum, off);
+        for (int off = 4; off >= 1; off >>= 1) sum += __shfl_xor_sync(FULL, sum, off);
         prior = __fdiv_rn(e, sum);
     }
-    if (my_legal && first_sub) write_child(Wt, Nt, a.P + base, a.CB + base, used + j, prior);
-    const double v = (double)values[(size_t)t * 2 + pl];
-    if (writer) {
-        a.CB[base + node] = used;
-        a.used[t] = used + k;
-        a.leaf_status[t] = AZ_LEAF_IDLE;  // consumed: a second az_expand_backup without a select is a no-op
-        uint32_t *st = a.tstats + (size_t)t * NSTAT;
-        st[1] += 1u;
-        st[3] += (uint32_t)k;
+    __syncwarp();  // every lane has read used / leaf_* before the writer updates them
+    if (alive) {
+        if (can && first_q) store_new_child(Wt, Mt, used + j, prior);
+        const double v = (double)values[(size_t)tt * 2 + pl];
+        if (writer) {
+            *node_CB(Mt, node) = used;
+            a.used[t] = used + k;
+            a.leaf_status[t] = AZ_LEAF_IDLE;  // consumed: a second az_expand_backup without a select is a no-op
+            uint32_t *st = a.tstats + (size_t)t * NSTAT;
+            st[1] += 1u;
+            st[3] += (uint32_t)k;
+        }
+        backup(Wt, Mt, a.path + (size_t)tt * PATH_STRIDE, depth, v, false, lit, NL, 0);
     }
-    __syncwarp(gmask);
-    backup<G>(Wt, Nt, a.path + (size_t)t * PATH_STRIDE, depth, v, false);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -507,9 +599,7 @@ k_masked_softmax(const float *__restrict__ logits, const uint8_t *__restrict__ l
 __device__ __forceinline__ void reset_tree(const Arena &a, int t) {
     const size_t base = (size_t)t * a.cap;
     a.W[base] = 0.0;
-    a.N[base] = 0u;
-    a.P[base] = 0.0f;
-    a.CB[base] = 0u;
+    a.M[base] = make_uint4(0u, 0u, 0u, 0u);
     a.used[t] = 1u;
 }
 
@@ -535,20 +625,20 @@ k_root_stats(Arena a, int n, int32_t *child_N, double *child_W, float *child_P, 
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const size_t base = (size_t)t * a.cap;
-    const uint32_t cb = a.CB[base];
+    const uint32_t cb = a.M[base].z;
     const int terr = a.tree_err[t];
     const uint32_t legal = terr ? 0u : c4::legal_mask(a.root_bb0[t] | a.root_bb1[t]);
     int j = 0;
     for (int c = 0; c < 7; ++c) {
         const bool has = cb != 0 && ((legal >> c) & 1u);
         const size_t idx = base + cb + j;
-        if (child_N) child_N[(size_t)t * 7 + c] = has ? (int32_t)a.N[idx] : 0;
+        if (child_N) child_N[(size_t)t * 7 + c] = has ? (int32_t)a.M[idx].x : 0;
         if (child_W) child_W[(size_t)t * 7 + c] = has ? a.W[idx] : 0.0;
-        if (child_P) child_P[(size_t)t * 7 + c] = has ? a.P[idx] : 0.0f;
+        if (child_P) child_P[(size_t)t * 7 + c] = has ? __uint_as_float(a.M[idx].y) : 0.0f;
         if (has) ++j;
     }
     if (root_W) root_W[t] = a.W[base];
-    if (root_N) root_N[t] = (int32_t)a.N[base];
+    if (root_N) root_N[t] = (int32_t)a.M[base].x;
     if (legal_out) legal_out[t] = (uint8_t)legal;
     if (err) err[t] = terr;
 }
@@ -575,13 +665,14 @@ k_sample_moves(Arena a, int n, const double *__restrict__ uniforms, uint8_t *fin
     if (finished) finished[t] = 0;
     if (a.tree_err[t]) return;
     const size_t base = (size_t)t * a.cap;
-    const uint32_t cb = a.CB[base];
+    const uint4 rootm = a.M[base];
+    const uint32_t cb = rootm.z;
     if (cb == 0) return;  // no search ran on this root
     uint64_t b0 = a.root_bb0[t], b1 = a.root_bb1[t];
     int pl = a.root_player[t];
     const uint32_t legal = c4::legal_mask(b0 | b1);
     const int k = __popc(legal);
-    const double denom = (double)((int)a.N[base] - 1);  // improved_policy denominator (node.py:27)
+    const double denom = (double)((int)rootm.x - 1);  // improved_policy denominator (node.py:27)
     // sample = (state, improved_policy) recorded before the move (episode_generator.py:56-62)
     const int len = a.g_len[t];
     int32_t cnt[7];
@@ -594,7 +685,7 @@ k_sample_moves(Arena a, int n, const double *__restrict__ uniforms, uint8_t *fin
             cnt[c] = 0;
             cdf[c] = 0.0;
             if ((legal >> c) & 1u) {
-                const int32_t nc = (int32_t)a.N[base + cb + j];
+                const int32_t nc = (int32_t)a.M[base + cb + j].x;
                 cnt[c] = nc;
                 const double p = __ddiv_rn((double)nc, denom);
                 acc = (j == 0) ? p : __dadd_rn(acc, p);  // p.cumsum()
@@ -664,6 +755,45 @@ k_sample_moves(Arena a, int n, const double *__restrict__ uniforms, uint8_t *fin
     reset_tree(a, t);  // no subtree reuse: the new root has no children (node.py:37-41)
 }
 
+__global__ void __launch_bounds__(256) k_init_tables(double *rcp, double *sqt, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rcp[i] = i ? __drcp_rn((double)i) : 0.0;
+    sqt[i] = __dsqrt_rn((double)i);
+}
+
+__global__ void __launch_bounds__(256)
+k_export_tree(Arena a, int slot, double *W, uint32_t *N, float *P, uint32_t *CB) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.cap) return;
+    const size_t idx = (size_t)slot * a.cap + i;
+    const uint4 m = a.M[idx];
+    if (W) W[i] = a.W[idx];
+    if (N) N[i] = m.x;
+    if (P) P[i] = __uint_as_float(m.y);
+    if (CB) CB[i] = m.z;
+}
+
+// self-test of div_tab against the IEEE division: x = a random double built from the counter, d = 1 .. tab_n-1
+__global__ void __launch_bounds__(256)
+k_selftest_div(const double *__restrict__ rcp, int tab_n, unsigned long long seed, long long n, unsigned long long *mismatch) {
+    unsigned long long bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint64_t h = azeval::mix64(seed + (uint64_t)i);
+        const uint32_t d = 1u + (uint32_t)((h >> 40) % (uint32_t)(tab_n - 1));
+        double x;
+        switch (h & 3u) {
+            case 0: x = __longlong_as_double((long long)((h >> 2) & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ll) * (double)(1u + (uint32_t)((h >> 54) & 255u)); break;  // [1,2) * small int
+            case 1: x = (double)(float)__longlong_as_double((long long)((azeval::mix64(h) >> 12) | 0x3FF0000000000000ll)) * (double)d; break;  // fp32 value times d
+            case 2: x = (double)(long long)(h >> 33) * (1.0 / 128.0); break;  // dyadic sums (hash evaluator values)
+            default: x = __longlong_as_double((long long)((azeval::mix64(h ^ 0x55ull) >> 12) | 0x3FE0000000000000ll)) * __dsqrt_rn((double)(1u + (uint32_t)((h >> 20) & 1023u))); break;  // prior * sqrt(N)
+        }
+        if ((h >> 63) & 1ull) x = -x;
+        if (div_tab(x, d, rcp) != __ddiv_rn(x, (double)d)) ++bad;
+    }
+    if (bad) atomicAdd(mismatch, bad);
+}
+
 __global__ void __launch_bounds__(256) k_sum_stats(const uint32_t *__restrict__ tstats, int E, unsigned long long *tot) {
     unsigned long long loc[NSTAT] = {0, 0, 0, 0, 0, 0, 0};
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < E; t += gridDim.x * blockDim.x)
@@ -691,6 +821,7 @@ struct az_engine {
     int G;
     int n_active;
     int step;
+    int sims_done;  // simulations run on the current roots (arena and tables are sized for num_simulations)
     uint64_t init0, init1;
     int initpl;
     bool have_init;
@@ -798,7 +929,10 @@ int32_t az_create(const az_config *cfg, az_engine **out) {
     const size_t nodes = (size_t)E * a.cap;
     int rc = AZ_OK;
 #define AL(ptr, count) if (rc == AZ_OK) rc = dev_alloc(h, &(ptr), (size_t)(count))
-    AL(a.W, nodes); AL(a.N, nodes); AL(a.P, nodes); AL(a.CB, nodes);
+    AL(a.W, nodes); AL(a.M, nodes);
+    double *d_rcp = nullptr, *d_sqt = nullptr;
+    a.tab_n = cfg->num_simulations + 8;
+    AL(d_rcp, a.tab_n); AL(d_sqt, a.tab_n);
     AL(a.root_bb0, E); AL(a.root_bb1, E); AL(a.root_player, E); AL(a.used, E); AL(a.tree_err, E);
     AL(a.leaf_node, E); AL(a.leaf_bb0, E); AL(a.leaf_bb1, E); AL(a.leaf_player, E); AL(a.leaf_status, E);
     AL(a.leaf_depth, E); AL(a.path, (size_t)E * PATH_STRIDE); AL(a.tstats, (size_t)E * NSTAT);
@@ -816,6 +950,10 @@ int32_t az_create(const az_config *cfg, az_engine **out) {
         free(h);
         return rc;
     }
+    a.rcp = d_rcp;
+    a.sqt = d_sqt;
+    k_init_tables<<<blocks_for(a.tab_n, 256), 256>>>(d_rcp, d_sqt, a.tab_n);
+    h->launches++;
     cudaMemset(a.tstats, 0, (size_t)E * NSTAT * sizeof(uint32_t));
     cudaMemset(a.ring, 0, 4 * sizeof(unsigned long long));
     cudaMemset(h->d_tot, 0, 8 * sizeof(unsigned long long));
@@ -920,6 +1058,7 @@ int32_t az_reset_games(az_engine *h, uint64_t init_bb0, uint64_t init_bb1, int32
     h->have_init = true;
     h->n_active = E;
     h->step = 0;
+    h->sims_done = 0;
     return AZ_OK;
 }
 
@@ -931,28 +1070,30 @@ int32_t az_set_roots(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, con
     k_set_roots<<<blocks_for(n, 256), 256, 0, S(stream)>>>(h->a, bb0, bb1, player, 0ull, 0ull, 0, n, 0);
     AZ_LAUNCH_CHECK(h, "k_set_roots");
     h->n_active = n;
+    h->sims_done = 0;
     return AZ_OK;
 }
 
 int32_t az_run_simulations(az_engine *h, int32_t num_sims, int32_t eval_kind, void *stream) {
     if (!h) return AZ_E_INVALID;
     if (num_sims < 0) return fail(h, AZ_E_INVALID, "%s", "az_run_simulations: num_sims < 0");
-    if (num_sims > h->cfg.num_simulations)
-        return fail(h, AZ_E_INVALID, "%s", "az_run_simulations: num_sims exceeds the arena (1 + 7*num_simulations nodes per tree)");
+    if (h->sims_done + num_sims > h->cfg.num_simulations)
+        return fail(h, AZ_E_INVALID, "%s", "az_run_simulations: more simulations on these roots than the arena holds (1 + 7*num_simulations nodes per tree)");
     if (eval_kind != AZ_EVAL_UNIFORM && eval_kind != AZ_EVAL_HASH) return fail(h, AZ_E_INVALID, "%s", "az_run_simulations: unknown evaluator");
     if (num_sims == 0) return AZ_OK;
     if (int rc = set_device(h)) return rc;
     const int n = h->n_active;
     const double c = h->cfg.c_puct;
     if (h->G == 32) {
-        const int blocks = blocks_for(n, 4);
-        if (eval_kind == AZ_EVAL_UNIFORM) k_run_sims<32, AZ_EVAL_UNIFORM><<<blocks, 128, 0, S(stream)>>>(h->a, n, num_sims, c);
-        else k_run_sims<32, AZ_EVAL_HASH><<<blocks, 128, 0, S(stream)>>>(h->a, n, num_sims, c);
+        const int blocks = blocks_for(n, 2);
+        if (eval_kind == AZ_EVAL_UNIFORM) k_run_sims<1, AZ_EVAL_UNIFORM><<<blocks, 64, 0, S(stream)>>>(h->a, n, num_sims, c);
+        else k_run_sims<1, AZ_EVAL_HASH><<<blocks, 64, 0, S(stream)>>>(h->a, n, num_sims, c);
     } else {
         const int blocks = blocks_for(n, 8);
-        if (eval_kind == AZ_EVAL_UNIFORM) k_run_sims<8, AZ_EVAL_UNIFORM><<<blocks, 64, 0, S(stream)>>>(h->a, n, num_sims, c);
-        else k_run_sims<8, AZ_EVAL_HASH><<<blocks, 64, 0, S(stream)>>>(h->a, n, num_sims, c);
+        if (eval_kind == AZ_EVAL_UNIFORM) k_run_sims<4, AZ_EVAL_UNIFORM><<<blocks, 64, 0, S(stream)>>>(h->a, n, num_sims, c);
+        else k_run_sims<4, AZ_EVAL_HASH><<<blocks, 64, 0, S(stream)>>>(h->a, n, num_sims, c);
     }
+    h->sims_done += num_sims;
     AZ_LAUNCH_CHECK(h, "k_run_sims");
     return AZ_OK;
 }
@@ -961,9 +1102,12 @@ int32_t az_select_leaves(az_engine *h, void *stream) {
     if (!h) return AZ_E_INVALID;
     if (int rc = set_device(h)) return rc;
     const int n = h->n_active;
-    if (h->G == 32) k_select<32><<<blocks_for(n, 4), 128, 0, S(stream)>>>(h->a, n, h->cfg.c_puct);
-    else k_select<8><<<blocks_for(n, 8), 64, 0, S(stream)>>>(h->a, n, h->cfg.c_puct);
+    if (h->sims_done + 1 > h->cfg.num_simulations)
+        return fail(h, AZ_E_INVALID, "%s", "az_select_leaves: more simulations on these roots than the arena holds");
+    if (h->G == 32) k_select<1><<<blocks_for(n, 2), 64, 0, S(stream)>>>(h->a, n, h->cfg.c_puct);
+    else k_select<4><<<blocks_for(n, 8), 64, 0, S(stream)>>>(h->a, n, h->cfg.c_puct);
     AZ_LAUNCH_CHECK(h, "k_select");
+    h->sims_done += 1;
     return AZ_OK;
 }
 
@@ -986,8 +1130,8 @@ int32_t az_expand_backup(az_engine *h, const float *policy, const float *values,
     if (policy_kind != AZ_POLICY_LOGITS && policy_kind != AZ_POLICY_PRIORS) return fail(h, AZ_E_INVALID, "%s", "az_expand_backup: bad policy_kind");
     if (int rc = set_device(h)) return rc;
     const int n = h->n_active;
-    if (h->G == 32) k_expand_backup<32><<<blocks_for(n, 4), 128, 0, S(stream)>>>(h->a, n, policy, values, policy_kind);
-    else k_expand_backup<8><<<blocks_for(n, 8), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind);
+    if (h->G == 32) k_expand_backup<1><<<blocks_for(n, 2), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind);
+    else k_expand_backup<4><<<blocks_for(n, 8), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind);
     AZ_LAUNCH_CHECK(h, "k_expand_backup");
     return AZ_OK;
 }
@@ -1018,11 +1162,8 @@ int32_t az_export_tree(az_engine *h, int32_t slot, double *W, uint32_t *N, float
     if (slot < 0 || slot >= h->a.E) return fail(h, AZ_E_INVALID, "%s", "az_export_tree: bad slot");
     if (int rc = set_device(h)) return rc;
     AZ_CUDA(h, cudaDeviceSynchronize());
-    const size_t base = (size_t)slot * h->a.cap, cap = (size_t)h->a.cap;
-    if (W) AZ_CUDA(h, cudaMemcpy(W, h->a.W + base, cap * sizeof(double), cudaMemcpyDeviceToDevice));
-    if (N) AZ_CUDA(h, cudaMemcpy(N, h->a.N + base, cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
-    if (P) AZ_CUDA(h, cudaMemcpy(P, h->a.P + base, cap * sizeof(float), cudaMemcpyDeviceToDevice));
-    if (first_child) AZ_CUDA(h, cudaMemcpy(first_child, h->a.CB + base, cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+    k_export_tree<<<blocks_for(h->a.cap, 256), 256>>>(h->a, slot, W, N, P, first_child);
+    AZ_LAUNCH_CHECK(h, "k_export_tree");
     if (used_host) {
         uint32_t u = 0;
         AZ_CUDA(h, cudaMemcpy(&u, h->a.used + slot, sizeof u, cudaMemcpyDeviceToHost));
@@ -1042,6 +1183,7 @@ int32_t az_sample_moves(az_engine *h, const double *uniforms, uint8_t *finished,
                                                              h->initpl);
     AZ_LAUNCH_CHECK(h, "k_sample_moves");
     h->step++;
+    h->sims_done = 0;
     return AZ_OK;
 }
 
@@ -1100,6 +1242,18 @@ int32_t az_get_stats(az_engine *h, az_stats *out, void *stream) {
     out->moves = r[4];
     out->episodes = r[5];
     out->children_scanned = r[6];
+    return AZ_OK;
+}
+
+int32_t az_selftest_division(az_engine *h, int64_t n, uint64_t seed, int64_t *mismatches_host) {
+    if (!h || !mismatches_host || n < 0) return AZ_E_INVALID;
+    if (int rc = set_device(h)) return rc;
+    AZ_CUDA(h, cudaMemset(h->d_tot, 0, 8 * sizeof(unsigned long long)));
+    k_selftest_div<<<148 * 8, 256>>>(h->a.rcp, h->a.tab_n - 6, seed, n, h->d_tot);
+    AZ_LAUNCH_CHECK(h, "k_selftest_div");
+    unsigned long long bad = 0;
+    AZ_CUDA(h, cudaMemcpy(&bad, h->d_tot, sizeof bad, cudaMemcpyDeviceToHost));
+    *mismatches_host = (int64_t)bad;
     return AZ_OK;
 }
 

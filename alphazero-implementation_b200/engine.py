@@ -262,6 +262,11 @@ class Engine:
         self._check(self.lib.az_get_stats(self.h, C.byref(st), _stream()), "az_get_stats")
         return {n: int(getattr(st, n)) for n, _ in AzStats._fields_}
 
+    def selftest_division(self, n: int = 1 << 26, seed: int = 1) -> int:
+        bad = C.c_int64(-1)
+        self._check(self.lib.az_selftest_division(self.h, int(n), int(seed), C.byref(bad)), "az_selftest_division")
+        return bad.value
+
     def reset_stats(self):
         self._check(self.lib.az_reset_stats(self.h, _stream()), "az_reset_stats")
 

@@ -184,6 +184,9 @@ int32_t az_drain_episodes(az_engine *h, int64_t ep_cap, int64_t s_cap, int32_t *
 /* ---- instrumentation ---- */
 int32_t az_get_stats(az_engine *h, az_stats *out_host, void *stream); /* synchronises */
 int32_t az_reset_stats(az_engine *h, void *stream);
+/* checks the table-based fp64 division used by the PUCT score against IEEE division on n pseudo-random
+ * (x, d) pairs, d an integer below num_simulations + 2; *mismatches_host must come back 0.  Synchronises. */
+int32_t az_selftest_division(az_engine *h, int64_t n, uint64_t seed, int64_t *mismatches_host);
 /* number of kernels this engine has launched since az_create */
 int64_t az_launch_count(const az_engine *h);
 

@@ -138,3 +138,24 @@ def test_gather_leaves_layouts(oracle):
     assert (eng.gather_leaves(LAYOUT_PLANES_BF16).float().cpu().numpy() == planes).all()
     assert live.sum() > 0
     eng.close()
+
+
+@pytest.mark.parametrize("S", [200, 800, 20000])
+def test_table_division_is_correctly_rounded(S):
+    """PUCT divides by small integers through a reciprocal table + two FMA corrections; the result must equal
+    the IEEE quotient (what CPython computes) for every (x, d): 2^28 pseudo-random pairs per table size."""
+    eng = Engine(num_games=8, num_simulations=S)
+    assert eng.selftest_division(1 << 28, seed=S) == 0
+    eng.close()
+
+
+def test_simulation_budget_is_enforced():
+    eng = Engine(num_games=4, num_simulations=50)
+    eng.run_simulations(30, 1)
+    eng.run_simulations(20, 1)  # continuing the same roots is fine up to the arena size
+    with pytest.raises(RuntimeError):
+        eng.run_simulations(1, 1)
+    assert eng.root_stats()["root_N"].cpu().tolist() == [50] * 4
+    eng.reset_games()
+    eng.run_simulations(50, 2)
+    eng.close()
