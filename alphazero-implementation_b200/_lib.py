@@ -59,7 +59,7 @@ def library_available() -> bool:
 class AzConfig(C.Structure):
     _fields_ = [
         ("height", C.c_int32), ("width", C.c_int32), ("count", C.c_int32), ("num_games", C.c_int32),
-        ("num_simulations", C.c_int32), ("device", C.c_int32), ("lanes_per_tree", C.c_int32), ("reserved", C.c_int32),
+        ("num_simulations", C.c_int32), ("device", C.c_int32), ("lanes_per_tree", C.c_int32), ("hot_nodes_plus1", C.c_int32),
         ("c_puct", C.c_double),
     ]
 

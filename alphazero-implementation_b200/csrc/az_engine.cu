@@ -115,23 +115,59 @@ struct Child {  // the record of "my" column's child at the current node
     float p;
 };
 
-__device__ __forceinline__ Child load_child(const double *__restrict__ Wt, const uint4 *__restrict__ Mt, uint32_t idx) {
+// One tree's node storage as seen by a kernel: nodes [0, K) may live in shared memory for the duration
+// of a launch (the fused kernel keeps the first, hottest nodes of every tree there: node indices grow
+// in creation order, so the shallow levels every simulation walks through have the smallest indices);
+// nodes >= K are in the HBM arena.  K == 0: everything in HBM.
+struct TreeMem {
+    double *gW;
+    uint4 *gM;
+    double *sW;
+    uint4 *sM;
+    uint32_t K;
+};
+
+__device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx) {
     Child ch;
-    const uint4 m = Mt[idx];
-    ch.w = Wt[idx];
+    uint4 m;
+    if (idx < tm.K) {
+        m = tm.sM[idx];
+        ch.w = tm.sW[idx];
+    } else {
+        m = tm.gM[idx];
+        ch.w = tm.gW[idx];
+    }
     ch.n = m.x;
     ch.p = __uint_as_float(m.y);
     ch.cb = m.z;
     return ch;
 }
 
-__device__ __forceinline__ void store_new_child(double *Wt, uint4 *Mt, uint32_t idx, float prior) {
-    Wt[idx] = 0.0;
-    Mt[idx] = make_uint4(0u, __float_as_uint(prior), 0u, 0u);
+__device__ __forceinline__ void store_new_child(const TreeMem &tm, uint32_t idx, float prior) {
+    const uint4 m = make_uint4(0u, __float_as_uint(prior), 0u, 0u);
+    if (idx < tm.K) {
+        tm.sW[idx] = 0.0;
+        tm.sM[idx] = m;
+    } else {
+        tm.gW[idx] = 0.0;
+        tm.gM[idx] = m;
+    }
 }
 
-__device__ __forceinline__ uint32_t *node_N(uint4 *Mt, uint32_t idx) { return reinterpret_cast<uint32_t *>(Mt + idx); }
-__device__ __forceinline__ uint32_t *node_CB(uint4 *Mt, uint32_t idx) { return reinterpret_cast<uint32_t *>(Mt + idx) + 2; }
+__device__ __forceinline__ void set_first_child(const TreeMem &tm, uint32_t idx, uint32_t first) {
+    uint4 *p = (idx < tm.K) ? (tm.sM + idx) : (tm.gM + idx);
+    reinterpret_cast<uint32_t *>(p)[2] = first;
+}
+
+__device__ __forceinline__ void visit_node(const TreeMem &tm, uint32_t idx, double dv) {
+    if (idx < tm.K) {
+        tm.sW[idx] = __dadd_rn(tm.sW[idx], dv);
+        reinterpret_cast<uint32_t *>(tm.sM + idx)[0] += 1u;
+    } else {
+        tm.gW[idx] = __dadd_rn(tm.gW[idx], dv);
+        reinterpret_cast<uint32_t *>(tm.gM + idx)[0] += 1u;
+    }
+}
 
 struct Leaf {
     uint64_t b0, b1;
@@ -148,8 +184,7 @@ struct Leaf {
 // (cb, n_parent) describe the root and (root_legal, ch) hold the root's legal mask and this lane's
 // root child record (valid when alive && cb != 0) — the fused kernel keeps them in registers across
 // simulations.  `path[d]` receives the node index at depth d (written by lane 0 of the tree's lanes).
-__device__ __forceinline__ Leaf descend(const double *__restrict__ Wt, const uint4 *__restrict__ Mt,
-                                        const double *__restrict__ rcp, const double *__restrict__ sqt,
+__device__ __forceinline__ Leaf descend(const TreeMem &tm, const double *__restrict__ rcp, const double *__restrict__ sqt,
                                         uint64_t rb0, uint64_t rb1, int rpl, double c_puct, uint32_t cb,
                                         uint32_t n_parent, unsigned legal, Child ch, bool alive, bool writer,
                                         uint32_t *path, uint32_t &levels, uint32_t &scanned) {
@@ -193,7 +228,7 @@ __device__ __forceinline__ Leaf descend(const double *__restrict__ Wt, const uin
         if (go) {
             legal = lg;
             my_legal = can;
-            if (can) ch = load_child(Wt, Mt, cb + __popc(lg & ((1u << c) - 1u)));
+            if (can) ch = load_child(tm, cb + __popc(lg & ((1u << c) - 1u)));
         }
     }
     // Node.is_terminal of the leaf (node.py:61-63).  Interior nodes are never terminal (a terminal
@@ -210,14 +245,12 @@ __device__ __forceinline__ Leaf descend(const double *__restrict__ Wt, const uin
 // AlphaZeroSearch.backpropagate (search.py:48-57) along the recorded path: the leaf gets +v, the sign
 // flips going up except across a terminal leaf.  Stops at the current root (older ancestors are never
 // read again).  `lit` = lane index within the tree's lanes, `nl` = lanes per tree.
-__device__ __forceinline__ void backup(double *Wt, uint4 *Mt, const uint32_t *path, int depth, double v,
-                                       bool leaf_terminal, int lit, int nl, int first) {
-    for (int i = first + lit; i <= depth; i += nl) {
-        const uint32_t nd = path[i];
+__device__ __forceinline__ void backup(const TreeMem &tm, const uint32_t *path, int depth, double v, bool leaf_terminal,
+                                       int lit, int nl) {
+    for (int i = lit; i <= depth; i += nl) {
         const int d = depth - i;
         const bool neg = leaf_terminal ? (d >= 1 && ((d - 1) & 1)) : (d & 1);
-        Wt[nd] = __dadd_rn(Wt[nd], neg ? -v : v);
-        *node_N(Mt, nd) += 1u;
+        visit_node(tm, path[i], neg ? -v : v);
     }
 }
 
@@ -230,12 +263,13 @@ __device__ __forceinline__ double backup_sign(double v, int depth, int i, bool l
 // ------------------------------------------------------------------------------------------------
 // fused search: all S simulations of a tree in one launch, built-in evaluator.
 // The root's scalars (N, first child, legal mask) and each lane's root-child record live in registers
-// for the whole launch; memory is kept in step so that every other kernel sees a complete tree.
+// for the whole launch, the first K nodes of every tree in shared memory (loaded at entry, written back
+// at exit), the rest in HBM.  Dynamic shared memory: [TREES][K] uint4, [TREES][K] f64, [TREES][44] u32.
 template <int TPW, int EVAL>
-__global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, double c_puct) {
+__global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, double c_puct, int K) {
     constexpr int TREES = 2 * TPW;  // per 64-thread block
     constexpr int NL = 32 / TPW;    // lanes per tree
-    __shared__ uint32_t s_path[TREES][PATH_STRIDE];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int sub = lane & 24;
@@ -251,28 +285,42 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     const bool first_q = lit < 8;
 
     const size_t base = (size_t)tt * a.cap;
-    double *Wt = a.W + base;
-    uint4 *Mt = a.M + base;
-    uint32_t *path = s_path[tib];
+    TreeMem tm;
+    tm.gW = a.W + base;
+    tm.gM = a.M + base;
+    tm.sM = reinterpret_cast<uint4 *>(smem_raw) + (size_t)tib * K;
+    tm.sW = reinterpret_cast<double *>(smem_raw + (size_t)TREES * K * sizeof(uint4)) + (size_t)tib * K;
+    tm.K = (uint32_t)K;
+    uint32_t *path = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TREES * K * (sizeof(uint4) + sizeof(double))) + tib * PATH_STRIDE;
     const uint64_t rb0 = a.root_bb0[tt], rb1 = a.root_bb1[tt];
     const int rpl = a.root_player[tt];
     uint32_t used = a.used[tt];
     uint32_t levels = 0, evals = 0, children = 0, scanned = 0;
 
+    // hot prefix of the tree -> shared memory
+    if (alive) {
+        const uint32_t hot = used < tm.K ? used : tm.K;
+        for (uint32_t i = lit; i < hot; i += NL) {
+            tm.sM[i] = tm.gM[i];
+            tm.sW[i] = tm.gW[i];
+        }
+    }
+    __syncwarp();
+
     // root registers
-    const uint4 rm = Mt[0];
+    const uint4 rm = (K > 0) ? tm.sM[0] : tm.gM[0];
     uint32_t root_n = rm.x, root_cb = rm.z;
     const bool r_can = (c < c4::W) && !(((rb0 | rb1) >> (c4::STRIDE * c + 5)) & 1ull);
     const unsigned r_legal = (__ballot_sync(FULL, r_can) >> sub) & 0x7Fu;
     const int r_j = __popc(r_legal & ((1u << c) - 1u));
     Child rch;
     rch.w = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
-    if (alive && root_cb != 0 && r_can) rch = load_child(Wt, Mt, root_cb + r_j);
+    if (alive && root_cb != 0 && r_can) rch = load_child(tm, root_cb + r_j);
     if (writer) path[0] = 0;
 
     for (int s = 0; s < S; ++s) {
-        Leaf L = descend(Wt, Mt, a.rcp, a.sqt, rb0, rb1, rpl, c_puct, root_cb, root_n, r_legal, rch, alive, writer, path,
-                         levels, scanned);
+        Leaf L = descend(tm, a.rcp, a.sqt, rb0, rb1, rpl, c_puct, root_cb, root_n, r_legal, rch, alive, writer, path, levels,
+                         scanned);
         // leaf: evaluate + expand, or terminal value
         const uint64_t occ = L.b0 | L.b1;
         const bool can = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);
@@ -286,7 +334,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
             const int j = __popc(legal & ((1u << c) - 1u));
             float prior, val;
             if (EVAL == AZ_EVAL_UNIFORM) {
-                prior = __fdiv_rn(1.0f, (float)k);
+                prior = __frcp_rn((float)k);  // == fp32(1)/fp32(k): both are the correctly rounded reciprocal
                 val = 0.0f;
             } else {
                 const uint64_t h = azeval::board_hash(L.b0, L.b1, L.pl);
@@ -295,8 +343,8 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
                 val = L.pl == 0 ? v0 : -v0;
             }
             if (alive) {
-                if (can && first_q) store_new_child(Wt, Mt, used + j, prior);
-                if (writer) *node_CB(Mt, L.node) = used;
+                if (can && first_q) store_new_child(tm, used + j, prior);
+                if (writer) set_first_child(tm, L.node, used);
                 if (L.depth == 0) {  // the root itself was expanded: its children enter the registers
                     root_cb = used;
                     rch.w = 0.0; rch.n = 0; rch.cb = 0; rch.p = prior;
@@ -317,9 +365,17 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
                 rch.n += 1u;
                 rch.w = __dadd_rn(rch.w, backup_sign(v, L.depth, 1, L.term));
             }
-            backup(Wt, Mt, path, L.depth, v, L.term, lit, NL, 0);
+            backup(tm, path, L.depth, v, L.term, lit, NL);
         }
         __syncwarp();
+    }
+    // hot prefix back to the arena
+    if (alive) {
+        const uint32_t hot = used < tm.K ? used : tm.K;
+        for (uint32_t i = lit; i < hot; i += NL) {
+            tm.gM[i] = tm.sM[i];
+            tm.gW[i] = tm.sW[i];
+        }
     }
     if (writer) {
         a.used[t] = used;
@@ -352,20 +408,24 @@ __global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_p
     const int tt = alive ? t : 0;
     const bool writer = alive && lit == 0;
     const size_t base = (size_t)tt * a.cap;
-    double *Wt = a.W + base;
-    uint4 *Mt = a.M + base;
+    TreeMem tm;
+    tm.gW = a.W + base;
+    tm.gM = a.M + base;
+    tm.sW = nullptr;
+    tm.sM = nullptr;
+    tm.K = 0;
     uint32_t *path = a.path + (size_t)tt * PATH_STRIDE;
     const uint64_t rb0 = a.root_bb0[tt], rb1 = a.root_bb1[tt];
-    const uint4 rm = Mt[0];
+    const uint4 rm = tm.gM[0];
     const bool r_can = (c < c4::W) && !(((rb0 | rb1) >> (c4::STRIDE * c + 5)) & 1ull);
     const unsigned r_legal = (__ballot_sync(FULL, r_can) >> sub) & 0x7Fu;
     Child rch;
     rch.w = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
-    if (alive && rm.z != 0 && r_can) rch = load_child(Wt, Mt, rm.z + __popc(r_legal & ((1u << c) - 1u)));
+    if (alive && rm.z != 0 && r_can) rch = load_child(tm, rm.z + __popc(r_legal & ((1u << c) - 1u)));
     if (writer) path[0] = 0;
     uint32_t levels = 0, scanned = 0;
-    Leaf L = descend(Wt, Mt, a.rcp, a.sqt, rb0, rb1, a.root_player[tt], c_puct, rm.z, rm.x, r_legal, rch, alive, writer, path,
-                     levels, scanned);
+    Leaf L = descend(tm, a.rcp, a.sqt, rb0, rb1, a.root_player[tt], c_puct, rm.z, rm.x, r_legal, rch, alive, writer, path, levels,
+                     scanned);
     if (writer) {
         a.leaf_node[t] = L.node;
         a.leaf_bb0[t] = L.b0;
@@ -379,7 +439,7 @@ __global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_p
         st[6] += scanned;
     }
     __syncwarp();
-    if (alive && L.term) backup(Wt, Mt, path, L.depth, L.win ? 1.0 : 0.0, true, lit, NL, 0);
+    if (alive && L.term) backup(tm, path, L.depth, L.win ? 1.0 : 0.0, true, lit, NL);
 }
 
 // split path, step 3: search.py:87-91 with the evaluator's outputs
@@ -402,8 +462,12 @@ k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const f
     const bool writer = alive && lit == 0;
     const bool first_q = lit < 8;
     const size_t base = (size_t)tt * a.cap;
-    double *Wt = a.W + base;
-    uint4 *Mt = a.M + base;
+    TreeMem tm;
+    tm.gW = a.W + base;
+    tm.gM = a.M + base;
+    tm.sW = nullptr;
+    tm.sM = nullptr;
+    tm.K = 0;
     const uint64_t occ = a.leaf_bb0[tt] | a.leaf_bb1[tt];
     const int pl = a.leaf_player[tt];
     const uint32_t node = a.leaf_node[tt];
@@ -430,17 +494,17 @@ k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const f
     }
     __syncwarp();  // every lane has read used / leaf_* before the writer updates them
     if (alive) {
-        if (can && first_q) store_new_child(Wt, Mt, used + j, prior);
+        if (can && first_q) store_new_child(tm, used + j, prior);
         const double v = (double)values[(size_t)tt * 2 + pl];
         if (writer) {
-            *node_CB(Mt, node) = used;
+            set_first_child(tm, node, used);
             a.used[t] = used + k;
             a.leaf_status[t] = AZ_LEAF_IDLE;  // consumed: a second az_expand_backup without a select is a no-op
             uint32_t *st = a.tstats + (size_t)t * NSTAT;
             st[1] += 1u;
             st[3] += (uint32_t)k;
         }
-        backup(Wt, Mt, a.path + (size_t)tt * PATH_STRIDE, depth, v, false, lit, NL, 0);
+        backup(tm, a.path + (size_t)tt * PATH_STRIDE, depth, v, false, lit, NL);
     }
 }
 
@@ -821,6 +885,9 @@ struct az_engine {
     int G;
     int n_active;
     int step;
+    int num_sms;
+    int force_hot_nodes;  // -1 = automatic
+    int last_hot_nodes;
     int sims_done;  // simulations run on the current roots (arena and tables are sized for num_simulations)
     uint64_t init0, init1;
     int initpl;
@@ -915,6 +982,8 @@ int32_t az_create(const az_config *cfg, az_engine **out) {
     h->cfg = *cfg;
     h->G = G;
     h->n_active = cfg->num_games;
+    h->num_sms = prop.multiProcessorCount;
+    h->force_hot_nodes = cfg->hot_nodes_plus1 > 0 ? cfg->hot_nodes_plus1 - 1 : -1;
     e = cudaSetDevice(cfg->device);
     if (e != cudaSuccess) {
         free(h);
@@ -1084,15 +1153,30 @@ int32_t az_run_simulations(az_engine *h, int32_t num_sims, int32_t eval_kind, vo
     if (int rc = set_device(h)) return rc;
     const int n = h->n_active;
     const double c = h->cfg.c_puct;
-    if (h->G == 32) {
-        const int blocks = blocks_for(n, 2);
-        if (eval_kind == AZ_EVAL_UNIFORM) k_run_sims<1, AZ_EVAL_UNIFORM><<<blocks, 64, 0, S(stream)>>>(h->a, n, num_sims, c);
-        else k_run_sims<1, AZ_EVAL_HASH><<<blocks, 64, 0, S(stream)>>>(h->a, n, num_sims, c);
-    } else {
-        const int blocks = blocks_for(n, 8);
-        if (eval_kind == AZ_EVAL_UNIFORM) k_run_sims<4, AZ_EVAL_UNIFORM><<<blocks, 64, 0, S(stream)>>>(h->a, n, num_sims, c);
-        else k_run_sims<4, AZ_EVAL_HASH><<<blocks, 64, 0, S(stream)>>>(h->a, n, num_sims, c);
+    // hot-node count K: as many as shared memory allows while every block of the grid stays resident
+    const int tpw = (h->G == 32) ? 1 : 4, trees_per_block = 2 * tpw;
+    const int blocks = blocks_for(n, trees_per_block);
+    int per_sm = (blocks + h->num_sms - 1) / h->num_sms;
+    if (per_sm > 14) per_sm = 14;  // register-limited residency of 64-thread blocks (72 registers)
+    int K = 0;
+    for (int cand = 512; cand >= 16; cand >>= 1) {
+        const size_t bytes = (size_t)trees_per_block * ((size_t)cand * 24 + PATH_STRIDE * 4);
+        if (cand <= h->a.cap && bytes <= 200u * 1024u && bytes * per_sm <= 200u * 1024u) { K = cand; break; }
     }
+    if (h->force_hot_nodes >= 0) K = (h->force_hot_nodes < h->a.cap ? h->force_hot_nodes : h->a.cap) & ~7;
+    const size_t smem = (size_t)trees_per_block * ((size_t)K * 24 + PATH_STRIDE * 4);
+#define AZ_RUN(TPW_, EV_)                                                                                                \
+    do {                                                                                                                 \
+        AZ_CUDA(h, cudaFuncSetAttribute(k_run_sims<TPW_, EV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_run_sims<TPW_, EV_><<<blocks, 64, smem, S(stream)>>>(h->a, n, num_sims, c, K);                                 \
+    } while (0)
+    if (tpw == 1) {
+        if (eval_kind == AZ_EVAL_UNIFORM) AZ_RUN(1, AZ_EVAL_UNIFORM); else AZ_RUN(1, AZ_EVAL_HASH);
+    } else {
+        if (eval_kind == AZ_EVAL_UNIFORM) AZ_RUN(4, AZ_EVAL_UNIFORM); else AZ_RUN(4, AZ_EVAL_HASH);
+    }
+#undef AZ_RUN
+    h->last_hot_nodes = K;
     h->sims_done += num_sims;
     AZ_LAUNCH_CHECK(h, "k_run_sims");
     return AZ_OK;

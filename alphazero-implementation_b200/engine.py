@@ -74,7 +74,7 @@ class Engine:
     """E game slots, each with a tree arena sized for S simulations per move."""
 
     def __init__(self, num_games: int, num_simulations: int, c_puct: float = 1.0, device: int | None = None,
-                 lanes_per_tree: int = 0):
+                 lanes_per_tree: int = 0, hot_nodes: int | None = None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("alphazero_implementation_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
@@ -83,7 +83,8 @@ class Engine:
         self.num_games = int(num_games)
         self.num_simulations = int(num_simulations)
         self.c_puct = float(c_puct)
-        cfg = AzConfig(6, 7, 4, self.num_games, self.num_simulations, self.device_index, int(lanes_per_tree), 0, self.c_puct)
+        cfg = AzConfig(6, 7, 4, self.num_games, self.num_simulations, self.device_index, int(lanes_per_tree),
+                       0 if hot_nodes is None else int(hot_nodes) + 1, self.c_puct)
         h = C.c_void_p()
         rc = self.lib.az_create(C.byref(cfg), C.byref(h))
         if rc != 0:

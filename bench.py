@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--sims", type=int, default=200)
     ap.add_argument("--evaluator", default="uniform", choices=["uniform", "hash"])
     ap.add_argument("--lanes", type=int, default=0, help="lanes per tree: 8, 32 or 0 = engine default")
+    ap.add_argument("--hot-nodes", type=int, default=None, help="nodes per tree kept in shared memory by the fused kernel (default: automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--net", default="resnet4x64", help="network-in-the-loop side measurement: resnetBxC | basic | none")
@@ -229,7 +230,7 @@ def run_b200(args):
     kind = EVAL_UNIFORM if args.evaluator == "uniform" else EVAL_HASH
     peaks = load_peaks()
 
-    eng = az.Engine(num_games=E, num_simulations=S, device=local, lanes_per_tree=args.lanes)
+    eng = az.Engine(num_games=E, num_simulations=S, device=local, lanes_per_tree=args.lanes, hot_nodes=args.hot_nodes)
     eng.reset_games()
     rng = np.random.RandomState(1000 + rank)
     u_all = torch.from_numpy(rng.random_sample((W + K, E))).to(eng.device)  # inputs resident in HBM
