@@ -96,6 +96,9 @@ SIGNATURES = {
     "az_sample_moves": (I32, [P, P, P, P]),
     "az_episode_counts": (I32, [P, C.POINTER(I64), C.POINTER(I64), P]),
     "az_drain_episodes": (I32, [P, I64, I64, P, P, P, P, P, P, P, P, P, C.POINTER(I64), C.POINTER(I64), P]),
+    "az_swap_episode_ring": (I32, [P, C.POINTER(I32), P]),
+    "az_ring_counts": (I32, [P, I32, C.POINTER(I64), C.POINTER(I64), P]),
+    "az_read_episode_ring": (I32, [P, I32, I64, I64, P, P, P, P, P, P, P, P, P, P]),
     "az_get_stats": (I32, [P, C.POINTER(AzStats), P]),
     "az_reset_stats": (I32, [P, P]),
     "az_selftest_division": (I32, [P, I64, C.c_uint64, C.POINTER(I64)]),

@@ -879,9 +879,21 @@ char g_create_error[512] = "";
 }  // namespace
 
 // ==================================================================================================
+struct RingPtrs {
+    unsigned long long *ring;
+    int32_t *ep_slot, *ep_step, *ep_len;
+    int64_t *ep_offset;
+    int8_t *ep_outcome;
+    uint64_t *s_bb0, *s_bb1;
+    uint8_t *s_player;
+    int32_t *s_counts;
+};
+
 struct az_engine {
     az_config cfg;
     Arena a;
+    RingPtrs rings[2];
+    int active_ring;
     int G;
     int n_active;
     int step;
@@ -896,7 +908,7 @@ struct az_engine {
     int64_t launches;
     unsigned long long *d_tot;   // [8] stats totals (device)
     unsigned long long acc_tot[NSTAT];  // totals folded on the host across resets
-    void *allocs[64];
+    void *allocs[96];
     int n_allocs;
     char err[512];
 };
@@ -931,11 +943,19 @@ int dev_alloc(az_engine *h, T **p, size_t count) {
         cudaGetLastError();
         return fail(h, AZ_E_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
     }
-    if (h->n_allocs >= 64) return fail(h, AZ_E_INVALID, "%s", "allocation table full");
+    if (h->n_allocs >= 96) return fail(h, AZ_E_INVALID, "%s", "allocation table full");
     h->allocs[h->n_allocs++] = q;
     h->bytes += (int64_t)bytes;
     *p = (T *)q;
     return AZ_OK;
+}
+
+void use_ring(az_engine *h, int r) {
+    const RingPtrs &g = h->rings[r];
+    Arena &a = h->a;
+    a.ring = g.ring; a.ep_slot = g.ep_slot; a.ep_step = g.ep_step; a.ep_len = g.ep_len; a.ep_offset = g.ep_offset;
+    a.ep_outcome = g.ep_outcome; a.s_bb0 = g.s_bb0; a.s_bb1 = g.s_bb1; a.s_player = g.s_player; a.s_counts = g.s_counts;
+    h->active_ring = r;
 }
 
 inline cudaStream_t S(void *s) { return (cudaStream_t)s; }
@@ -1007,10 +1027,13 @@ int32_t az_create(const az_config *cfg, az_engine **out) {
     AL(a.leaf_depth, E); AL(a.path, (size_t)E * PATH_STRIDE); AL(a.tstats, (size_t)E * NSTAT);
     AL(a.g_bb0, (size_t)E * MAX_PLIES); AL(a.g_bb1, (size_t)E * MAX_PLIES); AL(a.g_player, (size_t)E * MAX_PLIES);
     AL(a.g_counts, (size_t)E * MAX_PLIES * 7); AL(a.g_len, E);
-    AL(a.ring, 4);
-    AL(a.ep_slot, a.ep_cap); AL(a.ep_step, a.ep_cap); AL(a.ep_len, a.ep_cap); AL(a.ep_offset, a.ep_cap);
-    AL(a.ep_outcome, a.ep_cap * 2);
-    AL(a.s_bb0, a.s_cap); AL(a.s_bb1, a.s_cap); AL(a.s_player, a.s_cap); AL(a.s_counts, a.s_cap * 7);
+    for (int r = 0; r < 2; ++r) {
+        RingPtrs &g = h->rings[r];
+        AL(g.ring, 4);
+        AL(g.ep_slot, a.ep_cap); AL(g.ep_step, a.ep_cap); AL(g.ep_len, a.ep_cap); AL(g.ep_offset, a.ep_cap);
+        AL(g.ep_outcome, a.ep_cap * 2);
+        AL(g.s_bb0, a.s_cap); AL(g.s_bb1, a.s_cap); AL(g.s_player, a.s_cap); AL(g.s_counts, a.s_cap * 7);
+    }
     AL(h->d_tot, 8);
 #undef AL
     if (rc != AZ_OK) {
@@ -1024,7 +1047,9 @@ int32_t az_create(const az_config *cfg, az_engine **out) {
     k_init_tables<<<blocks_for(a.tab_n, 256), 256>>>(d_rcp, d_sqt, a.tab_n);
     h->launches++;
     cudaMemset(a.tstats, 0, (size_t)E * NSTAT * sizeof(uint32_t));
-    cudaMemset(a.ring, 0, 4 * sizeof(unsigned long long));
+    cudaMemset(h->rings[0].ring, 0, 4 * sizeof(unsigned long long));
+    cudaMemset(h->rings[1].ring, 0, 4 * sizeof(unsigned long long));
+    use_ring(h, 0);
     cudaMemset(h->d_tot, 0, 8 * sizeof(unsigned long long));
     cudaMemset(a.g_len, 0, (size_t)E * sizeof(int32_t));
     // every slot starts at the empty board, player 0 (Config.sample_initial_state())
@@ -1120,7 +1145,8 @@ int32_t az_reset_games(az_engine *h, uint64_t init_bb0, uint64_t init_bb1, int32
     k_set_roots<<<blocks_for(E, 256), 256, 0, S(stream)>>>(h->a, nullptr, nullptr, nullptr, init_bb0, init_bb1, init_player,
                                                           E, 1);
     AZ_LAUNCH_CHECK(h, "k_set_roots");
-    AZ_CUDA(h, cudaMemsetAsync(h->a.ring, 0, 4 * sizeof(unsigned long long), S(stream)));
+    AZ_CUDA(h, cudaMemsetAsync(h->rings[0].ring, 0, 4 * sizeof(unsigned long long), S(stream)));
+    AZ_CUDA(h, cudaMemsetAsync(h->rings[1].ring, 0, 4 * sizeof(unsigned long long), S(stream)));
     h->init0 = init_bb0;
     h->init1 = init_bb1;
     h->initpl = init_player;
@@ -1271,16 +1297,34 @@ int32_t az_sample_moves(az_engine *h, const double *uniforms, uint8_t *finished,
     return AZ_OK;
 }
 
+static int ring_counts(az_engine *h, int ring, int64_t *ne, int64_t *ns, cudaStream_t st) {
+    unsigned long long r[4];
+    AZ_CUDA(h, cudaMemcpyAsync(r, h->rings[ring].ring, sizeof r, cudaMemcpyDeviceToHost, st));
+    AZ_CUDA(h, cudaStreamSynchronize(st));
+    if (ne) *ne = (int64_t)r[0];
+    if (ns) *ns = (int64_t)r[1];
+    if (r[2]) return fail(h, AZ_E_OVERFLOW, "%s", "episode ring overflowed: drain more often (capacity 2*num_games + 64 episodes)");
+    return AZ_OK;
+}
+
+static int ring_read(az_engine *h, int ring, int64_t ne, int64_t ns, int32_t *ep_slot, int32_t *ep_step, int32_t *ep_len,
+                     int64_t *ep_offset, int8_t *ep_outcome, uint64_t *s_bb0, uint64_t *s_bb1, uint8_t *s_player,
+                     int32_t *s_counts, cudaStream_t st) {
+    const RingPtrs &g = h->rings[ring];
+    // destinations may be device memory or pinned host memory
+#define CP(dst, src, count, T) if ((dst) && (count) > 0) AZ_CUDA(h, cudaMemcpyAsync((dst), (src), (size_t)(count) * sizeof(T), cudaMemcpyDefault, st))
+    CP(ep_slot, g.ep_slot, ne, int32_t); CP(ep_step, g.ep_step, ne, int32_t); CP(ep_len, g.ep_len, ne, int32_t);
+    CP(ep_offset, g.ep_offset, ne, int64_t); CP(ep_outcome, g.ep_outcome, ne * 2, int8_t);
+    CP(s_bb0, g.s_bb0, ns, uint64_t); CP(s_bb1, g.s_bb1, ns, uint64_t); CP(s_player, g.s_player, ns, uint8_t);
+    CP(s_counts, g.s_counts, ns * 7, int32_t);
+#undef CP
+    return AZ_OK;
+}
+
 int32_t az_episode_counts(az_engine *h, int64_t *n_episodes_host, int64_t *n_samples_host, void *stream) {
     if (!h) return AZ_E_INVALID;
     if (int rc = set_device(h)) return rc;
-    unsigned long long r[4];
-    AZ_CUDA(h, cudaMemcpyAsync(r, h->a.ring, sizeof r, cudaMemcpyDeviceToHost, S(stream)));
-    AZ_CUDA(h, cudaStreamSynchronize(S(stream)));
-    if (n_episodes_host) *n_episodes_host = (int64_t)r[0];
-    if (n_samples_host) *n_samples_host = (int64_t)r[1];
-    if (r[2]) return fail(h, AZ_E_OVERFLOW, "%s", "episode ring overflowed: drain more often (capacity 2*num_games + 64 episodes)");
-    return AZ_OK;
+    return ring_counts(h, h->active_ring, n_episodes_host, n_samples_host, S(stream));
 }
 
 int32_t az_drain_episodes(az_engine *h, int64_t ep_cap, int64_t s_cap, int32_t *ep_slot, int32_t *ep_step,
@@ -1288,23 +1332,45 @@ int32_t az_drain_episodes(az_engine *h, int64_t ep_cap, int64_t s_cap, int32_t *
                           uint8_t *s_player, int32_t *s_counts, int64_t *n_episodes_host, int64_t *n_samples_host,
                           void *stream) {
     if (!h) return AZ_E_INVALID;
+    if (int rc = set_device(h)) return rc;
     int64_t ne = 0, ns = 0;
-    int rc = az_episode_counts(h, &ne, &ns, stream);
+    cudaStream_t st = S(stream);
+    int rc = ring_counts(h, h->active_ring, &ne, &ns, st);
     if (rc != AZ_OK) return rc;
     if (ne > ep_cap || ns > s_cap) return fail(h, AZ_E_OVERFLOW, "%s", "az_drain_episodes: caller buffers too small");
-    cudaStream_t st = S(stream);
-    const Arena &a = h->a;
-#define CP(dst, src, count, T) if ((dst) && (count) > 0) AZ_CUDA(h, cudaMemcpyAsync((dst), (src), (size_t)(count) * sizeof(T), cudaMemcpyDeviceToDevice, st))
-    CP(ep_slot, a.ep_slot, ne, int32_t); CP(ep_step, a.ep_step, ne, int32_t); CP(ep_len, a.ep_len, ne, int32_t);
-    CP(ep_offset, a.ep_offset, ne, int64_t); CP(ep_outcome, a.ep_outcome, ne * 2, int8_t);
-    CP(s_bb0, a.s_bb0, ns, uint64_t); CP(s_bb1, a.s_bb1, ns, uint64_t); CP(s_player, a.s_player, ns, uint8_t);
-    CP(s_counts, a.s_counts, ns * 7, int32_t);
-#undef CP
-    AZ_CUDA(h, cudaMemsetAsync(a.ring, 0, 4 * sizeof(unsigned long long), st));
+    rc = ring_read(h, h->active_ring, ne, ns, ep_slot, ep_step, ep_len, ep_offset, ep_outcome, s_bb0, s_bb1, s_player, s_counts, st);
+    if (rc != AZ_OK) return rc;
+    AZ_CUDA(h, cudaMemsetAsync(h->rings[h->active_ring].ring, 0, 4 * sizeof(unsigned long long), st));
     AZ_CUDA(h, cudaStreamSynchronize(st));
     if (n_episodes_host) *n_episodes_host = ne;
     if (n_samples_host) *n_samples_host = ns;
     return AZ_OK;
+}
+
+int32_t az_swap_episode_ring(az_engine *h, int32_t *previous_ring_host, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (int rc = set_device(h)) return rc;
+    const int prev = h->active_ring, next = prev ^ 1;
+    AZ_CUDA(h, cudaMemsetAsync(h->rings[next].ring, 0, 4 * sizeof(unsigned long long), S(stream)));
+    use_ring(h, next);
+    if (previous_ring_host) *previous_ring_host = prev;
+    return AZ_OK;
+}
+
+int32_t az_ring_counts(az_engine *h, int32_t ring, int64_t *n_episodes_host, int64_t *n_samples_host, void *stream) {
+    if (!h || ring < 0 || ring > 1) return AZ_E_INVALID;
+    if (int rc = set_device(h)) return rc;
+    return ring_counts(h, ring, n_episodes_host, n_samples_host, S(stream));
+}
+
+int32_t az_read_episode_ring(az_engine *h, int32_t ring, int64_t n_episodes, int64_t n_samples, int32_t *ep_slot,
+                             int32_t *ep_step, int32_t *ep_len, int64_t *ep_offset, int8_t *ep_outcome, uint64_t *s_bb0,
+                             uint64_t *s_bb1, uint8_t *s_player, int32_t *s_counts, void *stream) {
+    if (!h || ring < 0 || ring > 1 || n_episodes < 0 || n_samples < 0) return AZ_E_INVALID;
+    if (n_episodes > h->a.ep_cap || n_samples > h->a.s_cap) return fail(h, AZ_E_INVALID, "%s", "az_read_episode_ring: counts exceed the ring");
+    if (int rc = set_device(h)) return rc;
+    return ring_read(h, ring, n_episodes, n_samples, ep_slot, ep_step, ep_len, ep_offset, ep_outcome, s_bb0, s_bb1, s_player, s_counts,
+                     S(stream));
 }
 
 int32_t az_get_stats(az_engine *h, az_stats *out, void *stream) {

@@ -252,6 +252,29 @@ class Engine:
         assert one.value == ne and ons.value == ns
         return d
 
+    # double-buffered ring: read one step's episodes on a copy stream while the next step runs
+    def swap_episode_ring(self) -> int:
+        prev = C.c_int32(0)
+        self._check(self.lib.az_swap_episode_ring(self.h, C.byref(prev), _stream()), "az_swap_episode_ring")
+        return prev.value
+
+    def read_ring_to_host(self, ring: int, host: "PinnedEpisodeBuffers", stream: torch.cuda.Stream) -> EpisodeBatch | None:
+        """Counters, then exactly-sized copies of ring `ring` into pinned host memory, all on `stream`."""
+        ne, ns = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.az_ring_counts(self.h, ring, C.byref(ne), C.byref(ns), stream.cuda_stream), "az_ring_counts")
+        ne, ns = ne.value, ns.value
+        if ne == 0:
+            return None
+        host.reserve(ne, ns)
+        t = host.t
+        self._check(self.lib.az_read_episode_ring(self.h, ring, ne, ns, t["ep_slot"].data_ptr(), t["ep_step"].data_ptr(),
+                                                  t["ep_len"].data_ptr(), t["ep_offset"].data_ptr(), t["ep_outcome"].data_ptr(),
+                                                  t["s_bb0"].data_ptr(), t["s_bb1"].data_ptr(), t["s_player"].data_ptr(),
+                                                  t["s_counts"].data_ptr(), stream.cuda_stream), "az_read_episode_ring")
+        stream.synchronize()
+        d = {k: (v[:ne] if k.startswith("ep_") else v[:ns]).numpy() for k, v in t.items()}
+        return sort_episode_batch(d)  # fancy indexing copies out of the pinned buffers
+
     def drain_episodes(self) -> EpisodeBatch:
         """Ring -> host, sorted into the reference's yield order (move step, then slot)."""
         d = {k: v.cpu().numpy() for k, v in self.drain_episodes_device().items()}
@@ -270,6 +293,30 @@ class Engine:
 
     def reset_stats(self):
         self._check(self.lib.az_reset_stats(self.h, _stream()), "az_reset_stats")
+
+
+class PinnedEpisodeBuffers:
+    """Page-locked host staging for one ring read; grows geometrically."""
+
+    _SPEC = dict(ep_slot=(torch.int32, ()), ep_step=(torch.int32, ()), ep_len=(torch.int32, ()), ep_offset=(torch.int64, ()),
+                 ep_outcome=(torch.int8, (2,)), s_bb0=(torch.int64, ()), s_bb1=(torch.int64, ()), s_player=(torch.uint8, ()),
+                 s_counts=(torch.int32, (7,)))
+
+    def __init__(self):
+        self.ne = self.ns = 0
+        self.t: dict[str, torch.Tensor] = {}
+
+    def reserve(self, ne: int, ns: int):
+        if ne <= self.ne and ns <= self.ns:
+            return
+        self.ne, self.ns = max(2 * ne, self.ne, 64), max(2 * ns, self.ns, 1024)
+        for k, (dt, tail) in self._SPEC.items():
+            n = self.ne if k.startswith("ep_") else self.ns
+            self.t[k] = torch.empty((n, *tail), dtype=dt).pin_memory()
+
+    @property
+    def nbytes(self) -> int:
+        return sum(v.numel() * v.element_size() for v in self.t.values())
 
 
 def sort_episode_batch(d: dict) -> EpisodeBatch:

@@ -35,9 +35,15 @@ class EpisodeGenerator:
 
     # ------------------------------------------------------------------------------------------
     def iter_steps(self, initial_state: State | None = None, max_steps: int | None = None):
-        """Run the self-play loop; after every move step yield (step, EpisodeBatch-or-None, rng_state_before_draw).
-        Host buffers in, host buffers out: the step's uniforms are copied from pinned host memory and the
-        finished episodes (if any) plus the ring counters are read back."""
+        """Run the self-play loop; for every move step yield (step, EpisodeBatch-or-None, rng_state_before_draw).
+
+        Host buffers in, host buffers out: each step's uniforms are copied from pinned host memory, its finished
+        episodes are copied to pinned host memory.  The loop is software-pipelined one step deep: step k+1 is
+        enqueued on the compute stream before step k's episodes are read back on a copy stream from the other
+        half of the device's double-buffered episode ring, so the readback overlaps the next step's kernels.
+        Consequently a step's tuple is yielded one step late (and the last one after the loop)."""
+        from .engine import PinnedEpisodeBuffers
+
         if initial_state is None:
             initial_state = self.game_initial_state
         E = self.num_episodes
@@ -45,20 +51,41 @@ class EpisodeGenerator:
         if eng.num_games != E:
             raise RuntimeError("engine was sized for a different number of games")
         eng.reset_games(initial_state.bb0, initial_state.bb1, initial_state.player)
-        u_host = torch.empty(E, dtype=torch.float64).pin_memory()
-        u_dev = torch.empty(E, dtype=torch.float64, device=eng.device)
+        u_host = [torch.empty(E, dtype=torch.float64).pin_memory() for _ in range(2)]
+        u_dev = [torch.empty(E, dtype=torch.float64, device=eng.device) for _ in range(2)]
+        host_buf = PinnedEpisodeBuffers()
+        copy_stream = torch.cuda.Stream(device=eng.device)
+        compute = torch.cuda.current_stream(eng.device)
+        pending = None  # (step, ring, event, rng_state)
         step = 0
+        self.h2d_bytes = self.d2h_bytes = 0
         while max_steps is None or step < max_steps:
             self.search.simulate(eng)
             rng_state = np.random.get_state() if self.uniform_source is None else None
             u = np.random.random_sample(E) if self.uniform_source is None else np.asarray(self.uniform_source(step, E), np.float64)
-            u_host.copy_(torch.from_numpy(u))
-            u_dev.copy_(u_host, non_blocking=True)
-            eng.sample_moves(u_dev)
-            n_ep, _ = eng.episode_counts()
-            batch = eng.drain_episodes() if n_ep else None
-            yield step, batch, rng_state
+            uh, ud = u_host[step & 1], u_dev[step & 1]
+            uh.numpy()[:] = u
+            ud.copy_(uh, non_blocking=True)
+            eng.sample_moves(ud)  # finished games of this step go to the active ring
+            ev = torch.cuda.Event()
+            ev.record(compute)
+            self.h2d_bytes += E * 8
+            if pending is not None:  # read the previous step's ring (the inactive one) while this step runs
+                yield self._finish_step(eng, pending, host_buf, copy_stream)
+            # only now may the other ring be recycled: zero it and make it the target of the next step
+            ring = eng.swap_episode_ring()
+            pending = (step, ring, ev, rng_state)
             step += 1
+        if pending is not None:
+            yield self._finish_step(eng, pending, host_buf, copy_stream)
+
+    def _finish_step(self, eng, pending, host_buf, copy_stream):
+        step, ring, ev, rng_state = pending
+        copy_stream.wait_event(ev)
+        batch = eng.read_ring_to_host(ring, host_buf, copy_stream)
+        self.d2h_bytes += 32 + (0 if batch is None else sum(getattr(batch, f).nbytes for f in (
+            "ep_slot", "ep_step", "ep_len", "ep_offset", "ep_outcome", "s_bb0", "s_bb1", "s_player", "s_counts")))
+        return step, batch, rng_state
 
     def generate_episodes(self, initial_state: State | None = None) -> Generator[Episode, None, None]:
         """Reference semantics: yield episodes in (move step, slot) order, stop after `num_episodes`,

@@ -1,0 +1,91 @@
+"""AlphaZero iteration loop with the reference `Trainer.train(...)` signature (core/training/trainer.py:28-38),
+without Lightning: self-play on the GPU engine -> replay buffer -> `Model.training_step` epochs -> weight sync.
+
+Multi-GPU (one process per GPU): every rank plays its shard of the games; finished episodes are all-gathered
+over NCCL into every rank's replay buffer; rank 0 runs the optimiser and broadcasts the new weights
+(`update_inference_model`, search.py:22-25 / datamodule.py:100).  The reference overlaps self-play of iteration
+k+1 with training of iteration k on a daemon thread (datamodule.py:89-101); this loop runs them back to back.
+"""
+from __future__ import annotations
+
+import time
+
+import torch
+import torch.distributed as dist
+
+from .distributed import all_gather_episodes, broadcast_weights, shard_range
+from .episode_generator import EpisodeGenerator
+from .replay import ReplayBuffer
+
+
+class Trainer:
+    def __init__(self, model, device: int | None = None):
+        self.model = model
+        self.device_index = torch.cuda.current_device() if device is None else device
+        self.device = torch.device("cuda", self.device_index)
+        self.history: list[dict] = []
+
+    def train(self, *, num_iterations: int, episodes_per_iter: int, simulations_per_episode: int, epochs_per_iter: int,
+              initial_state, buffer_size: int, save_every_n_iterations: int = 0, batch_size: int = 32, seed: int = 0):
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        lo, hi = shard_range(episodes_per_iter, rank, world)
+        model = self.model.to(self.device)
+        gen = EpisodeGenerator(model=model, num_simulations=simulations_per_episode, num_episodes=hi - lo,
+                               game_initial_state=initial_state, device=self.device_index)
+        replay = ReplayBuffer(buffer_size, simulations_per_episode, self.device)
+        opt = model.configure_optimizers()
+        g = torch.Generator().manual_seed(seed)
+        for it in range(num_iterations):
+            t0 = time.perf_counter()
+            # self-play: this rank's games until its quota, kept on the device
+            eng = gen.search.engine_for(hi - lo)
+            local = None
+            for batch in gen.generate_batches(quota=hi - lo):
+                replay_part = batch
+                local = replay_part if local is None else _concat(local, replay_part)
+            t1 = time.perf_counter()
+            if world > 1:
+                merged = all_gather_episodes(_to_device(local, self.device), slot_offset=lo)
+                replay.extend({k: merged[k] for k in ("ep_len", "ep_offset", "ep_outcome", "s_bb0", "s_bb1", "s_player", "s_counts")})
+            else:
+                replay.extend(local)
+            t2 = time.perf_counter()
+            losses = []
+            if rank == 0:
+                model.train()
+                for _ in range(epochs_per_iter):
+                    for x, pt, vt in replay.batches(model.input_layout, batch_size, True, g):
+                        opt.zero_grad(set_to_none=True)
+                        loss = model.training_step((x, pt, vt), 0)
+                        loss.backward()
+                        opt.step()
+                        losses.append(loss.detach())
+                model.eval()
+            nbytes = broadcast_weights(model, src=0) if world > 1 else 0
+            gen.update_inference_model(model)
+            torch.cuda.synchronize(self.device)
+            t3 = time.perf_counter()
+            self.history.append(dict(iteration=it, episodes=len(replay), samples=replay.num_samples, selfplay_s=t1 - t0,
+                                     gather_s=t2 - t1, train_s=t3 - t2, weight_bytes=nbytes,
+                                     loss=float(torch.stack(losses).mean()) if losses else None))
+        return self.history
+
+
+def _concat(a, b):
+    import numpy as np
+
+    from .engine import EpisodeBatch
+
+    off = np.concatenate([a.ep_offset, b.ep_offset + len(a.s_bb0)])
+    return EpisodeBatch(np.concatenate([a.ep_slot, b.ep_slot]), np.concatenate([a.ep_step, b.ep_step]), np.concatenate([a.ep_len, b.ep_len]),
+                        off, np.concatenate([a.ep_outcome, b.ep_outcome]), np.concatenate([a.s_bb0, b.s_bb0]),
+                        np.concatenate([a.s_bb1, b.s_bb1]), np.concatenate([a.s_player, b.s_player]), np.concatenate([a.s_counts, b.s_counts]))
+
+
+def _to_device(b, device):
+    import numpy as np
+
+    d = dict(ep_slot=b.ep_slot, ep_step=b.ep_step, ep_len=b.ep_len, ep_offset=b.ep_offset, ep_outcome=b.ep_outcome,
+             s_bb0=b.s_bb0.view(np.int64), s_bb1=b.s_bb1.view(np.int64), s_player=b.s_player, s_counts=b.s_counts)
+    return {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in d.items()}

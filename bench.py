@@ -304,31 +304,31 @@ def run_b200(args):
                                   lanes_per_tree=args.lanes)
         np.random.seed(7 + rank)
         g_eng = gen.search.engine_for(E)
-        d2h, eps, e2e_t0, sims_before, n_steps = 0, 0, None, None, 0
-        for step, batch, _ in gen.iter_steps(max_steps=W + K):
-            if step == W - 1:  # warm-up done: open the timed region on a quiet device
-                barrier()
+        eps, e2e_t0, sims_before, bytes0 = 0, None, None, (0, 0)
+        for step, batch, _ in gen.iter_steps(max_steps=W + K + 1):
+            if step == W - 1:  # warm-up done: open the timed region on a quiet device (step W is already enqueued: it is
+                barrier()      # finished by this barrier and counted as warm-up by the statistics snapshot below)
                 sims_before = g_eng.stats()
+                bytes0 = (gen.h2d_bytes, gen.d2h_bytes)
                 e2e_t0 = time.perf_counter()
                 continue
             if e2e_t0 is None:
                 continue
-            n_steps += 1
             if batch is not None:
-                d2h += sum(getattr(batch, f).nbytes for f in ("ep_slot", "ep_step", "ep_len", "ep_offset", "ep_outcome", "s_bb0", "s_bb1",
-                                                              "s_player", "s_counts"))
                 eps += len(batch)
         barrier()
         e2e_s = time.perf_counter() - e2e_t0
         d = diff(sims_before, g_eng.stats())
+        n_steps = d["moves"] // E
+        h2d, d2h = gen.h2d_bytes - bytes0[0], gen.d2h_bytes - bytes0[1]
         t = torch.tensor([e2e_s], dtype=torch.float64, device=eng.device)
         c = torch.tensor([float(d["simulations"])], dtype=torch.float64, device=eng.device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        e2e = {"value": float(c.item()) / float(t.item()), "unit": "sims/s", "h2d_bytes_per_step": E * 8,
-               "d2h_bytes_per_step": int(d2h / max(1, n_steps)) + 32, "steps": int(n_steps), "games_per_sec": eps / e2e_s * world,
-               "api": "EpisodeGenerator.generate_batches (pinned-host uniforms in, finished episodes + counters out, every step)"}
+        e2e = {"value": float(c.item()) / float(t.item()), "unit": "sims/s", "h2d_bytes_per_step": int(h2d / max(1, n_steps)),
+               "d2h_bytes_per_step": int(d2h / max(1, n_steps)), "steps": int(n_steps), "games_per_sec": eps / e2e_s * world,
+               "api": "EpisodeGenerator.iter_steps: pinned-host uniforms in, finished episodes + ring counters out to pinned host memory every step; readback of step k overlaps step k+1"}
 
     # multi-GPU: all-gather of finished episodes over NCCL (config 4), timed apart from the data path
     allgather = None

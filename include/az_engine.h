@@ -181,6 +181,18 @@ int32_t az_drain_episodes(az_engine *h, int64_t ep_cap, int64_t s_cap, int32_t *
                           uint64_t *s_bb1, uint8_t *s_player, int32_t *s_counts /*[n][7]*/,
                           int64_t *n_episodes_host, int64_t *n_samples_host, void *stream);
 
+/* Double-buffered use of the ring (lets the host read one move step's episodes while the next step runs):
+ * az_swap_episode_ring makes the other ring the active one (zeroing its counters on `stream`) and reports the
+ * index of the ring that was active; that ring keeps its contents until it becomes active again.
+ * az_ring_counts synchronises `stream` and returns a ring's counters; az_read_episode_ring enqueues copies of
+ * exactly n_episodes / n_samples entries.  Destinations may be device or pinned host memory. */
+int32_t az_swap_episode_ring(az_engine *h, int32_t *previous_ring_host, void *stream);
+int32_t az_ring_counts(az_engine *h, int32_t ring, int64_t *n_episodes_host, int64_t *n_samples_host, void *stream);
+int32_t az_read_episode_ring(az_engine *h, int32_t ring, int64_t n_episodes, int64_t n_samples, int32_t *ep_slot,
+                             int32_t *ep_step, int32_t *ep_len, int64_t *ep_offset, int8_t *ep_outcome /*[n][2]*/,
+                             uint64_t *s_bb0, uint64_t *s_bb1, uint8_t *s_player, int32_t *s_counts /*[n][7]*/,
+                             void *stream);
+
 /* ---- instrumentation ---- */
 int32_t az_get_stats(az_engine *h, az_stats *out_host, void *stream); /* synchronises */
 int32_t az_reset_stats(az_engine *h, void *stream);

@@ -75,7 +75,7 @@ def test_state_action_interface():
     assert az.State.from_json(s.to_json()) == s
 
 
-@pytest.mark.parametrize("idx", [0, 1, 3, 7])
+@pytest.mark.parametrize("idx", [0, 1, 2, 3, 4, 7])
 def test_episode_generator_matches_reference_transcript(selfplay_goldens, idx):
     run = selfplay_goldens[idx]
     ev = az.UniformEvaluator() if run["eval_kind"] == 1 else az.HashEvaluator()
@@ -201,3 +201,39 @@ def test_resnet_bf16_inference_within_tolerance():
     assert torch.allclose(torch.softmax(l16, 1), torch.softmax(l_ref, 1), atol=1e-2)
     assert torch.allclose(v16, v_ref, atol=2e-2)
     eng.close()
+
+
+def test_training_iteration_reduces_loss_and_syncs_weights():
+    """Row (f1/f2): self-play -> replay buffer -> CE + MSE training step (Adam 1e-3, wd 1e-4) -> weight sync."""
+    from alphazero_implementation_b200.trainer import Trainer
+
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = az.BasicNN()
+    tr = Trainer(model)
+    hist = tr.train(num_iterations=2, episodes_per_iter=32, simulations_per_episode=32, epochs_per_iter=3,
+                    initial_state=az.Config(6, 7, 4).sample_initial_state(), buffer_size=64)
+    assert len(hist) == 2 and hist[0]["episodes"] == 32 and hist[1]["episodes"] == 64
+    assert hist[0]["samples"] >= 32 * 7 and hist[1]["loss"] < hist[0]["loss"]
+
+
+def test_replay_buffer_targets_match_reference_format(selfplay_goldens):
+    """Dense policy / value targets built on the device equal the reference's format_dataset tensors."""
+    from alphazero_implementation_b200.replay import ReplayBuffer
+
+    run = selfplay_goldens[2]
+    gen = az.EpisodeGenerator(model=az.UniformEvaluator(), num_simulations=run["S"], num_episodes=run["E"],
+                              game_initial_state=az.Config().sample_initial_state())
+    np.random.seed(run["seed"])
+    rb = ReplayBuffer(buffer_size=5, num_simulations=run["S"])
+    for batch in gen.generate_batches(quota=run["E"]):
+        rb.extend(batch)
+    assert len(rb) == 5  # deque(maxlen=buffer_size): only the last 5 episodes stay
+    bb0, bb1, pl, policy, value = rb.tensors()
+    ref_eps = run["episodes"][-5:]
+    ref_pol = torch.tensor([s["policy"] for ep in ref_eps for s in ep["samples"]], dtype=torch.float32)
+    ref_val = torch.tensor([ep["outcome"] for ep in ref_eps for _ in ep["samples"]], dtype=torch.float32)
+    assert torch.allclose(policy.cpu(), ref_pol, atol=1e-7) and torch.equal(value.cpu(), ref_val)
+    assert bb0.cpu().tolist() == [s["bb0"] for ep in ref_eps for s in ep["samples"]]
+    x, p, v = next(rb.batches(az.BasicNN.input_layout, batch_size=8, shuffle=False))
+    assert x.shape == (8, 6, 7) and p.shape == (8, 7) and v.shape == (8, 2)
