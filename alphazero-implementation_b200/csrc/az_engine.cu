@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     const int warp = threadIdx.x >> 5;
     const int sub = lane & 24;
     const int c = lane & 7;
-    const int q = (TPW == 4) ? (lane >> 3) : 0;
+    const int q = lane / (32 / TPW);
     const int tib = warp * TPW + q;
     const int t = blockIdx.x * TREES + tib;
     const bool alive = (t < n_active) && (a.tree_err[t < n_active ? t : 0] == 0);
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_p
     const int warp = threadIdx.x >> 5;
     const int sub = lane & 24;
     const int c = lane & 7;
-    const int q = (TPW == 4) ? (lane >> 3) : 0;
+    const int q = lane / (32 / TPW);
     const int t = blockIdx.x * TREES + warp * TPW + q;
     const bool in_range = t < n_active;
     const bool alive = in_range && (a.tree_err[in_range ? t : 0] == 0);
@@ -453,7 +453,7 @@ k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const f
     const int warp = threadIdx.x >> 5;
     const int sub = lane & 24;
     const int c = lane & 7;
-    const int q = (TPW == 4) ? (lane >> 3) : 0;
+    const int q = lane / (32 / TPW);
     const int t = blockIdx.x * TREES + warp * TPW + q;
     const bool alive = (t < n_active) && (a.leaf_status[t < n_active ? t : 0] == AZ_LEAF_EVAL);
     if (!__any_sync(FULL, alive)) return;
@@ -509,83 +509,99 @@ k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const f
 }
 
 // ------------------------------------------------------------------------------------------------
-// plane encoders.  One thread produces 4 consecutive output elements (16-byte / 8-byte stores).
-__device__ __forceinline__ float plane_value(uint64_t b0, uint64_t b1, int pl, bool live, int layout, int e) {
-    // e = element index inside one position's block
-    if (!live) return 0.0f;
-    if (layout == AZ_LAYOUT_GRID_F32) {
-        const int r = e / 7, col = e % 7;  // [6][7], row 0 = bottom
-        const int bit = col * 7 + r;
-        return ((b0 >> bit) & 1ull) ? 0.0f : (((b1 >> bit) & 1ull) ? 1.0f : -1.0f);
-    }
-    int ch, r, col;
-    if (layout == AZ_LAYOUT_PLANES_BF16_NHWC) {  // [6][7][8]
-        ch = e & 7;
-        col = (e >> 3) % 7;
-        r = (e >> 3) / 7;
-        if (ch > 2) return 0.0f;
-    } else {  // [3][6][7]
-        ch = e / 42;
-        r = (e % 42) / 7;
-        col = e % 7;
-    }
-    const int bit = col * 7 + r;
-    const uint64_t mine = pl ? b1 : b0, theirs = pl ? b0 : b1;
-    const uint64_t src = ch == 0 ? ~(b0 | b1) : (ch == 1 ? mine : theirs);  // empty, side to move, opponent (cnn.py:93-95)
-    return (float)((src >> bit) & 1ull);
-}
-
+// plane encoders (the "leaf gather").  One thread per position builds the position's output words from
+// row-major plane masks (a handful of integer ops per word), stages them in shared memory, and the block
+// then streams the staged tile to HBM with coalesced 16-byte stores: a tile of B positions is contiguous in
+// the output, so the write side runs at copy speed regardless of the 252 / 168 / 504 / 672-byte record size.
 __host__ __device__ inline int layout_elems(int layout) {
     return layout == AZ_LAYOUT_GRID_F32 ? 42 : (layout == AZ_LAYOUT_PLANES_BF16_NHWC ? 336 : 126);
 }
+__host__ __device__ inline int layout_words(int layout) {  // 32-bit words per position
+    return layout == AZ_LAYOUT_GRID_F32 ? 42 : (layout == AZ_LAYOUT_PLANES_F32 ? 126 : (layout == AZ_LAYOUT_PLANES_BF16 ? 63 : 168));
+}
 
-__global__ void __launch_bounds__(256)
-k_encode(const uint64_t *__restrict__ bb0, const uint64_t *__restrict__ bb1, const uint8_t *__restrict__ player,
-         const uint8_t *__restrict__ status, long long n, void *out, int layout) {
-    const int elems = layout_elems(layout);
-    const long long total = n * elems;
-    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i0 >= total) return;
-    float v[4];
-    long long t = i0 / elems;
-    int e = (int)(i0 - t * elems);
-    uint64_t b0 = bb0[t], b1 = bb1[t];
-    int pl = player[t];
-    bool live = status ? (status[t] == AZ_LEAF_EVAL) : true;
+// column-major bitboard (bit = 7*col + row) -> row-major 42-bit mask (bit = 7*row + col), the element order of [6][7]
+__device__ __forceinline__ uint64_t to_row_major(uint64_t bb) {
+    uint64_t m = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        if (i0 + q < total) {
-            if (e == elems) {
-                e = 0;
-                ++t;
-                b0 = bb0[t];
-                b1 = bb1[t];
-                pl = player[t];
-                live = status ? (status[t] == AZ_LEAF_EVAL) : true;
+    for (int r = 0; r < c4::H; ++r) {
+        const uint64_t row = ((((bb >> r) & 0x40810204081ull) * c4::LEGAL_MAGIC) >> 36) & 0x7Full;
+        m |= row << (7 * r);
+    }
+    return m;
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(128)
+k_encode(const uint64_t *__restrict__ bb0, const uint64_t *__restrict__ bb1, const uint8_t *__restrict__ player,
+         const uint8_t *__restrict__ status, long long n, uint32_t *__restrict__ out) {
+    constexpr int W = (LAYOUT == AZ_LAYOUT_GRID_F32) ? 42 : (LAYOUT == AZ_LAYOUT_PLANES_F32) ? 126 : (LAYOUT == AZ_LAYOUT_PLANES_BF16) ? 63 : 168;
+    constexpr int WP = (W % 2 == 0) ? W + 1 : W;  // odd row stride: conflict-free staging
+    extern __shared__ uint32_t s_tile[];          // [blockDim.x][WP]
+    const int B = blockDim.x;
+    const long long t0 = (long long)blockIdx.x * B;
+    const long long t = t0 + threadIdx.x;
+    uint32_t *row = s_tile + threadIdx.x * WP;
+    if (t < n) {
+        uint64_t b0 = bb0[t], b1 = bb1[t];
+        const int pl = player[t] & 1;
+        const bool live = status ? (status[t] == AZ_LEAF_EVAL) : true;
+        if (LAYOUT == AZ_LAYOUT_GRID_F32) {
+            // state.grid as f32: -1 empty / 0 / 1 owner (basic.py:41-47)
+            const uint64_t m0 = to_row_major(b0), m1 = to_row_major(b1);
+#pragma unroll
+            for (int e = 0; e < 42; ++e) {
+                const uint32_t v = ((m0 >> e) & 1ull) ? 0x00000000u : (((m1 >> e) & 1ull) ? 0x3F800000u : 0xBF800000u);
+                row[e] = live ? v : 0u;
             }
-            v[q] = plane_value(b0, b1, pl, live, layout, e);
-            ++e;
         } else {
-            v[q] = 0.0f;
+            // planes: empty, side to move, opponent (cnn.py:93-95)
+            const uint64_t mine = pl ? b1 : b0, theirs = pl ? b0 : b1;
+            uint64_t p0 = to_row_major(~(b0 | b1) & c4::BOARD), p1 = to_row_major(mine), p2 = to_row_major(theirs);
+            if (!live) p0 = p1 = p2 = 0;
+            if (LAYOUT == AZ_LAYOUT_PLANES_F32) {
+#pragma unroll
+                for (int e = 0; e < 42; ++e) {
+                    row[e] = ((p0 >> e) & 1ull) ? 0x3F800000u : 0u;
+                    row[42 + e] = ((p1 >> e) & 1ull) ? 0x3F800000u : 0u;
+                    row[84 + e] = ((p2 >> e) & 1ull) ? 0x3F800000u : 0u;
+                }
+            } else if (LAYOUT == AZ_LAYOUT_PLANES_BF16) {
+                // 126 bf16 = 63 words; element stream = p0 (42 bits) | p1 (42) | p2 (42)
+                const uint64_t lo = p0 | (p1 << 42);          // elements 0..63
+                const uint64_t hi = (p1 >> 22) | (p2 << 20);  // elements 64..125
+#pragma unroll
+                for (int w = 0; w < 63; ++w) {
+                    const uint32_t two = (w < 32) ? (uint32_t)(lo >> (2 * w)) & 3u : (uint32_t)(hi >> (2 * (w - 32))) & 3u;
+                    row[w] = ((two & 1u) ? 0x00003F80u : 0u) | ((two & 2u) ? 0x3F800000u : 0u);
+                }
+            } else {  // NHWC, 8 channels per cell: c0 c1 | c2 0 | 0 0 | 0 0
+#pragma unroll
+                for (int e = 0; e < 42; ++e) {
+                    row[4 * e] = (((p0 >> e) & 1ull) ? 0x00003F80u : 0u) | (((p1 >> e) & 1ull) ? 0x3F800000u : 0u);
+                    row[4 * e + 1] = ((p2 >> e) & 1ull) ? 0x00003F80u : 0u;
+                    row[4 * e + 2] = 0u;
+                    row[4 * e + 3] = 0u;
+                }
+            }
         }
     }
-    const bool is_bf16 = (layout == AZ_LAYOUT_PLANES_BF16 || layout == AZ_LAYOUT_PLANES_BF16_NHWC);
-    if (i0 + 3 < total) {
-        if (is_bf16) {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t *>(&lo);
-            pk.y = *reinterpret_cast<uint32_t *>(&hi);
-            reinterpret_cast<uint2 *>(out)[i0 >> 2] = pk;
-        } else {
-            reinterpret_cast<float4 *>(out)[i0 >> 2] = make_float4(v[0], v[1], v[2], v[3]);
+    __syncthreads();
+    const long long remaining = n - t0;
+    const int valid = remaining < B ? (int)remaining : B;
+    const int total_words = valid * W;
+    uint32_t *dst = out + t0 * W;  // B*W*4 bytes per full tile: 16-byte aligned whenever B is a multiple of 4
+    const int quads = total_words >> 2;
+    for (int qd = threadIdx.x; qd < quads; qd += B) {
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int w = 4 * qd + k;
+            v[k] = s_tile[(w / W) * WP + (w % W)];
         }
-    } else {
-        for (int q = 0; q < 4 && i0 + q < total; ++q) {
-            if (is_bf16) reinterpret_cast<__nv_bfloat16 *>(out)[i0 + q] = __float2bfloat16_rn(v[q]);
-            else reinterpret_cast<float *>(out)[i0 + q] = v[q];
-        }
+        reinterpret_cast<uint4 *>(dst)[qd] = make_uint4(v[0], v[1], v[2], v[3]);
     }
+    for (int w = 4 * quads + threadIdx.x; w < total_words; w += B) dst[w] = s_tile[(w / W) * WP + (w % W)];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -620,6 +636,84 @@ k_env_step(const uint64_t *__restrict__ bb0, const uint64_t *__restrict__ bb1, c
         oreward[2 * i + 1] = (int8_t)-T.reward0;
     }
     if (ostatus) ostatus[i] = status;
+}
+
+// 4 positions per thread: 128-bit loads/stores of the bitboards, 32-bit loads/stores of the byte arrays.
+// Used when every pointer is present and 16-byte aligned (the normal case); the scalar kernel covers the rest.
+__device__ __forceinline__ void env_step_one(uint64_t &b0, uint64_t &b1, int &pl, int cc, uint8_t &legal, uint8_t &ended,
+                                             int8_t &r0, uint8_t &status) {
+    c4::Terminal T = c4::terminal_of(b0, b1);
+    status = 1;
+    if (!T.ended && cc < c4::W && !(((b0 | b1) >> (c4::STRIDE * cc + 5)) & 1ull)) {
+        const uint64_t bit = c4::drop_bit(b0 | b1, cc);
+        if (pl == 0) b0 |= bit; else b1 |= bit;
+        const bool win = c4::has4_nb(pl ? b1 : b0);
+        T.ended = win || c4::is_full(b0 | b1);
+        T.reward0 = win ? (pl == 0 ? 1 : -1) : 0;
+        pl ^= 1;
+        status = 0;
+    }
+    legal = T.ended ? 0 : (uint8_t)c4::legal_mask(b0 | b1);
+    ended = T.ended ? 1 : 0;
+    r0 = T.reward0;
+}
+
+__global__ void __launch_bounds__(256)
+k_env_step_v4(const ulonglong2 *__restrict__ bb0, const ulonglong2 *__restrict__ bb1, const uint32_t *__restrict__ player,
+              const uint32_t *__restrict__ col, long long quads, ulonglong2 *o0, ulonglong2 *o1, uint32_t *opl, uint32_t *olegal,
+              uint32_t *oended, uint2 *oreward, uint32_t *ostatus) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= quads) return;
+    const ulonglong2 a0 = bb0[2 * i], a1 = bb0[2 * i + 1], c0 = bb1[2 * i], c1 = bb1[2 * i + 1];
+    uint64_t x0[4] = {a0.x, a0.y, a1.x, a1.y}, x1[4] = {c0.x, c0.y, c1.x, c1.y};
+    const uint32_t pw = player[i], cw = col[i];
+    uint32_t plw = 0, lgw = 0, enw = 0, stw = 0;
+    uint32_t rw[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int pl = (pw >> (8 * k)) & 1;
+        uint8_t lg, en, st;
+        int8_t r0;
+        env_step_one(x0[k], x1[k], pl, (cw >> (8 * k)) & 0xFF, lg, en, r0, st);
+        plw |= (uint32_t)pl << (8 * k);
+        lgw |= (uint32_t)lg << (8 * k);
+        enw |= (uint32_t)en << (8 * k);
+        stw |= (uint32_t)st << (8 * k);
+        const uint32_t pair = (uint32_t)(uint8_t)r0 | ((uint32_t)(uint8_t)(int8_t)-r0 << 8);
+        rw[k >> 1] |= pair << (16 * (k & 1));
+    }
+    o0[2 * i] = make_ulonglong2(x0[0], x0[1]);
+    o0[2 * i + 1] = make_ulonglong2(x0[2], x0[3]);
+    o1[2 * i] = make_ulonglong2(x1[0], x1[1]);
+    o1[2 * i + 1] = make_ulonglong2(x1[2], x1[3]);
+    opl[i] = plw;
+    olegal[i] = lgw;
+    oended[i] = enw;
+    oreward[i] = make_uint2(rw[0], rw[1]);
+    ostatus[i] = stw;
+}
+
+__global__ void __launch_bounds__(256)
+k_state_info_v4(const ulonglong2 *__restrict__ bb0, const ulonglong2 *__restrict__ bb1, long long quads, uint32_t *olegal,
+                uint32_t *oended, uint2 *oreward) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= quads) return;
+    const ulonglong2 a0 = bb0[2 * i], a1 = bb0[2 * i + 1], c0 = bb1[2 * i], c1 = bb1[2 * i + 1];
+    const uint64_t x0[4] = {a0.x, a0.y, a1.x, a1.y}, x1[4] = {c0.x, c0.y, c1.x, c1.y};
+    uint32_t lgw = 0, enw = 0, rw[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const bool w0 = c4::has4_nb(x0[k]), w1 = c4::has4_nb(x1[k]);
+        const bool ended = w0 || w1 || c4::is_full(x0[k] | x1[k]);
+        const int8_t r0 = w0 ? 1 : (w1 ? -1 : 0);
+        lgw |= (ended ? 0u : c4::legal_mask(x0[k] | x1[k])) << (8 * k);
+        enw |= (ended ? 1u : 0u) << (8 * k);
+        const uint32_t pair = (uint32_t)(uint8_t)r0 | ((uint32_t)(uint8_t)(int8_t)-r0 << 8);
+        rw[k >> 1] |= pair << (16 * (k & 1));
+    }
+    olegal[i] = lgw;
+    oended[i] = enw;
+    oreward[i] = make_uint2(rw[0], rw[1]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -968,6 +1062,27 @@ int set_device(az_engine *h) {
 
 }  // namespace
 
+namespace {
+int launch_encode(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, const uint8_t *player, const uint8_t *status,
+                  long long n, void *out, int layout, cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(out) & 15u) != 0) return fail(h, AZ_E_INVALID, "%s", "plane output buffer must be 16-byte aligned");
+    const int W = layout_words(layout);
+    const int B = (W <= 63) ? 128 : 64;
+    const int WP = (W % 2 == 0) ? W + 1 : W;
+    const size_t smem = (size_t)B * WP * sizeof(uint32_t);
+    const int blocks = blocks_for(n, B);
+    uint32_t *o = static_cast<uint32_t *>(out);
+    switch (layout) {
+        case AZ_LAYOUT_GRID_F32: k_encode<AZ_LAYOUT_GRID_F32><<<blocks, B, smem, st>>>(bb0, bb1, player, status, n, o); break;
+        case AZ_LAYOUT_PLANES_F32: k_encode<AZ_LAYOUT_PLANES_F32><<<blocks, B, smem, st>>>(bb0, bb1, player, status, n, o); break;
+        case AZ_LAYOUT_PLANES_BF16: k_encode<AZ_LAYOUT_PLANES_BF16><<<blocks, B, smem, st>>>(bb0, bb1, player, status, n, o); break;
+        default: k_encode<AZ_LAYOUT_PLANES_BF16_NHWC><<<blocks, B, smem, st>>>(bb0, bb1, player, status, n, o); break;
+    }
+    AZ_LAUNCH_CHECK(h, "k_encode");
+    return AZ_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int32_t az_abi_version(void) { return AZ_ABI_VERSION; }
@@ -982,7 +1097,7 @@ int32_t az_create(const az_config *cfg, az_engine **out) {
     if (cfg->num_games < 1 || cfg->num_simulations < 1 || cfg->num_simulations > 1000000)
         return fail(nullptr, AZ_E_INVALID, "%s", "az_create: num_games >= 1 and 1 <= num_simulations <= 1e6 required");
     int G = cfg->lanes_per_tree == 0 ? 8 : cfg->lanes_per_tree;
-    if (G != 8 && G != 32) return fail(nullptr, AZ_E_INVALID, "%s", "az_create: lanes_per_tree must be 8 or 32");
+    if (G != 8 && G != 16 && G != 32) return fail(nullptr, AZ_E_INVALID, "%s", "az_create: lanes_per_tree must be 8, 16 or 32");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -1090,9 +1205,26 @@ int32_t az_env_step(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, cons
     if (n < 0 || (n > 0 && (!bb0 || !bb1 || !player || !col))) return fail(h, AZ_E_INVALID, "%s", "az_env_step: null input");
     if (n == 0) return AZ_OK;
     if (int rc = set_device(h)) return rc;
-    k_env_step<<<blocks_for(n, 256), 256, 0, S(stream)>>>(bb0, bb1, player, col, n, o0, o1, opl, olegal, oended, oreward,
-                                                         ostatus);
-    AZ_LAUNCH_CHECK(h, "k_env_step");
+    const void *ptrs[] = {bb0, bb1, player, col, o0, o1, opl, olegal, oended, oreward, ostatus};
+    bool vec = true;
+    for (const void *p : ptrs) vec = vec && p && (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+    const long long quads = vec ? n / 4 : 0, head = quads * 4;
+    if (quads) {
+        k_env_step_v4<<<blocks_for(quads, 256), 256, 0, S(stream)>>>(
+            reinterpret_cast<const ulonglong2 *>(bb0), reinterpret_cast<const ulonglong2 *>(bb1), reinterpret_cast<const uint32_t *>(player),
+            reinterpret_cast<const uint32_t *>(col), quads, reinterpret_cast<ulonglong2 *>(o0), reinterpret_cast<ulonglong2 *>(o1),
+            reinterpret_cast<uint32_t *>(opl), reinterpret_cast<uint32_t *>(olegal), reinterpret_cast<uint32_t *>(oended),
+            reinterpret_cast<uint2 *>(oreward), reinterpret_cast<uint32_t *>(ostatus));
+        AZ_LAUNCH_CHECK(h, "k_env_step_v4");
+    }
+    if (head < n) {
+#define OFF(p, k) ((p) ? (p) + (k) : (p))
+        k_env_step<<<blocks_for(n - head, 256), 256, 0, S(stream)>>>(bb0 + head, bb1 + head, player + head, col + head, n - head,
+                                                                OFF(o0, head), OFF(o1, head), OFF(opl, head), OFF(olegal, head),
+                                                                OFF(oended, head), OFF(oreward, 2 * head), OFF(ostatus, head));
+        AZ_LAUNCH_CHECK(h, "k_env_step");
+#undef OFF
+    }
     return AZ_OK;
 }
 
@@ -1103,8 +1235,24 @@ int32_t az_state_info(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, co
     if (n < 0 || (n > 0 && (!bb0 || !bb1))) return fail(h, AZ_E_INVALID, "%s", "az_state_info: null input");
     if (n == 0) return AZ_OK;
     if (int rc = set_device(h)) return rc;
-    k_state_info<<<blocks_for(n, 256), 256, 0, S(stream)>>>(bb0, bb1, n, olegal, oended, oreward);
-    AZ_LAUNCH_CHECK(h, "k_state_info");
+    const void *ptrs[] = {bb0, bb1, olegal, oended, oreward};
+    bool vec = true;
+    for (const void *p : ptrs) vec = vec && p && (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+    const long long quads = vec ? n / 4 : 0, head = quads * 4;
+    if (quads) {
+        k_state_info_v4<<<blocks_for(quads, 256), 256, 0, S(stream)>>>(reinterpret_cast<const ulonglong2 *>(bb0),
+                                                                  reinterpret_cast<const ulonglong2 *>(bb1), quads,
+                                                                  reinterpret_cast<uint32_t *>(olegal), reinterpret_cast<uint32_t *>(oended),
+                                                                  reinterpret_cast<uint2 *>(oreward));
+        AZ_LAUNCH_CHECK(h, "k_state_info_v4");
+    }
+    if (head < n) {
+#define OFF(p, k) ((p) ? (p) + (k) : (p))
+        k_state_info<<<blocks_for(n - head, 256), 256, 0, S(stream)>>>(bb0 + head, bb1 + head, n - head, OFF(olegal, head),
+                                                                  OFF(oended, head), OFF(oreward, 2 * head));
+        AZ_LAUNCH_CHECK(h, "k_state_info");
+#undef OFF
+    }
     return AZ_OK;
 }
 
@@ -1130,10 +1278,7 @@ int32_t az_encode_states(az_engine *h, const uint64_t *bb0, const uint64_t *bb1,
     if (int rc = check_layout(h, layout)) return rc;
     if (n == 0) return AZ_OK;
     if (int rc = set_device(h)) return rc;
-    const long long quads = (n * layout_elems(layout) + 3) / 4;
-    k_encode<<<blocks_for(quads, 256), 256, 0, S(stream)>>>(bb0, bb1, player, nullptr, n, out, layout);
-    AZ_LAUNCH_CHECK(h, "k_encode");
-    return AZ_OK;
+    return launch_encode(h, bb0, bb1, player, nullptr, n, out, layout, S(stream));
 }
 
 int32_t az_reset_games(az_engine *h, uint64_t init_bb0, uint64_t init_bb1, int32_t init_player, void *stream) {
@@ -1180,7 +1325,7 @@ int32_t az_run_simulations(az_engine *h, int32_t num_sims, int32_t eval_kind, vo
     const int n = h->n_active;
     const double c = h->cfg.c_puct;
     // hot-node count K: as many as shared memory allows while every block of the grid stays resident
-    const int tpw = (h->G == 32) ? 1 : 4, trees_per_block = 2 * tpw;
+    const int tpw = 32 / h->G, trees_per_block = 2 * tpw;
     const int blocks = blocks_for(n, trees_per_block);
     int per_sm = (blocks + h->num_sms - 1) / h->num_sms;
     if (per_sm > 14) per_sm = 14;  // register-limited residency of 64-thread blocks (72 registers)
@@ -1198,6 +1343,8 @@ int32_t az_run_simulations(az_engine *h, int32_t num_sims, int32_t eval_kind, vo
     } while (0)
     if (tpw == 1) {
         if (eval_kind == AZ_EVAL_UNIFORM) AZ_RUN(1, AZ_EVAL_UNIFORM); else AZ_RUN(1, AZ_EVAL_HASH);
+    } else if (tpw == 2) {
+        if (eval_kind == AZ_EVAL_UNIFORM) AZ_RUN(2, AZ_EVAL_UNIFORM); else AZ_RUN(2, AZ_EVAL_HASH);
     } else {
         if (eval_kind == AZ_EVAL_UNIFORM) AZ_RUN(4, AZ_EVAL_UNIFORM); else AZ_RUN(4, AZ_EVAL_HASH);
     }
@@ -1215,6 +1362,7 @@ int32_t az_select_leaves(az_engine *h, void *stream) {
     if (h->sims_done + 1 > h->cfg.num_simulations)
         return fail(h, AZ_E_INVALID, "%s", "az_select_leaves: more simulations on these roots than the arena holds");
     if (h->G == 32) k_select<1><<<blocks_for(n, 2), 64, 0, S(stream)>>>(h->a, n, h->cfg.c_puct);
+    else if (h->G == 16) k_select<2><<<blocks_for(n, 4), 64, 0, S(stream)>>>(h->a, n, h->cfg.c_puct);
     else k_select<4><<<blocks_for(n, 8), 64, 0, S(stream)>>>(h->a, n, h->cfg.c_puct);
     AZ_LAUNCH_CHECK(h, "k_select");
     h->sims_done += 1;
@@ -1227,11 +1375,7 @@ int32_t az_gather_leaves(az_engine *h, void *out, int32_t layout, void *stream) 
     if (int rc = check_layout(h, layout)) return rc;
     if (int rc = set_device(h)) return rc;
     const long long n = h->n_active;
-    const long long quads = (n * layout_elems(layout) + 3) / 4;
-    k_encode<<<blocks_for(quads, 256), 256, 0, S(stream)>>>(h->a.leaf_bb0, h->a.leaf_bb1, h->a.leaf_player, h->a.leaf_status,
-                                                           n, out, layout);
-    AZ_LAUNCH_CHECK(h, "k_encode");
-    return AZ_OK;
+    return launch_encode(h, h->a.leaf_bb0, h->a.leaf_bb1, h->a.leaf_player, h->a.leaf_status, n, out, layout, S(stream));
 }
 
 int32_t az_expand_backup(az_engine *h, const float *policy, const float *values, int32_t policy_kind, void *stream) {
@@ -1241,6 +1385,7 @@ int32_t az_expand_backup(az_engine *h, const float *policy, const float *values,
     if (int rc = set_device(h)) return rc;
     const int n = h->n_active;
     if (h->G == 32) k_expand_backup<1><<<blocks_for(n, 2), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind);
+    else if (h->G == 16) k_expand_backup<2><<<blocks_for(n, 4), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind);
     else k_expand_backup<4><<<blocks_for(n, 8), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind);
     AZ_LAUNCH_CHECK(h, "k_expand_backup");
     return AZ_OK;

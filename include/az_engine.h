@@ -74,7 +74,7 @@ typedef struct az_config {
     int32_t num_games;       /* E: concurrent game slots / trees (EpisodeGenerator num_episodes) */
     int32_t num_simulations; /* S: arena is sized for 1 + 7*S nodes per tree (search.py:15) */
     int32_t device;          /* CUDA device ordinal */
-    int32_t lanes_per_tree;  /* 32 = one warp per tree, 8 = four trees per warp; 0 = default */
+    int32_t lanes_per_tree;  /* 32 = one warp per tree, 16 = two, 8 = four trees per warp; 0 = default (8) */
     int32_t hot_nodes_plus1; /* tuning: 0 = automatic; k+1 = keep the first k nodes of every tree in shared memory in az_run_simulations */
     double c_puct;           /* exploration_weight (search.py:16) */
 } az_config;

@@ -103,3 +103,45 @@ def test_masked_softmax_matches_torch(eng):
         assert torch.allclose(got[i, cols], ref, atol=1e-6, rtol=1e-5)
         assert got[i].sum().item() == pytest.approx(1.0, abs=1e-5)
         assert all(got[i, c] == 0 for c in range(7) if c not in cols)
+
+
+def test_env_step_vector_and_scalar_paths_agree(eng, oracle):
+    """16-byte-aligned batches take the 4-positions-per-thread kernel, anything else the scalar one (plus a scalar tail)."""
+    rng = np.random.RandomState(3)
+    n = 4099
+    b0 = np.zeros(n, np.uint64); b1 = np.zeros(n, np.uint64); pl = np.zeros(n, np.uint8)
+    for d in range(14):
+        r = oracle.env_step(b0, b1, pl, rng.randint(0, 7, n).astype(np.uint8))
+        b0, b1, pl = r["bb0"], r["bb1"], r["player"]
+    col = rng.randint(0, 8, n).astype(np.uint8)
+    ref = oracle.env_step(b0, b1, pl, col)
+    tb0 = torch.from_numpy(b0.view(np.int64)).cuda(); tb1 = torch.from_numpy(b1.view(np.int64)).cuda()
+    tpl = torch.from_numpy(pl).cuda(); tcol = torch.from_numpy(col).cuda()
+    for off in (0, 1, 2, 3):  # off != 0: 8-byte aligned bitboards, odd byte arrays -> scalar kernel
+        got = _np(eng.env_step(tb0[off:], tb1[off:], tpl[off:], tcol[off:]))
+        for k in ("status", "player", "legal", "ended"):
+            assert (got[k] == ref[k][off:]).all(), (off, k)
+        assert (got["bb0"].view(np.uint64) == ref["bb0"][off:]).all() and (got["reward"] == ref["reward"][off:]).all()
+        info = _np(eng.state_info(tb0[off:], tb1[off:]))
+        iref = oracle.state_info(b0[off:], b1[off:], pl[off:])
+        for k in ("legal", "ended", "reward"):
+            assert (info[k] == iref[k]).all(), (off, k)
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 129, 1000])
+def test_plane_encoder_tile_edges(eng, oracle, n):
+    from alphazero_implementation_b200.engine import LAYOUT_GRID_F32, LAYOUT_PLANES_BF16, LAYOUT_PLANES_BF16_NHWC, LAYOUT_PLANES_F32
+    from alphazero_implementation_b200.game import bitboards_to_grid
+
+    rng = np.random.RandomState(n)
+    b0 = np.zeros(n, np.uint64); b1 = np.zeros(n, np.uint64); pl = np.zeros(n, np.uint8)
+    for d in range(9):
+        r = oracle.env_step(b0, b1, pl, rng.randint(0, 7, n).astype(np.uint8))
+        b0, b1, pl = r["bb0"], r["bb1"], r["player"]
+    grids = np.stack([bitboards_to_grid(int(a), int(b)) for a, b in zip(b0, b1)]).astype(np.float32)
+    planes = np.stack([grids == -1, grids == pl[:, None, None], grids == (1 - pl)[:, None, None]], axis=1).astype(np.float32)
+    assert (eng.encode_states(b0, b1, pl, LAYOUT_GRID_F32).cpu().numpy() == grids).all()
+    assert (eng.encode_states(b0, b1, pl, LAYOUT_PLANES_F32).cpu().numpy() == planes).all()
+    assert (eng.encode_states(b0, b1, pl, LAYOUT_PLANES_BF16).float().cpu().numpy() == planes).all()
+    nhwc = eng.encode_states(b0, b1, pl, LAYOUT_PLANES_BF16_NHWC).float().cpu().numpy()
+    assert (nhwc[..., :3] == planes.transpose(0, 2, 3, 1)).all() and (nhwc[..., 3:] == 0).all()
