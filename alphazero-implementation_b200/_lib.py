@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libaz_engine.so")
-SOURCES = ["az_engine.cu"]
+SOURCES = ["az_engine.cu", "az_mlp.cu"]
 HEADERS = ["az_eval.cuh", "c4_bitboard.cuh", os.path.join("..", "..", "include", "az_engine.h")]
 
 NVCC_FLAGS = [
@@ -103,6 +103,12 @@ SIGNATURES = {
     "az_reset_stats": (I32, [P, P]),
     "az_selftest_division": (I32, [P, I64, C.c_uint64, C.POINTER(I64)]),
     "az_launch_count": (I64, [P]),
+    "az_mlp_create": (I32, [I32, C.POINTER(P)]),
+    "az_mlp_destroy": (I32, [P]),
+    "az_mlp_last_error": (C.c_char_p, [P]),
+    "az_mlp_set_weights": (I32, [P, P, P, P, P, P, P, P, P, P]),
+    "az_mlp_forward": (I32, [P, P, I64, P, P, P]),
+    "az_mlp_launch_count": (I64, [P]),
 }
 
 _lib = None

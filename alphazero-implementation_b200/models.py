@@ -226,6 +226,59 @@ def _fold_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d):
     return w * scale.view(-1, 1, 1, 1), (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
 
 
+class TensorCoreMLP:
+    """BasicNN.forward as one tcgen05 kernel (csrc/az_mlp.cu): bf16 operands, fp32 accumulation in tensor memory."""
+
+    def __init__(self, model: "BasicNN", device: torch.device):
+        import ctypes as C
+
+        from . import _lib
+
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        h = C.c_void_p()
+        rc = self.lib.az_mlp_create(self.device.index or 0, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"az_mlp_create failed ({rc}): needs an sm_100 device")
+        self.h = h
+        self._out: dict[int, tuple[Tensor, Tensor]] = {}
+        self.set_weights(model)
+
+    def set_weights(self, model: "BasicNN"):
+        f = lambda t: t.detach().to(self.device, torch.float32).contiguous()
+        ws = [f(model.shared_layers[0].weight), f(model.shared_layers[0].bias), f(model.shared_layers[2].weight),
+              f(model.shared_layers[2].bias), f(model.policy_head.weight), f(model.policy_head.bias),
+              f(model.value_head[0].weight), f(model.value_head[0].bias)]
+        rc = self.lib.az_mlp_set_weights(self.h, *[w.data_ptr() for w in ws], torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"az_mlp_set_weights failed ({rc}): {self.lib.az_mlp_last_error(self.h).decode()}")
+        torch.cuda.current_stream(self.device).synchronize()  # `ws` may be temporaries
+
+    def __call__(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x[0].numel() == 42
+        n = x.shape[0]
+        if n not in self._out:
+            self._out[n] = (torch.empty((n, 7), device=x.device), torch.empty((n, 2), device=x.device))
+        logits, values = self._out[n]
+        rc = self.lib.az_mlp_forward(self.h, x.data_ptr(), n, logits.data_ptr(), values.data_ptr(),
+                                     torch.cuda.current_stream(x.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"az_mlp_forward failed ({rc}): {self.lib.az_mlp_last_error(self.h).decode()}")
+        return logits, values
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.az_mlp_launch_count(self.h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.az_mlp_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 class InferenceNet(nn.Module):
     """Search-time form of a `Model` (the role of `get_inference_clone()`, models/base/model.py:92-96):
     eval-mode, BatchNorm folded, conv/linear weights in `dtype` (bf16 on the hot path), activations
@@ -238,10 +291,14 @@ class InferenceNet(nn.Module):
         self.kind = type(model).__name__
         self.dtype = dtype
         self.layers: list[tuple[str, Tensor, Tensor]] = []
+        self.fused = None
         if isinstance(m, BasicNN):
-            self.dtype = torch.float32
             self.input_layout = LAYOUT_GRID_F32
             self.net = m
+            if dtype == torch.bfloat16:  # hand-written tensor-core path
+                self.fused = TensorCoreMLP(m, torch.device(device))
+            else:
+                self.dtype = torch.float32
         elif isinstance(m, (CNNModel, ResNet)):
             self.input_layout = LAYOUT_PLANES_BF16 if dtype == torch.bfloat16 else LAYOUT_PLANES_F32
             self.net = self._fold(m).to(dtype).to(memory_format=torch.channels_last)
@@ -286,6 +343,8 @@ class InferenceNet(nn.Module):
 
     @torch.no_grad()
     def forward(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        if self.fused is not None:
+            return self.fused(x)
         if x.dim() == 4:
             x = x.contiguous(memory_format=torch.channels_last)
         logits, values = self.net(x.to(self.dtype))

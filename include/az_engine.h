@@ -202,6 +202,24 @@ int32_t az_selftest_division(az_engine *h, int64_t n, uint64_t seed, int64_t *mi
 /* number of kernels this engine has launched since az_create */
 int64_t az_launch_count(const az_engine *h);
 
+/* ---- fused tensor-core evaluator for the reference's BasicNN (models/games/connect4/basic.py:8-39) ----
+ * 42 -> 512 (ReLU) -> 512 (ReLU) -> {7 policy logits, 2 values (tanh)} in ONE kernel: tcgen05.mma (bf16 in, fp32
+ * accumulate in tensor memory), bias / ReLU / tanh epilogues in fp32, activations never leave the SM.
+ * az_mlp_set_weights takes fp32 DEVICE pointers in nn.Linear layout (weight [out][in]) — the analogue of
+ * `inference_model.load_state_dict(model.state_dict())` (search.py:22-25) — and repacks them as bf16 MMA operands.
+ * az_mlp_forward consumes the AZ_LAYOUT_GRID_F32 batch written by az_gather_leaves and writes logits [n][7] and
+ * values [n][2] in the form az_expand_backup reads. */
+typedef struct az_mlp az_mlp;
+int32_t az_mlp_create(int32_t device, az_mlp **out);
+int32_t az_mlp_destroy(az_mlp *m);
+const char *az_mlp_last_error(const az_mlp *m);
+int32_t az_mlp_set_weights(az_mlp *m, const float *w1 /*[512][42]*/, const float *b1, const float *w2 /*[512][512]*/,
+                           const float *b2, const float *w_policy /*[7][512]*/, const float *b_policy,
+                           const float *w_value /*[2][512]*/, const float *b_value, void *stream);
+int32_t az_mlp_forward(az_mlp *m, const float *grid /*[n][42]*/, int64_t n, float *logits /*[n][7]*/,
+                       float *values /*[n][2]*/, void *stream);
+int64_t az_mlp_launch_count(const az_mlp *m);
+
 #ifdef __cplusplus
 }
 #endif
