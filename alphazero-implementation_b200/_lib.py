@@ -108,7 +108,9 @@ SIGNATURES = {
     "az_mlp_last_error": (C.c_char_p, [P]),
     "az_mlp_set_weights": (I32, [P, P, P, P, P, P, P, P, P, P]),
     "az_mlp_forward": (I32, [P, P, I64, P, P, P]),
+    "az_mlp_forward_leaves": (I32, [P, P, P, P, P]),
     "az_mlp_launch_count": (I64, [P]),
+    "az_leaf_arrays": (I32, [P, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(I32)]),
 }
 
 _lib = None

@@ -1401,6 +1401,15 @@ int32_t az_leaf_info(az_engine *h, uint64_t *o0, uint64_t *o1, uint8_t *opl, uin
     return AZ_OK;
 }
 
+int32_t az_leaf_arrays(az_engine *h, const uint64_t **bb0, const uint64_t **bb1, const uint8_t **status, int32_t *n_active) {
+    if (!h) return AZ_E_INVALID;
+    if (bb0) *bb0 = h->a.leaf_bb0;
+    if (bb1) *bb1 = h->a.leaf_bb1;
+    if (status) *status = h->a.leaf_status;
+    if (n_active) *n_active = h->n_active;
+    return AZ_OK;
+}
+
 int32_t az_root_stats(az_engine *h, int32_t *child_N, double *child_W, float *child_P, double *root_W, int32_t *root_N,
                       uint8_t *legal, int32_t *err, void *stream) {
     if (!h) return AZ_E_INVALID;

@@ -8,9 +8,11 @@
 // apply bias + ReLU in fp32, round to bf16 and write the next layer's A operand straight into shared memory in
 // the canonical K-major no-swizzle core-matrix layout the MMA descriptors address (8 rows x 16 bytes per core
 // matrix; LBO = 128 B between K-adjacent core matrices, SBO between 8-row groups).  Weights are packed once per
-// weight update (az_mlp_set_weights) into the same canonical layout, bf16, in 64-wide K chunks, so a chunk
-// is a flat 64 KB copy into shared memory.  Only the conv/GEMM work runs on tensor cores; bias, ReLU and tanh
-// are fp32 epilogues (north_star: "uses tensor cores only for its conv/GEMM layers").
+// weight update (az_mlp_set_weights) into the same canonical layout, bf16, in 32-wide K chunks, so a chunk is a
+// flat 32 KB region that ONE thread streams into a two-stage shared-memory ring with bulk async copies
+// (cp.async.bulk + mbarrier complete_tx) while the tensor core works on the other stage; tcgen05.commit on a
+// per-stage mbarrier hands the stage back.  Only the GEMM work runs on tensor cores; bias, ReLU and tanh are
+// fp32 epilogues (north_star: "uses tensor cores only for its conv/GEMM layers").
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,21 +20,24 @@
 #include <stdlib.h>
 
 #include "../../include/az_engine.h"
+#include "c4_bitboard.cuh"
 
 namespace {
 
 constexpr int TILE_M = 128;  // positions per CTA = UMMA M
 constexpr int IN = 42;       // 6 x 7 grid
-constexpr int K1 = 64;       // IN padded to one K chunk
+constexpr int K1 = 64;       // IN padded to a multiple of the K chunk
 constexpr int HID = 512;
 constexpr int NH = 16;       // 7 logits + 2 values, padded to the smallest UMMA N for M = 128
-constexpr int KC = 64;       // K chunk staged in shared memory
+constexpr int KC = 32;       // K chunk staged in shared memory (two stages, filled by bulk async copies)
 constexpr uint32_t LBO = 128;                       // bytes between K-adjacent core matrices
 constexpr uint32_t SBO_ACT = (HID / 8) * 128;       // 8192: bytes between 8-row groups of the [128][512] activation tile
-constexpr uint32_t SBO_CHUNK = (KC / 8) * 128;      // 1024: same for any [rows][64] tile (input tile, weight chunks)
+constexpr uint32_t SBO_X = (K1 / 8) * 128;          // 1024: same for the [128][64] input tile
+constexpr uint32_t SBO_CHUNK = (KC / 8) * 128;      // 512: same for a [rows][32] weight chunk
 constexpr uint32_t ACT_BYTES = TILE_M * HID * 2;    // 131072
-constexpr uint32_t WBUF_BYTES = HID * KC * 2;       // 65536
-constexpr uint32_t SMEM_BYTES = ACT_BYTES + WBUF_BYTES + 64;
+constexpr uint32_t STAGE_BYTES = HID * KC * 2;      // 32768
+constexpr uint32_t BIAS_BYTES = 2 * HID * 4;          // both hidden layers' biases, fp32
+constexpr uint32_t SMEM_BYTES = ACT_BYTES + 2 * STAGE_BYTES + BIAS_BYTES + 64;
 constexpr uint32_t W1_ELEMS = HID * K1, W2_ELEMS = HID * HID, WH_ELEMS = NH * HID;
 
 __host__ __device__ inline uint32_t canon(uint32_t r, uint32_t k, uint32_t sbo) {  // byte offset of element (r, k)
@@ -106,15 +111,46 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&p);
 }
 
-// flat copy of a packed weight chunk into the shared-memory staging buffer
-__device__ __forceinline__ void load_chunk(uint8_t *wbuf, const uint8_t *__restrict__ src, uint32_t bytes) {
-    const uint4 *s = reinterpret_cast<const uint4 *>(src);
-    uint4 *d = reinterpret_cast<uint4 *>(wbuf);
-    for (uint32_t i = threadIdx.x; i < bytes / 16; i += TILE_M) d[i] = __ldg(s + i);
+// ---- weight pipeline (thread 0 only): bulk async copies (TMA, 1-D) fill two shared-memory stages; an mbarrier
+// per stage reports the bytes landed ("full"); tcgen05.commit reports when the MMAs that read a stage are done ("empty").
+struct Pipe {
+    uint32_t full[2], empty[2], done;  // shared-memory addresses of the mbarriers
+    uint32_t stage[2];                 // shared-memory addresses of the two stages
+    uint32_t g;                        // chunks issued so far in this kernel (stage = g & 1, use = g >> 1)
+};
+
+__device__ __forceinline__ void pipe_load(const Pipe &p, uint32_t gj, const uint8_t *src, uint32_t bytes) {
+    const uint32_t st = gj & 1u;
+    if (gj >= 2) mbar_wait(p.empty[st], ((gj >> 1) - 1u) & 1u);  // the MMAs of the previous use have finished reading
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(p.full[st]), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(p.stage[st]),
+                 "l"(src), "r"(bytes), "r"(p.full[st])
+                 : "memory");
+}
+
+// One layer: D[128 x N] (+)= A[128 x K] . W[N x K]^T with W streamed in `nchunks` chunks of `chunk_bytes`.
+// `ksteps` MMAs of K = 16 per chunk and N half.  The first two chunks must already be in flight (prefetched).
+__device__ __forceinline__ void pipe_layer(Pipe &p, const uint8_t *src, uint32_t nchunks, uint32_t chunk_bytes, uint32_t ksteps,
+                                           uint32_t a_addr, uint32_t a_sbo, uint32_t n_halves, uint32_t idesc, uint32_t tmem_base) {
+    for (uint32_t i = 0; i < nchunks; ++i) {
+        const uint32_t gi = p.g + i, st = gi & 1u;
+        mbar_wait(p.full[st], (gi >> 1) & 1u);
+        tc_fence_after();
+        for (uint32_t ks = 0; ks < ksteps; ++ks)
+            for (uint32_t half = 0; half < n_halves; ++half)
+                umma(tmem_base + half * 256, smem_desc(a_addr + (i * ksteps + ks) * 2 * LBO, a_sbo),
+                     // inside a stage: [rows][32] sub-chunks back to back; K step ks -> sub-chunk ks / 2, half (ks & 1) of it
+                     smem_desc(p.stage[st] + half * (256 / 8) * SBO_CHUNK + (ks >> 1) * (NH * KC * 2) + (ks & 1u) * 2 * LBO, SBO_CHUNK),
+                     idesc, (i | ks) > 0);
+        umma_commit(p.empty[st]);
+        if (i + 2 < nchunks) pipe_load(p, gi + 2, src + (size_t)(i + 2) * chunk_bytes, chunk_bytes);
+    }
+    umma_commit(p.done);
+    p.g += nchunks;
 }
 
 // accumulator (128 x 512 fp32 in TMEM) -> bias + ReLU -> bf16 -> canonical [128][512] A operand in shared memory
-__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_base, uint8_t *act, const float *__restrict__ bias) {
+__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_base, uint8_t *act, const float *bias /* shared memory */) {
     const uint32_t row = threadIdx.x;                                  // lane of TMEM = row of the tile
     const uint32_t taddr = tmem_base + ((row & ~31u) << 16);          // this warp's 32 lanes
     uint8_t *rowp = act + (row >> 3) * SBO_ACT + (row & 7) * 16;
@@ -126,104 +162,130 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_base, uint8_t *act
         for (int q = 0; q < 4; ++q) {
             float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(v[q * 8 + j]) + __ldg(bias + cb * 32 + q * 8 + j), 0.0f);
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(v[q * 8 + j]) + bias[cb * 32 + q * 8 + j], 0.0f);
             *reinterpret_cast<uint4 *>(rowp + (cb * 4 + q) * LBO) =
                 make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
         }
     }
 }
 
+// column-major bitboard (bit = 7*col + row) -> row-major 42-bit mask (bit = 7*row + col): the element order of state.grid
+__device__ __forceinline__ uint64_t row_major42(uint64_t bb) {
+    uint64_t m = 0;
+#pragma unroll
+    for (int r = 0; r < c4::H; ++r) m |= (((((bb >> r) & 0x40810204081ull) * c4::LEGAL_MAGIC) >> 36) & 0x7Full) << (7 * r);
+    return m;
+}
+
+// FROM_LEAVES: the input rows are built in the kernel from the engine's leaf bitboards (the leaf gather fused in);
+// otherwise they are read from an AZ_LAYOUT_GRID_F32 batch.
+template <bool FROM_LEAVES>
 __global__ void __launch_bounds__(TILE_M, 1)
-k_mlp_fused(const float *__restrict__ grid, long long n, const uint8_t *__restrict__ w1p, const float *__restrict__ b1,
+k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1,
+            const uint8_t *__restrict__ leaf_status, long long n, const uint8_t *__restrict__ w1p, const float *__restrict__ b1,
             const uint8_t *__restrict__ w2p, const float *__restrict__ b2, const uint8_t *__restrict__ whp,
             const float *__restrict__ bh, float *__restrict__ logits, float *__restrict__ values) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *act = smem;
-    uint8_t *wbuf = smem + ACT_BYTES;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + ACT_BYTES + WBUF_BYTES);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + ACT_BYTES + WBUF_BYTES + 16);
+    float *s_bias = reinterpret_cast<float *>(smem + ACT_BYTES + 2 * STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ACT_BYTES + 2 * STAGE_BYTES + BIAS_BYTES);  // full0 full1 empty0 empty1 done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + ACT_BYTES + 2 * STAGE_BYTES + BIAS_BYTES + 48);
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const long long row0 = (long long)blockIdx.x * TILE_M;
-    const uint32_t bar_addr = smem_u32(bar);
+    Pipe p;
+    p.full[0] = smem_u32(bars + 0); p.full[1] = smem_u32(bars + 1);
+    p.empty[0] = smem_u32(bars + 2); p.empty[1] = smem_u32(bars + 3);
+    p.done = smem_u32(bars + 4);
+    p.stage[0] = smem_u32(smem + ACT_BYTES); p.stage[1] = p.stage[0] + STAGE_BYTES;
+    p.g = 0;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+#pragma unroll
+        for (int i = 0; i < 5; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        pipe_load(p, 0, w1p, STAGE_BYTES);  // layer-1 weights: 2 chunks of [512][32]
+        pipe_load(p, 1, w1p + STAGE_BYTES, STAGE_BYTES);
     }
     // input tile: raw grid values (-1 / 0 / 1, exact in bf16) as a [128][64] K-major tile, zero padded
-    for (uint32_t i = tid; i < TILE_M * K1 * 2 / 16; i += TILE_M) reinterpret_cast<uint4 *>(act)[i] = make_uint4(0, 0, 0, 0);
-    load_chunk(wbuf, w1p, W1_ELEMS * 2);
-    __syncthreads();
-    for (uint32_t e = tid; e < TILE_M * IN; e += TILE_M) {
-        const uint32_t r = e / IN, k = e - r * IN;
-        if (row0 + r < n) *reinterpret_cast<__nv_bfloat16 *>(act + canon(r, k, SBO_CHUNK)) = __float2bfloat16_rn(__ldg(grid + (row0 + r) * IN + k));
+    for (uint32_t i = tid; i < 2 * HID; i += TILE_M) s_bias[i] = i < HID ? __ldg(b1 + i) : __ldg(b2 + i - HID);
+    if (FROM_LEAVES) {
+        // thread = row: 42 grid values from the leaf's bitboards, written as 8 x 16-byte core-matrix rows
+        const long long row = row0 + tid;
+        uint64_t m0 = 0, m1 = 0;
+        bool live = false;
+        if (row < n) {
+            live = leaf_status[row] == AZ_LEAF_EVAL;
+            m0 = row_major42(leaf_bb0[row]);
+            m1 = row_major42(leaf_bb1[row]);
+        }
+        uint8_t *rowp = act + (tid >> 3) * SBO_X + (tid & 7) * 16;
+#pragma unroll
+        for (int kg = 0; kg < K1 / 8; ++kg) {
+            uint32_t w[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                uint32_t pair = 0;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int e = kg * 8 + h * 2 + q;
+                    uint32_t v = 0;
+                    if (e < IN) v = ((m0 >> e) & 1ull) ? 0x0000u : (((m1 >> e) & 1ull) ? 0x3F80u : 0xBF80u);  // 0, +1, -1 in bf16
+                    pair |= v << (16 * q);
+                }
+                w[h] = live ? pair : 0u;
+            }
+            *reinterpret_cast<uint4 *>(rowp + kg * LBO) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    } else {
+        for (uint32_t i = tid; i < TILE_M * K1 * 2 / 16; i += TILE_M) reinterpret_cast<uint4 *>(act)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+#pragma unroll 6
+        for (uint32_t e = tid; e < TILE_M * IN; e += TILE_M) {
+            const uint32_t r = e / IN, k = e - r * IN;
+            if (row0 + r < n) *reinterpret_cast<__nv_bfloat16 *>(act + canon(r, k, SBO_X)) = __float2bfloat16_rn(__ldg(grid + (row0 + r) * IN + k));
+        }
     }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t act_addr = smem_u32(act), wbuf_addr = smem_u32(wbuf);
-    uint32_t phase = 0;
+    const uint32_t act_addr = smem_u32(act);
 
     // ---- layer 1: [128 x 64] . [512 x 64]^T
     if (tid == 0) {
-#pragma unroll
-        for (int ks = 0; ks < K1 / 16; ++ks)
-#pragma unroll
-            for (int half = 0; half < 2; ++half)
-                umma(tmem_base + half * 256, smem_desc(act_addr + ks * 2 * LBO, SBO_CHUNK),
-                     smem_desc(wbuf_addr + half * (256 / 8) * SBO_CHUNK + ks * 2 * LBO, SBO_CHUNK), instr_desc(128, 256), ks > 0);
-        umma_commit(bar_addr);
+        pipe_layer(p, w1p, K1 / KC, STAGE_BYTES, KC / 16, act_addr, SBO_X, 2, instr_desc(128, 256), tmem_base);
+        pipe_load(p, p.g, w2p, STAGE_BYTES);  // prefetch layer 2 behind the epilogue
+        pipe_load(p, p.g + 1, w2p + STAGE_BYTES, STAGE_BYTES);
     }
-    mbar_wait(bar_addr, phase);
-    phase ^= 1;
+    mbar_wait(p.done, 0);
     tc_fence_after();
-    load_chunk(wbuf, w2p, WBUF_BYTES);  // first K chunk of layer 2 (layer-1 MMAs are done with wbuf)
-    epilogue_hidden(tmem_base, act, b1);
-
-    // ---- layer 2: [128 x 512] . [512 x 512]^T, K in 8 chunks of 64
-    for (int kc = 0; kc < HID / KC; ++kc) {
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (tid == 0) {
-#pragma unroll
-            for (int ks = 0; ks < KC / 16; ++ks)
-#pragma unroll
-                for (int half = 0; half < 2; ++half)
-                    umma(tmem_base + half * 256, smem_desc(act_addr + (kc * 8 + ks * 2) * LBO, SBO_ACT),
-                         smem_desc(wbuf_addr + half * (256 / 8) * SBO_CHUNK + ks * 2 * LBO, SBO_CHUNK), instr_desc(128, 256),
-                         (kc | ks) > 0);
-            umma_commit(bar_addr);
-        }
-        mbar_wait(bar_addr, phase);
-        phase ^= 1;
-        tc_fence_after();
-        if (kc + 1 < HID / KC) load_chunk(wbuf, w2p + (size_t)(kc + 1) * WBUF_BYTES, WBUF_BYTES);
-        else load_chunk(wbuf, whp, WH_ELEMS * 2);  // head weights: 8 chunks of [16][64], 16 KB in all
-    }
-    epilogue_hidden(tmem_base, act, b2);
-
-    // ---- heads: [128 x 512] . [16 x 512]^T
+    epilogue_hidden(tmem_base, act, s_bias);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+
+    // ---- layer 2: [128 x 512] . [512 x 512]^T, K in 16 chunks of 32
     if (tid == 0) {
-        for (int kc = 0; kc < HID / KC; ++kc)
-#pragma unroll
-            for (int ks = 0; ks < KC / 16; ++ks)
-                umma(tmem_base, smem_desc(act_addr + (kc * 8 + ks * 2) * LBO, SBO_ACT),
-                     smem_desc(wbuf_addr + kc * (NH / 8) * SBO_CHUNK + ks * 2 * LBO, SBO_CHUNK), instr_desc(128, NH), (kc | ks) > 0);
-        umma_commit(bar_addr);
+        pipe_layer(p, w2p, HID / KC, STAGE_BYTES, KC / 16, act_addr, SBO_ACT, 2, instr_desc(128, 256), tmem_base);
+        pipe_load(p, p.g, whp, WH_ELEMS * 2);  // head weights: one 16 KB "chunk" of 16 x [16][32]
     }
-    mbar_wait(bar_addr, phase);
+    mbar_wait(p.done, 1);
+    tc_fence_after();
+    epilogue_hidden(tmem_base, act, s_bias + HID);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- heads: [128 x 512] . [16 x 512]^T
+    if (tid == 0) pipe_layer(p, whp, 1, WH_ELEMS * 2, HID / 16, act_addr, SBO_ACT, 1, instr_desc(128, NH), tmem_base);
+    mbar_wait(p.done, 0);
     tc_fence_after();
     {
         uint32_t v[16];
@@ -287,7 +349,8 @@ int32_t az_mlp_create(int32_t device, az_mlp **out) {
     AL(w1p, W1_ELEMS * 2); AL(w2p, W2_ELEMS * 2); AL(whp, WH_ELEMS * 2);
     AL(b1, HID * 4); AL(b2, HID * 4); AL(bh, NH * 4); AL(wh_tmp, 9 * HID * 4);
 #undef AL
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) {
         cudaGetLastError();
         free(m);
@@ -338,7 +401,29 @@ int32_t az_mlp_forward(az_mlp *m, const float *grid, int64_t n, float *logits, f
     if (n == 0) return AZ_OK;
     cudaSetDevice(m->device);
     const int blocks = (int)((n + TILE_M - 1) / TILE_M);
-    k_mlp_fused<<<blocks, TILE_M, SMEM_BYTES, (cudaStream_t)stream>>>(grid, n, m->w1p, m->b1, m->w2p, m->b2, m->whp, m->bh, logits, values);
+    k_mlp_fused<false><<<blocks, TILE_M, SMEM_BYTES, (cudaStream_t)stream>>>(grid, nullptr, nullptr, nullptr, n, m->w1p, m->b1, m->w2p, m->b2,
+                                                                             m->whp, m->bh, logits, values);
+    m->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(m->err, sizeof m->err, "k_mlp_fused launch: %s", cudaGetErrorString(e));
+        return AZ_E_CUDA;
+    }
+    return AZ_OK;
+}
+
+/* same, with the leaf gather fused in: rows are the leaves chosen by the engine's last az_select_leaves
+ * (row i = slot i; rows of terminal / idle slots are zero), so no az_gather_leaves launch is needed */
+int32_t az_mlp_forward_leaves(az_mlp *m, az_engine *engine, float *logits, float *values, void *stream) {
+    if (!m || !engine || !logits || !values) return AZ_E_INVALID;
+    const uint64_t *bb0 = nullptr, *bb1 = nullptr;
+    const uint8_t *status = nullptr;
+    int32_t n = 0;
+    if (az_leaf_arrays(engine, &bb0, &bb1, &status, &n) != AZ_OK || n <= 0) return AZ_E_INVALID;
+    cudaSetDevice(m->device);
+    const int blocks = (n + TILE_M - 1) / TILE_M;
+    k_mlp_fused<true><<<blocks, TILE_M, SMEM_BYTES, (cudaStream_t)stream>>>(nullptr, bb0, bb1, status, n, m->w1p, m->b1, m->w2p, m->b2, m->whp,
+                                                                            m->bh, logits, values);
     m->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -266,6 +266,19 @@ class TensorCoreMLP:
             raise RuntimeError(f"az_mlp_forward failed ({rc}): {self.lib.az_mlp_last_error(self.h).decode()}")
         return logits, values
 
+    def forward_leaves(self, engine) -> tuple[Tensor, Tensor]:
+        """Evaluate the leaves chosen by `engine.select_leaves()` directly from the engine's leaf bitboards (the gather is
+        fused into the kernel); row i = slot i."""
+        n = engine.n_active
+        if n not in self._out:
+            self._out[n] = (torch.empty((n, 7), device=self.device), torch.empty((n, 2), device=self.device))
+        logits, values = self._out[n]
+        rc = self.lib.az_mlp_forward_leaves(self.h, engine.h, logits.data_ptr(), values.data_ptr(),
+                                            torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"az_mlp_forward_leaves failed ({rc}): {self.lib.az_mlp_last_error(self.h).decode()}")
+        return logits, values
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.az_mlp_launch_count(self.h))

@@ -147,6 +147,10 @@ int32_t az_expand_backup(az_engine *h, const float *policy /*[E][7]*/, const flo
 int32_t az_leaf_info(az_engine *h, uint64_t *out_bb0, uint64_t *out_bb1, uint8_t *out_player, uint8_t *out_legal,
                      uint8_t *out_status, void *stream);
 
+/* engine-owned device arrays describing the leaves of the last az_select_leaves (borrowed; valid until az_destroy):
+ * lets another kernel consume the leaves without a gather launch (see az_mlp_forward_leaves) */
+int32_t az_leaf_arrays(az_engine *h, const uint64_t **bb0, const uint64_t **bb1, const uint8_t **status, int32_t *n_active);
+
 /* ---- results ---- */
 /* root statistics of every active tree, per column (0 on illegal columns):
  * child visit counts (Node.improved_policy = child_N / (root_N - 1), node.py:23-29), child value sums,
@@ -218,6 +222,8 @@ int32_t az_mlp_set_weights(az_mlp *m, const float *w1 /*[512][42]*/, const float
                            const float *w_value /*[2][512]*/, const float *b_value, void *stream);
 int32_t az_mlp_forward(az_mlp *m, const float *grid /*[n][42]*/, int64_t n, float *logits /*[n][7]*/,
                        float *values /*[n][2]*/, void *stream);
+/* the same with the leaf gather fused in: row i = the leaf of slot i chosen by the last az_select_leaves on `engine` */
+int32_t az_mlp_forward_leaves(az_mlp *m, az_engine *engine, float *logits /*[E][7]*/, float *values /*[E][2]*/, void *stream);
 int64_t az_mlp_launch_count(const az_mlp *m);
 
 #ifdef __cplusplus

@@ -9,14 +9,18 @@ E = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 nets = sys.argv[2:] or ["resnet4x64", "resnet2x64", "resnet9x128", "basic", "cnn"]
 torch.backends.cudnn.benchmark = True
 for name in nets:
-    if name == "basic":
+    kw = {}
+    if name == "basic_tc":  # BasicNN through the hand-written tcgen05 kernel
+        model = az.BasicNN()
+        kw = dict(inference_dtype=torch.bfloat16)
+    elif name == "basic":
         model = az.BasicNN()
     elif name == "cnn":
         model = az.CNNModel()
     else:
         b, c = name.replace("resnet", "").split("x")
         model = az.ResNet(int(b), int(c))
-    search = az.AlphaZeroSearch(model=model, num_simulations=64, use_cuda_graph=False)
+    search = az.AlphaZeroSearch(model=model, num_simulations=64, use_cuda_graph=False, **kw)
     eng = search.engine_for(E)
     eng.reset_games()
     net = search._net
@@ -25,8 +29,11 @@ for name in nets:
     tot = [0.0] * 4
     for it in range(40):
         ev[0].record(); eng.select_leaves()
-        ev[1].record(); eng.gather_leaves(net.input_layout, x)
-        ev[2].record(); logits, values = net(x)
+        ev[1].record()
+        if net.fused is None:
+            eng.gather_leaves(net.input_layout, x)
+        ev[2].record()
+        logits, values = net.fused.forward_leaves(eng) if net.fused is not None else net(x)
         ev[3].record(); eng.expand_backup(logits, values, POLICY_LOGITS)
         ev[4].record()
         torch.cuda.synchronize()

@@ -76,3 +76,27 @@ def test_fused_mlp_in_the_search_loop():
     nodes = [az.Node(r) for r in roots]
     s.run_simulations(nodes)
     assert [ch.visit_count for ch in nodes[0].children.values()] == out[1]
+
+
+def test_fused_leaf_gather_equals_separate_gather():
+    """az_mlp_forward_leaves (rows built from the leaf bitboards inside the kernel) == az_gather_leaves + az_mlp_forward,
+    and rows of terminal / idle slots behave like all-zero inputs."""
+    torch.manual_seed(5)
+    m = az.BasicNN().cuda().eval()
+    n = 3000
+    eng = az.Engine(num_games=n, num_simulations=64)
+    eng.reset_games()
+    u = torch.from_numpy(np.random.RandomState(1).random_sample(n)).cuda()
+    for _ in range(14):  # deep enough that some leaves are terminal
+        eng.run_simulations(40, 2)
+        eng.sample_moves(u)
+    eng.run_simulations(40, 2)
+    eng.select_leaves()
+    status = eng.leaf_info()["status"]
+    assert (status == 1).any() and (status == 0).any()
+    mlp = TensorCoreMLP(m, torch.device("cuda", torch.cuda.current_device()))
+    a_l, a_v = [t.clone() for t in mlp(eng.gather_leaves(LAYOUT_GRID_F32))]
+    b_l, b_v = mlp.forward_leaves(eng)
+    torch.cuda.synchronize()
+    assert torch.equal(a_l, b_l) and torch.equal(a_v, b_v)
+    eng.close()
