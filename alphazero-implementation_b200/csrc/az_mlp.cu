@@ -29,15 +29,16 @@ constexpr int IN = 42;       // 6 x 7 grid
 constexpr int K1 = 64;       // IN padded to a multiple of the K chunk
 constexpr int HID = 512;
 constexpr int NH = 16;       // 7 logits + 2 values, padded to the smallest UMMA N for M = 128
-constexpr int KC = 32;       // K chunk staged in shared memory (two stages, filled by bulk async copies)
+constexpr int KC = 32;       // K chunk staged in shared memory (two MMA K steps)
+constexpr int NS = 2;        // stages of the weight ring, filled by bulk async copies (KC = 16 x 4 stages measured slower)
 constexpr uint32_t LBO = 128;                       // bytes between K-adjacent core matrices
 constexpr uint32_t SBO_ACT = (HID / 8) * 128;       // 8192: bytes between 8-row groups of the [128][512] activation tile
 constexpr uint32_t SBO_X = (K1 / 8) * 128;          // 1024: same for the [128][64] input tile
-constexpr uint32_t SBO_CHUNK = (KC / 8) * 128;      // 512: same for a [rows][32] weight chunk
+constexpr uint32_t SBO_CHUNK = (KC / 8) * 128;      // same for a [rows][KC] weight chunk
 constexpr uint32_t ACT_BYTES = TILE_M * HID * 2;    // 131072
 constexpr uint32_t STAGE_BYTES = HID * KC * 2;      // 32768
 constexpr uint32_t BIAS_BYTES = 2 * HID * 4;          // both hidden layers' biases, fp32
-constexpr uint32_t SMEM_BYTES = ACT_BYTES + 2 * STAGE_BYTES + BIAS_BYTES + 64;
+constexpr uint32_t SMEM_BYTES = ACT_BYTES + NS * STAGE_BYTES + BIAS_BYTES + (2 * NS + 1) * 8 + 16;
 constexpr uint32_t W1_ELEMS = HID * K1, W2_ELEMS = HID * HID, WH_ELEMS = NH * HID;
 
 __host__ __device__ inline uint32_t canon(uint32_t r, uint32_t k, uint32_t sbo) {  // byte offset of element (r, k)
@@ -114,14 +115,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // ---- weight pipeline (thread 0 only): bulk async copies (TMA, 1-D) fill two shared-memory stages; an mbarrier
 // per stage reports the bytes landed ("full"); tcgen05.commit reports when the MMAs that read a stage are done ("empty").
 struct Pipe {
-    uint32_t full[2], empty[2], done;  // shared-memory addresses of the mbarriers
-    uint32_t stage[2];                 // shared-memory addresses of the two stages
-    uint32_t g;                        // chunks issued so far in this kernel (stage = g & 1, use = g >> 1)
+    uint32_t full[NS], empty[NS], done;  // shared-memory addresses of the mbarriers
+    uint32_t stage[NS];                  // shared-memory addresses of the stages
+    uint32_t g;                          // chunks consumed so far in this kernel (stage = g % NS, use = g / NS)
 };
 
 __device__ __forceinline__ void pipe_load(const Pipe &p, uint32_t gj, const uint8_t *src, uint32_t bytes) {
-    const uint32_t st = gj & 1u;
-    if (gj >= 2) mbar_wait(p.empty[st], ((gj >> 1) - 1u) & 1u);  // the MMAs of the previous use have finished reading
+    const uint32_t st = gj % NS;
+    if (gj >= NS) mbar_wait(p.empty[st], ((gj / NS) - 1u) & 1u);  // the MMAs of the previous use have finished reading
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(p.full[st]), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(p.stage[st]),
                  "l"(src), "r"(bytes), "r"(p.full[st])
@@ -129,21 +130,22 @@ __device__ __forceinline__ void pipe_load(const Pipe &p, uint32_t gj, const uint
 }
 
 // One layer: D[128 x N] (+)= A[128 x K] . W[N x K]^T with W streamed in `nchunks` chunks of `chunk_bytes`.
-// `ksteps` MMAs of K = 16 per chunk and N half.  The first two chunks must already be in flight (prefetched).
+// `ksteps` MMAs of K = 16 per chunk and N half.  The first min(NS, nchunks) chunks must already be in flight.
 __device__ __forceinline__ void pipe_layer(Pipe &p, const uint8_t *src, uint32_t nchunks, uint32_t chunk_bytes, uint32_t ksteps,
                                            uint32_t a_addr, uint32_t a_sbo, uint32_t n_halves, uint32_t idesc, uint32_t tmem_base) {
     for (uint32_t i = 0; i < nchunks; ++i) {
-        const uint32_t gi = p.g + i, st = gi & 1u;
-        mbar_wait(p.full[st], (gi >> 1) & 1u);
+        const uint32_t gi = p.g + i, st = gi % NS;
+        mbar_wait(p.full[st], (gi / NS) & 1u);
         tc_fence_after();
         for (uint32_t ks = 0; ks < ksteps; ++ks)
             for (uint32_t half = 0; half < n_halves; ++half)
                 umma(tmem_base + half * 256, smem_desc(a_addr + (i * ksteps + ks) * 2 * LBO, a_sbo),
-                     // inside a stage: [rows][32] sub-chunks back to back; K step ks -> sub-chunk ks / 2, half (ks & 1) of it
-                     smem_desc(p.stage[st] + half * (256 / 8) * SBO_CHUNK + (ks >> 1) * (NH * KC * 2) + (ks & 1u) * 2 * LBO, SBO_CHUNK),
+                     // inside a stage: [rows][KC] sub-chunks back to back; K step ks -> sub-chunk ks / (KC/16), part ks % (KC/16)
+                     smem_desc(p.stage[st] + half * (256 / 8) * SBO_CHUNK + (ks / (KC / 16)) * (NH * KC * 2) + (ks % (KC / 16)) * 2 * LBO,
+                               SBO_CHUNK),
                      idesc, (i | ks) > 0);
         umma_commit(p.empty[st]);
-        if (i + 2 < nchunks) pipe_load(p, gi + 2, src + (size_t)(i + 2) * chunk_bytes, chunk_bytes);
+        if (i + NS < nchunks) pipe_load(p, gi + NS, src + (size_t)(i + NS) * chunk_bytes, chunk_bytes);
     }
     umma_commit(p.done);
     p.g += nchunks;
@@ -187,16 +189,19 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
             const float *__restrict__ bh, float *__restrict__ logits, float *__restrict__ values) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *act = smem;
-    float *s_bias = reinterpret_cast<float *>(smem + ACT_BYTES + 2 * STAGE_BYTES);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ACT_BYTES + 2 * STAGE_BYTES + BIAS_BYTES);  // full0 full1 empty0 empty1 done
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + ACT_BYTES + 2 * STAGE_BYTES + BIAS_BYTES + 48);
+    float *s_bias = reinterpret_cast<float *>(smem + ACT_BYTES + NS * STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ACT_BYTES + NS * STAGE_BYTES + BIAS_BYTES);  // full[NS] empty[NS] done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + ACT_BYTES + NS * STAGE_BYTES + BIAS_BYTES + (2 * NS + 1) * 8);
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const long long row0 = (long long)blockIdx.x * TILE_M;
     Pipe p;
-    p.full[0] = smem_u32(bars + 0); p.full[1] = smem_u32(bars + 1);
-    p.empty[0] = smem_u32(bars + 2); p.empty[1] = smem_u32(bars + 3);
-    p.done = smem_u32(bars + 4);
-    p.stage[0] = smem_u32(smem + ACT_BYTES); p.stage[1] = p.stage[0] + STAGE_BYTES;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        p.full[i] = smem_u32(bars + i);
+        p.empty[i] = smem_u32(bars + NS + i);
+        p.stage[i] = smem_u32(smem + ACT_BYTES) + i * STAGE_BYTES;
+    }
+    p.done = smem_u32(bars + 2 * NS);
     p.g = 0;
 
     if (warp == 0) {
@@ -205,10 +210,9 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
     }
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
+        for (int i = 0; i < 2 * NS + 1; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        pipe_load(p, 0, w1p, STAGE_BYTES);  // layer-1 weights: 2 chunks of [512][32]
-        pipe_load(p, 1, w1p + STAGE_BYTES, STAGE_BYTES);
+        for (uint32_t i = 0; i < K1 / KC && i < NS; ++i) pipe_load(p, i, w1p + (size_t)i * STAGE_BYTES, STAGE_BYTES);  // layer-1 weights
     }
     // input tile: raw grid values (-1 / 0 / 1, exact in bf16) as a [128][64] K-major tile, zero padded
     for (uint32_t i = tid; i < 2 * HID; i += TILE_M) s_bias[i] = i < HID ? __ldg(b1 + i) : __ldg(b2 + i - HID);
@@ -259,8 +263,7 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
     // ---- layer 1: [128 x 64] . [512 x 64]^T
     if (tid == 0) {
         pipe_layer(p, w1p, K1 / KC, STAGE_BYTES, KC / 16, act_addr, SBO_X, 2, instr_desc(128, 256), tmem_base);
-        pipe_load(p, p.g, w2p, STAGE_BYTES);  // prefetch layer 2 behind the epilogue
-        pipe_load(p, p.g + 1, w2p + STAGE_BYTES, STAGE_BYTES);
+        for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w2p + (size_t)i * STAGE_BYTES, STAGE_BYTES);  // prefetch layer 2 behind the epilogue
     }
     mbar_wait(p.done, 0);
     tc_fence_after();
@@ -270,10 +273,10 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
     __syncthreads();
     tc_fence_after();
 
-    // ---- layer 2: [128 x 512] . [512 x 512]^T, K in 16 chunks of 32
+    // ---- layer 2: [128 x 512] . [512 x 512]^T, K in chunks of KC
     if (tid == 0) {
         pipe_layer(p, w2p, HID / KC, STAGE_BYTES, KC / 16, act_addr, SBO_ACT, 2, instr_desc(128, 256), tmem_base);
-        pipe_load(p, p.g, whp, WH_ELEMS * 2);  // head weights: one 16 KB "chunk" of 16 x [16][32]
+        pipe_load(p, p.g, whp, WH_ELEMS * 2);  // head weights: one 16 KB "chunk" of [16][KC] sub-chunks
     }
     mbar_wait(p.done, 1);
     tc_fence_after();

@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--hot-nodes", type=int, default=None, help="nodes per tree kept in shared memory by the fused kernel (default: automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--net", default="resnet4x64", help="network-in-the-loop side measurement: resnetBxC | basic | none")
+    ap.add_argument("--net", default="basic_tc,resnet4x64", help="network-in-the-loop side measurements, comma separated: basic_tc | basic | resnetBxC | none")
     ap.add_argument("--net-games", type=int, default=16384)
     ap.add_argument("--net-sims", type=int, default=800)
     ap.add_argument("--net-steps", type=int, default=2)
@@ -166,47 +166,56 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------------------------------
 def net_in_loop(args, device_index: int, peaks: dict):
-    """Side measurement (BASELINE configs[2]): self-play with a bf16 ResNet-style net in the loop."""
+    """Side measurements with a network in the loop (BASELINE configs[2]): self-play move steps of E games x S sims, one
+    evaluator call per simulation step.  `resnetBxC`: bf16 ResNet-style net, conv/linear layers = cuDNN/cuBLAS tensor-core
+    GEMMs.  `basic_tc`: the reference's BasicNN on the hand-written tcgen05 kernel (csrc/az_mlp.cu, leaf gather fused)."""
     import torch
 
     import alphazero_implementation_b200 as az
 
-    if args.net == "none":
-        return None
-    if args.net == "basic":
-        model, name, flops = az.BasicNN(), "BasicNN", 577_000
-    else:
-        b, c = args.net.replace("resnet", "").split("x")
-        model = az.ResNet(num_res_blocks=int(b), num_channels=int(c))
-        name, flops = f"ResNet {b}x{c}", model.flops_per_position()
-    E, S = args.net_games, args.net_sims
-    torch.manual_seed(0)
-    search = az.AlphaZeroSearch(model=model, num_simulations=S, device=device_index)
-    eng = search.engine_for(E)
-    eng.reset_games()
-    g = torch.Generator(device="cpu").manual_seed(1)
-    u = torch.rand((args.net_steps + 1, E), dtype=torch.float64, generator=g).to(eng.device)
-    search.simulate(eng)  # warm-up move step (includes graph capture)
-    eng.sample_moves(u[0])
-    torch.cuda.synchronize()
-    st0 = eng.stats()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(args.net_steps):
-        search.simulate(eng)
-        eng.sample_moves(u[i + 1])
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
-    st = diff(st0, eng.stats())
-    eng.drain_episodes()
-    sims_s = st["simulations"] / ms * 1e3
-    evals_s = E * S * args.net_steps / ms * 1e3  # every slot occupies a batch row each simulation
-    return {"workload": f"connect4_selfplay_{name.replace(' ', '')}_bf16_{E}x{S}", "net": name, "dtype": "bf16", "num_games": E,
-            "num_simulations": S, "move_steps": args.net_steps, "sims_per_s": sims_s, "ms_per_sim_step": ms / (args.net_steps * S),
-            "flops_per_position": flops, "tensor_tflops": evals_s * flops / 1e12,
-            "tensor_pipe_frac_of_measured_bf16": evals_s * flops / 1e12 / peaks["bf16_tflops"],
-            "leaf_eval_fraction": st["evaluations"] / max(1, st["simulations"])}
+    out = []
+    for spec in [s for s in args.net.split(",") if s and s != "none"]:
+        kw = {}
+        if spec == "basic_tc":
+            model, name, flops, kw = az.BasicNN(), "BasicNN (tcgen05 fused MLP, bf16)", 577_024, dict(inference_dtype=torch.bfloat16)
+        elif spec == "basic":
+            model, name, flops = az.BasicNN(), "BasicNN (fp32, cuBLAS)", 577_024
+        else:
+            b, c = spec.replace("resnet", "").split("x")
+            model = az.ResNet(num_res_blocks=int(b), num_channels=int(c))
+            name, flops = f"ResNet {b}x{c} (bf16, cuDNN)", model.flops_per_position()
+        E, S = args.net_games, args.net_sims
+        torch.manual_seed(0)
+        search = az.AlphaZeroSearch(model=model, num_simulations=S, device=device_index, **kw)
+        eng = search.engine_for(E)
+        eng.reset_games()
+        g = torch.Generator(device="cpu").manual_seed(1)
+        u = torch.rand((args.net_steps + 1, E), dtype=torch.float64, generator=g).to(eng.device)
+        search.simulate(eng)  # warm-up move step (includes graph capture)
+        eng.sample_moves(u[0])
+        torch.cuda.synchronize()
+        st0 = eng.stats()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(args.net_steps):
+            search.simulate(eng)
+            eng.sample_moves(u[i + 1])
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        st = diff(st0, eng.stats())
+        eng.drain_episodes()
+        sims_s = st["simulations"] / ms * 1e3
+        evals_s = E * S * args.net_steps / ms * 1e3  # every slot occupies a batch row each simulation
+        out.append({"workload": f"connect4_selfplay_{spec}_{E}x{S}", "net": name, "num_games": E, "num_simulations": S,
+                    "move_steps": args.net_steps, "sims_per_s": sims_s, "us_per_sim_step": ms * 1e3 / (args.net_steps * S),
+                    "flops_per_position": flops, "tensor_tflops": evals_s * flops / 1e12,
+                    "tensor_pipe_frac_of_measured_bf16": evals_s * flops / 1e12 / peaks["bf16_tflops"],
+                    "leaf_eval_fraction": st["evaluations"] / max(1, st["simulations"])})
+        search._engine.close()
+        del search, eng
+        torch.cuda.empty_cache()
+    return out or None
 
 
 def run_b200(args):
@@ -345,6 +354,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         allgather = {"ms": a0.elapsed_time(a1), "episodes": int(merged["ep_len"].numel()), "samples": int(merged["s_bb0"].numel())}
 
+    arena_bytes = eng.device_bytes
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_arm(E, S, kind)
@@ -354,6 +364,7 @@ def run_b200(args):
     extra = None
     if rank == 0 and world == 1 and args.net != "none":
         try:
+            arena_bytes = eng.device_bytes
             eng.close()
             extra = net_in_loop(args, local, peaks)
         except Exception as exc:  # the side measurement must not sink the headline
@@ -367,7 +378,7 @@ def run_b200(args):
             "config": {"workload": f"connect4_selfplay_{args.evaluator}_{E}x{S}", "num_games_per_gpu": E, "num_simulations": S,
                        "evaluator": args.evaluator, "c_puct": 1.0, "lanes_per_tree": args.lanes or 8, "parallelism": f"games sharded x{world}",
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step event pair)",
-                       "tree_arena_bytes": eng.device_bytes if eng.h else None},
+                       "tree_arena_bytes": arena_bytes},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "wall_s_timed_region": wall_s, "work": {k: v / K for k, v in st.items()},
         }
