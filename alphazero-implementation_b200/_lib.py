@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libaz_engine.so")
-SOURCES = ["az_engine.cu", "az_mlp.cu"]
+SOURCES = ["az_engine.cu", "az_mlp.cu", "az_conv.cu"]
 HEADERS = ["az_eval.cuh", "c4_bitboard.cuh", os.path.join("..", "..", "include", "az_engine.h")]
 
 NVCC_FLAGS = [
@@ -110,6 +110,9 @@ SIGNATURES = {
     "az_mlp_forward": (I32, [P, P, I64, P, P, P]),
     "az_mlp_forward_leaves": (I32, [P, P, P, P, P]),
     "az_mlp_launch_count": (I64, [P]),
+    "az_leaf_players": (I32, [P, C.POINTER(P)]),
+    "az_trunk_weight_bytes": (I64, [I32]),
+    "az_trunk_forward_leaves": (I32, [P, P, P, I32, P, P]),
     "az_leaf_arrays": (I32, [P, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(I32)]),
 }
 

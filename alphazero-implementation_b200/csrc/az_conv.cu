@@ -1,0 +1,327 @@
+// Fused ResNet-style trunk on the 5th-generation tensor cores (tcgen05 + TMEM): stem conv3x3 (3 -> 64) and any
+// number of residual blocks (2 x conv3x3 64 -> 64, skip, ReLU) of the reference's ResNet
+// (src/alphazero_simple/resnet.py:13-53, BatchNorm folded) for a batch of leaf positions in ONE kernel; the
+// activations of a position never leave the SM between layers.
+//
+// Convolution as implicit GEMM without im2col.  Every position is laid out as a zero-padded 8 x 9 grid of
+// "pixels" (6 x 7 cells plus a border), pixel = one GEMM row, channels = K.  The activation buffer is stored
+// K-group-major: for every group of 8 channels, all rows back to back at 16 bytes per row.  In the MMA's
+// K-major no-swizzle shared-memory descriptor this is "stride between 8-row groups = 128 B, stride between
+// K-adjacent core matrices = rows * 16 B", so the A operand of filter tap (dy, dx) is THE SAME buffer with the
+// start address moved by (9*dy + dx) rows: nine taps = nine descriptor offsets, no data movement.  The zero
+// border supplies the padding; outputs computed for border pixels are discarded (written back as zeros, which
+// keeps the border zero for the next layer).  8 positions = 576 pixels = 5 accumulator tiles of 128 rows x 64
+// fp32 columns in tensor memory.  Per layer one thread issues 9 taps x 5 tiles x 4 K-steps tcgen05.mma; the
+// tap weights ([64 out][64 in] bf16, 8 KB, packed once per weight update) stream through a 4-stage ring filled
+// by bulk async copies.  Epilogue (4 warps = the 128 accumulator lanes): tcgen05.ld, bias (+ skip) + ReLU in
+// fp32, round to bf16, write the next layer's A operand.  The leaf gather is fused in: the stem's input planes
+// (empty / side to move / opponent, cnn.py:93-95) are built from the engine's leaf bitboards.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "../../include/az_engine.h"
+#include "c4_bitboard.cuh"
+
+namespace {
+
+constexpr int C = 64;            // trunk channels
+constexpr int P = 8;             // positions per CTA
+constexpr int PW = 9, PH = 8;    // padded grid
+constexpr int PIX = PW * PH;     // 72 rows per position
+constexpr int ROWS = P * PIX;    // 576 real rows
+constexpr int TILES = 5;         // accumulator tiles of 128 rows (640 >= 576)
+constexpr int GUARD = 16;        // rows before / after (a tap moves the window by up to 10 rows)
+constexpr int RTOT = TILES * 128 + 2 * GUARD;       // 672 rows per buffer
+constexpr uint32_t ROWB = 16;                        // bytes per row per K group
+constexpr uint32_t LBO_A = RTOT * ROWB;              // 10752: between K groups (8 channels)
+constexpr uint32_t SBO_A = 128;                      // between 8-row groups
+constexpr uint32_t BUF_BYTES = (C / 8) * LBO_A;      // 86016
+constexpr uint32_t TAP_BYTES = C * C * 2;            // 8192: one tap's [64][64] weights
+constexpr uint32_t SBO_W = (C / 8) * 128;            // 1024 (canonical K-major [64][64])
+constexpr uint32_t LBO_W = 128;
+constexpr uint32_t STEM_TAP_BYTES = C * 16 * 2;      // 2048: stem tap [64][16]
+constexpr uint32_t SBO_WS = (16 / 8) * 128;          // 256
+constexpr int NS = 4;                                // weight ring stages
+constexpr uint32_t OFF_RING = 2 * BUF_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_RING + NS * TAP_BYTES;
+constexpr uint32_t OFF_BARS = OFF_BIAS + C * 4;
+constexpr uint32_t SMEM_BYTES = OFF_BARS + (2 * NS + 1) * 8 + 16;
+constexpr int THREADS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(phase)
+        : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+        " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&p);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+struct Pipe {
+    uint32_t full[NS], empty[NS], done, stage[NS];
+    uint32_t g;  // taps consumed so far (stage = g % NS, use = g / NS)
+};
+__device__ __forceinline__ void pipe_load(const Pipe &p, uint32_t gj, const uint8_t *src, uint32_t bytes) {
+    const uint32_t st = gj % NS;
+    if (gj >= NS) mbar_wait(p.empty[st], ((gj / NS) - 1u) & 1u);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(p.full[st]), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(p.stage[st]),
+                 "l"(src), "r"(bytes), "r"(p.full[st])
+                 : "memory");
+}
+
+// row index inside a CTA -> is it a real board cell, and which (position, y, x)
+__device__ __forceinline__ bool decode_row(int r, int &pos, int &y, int &x) {
+    pos = r / PIX;
+    const int q = r - pos * PIX;
+    const int py = q / PW, px = q - py * PW;
+    y = py - 1;
+    x = px - 1;
+    return r < ROWS && py >= 1 && py <= c4::H && px >= 1 && px <= c4::W;
+}
+
+// One conv layer's MMAs (thread 0): 9 taps x TILES x ksteps.  A = `a_addr` (row 0 of the buffer, after the guard).
+__device__ __forceinline__ void conv_mmas(Pipe &p, const uint8_t *w, uint32_t tap_bytes, uint32_t ksteps, uint32_t sbo_w,
+                                          uint32_t a_addr, uint32_t tmem_base, bool prefetched) {
+    if (!prefetched)
+        for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w + (size_t)i * tap_bytes, tap_bytes);
+    for (uint32_t tap = 0; tap < 9; ++tap) {
+        const uint32_t gi = p.g + tap, st = gi % NS;
+        const int dy = (int)(tap / 3) - 1, dx = (int)(tap % 3) - 1;
+        const uint32_t a_tap = a_addr + (uint32_t)((dy * PW + dx) * (int)ROWB);
+        mbar_wait(p.full[st], (gi / NS) & 1u);
+        tc_fence_after();
+        for (uint32_t t = 0; t < TILES; ++t)
+            for (uint32_t ks = 0; ks < ksteps; ++ks)
+                umma(tmem_base + t * C, smem_desc(a_tap + t * 128 * ROWB + ks * 2 * LBO_A, LBO_A, SBO_A),
+                     smem_desc(p.stage[st] + ks * 2 * LBO_W, LBO_W, sbo_w), instr_desc(128, C), (tap | ks) > 0);
+        umma_commit(p.empty[st]);
+        if (tap + NS < 9) pipe_load(p, gi + NS, w + (size_t)(tap + NS) * tap_bytes, tap_bytes);
+    }
+    umma_commit(p.done);
+    p.g += 9;
+}
+
+// Epilogue of one layer: accumulators -> (+ bias, + skip) -> ReLU -> bf16 -> destination buffer (K-group-major);
+// border / padding rows are written as zeros.  `skip` (may be null) is the residual input buffer.
+__device__ __forceinline__ void conv_epilogue(uint32_t tmem_base, uint8_t *dst, const uint8_t *skip, const float *bias) {
+    const uint32_t lane_row = threadIdx.x;
+    const uint32_t taddr = tmem_base + ((lane_row & ~31u) << 16);
+#pragma unroll 1
+    for (int t = 0; t < TILES; ++t) {
+        const int r = t * 128 + (int)lane_row;
+        int pos, y, x;
+        const bool valid = decode_row(r, pos, y, x);
+        uint8_t *drow = dst + (GUARD + r) * ROWB;
+        const uint8_t *srow = skip ? skip + (GUARD + r) * ROWB : nullptr;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld32(taddr + t * C + half * 32, v);
+#pragma unroll
+            for (int kg = 0; kg < 4; ++kg) {
+                const int grp = half * 4 + kg;  // channel group of 8
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[kg * 8 + j]) + bias[grp * 8 + j];
+                if (srow) {
+                    const uint4 s = *reinterpret_cast<const uint4 *>(srow + grp * LBO_A);
+                    f[0] += bf16_lo(s.x); f[1] += bf16_hi(s.x); f[2] += bf16_lo(s.y); f[3] += bf16_hi(s.y);
+                    f[4] += bf16_lo(s.z); f[5] += bf16_hi(s.z); f[6] += bf16_lo(s.w); f[7] += bf16_hi(s.w);
+                }
+                uint4 o = make_uint4(0, 0, 0, 0);
+                if (valid)
+                    o = make_uint4(pack_bf16(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f)), pack_bf16(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f)),
+                                   pack_bf16(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f)), pack_bf16(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f)));
+                *reinterpret_cast<uint4 *>(drow + grp * LBO_A) = o;
+            }
+        }
+    }
+}
+
+// weights: [stem: 9 taps x [64][16]] [layer 1: 9 taps x [64][64]] ... all bf16 canonical; biases: [L][64] fp32
+__global__ void __launch_bounds__(THREADS, 1)
+k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1, const uint8_t *__restrict__ leaf_player,
+               const uint8_t *__restrict__ leaf_status, long long n, const uint8_t *__restrict__ weights,
+               const float *__restrict__ biases, int num_blocks, __nv_bfloat16 *__restrict__ out /*[n][6][7][64]*/) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *buf[2] = {smem, smem + BUF_BYTES};
+    float *s_bias = reinterpret_cast<float *>(smem + OFF_BIAS);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BARS);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + (2 * NS + 1) * 8);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const long long pos0 = (long long)blockIdx.x * P;
+    Pipe p;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        p.full[i] = smem_u32(bars + i);
+        p.empty[i] = smem_u32(bars + NS + i);
+        p.stage[i] = smem_u32(smem + OFF_RING) + i * TAP_BYTES;
+    }
+    p.done = smem_u32(bars + 2 * NS);
+    p.g = 0;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 2 * NS + 1; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (uint32_t i = 0; i < NS; ++i) pipe_load(p, i, weights + (size_t)i * STEM_TAP_BYTES, STEM_TAP_BYTES);
+    }
+    // zero both activation buffers (borders, guards and the unused K groups of the stem input must be zero)
+    for (uint32_t i = tid; i < 2 * BUF_BYTES / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < C; i += THREADS) s_bias[i] = __ldg(biases + i);
+    __syncthreads();
+    // stem input in buf[1]: channels 0..2 = empty / side to move / opponent (cnn.py:93-95), K group 0
+    for (int r = tid; r < ROWS; r += THREADS) {
+        int pos, y, x;
+        if (!decode_row(r, pos, y, x)) continue;
+        const long long gp = pos0 + pos;
+        if (gp >= n || leaf_status[gp] != AZ_LEAF_EVAL) continue;
+        const uint64_t b0 = leaf_bb0[gp], b1 = leaf_bb1[gp];
+        const int pl = leaf_player[gp] & 1;
+        const int bit = x * c4::STRIDE + y;
+        const uint32_t s0 = (uint32_t)((b0 >> bit) & 1ull), s1 = (uint32_t)((b1 >> bit) & 1ull);
+        const uint32_t mine = pl ? s1 : s0, theirs = pl ? s0 : s1, empty = 1u - (s0 | s1);
+        const uint32_t one = 0x3F80u;
+        *reinterpret_cast<uint4 *>(buf[1] + (GUARD + r) * ROWB) = make_uint4(empty * one | (mine * one) << 16, theirs * one, 0u, 0u);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a0 = smem_u32(buf[0]) + GUARD * ROWB, a1 = smem_u32(buf[1]) + GUARD * ROWB;
+    uint32_t done_phase = 0;
+    const uint8_t *w_layer = weights + 9 * STEM_TAP_BYTES;  // first trunk layer's weights
+
+    // ---- stem: buf[1] (16 input channels, 3 used) -> buf[0]
+    if (tid == 0) {
+        conv_mmas(p, weights, STEM_TAP_BYTES, 1, SBO_WS, a1, tmem_base, true);
+        if (num_blocks > 0)
+            for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w_layer + (size_t)i * TAP_BYTES, TAP_BYTES);
+    }
+    mbar_wait(p.done, done_phase);
+    done_phase ^= 1;
+    tc_fence_after();
+    conv_epilogue(tmem_base, buf[0], nullptr, s_bias);
+
+    // ---- residual blocks: x in buf[0]; t = relu(conv1(x)) -> buf[1]; x = relu(conv2(t) + x) -> buf[0]
+    for (int blk = 0; blk < num_blocks; ++blk) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int layer = 1 + 2 * blk + half;
+            __syncthreads();  // everyone is done with s_bias of the previous layer
+            for (uint32_t i = tid; i < C; i += THREADS) s_bias[i] = __ldg(biases + layer * C + i);
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            if (tid == 0) {
+                conv_mmas(p, w_layer, TAP_BYTES, C / 16, SBO_W, half == 0 ? a0 : a1, tmem_base, true);
+                const bool more = !(blk == num_blocks - 1 && half == 1);
+                if (more)
+                    for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w_layer + 9 * TAP_BYTES + (size_t)i * TAP_BYTES, TAP_BYTES);
+            }
+            w_layer += 9 * TAP_BYTES;
+            mbar_wait(p.done, done_phase);
+            done_phase ^= 1;
+            tc_fence_after();
+            if (half == 0) conv_epilogue(tmem_base, buf[1], nullptr, s_bias);
+            else conv_epilogue(tmem_base, buf[0], buf[0], s_bias);
+        }
+    }
+    __syncthreads();
+    // ---- trunk output, NHWC bf16
+    for (int r = tid; r < ROWS; r += THREADS) {
+        int pos, y, x;
+        if (!decode_row(r, pos, y, x)) continue;
+        const long long gp = pos0 + pos;
+        if (gp >= n) continue;
+        uint4 *o = reinterpret_cast<uint4 *>(out + ((gp * c4::H + y) * c4::W + x) * C);
+        const uint8_t *row = buf[0] + (GUARD + r) * ROWB;
+#pragma unroll
+        for (int grp = 0; grp < C / 8; ++grp) o[grp] = *reinterpret_cast<const uint4 *>(row + grp * LBO_A);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+}  // namespace
+
+extern "C" {
+
+/* bytes of packed weights the trunk kernel expects for `num_blocks` residual blocks */
+int64_t az_trunk_weight_bytes(int32_t num_blocks) { return 9ll * STEM_TAP_BYTES + (int64_t)num_blocks * 2 * 9 * TAP_BYTES; }
+
+/* ResNet trunk (stem + num_blocks residual blocks, 64 channels, BatchNorm folded) on the leaves chosen by the last
+ * az_select_leaves of `engine`: out[slot][6][7][64] bf16 (NHWC, row 0 = bottom).  `weights`: bf16 MMA operands packed as
+ * alphazero-implementation_b200/models.py:pack_trunk_weights does; `biases`: fp32 [1 + 2*num_blocks][64]. */
+int32_t az_trunk_forward_leaves(az_engine *engine, const void *weights, const float *biases, int32_t num_blocks, void *out,
+                                void *stream) {
+    if (!engine || !weights || !biases || !out || num_blocks < 0) return AZ_E_INVALID;
+    const uint64_t *bb0 = nullptr, *bb1 = nullptr;
+    const uint8_t *status = nullptr, *player = nullptr;
+    int32_t n = 0;
+    if (az_leaf_arrays(engine, &bb0, &bb1, &status, &n) != AZ_OK || az_leaf_players(engine, &player) != AZ_OK || n <= 0) return AZ_E_INVALID;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_resnet_trunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
+        attr_set = true;
+    }
+    const int blocks = (n + P - 1) / P;
+    k_resnet_trunk<<<blocks, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(bb0, bb1, player, status, n, (const uint8_t *)weights, biases,
+                                                                          num_blocks, (__nv_bfloat16 *)out);
+    return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;
+}
+
+}  // extern "C"

@@ -1410,6 +1410,12 @@ int32_t az_leaf_arrays(az_engine *h, const uint64_t **bb0, const uint64_t **bb1,
     return AZ_OK;
 }
 
+int32_t az_leaf_players(az_engine *h, const uint8_t **player) {
+    if (!h || !player) return AZ_E_INVALID;
+    *player = h->a.leaf_player;
+    return AZ_OK;
+}
+
 int32_t az_root_stats(az_engine *h, int32_t *child_N, double *child_W, float *child_P, double *root_W, int32_t *root_N,
                       uint8_t *legal, int32_t *err, void *stream) {
     if (!h) return AZ_E_INVALID;

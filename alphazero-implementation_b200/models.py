@@ -292,6 +292,60 @@ class TensorCoreMLP:
             pass
 
 
+def _canonical_kmajor(w: Tensor) -> Tensor:
+    """[N][K] -> bf16 in the MMA's K-major no-swizzle core-matrix order: [N/8][K/8][8 rows][8 k]."""
+    n, k = w.shape
+    return w.reshape(n // 8, 8, k // 8, 8).permute(0, 2, 1, 3).contiguous().to(torch.bfloat16).reshape(-1)
+
+
+def pack_trunk_weights(model: "ResNet", device) -> tuple[Tensor, Tensor]:
+    """BatchNorm-folded stem + residual-block convolutions of a 64-channel ResNet as operands of csrc/az_conv.cu:
+    per layer 9 taps (tap = 3*ky + kx) of [64 out][K in] bf16 (K = 16 for the stem, zero padded), and fp32 biases."""
+    assert model.num_channels == 64, "the tensor-core trunk kernel is built for 64 channels"
+    m = copy.deepcopy(model).eval().float().to(device)
+    convs = [_fold_bn(m.input_conv[0], m.input_conv[1])]
+    for blk in m.residual_blocks:
+        convs.append(_fold_bn(blk.conv1, blk.bn1))
+        convs.append(_fold_bn(blk.conv2, blk.bn2))
+    parts, biases = [], []
+    for li, (w, b) in enumerate(convs):
+        if li == 0:
+            w = torch.cat([w, torch.zeros(64, 13, 3, 3, device=w.device)], dim=1)  # 3 -> 16 input channels
+        for ky in range(3):
+            for kx in range(3):
+                parts.append(_canonical_kmajor(w[:, :, ky, kx]))
+        biases.append(b)
+    return torch.cat(parts).contiguous(), torch.stack(biases).contiguous().float()
+
+
+class TensorCoreTrunk:
+    """Stem + residual blocks of a 64-channel ResNet as one tcgen05 kernel on the engine's leaves (csrc/az_conv.cu)."""
+
+    def __init__(self, model: "ResNet", device: torch.device):
+        from . import _lib
+
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.num_blocks = model.num_res_blocks
+        self.weights, self.biases = pack_trunk_weights(model, self.device)
+        assert self.weights.numel() * 2 == self.lib.az_trunk_weight_bytes(self.num_blocks)
+        self._out: dict[int, Tensor] = {}
+        self.launches = 0
+
+    def forward_leaves(self, engine) -> Tensor:
+        """-> trunk activations [n, 64, 6, 7] bf16 (channels-last memory) for the leaves of `engine.select_leaves()`."""
+        n = engine.n_active
+        if n not in self._out:
+            self._out[n] = torch.empty((n, 6, 7, 64), dtype=torch.bfloat16, device=self.device)
+        out = self._out[n]
+        rc = self.lib.az_trunk_forward_leaves(engine.h, self.weights.data_ptr(), self.biases.data_ptr(), self.num_blocks,
+                                              out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"az_trunk_forward_leaves failed ({rc})")
+        self.launches += 1
+        return out.permute(0, 3, 1, 2)  # NCHW view of NHWC memory == channels_last
+
+
 class InferenceNet(nn.Module):
     """Search-time form of a `Model` (the role of `get_inference_clone()`, models/base/model.py:92-96):
     eval-mode, BatchNorm folded, conv/linear weights in `dtype` (bf16 on the hot path), activations

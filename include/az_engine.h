@@ -150,6 +150,7 @@ int32_t az_leaf_info(az_engine *h, uint64_t *out_bb0, uint64_t *out_bb1, uint8_t
 /* engine-owned device arrays describing the leaves of the last az_select_leaves (borrowed; valid until az_destroy):
  * lets another kernel consume the leaves without a gather launch (see az_mlp_forward_leaves) */
 int32_t az_leaf_arrays(az_engine *h, const uint64_t **bb0, const uint64_t **bb1, const uint8_t **status, int32_t *n_active);
+int32_t az_leaf_players(az_engine *h, const uint8_t **player);
 
 /* ---- results ---- */
 /* root statistics of every active tree, per column (0 on illegal columns):
@@ -225,6 +226,13 @@ int32_t az_mlp_forward(az_mlp *m, const float *grid /*[n][42]*/, int64_t n, floa
 /* the same with the leaf gather fused in: row i = the leaf of slot i chosen by the last az_select_leaves on `engine` */
 int32_t az_mlp_forward_leaves(az_mlp *m, az_engine *engine, float *logits /*[E][7]*/, float *values /*[E][2]*/, void *stream);
 int64_t az_mlp_launch_count(const az_mlp *m);
+
+/* ---- fused tensor-core trunk of the ResNet-style net (src/alphazero_simple/resnet.py:13-53, 64 channels, BatchNorm folded) ----
+ * stem conv3x3 + num_blocks residual blocks in ONE tcgen05 kernel (csrc/az_conv.cu), the leaf gather fused in;
+ * activations stay in shared memory between layers.  Output: [E][6][7][64] bf16 NHWC for the policy / value heads. */
+int64_t az_trunk_weight_bytes(int32_t num_blocks);
+int32_t az_trunk_forward_leaves(az_engine *engine, const void *packed_weights, const float *biases /*[1+2*num_blocks][64]*/,
+                                int32_t num_blocks, void *out, void *stream);
 
 #ifdef __cplusplus
 }

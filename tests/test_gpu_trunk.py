@@ -1,0 +1,73 @@
+"""GPU: the hand-written tcgen05 ResNet trunk (csrc/az_conv.cu) vs a plain PyTorch reference of the same op."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import alphazero_implementation_b200 as az  # noqa: E402
+from alphazero_implementation_b200.engine import LAYOUT_PLANES_F32  # noqa: E402
+from alphazero_implementation_b200.models import TensorCoreTrunk, _fold_bn  # noqa: E402
+
+
+def _engine_with_leaves(n, seed=0, deep=True):
+    eng = az.Engine(num_games=n, num_simulations=48)
+    eng.reset_games()
+    u = torch.from_numpy(np.random.RandomState(seed).random_sample(n)).cuda()
+    for _ in range(12 if deep else 3):
+        eng.run_simulations(30, 2)
+        eng.sample_moves(u)
+    eng.run_simulations(30, 2)
+    eng.select_leaves()
+    return eng
+
+
+def _randomise_bn(m):
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.2)
+            mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+            mod.weight.data.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+            mod.bias.data.copy_(torch.randn(mod.num_features, generator=g) * 0.2)
+
+
+def _reference_trunk(model, x):
+    """Same arithmetic in PyTorch: BN folded, bf16-rounded weights and inter-layer activations, fp32 accumulation."""
+    r = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    w, b = _fold_bn(model.input_conv[0], model.input_conv[1])
+    h = r(torch.relu(F.conv2d(r(x), r(w), b, padding=1)))
+    for blk in model.residual_blocks:
+        w1, b1 = _fold_bn(blk.conv1, blk.bn1)
+        w2, b2 = _fold_bn(blk.conv2, blk.bn2)
+        t = r(torch.relu(F.conv2d(h, r(w1), b1, padding=1)))
+        h = r(torch.relu(F.conv2d(t, r(w2), b2, padding=1) + h))
+    return h
+
+
+@pytest.mark.parametrize("blocks,n", [(0, 8), (1, 5), (1, 64), (4, 100), (2, 1000)])
+def test_trunk_matches_pytorch_reference(blocks, n):
+    torch.manual_seed(blocks * 100 + n)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = az.ResNet(num_res_blocks=blocks, num_channels=64).cuda().eval()
+    _randomise_bn(model)
+    eng = _engine_with_leaves(n, seed=n)
+    status = eng.leaf_info()["status"]
+    x = eng.gather_leaves(LAYOUT_PLANES_F32)
+    trunk = TensorCoreTrunk(model, torch.device("cuda", torch.cuda.current_device()))
+    got = trunk.forward_leaves(eng).float()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = _reference_trunk(model, x)
+    assert got.shape == ref.shape == (n, 64, 6, 7)
+    assert torch.isfinite(got).all()
+    live = status == 0
+    assert live.any()
+    err = (got[live] - ref[live]).abs()
+    scale = ref[live].abs().max().item()
+    # bf16 output rounding (2^-8 relative) + accumulation-order noise across 4..9 layers
+    assert err.max().item() <= 0.03 * max(scale, 1.0), (err.max().item(), scale)
+    assert err.mean().item() <= 2e-3 * max(scale, 1.0)
+    eng.close()
