@@ -49,7 +49,7 @@ constexpr uint32_t OFF_RING = 2 * BUF_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_RING + NS * TAP_BYTES;
 constexpr uint32_t OFF_BARS = OFF_BIAS + C * 4;
 constexpr uint32_t SMEM_BYTES = OFF_BARS + (2 * NS + 1) * 8 + 16;
-constexpr int THREADS = 128;
+constexpr int THREADS = 256;  // 8 warps: warps w and w+4 share the 32 accumulator lanes 32*(w%4).., each takes half the channels
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -130,6 +130,7 @@ __device__ __forceinline__ bool decode_row(int r, int &pos, int &y, int &x) {
 // One conv layer's MMAs (thread 0): 9 taps x TILES x ksteps.  A = `a_addr` (row 0 of the buffer, after the guard).
 __device__ __forceinline__ void conv_mmas(Pipe &p, const uint8_t *w, uint32_t tap_bytes, uint32_t ksteps, uint32_t sbo_w,
                                           uint32_t a_addr, uint32_t tmem_base, bool prefetched) {
+    const uint32_t idesc = instr_desc(128, C);
     if (!prefetched)
         for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w + (size_t)i * tap_bytes, tap_bytes);
     for (uint32_t tap = 0; tap < 9; ++tap) {
@@ -138,10 +139,20 @@ __device__ __forceinline__ void conv_mmas(Pipe &p, const uint8_t *w, uint32_t ta
         const uint32_t a_tap = a_addr + (uint32_t)((dy * PW + dx) * (int)ROWB);
         mbar_wait(p.full[st], (gi / NS) & 1u);
         tc_fence_after();
-        for (uint32_t t = 0; t < TILES; ++t)
-            for (uint32_t ks = 0; ks < ksteps; ++ks)
-                umma(tmem_base + t * C, smem_desc(a_tap + t * 128 * ROWB + ks * 2 * LBO_A, LBO_A, SBO_A),
-                     smem_desc(p.stage[st] + ks * 2 * LBO_W, LBO_W, sbo_w), instr_desc(128, C), (tap | ks) > 0);
+        // descriptors differ only in the start-address field (low 14 bits, 16-byte units): build once, add offsets
+        const uint64_t a_base = smem_desc(a_tap, LBO_A, SBO_A), b_base = smem_desc(p.stage[st], LBO_W, sbo_w);
+        const uint32_t acc0 = tap > 0;
+        if (ksteps == 1) {
+#pragma unroll
+            for (uint32_t t = 0; t < TILES; ++t) umma(tmem_base + t * C, a_base + t * (128 * ROWB >> 4), b_base, idesc, acc0);
+        } else {
+#pragma unroll
+            for (uint32_t t = 0; t < TILES; ++t)
+#pragma unroll
+                for (uint32_t ks = 0; ks < C / 16; ++ks)
+                    umma(tmem_base + t * C, a_base + t * (128 * ROWB >> 4) + ks * (2 * LBO_A >> 4), b_base + ks * (2 * LBO_W >> 4), idesc,
+                         acc0 | (ks > 0));
+        }
         umma_commit(p.empty[st]);
         if (tap + NS < 9) pipe_load(p, gi + NS, w + (size_t)(tap + NS) * tap_bytes, tap_bytes);
     }
@@ -152,8 +163,9 @@ __device__ __forceinline__ void conv_mmas(Pipe &p, const uint8_t *w, uint32_t ta
 // Epilogue of one layer: accumulators -> (+ bias, + skip) -> ReLU -> bf16 -> destination buffer (K-group-major);
 // border / padding rows are written as zeros.  `skip` (may be null) is the residual input buffer.
 __device__ __forceinline__ void conv_epilogue(uint32_t tmem_base, uint8_t *dst, const uint8_t *skip, const float *bias) {
-    const uint32_t lane_row = threadIdx.x;
-    const uint32_t taddr = tmem_base + ((lane_row & ~31u) << 16);
+    const uint32_t lane_row = threadIdx.x & 127u;
+    const int half = threadIdx.x >> 7;  // which 32 of the 64 channels this warp group handles
+    const uint32_t taddr = tmem_base + ((lane_row & ~31u) << 16) + half * 32;
 #pragma unroll 1
     for (int t = 0; t < TILES; ++t) {
         const int r = t * 128 + (int)lane_row;
@@ -161,27 +173,24 @@ __device__ __forceinline__ void conv_epilogue(uint32_t tmem_base, uint8_t *dst, 
         const bool valid = decode_row(r, pos, y, x);
         uint8_t *drow = dst + (GUARD + r) * ROWB;
         const uint8_t *srow = skip ? skip + (GUARD + r) * ROWB : nullptr;
+        uint32_t v[32];
+        tmem_ld32(taddr + t * C, v);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tmem_ld32(taddr + t * C + half * 32, v);
+        for (int kg = 0; kg < 4; ++kg) {
+            const int grp = half * 4 + kg;  // channel group of 8
+            float f[8];
 #pragma unroll
-            for (int kg = 0; kg < 4; ++kg) {
-                const int grp = half * 4 + kg;  // channel group of 8
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[kg * 8 + j]) + bias[grp * 8 + j];
-                if (srow) {
-                    const uint4 s = *reinterpret_cast<const uint4 *>(srow + grp * LBO_A);
-                    f[0] += bf16_lo(s.x); f[1] += bf16_hi(s.x); f[2] += bf16_lo(s.y); f[3] += bf16_hi(s.y);
-                    f[4] += bf16_lo(s.z); f[5] += bf16_hi(s.z); f[6] += bf16_lo(s.w); f[7] += bf16_hi(s.w);
-                }
-                uint4 o = make_uint4(0, 0, 0, 0);
-                if (valid)
-                    o = make_uint4(pack_bf16(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f)), pack_bf16(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f)),
-                                   pack_bf16(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f)), pack_bf16(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f)));
-                *reinterpret_cast<uint4 *>(drow + grp * LBO_A) = o;
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[kg * 8 + j]) + bias[grp * 8 + j];
+            if (srow) {
+                const uint4 s = *reinterpret_cast<const uint4 *>(srow + grp * LBO_A);
+                f[0] += bf16_lo(s.x); f[1] += bf16_hi(s.x); f[2] += bf16_lo(s.y); f[3] += bf16_hi(s.y);
+                f[4] += bf16_lo(s.z); f[5] += bf16_hi(s.z); f[6] += bf16_lo(s.w); f[7] += bf16_hi(s.w);
             }
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (valid)
+                o = make_uint4(pack_bf16(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f)), pack_bf16(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f)),
+                               pack_bf16(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f)), pack_bf16(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f)));
+            *reinterpret_cast<uint4 *>(drow + grp * LBO_A) = o;
         }
     }
 }

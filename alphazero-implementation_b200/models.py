@@ -352,8 +352,10 @@ class InferenceNet(nn.Module):
     channels-last.  `forward(planes) -> (logits f32 [B,7], values f32 [B,2])`, consumed directly by
     `az_expand_backup`.  BasicNN stays fp32 (config 1 parity is quoted in fp32)."""
 
-    def __init__(self, model: Model, dtype: torch.dtype = torch.bfloat16, device: torch.device | str = "cuda"):
+    def __init__(self, model: Model, dtype: torch.dtype = torch.bfloat16, device: torch.device | str = "cuda",
+                 use_tensor_core_kernels: bool = True):
         super().__init__()
+        self.trunk = None
         m = copy.deepcopy(model).eval().to(device)
         self.kind = type(model).__name__
         self.dtype = dtype
@@ -368,6 +370,9 @@ class InferenceNet(nn.Module):
                 self.dtype = torch.float32
         elif isinstance(m, (CNNModel, ResNet)):
             self.input_layout = LAYOUT_PLANES_BF16 if dtype == torch.bfloat16 else LAYOUT_PLANES_F32
+            self.trunk = None
+            if isinstance(m, ResNet) and m.num_channels == 64 and dtype == torch.bfloat16 and use_tensor_core_kernels:
+                self.trunk = TensorCoreTrunk(m, torch.device(device))  # hand-written tcgen05 trunk; heads stay library GEMMs
             self.net = self._fold(m).to(dtype).to(memory_format=torch.channels_last)
         else:
             self.input_layout = getattr(model, "input_layout", LAYOUT_PLANES_F32)
@@ -407,6 +412,20 @@ class InferenceNet(nn.Module):
             m.policy_head = fold_seq(m.policy_head)
             m.value_head = fold_seq(m.value_head)
         return m
+
+    @torch.no_grad()
+    def forward_leaves(self, engine) -> tuple[Tensor, Tensor]:
+        """Evaluate the engine's current leaves without a separate gather launch (tensor-core kernels only)."""
+        if self.fused is not None:
+            return self.fused.forward_leaves(engine)
+        h = self.trunk.forward_leaves(engine)  # [n, 64, 6, 7] bf16, channels-last
+        logits = self.net.policy_head(h)
+        v = torch.tanh(self.net.value_head(h))
+        return logits.float().contiguous(), torch.cat([v, -v], dim=1).float().contiguous()
+
+    @property
+    def evaluates_leaves_directly(self) -> bool:
+        return self.fused is not None or self.trunk is not None
 
     @torch.no_grad()
     def forward(self, x: Tensor) -> tuple[Tensor, Tensor]:

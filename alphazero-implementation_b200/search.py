@@ -92,9 +92,8 @@ class _GraphedStep:
     def step(self):
         e = self.engine
         e.select_leaves()
-        fused = getattr(self.net, "fused", None)
-        if fused is not None:  # tcgen05 MLP with the leaf gather fused in: 3 launches per simulation step
-            logits, values = fused.forward_leaves(e)
+        if getattr(self.net, "evaluates_leaves_directly", False):  # tcgen05 kernels with the leaf gather fused in
+            logits, values = self.net.forward_leaves(e)
         else:
             e.gather_leaves(self.layout, self.x)
             logits, values = self.net(self.x)
@@ -129,7 +128,8 @@ class _GraphedStep:
 
 class AlphaZeroSearch:
     def __init__(self, *, model, num_simulations: int, exploration_weight: float = 1.0, device: int | None = None,
-                 lanes_per_tree: int = 0, inference_dtype: torch.dtype | None = None, use_cuda_graph: bool = True):
+                 lanes_per_tree: int = 0, inference_dtype: torch.dtype | None = None, use_cuda_graph: bool = True,
+                 use_tensor_core_kernels: bool = True):
         self.inference_model = model.get_inference_clone()
         self.num_simulations = int(num_simulations)
         self.exploration_weight = exploration_weight
@@ -137,6 +137,7 @@ class AlphaZeroSearch:
         self.lanes_per_tree = lanes_per_tree
         self.inference_dtype = inference_dtype
         self.use_cuda_graph = use_cuda_graph
+        self.use_tensor_core_kernels = use_tensor_core_kernels
         self._engine: Engine | None = None
         self._net = None
         self._graphed: _GraphedStep | None = None
@@ -159,7 +160,7 @@ class AlphaZeroSearch:
         elif isinstance(m, Model):
             dtype = self.inference_dtype or (torch.float32 if isinstance(m, BasicNN) else torch.bfloat16)
             dev = torch.device("cuda", torch.cuda.current_device() if self.device_index is None else self.device_index)
-            self._mode, self._net = "net", InferenceNet(m, dtype=dtype, device=dev)
+            self._mode, self._net = "net", InferenceNet(m, dtype=dtype, device=dev, use_tensor_core_kernels=self.use_tensor_core_kernels)
         else:
             self._mode, self._net = "predict", None
 

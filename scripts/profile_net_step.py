@@ -15,6 +15,10 @@ for name in nets:
         kw = dict(inference_dtype=torch.bfloat16)
     elif name == "basic":
         model = az.BasicNN()
+    elif name.endswith("_lib"):  # ResNet through cuDNN only (no hand-written trunk)
+        b, c = name[:-4].replace("resnet", "").split("x")
+        model = az.ResNet(int(b), int(c))
+        kw = dict(use_tensor_core_kernels=False)
     elif name == "cnn":
         model = az.CNNModel()
     else:
@@ -30,10 +34,11 @@ for name in nets:
     for it in range(40):
         ev[0].record(); eng.select_leaves()
         ev[1].record()
-        if net.fused is None:
+        direct = net.evaluates_leaves_directly
+        if not direct:
             eng.gather_leaves(net.input_layout, x)
         ev[2].record()
-        logits, values = net.fused.forward_leaves(eng) if net.fused is not None else net(x)
+        logits, values = net.forward_leaves(eng) if direct else net(x)
         ev[3].record(); eng.expand_backup(logits, values, POLICY_LOGITS)
         ev[4].record()
         torch.cuda.synchronize()

@@ -71,3 +71,22 @@ def test_trunk_matches_pytorch_reference(blocks, n):
     assert err.max().item() <= 0.03 * max(scale, 1.0), (err.max().item(), scale)
     assert err.mean().item() <= 2e-3 * max(scale, 1.0)
     eng.close()
+
+
+def test_resnet_in_the_search_loop_matches_library_path():
+    """ResNet 2x64 evaluated through the tcgen05 trunk (+ library heads) inside AlphaZeroSearch gives the same trees, up
+    to bf16 accumulation-order noise, as the all-cuDNN bf16 path: root visit counts within a few visits."""
+    torch.manual_seed(11)
+    model = az.ResNet(num_res_blocks=2, num_channels=64)
+    _randomise_bn(model)
+    roots = [az.Config().sample_initial_state() for _ in range(4)]
+    out = []
+    for tc in (True, False):
+        s = az.AlphaZeroSearch(model=model, num_simulations=96, use_tensor_core_kernels=tc)
+        assert (s._net.trunk is not None) == tc
+        nodes = [az.Node(r) for r in roots]
+        s.run_simulations(nodes)
+        out.append([[ch.visit_count for ch in n.children.values()] for n in nodes])
+        assert all(sum(v) == 95 for v in out[-1])
+    for a, b in zip(*out):
+        assert max(abs(x - y) for x, y in zip(a, b)) <= 10
