@@ -113,6 +113,7 @@ SIGNATURES = {
     "az_leaf_players": (I32, [P, C.POINTER(P)]),
     "az_trunk_weight_bytes": (I64, [I32]),
     "az_trunk_forward_leaves": (I32, [P, P, P, I32, P, P]),
+    "az_resnet_forward_leaves": (I32, [P, P, P, I32, P, P, P, P, P, P, P, P, P]),
     "az_leaf_arrays": (I32, [P, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(I32)]),
 }
 

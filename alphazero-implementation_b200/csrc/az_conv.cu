@@ -45,9 +45,13 @@ constexpr uint32_t LBO_W = 128;
 constexpr uint32_t STEM_TAP_BYTES = C * 16 * 2;      // 2048: stem tap [64][16]
 constexpr uint32_t SBO_WS = (16 / 8) * 128;          // 256
 constexpr int NS = 4;                                // weight ring stages
+constexpr int NHC = 48;                              // head conv channels: 32 policy (1x1, centre tap) + 3 value (3x3) + padding
+constexpr uint32_t HEAD_TAP_BYTES = NHC * C * 2;     // 6144
+constexpr int NHU = 35;                              // head channels actually used
+constexpr int MAX_LAYERS = 24;                       // biases of every layer are staged in shared memory once
 constexpr uint32_t OFF_RING = 2 * BUF_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_RING + NS * TAP_BYTES;
-constexpr uint32_t OFF_BARS = OFF_BIAS + C * 4;
+constexpr uint32_t OFF_BARS = OFF_BIAS + MAX_LAYERS * C * 4;
 constexpr uint32_t SMEM_BYTES = OFF_BARS + (2 * NS + 1) * 8 + 16;
 constexpr int THREADS = 256;  // 8 warps: warps w and w+4 share the 32 accumulator lanes 32*(w%4).., each takes half the channels
 
@@ -129,8 +133,8 @@ __device__ __forceinline__ bool decode_row(int r, int &pos, int &y, int &x) {
 
 // One conv layer's MMAs (thread 0): 9 taps x TILES x ksteps.  A = `a_addr` (row 0 of the buffer, after the guard).
 __device__ __forceinline__ void conv_mmas(Pipe &p, const uint8_t *w, uint32_t tap_bytes, uint32_t ksteps, uint32_t sbo_w,
-                                          uint32_t a_addr, uint32_t tmem_base, bool prefetched) {
-    const uint32_t idesc = instr_desc(128, C);
+                                          uint32_t a_addr, uint32_t tmem_base, bool prefetched, int n_out = C) {
+    const uint32_t idesc = instr_desc(128, n_out);
     if (!prefetched)
         for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w + (size_t)i * tap_bytes, tap_bytes);
     for (uint32_t tap = 0; tap < 9; ++tap) {
@@ -199,7 +203,11 @@ __device__ __forceinline__ void conv_epilogue(uint32_t tmem_base, uint8_t *dst, 
 __global__ void __launch_bounds__(THREADS, 1)
 k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1, const uint8_t *__restrict__ leaf_player,
                const uint8_t *__restrict__ leaf_status, long long n, const uint8_t *__restrict__ weights,
-               const float *__restrict__ biases, int num_blocks, __nv_bfloat16 *__restrict__ out /*[n][6][7][64]*/) {
+               const float *__restrict__ biases, int num_blocks, __nv_bfloat16 *__restrict__ out /*[n][6][7][64] or null*/,
+               const uint8_t *__restrict__ head_w /*9 taps x [48][64] or null*/, const float *__restrict__ head_b /*[48]*/,
+               const float *__restrict__ fc_policy_w /*[7][1344]*/, const float *__restrict__ fc_policy_b,
+               const float *__restrict__ fc_value_w /*[126]*/, const float *__restrict__ fc_value_b,
+               float *__restrict__ logits /*[n][7]*/, float *__restrict__ values /*[n][2]*/) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *buf[2] = {smem, smem + BUF_BYTES};
     float *s_bias = reinterpret_cast<float *>(smem + OFF_BIAS);
@@ -227,7 +235,10 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
     }
     // zero both activation buffers (borders, guards and the unused K groups of the stem input must be zero)
     for (uint32_t i = tid; i < 2 * BUF_BYTES / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
-    for (uint32_t i = tid; i < C; i += THREADS) s_bias[i] = __ldg(biases + i);
+    const int n_layers = 1 + 2 * num_blocks;
+    for (uint32_t i = tid; i < (uint32_t)n_layers * C; i += THREADS) s_bias[i] = __ldg(biases + i);
+    if (head_w)
+        for (uint32_t i = tid; i < NHC; i += THREADS) s_bias[n_layers * C + i] = __ldg(head_b + i);
     __syncthreads();
     // stem input in buf[1]: channels 0..2 = empty / side to move / opponent (cnn.py:93-95), K group 0
     for (int r = tid; r < ROWS; r += THREADS) {
@@ -257,6 +268,8 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
         conv_mmas(p, weights, STEM_TAP_BYTES, 1, SBO_WS, a1, tmem_base, true);
         if (num_blocks > 0)
             for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w_layer + (size_t)i * TAP_BYTES, TAP_BYTES);
+        else if (head_w)
+            for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, head_w + (size_t)i * HEAD_TAP_BYTES, HEAD_TAP_BYTES);
     }
     mbar_wait(p.done, done_phase);
     done_phase ^= 1;
@@ -268,37 +281,100 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             const int layer = 1 + 2 * blk + half;
-            __syncthreads();  // everyone is done with s_bias of the previous layer
-            for (uint32_t i = tid; i < C; i += THREADS) s_bias[i] = __ldg(biases + layer * C + i);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
             tc_fence_after();
             if (tid == 0) {
                 conv_mmas(p, w_layer, TAP_BYTES, C / 16, SBO_W, half == 0 ? a0 : a1, tmem_base, true);
-                const bool more = !(blk == num_blocks - 1 && half == 1);
-                if (more)
+                const bool last = (blk == num_blocks - 1 && half == 1);
+                if (!last)
                     for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w_layer + 9 * TAP_BYTES + (size_t)i * TAP_BYTES, TAP_BYTES);
+                else if (head_w)
+                    for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, head_w + (size_t)i * HEAD_TAP_BYTES, HEAD_TAP_BYTES);
             }
             w_layer += 9 * TAP_BYTES;
             mbar_wait(p.done, done_phase);
             done_phase ^= 1;
             tc_fence_after();
-            if (half == 0) conv_epilogue(tmem_base, buf[1], nullptr, s_bias);
-            else conv_epilogue(tmem_base, buf[0], buf[0], s_bias);
+            if (half == 0) conv_epilogue(tmem_base, buf[1], nullptr, s_bias + layer * C);
+            else conv_epilogue(tmem_base, buf[0], buf[0], s_bias + layer * C);
         }
     }
     __syncthreads();
-    // ---- trunk output, NHWC bf16
-    for (int r = tid; r < ROWS; r += THREADS) {
-        int pos, y, x;
-        if (!decode_row(r, pos, y, x)) continue;
-        const long long gp = pos0 + pos;
-        if (gp >= n) continue;
-        uint4 *o = reinterpret_cast<uint4 *>(out + ((gp * c4::H + y) * c4::W + x) * C);
-        const uint8_t *row = buf[0] + (GUARD + r) * ROWB;
+    // ---- trunk output, NHWC bf16 (optional)
+    if (out) {
+        for (int r = tid; r < ROWS; r += THREADS) {
+            int pos, y, x;
+            if (!decode_row(r, pos, y, x)) continue;
+            const long long gp = pos0 + pos;
+            if (gp >= n) continue;
+            uint4 *o = reinterpret_cast<uint4 *>(out + ((gp * c4::H + y) * c4::W + x) * C);
+            const uint8_t *row = buf[0] + (GUARD + r) * ROWB;
 #pragma unroll
-        for (int grp = 0; grp < C / 8; ++grp) o[grp] = *reinterpret_cast<const uint4 *>(row + grp * LBO_A);
+            for (int grp = 0; grp < C / 8; ++grp) o[grp] = *reinterpret_cast<const uint4 *>(row + grp * LBO_A);
+        }
+    }
+    // ---- heads (resnet.py:56-72): policy conv1x1 -> 32 and value conv3x3 -> 3 as ONE 48-channel conv layer (the 1x1
+    // weights sit in the centre tap), ReLU, then the two small fully connected layers on CUDA cores in fp32
+    if (head_w) {
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) conv_mmas(p, head_w, HEAD_TAP_BYTES, C / 16, SBO_W, a0, tmem_base, true, NHC);
+        mbar_wait(p.done, done_phase);
+        done_phase ^= 1;
+        tc_fence_after();
+        float *hact = reinterpret_cast<float *>(buf[1]);  // [P][35][42] fp32, the Flatten() order of NCHW
+        const float *hb = s_bias + n_layers * C;
+        if (tid < 128) {
+            const uint32_t taddr = tmem_base + ((tid & ~31u) << 16);
+#pragma unroll 1
+            for (int t = 0; t < TILES; ++t) {
+                const int r = t * 128 + (int)tid;
+                int pos, y, x;
+                const bool valid = decode_row(r, pos, y, x);
+                uint32_t v[32];
+                tmem_ld32(taddr + t * C, v);  // policy channels 0..31
+                if (valid) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) hact[(pos * NHU + c) * 42 + y * c4::W + x] = fmaxf(__uint_as_float(v[c]) + hb[c], 0.f);
+                }
+                tmem_ld32(taddr + t * C + 32, v);  // value channels 32..34 (+ padding)
+                if (valid) {
+#pragma unroll
+                    for (int c = 32; c < NHU; ++c) hact[(pos * NHU + c) * 42 + y * c4::W + x] = fmaxf(__uint_as_float(v[c - 32]) + hb[c], 0.f);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        // thread = (position, output, quarter of the dot product); 8 outputs = 7 logits + the value
+        {
+            const int pos = tid >> 5, j = (tid >> 2) & 7, part = tid & 3;
+            const long long gp = pos0 + pos;
+            float acc = 0.f;
+            if (j < 7) {
+                const float *w = fc_policy_w + (size_t)j * (32 * 42);
+                const float *a = hact + pos * NHU * 42;
+                for (int i = part; i < 32 * 42; i += 4) acc += __ldg(w + i) * a[i];
+            } else {
+                const float *a = hact + (pos * NHU + 32) * 42;
+                for (int i = part; i < 3 * 42; i += 4) acc += __ldg(fc_value_w + i) * a[i];
+            }
+            acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+            acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+            if (part == 0 && gp < n) {
+                if (j < 7) {
+                    logits[gp * 7 + j] = acc + __ldg(fc_policy_b + j);
+                } else {
+                    const float v = tanhf(acc + __ldg(fc_value_b));
+                    values[gp * 2] = v;
+                    values[gp * 2 + 1] = -v;
+                }
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -312,12 +388,10 @@ extern "C" {
 /* bytes of packed weights the trunk kernel expects for `num_blocks` residual blocks */
 int64_t az_trunk_weight_bytes(int32_t num_blocks) { return 9ll * STEM_TAP_BYTES + (int64_t)num_blocks * 2 * 9 * TAP_BYTES; }
 
-/* ResNet trunk (stem + num_blocks residual blocks, 64 channels, BatchNorm folded) on the leaves chosen by the last
- * az_select_leaves of `engine`: out[slot][6][7][64] bf16 (NHWC, row 0 = bottom).  `weights`: bf16 MMA operands packed as
- * alphazero-implementation_b200/models.py:pack_trunk_weights does; `biases`: fp32 [1 + 2*num_blocks][64]. */
-int32_t az_trunk_forward_leaves(az_engine *engine, const void *weights, const float *biases, int32_t num_blocks, void *out,
-                                void *stream) {
-    if (!engine || !weights || !biases || !out || num_blocks < 0) return AZ_E_INVALID;
+static int32_t launch_trunk(az_engine *engine, const void *weights, const float *biases, int32_t num_blocks, void *out,
+                            const void *head_w, const float *head_b, const float *fcp_w, const float *fcp_b, const float *fcv_w,
+                            const float *fcv_b, float *logits, float *values, void *stream) {
+    if (!engine || !weights || !biases || num_blocks < 0 || 1 + 2 * num_blocks + 1 > MAX_LAYERS) return AZ_E_INVALID;
     const uint64_t *bb0 = nullptr, *bb1 = nullptr;
     const uint8_t *status = nullptr, *player = nullptr;
     int32_t n = 0;
@@ -329,8 +403,29 @@ int32_t az_trunk_forward_leaves(az_engine *engine, const void *weights, const fl
     }
     const int blocks = (n + P - 1) / P;
     k_resnet_trunk<<<blocks, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(bb0, bb1, player, status, n, (const uint8_t *)weights, biases,
-                                                                          num_blocks, (__nv_bfloat16 *)out);
+                                                                          num_blocks, (__nv_bfloat16 *)out, (const uint8_t *)head_w, head_b,
+                                                                          fcp_w, fcp_b, fcv_w, fcv_b, logits, values);
     return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;
+}
+
+/* ResNet trunk (stem + num_blocks residual blocks, 64 channels, BatchNorm folded) on the leaves chosen by the last
+ * az_select_leaves of `engine`: out[slot][6][7][64] bf16 (NHWC, row 0 = bottom).  `weights`: bf16 MMA operands packed as
+ * alphazero-implementation_b200/models.py:pack_trunk_weights does; `biases`: fp32 [1 + 2*num_blocks][64]. */
+int32_t az_trunk_forward_leaves(az_engine *engine, const void *weights, const float *biases, int32_t num_blocks, void *out,
+                                void *stream) {
+    if (!out) return AZ_E_INVALID;
+    return launch_trunk(engine, weights, biases, num_blocks, out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+/* The whole net (trunk + policy / value heads, resnet.py:30-103 with tanh and the [v, -v] value convention of cnn.py:73) in the
+ * same kernel: logits [E][7] and values [E][2] fp32, the inputs of az_expand_backup.  head_conv_w: 9 taps x [48][64] bf16
+ * (rows 0..31 policy conv1x1 in the centre tap, rows 32..34 value conv3x3), head_conv_b [48]; fc_*: fp32 nn.Linear layout. */
+int32_t az_resnet_forward_leaves(az_engine *engine, const void *weights, const float *biases, int32_t num_blocks,
+                                 const void *head_conv_w, const float *head_conv_b, const float *fc_policy_w, const float *fc_policy_b,
+                                 const float *fc_value_w, const float *fc_value_b, float *logits, float *values, void *stream) {
+    if (!head_conv_w || !head_conv_b || !fc_policy_w || !fc_policy_b || !fc_value_w || !fc_value_b || !logits || !values) return AZ_E_INVALID;
+    return launch_trunk(engine, weights, biases, num_blocks, nullptr, head_conv_w, head_conv_b, fc_policy_w, fc_policy_b, fc_value_w,
+                        fc_value_b, logits, values, stream);
 }
 
 }  // extern "C"

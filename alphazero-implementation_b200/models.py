@@ -318,6 +318,22 @@ def pack_trunk_weights(model: "ResNet", device) -> tuple[Tensor, Tensor]:
     return torch.cat(parts).contiguous(), torch.stack(biases).contiguous().float()
 
 
+def pack_head_weights(model: "ResNet", device):
+    """Policy conv1x1 (-> 32) and value conv3x3 (-> 3), BatchNorm folded, as ONE 48-output 3x3 conv for csrc/az_conv.cu
+    (the 1x1 weights occupy the centre tap), plus the two fully connected layers in fp32."""
+    m = copy.deepcopy(model).eval().float().to(device)
+    wp, bp = _fold_bn(m.policy_head[0], m.policy_head[1])  # [32, 64, 1, 1]
+    wv, bv = _fold_bn(m.value_head[0], m.value_head[1])    # [3, 64, 3, 3]
+    w = torch.zeros(48, 64, 3, 3, device=device)
+    w[:32, :, 1, 1] = wp[:, :, 0, 0]
+    w[32:35] = wv
+    b = torch.zeros(48, device=device)
+    b[:32], b[32:35] = bp, bv
+    conv = torch.cat([_canonical_kmajor(w[:, :, ky, kx]) for ky in range(3) for kx in range(3)]).contiguous()
+    f = lambda t: t.detach().float().contiguous()
+    return conv, b.contiguous(), f(m.policy_head[4].weight), f(m.policy_head[4].bias), f(m.value_head[4].weight).reshape(-1), f(m.value_head[4].bias)
+
+
 class TensorCoreTrunk:
     """Stem + residual blocks of a 64-channel ResNet as one tcgen05 kernel on the engine's leaves (csrc/az_conv.cu)."""
 
@@ -329,8 +345,26 @@ class TensorCoreTrunk:
         self.num_blocks = model.num_res_blocks
         self.weights, self.biases = pack_trunk_weights(model, self.device)
         assert self.weights.numel() * 2 == self.lib.az_trunk_weight_bytes(self.num_blocks)
+        self.heads = pack_head_weights(model, self.device)
         self._out: dict[int, Tensor] = {}
+        self._lv: dict[int, tuple[Tensor, Tensor]] = {}
         self.launches = 0
+
+    def forward_leaves_full(self, engine) -> tuple[Tensor, Tensor]:
+        """Trunk AND heads in the one kernel -> (logits [n,7] f32, values [n,2] f32) for the engine's current leaves."""
+        n = engine.n_active
+        if n not in self._lv:
+            self._lv[n] = (torch.empty((n, 7), device=self.device), torch.empty((n, 2), device=self.device))
+        logits, values = self._lv[n]
+        hw, hb, fpw, fpb, fvw, fvb = self.heads
+        rc = self.lib.az_resnet_forward_leaves(engine.h, self.weights.data_ptr(), self.biases.data_ptr(), self.num_blocks,
+                                               hw.data_ptr(), hb.data_ptr(), fpw.data_ptr(), fpb.data_ptr(), fvw.data_ptr(),
+                                               fvb.data_ptr(), logits.data_ptr(), values.data_ptr(),
+                                               torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"az_resnet_forward_leaves failed ({rc})")
+        self.launches += 1
+        return logits, values
 
     def forward_leaves(self, engine) -> Tensor:
         """-> trunk activations [n, 64, 6, 7] bf16 (channels-last memory) for the leaves of `engine.select_leaves()`."""
@@ -418,10 +452,7 @@ class InferenceNet(nn.Module):
         """Evaluate the engine's current leaves without a separate gather launch (tensor-core kernels only)."""
         if self.fused is not None:
             return self.fused.forward_leaves(engine)
-        h = self.trunk.forward_leaves(engine)  # [n, 64, 6, 7] bf16, channels-last
-        logits = self.net.policy_head(h)
-        v = torch.tanh(self.net.value_head(h))
-        return logits.float().contiguous(), torch.cat([v, -v], dim=1).float().contiguous()
+        return self.trunk.forward_leaves_full(engine)  # trunk + heads, one tcgen05 kernel
 
     @property
     def evaluates_leaves_directly(self) -> bool:

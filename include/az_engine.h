@@ -233,6 +233,13 @@ int64_t az_mlp_launch_count(const az_mlp *m);
 int64_t az_trunk_weight_bytes(int32_t num_blocks);
 int32_t az_trunk_forward_leaves(az_engine *engine, const void *packed_weights, const float *biases /*[1+2*num_blocks][64]*/,
                                 int32_t num_blocks, void *out, void *stream);
+/* trunk + policy / value heads in the same kernel -> logits [E][7], values [E][2] (tanh, [v, -v] as cnn.py:73), the inputs
+ * of az_expand_backup.  head_conv_w: 9 taps x [48 out][64 in] bf16 MMA operands (rows 0..31 = policy conv1x1 in the centre tap,
+ * rows 32..34 = value conv3x3, BatchNorm folded); head_conv_b [48]; fc_* fp32 in nn.Linear layout ([7][1344], [7], [126], [1]). */
+int32_t az_resnet_forward_leaves(az_engine *engine, const void *packed_weights, const float *biases, int32_t num_blocks,
+                                 const void *head_conv_w, const float *head_conv_b, const float *fc_policy_w,
+                                 const float *fc_policy_b, const float *fc_value_w, const float *fc_value_b, float *logits,
+                                 float *values, void *stream);
 
 #ifdef __cplusplus
 }

@@ -90,3 +90,37 @@ def test_resnet_in_the_search_loop_matches_library_path():
         assert all(sum(v) == 95 for v in out[-1])
     for a, b in zip(*out):
         assert max(abs(x - y) for x, y in zip(a, b)) <= 10
+
+
+@pytest.mark.parametrize("blocks,n", [(0, 8), (2, 77), (4, 1000)])
+def test_full_net_kernel_matches_pytorch_reference(blocks, n):
+    """Trunk + fused heads (policy conv1x1 + FC, value conv3x3 + FC + tanh) vs the fp32 PyTorch module evaluated on the
+    bf16-emulated trunk: logits / values within bf16 noise, and vs the plain fp32 module within the bf16 budget."""
+    torch.manual_seed(7 * blocks + n)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = az.ResNet(num_res_blocks=blocks, num_channels=64).cuda().eval()
+    _randomise_bn(model)
+    eng = _engine_with_leaves(n, seed=n + 1)
+    live = eng.leaf_info()["status"] == 0
+    x = eng.gather_leaves(LAYOUT_PLANES_F32)
+    trunk = TensorCoreTrunk(model, torch.device("cuda", torch.cuda.current_device()))
+    logits, values = trunk.forward_leaves_full(eng)
+    torch.cuda.synchronize()
+    r = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    with torch.no_grad():
+        h = _reference_trunk(model, x)
+        wp, bp = _fold_bn(model.policy_head[0], model.policy_head[1])
+        wv, bv = _fold_bn(model.value_head[0], model.value_head[1])
+        pa = torch.relu(F.conv2d(h, r(wp), bp))
+        va = torch.relu(F.conv2d(h, r(wv), bv, padding=1))
+        l_ref = model.policy_head[4](pa.flatten(1))
+        v_ref = torch.tanh(model.value_head[4](va.flatten(1)))
+        l_fp32, v_fp32 = model(x)
+    assert torch.isfinite(logits).all() and torch.isfinite(values).all()
+    assert torch.allclose(logits[live], l_ref[live], atol=3e-2, rtol=2e-2), float((logits[live] - l_ref[live]).abs().max())
+    assert torch.allclose(values[live, :1], v_ref[live], atol=2e-2), float((values[live, :1] - v_ref[live]).abs().max())
+    assert torch.equal(values[:, 1], -values[:, 0])
+    assert float((torch.softmax(logits[live], 1) - torch.softmax(l_fp32[live], 1)).abs().max()) < 5e-2
+    assert float((values[live] - v_fp32[live]).abs().max()) < 8e-2
+    eng.close()
