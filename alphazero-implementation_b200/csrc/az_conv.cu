@@ -350,26 +350,32 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
         }
         tc_fence_before();
         __syncthreads();
-        // thread = (position, output, quarter of the dot product); 8 outputs = 7 logits + the value
+        // warp = position; lanes stride over the 1344 (policy) / 126 (value) inputs with coalesced weight reads and
+        // seven independent accumulators, then a shuffle reduction
         {
-            const int pos = tid >> 5, j = (tid >> 2) & 7, part = tid & 3;
+            const int pos = warp, lane = tid & 31;
             const long long gp = pos0 + pos;
-            float acc = 0.f;
-            if (j < 7) {
-                const float *w = fc_policy_w + (size_t)j * (32 * 42);
-                const float *a = hact + pos * NHU * 42;
-                for (int i = part; i < 32 * 42; i += 4) acc += __ldg(w + i) * a[i];
-            } else {
-                const float *a = hact + (pos * NHU + 32) * 42;
-                for (int i = part; i < 3 * 42; i += 4) acc += __ldg(fc_value_w + i) * a[i];
+            const float *a = hact + pos * NHU * 42;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+            for (int i = lane; i < 32 * 42; i += 32) {
+                const float x = a[i];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) acc[j] = fmaf(__ldg(fc_policy_w + j * (32 * 42) + i), x, acc[j]);
             }
-            acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
-            acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
-            if (part == 0 && gp < n) {
-                if (j < 7) {
-                    logits[gp * 7 + j] = acc + __ldg(fc_policy_b + j);
-                } else {
-                    const float v = tanhf(acc + __ldg(fc_value_b));
+            for (int i = lane; i < 3 * 42; i += 32) acc[7] = fmaf(__ldg(fc_value_w + i), a[32 * 42 + i], acc[7]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) acc[j] += __shfl_xor_sync(0xFFFFFFFFu, acc[j], off);
+            if (gp < n) {
+                if (lane < 7) {
+                    float v = acc[0];
+#pragma unroll
+                    for (int j = 1; j < 7; ++j) v = lane == j ? acc[j] : v;
+                    logits[gp * 7 + lane] = v + __ldg(fc_policy_b + lane);
+                } else if (lane == 7) {
+                    const float v = tanhf(acc[7] + __ldg(fc_value_b));
                     values[gp * 2] = v;
                     values[gp * 2 + 1] = -v;
                 }
