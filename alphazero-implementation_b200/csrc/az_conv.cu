@@ -13,8 +13,14 @@
 // keeps the border zero for the next layer).  8 positions = 576 pixels = 5 accumulator tiles of 128 rows x 64
 // fp32 columns in tensor memory.  Per layer one thread issues 9 taps x 5 tiles x 4 K-steps tcgen05.mma; the
 // tap weights ([64 out][64 in] bf16, 8 KB, packed once per weight update) stream through a 4-stage ring filled
-// by bulk async copies.  Epilogue (4 warps = the 128 accumulator lanes): tcgen05.ld, bias (+ skip) + ReLU in
-// fp32, round to bf16, write the next layer's A operand.  The leaf gather is fused in: the stem's input planes
+// by bulk async copies.  Epilogue (8 warps: two per 32 accumulator lanes, half the channels each): tcgen05.ld, bias
+// (+ skip) + ReLU in fp32, round to bf16, write the next layer's A operand.  After the last block the policy conv1x1 and the
+// value conv3x3 run as one 48-channel conv layer (the 1x1 weights in the centre tap) and the two small FC layers on CUDA cores.
+// Measured (ncu, 16384 positions, 4 blocks): 1.35 ms trunk, tensor pipe 24-28 % active; a 128x64x16 MMA takes ~65 cycles, not the
+// 32-cycle floor, because it fetches 6 KB of operands from shared memory (~96 B/clk): with 64 output channels the conv MMAs are
+// shared-memory-operand-bound.  A software-pipelined variant (issuer warp + two position groups so that one group's epilogue
+// overlaps the other's MMAs) was built and is bit-identical but ran SLOWER (2.4-2.6 ms): the MMAs slow down to ~97 ns each when
+// the epilogue warps' shared-memory traffic competes with the operand fetch; it was removed.  The leaf gather is fused in: the stem's input planes
 // (empty / side to move / opponent, cnn.py:93-95) are built from the engine's leaf bitboards.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -44,7 +50,7 @@ constexpr uint32_t SBO_W = (C / 8) * 128;            // 1024 (canonical K-major 
 constexpr uint32_t LBO_W = 128;
 constexpr uint32_t STEM_TAP_BYTES = C * 16 * 2;      // 2048: stem tap [64][16]
 constexpr uint32_t SBO_WS = (16 / 8) * 128;          // 256
-constexpr int NS = 4;                                // weight ring stages
+constexpr int NS = 4;                                // weight ring stages (6 measured no faster: the MMAs, not the copies, pace a layer)
 constexpr int NHC = 48;                              // head conv channels: 32 policy (1x1, centre tap) + 3 value (3x3) + padding
 constexpr uint32_t HEAD_TAP_BYTES = NHC * C * 2;     // 6144
 constexpr int NHU = 35;                              // head channels actually used
