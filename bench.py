@@ -65,44 +65,57 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampled every 200 ms during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a thread (the timed
+    region of this workload lasts only milliseconds, far below nvidia-smi's own start-up time)."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self, index: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+
+        self.samples, self.reason_bits, self.power = [], 0, []
+        self.stop_flag = False
+        self.ok = False
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as exc:  # pragma: no cover
+            self.err = repr(exc)
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self) -> dict:
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        rows = [ln.strip().split(", ") for ln in open(self.f.name) if ln.strip()]
-        os.unlink(self.f.name)
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for nm, v in zip(names, r[3:7]):
-                if v.strip() == "Active":
-                    reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        sm = sorted(self.samples)
+        reasons = sorted(k for k, bit in self.REASONS.items() if self.reason_bits & bit)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "power_w_max": max(self.power) if self.power else None,
+                "samples": len(sm), "reasons": reasons, "source": "NVML polled every 2 ms during the timed region"}
 
 
 def algorithmic_bytes(st: dict) -> int:
@@ -167,8 +180,8 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 def net_in_loop(args, device_index: int, peaks: dict):
     """Side measurements with a network in the loop (BASELINE configs[2]): self-play move steps of E games x S sims, one
-    evaluator call per simulation step.  `resnetBxC`: bf16 ResNet-style net, conv/linear layers = cuDNN/cuBLAS tensor-core
-    GEMMs.  `basic_tc`: the reference's BasicNN on the hand-written tcgen05 kernel (csrc/az_mlp.cu, leaf gather fused)."""
+    evaluator call per simulation step.  `resnetBx64`: bf16 ResNet-style net on the hand-written tcgen05 kernel (csrc/az_conv.cu: trunk + heads,
+    leaf gather fused); other widths: conv/linear layers = cuDNN/cuBLAS tensor-core GEMMs.  `basic_tc`: the reference's BasicNN on the hand-written tcgen05 kernel (csrc/az_mlp.cu, leaf gather fused)."""
     import torch
 
     import alphazero_implementation_b200 as az
@@ -183,7 +196,8 @@ def net_in_loop(args, device_index: int, peaks: dict):
         else:
             b, c = spec.replace("resnet", "").split("x")
             model = az.ResNet(num_res_blocks=int(b), num_channels=int(c))
-            name, flops = f"ResNet {b}x{c} (bf16, cuDNN)", model.flops_per_position()
+            how = "tcgen05 fused kernel" if int(c) == 64 else "cuDNN"
+            name, flops = f"ResNet {b}x{c} (bf16, {how})", model.flops_per_position()
         E, S = args.net_games, args.net_sims
         torch.manual_seed(0)
         search = az.AlphaZeroSearch(model=model, num_simulations=S, device=device_index, **kw)
@@ -226,6 +240,7 @@ def run_b200(args):
     import alphazero_implementation_b200 as az
     from alphazero_implementation_b200.engine import EVAL_HASH, EVAL_UNIFORM
 
+    os.environ["NCCL_DEBUG"] = "WARN"  # NCCL_DEBUG=VERSION/INFO prints to stdout; stdout carries exactly one JSON line
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
