@@ -8,11 +8,12 @@
 `lightning` is not required: `Model` is a plain `nn.Module` exposing the hooks a Lightning trainer calls.
 Parameter names match the reference classes, so their checkpoints' `state_dict`s load unchanged.
 
-What runs where: plane encoding (`_states_to_tensor`) and the legal-only softmax of `predict` are CUDA
-kernels of libaz_engine.so (`az_encode_states`, `az_masked_softmax`); the conv / linear layers are
-library GEMMs (cuBLAS / cuDNN through torch).  For the search hot path `InferenceNet` folds BatchNorm
-into the convolutions and runs them in bf16 channels-last so that only the conv/GEMM layers touch the
-tensor cores; softmax / tanh epilogues stay in fp32.
+What runs where: plane encoding (`_states_to_tensor`) and the legal-only softmax of `predict` are CUDA kernels of
+libaz_engine.so (`az_encode_states`, `az_masked_softmax`).  On the search hot path `InferenceNet` picks the evaluator:
+`BasicNN` in bf16 -> `TensorCoreMLP` (csrc/az_mlp.cu) and 64-channel `ResNet`s in bf16 -> `TensorCoreTrunk`
+(csrc/az_conv.cu), both hand-written tcgen05/TMEM kernels with the leaf gather fused in; every other model runs its
+conv / linear layers as library GEMMs (cuBLAS / cuDNN through torch) with BatchNorm folded, bf16 channels-last, so that
+only the conv/GEMM layers touch the tensor cores; softmax / tanh epilogues stay in fp32.
 """
 from __future__ import annotations
 

@@ -159,3 +159,37 @@ def test_simulation_budget_is_enforced():
     eng.reset_games()
     eng.run_simulations(50, 2)
     eng.close()
+
+
+@pytest.mark.parametrize("E,S", [(16384, 800), (65536, 800)])
+def test_full_size_configs_by_invariants(oracle, E, S):
+    """BASELINE configs 3 / 4 sizes (16384 and 65536 trees x 800 sims): too large for the CPU oracle in a test, so
+    checked through size-independent properties — every root has N = S and child visits summing to S - 1 (App. A.4),
+    visits only on legal columns, identical roots give identical trees, and a random sample of trees is bit-exact
+    against the oracle."""
+    rng = np.random.RandomState(E)
+    n_distinct = 64
+    b0d, b1d, pld = _random_roots(oracle, n_distinct, seed=E, max_depth=20)
+    pick = rng.randint(0, n_distinct, E)
+    b0, b1, pl = b0d[pick], b1d[pick], pld[pick]
+    eng = Engine(num_games=E, num_simulations=S)
+    eng.set_roots(b0, b1, pl)
+    eng.run_simulations(S, 2)
+    st = _np(eng.root_stats())
+    assert (st["root_N"] == S).all() and (st["child_N"].sum(1) == S - 1).all() and (st["err"] == 0).all()
+    legal_bits = ((st["legal"][:, None] >> np.arange(7)[None, :]) & 1).astype(bool)
+    assert (st["child_N"][~legal_bits] == 0).all()
+    # identical roots -> identical statistics, wherever the slot sits in the arena
+    first = {}
+    for i, p in enumerate(pick[:4096]):
+        j = first.setdefault(int(p), i)
+        assert (st["child_N"][i] == st["child_N"][j]).all() and (st["child_W"][i] == st["child_W"][j]).all()
+    ref = oracle.search(b0d, b1d, pld, S, eval_kind=2)
+    for p in range(n_distinct):
+        i = first.get(p)
+        if i is None:
+            continue
+        assert (st["child_N"][i] == ref["child_N"][p]).all() and (st["child_W"][i] == ref["child_W"][p]).all()
+    s = eng.stats()
+    assert s["simulations"] == E * S and s["backup_nodes"] == s["levels"] + s["simulations"]
+    eng.close()
