@@ -327,7 +327,8 @@ def sort_episode_batch(d: dict) -> EpisodeBatch:
     new_off = np.zeros(len(order), np.int64)
     if len(order):
         new_off[1:] = np.cumsum(ep_len[:-1])
-    idx = np.concatenate([np.arange(o, o + l) for o, l in zip(old_off, ep_len)]) if len(order) else np.zeros(0, np.int64)
+    # sample i of the sorted batch comes from old position i + (old offset - new offset of its episode)
+    idx = (np.arange(int(ep_len.sum()), dtype=np.int64) + np.repeat(old_off - new_off, ep_len)) if len(order) else np.zeros(0, np.int64)
     return EpisodeBatch(
         ep_slot=d["ep_slot"][order], ep_step=d["ep_step"][order], ep_len=ep_len, ep_offset=new_off,
         ep_outcome=d["ep_outcome"][order], s_bb0=d["s_bb0"][idx].view(np.uint64), s_bb1=d["s_bb1"][idx].view(np.uint64),
