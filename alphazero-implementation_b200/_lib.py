@@ -79,6 +79,7 @@ SIGNATURES = {
     "az_create": (I32, [C.POINTER(AzConfig), C.POINTER(P)]),
     "az_destroy": (I32, [P]),
     "az_device_bytes": (I64, [P]),
+    "az_device": (I32, [P]),
     "az_env_step": (I32, [P, P, P, P, P, I64, P, P, P, P, P, P, P, P]),
     "az_state_info": (I32, [P, P, P, P, I64, P, P, P, P]),
     "az_masked_softmax": (I32, [P, P, P, I64, P, P]),

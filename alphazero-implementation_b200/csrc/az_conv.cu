@@ -408,10 +408,12 @@ static int32_t launch_trunk(az_engine *engine, const void *weights, const float 
     const uint8_t *status = nullptr, *player = nullptr;
     int32_t n = 0;
     if (az_leaf_arrays(engine, &bb0, &bb1, &status, &n) != AZ_OK || az_leaf_players(engine, &player) != AZ_OK || n <= 0) return AZ_E_INVALID;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // the opt-in to > 48 KB of dynamic shared memory is per device
+    const int dev = az_device(engine);
+    if (dev < 0 || dev >= 64 || cudaSetDevice(dev) != cudaSuccess) return AZ_E_CUDA;
+    if (!attr_set[dev]) {
         if (cudaFuncSetAttribute(k_resnet_trunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
-        attr_set = true;
+        attr_set[dev] = true;
     }
     const int blocks = (n + P - 1) / P;
     k_resnet_trunk<<<blocks, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(bb0, bb1, player, status, n, (const uint8_t *)weights, biases,

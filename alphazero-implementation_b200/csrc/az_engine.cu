@@ -1195,6 +1195,7 @@ int32_t az_destroy(az_engine *h) {
 }
 
 int64_t az_device_bytes(const az_engine *h) { return h ? h->bytes : 0; }
+int32_t az_device(const az_engine *h) { return h ? h->cfg.device : -1; }
 int64_t az_launch_count(const az_engine *h) { return h ? h->launches : 0; }
 int32_t az_tree_capacity(const az_engine *h) { return h ? h->a.cap : 0; }
 

@@ -102,6 +102,8 @@ int32_t az_create(const az_config *cfg, az_engine **out);
 int32_t az_destroy(az_engine *h);
 /* bytes of device memory the engine allocated */
 int64_t az_device_bytes(const az_engine *h);
+/* CUDA device ordinal the engine lives on */
+int32_t az_device(const az_engine *h);
 
 /* ---- game rules (stand-alone; replaces third-party simulator.game.connect) ---- */
 /* Action.sample_next_state() (search.py:89, node.py:38) on n boards, plus the successor's
