@@ -89,3 +89,19 @@ def episodes_from_batch(batch, num_simulations: int) -> list[Episode]:
             ep.add_sample(Sample(state=st, policy=policy, value=value))
         out.append(ep)
     return out
+
+
+def save_episodes(episodes: list[Episode], path: str) -> None:
+    """`episodes_iter{N}.json` writer (DataModule.save_episodes, datamodule.py:71-80): a JSON list of `Episode.to_dict()`."""
+    import json
+
+    with open(path, "w") as f:
+        json.dump([ep.to_dict() for ep in episodes], f)
+
+
+def load_episodes(path: str) -> list[Episode]:
+    """Reader for the same file (DataModule.load_episodes, datamodule.py:82-87)."""
+    import json
+
+    with open(path) as f:
+        return [Episode.from_dict(d) for d in json.load(f)]

@@ -115,7 +115,8 @@ class _GraphedStep:
             side = torch.cuda.Stream(device=e.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                with torch.cuda.graph(g, stream=side):
+                # thread_local: a training thread may allocate while the self-play thread captures (trainer.py overlap)
+                with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
                     self.step()
             torch.cuda.current_stream().wait_stream(side)
             self.graph = g

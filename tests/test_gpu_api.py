@@ -211,10 +211,10 @@ def test_training_iteration_reduces_loss_and_syncs_weights():
     np.random.seed(0)
     model = az.BasicNN()
     tr = Trainer(model)
-    hist = tr.train(num_iterations=2, episodes_per_iter=32, simulations_per_episode=32, epochs_per_iter=3,
+    hist = tr.train(num_iterations=3, episodes_per_iter=32, simulations_per_episode=32, epochs_per_iter=3,
                     initial_state=az.Config(6, 7, 4).sample_initial_state(), buffer_size=64)
-    assert len(hist) == 2 and hist[0]["episodes"] == 32 and hist[1]["episodes"] == 64
-    assert hist[0]["samples"] >= 32 * 7 and hist[1]["loss"] < hist[0]["loss"]
+    assert len(hist) == 3 and hist[0]["episodes"] == 32 and hist[1]["episodes"] == 64
+    assert hist[0]["samples"] >= 32 * 7 and hist[2]["loss"] < hist[0]["loss"]
 
 
 def test_replay_buffer_targets_match_reference_format(selfplay_goldens):

@@ -51,3 +51,23 @@ def test_sort_episode_batch_orders_by_step_then_slot():
     assert b.s_bb0.tolist() == [3, 4, 5, 2, 0, 1]
     assert b.ep_outcome.tolist() == [[-1, 1], [0, 0], [1, -1]]
     assert b.num_samples == 6 and len(b) == 3
+
+
+def test_episode_file_round_trip(tmp_path):
+    from alphazero_implementation_b200.episode import load_episodes, save_episodes
+
+    cfg = Config(6, 7, 4)
+    eps = []
+    for k in range(3):
+        s = State(cfg, 1 << (7 * k), 1 << (7 * k + 1), 0, legal=0x7F, ended=False, reward=(0, 0))
+        ep = Episode()
+        ep.add_sample(Sample(s, {Action(s, c): 1 / 7 for c in range(7)}, [0.0, 0.0]))
+        ep.backpropagate_outcome([-1.0, 1.0])
+        eps.append(ep)
+    path = tmp_path / "episodes_iter1.json"
+    save_episodes(eps, str(path))
+    raw = json.load(open(path))
+    assert isinstance(raw, list) and set(raw[0]) == {"samples"} and set(raw[0]["samples"][0]) == {"state", "policy", "value"}
+    back = load_episodes(str(path))
+    assert [e.samples[0].state for e in back] == [e.samples[0].state for e in eps]
+    assert back[2].samples[0].value == [-1.0, 1.0]
