@@ -92,6 +92,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
         "}" ::"r"(bar), "r"(phase)
         : "memory");
 }
+// one lane of a converged warp (the caller keeps every operand warp-uniform, so the MMA operands stay in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -121,10 +127,13 @@ struct Pipe {
 __device__ __forceinline__ void pipe_load(const Pipe &p, uint32_t gj, const uint8_t *src, uint32_t bytes) {
     const uint32_t st = gj % NS;
     if (gj >= NS) mbar_wait(p.empty[st], ((gj / NS) - 1u) & 1u);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(p.full[st]), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(p.stage[st]),
-                 "l"(src), "r"(bytes), "r"(p.full[st])
-                 : "memory");
+    if (elect_one()) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(p.full[st]), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(p.stage[st]),
+                     "l"(src), "r"(bytes), "r"(p.full[st])
+                     : "memory");
+    }
+    __syncwarp();
 }
 
 // row index inside a CTA -> is it a real board cell, and which (position, y, x)
@@ -137,7 +146,7 @@ __device__ __forceinline__ bool decode_row(int r, int &pos, int &y, int &x) {
     return r < ROWS && py >= 1 && py <= c4::H && px >= 1 && px <= c4::W;
 }
 
-// One conv layer's MMAs (thread 0): 9 taps x TILES x ksteps.  A = `a_addr` (row 0 of the buffer, after the guard).
+// One conv layer's MMAs (warp 0, converged; one elected lane issues): 9 taps x TILES x ksteps.  A = `a_addr` (row 0 of the buffer, after the guard).
 __device__ __forceinline__ void conv_mmas(Pipe &p, const uint8_t *w, uint32_t tap_bytes, uint32_t ksteps, uint32_t sbo_w,
                                           uint32_t a_addr, uint32_t tmem_base, bool prefetched, int n_out = C) {
     const uint32_t idesc = instr_desc(128, n_out);
@@ -152,21 +161,25 @@ __device__ __forceinline__ void conv_mmas(Pipe &p, const uint8_t *w, uint32_t ta
         // descriptors differ only in the start-address field (low 14 bits, 16-byte units): build once, add offsets
         const uint64_t a_base = smem_desc(a_tap, LBO_A, SBO_A), b_base = smem_desc(p.stage[st], LBO_W, sbo_w);
         const uint32_t acc0 = tap > 0;
-        if (ksteps == 1) {
+        if (elect_one()) {
+            if (ksteps == 1) {
 #pragma unroll
-            for (uint32_t t = 0; t < TILES; ++t) umma(tmem_base + t * C, a_base + t * (128 * ROWB >> 4), b_base, idesc, acc0);
-        } else {
+                for (uint32_t t = 0; t < TILES; ++t) umma(tmem_base + t * C, a_base + t * (128 * ROWB >> 4), b_base, idesc, acc0);
+            } else {
 #pragma unroll
-            for (uint32_t t = 0; t < TILES; ++t)
+                for (uint32_t t = 0; t < TILES; ++t)
 #pragma unroll
-                for (uint32_t ks = 0; ks < C / 16; ++ks)
-                    umma(tmem_base + t * C, a_base + t * (128 * ROWB >> 4) + ks * (2 * LBO_A >> 4), b_base + ks * (2 * LBO_W >> 4), idesc,
-                         acc0 | (ks > 0));
+                    for (uint32_t ks = 0; ks < C / 16; ++ks)
+                        umma(tmem_base + t * C, a_base + t * (128 * ROWB >> 4) + ks * (2 * LBO_A >> 4), b_base + ks * (2 * LBO_W >> 4), idesc,
+                             acc0 | (ks > 0));
+            }
+            umma_commit(p.empty[st]);
         }
-        umma_commit(p.empty[st]);
+        __syncwarp();
         if (tap + NS < 9) pipe_load(p, gi + NS, w + (size_t)(tap + NS) * tap_bytes, tap_bytes);
     }
-    umma_commit(p.done);
+    if (elect_one()) umma_commit(p.done);
+    __syncwarp();
     p.g += 9;
 }
 
@@ -237,8 +250,10 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
     if (tid == 0) {
         for (int i = 0; i < 2 * NS + 1; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (uint32_t i = 0; i < NS; ++i) pipe_load(p, i, weights + (size_t)i * STEM_TAP_BYTES, STEM_TAP_BYTES);
     }
+    __syncwarp();
+    if (warp == 0)
+        for (uint32_t i = 0; i < NS; ++i) pipe_load(p, i, weights + (size_t)i * STEM_TAP_BYTES, STEM_TAP_BYTES);
     // zero both activation buffers (borders, guards and the unused K groups of the stem input must be zero)
     for (uint32_t i = tid; i < 2 * BUF_BYTES / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     const int n_layers = 1 + 2 * num_blocks;
@@ -270,7 +285,7 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
     const uint8_t *w_layer = weights + 9 * STEM_TAP_BYTES;  // first trunk layer's weights
 
     // ---- stem: buf[1] (16 input channels, 3 used) -> buf[0]
-    if (tid == 0) {
+    if (warp == 0) {
         conv_mmas(p, weights, STEM_TAP_BYTES, 1, SBO_WS, a1, tmem_base, true);
         if (num_blocks > 0)
             for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w_layer + (size_t)i * TAP_BYTES, TAP_BYTES);
@@ -291,7 +306,7 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
             tc_fence_before();
             __syncthreads();
             tc_fence_after();
-            if (tid == 0) {
+            if (warp == 0) {
                 conv_mmas(p, w_layer, TAP_BYTES, C / 16, SBO_W, half == 0 ? a0 : a1, tmem_base, true);
                 const bool last = (blk == num_blocks - 1 && half == 1);
                 if (!last)
@@ -328,7 +343,7 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        if (tid == 0) conv_mmas(p, head_w, HEAD_TAP_BYTES, C / 16, SBO_W, a0, tmem_base, true, NHC);
+        if (warp == 0) conv_mmas(p, head_w, HEAD_TAP_BYTES, C / 16, SBO_W, a0, tmem_base, true, NHC);
         mbar_wait(p.done, done_phase);
         done_phase ^= 1;
         tc_fence_after();
