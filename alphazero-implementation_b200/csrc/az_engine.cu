@@ -200,10 +200,9 @@ __device__ __forceinline__ Leaf descend(const TreeMem &tm, const double *__restr
     L.first_col = 0;
     bool go = alive && cb != 0;
     bool my_legal = (legal >> c) & 1u;
-    double sq = __ldg(sqt + n_parent);  // sqrt(node.visit_count): fetched as soon as the parent's N is known
     while (__any_sync(FULL, go)) {
         double score = -INFINITY;
-        if (go && my_legal) score = puct_score(ch.n, ch.w, ch.p, sq, c_puct, rcp);
+        if (go && my_legal) score = puct_score(ch.n, ch.w, ch.p, __ldg(sqt + n_parent), c_puct, rcp);
         const int bc = argmax_first(score, sub);
         const uint32_t n_sel = __shfl_sync(FULL, ch.n, sub + bc);
         const uint32_t cb_sel = __shfl_sync(FULL, ch.cb, sub + bc);
@@ -222,7 +221,6 @@ __device__ __forceinline__ Leaf descend(const TreeMem &tm, const double *__restr
             cb = cb_sel;
             go = cb != 0;
         }
-        sq = __ldg(sqt + n_sel);  // for the next level; overlaps the position replay and the child load
         // the children of the node just entered
         const uint64_t occ = L.b0 | L.b1;
         const bool can = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);

@@ -81,6 +81,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
         "}" ::"r"(bar), "r"(phase)
         : "memory");
 }
+// one lane of a converged warp (the caller keeps every operand warp-uniform, so the MMA operands stay in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -112,7 +118,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&p);
 }
 
-// ---- weight pipeline (thread 0 only): bulk async copies (TMA, 1-D) fill two shared-memory stages; an mbarrier
+// ---- weight pipeline (warp 0, converged; one elected lane issues): bulk async copies (TMA, 1-D) fill two shared-memory stages; an mbarrier
 // per stage reports the bytes landed ("full"); tcgen05.commit reports when the MMAs that read a stage are done ("empty").
 struct Pipe {
     uint32_t full[NS], empty[NS], done;  // shared-memory addresses of the mbarriers
@@ -123,10 +129,13 @@ struct Pipe {
 __device__ __forceinline__ void pipe_load(const Pipe &p, uint32_t gj, const uint8_t *src, uint32_t bytes) {
     const uint32_t st = gj % NS;
     if (gj >= NS) mbar_wait(p.empty[st], ((gj / NS) - 1u) & 1u);  // the MMAs of the previous use have finished reading
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(p.full[st]), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(p.stage[st]),
-                 "l"(src), "r"(bytes), "r"(p.full[st])
-                 : "memory");
+    if (elect_one()) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(p.full[st]), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(p.stage[st]),
+                     "l"(src), "r"(bytes), "r"(p.full[st])
+                     : "memory");
+    }
+    __syncwarp();
 }
 
 // One layer: D[128 x N] (+)= A[128 x K] . W[N x K]^T with W streamed in `nchunks` chunks of `chunk_bytes`.
@@ -137,17 +146,21 @@ __device__ __forceinline__ void pipe_layer(Pipe &p, const uint8_t *src, uint32_t
         const uint32_t gi = p.g + i, st = gi % NS;
         mbar_wait(p.full[st], (gi / NS) & 1u);
         tc_fence_after();
-        for (uint32_t ks = 0; ks < ksteps; ++ks)
-            for (uint32_t half = 0; half < n_halves; ++half)
-                umma(tmem_base + half * 256, smem_desc(a_addr + (i * ksteps + ks) * 2 * LBO, a_sbo),
-                     // inside a stage: [rows][KC] sub-chunks back to back; K step ks -> sub-chunk ks / (KC/16), part ks % (KC/16)
-                     smem_desc(p.stage[st] + half * (256 / 8) * SBO_CHUNK + (ks / (KC / 16)) * (NH * KC * 2) + (ks % (KC / 16)) * 2 * LBO,
-                               SBO_CHUNK),
-                     idesc, (i | ks) > 0);
-        umma_commit(p.empty[st]);
+        if (elect_one()) {
+            for (uint32_t ks = 0; ks < ksteps; ++ks)
+                for (uint32_t half = 0; half < n_halves; ++half)
+                    umma(tmem_base + half * 256, smem_desc(a_addr + (i * ksteps + ks) * 2 * LBO, a_sbo),
+                         // inside a stage: [rows][KC] sub-chunks back to back; K step ks -> sub-chunk ks / (KC/16), part ks % (KC/16)
+                         smem_desc(p.stage[st] + half * (256 / 8) * SBO_CHUNK + (ks / (KC / 16)) * (NH * KC * 2) + (ks % (KC / 16)) * 2 * LBO,
+                                   SBO_CHUNK),
+                         idesc, (i | ks) > 0);
+            umma_commit(p.empty[st]);
+        }
+        __syncwarp();
         if (i + NS < nchunks) pipe_load(p, gi + NS, src + (size_t)(i + NS) * chunk_bytes, chunk_bytes);
     }
-    umma_commit(p.done);
+    if (elect_one()) umma_commit(p.done);
+    __syncwarp();
     p.g += nchunks;
 }
 
@@ -212,8 +225,10 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
 #pragma unroll
         for (int i = 0; i < 2 * NS + 1; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (uint32_t i = 0; i < K1 / KC && i < NS; ++i) pipe_load(p, i, w1p + (size_t)i * STAGE_BYTES, STAGE_BYTES);  // layer-1 weights
     }
+    __syncwarp();
+    if (warp == 0)
+        for (uint32_t i = 0; i < K1 / KC && i < NS; ++i) pipe_load(p, i, w1p + (size_t)i * STAGE_BYTES, STAGE_BYTES);  // layer-1 weights
     // input tile: raw grid values (-1 / 0 / 1, exact in bf16) as a [128][64] K-major tile, zero padded
     for (uint32_t i = tid; i < 2 * HID; i += TILE_M) s_bias[i] = i < HID ? __ldg(b1 + i) : __ldg(b2 + i - HID);
     if (FROM_LEAVES) {
@@ -261,7 +276,7 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
     const uint32_t act_addr = smem_u32(act);
 
     // ---- layer 1: [128 x 64] . [512 x 64]^T
-    if (tid == 0) {
+    if (warp == 0) {
         pipe_layer(p, w1p, K1 / KC, STAGE_BYTES, KC / 16, act_addr, SBO_X, 2, instr_desc(128, 256), tmem_base);
         for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w2p + (size_t)i * STAGE_BYTES, STAGE_BYTES);  // prefetch layer 2 behind the epilogue
     }
@@ -274,7 +289,7 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
     tc_fence_after();
 
     // ---- layer 2: [128 x 512] . [512 x 512]^T, K in chunks of KC
-    if (tid == 0) {
+    if (warp == 0) {
         pipe_layer(p, w2p, HID / KC, STAGE_BYTES, KC / 16, act_addr, SBO_ACT, 2, instr_desc(128, 256), tmem_base);
         pipe_load(p, p.g, whp, WH_ELEMS * 2);  // head weights: one 16 KB "chunk" of [16][KC] sub-chunks
     }
@@ -287,7 +302,7 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
     tc_fence_after();
 
     // ---- heads: [128 x 512] . [16 x 512]^T
-    if (tid == 0) pipe_layer(p, whp, 1, WH_ELEMS * 2, HID / 16, act_addr, SBO_ACT, 1, instr_desc(128, NH), tmem_base);
+    if (warp == 0) pipe_layer(p, whp, 1, WH_ELEMS * 2, HID / 16, act_addr, SBO_ACT, 1, instr_desc(128, NH), tmem_base);
     mbar_wait(p.done, 0);
     tc_fence_after();
     {
