@@ -1,27 +1,36 @@
-// Fused ResNet-style trunk on the 5th-generation tensor cores (tcgen05 + TMEM): stem conv3x3 (3 -> 64) and any
-// number of residual blocks (2 x conv3x3 64 -> 64, skip, ReLU) of the reference's ResNet
-// (src/alphazero_simple/resnet.py:13-53, BatchNorm folded) for a batch of leaf positions in ONE kernel; the
-// activations of a position never leave the SM between layers.
+// Fused ResNet-style policy/value network on the 5th-generation tensor cores (tcgen05 + TMEM): stem conv3x3 (3 -> 64),
+// any number of residual blocks (2 x conv3x3 64 -> 64, skip, ReLU) and the policy / value heads of the reference's
+// ResNet (src/alphazero_simple/resnet.py:13-103, BatchNorm folded) for a batch of leaf positions in ONE kernel; the
+// activations of a position never leave the SM between layers.  The leaf gather is fused in: the stem's input
+// planes (empty / side to move / opponent, cnn.py:93-95) are built from the engine's leaf bitboards.
 //
-// Convolution as implicit GEMM without im2col.  Every position is laid out as a zero-padded 8 x 9 grid of
-// "pixels" (6 x 7 cells plus a border), pixel = one GEMM row, channels = K.  The activation buffer is stored
-// K-group-major: for every group of 8 channels, all rows back to back at 16 bytes per row.  In the MMA's
+// Convolution as implicit GEMM without im2col.  Pixel = one GEMM row, channels = K.  The activation buffer is
+// stored K-group-major: for every group of 8 channels, all rows back to back at 16 bytes per row.  In the MMA's
 // K-major no-swizzle shared-memory descriptor this is "stride between 8-row groups = 128 B, stride between
 // K-adjacent core matrices = rows * 16 B", so the A operand of filter tap (dy, dx) is THE SAME buffer with the
-// start address moved by (9*dy + dx) rows: nine taps = nine descriptor offsets, no data movement.  The zero
-// border supplies the padding; outputs computed for border pixels are discarded (written back as zeros, which
-// keeps the border zero for the next layer).  8 positions = 576 pixels = 5 accumulator tiles of 128 rows x 64
-// fp32 columns in tensor memory.  Per layer one thread issues 9 taps x 5 tiles x 4 K-steps tcgen05.mma; the
-// tap weights ([64 out][64 in] bf16, 8 KB, packed once per weight update) stream through a 4-stage ring filled
-// by bulk async copies.  Epilogue (8 warps: two per 32 accumulator lanes, half the channels each): tcgen05.ld, bias
-// (+ skip) + ReLU in fp32, round to bf16, write the next layer's A operand.  After the last block the policy conv1x1 and the
-// value conv3x3 run as one 48-channel conv layer (the 1x1 weights in the centre tap) and the two small FC layers on CUDA cores.
-// Measured (ncu, 16384 positions, 4 blocks): 1.35 ms trunk, tensor pipe 24-28 % active; a 128x64x16 MMA takes ~65 cycles, not the
-// 32-cycle floor, because it fetches 6 KB of operands from shared memory (~96 B/clk): with 64 output channels the conv MMAs are
-// shared-memory-operand-bound.  A software-pipelined variant (issuer warp + two position groups so that one group's epilogue
-// overlaps the other's MMAs) was built and is bit-identical but ran SLOWER (2.4-2.6 ms): the MMAs slow down to ~97 ns each when
-// the epilogue warps' shared-memory traffic competes with the operand fetch; it was removed.  The leaf gather is fused in: the stem's input planes
-// (empty / side to move / opponent, cnn.py:93-95) are built from the engine's leaf bitboards.
+// start address moved by (8*dy + dx) rows: nine taps = nine descriptor offsets, no data movement.
+//  * Compact padding.  A position is 7 x 8 pixel rows (6 x 7 cells + ONE zero column on the right + ONE zero row on
+//    top): with a pixel-row stride of 8 the cell left of x = 0 is the zero column of the row below, and the row under
+//    y = 0 is the zero row of the previous position (a leading zero row opens each group).  Outputs computed for
+//    padding rows are written back as zeros, which keeps the padding zero for the next layer.  4 positions + the
+//    leading row = 232 <= 256 rows = 2 accumulator tiles of 128 rows x 64 fp32 columns in tensor memory; a CTA takes
+//    two such groups: 8 positions in 4 tiles.
+//  * Two groups, ping-pong.  Warp 8 only issues MMAs: for every layer group A's 72 (9 taps x 2 tiles x 4 K-steps),
+//    then group B's 72.  The eight epilogue warps (two per 32 accumulator lanes, half the channels each) trail it:
+//    tcgen05.ld, bias (+ skip) + ReLU in fp32, round to bf16, write the next layer's A operand - while they work on
+//    A's accumulators the tensor core works on B, and vice versa.  Hand-offs are mbarriers: tcgen05.commit ->
+//    mma_done[g]; 256 arrivals -> epi_done[g].
+//  * Warp 9 only streams weights ([64 out][64 in] bf16 per tap, 8 KB, packed once per weight update) with bulk async
+//    copies.  The ring has 9 stages = the 9 taps of a layer (stage = tap, parity = layer): a tap is loaded once per
+//    layer, used by A and then by B, whose commit releases the stage for the next layer's tap.  The issuer never
+//    waits for a copy it has to start itself: the MMA queue is only 2-3 instructions deep (measured with the
+//    AZ_TRUNK_CLOCKS build, scripts/trunk_clocks.py), so every stall of the issuing warp is a stall of the tensor core.
+//  * Heads.  After the last block the policy conv1x1 and the value conv3x3 run as ONE 48-channel conv layer (the 1x1
+//    weights sit in the centre tap); the two small FC layers run on CUDA cores in fp32, each weight read once per CTA.
+// Measured (16384 positions, 4 blocks): 0.70 ms; a group's 72 MMAs take ~3750 cycles = 52 cycles per 128x64x16 MMA
+// against the 32-cycle floor: each fetches 6 KB of operands from shared memory (~115 B/clk), i.e. with 64 output
+// channels the conv MMAs are shared-memory-operand-bound.  History: a serial version (one 5-tile group of 8 x 9 padded
+// positions, the issuing warp also refilling the ring) took 1.33 ms - every tap waited for its own stage to drain.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -34,32 +43,18 @@
 namespace {
 
 constexpr int C = 64;            // trunk channels
-constexpr int P = 8;             // positions per CTA
-constexpr int PW = 9, PH = 8;    // padded grid
-constexpr int PIX = PW * PH;     // 72 rows per position
-constexpr int ROWS = P * PIX;    // 576 real rows
-constexpr int TILES = 5;         // accumulator tiles of 128 rows (640 >= 576)
-constexpr int GUARD = 16;        // rows before / after (a tap moves the window by up to 10 rows)
-constexpr int RTOT = TILES * 128 + 2 * GUARD;       // 672 rows per buffer
+constexpr int GUARD = 16;        // zero rows before / after (a tap moves the window by up to 9 rows)
 constexpr uint32_t ROWB = 16;                        // bytes per row per K group
-constexpr uint32_t LBO_A = RTOT * ROWB;              // 10752: between K groups (8 channels)
 constexpr uint32_t SBO_A = 128;                      // between 8-row groups
-constexpr uint32_t BUF_BYTES = (C / 8) * LBO_A;      // 86016
 constexpr uint32_t TAP_BYTES = C * C * 2;            // 8192: one tap's [64][64] weights
 constexpr uint32_t SBO_W = (C / 8) * 128;            // 1024 (canonical K-major [64][64])
 constexpr uint32_t LBO_W = 128;
 constexpr uint32_t STEM_TAP_BYTES = C * 16 * 2;      // 2048: stem tap [64][16]
 constexpr uint32_t SBO_WS = (16 / 8) * 128;          // 256
-constexpr int NS = 4;                                // weight ring stages (6 measured no faster: the MMAs, not the copies, pace a layer)
 constexpr int NHC = 48;                              // head conv channels: 32 policy (1x1, centre tap) + 3 value (3x3) + padding
 constexpr uint32_t HEAD_TAP_BYTES = NHC * C * 2;     // 6144
 constexpr int NHU = 35;                              // head channels actually used
 constexpr int MAX_LAYERS = 24;                       // biases of every layer are staged in shared memory once
-constexpr uint32_t OFF_RING = 2 * BUF_BYTES;
-constexpr uint32_t OFF_BIAS = OFF_RING + NS * TAP_BYTES;
-constexpr uint32_t OFF_BARS = OFF_BIAS + MAX_LAYERS * C * 4;
-constexpr uint32_t SMEM_BYTES = OFF_BARS + (2 * NS + 1) * 8 + 16;
-constexpr int THREADS = 256;  // 8 warps: warps w and w+4 share the 32 accumulator lanes 32*(w%4).., each takes half the channels
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -120,77 +115,47 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
-struct Pipe {
-    uint32_t full[NS], empty[NS], done, stage[NS];
-    uint32_t g;  // taps consumed so far (stage = g % NS, use = g / NS)
-};
-__device__ __forceinline__ void pipe_load(const Pipe &p, uint32_t gj, const uint8_t *src, uint32_t bytes) {
-    const uint32_t st = gj % NS;
-    if (gj >= NS) mbar_wait(p.empty[st], ((gj / NS) - 1u) & 1u);
-    if (elect_one()) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(p.full[st]), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(p.stage[st]),
-                     "l"(src), "r"(bytes), "r"(p.full[st])
-                     : "memory");
-    }
-    __syncwarp();
-}
+#ifdef AZ_TRUNK_CLOCKS
+// debug build only: per-layer timestamps of one CTA (issue start / issue end / accumulators ready / epilogue end)
+__device__ long long g_clk[4 * 2 * MAX_LAYERS];
+#define CLK(kind, l, g) do { if (blockIdx.x == 300 && (threadIdx.x & 31) == 0) g_clk[((kind) * MAX_LAYERS + (l)) * 2 + (g)] = clock64(); } while (0)
+#else
+#define CLK(kind, l, g) do { } while (0)
+#endif
 
-// row index inside a CTA -> is it a real board cell, and which (position, y, x)
+constexpr int THREADS = 320;  // warps 0..7 epilogue, warp 8 MMA issuer, warp 9 weight producer
+constexpr int PW = 8, PIX = 56, LEAD = 8;  // pixel-row stride, rows per position, leading zero row of a group
+constexpr int GPOS = 4, P = 2 * GPOS;        // positions per group / per CTA
+constexpr int GTILES = 2, TILES = 2 * GTILES, GROWS = GTILES * 128;
+constexpr int RTOT = TILES * 128 + 2 * GUARD;       // 544 rows per buffer
+constexpr uint32_t LBO_A = RTOT * ROWB;             // 8704
+constexpr uint32_t BUF_BYTES = (C / 8) * LBO_A;     // 69632
+constexpr int NS = 9;
+constexpr uint32_t OFF_RING = 2 * BUF_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_RING + NS * TAP_BYTES;
+constexpr uint32_t OFF_BARS = OFF_BIAS + MAX_LAYERS * C * 4;
+constexpr uint32_t SMEM_BYTES = OFF_BARS + (2 * NS + 4) * 8 + 16;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(LEAD + GPOS * PIX <= GROWS, "a group must fit its accumulator tiles");
+
 __device__ __forceinline__ bool decode_row(int r, int &pos, int &y, int &x) {
-    pos = r / PIX;
-    const int q = r - pos * PIX;
-    const int py = q / PW, px = q - py * PW;
-    y = py - 1;
-    x = px - 1;
-    return r < ROWS && py >= 1 && py <= c4::H && px >= 1 && px <= c4::W;
+    const int g = r >= GROWS;
+    const int rr = r - g * GROWS - LEAD;
+    const int p = rr / PIX;
+    const int q = rr - p * PIX;
+    y = q >> 3;
+    x = q & 7;
+    pos = g * GPOS + p;
+    return rr >= 0 && p < GPOS && y < c4::H && x < c4::W;
 }
 
-// One conv layer's MMAs (warp 0, converged; one elected lane issues): 9 taps x TILES x ksteps.  A = `a_addr` (row 0 of the buffer, after the guard).
-__device__ __forceinline__ void conv_mmas(Pipe &p, const uint8_t *w, uint32_t tap_bytes, uint32_t ksteps, uint32_t sbo_w,
-                                          uint32_t a_addr, uint32_t tmem_base, bool prefetched, int n_out = C) {
-    const uint32_t idesc = instr_desc(128, n_out);
-    if (!prefetched)
-        for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w + (size_t)i * tap_bytes, tap_bytes);
-    for (uint32_t tap = 0; tap < 9; ++tap) {
-        const uint32_t gi = p.g + tap, st = gi % NS;
-        const int dy = (int)(tap / 3) - 1, dx = (int)(tap % 3) - 1;
-        const uint32_t a_tap = a_addr + (uint32_t)((dy * PW + dx) * (int)ROWB);
-        mbar_wait(p.full[st], (gi / NS) & 1u);
-        tc_fence_after();
-        // descriptors differ only in the start-address field (low 14 bits, 16-byte units): build once, add offsets
-        const uint64_t a_base = smem_desc(a_tap, LBO_A, SBO_A), b_base = smem_desc(p.stage[st], LBO_W, sbo_w);
-        const uint32_t acc0 = tap > 0;
-        if (elect_one()) {
-            if (ksteps == 1) {
-#pragma unroll
-                for (uint32_t t = 0; t < TILES; ++t) umma(tmem_base + t * C, a_base + t * (128 * ROWB >> 4), b_base, idesc, acc0);
-            } else {
-#pragma unroll
-                for (uint32_t t = 0; t < TILES; ++t)
-#pragma unroll
-                    for (uint32_t ks = 0; ks < C / 16; ++ks)
-                        umma(tmem_base + t * C, a_base + t * (128 * ROWB >> 4) + ks * (2 * LBO_A >> 4), b_base + ks * (2 * LBO_W >> 4), idesc,
-                             acc0 | (ks > 0));
-            }
-            umma_commit(p.empty[st]);
-        }
-        __syncwarp();
-        if (tap + NS < 9) pipe_load(p, gi + NS, w + (size_t)(tap + NS) * tap_bytes, tap_bytes);
-    }
-    if (elect_one()) umma_commit(p.done);
-    __syncwarp();
-    p.g += 9;
-}
-
-// Epilogue of one layer: accumulators -> (+ bias, + skip) -> ReLU -> bf16 -> destination buffer (K-group-major);
-// border / padding rows are written as zeros.  `skip` (may be null) is the residual input buffer.
-__device__ __forceinline__ void conv_epilogue(uint32_t tmem_base, uint8_t *dst, const uint8_t *skip, const float *bias) {
+// epilogue of tiles [t0, t1) of one conv layer (8 warps; warp group `half` takes 32 of the 64 channels)
+__device__ __forceinline__ void conv_epilogue(uint32_t tmem_base, uint8_t *dst, const uint8_t *skip, const float *bias, int t0, int t1) {
     const uint32_t lane_row = threadIdx.x & 127u;
-    const int half = threadIdx.x >> 7;  // which 32 of the 64 channels this warp group handles
+    const int half = (threadIdx.x >> 7) & 1;
     const uint32_t taddr = tmem_base + ((lane_row & ~31u) << 16) + half * 32;
 #pragma unroll 1
-    for (int t = 0; t < TILES; ++t) {
+    for (int t = t0; t < t1; ++t) {
         const int r = t * 128 + (int)lane_row;
         int pos, y, x;
         const bool valid = decode_row(r, pos, y, x);
@@ -200,7 +165,7 @@ __device__ __forceinline__ void conv_epilogue(uint32_t tmem_base, uint8_t *dst, 
         tmem_ld32(taddr + t * C, v);
 #pragma unroll
         for (int kg = 0; kg < 4; ++kg) {
-            const int grp = half * 4 + kg;  // channel group of 8
+            const int grp = half * 4 + kg;
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[kg * 8 + j]) + bias[grp * 8 + j];
@@ -218,51 +183,67 @@ __device__ __forceinline__ void conv_epilogue(uint32_t tmem_base, uint8_t *dst, 
     }
 }
 
-// weights: [stem: 9 taps x [64][16]] [layer 1: 9 taps x [64][64]] ... all bf16 canonical; biases: [L][64] fp32
+// MMAs of one (layer, group), fully unrolled: 9 taps x 2 tiles x KSTEPS.  Every operand is warp-uniform; one elected
+// lane issues.  Group A waits for each tap's weights; group B finds them there and releases the stage afterwards.
+template <int KSTEPS, bool GROUP_B>
+__device__ __forceinline__ void issue_group(uint32_t full0, uint32_t empty0, uint32_t parity, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t tmem_tile0) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);  // rows; one row = 16 B = one descriptor address unit
+        if (!GROUP_B) {
+            mbar_wait(full0 + tap * 8, parity);
+            tc_fence_after();
+        }
+        if (elect_one()) {
+#pragma unroll
+            for (int t = 0; t < GTILES; ++t)
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks)
+                    umma(tmem_tile0 + t * C, a_desc + (uint64_t)(int64_t)(shift + t * 128 + ks * (int)(2 * LBO_A >> 4)),
+                         b_desc + (uint64_t)(tap * (int)(TAP_BYTES >> 4) + ks * (int)(2 * LBO_W >> 4)), idesc, (tap | ks) > 0);
+            if (GROUP_B) umma_commit(empty0 + tap * 8);
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1, const uint8_t *__restrict__ leaf_player,
-               const uint8_t *__restrict__ leaf_status, long long n, const uint8_t *__restrict__ weights,
-               const float *__restrict__ biases, int num_blocks, __nv_bfloat16 *__restrict__ out /*[n][6][7][64] or null*/,
-               const uint8_t *__restrict__ head_w /*9 taps x [48][64] or null*/, const float *__restrict__ head_b /*[48]*/,
-               const float *__restrict__ fc_policy_w /*[7][1344]*/, const float *__restrict__ fc_policy_b,
-               const float *__restrict__ fc_value_w /*[126]*/, const float *__restrict__ fc_value_b,
-               float *__restrict__ logits /*[n][7]*/, float *__restrict__ values /*[n][2]*/) {
+                   const uint8_t *__restrict__ leaf_status, long long n, const uint8_t *__restrict__ weights,
+                   const float *__restrict__ biases, int num_blocks, __nv_bfloat16 *__restrict__ out,
+                   const uint8_t *__restrict__ head_w, const float *__restrict__ head_b, const float *__restrict__ fc_policy_w,
+                   const float *__restrict__ fc_policy_b, const float *__restrict__ fc_value_w, const float *__restrict__ fc_value_b,
+                   float *__restrict__ logits, float *__restrict__ values) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *buf[2] = {smem, smem + BUF_BYTES};
     float *s_bias = reinterpret_cast<float *>(smem + OFF_BIAS);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BARS);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + (2 * NS + 1) * 8);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BARS);  // full[9] empty[9] mma_done[2] epi_done[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + (2 * NS + 4) * 8);
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const long long pos0 = (long long)blockIdx.x * P;
-    Pipe p;
-#pragma unroll
-    for (int i = 0; i < NS; ++i) {
-        p.full[i] = smem_u32(bars + i);
-        p.empty[i] = smem_u32(bars + NS + i);
-        p.stage[i] = smem_u32(smem + OFF_RING) + i * TAP_BYTES;
-    }
-    p.done = smem_u32(bars + 2 * NS);
-    p.g = 0;
+    if (warp == 0) CLK(0, MAX_LAYERS - 1, 0);
+    const int n_conv = 1 + 2 * num_blocks;            // stem + block convs
+    const int n_layers = n_conv + (head_w ? 1 : 0);   // + head conv
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS), ring0 = smem_u32(smem + OFF_RING);
+    const uint32_t mma_done0 = smem_u32(bars + 2 * NS), epi_done0 = smem_u32(bars + 2 * NS + 2);
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    if (tid == 0) {
-        for (int i = 0; i < 2 * NS + 1; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
+    if (tid == 32) {
+        for (int i = 0; i < 2 * NS + 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"(epi_done0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"(epi_done0 + 8));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
-    if (warp == 0)
-        for (uint32_t i = 0; i < NS; ++i) pipe_load(p, i, weights + (size_t)i * STEM_TAP_BYTES, STEM_TAP_BYTES);
-    // zero both activation buffers (borders, guards and the unused K groups of the stem input must be zero)
     for (uint32_t i = tid; i < 2 * BUF_BYTES / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
-    const int n_layers = 1 + 2 * num_blocks;
-    for (uint32_t i = tid; i < (uint32_t)n_layers * C; i += THREADS) s_bias[i] = __ldg(biases + i);
+    for (uint32_t i = tid; i < (uint32_t)n_conv * C; i += THREADS) s_bias[i] = __ldg(biases + i);
     if (head_w)
-        for (uint32_t i = tid; i < NHC; i += THREADS) s_bias[n_layers * C + i] = __ldg(head_b + i);
+        for (uint32_t i = tid; i < NHC; i += THREADS) s_bias[n_conv * C + i] = __ldg(head_b + i);
     __syncthreads();
     // stem input in buf[1]: channels 0..2 = empty / side to move / opponent (cnn.py:93-95), K group 0
-    for (int r = tid; r < ROWS; r += THREADS) {
+    for (int r = tid; r < TILES * 128; r += THREADS) {
         int pos, y, x;
         if (!decode_row(r, pos, y, x)) continue;
         const long long gp = pos0 + pos;
@@ -271,9 +252,9 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
         const int pl = leaf_player[gp] & 1;
         const int bit = x * c4::STRIDE + y;
         const uint32_t s0 = (uint32_t)((b0 >> bit) & 1ull), s1 = (uint32_t)((b1 >> bit) & 1ull);
-        const uint32_t mine = pl ? s1 : s0, theirs = pl ? s0 : s1, empty = 1u - (s0 | s1);
+        const uint32_t mine = pl ? s1 : s0, theirs = pl ? s0 : s1, emp = 1u - (s0 | s1);
         const uint32_t one = 0x3F80u;
-        *reinterpret_cast<uint4 *>(buf[1] + (GUARD + r) * ROWB) = make_uint4(empty * one | (mine * one) << 16, theirs * one, 0u, 0u);
+        *reinterpret_cast<uint4 *>(buf[1] + (GUARD + r) * ROWB) = make_uint4(emp * one | (mine * one) << 16, theirs * one, 0u, 0u);
     }
     fence_async_smem();
     tc_fence_before();
@@ -281,136 +262,191 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a0 = smem_u32(buf[0]) + GUARD * ROWB, a1 = smem_u32(buf[1]) + GUARD * ROWB;
-    uint32_t done_phase = 0;
-    const uint8_t *w_layer = weights + 9 * STEM_TAP_BYTES;  // first trunk layer's weights
 
-    // ---- stem: buf[1] (16 input channels, 3 used) -> buf[0]
-    if (warp == 0) {
-        conv_mmas(p, weights, STEM_TAP_BYTES, 1, SBO_WS, a1, tmem_base, true);
-        if (num_blocks > 0)
-            for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w_layer + (size_t)i * TAP_BYTES, TAP_BYTES);
-        else if (head_w)
-            for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, head_w + (size_t)i * HEAD_TAP_BYTES, HEAD_TAP_BYTES);
-    }
-    mbar_wait(p.done, done_phase);
-    done_phase ^= 1;
-    tc_fence_after();
-    conv_epilogue(tmem_base, buf[0], nullptr, s_bias);
-
-    // ---- residual blocks: x in buf[0]; t = relu(conv1(x)) -> buf[1]; x = relu(conv2(t) + x) -> buf[0]
-    for (int blk = 0; blk < num_blocks; ++blk) {
+    if (warp == 9) {
+        // ===== weight producer: tap `tap` of layer l into stage `tap`, once group B of layer l-1 has released it =====
+        for (int l = 0; l < n_layers; ++l) {
+            const uint8_t *w = l == 0 ? weights : (l < n_conv ? weights + 9 * STEM_TAP_BYTES + (size_t)(l - 1) * 9 * TAP_BYTES : head_w);
+            const uint32_t bytes = l == 0 ? STEM_TAP_BYTES : (l < n_conv ? TAP_BYTES : HEAD_TAP_BYTES);
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const int layer = 1 + 2 * blk + half;
-            fence_async_smem();
-            tc_fence_before();
-            __syncthreads();
-            tc_fence_after();
-            if (warp == 0) {
-                conv_mmas(p, w_layer, TAP_BYTES, C / 16, SBO_W, half == 0 ? a0 : a1, tmem_base, true);
-                const bool last = (blk == num_blocks - 1 && half == 1);
-                if (!last)
-                    for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w_layer + 9 * TAP_BYTES + (size_t)i * TAP_BYTES, TAP_BYTES);
-                else if (head_w)
-                    for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, head_w + (size_t)i * HEAD_TAP_BYTES, HEAD_TAP_BYTES);
+            for (uint32_t tap = 0; tap < 9; ++tap) {
+                if (l > 0) mbar_wait(empty0 + tap * 8, (uint32_t)(l - 1) & 1u);
+                if (elect_one()) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + tap * 8), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     ring0 + tap * TAP_BYTES),
+                                 "l"(w + (size_t)tap * bytes), "r"(bytes), "r"(full0 + tap * 8)
+                                 : "memory");
+                }
+                __syncwarp();
             }
-            w_layer += 9 * TAP_BYTES;
-            mbar_wait(p.done, done_phase);
-            done_phase ^= 1;
-            tc_fence_after();
-            if (half == 0) conv_epilogue(tmem_base, buf[1], nullptr, s_bias + layer * C);
-            else conv_epilogue(tmem_base, buf[0], buf[0], s_bias + layer * C);
         }
-    }
-    __syncthreads();
-    // ---- trunk output, NHWC bf16 (optional)
-    if (out) {
-        for (int r = tid; r < ROWS; r += THREADS) {
-            int pos, y, x;
-            if (!decode_row(r, pos, y, x)) continue;
-            const long long gp = pos0 + pos;
-            if (gp >= n) continue;
-            uint4 *o = reinterpret_cast<uint4 *>(out + ((gp * c4::H + y) * c4::W + x) * C);
-            const uint8_t *row = buf[0] + (GUARD + r) * ROWB;
-#pragma unroll
-            for (int grp = 0; grp < C / 8; ++grp) o[grp] = *reinterpret_cast<const uint4 *>(row + grp * LBO_A);
-        }
-    }
-    // ---- heads (resnet.py:56-72): policy conv1x1 -> 32 and value conv3x3 -> 3 as ONE 48-channel conv layer (the 1x1
-    // weights sit in the centre tap), ReLU, then the two small fully connected layers on CUDA cores in fp32
-    if (head_w) {
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (warp == 0) conv_mmas(p, head_w, HEAD_TAP_BYTES, C / 16, SBO_W, a0, tmem_base, true, NHC);
-        mbar_wait(p.done, done_phase);
-        done_phase ^= 1;
-        tc_fence_after();
-        float *hact = reinterpret_cast<float *>(buf[1]);  // [P][35][42] fp32, the Flatten() order of NCHW
-        const float *hb = s_bias + n_layers * C;
-        if (tid < 128) {
-            const uint32_t taddr = tmem_base + ((tid & ~31u) << 16);
+    } else if (warp == 8) {
+        // ===== MMA issuer (converged; one elected lane issues) =====
+        const uint32_t idesc_c = instr_desc(128, C), idesc_h = instr_desc(128, NHC);
+        for (int l = 0; l < n_layers; ++l) {
+            const bool is_head = l >= n_conv;
+            const uint32_t src = l == 0 ? a1 : (is_head ? a0 : ((l & 1) ? a0 : a1));  // conv1 (odd l) reads x = buf[0]; conv2 reads t = buf[1]
+            const uint32_t idesc = is_head ? idesc_h : idesc_c;
+            const uint64_t b_desc = smem_desc(ring0, LBO_W, l == 0 ? SBO_WS : SBO_W);
 #pragma unroll 1
-            for (int t = 0; t < TILES; ++t) {
-                const int r = t * 128 + (int)tid;
+            for (int g = 0; g < 2; ++g) {
+                if (l > 0) mbar_wait(epi_done0 + g * 8, (uint32_t)(l - 1) & 1u);  // this group's input is written, its TMEM tiles are free
+                tc_fence_after();
+                const uint32_t tile0 = tmem_base + g * GTILES * C;
+                const uint64_t a_desc = smem_desc(src + g * GROWS * ROWB, LBO_A, SBO_A);
+                CLK(0, l, g);
+                if (l == 0) {
+                    if (g == 0) issue_group<1, false>(full0, empty0, 0u, a_desc, b_desc, idesc, tile0);
+                    else issue_group<1, true>(full0, empty0, 0u, a_desc, b_desc, idesc, tile0);
+                } else {
+                    if (g == 0) issue_group<C / 16, false>(full0, empty0, (uint32_t)l & 1u, a_desc, b_desc, idesc, tile0);
+                    else issue_group<C / 16, true>(full0, empty0, (uint32_t)l & 1u, a_desc, b_desc, idesc, tile0);
+                }
+                if (elect_one()) umma_commit(mma_done0 + g * 8);
+                __syncwarp();
+                CLK(1, l, g);
+            }
+        }
+    } else {
+        // ===== epilogue warps (256 threads) =====
+        for (int l = 0; l < n_conv; ++l) {
+            // stem (l = 0) and conv2 of a block (even l) write x into buf[0]; conv1 (odd l) writes t into buf[1]
+            uint8_t *dst = (l & 1) ? buf[1] : buf[0];
+            const uint8_t *skip = (l > 0 && !(l & 1)) ? buf[0] : nullptr;
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+                mbar_wait(mma_done0 + g * 8, (uint32_t)l & 1u);
+                tc_fence_after();
+                if (warp == 0) CLK(2, l, g);
+                conv_epilogue(tmem_base, dst, skip, s_bias + l * C, g * GTILES, (g + 1) * GTILES);
+                fence_async_smem();
+                tc_fence_before();
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(epi_done0 + g * 8) : "memory");
+                if (warp == 0) CLK(3, l, g);
+            }
+        }
+        if (out) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int r = tid; r < TILES * 128; r += 256) {
                 int pos, y, x;
-                const bool valid = decode_row(r, pos, y, x);
-                uint32_t v[32];
-                tmem_ld32(taddr + t * C, v);  // policy channels 0..31
-                if (valid) {
+                if (!decode_row(r, pos, y, x)) continue;
+                const long long gp = pos0 + pos;
+                if (gp >= n) continue;
+                uint4 *o = reinterpret_cast<uint4 *>(out + ((gp * c4::H + y) * c4::W + x) * C);
+                const uint8_t *row = buf[0] + (GUARD + r) * ROWB;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) hact[(pos * NHU + c) * 42 + y * c4::W + x] = fmaxf(__uint_as_float(v[c]) + hb[c], 0.f);
-                }
-                tmem_ld32(taddr + t * C + 32, v);  // value channels 32..34 (+ padding)
-                if (valid) {
-#pragma unroll
-                    for (int c = 32; c < NHU; ++c) hact[(pos * NHU + c) * 42 + y * c4::W + x] = fmaxf(__uint_as_float(v[c - 32]) + hb[c], 0.f);
-                }
+                for (int grp = 0; grp < C / 8; ++grp) o[grp] = *reinterpret_cast<const uint4 *>(row + grp * LBO_A);
             }
         }
-        tc_fence_before();
-        __syncthreads();
-        // warp = position; lanes stride over the 1344 (policy) / 126 (value) inputs with coalesced weight reads and
-        // seven independent accumulators, then a shuffle reduction
-        {
-            const int pos = warp, lane = tid & 31;
-            const long long gp = pos0 + pos;
-            const float *a = hact + pos * NHU * 42;
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-            for (int i = lane; i < 32 * 42; i += 32) {
-                const float x = a[i];
+        if (head_w) {
+            float *hact = reinterpret_cast<float *>(buf[1]);  // [P][35][42] fp32, the Flatten() order of NCHW
+            const float *hb = s_bias + n_conv * C;
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+                mbar_wait(mma_done0 + g * 8, (uint32_t)n_conv & 1u);
+                tc_fence_after();
+                if (warp == 0) CLK(2, n_conv, g);
+                // warps 0..3: policy channels 0..31; warps 4..7: value channels 32..34
+                const int half = (tid >> 7) & 1;
+                const uint32_t taddr = tmem_base + (((tid & 127u) & ~31u) << 16) + half * 32;
+                for (int t = g * GTILES; t < (g + 1) * GTILES; ++t) {
+                    const int r = t * 128 + (int)(tid & 127u);
+                    int pos, y, x;
+                    const bool valid = decode_row(r, pos, y, x);
+                    uint32_t v[32];
+                    tmem_ld32(taddr + t * C, v);
+                    if (valid) {
+                        if (half == 0) {
 #pragma unroll
-                for (int j = 0; j < 7; ++j) acc[j] = fmaf(__ldg(fc_policy_w + j * (32 * 42) + i), x, acc[j]);
+                            for (int c = 0; c < 32; ++c) hact[(pos * NHU + c) * 42 + y * c4::W + x] = fmaxf(__uint_as_float(v[c]) + hb[c], 0.f);
+                        } else {
+#pragma unroll
+                            for (int c = 32; c < NHU; ++c) hact[(pos * NHU + c) * 42 + y * c4::W + x] = fmaxf(__uint_as_float(v[c - 32]) + hb[c], 0.f);
+                        }
+                    }
+                }
+                if (warp == 0) CLK(3, n_conv, g);
             }
-            for (int i = lane; i < 3 * 42; i += 32) acc[7] = fmaf(__ldg(fc_value_w + i), a[32 * 42 + i], acc[7]);
+            tc_fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // Both FC layers for the CTA's 8 positions at once, in fp32 on CUDA cores: thread t takes inputs k = t, t + 256, ...
+            // so every weight is read once per CTA (coalesced) and used for 8 positions; acc[p][j], j = 7 is the value head.
+            float acc[P * 8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int i = 0; i < P * 8; ++i) acc[i] = 0.f;
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) acc[j] += __shfl_xor_sync(0xFFFFFFFFu, acc[j], off);
-            if (gp < n) {
-                if (lane < 7) {
-                    float v = acc[0];
+            for (int it = 0; it < (32 * 42 + 255) / 256; ++it) {
+                const int k = (int)tid + it * 256;
+                const bool in = k < 32 * 42;
+                const int kk = in ? k : 0;
+                float w[7];
 #pragma unroll
-                    for (int j = 1; j < 7; ++j) v = lane == j ? acc[j] : v;
-                    logits[gp * 7 + lane] = v + __ldg(fc_policy_b + lane);
-                } else if (lane == 7) {
-                    const float v = tanhf(acc[7] + __ldg(fc_value_b));
-                    values[gp * 2] = v;
-                    values[gp * 2 + 1] = -v;
+                for (int j = 0; j < 7; ++j) w[j] = in ? __ldg(fc_policy_w + j * (32 * 42) + kk) : 0.f;
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const float xv = hact[p * NHU * 42 + kk];
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) acc[p * 8 + j] = fmaf(w[j], xv, acc[p * 8 + j]);
+                }
+            }
+            {
+                const bool in = tid < 3 * 42;
+                const int kk = in ? (int)tid : 0;
+                const float w = in ? __ldg(fc_value_w + kk) : 0.f;
+#pragma unroll
+                for (int p = 0; p < P; ++p) acc[p * 8 + 7] = fmaf(w, hact[p * NHU * 42 + 32 * 42 + kk], acc[p * 8 + 7]);
+            }
+            // warp reduction by recursive halving: each step exchanges half of the values, so 62 shuffles reduce all 64
+            // sums; lane L ends with the totals of indices 2L and 2L + 1
+            const uint32_t lane = tid & 31u;
+#pragma unroll
+            for (int h = 32; h >= 2; h >>= 1) {
+                const bool up = (lane & (uint32_t)(h >> 1)) != 0;
+#pragma unroll
+                for (int i = 0; i < h; ++i) {
+                    const float send = up ? acc[i] : acc[i + h];
+                    const float keep = up ? acc[i + h] : acc[i];
+                    acc[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, h >> 1);
+                }
+            }
+            float *red = reinterpret_cast<float *>(buf[1] + 48 * 1024);  // [8 warps][64], behind hact (47040 B)
+            *reinterpret_cast<float2 *>(red + warp * 64 + 2 * lane) = make_float2(acc[0], acc[1]);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid < P * 8) {
+                float sum = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) sum += red[w8 * 64 + tid];
+                const int p = (int)tid >> 3, j = (int)tid & 7;
+                const long long gp = pos0 + p;
+                if (gp < n) {
+                    if (j < 7) {
+                        logits[gp * 7 + j] = sum + __ldg(fc_policy_b + j);
+                    } else {
+                        const float v = tanhf(sum + __ldg(fc_value_b));
+                        values[gp * 2] = v;
+                        values[gp * 2 + 1] = -v;
+                    }
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    if (warp == 0) CLK(1, MAX_LAYERS - 1, 0);
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
 }
+
 
 }  // namespace
 
 extern "C" {
+
+#ifdef AZ_TRUNK_CLOCKS
+int32_t az_debug_trunk_clocks(long long *out) {
+    return cudaMemcpyFromSymbol(out, g_clk, sizeof(g_clk)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 /* bytes of packed weights the trunk kernel expects for `num_blocks` residual blocks */
 int64_t az_trunk_weight_bytes(int32_t num_blocks) { return 9ll * STEM_TAP_BYTES + (int64_t)num_blocks * 2 * 9 * TAP_BYTES; }
@@ -430,10 +466,9 @@ static int32_t launch_trunk(az_engine *engine, const void *weights, const float 
         if (cudaFuncSetAttribute(k_resnet_trunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
         attr_set[dev] = true;
     }
-    const int blocks = (n + P - 1) / P;
-    k_resnet_trunk<<<blocks, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(bb0, bb1, player, status, n, (const uint8_t *)weights, biases,
-                                                                          num_blocks, (__nv_bfloat16 *)out, (const uint8_t *)head_w, head_b,
-                                                                          fcp_w, fcp_b, fcv_w, fcv_b, logits, values);
+    k_resnet_trunk<<<(n + P - 1) / P, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(bb0, bb1, player, status, n, (const uint8_t *)weights, biases,
+                                                                                  num_blocks, (__nv_bfloat16 *)out, (const uint8_t *)head_w, head_b,
+                                                                                  fcp_w, fcp_b, fcv_w, fcv_b, logits, values);
     return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;
 }
 

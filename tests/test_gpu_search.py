@@ -50,7 +50,7 @@ def _random_roots(oracle, n, seed, max_depth=30):
     return b0, b1, pl
 
 
-@pytest.mark.parametrize("lanes,kind,S,n", [(16, 2, 200, 2048), (8, 1, 200, 4096), (32, 2, 200, 4096), (8, 2, 800, 512), (32, 1, 50, 1000), (8, 2, 37, 777)])
+@pytest.mark.parametrize("lanes,kind,S,n", [(8, 2, 16, 129), (8, 1, 40, 1), (16, 2, 33, 3), (32, 1, 12, 5), (16, 2, 200, 2048), (8, 1, 200, 4096), (32, 2, 200, 4096), (8, 2, 800, 512), (32, 1, 50, 1000), (8, 2, 37, 777)])
 def test_search_vs_oracle_config2_size(oracle, lanes, kind, S, n):
     """4096 trees x 200 sims (BASELINE config 2) from random mid-game roots, compared with the C oracle."""
     b0, b1, pl = _random_roots(oracle, n, seed=S + n)
