@@ -9,6 +9,8 @@ Works on any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests)
 """
 from __future__ import annotations
 
+import math
+
 import torch
 import torch.distributed as dist
 
@@ -46,44 +48,49 @@ def broadcast_weights(model: torch.nn.Module, src: int = 0, group=None) -> int:
 
 def all_gather_episodes(local: dict, group=None, slot_offset: int | None = None) -> dict:
     """Merge every rank's drained episodes (dict of tensors as returned by `Engine.drain_episodes_device`)
-    into one dict present on all ranks.  Two phases: all-gather the (episodes, samples) counts, then one padded
-    all-gather per field.  Episode slots are made global by adding the rank's slot offset; sample offsets are
-    rebased.  Merge order: rank, then the rank's own order."""
+    into one dict present on all ranks.  Two collectives: an all-gather of the (episodes, samples, slot offset)
+    triples, then ONE all-gather of a byte buffer into which every field is packed (padded to the largest rank).
+    Episode slots are made global by adding the owning rank's slot offset; sample offsets are rebased.
+    Merge order: rank, then the rank's own order."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    world = dist.get_world_size(group)
     dev = local["ep_len"].device
-    counts = torch.tensor([local["ep_len"].numel(), local["s_bb0"].numel()], dtype=torch.int64, device=dev)
-    all_counts = [torch.zeros_like(counts) for _ in range(world)]
-    dist.all_gather(all_counts, counts, group=group)
-    ne = [int(c[0]) for c in all_counts]
-    ns = [int(c[1]) for c in all_counts]
+    counts = torch.tensor([local["ep_len"].numel(), local["s_bb0"].numel(), slot_offset or 0], dtype=torch.int64, device=dev)
+    all_counts = torch.empty(world * 3, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_counts, counts, group=group)
+    all_counts = all_counts.view(world, 3).cpu()
+    ne, ns, offs = (all_counts[:, i].tolist() for i in range(3))
     max_e, max_s = max(ne + [1]), max(ns + [1])
-    out = {}
-    for fields, cnt, mx in ((_EP_FIELDS, ne, max_e), (_S_FIELDS, ns, max_s)):
+    # layout of one rank's packed buffer: every field padded to the largest rank, regions 16-byte aligned
+    layout, total = [], 0
+    for fields, mx in ((_EP_FIELDS, max_e), (_S_FIELDS, max_s)):
         for f in fields:
             x = local[f]
-            pad = torch.zeros((mx, *x.shape[1:]), dtype=x.dtype, device=dev)
-            pad[: x.shape[0]] = x
-            parts = [torch.empty_like(pad) for _ in range(world)]
-            dist.all_gather(parts, pad, group=group)
-            out[f] = torch.cat([p[:c] for p, c in zip(parts, cnt)])
-    # rebase sample offsets and slots
+            row = x.element_size() * math.prod(x.shape[1:])
+            layout.append((f, total, mx, row, x.dtype, tuple(x.shape[1:])))
+            total += (mx * row + 15) // 16 * 16
+    buf = torch.zeros(total, dtype=torch.uint8, device=dev)
+    for f, off, mx, row, dtype, tail in layout:
+        x = local[f].contiguous()
+        if x.shape[0]:
+            buf[off:off + x.shape[0] * row] = x.view(-1).view(torch.uint8)
+    gathered = torch.empty(world * total, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered, buf, group=group)
+    gathered = gathered.view(world, total)
+    out = {}
+    for f, off, mx, row, dtype, tail in layout:
+        cnt = ne if f in _EP_FIELDS else ns
+        parts = [gathered[r, off:off + cnt[r] * row].view(dtype).view(cnt[r], *tail) for r in range(world)]
+        out[f] = torch.cat(parts)
+    # rebase sample offsets; make slots global
     s_base, e_pos = 0, 0
     for r in range(world):
         sl = slice(e_pos, e_pos + ne[r])
         out["ep_offset"][sl] += s_base
         if slot_offset is not None:
-            pass
+            out["ep_slot"][sl] += offs[r]
         s_base += ns[r]
         e_pos += ne[r]
-    if slot_offset is not None:
-        offs = torch.tensor([slot_offset], dtype=torch.int64, device=dev)
-        all_offs = [torch.zeros_like(offs) for _ in range(world)]
-        dist.all_gather(all_offs, offs, group=group)
-        e_pos = 0
-        for r in range(world):
-            out["ep_slot"][e_pos:e_pos + ne[r]] += int(all_offs[r])
-            e_pos += ne[r]
     out["ep_rank"] = torch.cat([torch.full((c,), r, dtype=torch.int32, device=dev) for r, c in enumerate(ne)])
     return out

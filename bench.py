@@ -48,8 +48,10 @@ def parse_args():
     ap.add_argument("--hot-nodes", type=int, default=None, help="nodes per tree kept in shared memory by the fused kernel (default: automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tree-scaling", action="store_true")
     ap.add_argument("--net", default="basic_tc,resnet4x64", help="network-in-the-loop side measurements, comma separated: basic_tc | basic | resnetBxC | none")
-    ap.add_argument("--net-games", type=int, default=16384)
+    ap.add_argument("--net-games", type=int, default=16384, help="network-in-the-loop games on one GPU (BASELINE configs[2])")
+    ap.add_argument("--net-games-sharded", type=int, default=65536, help="total games sharded over the ranks when N > 1 (configs[3])")
     ap.add_argument("--net-sims", type=int, default=800)
     ap.add_argument("--net-steps", type=int, default=2)
     return ap.parse_args()
@@ -179,11 +181,16 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
-def net_in_loop(args, device_index: int, peaks: dict):
-    """Side measurements with a network in the loop (BASELINE configs[2]): self-play move steps of E games x S sims, one
-    evaluator call per simulation step.  `resnetBx64`: bf16 ResNet-style net on the hand-written tcgen05 kernel (csrc/az_conv.cu: trunk + heads,
-    leaf gather fused); other widths: conv/linear layers = cuDNN/cuBLAS tensor-core GEMMs.  `basic_tc`: the reference's BasicNN on the hand-written tcgen05 kernel (csrc/az_mlp.cu, leaf gather fused)."""
+def net_in_loop(args, device_index: int, peaks: dict, world: int = 1, rank: int = 0):
+    """Side measurements with a network in the loop: self-play move steps of E games x S sims, one evaluator call per
+    simulation step.  One GPU: BASELINE configs[2] (16384 games x 800 sims).  N > 1 GPUs: configs[3] — 65536 games sharded
+    over the ranks (65536 / N per GPU), every rank times its own shard between barriers and the job's time is the max over
+    ranks (the episode all-gather is timed in the main section; scripts/run_config4.py plays whole rounds).
+    `resnetBx64`: bf16 ResNet-style net on the hand-written tcgen05 kernel (csrc/az_conv.cu: trunk + heads, leaf gather
+    fused); other widths: conv/linear layers = cuDNN/cuBLAS tensor-core GEMMs.  `basic_tc`: the reference's BasicNN on the
+    hand-written tcgen05 kernel (csrc/az_mlp.cu, leaf gather fused)."""
     import torch
+    import torch.distributed as dist
 
     import alphazero_implementation_b200 as az
 
@@ -199,16 +206,19 @@ def net_in_loop(args, device_index: int, peaks: dict):
             model = az.ResNet(num_res_blocks=int(b), num_channels=int(c))
             how = "tcgen05 fused kernel" if int(c) == 64 else "cuDNN"
             name, flops = f"ResNet {b}x{c} (bf16, {how})", model.flops_per_position()
-        E, S = args.net_games, args.net_sims
+        total_games = args.net_games if world == 1 else args.net_games_sharded
+        E, S = total_games // world, args.net_sims
         torch.manual_seed(0)
         search = az.AlphaZeroSearch(model=model, num_simulations=S, device=device_index, **kw)
         eng = search.engine_for(E)
         eng.reset_games()
-        g = torch.Generator(device="cpu").manual_seed(1)
+        g = torch.Generator(device="cpu").manual_seed(1 + rank)
         u = torch.rand((args.net_steps + 1, E), dtype=torch.float64, generator=g).to(eng.device)
         search.simulate(eng)  # warm-up move step (includes graph capture)
         eng.sample_moves(u[0])
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         st0 = eng.stats()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -219,18 +229,65 @@ def net_in_loop(args, device_index: int, peaks: dict):
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1)
         st = diff(st0, eng.stats())
-        eng.drain_episodes()
-        sims_s = st["simulations"] / ms * 1e3
-        evals_s = E * S * args.net_steps / ms * 1e3  # every slot occupies a batch row each simulation
-        out.append({"workload": f"connect4_selfplay_{spec}_{E}x{S}", "net": name, "num_games": E, "num_simulations": S,
-                    "move_steps": args.net_steps, "sims_per_s": sims_s, "us_per_sim_step": ms * 1e3 / (args.net_steps * S),
-                    "flops_per_position": flops, "tensor_tflops": evals_s * flops / 1e12,
-                    "tensor_pipe_frac_of_measured_bf16": evals_s * flops / 1e12 / peaks["bf16_tflops"],
-                    "leaf_eval_fraction": st["evaluations"] / max(1, st["simulations"])})
+        sims, evals = float(st["simulations"]), float(st["evaluations"])
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            c = torch.tensor([sims, evals], dtype=torch.float64, device=eng.device)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            ms, sims, evals = float(t.item()), float(c[0].item()), float(c[1].item())
+            eng.drain_episodes_device()
+        else:
+            eng.drain_episodes()
+        sims_s = sims / ms * 1e3
+        evals_s = E * world * S * args.net_steps / ms * 1e3  # every slot occupies a batch row each simulation
+        rec = {"workload": f"connect4_selfplay_{spec}_{total_games}x{S}", "net": name, "num_games": total_games, "games_per_gpu": E,
+               "n_gpus": world, "num_simulations": S, "move_steps": args.net_steps, "sims_per_s": sims_s,
+               "us_per_sim_step": ms * 1e3 / (args.net_steps * S), "flops_per_position": flops, "tensor_tflops": evals_s * flops / 1e12,
+               "tensor_pipe_frac_of_measured_bf16": evals_s * flops / 1e12 / (peaks["bf16_tflops"] * world),
+               "leaf_eval_fraction": evals / max(1.0, sims)}
+        out.append(rec)
         search._engine.close()
         del search, eng
         torch.cuda.empty_cache()
     return out or None
+
+
+def tree_scaling(args, device_index: int, peaks: dict, kind: int):
+    """The fused tree kernel at larger tree counts (same S, same evaluator): the kernel is latency-bound, so its fraction
+    of the HBM roofline grows with the number of independent trees until the issue slots fill."""
+    import numpy as np
+    import torch
+
+    import alphazero_implementation_b200 as az
+
+    out = []
+    for E in (16384, 65536):
+        eng = az.Engine(num_games=E, num_simulations=args.sims, device=device_index, lanes_per_tree=args.lanes, hot_nodes=args.hot_nodes)
+        eng.reset_games()
+        u = torch.from_numpy(np.random.RandomState(5).random_sample((8, E))).to(eng.device)
+        for i in range(3):
+            eng.run_simulations(args.sims, kind)
+            eng.sample_moves(u[i])
+        torch.cuda.synchronize()
+        st0 = eng.stats()
+        ms = 0.0
+        for i in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.run_simulations(args.sims, kind)
+            b.record()
+            eng.sample_moves(u[3 + i])
+            torch.cuda.synchronize()
+            ms += a.elapsed_time(b)
+        st = diff(st0, eng.stats())
+        gbs = algorithmic_bytes(st) / (ms * 1e-3) / 1e9
+        out.append({"trees": E, "num_simulations": args.sims, "kernel": "k_run_sims", "kernel_ms": ms / 5, "sims_per_s": st["simulations"] / ms * 1e3,
+                    "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]})
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_b200(args):
@@ -360,7 +417,8 @@ def run_b200(args):
     if world > 1:
         from alphazero_implementation_b200.distributed import all_gather_episodes
 
-        for _ in range(3):
+        all_gather_episodes(eng.drain_episodes_device())  # first call: NCCL channel set-up
+        for _ in range(6):
             eng.run_simulations(S, kind); eng.sample_moves(u_all[0])
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -377,13 +435,19 @@ def run_b200(args):
         cpu = {"value": r["sims_per_s"], "unit": "sims/s", "cores": r["cores"], "kind": "port",
                "sample": f"{r['steps']} move steps of {E} games x {S} sims from the initial position ({r['seconds']:.1f} s), "
                          "oracle/c4_oracle.c with OpenMP over trees"}
-    extra = None
-    if rank == 0 and world == 1 and args.net != "none":
+    extra, scaling = None, None
+    eng.close()
+    if rank == 0 and world == 1 and not args.no_tree_scaling:
         try:
-            arena_bytes = eng.device_bytes
-            eng.close()
-            extra = net_in_loop(args, local, peaks)
-        except Exception as exc:  # the side measurement must not sink the headline
+            scaling = tree_scaling(args, local, peaks, kind)
+        except Exception as exc:  # side measurements must not sink the headline
+            scaling = {"error": repr(exc)}
+    if args.net != "none":
+        try:
+            extra = net_in_loop(args, local, peaks, world, rank)
+        except Exception as exc:
+            if world > 1:
+                raise  # a rank that skipped the collectives would hang the others
             extra = {"error": repr(exc)}
 
     if rank == 0:
@@ -400,6 +464,8 @@ def run_b200(args):
         }
         if allgather:
             line["episode_allgather"] = allgather
+        if scaling:
+            line["tree_scaling"] = scaling
         if extra:
             line["net_in_loop"] = extra
         print(json.dumps(line), flush=True)
