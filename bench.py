@@ -422,8 +422,10 @@ def run_b200(args):
             eng.run_simulations(S, kind); eng.sample_moves(u_all[0])
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        drained = eng.drain_episodes_device()
+        torch.cuda.synchronize()
         a0.record()
-        merged = all_gather_episodes(eng.drain_episodes_device())
+        merged = all_gather_episodes(drained)
         a1.record()
         torch.cuda.synchronize()
         allgather = {"ms": a0.elapsed_time(a1), "episodes": int(merged["ep_len"].numel()), "samples": int(merged["s_bb0"].numel())}
