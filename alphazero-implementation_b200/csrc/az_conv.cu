@@ -185,16 +185,20 @@ __device__ __forceinline__ void conv_epilogue(uint32_t tmem_base, uint8_t *dst, 
 
 // MMAs of one (layer, group), fully unrolled: 9 taps x 2 tiles x KSTEPS.  Every operand is warp-uniform; one elected
 // lane issues.  Group A waits for each tap's weights; group B finds them there and releases the stage afterwards.
+// Before its last tap the warp already waits for what the NEXT (layer, group) needs (`pre_bar`: that group's epi_done;
+// `pre_full`: tap 0 of the next layer), while the queued MMAs keep the tensor core busy - the hand-over costs no bubble.
 template <int KSTEPS, bool GROUP_B>
-__device__ __forceinline__ void issue_group(uint32_t full0, uint32_t empty0, uint32_t parity, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t tmem_tile0) {
+__device__ __forceinline__ void issue_group(uint32_t full0, uint32_t empty0, uint32_t parity, bool wait_tap0, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t tmem_tile0, uint32_t pre_bar, uint32_t pre_parity, bool pre_full) {
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
         const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);  // rows; one row = 16 B = one descriptor address unit
-        if (!GROUP_B) {
-            mbar_wait(full0 + tap * 8, parity);
-            tc_fence_after();
+        if (!GROUP_B && (tap > 0 || wait_tap0)) mbar_wait(full0 + tap * 8, parity);
+        if (tap == 8) {
+            if (pre_bar) mbar_wait(pre_bar, pre_parity);
+            if (pre_full) mbar_wait(full0, parity ^ 1u);
         }
+        tc_fence_after();
         if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < GTILES; ++t)
@@ -291,17 +295,20 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
             const uint64_t b_desc = smem_desc(ring0, LBO_W, l == 0 ? SBO_WS : SBO_W);
 #pragma unroll 1
             for (int g = 0; g < 2; ++g) {
-                if (l > 0) mbar_wait(epi_done0 + g * 8, (uint32_t)(l - 1) & 1u);  // this group's input is written, its TMEM tiles are free
-                tc_fence_after();
+                // this group's input is written and its TMEM tiles are free once epi_done[g] of the previous layer completes: the
+                // previous (layer, group) waited for that before its last tap (pre_bar below)
                 const uint32_t tile0 = tmem_base + g * GTILES * C;
                 const uint64_t a_desc = smem_desc(src + g * GROWS * ROWB, LBO_A, SBO_A);
+                const bool last = l + 1 == n_layers;
+                const uint32_t pre_bar = g == 0 ? (l > 0 ? epi_done0 + 8 : 0u) : (last ? 0u : epi_done0);
+                const uint32_t pre_parity = g == 0 ? (uint32_t)(l - 1) & 1u : (uint32_t)l & 1u;
                 CLK(0, l, g);
                 if (l == 0) {
-                    if (g == 0) issue_group<1, false>(full0, empty0, 0u, a_desc, b_desc, idesc, tile0);
-                    else issue_group<1, true>(full0, empty0, 0u, a_desc, b_desc, idesc, tile0);
+                    if (g == 0) issue_group<1, false>(full0, empty0, 0u, true, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, false);
+                    else issue_group<1, true>(full0, empty0, 0u, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, !last);
                 } else {
-                    if (g == 0) issue_group<C / 16, false>(full0, empty0, (uint32_t)l & 1u, a_desc, b_desc, idesc, tile0);
-                    else issue_group<C / 16, true>(full0, empty0, (uint32_t)l & 1u, a_desc, b_desc, idesc, tile0);
+                    if (g == 0) issue_group<C / 16, false>(full0, empty0, (uint32_t)l & 1u, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, false);
+                    else issue_group<C / 16, true>(full0, empty0, (uint32_t)l & 1u, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, !last);
                 }
                 if (elect_one()) umma_commit(mma_done0 + g * 8);
                 __syncwarp();

@@ -200,36 +200,38 @@ __device__ __forceinline__ Leaf descend(const TreeMem &tm, const double *__restr
     L.first_col = 0;
     bool go = alive && cb != 0;
     bool my_legal = (legal >> c) & 1u;
+    // The loop body is straight-line code: four trees share a warp and an idle eighth lane sits in every tree, so every
+    // `if` here would be a divergent branch with its reconvergence barrier on the dependent chain.  Lanes of finished
+    // trees keep computing on stale (valid) values and every update of the leaf is masked by `go`.
     while (__any_sync(FULL, go)) {
-        double score = -INFINITY;
-        if (go && my_legal) score = puct_score(ch.n, ch.w, ch.p, __ldg(sqt + n_parent), c_puct, rcp);
+        const double s = puct_score(ch.n, ch.w, ch.p, __ldg(sqt + n_parent), c_puct, rcp);
+        const double score = (go && my_legal) ? s : -INFINITY;
         const int bc = argmax_first(score, sub);
         const uint32_t n_sel = __shfl_sync(FULL, ch.n, sub + bc);
         const uint32_t cb_sel = __shfl_sync(FULL, ch.cb, sub + bc);
-        if (go) {
-            // Action.sample_next_state(): drop in column bc, flip the side to move
-            const uint64_t bit = c4::drop_bit(L.b0 | L.b1, bc);
-            if (L.pl == 0) L.b0 |= bit; else L.b1 |= bit;
-            L.pl ^= 1;
-            L.node = cb + __popc(legal & ((1u << bc) - 1u));
-            if (L.depth == 0) L.first_col = bc;
-            L.depth++;
-            if (writer) path[L.depth] = L.node;
-            levels++;
-            scanned += (uint32_t)__popc(legal);
-            n_parent = n_sel;
-            cb = cb_sel;
-            go = cb != 0;
-        }
-        // the children of the node just entered
+        // Action.sample_next_state(): drop in column bc, flip the side to move
+        const uint64_t bit = go ? c4::drop_bit(L.b0 | L.b1, bc) : 0ull;
+        const uint64_t bit0 = L.pl == 0 ? bit : 0ull;
+        L.b0 |= bit0;
+        L.b1 |= bit ^ bit0;
+        L.pl ^= (int)go;
+        const uint32_t entered = cb + __popc(legal & ((1u << bc) - 1u));
+        L.node = go ? entered : L.node;
+        L.first_col = (go && L.depth == 0) ? bc : L.first_col;
+        if (go && writer) path[L.depth + 1] = entered;
+        L.depth += (int)go;
+        levels += (uint32_t)go;
+        scanned += go ? (uint32_t)__popc(legal) : 0u;
+        n_parent = n_sel;
+        cb = cb_sel;
+        go = go && cb_sel != 0;
+        // the children of the node just entered (idle lanes read node 0)
         const uint64_t occ = L.b0 | L.b1;
         const bool can = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);
         const unsigned lg = (__ballot_sync(FULL, can) >> sub) & 0x7Fu;
-        if (go) {
-            legal = lg;
-            my_legal = can;
-            if (can) ch = load_child(tm, cb + __popc(lg & ((1u << c) - 1u)));
-        }
+        legal = lg;
+        my_legal = can;
+        ch = load_child(tm, (go && can) ? cb + __popc(lg & ((1u << c) - 1u)) : 0u);
     }
     // Node.is_terminal of the leaf (node.py:61-63).  Interior nodes are never terminal (a terminal
     // node is never expanded), so only the last mover's stones need the line test.
@@ -265,6 +267,15 @@ __device__ __forceinline__ double backup_sign(double v, int depth, int i, bool l
 // The root's scalars (N, first child, legal mask) and each lane's root-child record live in registers
 // for the whole launch, the first K nodes of every tree in shared memory (loaded at entry, written back
 // at exit), the rest in HBM.  Dynamic shared memory: [TREES][K] uint4, [TREES][K] f64, [TREES][44] u32.
+#ifdef AZ_TRUNK_CLOCKS
+__device__ long long g_run_clk[8];
+#define RCLK(var) const long long var = clock64()
+#define RACC(i, t1, t0) do { racc[i] += (t1) - (t0); } while (0)
+#else
+#define RCLK(var) do { } while (0)
+#define RACC(i, t1, t0) do { } while (0)
+#endif
+
 template <int TPW, int EVAL>
 __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, double c_puct, int K) {
     constexpr int TREES = 2 * TPW;  // per 64-thread block
@@ -318,57 +329,90 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     if (alive && root_cb != 0 && r_can) rch = load_child(tm, root_cb + r_j);
     if (writer) path[0] = 0;
 
+#ifdef AZ_TRUNK_CLOCKS
+    long long racc[4] = {0, 0, 0, 0};
+#endif
     for (int s = 0; s < S; ++s) {
+        RCLK(c0);
         Leaf L = descend(tm, a.rcp, a.sqt, rb0, rb1, rpl, c_puct, root_cb, root_n, r_legal, rch, alive, writer, path, levels,
                          scanned);
+        RCLK(c1);
+        RACC(0, c1, c0);
+        // Straight-line from here on as well (the four trees of a warp end in different cases).
+        // Backup, part 1: lane `lit` owns path[lit]; its W / N loads are issued now and used after the expansion.  A leaf that
+        // is expanded by this simulation is visited for the first time (N = 0, W = 0: a node is expanded on its first
+        // visit), so it needs no load.
+        __syncwarp();  // path[] (written by the tree's first lane) is visible to its other lanes
+        const bool own = alive && lit <= L.depth;
+        const bool fresh = lit == L.depth && !L.term;
+        const uint32_t my_idx = own ? path[lit] : 0u;
+        const bool my_hot = my_idx < tm.K;
+        double w_old = 0.0;
+        uint32_t n_old = 0u;
+        if (own && !fresh) {
+            w_old = my_hot ? tm.sW[my_idx] : tm.gW[my_idx];
+            n_old = my_hot ? reinterpret_cast<const uint32_t *>(tm.sM + my_idx)[0] : reinterpret_cast<const uint32_t *>(tm.gM + my_idx)[0];
+        }
         // leaf: evaluate + expand, or terminal value
         const uint64_t occ = L.b0 | L.b1;
         const bool can = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);
         const unsigned legal = (__ballot_sync(FULL, can) >> sub) & 0x7Fu;
-        double v;
-        if (L.term) {
-            // value = reward[parent.state.player]: the mover's own reward, +1 on a win, 0 on a draw (search.py:76)
-            v = L.win ? 1.0 : 0.0;
+        const int k = __popc(legal);
+        const int j = __popc(legal & ((1u << c) - 1u));
+        float prior, val;
+        if (EVAL == AZ_EVAL_UNIFORM) {
+            prior = __frcp_rn((float)k);  // == fp32(1)/fp32(k): both are the correctly rounded reciprocal
+            val = 0.0f;
         } else {
-            const int k = __popc(legal);
-            const int j = __popc(legal & ((1u << c) - 1u));
-            float prior, val;
-            if (EVAL == AZ_EVAL_UNIFORM) {
-                prior = __frcp_rn((float)k);  // == fp32(1)/fp32(k): both are the correctly rounded reciprocal
-                val = 0.0f;
+            const uint64_t h = azeval::board_hash(L.b0, L.b1, L.pl);
+            prior = __fdiv_rn((float)azeval::hash_weight(h, c), (float)azeval::hash_weight_total(h, legal));
+            const float v0 = azeval::hash_value0(h);
+            val = L.pl == 0 ? v0 : -v0;
+        }
+        const bool expand = alive && !L.term;
+        if (expand && can && first_q) store_new_child(tm, used + j, prior);
+        if (expand && writer) set_first_child(tm, L.node, used);
+        // the root itself was expanded: its children enter the registers; depth 1: the chosen root child got children
+        const bool root_exp = expand && L.depth == 0;
+        const bool mine = L.depth >= 1 && c == L.first_col;
+        root_cb = root_exp ? used : root_cb;
+        rch.w = root_exp ? 0.0 : rch.w;
+        rch.n = root_exp ? 0u : rch.n;
+        rch.p = root_exp ? prior : rch.p;
+        rch.cb = root_exp ? 0u : ((expand && mine && L.depth == 1) ? used : rch.cb);
+        used += expand ? (uint32_t)k : 0u;
+        children += expand ? (uint32_t)k : 0u;
+        evals += (uint32_t)expand;
+        // terminal leaf: reward[parent.state.player], the mover's own reward, +1 on a win, 0 on a draw (search.py:76);
+        // otherwise value[node.state.player] (search.py:91)
+        const double v = L.term ? (L.win ? 1.0 : 0.0) : (double)val;
+        RCLK(c2);
+        RACC(1, c2, c1);
+        // Backup, part 2.  Registers: root and the chosen root child; memory: every node on the path.
+        root_n += (uint32_t)alive;
+        rch.n += (uint32_t)(alive && mine);
+        rch.w = (alive && mine) ? __dadd_rn(rch.w, backup_sign(v, L.depth, 1, L.term)) : rch.w;
+        if (own) {
+            const double w_new = __dadd_rn(w_old, backup_sign(v, L.depth, lit, L.term));
+            if (my_hot) {
+                tm.sW[my_idx] = w_new;
+                reinterpret_cast<uint32_t *>(tm.sM + my_idx)[0] = n_old + 1u;
             } else {
-                const uint64_t h = azeval::board_hash(L.b0, L.b1, L.pl);
-                prior = __fdiv_rn((float)azeval::hash_weight(h, c), (float)azeval::hash_weight_total(h, legal));
-                const float v0 = azeval::hash_value0(h);
-                val = L.pl == 0 ? v0 : -v0;
+                tm.gW[my_idx] = w_new;
+                reinterpret_cast<uint32_t *>(tm.gM + my_idx)[0] = n_old + 1u;
             }
-            if (alive) {
-                if (can && first_q) store_new_child(tm, used + j, prior);
-                if (writer) set_first_child(tm, L.node, used);
-                if (L.depth == 0) {  // the root itself was expanded: its children enter the registers
-                    root_cb = used;
-                    rch.w = 0.0; rch.n = 0; rch.cb = 0; rch.p = prior;
-                } else if (L.depth == 1 && c == L.first_col) {
-                    rch.cb = used;
-                }
-                used += k;
-                children += k;
-                evals++;
-            }
-            v = (double)val;  // value[node.state.player] (search.py:91)
         }
+        if (alive)
+            for (int i = lit + NL; i <= L.depth; i += NL) visit_node(tm, path[i], backup_sign(v, L.depth, i, L.term));
         __syncwarp();
-        if (alive) {
-            // registers: root and the chosen root child; memory: every node on the path
-            root_n += 1u;
-            if (L.depth >= 1 && c == L.first_col) {
-                rch.n += 1u;
-                rch.w = __dadd_rn(rch.w, backup_sign(v, L.depth, 1, L.term));
-            }
-            backup(tm, path, L.depth, v, L.term, lit, NL);
-        }
-        __syncwarp();
+        RCLK(c3);
+        RACC(2, c3, c2);
+        RACC(3, L.depth, 0);
     }
+#ifdef AZ_TRUNK_CLOCKS
+    if (blockIdx.x == 100 && threadIdx.x == 0)
+        for (int i = 0; i < 4; ++i) g_run_clk[i] = racc[i];
+#endif
     // hot prefix back to the arena
     if (alive) {
         const uint32_t hot = used < tm.K ? used : tm.K;
@@ -1314,6 +1358,13 @@ int32_t az_set_roots(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, con
     h->sims_done = 0;
     return AZ_OK;
 }
+
+#ifdef AZ_TRUNK_CLOCKS
+int32_t az_debug_run_clocks(long long *out, int reset) {
+    if (reset) { long long z[8] = {0}; return cudaMemcpyToSymbol(g_run_clk, z, sizeof z) == cudaSuccess ? 0 : 1; }
+    return cudaMemcpyFromSymbol(out, g_run_clk, sizeof(g_run_clk)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 int32_t az_run_simulations(az_engine *h, int32_t num_sims, int32_t eval_kind, void *stream) {
     if (!h) return AZ_E_INVALID;

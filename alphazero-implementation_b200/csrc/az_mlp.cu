@@ -118,6 +118,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&p);
 }
 
+#ifdef AZ_TRUNK_CLOCKS
+__device__ long long g_mlp_clk[16];
+#define MCLK(i) do { if (blockIdx.x == 60 && threadIdx.x == 0) g_mlp_clk[i] = clock64(); } while (0)
+#else
+#define MCLK(i) do { } while (0)
+#endif
+
 // ---- weight pipeline (warp 0, converged; one elected lane issues): bulk async copies (TMA, 1-D) fill two shared-memory stages; an mbarrier
 // per stage reports the bytes landed ("full"); tcgen05.commit reports when the MMAs that read a stage are done ("empty").
 struct Pipe {
@@ -207,6 +214,7 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + ACT_BYTES + NS * STAGE_BYTES + BIAS_BYTES + (2 * NS + 1) * 8);
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const long long row0 = (long long)blockIdx.x * TILE_M;
+    MCLK(0);
     Pipe p;
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
@@ -276,35 +284,45 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
     const uint32_t act_addr = smem_u32(act);
 
     // ---- layer 1: [128 x 64] . [512 x 64]^T
+    MCLK(1);
     if (warp == 0) {
         pipe_layer(p, w1p, K1 / KC, STAGE_BYTES, KC / 16, act_addr, SBO_X, 2, instr_desc(128, 256), tmem_base);
         for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w2p + (size_t)i * STAGE_BYTES, STAGE_BYTES);  // prefetch layer 2 behind the epilogue
     }
+    MCLK(2);
     mbar_wait(p.done, 0);
     tc_fence_after();
+    MCLK(3);
     epilogue_hidden(tmem_base, act, s_bias);
+    MCLK(4);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
 
     // ---- layer 2: [128 x 512] . [512 x 512]^T, K in chunks of KC
+    MCLK(5);
     if (warp == 0) {
         pipe_layer(p, w2p, HID / KC, STAGE_BYTES, KC / 16, act_addr, SBO_ACT, 2, instr_desc(128, 256), tmem_base);
         pipe_load(p, p.g, whp, WH_ELEMS * 2);  // head weights: one 16 KB "chunk" of [16][KC] sub-chunks
     }
+    MCLK(6);
     mbar_wait(p.done, 1);
     tc_fence_after();
+    MCLK(7);
     epilogue_hidden(tmem_base, act, s_bias + HID);
+    MCLK(8);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
 
     // ---- heads: [128 x 512] . [16 x 512]^T
+    MCLK(9);
     if (warp == 0) pipe_layer(p, whp, 1, WH_ELEMS * 2, HID / 16, act_addr, SBO_ACT, 1, instr_desc(128, NH), tmem_base);
     mbar_wait(p.done, 0);
     tc_fence_after();
+    MCLK(10);
     {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((tid & ~31u) << 16), v);
@@ -318,6 +336,7 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
     }
     tc_fence_before();
     __syncthreads();
+    MCLK(11);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
@@ -351,6 +370,10 @@ struct az_mlp {
 };
 
 extern "C" {
+
+#ifdef AZ_TRUNK_CLOCKS
+int32_t az_debug_mlp_clocks(long long *out) { return cudaMemcpyFromSymbol(out, g_mlp_clk, sizeof(g_mlp_clk)) == cudaSuccess ? 0 : 1; }
+#endif
 
 int32_t az_mlp_create(int32_t device, az_mlp **out) {
     if (!out) return AZ_E_INVALID;
