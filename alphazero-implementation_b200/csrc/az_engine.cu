@@ -97,20 +97,27 @@ __device__ __forceinline__ double puct_score(uint32_t n, double w, float p, doub
     return __dadd_rn(q, u);
 }
 
-// first maximum over the 7 columns of an 8-lane quarter: butterfly max, then the lowest lane holding it
-__device__ __forceinline__ int argmax_first(double score, int sub) {
+// first maximum over the 7 columns of an 8-lane quarter: a butterfly over (score, column) pairs - the larger score wins,
+// equal scores keep the lower column (the reference's strict `>` scan keeps the first maximum).  Every lane of the
+// quarter ends with the same column.  (Carrying the column costs one extra shuffle per round, issued alongside the
+// score's two, and saves the equality ballot + find-first-set that would follow a plain max.)
+__device__ __forceinline__ int argmax_first(double score, int c) {
     double m = score;
+    int mi = c;
 #pragma unroll
     for (int off = 4; off >= 1; off >>= 1) {
         const double o = __shfl_xor_sync(FULL, m, off);
-        m = (o > m) ? o : m;
+        const int oi = __shfl_xor_sync(FULL, mi, off);
+        const bool take = (o > m) || (o == m && oi < mi);
+        m = take ? o : m;
+        mi = take ? oi : mi;
     }
-    const unsigned eq = __ballot_sync(FULL, score == m);
-    return __ffs((eq >> sub) & 0xFFu) - 1;
+    return mi;
 }
 
 struct Child {  // the record of "my" column's child at the current node
     double w;
+    double sq;  // sqrt(n): the sqrt(node.visit_count) of the NEXT level if this child is selected, fetched ahead of the need
     uint32_t n, cb;
     float p;
 };
@@ -127,7 +134,7 @@ struct TreeMem {
     uint32_t K;
 };
 
-__device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx) {
+__device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx, const double *__restrict__ sqt) {
     Child ch;
     uint4 m;
     if (idx < tm.K) {
@@ -140,6 +147,7 @@ __device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx) {
     ch.n = m.x;
     ch.p = __uint_as_float(m.y);
     ch.cb = m.z;
+    ch.sq = __ldg(sqt + m.x);
     return ch;
 }
 
@@ -155,8 +163,8 @@ __device__ __forceinline__ void store_new_child(const TreeMem &tm, uint32_t idx,
 }
 
 __device__ __forceinline__ void set_first_child(const TreeMem &tm, uint32_t idx, uint32_t first) {
-    uint4 *p = (idx < tm.K) ? (tm.sM + idx) : (tm.gM + idx);
-    reinterpret_cast<uint32_t *>(p)[2] = first;
+    if (idx < tm.K) reinterpret_cast<uint32_t *>(tm.sM + idx)[2] = first;
+    else reinterpret_cast<uint32_t *>(tm.gM + idx)[2] = first;
 }
 
 __device__ __forceinline__ void visit_node(const TreeMem &tm, uint32_t idx, double dv) {
@@ -181,16 +189,17 @@ struct Leaf {
 
 // AlphaZeroSearch.select_child repeated until an unexpanded node (search.py:72-73, 27-46).
 // Warp-converged: every lane of the warp calls this; `alive` is uniform per quarter.  On entry
-// (cb, n_parent) describe the root and (root_legal, ch) hold the root's legal mask and this lane's
+// (cb, sq_parent = sqrt(N)) describe the root and (root_legal, ch) hold the root's legal mask and this lane's
 // root child record (valid when alive && cb != 0) — the fused kernel keeps them in registers across
 // simulations.  `path[d]` receives the node index at depth d (written by lane 0 of the tree's lanes).
 __device__ __forceinline__ Leaf descend(const TreeMem &tm, const double *__restrict__ rcp, const double *__restrict__ sqt,
                                         uint64_t rb0, uint64_t rb1, int rpl, double c_puct, uint32_t cb,
-                                        uint32_t n_parent, unsigned legal, Child ch, bool alive, bool writer,
+                                        double sq_parent, unsigned legal, Child ch, bool alive, bool writer,
                                         uint32_t *path, uint32_t &levels, uint32_t &scanned) {
     const int lane = threadIdx.x & 31;
     const int sub = lane & 24;
     const int c = lane & 7;
+    const unsigned below = (1u << c) - 1u;
     Leaf L;
     L.b0 = rb0;
     L.b1 = rb1;
@@ -203,35 +212,42 @@ __device__ __forceinline__ Leaf descend(const TreeMem &tm, const double *__restr
     // The loop body is straight-line code: four trees share a warp and an idle eighth lane sits in every tree, so every
     // `if` here would be a divergent branch with its reconvergence barrier on the dependent chain.  Lanes of finished
     // trees keep computing on stale (valid) values and every update of the leaf is masked by `go`.
+    // Dependent chain of one level: child record -> rcp[n + 1] -> PUCT (6 fp64 operations) -> 3 butterfly rounds ->
+    // shuffle of the winner's first-child index -> next child record.  Everything else hangs off that chain: the
+    // winner's sqrt comes with its record, the next node's legal mask is the current one minus the winning column if
+    // that column fills up (known before the winner is), and the board update runs in the shadow of the next load.
     while (__any_sync(FULL, go)) {
-        const double s = puct_score(ch.n, ch.w, ch.p, __ldg(sqt + n_parent), c_puct, rcp);
-        const double score = (go && my_legal) ? s : -INFINITY;
-        const int bc = argmax_first(score, sub);
-        const uint32_t n_sel = __shfl_sync(FULL, ch.n, sub + bc);
+        const uint64_t occ = L.b0 | L.b1;
+        // columns with exactly five stones: one more and they leave the legal mask
+        const bool fills = ((occ >> (c4::STRIDE * c + 4)) & 3ull) == 1ull;
+        const unsigned fill_mask = (__ballot_sync(FULL, fills) >> sub) & 0x7Fu;
+        const double s = puct_score(ch.n, ch.w, ch.p, sq_parent, c_puct, rcp);
+        const int bc = argmax_first((go && my_legal) ? s : -INFINITY, c);
         const uint32_t cb_sel = __shfl_sync(FULL, ch.cb, sub + bc);
+        sq_parent = __shfl_sync(FULL, ch.sq, sub + bc);
+        const unsigned bcbit = 1u << bc;
+        const unsigned lg = legal & ~(fill_mask & bcbit);  // legal mask of the node being entered
+        const bool go_next = go && cb_sel != 0;
+        const bool can = (lg >> c) & 1u;
+        const Child nxt = load_child(tm, (go_next && can) ? cb_sel + __popc(lg & below) : 0u, sqt);
         // Action.sample_next_state(): drop in column bc, flip the side to move
-        const uint64_t bit = go ? c4::drop_bit(L.b0 | L.b1, bc) : 0ull;
+        const uint64_t bit = go ? c4::drop_bit(occ, bc) : 0ull;
         const uint64_t bit0 = L.pl == 0 ? bit : 0ull;
         L.b0 |= bit0;
         L.b1 |= bit ^ bit0;
         L.pl ^= (int)go;
-        const uint32_t entered = cb + __popc(legal & ((1u << bc) - 1u));
+        const uint32_t entered = cb + __popc(legal & (bcbit - 1u));
         L.node = go ? entered : L.node;
         L.first_col = (go && L.depth == 0) ? bc : L.first_col;
         if (go && writer) path[L.depth + 1] = entered;
         L.depth += (int)go;
         levels += (uint32_t)go;
         scanned += go ? (uint32_t)__popc(legal) : 0u;
-        n_parent = n_sel;
         cb = cb_sel;
-        go = go && cb_sel != 0;
-        // the children of the node just entered (idle lanes read node 0)
-        const uint64_t occ = L.b0 | L.b1;
-        const bool can = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);
-        const unsigned lg = (__ballot_sync(FULL, can) >> sub) & 0x7Fu;
+        go = go_next;
         legal = lg;
         my_legal = can;
-        ch = load_child(tm, (go && can) ? cb + __popc(lg & ((1u << c) - 1u)) : 0u);
+        ch = nxt;
     }
     // Node.is_terminal of the leaf (node.py:61-63).  Interior nodes are never terminal (a terminal
     // node is never expanded), so only the last mover's stones need the line test.
@@ -325,8 +341,9 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     const unsigned r_legal = (__ballot_sync(FULL, r_can) >> sub) & 0x7Fu;
     const int r_j = __popc(r_legal & ((1u << c) - 1u));
     Child rch;
-    rch.w = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
-    if (alive && root_cb != 0 && r_can) rch = load_child(tm, root_cb + r_j);
+    rch.w = 0.0; rch.sq = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
+    if (alive && root_cb != 0 && r_can) rch = load_child(tm, root_cb + r_j, a.sqt);
+    double root_sq = __ldg(a.sqt + root_n);
     if (writer) path[0] = 0;
 
 #ifdef AZ_TRUNK_CLOCKS
@@ -334,7 +351,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
 #endif
     for (int s = 0; s < S; ++s) {
         RCLK(c0);
-        Leaf L = descend(tm, a.rcp, a.sqt, rb0, rb1, rpl, c_puct, root_cb, root_n, r_legal, rch, alive, writer, path, levels,
+        Leaf L = descend(tm, a.rcp, a.sqt, rb0, rb1, rpl, c_puct, root_cb, root_sq, r_legal, rch, alive, writer, path, levels,
                          scanned);
         RCLK(c1);
         RACC(0, c1, c0);
@@ -361,7 +378,9 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
         const int j = __popc(legal & ((1u << c) - 1u));
         float prior, val;
         if (EVAL == AZ_EVAL_UNIFORM) {
-            prior = __frcp_rn((float)k);  // == fp32(1)/fp32(k): both are the correctly rounded reciprocal
+            // fp32(1) / fp32(k), k = 1..7: compile-time constants picked by a 3-level select tree (no MUFU slow path)
+            prior = (k & 4) ? ((k & 2) ? ((k & 1) ? 1.0f / 7.0f : 1.0f / 6.0f) : ((k & 1) ? 1.0f / 5.0f : 1.0f / 4.0f))
+                            : ((k & 2) ? ((k & 1) ? 1.0f / 3.0f : 1.0f / 2.0f) : 1.0f);
             val = 0.0f;
         } else {
             const uint64_t h = azeval::board_hash(L.b0, L.b1, L.pl);
@@ -377,7 +396,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
         const bool mine = L.depth >= 1 && c == L.first_col;
         root_cb = root_exp ? used : root_cb;
         rch.w = root_exp ? 0.0 : rch.w;
-        rch.n = root_exp ? 0u : rch.n;
+        rch.n = root_exp ? 0u : rch.n;  // (rch.sq follows rch.n below)
         rch.p = root_exp ? prior : rch.p;
         rch.cb = root_exp ? 0u : ((expand && mine && L.depth == 1) ? used : rch.cb);
         used += expand ? (uint32_t)k : 0u;
@@ -390,7 +409,9 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
         RACC(1, c2, c1);
         // Backup, part 2.  Registers: root and the chosen root child; memory: every node on the path.
         root_n += (uint32_t)alive;
+        root_sq = __ldg(a.sqt + root_n);  // next simulation's sqrt(N_root) and sqrt(N_child): loaded behind the backup
         rch.n += (uint32_t)(alive && mine);
+        rch.sq = __ldg(a.sqt + rch.n);
         rch.w = (alive && mine) ? __dadd_rn(rch.w, backup_sign(v, L.depth, 1, L.term)) : rch.w;
         if (own) {
             const double w_new = __dadd_rn(w_old, backup_sign(v, L.depth, lit, L.term));
@@ -464,11 +485,11 @@ __global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_p
     const bool r_can = (c < c4::W) && !(((rb0 | rb1) >> (c4::STRIDE * c + 5)) & 1ull);
     const unsigned r_legal = (__ballot_sync(FULL, r_can) >> sub) & 0x7Fu;
     Child rch;
-    rch.w = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
-    if (alive && rm.z != 0 && r_can) rch = load_child(tm, rm.z + __popc(r_legal & ((1u << c) - 1u)));
+    rch.w = 0.0; rch.sq = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
+    if (alive && rm.z != 0 && r_can) rch = load_child(tm, rm.z + __popc(r_legal & ((1u << c) - 1u)), a.sqt);
     if (writer) path[0] = 0;
     uint32_t levels = 0, scanned = 0;
-    Leaf L = descend(tm, a.rcp, a.sqt, rb0, rb1, a.root_player[tt], c_puct, rm.z, rm.x, r_legal, rch, alive, writer, path, levels,
+    Leaf L = descend(tm, a.rcp, a.sqt, rb0, rb1, a.root_player[tt], c_puct, rm.z, __ldg(a.sqt + rm.x), r_legal, rch, alive, writer, path, levels,
                      scanned);
     if (writer) {
         a.leaf_node[t] = L.node;
