@@ -108,11 +108,37 @@ __device__ __forceinline__ int argmax_first(double score, int c) {
     for (int off = 4; off >= 1; off >>= 1) {
         const double o = __shfl_xor_sync(FULL, m, off);
         const int oi = __shfl_xor_sync(FULL, mi, off);
-        const bool take = (o > m) || (o == m && oi < mi);
+        // take = (o > m) || (o == m && oi < mi), with the three compares issued side by side (the compiler's own
+        // short-circuit form chains them behind each other on the critical path)
+        int take;
+        asm("{\n\t"
+            ".reg .pred gt, eq, lt;\n\t"
+            "setp.gt.f64 gt, %1, %2;\n\t"
+            "setp.eq.f64 eq, %1, %2;\n\t"
+            "setp.lt.s32 lt, %3, %4;\n\t"
+            "and.pred eq, eq, lt;\n\t"
+            "or.pred gt, gt, eq;\n\t"
+            "selp.s32 %0, 1, 0, gt;\n\t"
+            "}"
+            : "=r"(take)
+            : "d"(o), "d"(m), "r"(oi), "r"(mi));
         m = take ? o : m;
         mi = take ? oi : mi;
     }
     return mi;
+}
+
+// Throughput variant of the same selection: plain max butterfly (two shuffles per round), then the lowest lane holding the
+// maximum by ballot + find-first-set.  Four shuffles fewer per level; the ballot / ffs tail is longer on the dependent chain.
+__device__ __forceinline__ int argmax_first_ballot(double score, int sub) {
+    double m = score;
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) {
+        const double o = __shfl_xor_sync(FULL, m, off);
+        m = (o > m) ? o : m;
+    }
+    const unsigned eq = __ballot_sync(FULL, score == m);
+    return __ffs((eq >> sub) & 0xFFu) - 1;
 }
 
 struct Child {  // the record of "my" column's child at the current node
@@ -134,6 +160,7 @@ struct TreeMem {
     uint32_t K;
 };
 
+template <bool LAT>
 __device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx, const double *__restrict__ sqt) {
     Child ch;
     uint4 m;
@@ -147,7 +174,7 @@ __device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx, con
     ch.n = m.x;
     ch.p = __uint_as_float(m.y);
     ch.cb = m.z;
-    ch.sq = __ldg(sqt + m.x);
+    ch.sq = LAT ? __ldg(sqt + m.x) : 0.0;
     return ch;
 }
 
@@ -192,6 +219,10 @@ struct Leaf {
 // (cb, sq_parent = sqrt(N)) describe the root and (root_legal, ch) hold the root's legal mask and this lane's
 // root child record (valid when alive && cb != 0) — the fused kernel keeps them in registers across
 // simulations.  `path[d]` receives the node index at depth d (written by lane 0 of the tree's lanes).
+// LAT = true: the latency-optimised variant, for launches with few warps per SM (a simulation is one long dependent chain
+// and nothing else hides it); LAT = false: fewer shuffles and loads per level, for launches that fill the issue slots.
+// Measured on B200 (sims/s, 200 sims/move): 4096 trees 1.97e9 vs 1.81e9; 16384 trees 3.78e9 vs 4.45e9.
+template <bool LAT>
 __device__ __forceinline__ Leaf descend(const TreeMem &tm, const double *__restrict__ rcp, const double *__restrict__ sqt,
                                         uint64_t rb0, uint64_t rb1, int rpl, double c_puct, uint32_t cb,
                                         double sq_parent, unsigned legal, Child ch, bool alive, bool writer,
@@ -222,14 +253,16 @@ __device__ __forceinline__ Leaf descend(const TreeMem &tm, const double *__restr
         const bool fills = ((occ >> (c4::STRIDE * c + 4)) & 3ull) == 1ull;
         const unsigned fill_mask = (__ballot_sync(FULL, fills) >> sub) & 0x7Fu;
         const double s = puct_score(ch.n, ch.w, ch.p, sq_parent, c_puct, rcp);
-        const int bc = argmax_first((go && my_legal) ? s : -INFINITY, c);
+        const double masked = (go && my_legal) ? s : -INFINITY;
+        const int bc = LAT ? argmax_first(masked, c) : argmax_first_ballot(masked, sub);
         const uint32_t cb_sel = __shfl_sync(FULL, ch.cb, sub + bc);
-        sq_parent = __shfl_sync(FULL, ch.sq, sub + bc);
+        if (LAT) sq_parent = __shfl_sync(FULL, ch.sq, sub + bc);
+        else sq_parent = __ldg(sqt + __shfl_sync(FULL, ch.n, sub + bc));
         const unsigned bcbit = 1u << bc;
         const unsigned lg = legal & ~(fill_mask & bcbit);  // legal mask of the node being entered
         const bool go_next = go && cb_sel != 0;
         const bool can = (lg >> c) & 1u;
-        const Child nxt = load_child(tm, (go_next && can) ? cb_sel + __popc(lg & below) : 0u, sqt);
+        const Child nxt = load_child<LAT>(tm, (go_next && can) ? cb_sel + __popc(lg & below) : 0u, sqt);
         // Action.sample_next_state(): drop in column bc, flip the side to move
         const uint64_t bit = go ? c4::drop_bit(occ, bc) : 0ull;
         const uint64_t bit0 = L.pl == 0 ? bit : 0ull;
@@ -292,7 +325,7 @@ __device__ long long g_run_clk[8];
 #define RACC(i, t1, t0) do { } while (0)
 #endif
 
-template <int TPW, int EVAL>
+template <int TPW, int EVAL, bool LAT>
 __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, double c_puct, int K) {
     constexpr int TREES = 2 * TPW;  // per 64-thread block
     constexpr int NL = 32 / TPW;    // lanes per tree
@@ -324,12 +357,17 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     uint32_t used = a.used[tt];
     uint32_t levels = 0, evals = 0, children = 0, scanned = 0;
 
-    // hot prefix of the tree -> shared memory
-    if (alive) {
+    // hot prefix of the tree -> shared memory.  Lanes without a tree of their own (tt = 0) fill their slot with tree 0's
+    // records: the straight-line code below lets every lane load and score (masked), so what it reads must be valid.
+    {
         const uint32_t hot = used < tm.K ? used : tm.K;
         for (uint32_t i = lit; i < hot; i += NL) {
             tm.sM[i] = tm.gM[i];
             tm.sW[i] = tm.gW[i];
+        }
+        if (hot == 0 && lit == 0 && tm.K > 0) {
+            tm.sM[0] = make_uint4(0u, 0u, 0u, 0u);
+            tm.sW[0] = 0.0;
         }
     }
     __syncwarp();
@@ -342,7 +380,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     const int r_j = __popc(r_legal & ((1u << c) - 1u));
     Child rch;
     rch.w = 0.0; rch.sq = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
-    if (alive && root_cb != 0 && r_can) rch = load_child(tm, root_cb + r_j, a.sqt);
+    if (alive && root_cb != 0 && r_can) rch = load_child<LAT>(tm, root_cb + r_j, a.sqt);
     double root_sq = __ldg(a.sqt + root_n);
     if (writer) path[0] = 0;
 
@@ -351,7 +389,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
 #endif
     for (int s = 0; s < S; ++s) {
         RCLK(c0);
-        Leaf L = descend(tm, a.rcp, a.sqt, rb0, rb1, rpl, c_puct, root_cb, root_sq, r_legal, rch, alive, writer, path, levels,
+        Leaf L = descend<LAT>(tm, a.rcp, a.sqt, rb0, rb1, rpl, c_puct, root_cb, root_sq, r_legal, rch, alive, writer, path, levels,
                          scanned);
         RCLK(c1);
         RACC(0, c1, c0);
@@ -411,7 +449,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
         root_n += (uint32_t)alive;
         root_sq = __ldg(a.sqt + root_n);  // next simulation's sqrt(N_root) and sqrt(N_child): loaded behind the backup
         rch.n += (uint32_t)(alive && mine);
-        rch.sq = __ldg(a.sqt + rch.n);
+        if (LAT) rch.sq = __ldg(a.sqt + rch.n);
         rch.w = (alive && mine) ? __dadd_rn(rch.w, backup_sign(v, L.depth, 1, L.term)) : rch.w;
         if (own) {
             const double w_new = __dadd_rn(w_old, backup_sign(v, L.depth, lit, L.term));
@@ -455,7 +493,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
 
 // ------------------------------------------------------------------------------------------------
 // split path, step 1: search.py:69-79
-template <int TPW>
+template <int TPW, bool LAT>
 __global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_puct) {
     constexpr int TREES = 2 * TPW;
     constexpr int NL = 32 / TPW;
@@ -486,10 +524,10 @@ __global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_p
     const unsigned r_legal = (__ballot_sync(FULL, r_can) >> sub) & 0x7Fu;
     Child rch;
     rch.w = 0.0; rch.sq = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
-    if (alive && rm.z != 0 && r_can) rch = load_child(tm, rm.z + __popc(r_legal & ((1u << c) - 1u)), a.sqt);
+    if (alive && rm.z != 0 && r_can) rch = load_child<LAT>(tm, rm.z + __popc(r_legal & ((1u << c) - 1u)), a.sqt);
     if (writer) path[0] = 0;
     uint32_t levels = 0, scanned = 0;
-    Leaf L = descend(tm, a.rcp, a.sqt, rb0, rb1, a.root_player[tt], c_puct, rm.z, __ldg(a.sqt + rm.x), r_legal, rch, alive, writer, path, levels,
+    Leaf L = descend<LAT>(tm, a.rcp, a.sqt, rb0, rb1, a.root_player[tt], c_puct, rm.z, __ldg(a.sqt + rm.x), r_legal, rch, alive, writer, path, levels,
                      scanned);
     if (writer) {
         a.leaf_node[t] = L.node;
@@ -1387,6 +1425,18 @@ int32_t az_debug_run_clocks(long long *out, int reset) {
 }
 #endif
 
+// Which descend variant a launch of `blocks` 64-thread blocks gets: the latency-optimised one while the grid leaves the SMs
+// mostly idle (<= 6 blocks = 12 warps per SM), the throughput one beyond.  AZ_TREE_VARIANT=lat|thr overrides (A/B runs).
+static bool latency_variant(const az_engine *h, int blocks) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char *e = getenv("AZ_TREE_VARIANT");
+        forced = !e ? -1 : (e[0] == 'l' ? 1 : (e[0] == 't' ? 0 : -1));
+    }
+    if (forced >= 0) return forced == 1;
+    return blocks <= 6 * h->num_sms;
+}
+
 int32_t az_run_simulations(az_engine *h, int32_t num_sims, int32_t eval_kind, void *stream) {
     if (!h) return AZ_E_INVALID;
     if (num_sims < 0) return fail(h, AZ_E_INVALID, "%s", "az_run_simulations: num_sims < 0");
@@ -1409,10 +1459,16 @@ int32_t az_run_simulations(az_engine *h, int32_t num_sims, int32_t eval_kind, vo
     }
     if (h->force_hot_nodes >= 0) K = (h->force_hot_nodes < h->a.cap ? h->force_hot_nodes : h->a.cap) & ~7;
     const size_t smem = (size_t)trees_per_block * ((size_t)K * 24 + PATH_STRIDE * 4);
-#define AZ_RUN(TPW_, EV_)                                                                                                \
-    do {                                                                                                                 \
-        AZ_CUDA(h, cudaFuncSetAttribute(k_run_sims<TPW_, EV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_run_sims<TPW_, EV_><<<blocks, 64, smem, S(stream)>>>(h->a, n, num_sims, c, K);                                 \
+    const bool lat = latency_variant(h, blocks);
+#define AZ_RUN1(TPW_, EV_, LAT_)                                                                                               \
+    do {                                                                                                                       \
+        AZ_CUDA(h, cudaFuncSetAttribute(k_run_sims<TPW_, EV_, LAT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_run_sims<TPW_, EV_, LAT_><<<blocks, 64, smem, S(stream)>>>(h->a, n, num_sims, c, K);                                 \
+    } while (0)
+#define AZ_RUN(TPW_, EV_)                 \
+    do {                                  \
+        if (lat) AZ_RUN1(TPW_, EV_, true); \
+        else AZ_RUN1(TPW_, EV_, false);   \
     } while (0)
     if (tpw == 1) {
         if (eval_kind == AZ_EVAL_UNIFORM) AZ_RUN(1, AZ_EVAL_UNIFORM); else AZ_RUN(1, AZ_EVAL_HASH);
@@ -1422,6 +1478,7 @@ int32_t az_run_simulations(az_engine *h, int32_t num_sims, int32_t eval_kind, vo
         if (eval_kind == AZ_EVAL_UNIFORM) AZ_RUN(4, AZ_EVAL_UNIFORM); else AZ_RUN(4, AZ_EVAL_HASH);
     }
 #undef AZ_RUN
+#undef AZ_RUN1
     h->last_hot_nodes = K;
     h->sims_done += num_sims;
     AZ_LAUNCH_CHECK(h, "k_run_sims");
@@ -1434,9 +1491,17 @@ int32_t az_select_leaves(az_engine *h, void *stream) {
     const int n = h->n_active;
     if (h->sims_done + 1 > h->cfg.num_simulations)
         return fail(h, AZ_E_INVALID, "%s", "az_select_leaves: more simulations on these roots than the arena holds");
-    if (h->G == 32) k_select<1><<<blocks_for(n, 2), 64, 0, S(stream)>>>(h->a, n, h->cfg.c_puct);
-    else if (h->G == 16) k_select<2><<<blocks_for(n, 4), 64, 0, S(stream)>>>(h->a, n, h->cfg.c_puct);
-    else k_select<4><<<blocks_for(n, 8), 64, 0, S(stream)>>>(h->a, n, h->cfg.c_puct);
+    const int tpb = 2 * (32 / h->G);
+    const bool lat = latency_variant(h, blocks_for(n, tpb));
+#define AZ_SEL(TPW_)                                                                                         \
+    do {                                                                                                     \
+        if (lat) k_select<TPW_, true><<<blocks_for(n, tpb), 64, 0, S(stream)>>>(h->a, n, h->cfg.c_puct);     \
+        else k_select<TPW_, false><<<blocks_for(n, tpb), 64, 0, S(stream)>>>(h->a, n, h->cfg.c_puct);        \
+    } while (0)
+    if (h->G == 32) AZ_SEL(1);
+    else if (h->G == 16) AZ_SEL(2);
+    else AZ_SEL(4);
+#undef AZ_SEL
     AZ_LAUNCH_CHECK(h, "k_select");
     h->sims_done += 1;
     return AZ_OK;
