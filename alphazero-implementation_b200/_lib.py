@@ -87,6 +87,7 @@ SIGNATURES = {
     "az_reset_games": (I32, [P, C.c_uint64, C.c_uint64, I32, P]),
     "az_set_roots": (I32, [P, P, P, P, I32, P]),
     "az_run_simulations": (I32, [P, I32, I32, P]),
+    "az_run_move_step": (I32, [P, I32, I32, P, P, P]),
     "az_select_leaves": (I32, [P, P]),
     "az_gather_leaves": (I32, [P, P, I32, P]),
     "az_expand_backup": (I32, [P, P, P, I32, P]),

@@ -325,8 +325,25 @@ __device__ long long g_run_clk[8];
 #define RACC(i, t1, t0) do { } while (0)
 #endif
 
-template <int TPW, int EVAL, bool LAT>
-__global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, double c_puct, int K) {
+__device__ __forceinline__ void reset_tree(const Arena &a, int t) {
+    const size_t base = (size_t)t * a.cap;
+    a.W[base] = 0.0;
+    a.M[base] = make_uint4(0u, 0u, 0u, 0u);
+    a.used[t] = 1u;
+}
+
+// MOVE = true: the launch also plays the self-play move of every tree (what k_sample_moves does) - the root's child
+// statistics are still in registers, the step's uniform and the game-log position were fetched at kernel entry, and the
+// tree is discarded anyway (node.py:37-41), so the hot prefix is not written back.
+struct MoveArgs {
+    const double *uniforms;
+    uint8_t *finished;
+    uint64_t init0, init1;
+    int step, initpl;
+};
+
+template <int TPW, int EVAL, bool LAT, bool MOVE>
+__global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, double c_puct, int K, MoveArgs mv) {
     constexpr int TREES = 2 * TPW;  // per 64-thread block
     constexpr int NL = 32 / TPW;    // lanes per tree
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -338,9 +355,10 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     const int tib = warp * TPW + q;
     const int t = blockIdx.x * TREES + tib;
     const bool alive = (t < n_active) && (a.tree_err[t < n_active ? t : 0] == 0);
+    const int lit = lane & (NL - 1);
+    if (MOVE && t < n_active && lit == 0 && mv.finished) mv.finished[t] = 0;
     if (!__any_sync(FULL, alive)) return;
     const int tt = alive ? t : 0;
-    const int lit = lane & (NL - 1);
     const bool writer = alive && lit == 0;
     const bool first_q = lit < 8;
 
@@ -356,6 +374,12 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     const int rpl = a.root_player[tt];
     uint32_t used = a.used[tt];
     uint32_t levels = 0, evals = 0, children = 0, scanned = 0;
+    double mv_u = 0.0;
+    int mv_len = 0;
+    if (MOVE && alive) {
+        mv_u = mv.uniforms[t];
+        mv_len = a.g_len[t];
+    }
 
     // hot prefix of the tree -> shared memory.  Lanes without a tree of their own (tt = 0) fill their slot with tree 0's
     // records: the straight-line code below lets every lane load and score (masked), so what it reads must be valid.
@@ -472,12 +496,99 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     if (blockIdx.x == 100 && threadIdx.x == 0)
         for (int i = 0; i < 4; ++i) g_run_clk[i] = racc[i];
 #endif
-    // hot prefix back to the arena
-    if (alive) {
-        const uint32_t hot = used < tm.K ? used : tm.K;
-        for (uint32_t i = lit; i < hot; i += NL) {
-            tm.gM[i] = tm.sM[i];
-            tm.gW[i] = tm.sW[i];
+    uint32_t moves = 0, episodes = 0;
+    if (!MOVE) {
+        // hot prefix back to the arena
+        if (alive) {
+            const uint32_t hot = used < tm.K ? used : tm.K;
+            for (uint32_t i = lit; i < hot; i += NL) {
+                tm.gM[i] = tm.sM[i];
+                tm.gW[i] = tm.sW[i];
+            }
+        }
+    } else {
+        // ---- the move step of this tree's game (episode_generator.py:53-78, node.py:23-42), same arithmetic as k_sample_moves
+        const bool mover = alive && root_cb != 0;
+        const int32_t cnt = (mover && r_can) ? (int32_t)rch.n : 0;
+        const double p = __ddiv_rn((double)cnt, (double)((int)root_n - 1));  // improved_policy (node.py:27)
+        double acc = 0.0, mycdf = 0.0;
+        bool first = true;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {  // p.cumsum() over the legal columns, left to right
+            const double pj = __shfl_sync(FULL, p, sub + j);
+            const bool lj = (r_legal >> j) & 1u;
+            acc = lj ? (first ? pj : __dadd_rn(acc, pj)) : acc;
+            first = first && !lj;
+            mycdf = (j == c) ? acc : mycdf;
+        }
+        // np.random.choice(k, p): cdf /= cdf[-1]; idx = searchsorted(cdf, u, side='right') = #{cdf <= u}
+        const bool le = mover && r_can && __ddiv_rn(mycdf, acc) <= mv_u;
+        int idx = __popc((__ballot_sync(FULL, le) >> sub) & 0x7Fu);
+        const int k = __popc(r_legal);
+        idx = idx >= k ? k - 1 : idx;
+        const int col = c4::nth_legal_column(r_legal, idx < 0 ? 0 : idx);
+        uint64_t nb0 = rb0, nb1 = rb1;
+        const uint64_t bit = c4::drop_bit(rb0 | rb1, col);
+        if (rpl == 0) nb0 |= bit; else nb1 |= bit;
+        const bool win = c4::has4(rpl ? nb1 : nb0);
+        const bool ended = win || c4::is_full(nb0 | nb1);
+        const int new_len = mv_len + 1;
+        // sample = (state, improved_policy) recorded before the move (episode_generator.py:56-62)
+        if (mover && first_q && mv_len < MAX_PLIES) {
+            const size_t o = (size_t)t * MAX_PLIES + mv_len;
+            if (c < 7) a.g_counts[o * 7 + c] = cnt;
+            if (lit == 0) {
+                a.g_bb0[o] = rb0;
+                a.g_bb1[o] = rb1;
+                a.g_player[o] = (uint8_t)rpl;
+            }
+        }
+        __syncwarp();
+        long long dst = -1;
+        if (mover && lit == 0) {
+            moves = 1;
+            if (!ended) {
+                a.root_bb0[t] = nb0;
+                a.root_bb1[t] = nb1;
+                a.root_player[t] = (uint8_t)(rpl ^ 1);
+                a.g_len[t] = new_len;
+            } else {
+                // outcome to every sample (episode.py:52-54); emit; recycle the slot (episode_generator.py:71-78)
+                const int8_t r0 = win ? (rpl == 0 ? 1 : -1) : 0;
+                const unsigned long long e = atomicAdd(&a.ring[0], 1ull);
+                const unsigned long long o = atomicAdd(&a.ring[1], (unsigned long long)new_len);
+                if ((long long)e < a.ep_cap && (long long)(o + new_len) <= a.s_cap) {
+                    a.ep_slot[e] = t;
+                    a.ep_step[e] = mv.step;
+                    a.ep_len[e] = new_len;
+                    a.ep_offset[e] = (int64_t)o;
+                    a.ep_outcome[2 * e] = r0;
+                    a.ep_outcome[2 * e + 1] = (int8_t)-r0;
+                    dst = (long long)o;
+                } else {
+                    atomicAdd(&a.ring[2], 1ull);
+                }
+                episodes = 1;
+                a.root_bb0[t] = mv.init0;
+                a.root_bb1[t] = mv.init1;
+                a.root_player[t] = (uint8_t)mv.initpl;
+                a.g_len[t] = 0;
+                if (mv.finished) mv.finished[t] = 1;
+            }
+            reset_tree(a, t);  // no subtree reuse: the new root has no children (node.py:37-41)
+            used = 1u;
+        }
+        // the finished game's samples -> ring, one lane per sample
+        dst = __shfl_sync(FULL, dst, lane - lit);
+        if (dst >= 0) {
+            const size_t g0 = (size_t)t * MAX_PLIES;
+            for (int qq = lit; qq < new_len; qq += NL) {
+                a.s_bb0[dst + qq] = a.g_bb0[g0 + qq];
+                a.s_bb1[dst + qq] = a.g_bb1[g0 + qq];
+                a.s_player[dst + qq] = a.g_player[g0 + qq];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) a.s_counts[(dst + qq) * 7 + i] = a.g_counts[(g0 + qq) * 7 + i];
+            }
         }
     }
     if (writer) {
@@ -487,6 +598,8 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
         st[1] += evals;
         st[2] += levels;
         st[3] += children;
+        st[4] += moves;
+        st[5] += episodes;
         st[6] += scanned;
     }
 }
@@ -857,13 +970,6 @@ k_masked_softmax(const float *__restrict__ logits, const uint8_t *__restrict__ l
 
 // ------------------------------------------------------------------------------------------------
 // roots / results
-__device__ __forceinline__ void reset_tree(const Arena &a, int t) {
-    const size_t base = (size_t)t * a.cap;
-    a.W[base] = 0.0;
-    a.M[base] = make_uint4(0u, 0u, 0u, 0u);
-    a.used[t] = 1u;
-}
-
 __global__ void __launch_bounds__(256)
 k_set_roots(Arena a, const uint64_t *bb0, const uint64_t *bb1, const uint8_t *player, uint64_t c0, uint64_t c1,
             int cpl, int n, int clear_logs) {
@@ -917,12 +1023,10 @@ k_leaf_info(Arena a, int n, uint64_t *o0, uint64_t *o1, uint8_t *opl, uint8_t *o
 }
 
 // ------------------------------------------------------------------------------------------------
-// self-play move step (episode_generator.py:53-78, node.py:23-42), one thread per slot
-__global__ void __launch_bounds__(128)
-k_sample_moves(Arena a, int n, const double *__restrict__ uniforms, uint8_t *finished, int step, uint64_t init0,
-               uint64_t init1, int initpl) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
+// This slot's part of a move step: record the sample, draw and play the move, emit the episode header if the game ended.
+// Returns through copy_len / copy_dst the finished game's samples still to be copied into the ring.
+__device__ __forceinline__ void sample_move_slot(const Arena &a, int t, const double *__restrict__ uniforms, uint8_t *finished, int step,
+                                                 uint64_t init0, uint64_t init1, int initpl, int &copy_len, long long &copy_dst) {
     if (finished) finished[t] = 0;
     if (a.tree_err[t]) return;
     const size_t base = (size_t)t * a.cap;
@@ -996,13 +1100,8 @@ k_sample_moves(Arena a, int n, const double *__restrict__ uniforms, uint8_t *fin
             a.ep_offset[e] = (int64_t)o;
             a.ep_outcome[2 * e] = r0;
             a.ep_outcome[2 * e + 1] = (int8_t)-r0;
-            for (int q = 0; q < new_len; ++q) {
-                const size_t src = (size_t)t * MAX_PLIES + q;
-                a.s_bb0[o + q] = a.g_bb0[src];
-                a.s_bb1[o + q] = a.g_bb1[src];
-                a.s_player[o + q] = a.g_player[src];
-                for (int c = 0; c < 7; ++c) a.s_counts[(o + q) * 7 + c] = a.g_counts[src * 7 + c];
-            }
+            copy_len = new_len;  // the samples are copied by the whole warp below
+            copy_dst = (long long)o;
         } else {
             atomicAdd(&a.ring[2], 1ull);
         }
@@ -1014,6 +1113,34 @@ k_sample_moves(Arena a, int n, const double *__restrict__ uniforms, uint8_t *fin
         if (finished) finished[t] = 1;
     }
     reset_tree(a, t);  // no subtree reuse: the new root has no children (node.py:37-41)
+}
+
+// self-play move step (episode_generator.py:53-78, node.py:23-42): one thread per slot for the move itself; the samples of
+// games that ended (up to 42 x 45 bytes each, cold in L2 / HBM) are then copied into the ring by the whole warp, one
+// lane per sample, so the few threads with a finished game do not serialise dozens of dependent loads.
+__global__ void __launch_bounds__(128)
+k_sample_moves(Arena a, int n, const double *__restrict__ uniforms, uint8_t *finished, int step, uint64_t init0,
+               uint64_t init1, int initpl) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int copy_len = 0;
+    long long copy_dst = 0;
+    if (t < n) sample_move_slot(a, t, uniforms, finished, step, init0, init1, initpl, copy_len, copy_dst);
+    __syncwarp();  // the sample recorded by this step is visible to the lanes that copy it
+    unsigned todo = __ballot_sync(FULL, copy_len > 0);
+    while (todo) {
+        const int src_lane = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int len = __shfl_sync(FULL, copy_len, src_lane);
+        const long long dst = __shfl_sync(FULL, copy_dst, src_lane);
+        const size_t g0 = (size_t)(t - lane + src_lane) * MAX_PLIES;
+        for (int q = lane; q < len; q += 32) {
+            a.s_bb0[dst + q] = a.g_bb0[g0 + q];
+            a.s_bb1[dst + q] = a.g_bb1[g0 + q];
+            a.s_player[dst + q] = a.g_player[g0 + q];
+        }
+        for (int i = lane; i < len * 7; i += 32) a.s_counts[dst * 7 + i] = a.g_counts[g0 * 7 + i];
+    }
 }
 
 __global__ void __launch_bounds__(256) k_init_tables(double *rcp, double *sqt, int n) {
@@ -1437,8 +1564,31 @@ static bool latency_variant(const az_engine *h, int blocks) {
     return blocks <= 6 * h->num_sms;
 }
 
+static int32_t run_sims_impl(az_engine *h, int32_t num_sims, int32_t eval_kind, const double *uniforms, uint8_t *finished, bool move,
+                             void *stream);
+
 int32_t az_run_simulations(az_engine *h, int32_t num_sims, int32_t eval_kind, void *stream) {
     if (!h) return AZ_E_INVALID;
+    if (num_sims == 0) return AZ_OK;
+    return run_sims_impl(h, num_sims, eval_kind, nullptr, nullptr, false, stream);
+}
+
+/* az_run_simulations followed by az_sample_moves in ONE launch (same results): the self-play move step for the built-in
+ * evaluators.  uniforms[num_games] f64 in [0,1) (device), finished[num_games] u8 or null. */
+int32_t az_run_move_step(az_engine *h, int32_t num_sims, int32_t eval_kind, const double *uniforms, uint8_t *finished, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (!uniforms) return fail(h, AZ_E_INVALID, "%s", "az_run_move_step: null uniforms");
+    if (!h->have_init) return fail(h, AZ_E_STATE, "%s", "az_run_move_step: call az_reset_games first");
+    if (num_sims < 1) return fail(h, AZ_E_INVALID, "%s", "az_run_move_step: num_sims < 1");
+    const int32_t rc = run_sims_impl(h, num_sims, eval_kind, uniforms, finished, true, stream);
+    if (rc != AZ_OK) return rc;
+    h->step++;
+    h->sims_done = 0;
+    return AZ_OK;
+}
+
+static int32_t run_sims_impl(az_engine *h, int32_t num_sims, int32_t eval_kind, const double *uniforms, uint8_t *finished, bool move,
+                             void *stream) {
     if (num_sims < 0) return fail(h, AZ_E_INVALID, "%s", "az_run_simulations: num_sims < 0");
     if (h->sims_done + num_sims > h->cfg.num_simulations)
         return fail(h, AZ_E_INVALID, "%s", "az_run_simulations: more simulations on these roots than the arena holds (1 + 7*num_simulations nodes per tree)");
@@ -1460,15 +1610,27 @@ int32_t az_run_simulations(az_engine *h, int32_t num_sims, int32_t eval_kind, vo
     if (h->force_hot_nodes >= 0) K = (h->force_hot_nodes < h->a.cap ? h->force_hot_nodes : h->a.cap) & ~7;
     const size_t smem = (size_t)trees_per_block * ((size_t)K * 24 + PATH_STRIDE * 4);
     const bool lat = latency_variant(h, blocks);
-#define AZ_RUN1(TPW_, EV_, LAT_)                                                                                               \
-    do {                                                                                                                       \
-        AZ_CUDA(h, cudaFuncSetAttribute(k_run_sims<TPW_, EV_, LAT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_run_sims<TPW_, EV_, LAT_><<<blocks, 64, smem, S(stream)>>>(h->a, n, num_sims, c, K);                                 \
+    MoveArgs mv;
+    mv.uniforms = uniforms;
+    mv.finished = finished;
+    mv.init0 = h->init0;
+    mv.init1 = h->init1;
+    mv.step = h->step;
+    mv.initpl = h->initpl;
+#define AZ_RUN2(TPW_, EV_, LAT_, MOVE_)                                                                                               \
+    do {                                                                                                                              \
+        AZ_CUDA(h, cudaFuncSetAttribute(k_run_sims<TPW_, EV_, LAT_, MOVE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_run_sims<TPW_, EV_, LAT_, MOVE_><<<blocks, 64, smem, S(stream)>>>(h->a, n, num_sims, c, K, mv);                             \
     } while (0)
-#define AZ_RUN(TPW_, EV_)                 \
-    do {                                  \
+#define AZ_RUN1(TPW_, EV_, LAT_)                  \
+    do {                                          \
+        if (move) AZ_RUN2(TPW_, EV_, LAT_, true); \
+        else AZ_RUN2(TPW_, EV_, LAT_, false);     \
+    } while (0)
+#define AZ_RUN(TPW_, EV_)                  \
+    do {                                   \
         if (lat) AZ_RUN1(TPW_, EV_, true); \
-        else AZ_RUN1(TPW_, EV_, false);   \
+        else AZ_RUN1(TPW_, EV_, false);    \
     } while (0)
     if (tpw == 1) {
         if (eval_kind == AZ_EVAL_UNIFORM) AZ_RUN(1, AZ_EVAL_UNIFORM); else AZ_RUN(1, AZ_EVAL_HASH);
@@ -1479,6 +1641,7 @@ int32_t az_run_simulations(az_engine *h, int32_t num_sims, int32_t eval_kind, vo
     }
 #undef AZ_RUN
 #undef AZ_RUN1
+#undef AZ_RUN2
     h->last_hot_nodes = K;
     h->sims_done += num_sims;
     AZ_LAUNCH_CHECK(h, "k_run_sims");

@@ -232,6 +232,12 @@ class Engine:
         assert uniforms.dtype == torch.float64 and uniforms.numel() >= self.n_active
         self._check(self.lib.az_sample_moves(self.h, _ptr(uniforms), _ptr(finished), _stream()), "az_sample_moves")
 
+    def run_move_step(self, num_sims: int, evaluator: int, uniforms: torch.Tensor, finished: torch.Tensor | None = None):
+        """`run_simulations` + `sample_moves` in one launch (built-in evaluators): one self-play move step."""
+        assert uniforms.dtype == torch.float64 and uniforms.numel() >= self.n_active
+        self._check(self.lib.az_run_move_step(self.h, int(num_sims), int(evaluator), _ptr(uniforms), _ptr(finished), _stream()),
+                    "az_run_move_step")
+
     def episode_counts(self) -> tuple[int, int]:
         ne, ns = C.c_int64(0), C.c_int64(0)
         self._check(self.lib.az_episode_counts(self.h, C.byref(ne), C.byref(ns), _stream()), "az_episode_counts")

@@ -60,13 +60,14 @@ class EpisodeGenerator:
         step = 0
         self.h2d_bytes = self.d2h_bytes = 0
         while max_steps is None or step < max_steps:
-            self.search.simulate(eng)
+            # the step's uniforms are drawn before its search is enqueued (the search consumes no NumPy randomness, so the
+            # global stream sees the same draws in the same order as the reference's search-then-sample loop)
             rng_state = np.random.get_state() if self.uniform_source is None else None
             u = np.random.random_sample(E) if self.uniform_source is None else np.asarray(self.uniform_source(step, E), np.float64)
             uh, ud = u_host[step & 1], u_dev[step & 1]
             uh.numpy()[:] = u
             ud.copy_(uh, non_blocking=True)
-            eng.sample_moves(ud)  # finished games of this step go to the active ring
+            self.search.simulate_and_move(eng, ud)  # finished games of this step go to the active ring
             ev = torch.cuda.Event()
             ev.record(compute)
             self.h2d_bytes += E * 8

@@ -187,6 +187,15 @@ class AlphaZeroSearch:
         else:
             self._simulate_predict(engine, S)
 
+    def simulate_and_move(self, engine: Engine, uniforms: torch.Tensor, finished: torch.Tensor | None = None):
+        """One self-play move step: `simulate` then `Engine.sample_moves(uniforms)`.  With a built-in evaluator both run in
+        one launch (`az_run_move_step`), with identical results."""
+        if self._mode == "builtin":
+            engine.run_move_step(self.num_simulations, self.inference_model.az_builtin_eval_kind, uniforms, finished)
+        else:
+            self.simulate(engine)
+            engine.sample_moves(uniforms, finished)
+
     def _simulate_predict(self, engine: Engine, S: int):
         """Generic evaluator: any object with the reference's `predict(states)`."""
         n = engine.n_active

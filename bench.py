@@ -6,8 +6,8 @@
 
 Workload (N=1): BASELINE.json configs[1] — 4096 concurrent games x 200 simulations/move with the
 deterministic uniform-prior evaluator (the bit-exact parity configuration).  One STEP = one move step of
-the self-play loop for every game: `az_run_simulations` (200 simulations per tree, one launch) followed by
-`az_sample_moves` (record samples, draw moves, recycle finished games).  With N > 1 every rank runs its own
+the self-play loop for every game: `az_run_move_step` = 200 simulations per tree (`az_run_simulations`) and the move
+(`az_sample_moves`: record samples, draw moves, recycle finished games) in ONE launch of `k_run_sims`.  With N > 1 every rank runs its own
 4096 games (weak scaling, no collective on the data path); finished episodes are all-gathered over NCCL
 after the timed region and that time is reported separately.
 
@@ -324,11 +324,10 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     for i in range(W):
-        eng.run_simulations(S, kind)
-        eng.sample_moves(u_all[i])
+        eng.run_move_step(S, kind, u_all[i])
         if eng.episode_counts()[0]:
             eng.drain_episodes_device()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     barrier()
     st0, l0 = eng.stats(), eng.launch_count
     sampler = ClockSampler(local)
@@ -336,10 +335,8 @@ def run_b200(args):
     for i in range(K):
         flush.zero_()  # L2 flush between timed iterations (outside the step's event pair)
         ev[i][0].record()
-        eng.run_simulations(S, kind)
+        eng.run_move_step(S, kind, u_all[W + i])  # az_run_move_step: 200 simulations per tree + the move, one launch
         ev[i][1].record()
-        eng.sample_moves(u_all[W + i])
-        ev[i][2].record()
         if (i + 1) % 16 == 0:  # keep the device ring from filling; not part of the device-resident step
             eng.drain_episodes_device()
     barrier()
@@ -347,8 +344,8 @@ def run_b200(args):
     clocks = sampler.stop()
     launches = eng.launch_count - l0 - K // 16 * 0
     st = diff(st0, eng.stats())
-    sim_ms = [a.elapsed_time(b) for a, b, _ in ev]
-    step_ms = [a.elapsed_time(c) for a, _, c in ev]
+    sim_ms = [a.elapsed_time(b) for a, b in ev]
+    step_ms = sim_ms
     total_ms = float(sum(step_ms))
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=eng.device)
@@ -419,7 +416,7 @@ def run_b200(args):
 
         all_gather_episodes(eng.drain_episodes_device())  # first call: NCCL channel set-up
         for _ in range(6):
-            eng.run_simulations(S, kind); eng.sample_moves(u_all[0])
+            eng.run_move_step(S, kind, u_all[0])
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         drained = eng.drain_episodes_device()

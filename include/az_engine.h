@@ -176,6 +176,11 @@ int32_t az_export_tree(az_engine *h, int32_t slot, double *W, uint32_t *N, float
  * recycle the slot to the initial state.  finished[slot] (may be NULL) = 1 where an episode finished.
  * Increments the move-step counter. */
 int32_t az_sample_moves(az_engine *h, const double *uniforms /*[E]*/, uint8_t *finished, void *stream);
+/* One whole move step of the self-play loop (episode_generator.py:53-78) with a built-in deterministic evaluator in ONE
+ * launch: az_run_simulations(num_sims, evaluator_kind) followed by az_sample_moves(uniforms, finished), same results.
+ * The root's child statistics never leave the registers and the discarded tree is not written back. */
+int32_t az_run_move_step(az_engine *h, int32_t num_sims, int32_t evaluator_kind, const double *uniforms /*[E]*/, uint8_t *finished,
+                         void *stream);
 /* number of finished episodes / samples waiting in the ring.  Synchronises on `stream`. */
 int32_t az_episode_counts(az_engine *h, int64_t *n_episodes_host, int64_t *n_samples_host, void *stream);
 /* copy the ring out (device buffers sized from az_episode_counts) and empty it.  Episodes appear in

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 from conftest import golden_uniforms  # noqa: E402
 
 
-def _run_engine(E, S, kind, uniforms_2d, init=(0, 0, 0), lanes=0, quota=None):
+def _run_engine(E, S, kind, uniforms_2d, init=(0, 0, 0), lanes=0, quota=None, fused=False):
     from alphazero_implementation_b200.engine import Engine, sort_episode_batch
 
     quota = E if quota is None else quota
@@ -17,8 +17,11 @@ def _run_engine(E, S, kind, uniforms_2d, init=(0, 0, 0), lanes=0, quota=None):
     eng.reset_games(*init)
     parts, count = [], 0
     for step in range(uniforms_2d.shape[0]):
-        eng.run_simulations(S, kind)
-        eng.sample_moves(torch.from_numpy(uniforms_2d[step]).cuda())
+        if fused:  # az_run_move_step: the same move step in one launch
+            eng.run_move_step(S, kind, torch.from_numpy(uniforms_2d[step]).cuda())
+        else:
+            eng.run_simulations(S, kind)
+            eng.sample_moves(torch.from_numpy(uniforms_2d[step]).cuda())
         ne, _ = eng.episode_counts()
         if ne:
             parts.append(eng.drain_episodes())
@@ -41,14 +44,16 @@ def _flatten(parts, quota):
     return eps[:quota]
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("lanes", [8, 32])
-def test_selfplay_goldens(selfplay_goldens, lanes):
+def test_selfplay_goldens(selfplay_goldens, lanes, fused):
     for run in selfplay_goldens:
         E, S = run["E"], run["S"]
         u = golden_uniforms(run)
         steps = (run["n_draws"] + E - 1) // E + 1
         u2 = u[: steps * E].reshape(steps, E)
-        parts, stats, _ = _run_engine(E, S, run["eval_kind"], u2, init=(run["init_bb0"], run["init_bb1"], run["init_player"]), lanes=lanes)
+        parts, stats, _ = _run_engine(E, S, run["eval_kind"], u2, init=(run["init_bb0"], run["init_bb1"], run["init_player"]), lanes=lanes,
+                                     fused=fused)
         got = _flatten(parts, E)
         assert len(got) == len(run["episodes"]) == E
         for g, ep in zip(got, run["episodes"]):
@@ -62,14 +67,15 @@ def test_selfplay_goldens(selfplay_goldens, lanes):
         assert last["step"] * E + last["slot"] + 1 == run["n_draws"]
 
 
-@pytest.mark.parametrize("E,S,kind,lanes", [(4096, 200, 1, 8), (4096, 200, 2, 32), (1024, 64, 2, 8)])
-def test_selfplay_vs_oracle_config2(oracle, E, S, kind, lanes):
+@pytest.mark.parametrize("E,S,kind,lanes,fused", [(4096, 200, 1, 8, False), (4096, 200, 1, 8, True), (4096, 200, 2, 32, False), (1024, 64, 2, 8, True),
+                                                  (4096, 200, 2, 16, True), (333, 37, 1, 32, True)])
+def test_selfplay_vs_oracle_config2(oracle, E, S, kind, lanes, fused):
     """BASELINE config 2 (4096 games x 200 sims): a whole self-play round until E episodes, all per-move visit
     counts, positions, outcomes and the episode order bit-exact against the C oracle."""
     rng = np.random.RandomState(E + S)
     u2 = rng.random_sample((60, E))
     ref = oracle.selfplay(E, S, u2, eval_kind=kind)
-    parts, stats, steps = _run_engine(E, S, kind, u2, lanes=lanes)
+    parts, stats, steps = _run_engine(E, S, kind, u2, lanes=lanes, fused=fused)
     got = _flatten(parts, E)
     assert len(got) == E == len(ref.ep_slot) and steps == ref.n_steps
     assert [g["slot"] for g in got] == ref.ep_slot.tolist() and [g["step"] for g in got] == ref.ep_step.tolist()
@@ -82,3 +88,34 @@ def test_selfplay_vs_oracle_config2(oracle, E, S, kind, lanes):
     assert stats["simulations"] == ref.n_sims and stats["evaluations"] == ref.n_evals
     outcomes = np.array([g["outcome"][0] for g in got])
     assert (outcomes == 1).sum() > 0 and (outcomes == -1).sum() > 0
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+def test_fused_move_step_equals_two_calls(kind):
+    """az_run_move_step == az_run_simulations + az_sample_moves: finished flags, next roots, move counters, ring."""
+    import alphazero_implementation_b200 as az
+
+    E, S = 777, 48
+    u = torch.from_numpy(np.random.RandomState(3).random_sample((30, E))).cuda()
+    engs = [az.Engine(num_games=E, num_simulations=S + 1) for _ in range(2)]  # + 1: the root probe below is a simulation
+    fin = [torch.full((E,), 7, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    for e in engs:
+        e.reset_games()
+    for step in range(30):
+        engs[0].run_simulations(S, kind)
+        engs[0].sample_moves(u[step], fin[0])
+        engs[1].run_move_step(S, kind, u[step], fin[1])
+        assert torch.equal(fin[0], fin[1])
+        # the next move's search starts from the same roots: the first selection of a fresh tree returns the root itself
+        for e in engs:
+            e.select_leaves()
+        a, b = engs[0].leaf_info(), engs[1].leaf_info()
+        for k in a:
+            assert torch.equal(a[k], b[k]), (step, k)
+    sa, sb = engs[0].stats(), engs[1].stats()
+    assert sa["moves"] == sb["moves"] and sa["episodes"] == sb["episodes"] and sa["episodes"] > 0
+    da, db = engs[0].drain_episodes(), engs[1].drain_episodes()
+    for f in ("ep_slot", "ep_step", "ep_len", "ep_outcome", "s_bb0", "s_bb1", "s_player", "s_counts"):
+        assert (getattr(da, f) == getattr(db, f)).all(), f
+    for e in engs:
+        e.close()
