@@ -19,7 +19,7 @@
 //    then group B's 72.  The eight epilogue warps (two per 32 accumulator lanes, half the channels each) trail it:
 //    tcgen05.ld, bias (+ skip) + ReLU in fp32, round to bf16, write the next layer's A operand - while they work on
 //    A's accumulators the tensor core works on B, and vice versa.  Hand-offs are mbarriers: tcgen05.commit ->
-//    mma_done[g]; 256 arrivals -> epi_done[g].
+//    mma_done[g]; one arrival per epilogue warp -> epi_done[g].
 //  * Warp 9 only streams weights ([64 out][64 in] bf16 per tap, 8 KB, packed once per weight update) with bulk async
 //    copies.  The ring has 9 stages = the 9 taps of a layer (stage = tap, parity = layer): a tap is loaded once per
 //    layer, used by A and then by B, whose commit releases the stage for the next layer's tap.  The issuer never
@@ -29,7 +29,9 @@
 //    weights sit in the centre tap); the two small FC layers run on CUDA cores in fp32, each weight read once per CTA.
 // Measured (16384 positions, 4 blocks): 0.70 ms; a group's 72 MMAs take ~3750 cycles = 52 cycles per 128x64x16 MMA
 // against the 32-cycle floor: each fetches 6 KB of operands from shared memory (~115 B/clk), i.e. with 64 output
-// channels the conv MMAs are shared-memory-operand-bound.  History: a serial version (one 5-tile group of 8 x 9 padded
+// channels the conv MMAs are shared-memory-operand-bound.  A CTA-pair variant (template PAIR: cta_group::2 MMAs with M = 256, each
+// CTA staging half of every tap so that B is fetched once per SM pair) is built in and bit-identical, but measured 8 % slower
+// (az_trunk_set_cta_pair).  History: a serial version (one 5-tile group of 8 x 9 padded
 // positions, the issuing warp also refilling the ring) took 1.33 ms - every tap waited for its own stage to drain.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -93,6 +95,52 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+// ---- CTA-pair (cta_group::2) variants: one MMA spans the two SMs of a cluster, 128 rows of A and half of B from each
+__device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all MMAs issued so far -> the mbarrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a barrier that threads / the tensor core of the OTHER CTA arrive on
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAITC_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAITC_DONE;\n\t"
+        "bra WAITC_LOOP;\n\t"
+        "WAITC_DONE:\n\t"
+        "}" ::"r"(bar), "r"(phase)
+        : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -134,7 +182,7 @@ constexpr int NS = 9;
 constexpr uint32_t OFF_RING = 2 * BUF_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_RING + NS * TAP_BYTES;
 constexpr uint32_t OFF_BARS = OFF_BIAS + MAX_LAYERS * C * 4;
-constexpr uint32_t SMEM_BYTES = OFF_BARS + (2 * NS + 4) * 8 + 16;
+constexpr uint32_t SMEM_BYTES = OFF_BARS + (3 * NS + 4) * 8 + 16;  // full[9] empty[9] mma_done[2] epi_done[2] pfull[9], TMEM slot
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(LEAD + GPOS * PIX <= GROWS, "a group must fit its accumulator tiles");
 
@@ -187,31 +235,50 @@ __device__ __forceinline__ void conv_epilogue(uint32_t tmem_base, uint8_t *dst, 
 // lane issues.  Group A waits for each tap's weights; group B finds them there and releases the stage afterwards.
 // Before its last tap the warp already waits for what the NEXT (layer, group) needs (`pre_bar`: that group's epi_done;
 // `pre_full`: tap 0 of the next layer), while the queued MMAs keep the tensor core busy - the hand-over costs no bubble.
-template <int KSTEPS, bool GROUP_B>
-__device__ __forceinline__ void issue_group(uint32_t full0, uint32_t empty0, uint32_t parity, bool wait_tap0, uint64_t a_desc, uint64_t b_desc,
-                                            uint32_t idesc, uint32_t tmem_tile0, uint32_t pre_bar, uint32_t pre_parity, bool pre_full) {
+// PAIR: the MMAs are cta_group::2 (M = 256: this CTA's tile and the peer's), a tap's weights are complete when this CTA's
+// half (full) and the peer's half (pfull, forwarded by the peer) have landed, and commits arrive in both CTAs.
+template <int KSTEPS, bool GROUP_B, bool PAIR>
+__device__ __forceinline__ void issue_group(uint32_t full0, uint32_t pfull0, uint32_t empty0, uint32_t parity, bool wait_tap0, uint64_t a_desc,
+                                            uint64_t b_desc, uint32_t idesc, uint32_t tmem_tile0, uint32_t pre_bar, uint32_t pre_parity,
+                                            bool pre_full) {
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
         const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);  // rows; one row = 16 B = one descriptor address unit
-        if (!GROUP_B && (tap > 0 || wait_tap0)) mbar_wait(full0 + tap * 8, parity);
+        if (!GROUP_B && (tap > 0 || wait_tap0)) {
+            mbar_wait(full0 + tap * 8, parity);
+            if (PAIR) mbar_wait_cluster(pfull0 + tap * 8, parity);
+        }
         if (tap == 8) {
-            if (pre_bar) mbar_wait(pre_bar, pre_parity);
-            if (pre_full) mbar_wait(full0, parity ^ 1u);
+            if (pre_bar) {
+                if (PAIR) mbar_wait_cluster(pre_bar, pre_parity);
+                else mbar_wait(pre_bar, pre_parity);
+            }
+            if (pre_full) {
+                mbar_wait(full0, parity ^ 1u);
+                if (PAIR) mbar_wait_cluster(pfull0, parity ^ 1u);
+            }
         }
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < GTILES; ++t)
 #pragma unroll
-                for (int ks = 0; ks < KSTEPS; ++ks)
-                    umma(tmem_tile0 + t * C, a_desc + (uint64_t)(int64_t)(shift + t * 128 + ks * (int)(2 * LBO_A >> 4)),
-                         b_desc + (uint64_t)(tap * (int)(TAP_BYTES >> 4) + ks * (int)(2 * LBO_W >> 4)), idesc, (tap | ks) > 0);
-            if (GROUP_B) umma_commit(empty0 + tap * 8);
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                    const uint64_t ad = a_desc + (uint64_t)(int64_t)(shift + t * 128 + ks * (int)(2 * LBO_A >> 4));
+                    const uint64_t bd = b_desc + (uint64_t)(tap * (int)(TAP_BYTES >> 4) + ks * (int)(2 * LBO_W >> 4));
+                    if (PAIR) umma2(tmem_tile0 + t * C, ad, bd, idesc, (tap | ks) > 0);
+                    else umma(tmem_tile0 + t * C, ad, bd, idesc, (tap | ks) > 0);
+                }
+            if (GROUP_B) {
+                if (PAIR) umma_commit2(empty0 + tap * 8);
+                else umma_commit(empty0 + tap * 8);
+            }
         }
         __syncwarp();
     }
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1, const uint8_t *__restrict__ leaf_player,
                    const uint8_t *__restrict__ leaf_status, long long n, const uint8_t *__restrict__ weights,
@@ -230,15 +297,24 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
     const int n_conv = 1 + 2 * num_blocks;            // stem + block convs
     const int n_layers = n_conv + (head_w ? 1 : 0);   // + head conv
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS), ring0 = smem_u32(smem + OFF_RING);
-    const uint32_t mma_done0 = smem_u32(bars + 2 * NS), epi_done0 = smem_u32(bars + 2 * NS + 2);
+    const uint32_t mma_done0 = smem_u32(bars + 2 * NS), epi_done0 = smem_u32(bars + 2 * NS + 2), pfull0 = smem_u32(bars + 2 * NS + 4);
+    // PAIR: two CTAs (one cluster, the two SMs of a TPC) run every MMA together; rank 0 issues them
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
     }
     if (tid == 32) {
-        for (int i = 0; i < 2 * NS + 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"(epi_done0));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"(epi_done0 + 8));
+        for (int i = 0; i < 3 * NS + 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
+        // epi_done[g]: one arrival per epilogue warp of the CTA - and, in a pair, of the peer - on the LEADER's barrier
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(epi_done0), "r"(PAIR ? 16u : 8u));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(epi_done0 + 8), "r"(PAIR ? 16u : 8u));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t i = tid; i < 2 * BUF_BYTES / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -263,31 +339,46 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // the peer's barriers are initialised and its stem input is written before anything remote happens
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a0 = smem_u32(buf[0]) + GUARD * ROWB, a1 = smem_u32(buf[1]) + GUARD * ROWB;
+    const uint32_t epi_done_lead = PAIR ? mapa(epi_done0, 0u) : epi_done0;  // shared::cluster address in a pair
 
     if (warp == 9) {
         // ===== weight producer: tap `tap` of layer l into stage `tap`, once group B of layer l-1 has released it =====
         for (int l = 0; l < n_layers; ++l) {
             const uint8_t *w = l == 0 ? weights : (l < n_conv ? weights + 9 * STEM_TAP_BYTES + (size_t)(l - 1) * 9 * TAP_BYTES : head_w);
-            const uint32_t bytes = l == 0 ? STEM_TAP_BYTES : (l < n_conv ? TAP_BYTES : HEAD_TAP_BYTES);
+            const uint32_t tap_bytes = l == 0 ? STEM_TAP_BYTES : (l < n_conv ? TAP_BYTES : HEAD_TAP_BYTES);
+            // a pair splits B by output channel: this CTA stages rows [rank * N/2, (rank + 1) * N/2) of every tap - the first /
+            // second half of the packed tap, whose 8-row groups are contiguous
+            const uint32_t bytes = PAIR ? tap_bytes / 2 : tap_bytes;
 #pragma unroll 1
             for (uint32_t tap = 0; tap < 9; ++tap) {
-                if (l > 0) mbar_wait(empty0 + tap * 8, (uint32_t)(l - 1) & 1u);
+                if (l > 0) mbar_wait_cluster(empty0 + tap * 8, (uint32_t)(l - 1) & 1u);
                 if (elect_one()) {
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + tap * 8), "r"(bytes) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                                      ring0 + tap * TAP_BYTES),
-                                 "l"(w + (size_t)tap * bytes), "r"(bytes), "r"(full0 + tap * 8)
+                                 "l"(w + (size_t)tap * tap_bytes + (size_t)rank * bytes), "r"(bytes), "r"(full0 + tap * 8)
                                  : "memory");
                 }
                 __syncwarp();
             }
         }
+    } else if (warp == 8 && !leader) {
+        // ===== peer CTA of a pair: tell the leader when this CTA's half of a tap has landed =====
+        const uint32_t pfull_lead = mapa(pfull0, 0u);
+        for (int l = 0; l < n_layers; ++l)
+#pragma unroll 1
+            for (uint32_t tap = 0; tap < 9; ++tap) {
+                mbar_wait(full0 + tap * 8, (uint32_t)l & 1u);
+                if (elect_one()) mbar_arrive_cluster(pfull_lead + tap * 8);
+                __syncwarp();
+            }
     } else if (warp == 8) {
         // ===== MMA issuer (converged; one elected lane issues) =====
-        const uint32_t idesc_c = instr_desc(128, C), idesc_h = instr_desc(128, NHC);
+        const uint32_t idesc_c = instr_desc(PAIR ? 256 : 128, C), idesc_h = instr_desc(PAIR ? 256 : 128, NHC);
         for (int l = 0; l < n_layers; ++l) {
             const bool is_head = l >= n_conv;
             const uint32_t src = l == 0 ? a1 : (is_head ? a0 : ((l & 1) ? a0 : a1));  // conv1 (odd l) reads x = buf[0]; conv2 reads t = buf[1]
@@ -304,13 +395,18 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
                 const uint32_t pre_parity = g == 0 ? (uint32_t)(l - 1) & 1u : (uint32_t)l & 1u;
                 CLK(0, l, g);
                 if (l == 0) {
-                    if (g == 0) issue_group<1, false>(full0, empty0, 0u, true, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, false);
-                    else issue_group<1, true>(full0, empty0, 0u, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, !last);
+                    if (g == 0) issue_group<1, false, PAIR>(full0, pfull0, empty0, 0u, true, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, false);
+                    else issue_group<1, true, PAIR>(full0, pfull0, empty0, 0u, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, !last);
                 } else {
-                    if (g == 0) issue_group<C / 16, false>(full0, empty0, (uint32_t)l & 1u, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, false);
-                    else issue_group<C / 16, true>(full0, empty0, (uint32_t)l & 1u, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, !last);
+                    if (g == 0)
+                        issue_group<C / 16, false, PAIR>(full0, pfull0, empty0, (uint32_t)l & 1u, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, false);
+                    else
+                        issue_group<C / 16, true, PAIR>(full0, pfull0, empty0, (uint32_t)l & 1u, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, !last);
                 }
-                if (elect_one()) umma_commit(mma_done0 + g * 8);
+                if (elect_one()) {
+                    if (PAIR) umma_commit2(mma_done0 + g * 8);
+                    else umma_commit(mma_done0 + g * 8);
+                }
                 __syncwarp();
                 CLK(1, l, g);
             }
@@ -323,13 +419,19 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
             const uint8_t *skip = (l > 0 && !(l & 1)) ? buf[0] : nullptr;
 #pragma unroll 1
             for (int g = 0; g < 2; ++g) {
-                mbar_wait(mma_done0 + g * 8, (uint32_t)l & 1u);
+                if (PAIR) mbar_wait_cluster(mma_done0 + g * 8, (uint32_t)l & 1u);
+                else mbar_wait(mma_done0 + g * 8, (uint32_t)l & 1u);
                 tc_fence_after();
                 if (warp == 0) CLK(2, l, g);
                 conv_epilogue(tmem_base, dst, skip, s_bias + l * C, g * GTILES, (g + 1) * GTILES);
-                fence_async_smem();
+                // every thread orders its own rows for the tensor core's reads, the warp syncs, one lane arrives for the warp
                 tc_fence_before();
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(epi_done0 + g * 8) : "memory");
+                fence_async_smem();
+                __syncwarp();
+                if ((tid & 31u) == 0) {
+                    if (PAIR && !leader) mbar_arrive_cluster(epi_done_lead + g * 8);
+                    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(epi_done0 + g * 8) : "memory");
+                }
                 if (warp == 0) CLK(3, l, g);
             }
         }
@@ -351,7 +453,8 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
             const float *hb = s_bias + n_conv * C;
 #pragma unroll 1
             for (int g = 0; g < 2; ++g) {
-                mbar_wait(mma_done0 + g * 8, (uint32_t)n_conv & 1u);
+                if (PAIR) mbar_wait_cluster(mma_done0 + g * 8, (uint32_t)n_conv & 1u);
+                else mbar_wait(mma_done0 + g * 8, (uint32_t)n_conv & 1u);
                 tc_fence_after();
                 if (warp == 0) CLK(2, n_conv, g);
                 // warps 0..3: policy channels 0..31; warps 4..7: value channels 32..34
@@ -440,8 +543,12 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the pair's MMAs may still touch it
     if (warp == 0) CLK(1, MAX_LAYERS - 1, 0);
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+    if (warp == 0) {
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+    }
 }
 
 
@@ -458,6 +565,17 @@ int32_t az_debug_trunk_clocks(long long *out) {
 /* bytes of packed weights the trunk kernel expects for `num_blocks` residual blocks */
 int64_t az_trunk_weight_bytes(int32_t num_blocks) { return 9ll * STEM_TAP_BYTES + (int64_t)num_blocks * 2 * 9 * TAP_BYTES; }
 
+// 0 (default): one CTA per 8 positions.  1: CTA pairs (cta_group::2 MMAs, M = 256, each CTA stages half of B) - bit-identical,
+// measured 8 % SLOWER on B200 for this shape (0.75 vs 0.70 ms at 16384 positions: the per-MMA time does not drop below the single-CTA
+// kernel's ~52 cycles and the cross-CTA hand-offs lengthen the epilogues), kept selectable for measurements and tests.
+static int g_trunk_cta_pair = 0;
+
+int32_t az_trunk_set_cta_pair(int32_t on) {
+    const int prev = g_trunk_cta_pair;
+    g_trunk_cta_pair = on ? 1 : 0;
+    return prev;
+}
+
 static int32_t launch_trunk(az_engine *engine, const void *weights, const float *biases, int32_t num_blocks, void *out,
                             const void *head_w, const float *head_b, const float *fcp_w, const float *fcp_b, const float *fcv_w,
                             const float *fcv_b, float *logits, float *values, void *stream) {
@@ -470,12 +588,35 @@ static int32_t launch_trunk(az_engine *engine, const void *weights, const float 
     const int dev = az_device(engine);
     if (dev < 0 || dev >= 64 || cudaSetDevice(dev) != cudaSuccess) return AZ_E_CUDA;
     if (!attr_set[dev]) {
-        if (cudaFuncSetAttribute(k_resnet_trunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
+        if (cudaFuncSetAttribute(k_resnet_trunk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
+        if (cudaFuncSetAttribute(k_resnet_trunk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
         attr_set[dev] = true;
     }
-    k_resnet_trunk<<<(n + P - 1) / P, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(bb0, bb1, player, status, n, (const uint8_t *)weights, biases,
-                                                                                  num_blocks, (__nv_bfloat16 *)out, (const uint8_t *)head_w, head_b,
-                                                                                  fcp_w, fcp_b, fcv_w, fcv_b, logits, values);
+    const int pair = g_trunk_cta_pair;
+    const long long nn = n;
+    const uint8_t *w8 = (const uint8_t *)weights, *hw8 = (const uint8_t *)head_w;
+    __nv_bfloat16 *o16 = (__nv_bfloat16 *)out;
+    if (pair) {
+        // clusters of two CTAs = the two SMs of a TPC; an odd tail CTA gets an empty partner
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(((n + P - 1) / P + 1) / 2 * 2));
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, k_resnet_trunk<true>, bb0, bb1, player, status, nn, w8, biases, (int)num_blocks, o16, hw8, head_b, fcp_w, fcp_b,
+                               fcv_w, fcv_b, logits, values) != cudaSuccess)
+            return AZ_E_CUDA;
+    } else {
+        k_resnet_trunk<false><<<(n + P - 1) / P, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(bb0, bb1, player, status, nn, w8, biases, num_blocks, o16,
+                                                                                             hw8, head_b, fcp_w, fcp_b, fcv_w, fcv_b, logits, values);
+    }
     return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;
 }
 

@@ -247,6 +247,9 @@ int32_t az_resnet_forward_leaves(az_engine *engine, const void *packed_weights, 
                                  const void *head_conv_w, const float *head_conv_b, const float *fc_policy_w,
                                  const float *fc_policy_b, const float *fc_value_w, const float *fc_value_b, float *logits,
                                  float *values, void *stream);
+/* Tuning switch of the kernel behind the two calls above: 0 (default) = one CTA per 8 positions, 1 = CTA pairs
+ * (tcgen05 cta_group::2, M = 256).  Same results; returns the previous setting. */
+int32_t az_trunk_set_cta_pair(int32_t on);
 
 #ifdef __cplusplus
 }

@@ -124,3 +124,32 @@ def test_full_net_kernel_matches_pytorch_reference(blocks, n):
     assert float((torch.softmax(logits[live], 1) - torch.softmax(l_fp32[live], 1)).abs().max()) < 5e-2
     assert float((values[live] - v_fp32[live]).abs().max()) < 8e-2
     eng.close()
+
+
+@pytest.mark.parametrize("blocks,n", [(1, 5), (3, 1001)])
+def test_cta_pair_variant_is_bit_identical(blocks, n):
+    """The cta_group::2 variant of the kernel (two CTAs per MMA, M = 256) must give exactly the single-CTA results,
+    including an odd tail (the last pair has an empty partner)."""
+    from alphazero_implementation_b200 import _lib
+    from alphazero_implementation_b200.models import InferenceNet
+
+    lib = _lib.load()
+    torch.manual_seed(7 + n)
+    model = az.ResNet(num_res_blocks=blocks, num_channels=64).cuda().eval()
+    _randomise_bn(model)
+    eng = _engine_with_leaves(n, seed=n)
+    net = InferenceNet(model, dtype=torch.bfloat16)
+    assert net.evaluates_leaves_directly
+    outs = []
+    try:
+        for pair in (0, 1):
+            lib.az_trunk_set_cta_pair(pair)
+            trunk_out = net.trunk.forward_leaves(eng).clone()
+            logits, values = net.forward_leaves(eng)
+            outs.append((trunk_out, logits.clone(), values.clone()))
+        torch.cuda.synchronize()
+    finally:
+        lib.az_trunk_set_cta_pair(0)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    eng.close()
