@@ -32,10 +32,11 @@ _LAYOUT_SHAPE = {
 }
 
 
-def _ptr(t: torch.Tensor | None) -> int | None:
+def _ptr(t: torch.Tensor | None, allow_pinned: bool = False) -> int | None:
     if t is None:
         return None
-    assert t.is_cuda and t.is_contiguous(), "engine buffers must be contiguous CUDA tensors"
+    ok = t.is_cuda or (allow_pinned and t.is_pinned())  # page-locked host memory is device-addressable (UVA): zero-copy
+    assert ok and t.is_contiguous(), "engine buffers must be contiguous CUDA tensors" + (" or pinned host tensors" if allow_pinned else "")
     return t.data_ptr()
 
 
@@ -187,16 +188,19 @@ class Engine:
         self._check(self.lib.az_select_leaves(self.h, _stream()), "az_select_leaves")
 
     def gather_leaves(self, layout: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Pack the leaves' planes into `out`: a device batch, or a PINNED host batch the kernel writes straight into (for an
+        evaluator that lives on the host; synchronise the stream before reading it)."""
         shape, dtype = _LAYOUT_SHAPE[layout]
         if out is None:
             out = self.empty((self.n_active, *shape), dtype)
-        self._check(self.lib.az_gather_leaves(self.h, _ptr(out), layout, _stream()), "az_gather_leaves")
+        self._check(self.lib.az_gather_leaves(self.h, _ptr(out, allow_pinned=True), layout, _stream()), "az_gather_leaves")
         return out
 
     def expand_backup(self, policy: torch.Tensor, values: torch.Tensor, policy_kind: int = POLICY_LOGITS):
         assert policy.dtype == torch.float32 and values.dtype == torch.float32
         assert policy.shape[0] >= self.n_active and policy.shape[-1] == 7 and values.shape[-1] == 2
-        self._check(self.lib.az_expand_backup(self.h, _ptr(policy), _ptr(values), policy_kind, _stream()), "az_expand_backup")
+        self._check(self.lib.az_expand_backup(self.h, _ptr(policy, allow_pinned=True), _ptr(values, allow_pinned=True), policy_kind, _stream()),
+                    "az_expand_backup")
 
     def leaf_info(self):
         n = self.n_active

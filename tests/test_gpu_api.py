@@ -237,3 +237,50 @@ def test_replay_buffer_targets_match_reference_format(selfplay_goldens):
     assert bb0.cpu().tolist() == [s["bb0"] for ep in ref_eps for s in ep["samples"]]
     x, p, v = next(rb.batches(az.BasicNN.input_layout, batch_size=8, shuffle=False))
     assert x.shape == (8, 6, 7) and p.shape == (8, 7) and v.shape == (8, 2)
+
+
+def test_leaf_gather_into_pinned_host_batch_and_host_evaluator():
+    """north_star (3): the leaf gather packs the board planes into a PINNED batch; a host-side evaluator reads it and its
+    outputs go back through pinned buffers.  The search must equal the all-device path."""
+    from alphazero_implementation_b200.engine import LAYOUT_GRID_F32, LAYOUT_PLANES_F32, POLICY_LOGITS
+
+    E, S = 300, 24
+    torch.manual_seed(5)
+    net = az.BasicNN().eval()
+    engs = [az.Engine(num_games=E, num_simulations=S) for _ in range(2)]
+    for e in engs:
+        e.reset_games()
+    pinned_x = torch.empty((E, 6, 7), dtype=torch.float32).pin_memory()
+    pinned_l = torch.empty((E, 7), dtype=torch.float32).pin_memory()
+    pinned_v = torch.empty((E, 2), dtype=torch.float32).pin_memory()
+    dev_net = az.BasicNN().cuda().eval()
+    dev_net.load_state_dict(net.state_dict())
+    for s in range(S):
+        # device path
+        engs[0].select_leaves()
+        x = engs[0].gather_leaves(LAYOUT_GRID_F32)
+        with torch.no_grad():
+            l, v = dev_net(x)
+        # pinned path: kernel writes the host batch, the host net reads it, the expand kernel reads host outputs
+        engs[1].select_leaves()
+        engs[1].gather_leaves(LAYOUT_GRID_F32, pinned_x)
+        torch.cuda.synchronize()
+        assert torch.equal(pinned_x, x.cpu())
+        # feed both engines the SAME numbers so that the trees stay comparable bit for bit
+        pinned_l.copy_(l.float().cpu())
+        pinned_v.copy_(v.float().cpu())
+        engs[0].expand_backup(l.float().contiguous(), v.float().contiguous(), POLICY_LOGITS)
+        engs[1].expand_backup(pinned_l, pinned_v, POLICY_LOGITS)
+        torch.cuda.synchronize()
+    a, b = engs[0].root_stats(), engs[1].root_stats()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    # the 3-plane layout lands in a pinned batch as well
+    engs[1].set_roots(*[t.clone() for t in (engs[1].leaf_info()[k] for k in ("bb0", "bb1", "player"))])
+    engs[1].select_leaves()
+    px = torch.empty((E, 3, 6, 7), dtype=torch.float32).pin_memory()
+    engs[1].gather_leaves(LAYOUT_PLANES_F32, px)
+    torch.cuda.synchronize()
+    assert torch.equal(px, engs[1].gather_leaves(LAYOUT_PLANES_F32).cpu())
+    for e in engs:
+        e.close()
