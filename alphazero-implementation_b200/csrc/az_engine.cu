@@ -508,6 +508,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
         }
     } else {
         // ---- the move step of this tree's game (episode_generator.py:53-78, node.py:23-42), same arithmetic as k_sample_moves
+        RCLK(m0);
         const bool mover = alive && root_cb != 0;
         const int32_t cnt = (mover && r_can) ? (int32_t)rch.n : 0;
         const double p = __ddiv_rn((double)cnt, (double)((int)root_n - 1));  // improved_policy (node.py:27)
@@ -544,6 +545,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
             }
         }
         __syncwarp();
+        RCLK(m1);
         long long dst = -1;
         if (mover && lit == 0) {
             moves = 1;
@@ -579,6 +581,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
             used = 1u;
         }
         // the finished game's samples -> ring, one lane per sample
+        RCLK(m2);
         dst = __shfl_sync(FULL, dst, lane - lit);
         if (dst >= 0) {
             const size_t g0 = (size_t)t * MAX_PLIES;
@@ -590,6 +593,14 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
                 for (int i = 0; i < 7; ++i) a.s_counts[(dst + qq) * 7 + i] = a.g_counts[(g0 + qq) * 7 + i];
             }
         }
+#ifdef AZ_TRUNK_CLOCKS
+        {
+            const long long m3 = clock64();
+            if (blockIdx.x == 100 && threadIdx.x == 0) {
+                g_run_clk[4] = m1 - m0; g_run_clk[5] = m2 - m1; g_run_clk[6] = m3 - m2;
+            }
+        }
+#endif
     }
     if (writer) {
         a.used[t] = used;
