@@ -628,12 +628,7 @@ __global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_p
     const int q = lane / (32 / TPW);
     const int t = blockIdx.x * TREES + warp * TPW + q;
     const bool in_range = t < n_active;
-    const bool alive = in_range && (a.tree_err[in_range ? t : 0] == 0);
-    const int lit = lane & (NL - 1);
-    if (in_range && !alive && lit == 0) a.leaf_status[t] = AZ_LEAF_IDLE;
-    if (!__any_sync(FULL, alive)) return;
-    const int tt = alive ? t : 0;
-    const bool writer = alive && lit == 0;
+    const int tt = in_range ? t : 0;
     const size_t base = (size_t)tt * a.cap;
     TreeMem tm;
     tm.gW = a.W + base;
@@ -641,9 +636,17 @@ __global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_p
     tm.sW = nullptr;
     tm.sM = nullptr;
     tm.K = 0;
-    uint32_t *path = a.path + (size_t)tt * PATH_STRIDE;
+    // first round of loads, all independent: error flag, root position, root record
+    const int32_t err = a.tree_err[tt];
     const uint64_t rb0 = a.root_bb0[tt], rb1 = a.root_bb1[tt];
+    const int rpl = a.root_player[tt];
     const uint4 rm = tm.gM[0];
+    const bool alive = in_range && err == 0;
+    const int lit = lane & (NL - 1);
+    if (in_range && !alive && lit == 0) a.leaf_status[t] = AZ_LEAF_IDLE;
+    if (!__any_sync(FULL, alive)) return;
+    const bool writer = alive && lit == 0;
+    uint32_t *path = a.path + (size_t)tt * PATH_STRIDE;
     const bool r_can = (c < c4::W) && !(((rb0 | rb1) >> (c4::STRIDE * c + 5)) & 1ull);
     const unsigned r_legal = (__ballot_sync(FULL, r_can) >> sub) & 0x7Fu;
     Child rch;
@@ -651,7 +654,7 @@ __global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_p
     if (alive && rm.z != 0 && r_can) rch = load_child<LAT>(tm, rm.z + __popc(r_legal & ((1u << c) - 1u)), a.sqt);
     if (writer) path[0] = 0;
     uint32_t levels = 0, scanned = 0;
-    Leaf L = descend<LAT>(tm, a.rcp, a.sqt, rb0, rb1, a.root_player[tt], c_puct, rm.z, __ldg(a.sqt + rm.x), r_legal, rch, alive, writer, path, levels,
+    Leaf L = descend<LAT>(tm, a.rcp, a.sqt, rb0, rb1, rpl, c_puct, rm.z, __ldg(a.sqt + rm.x), r_legal, rch, alive, writer, path, levels,
                      scanned);
     if (writer) {
         a.leaf_node[t] = L.node;
@@ -682,10 +685,22 @@ k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const f
     const int c = lane & 7;
     const int q = lane / (32 / TPW);
     const int t = blockIdx.x * TREES + warp * TPW + q;
-    const bool alive = (t < n_active) && (a.leaf_status[t < n_active ? t : 0] == AZ_LEAF_EVAL);
-    if (!__any_sync(FULL, alive)) return;
-    const int tt = alive ? t : 0;
+    // Every load that does not depend on another is issued in the first round (the slot's leaf record, the evaluator's
+    // outputs, this lane's path entry): the kernel is a chain of dependent HBM / L2 round trips, nothing else.
+    const int tt = t < n_active ? t : 0;
     const int lit = lane & (NL - 1);
+    const uint8_t status = a.leaf_status[tt];
+    const uint64_t occ = a.leaf_bb0[tt] | a.leaf_bb1[tt];
+    const int pl = a.leaf_player[tt];
+    const uint32_t node = a.leaf_node[tt];
+    const int depth = a.leaf_depth[tt];
+    const uint32_t used = a.used[tt];
+    const uint32_t *path = a.path + (size_t)tt * PATH_STRIDE;
+    const uint32_t my_idx = path[lit < PATH_STRIDE ? lit : 0];
+    const float x_raw = policy[(size_t)tt * 7 + (c < 7 ? c : 0)];
+    const float v0 = values[(size_t)tt * 2], v1 = values[(size_t)tt * 2 + 1];
+    const bool alive = (t < n_active) && status == AZ_LEAF_EVAL;
+    if (!__any_sync(FULL, alive)) return;
     const bool writer = alive && lit == 0;
     const bool first_q = lit < 8;
     const size_t base = (size_t)tt * a.cap;
@@ -695,16 +710,20 @@ k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const f
     tm.sW = nullptr;
     tm.sM = nullptr;
     tm.K = 0;
-    const uint64_t occ = a.leaf_bb0[tt] | a.leaf_bb1[tt];
-    const int pl = a.leaf_player[tt];
-    const uint32_t node = a.leaf_node[tt];
-    const int depth = a.leaf_depth[tt];
-    const uint32_t used = a.used[tt];
+    // second round: W / N of this lane's path node (the leaf itself is visited for the first time: nothing to load)
+    const bool own = alive && lit <= depth;
+    const bool fresh = lit == depth;
+    double w_old = 0.0;
+    uint32_t n_old = 0u;
+    if (own && !fresh) {
+        w_old = tm.gW[my_idx];
+        n_old = reinterpret_cast<const uint32_t *>(tm.gM + my_idx)[0];
+    }
     const bool can = (c < c4::W) && !((occ >> (c4::STRIDE * c + 5)) & 1ull);
     const unsigned legal = (__ballot_sync(FULL, can) >> sub) & 0x7Fu;
     const int k = __popc(legal);
     const int j = __popc(legal & ((1u << c) - 1u));
-    const float x = (alive && can) ? policy[(size_t)tt * 7 + c] : -INFINITY;
+    const float x = (alive && can) ? x_raw : -INFINITY;
     float prior;
     if (policy_kind == AZ_POLICY_PRIORS) {
         prior = x;
@@ -722,7 +741,7 @@ k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const f
     __syncwarp();  // every lane has read used / leaf_* before the writer updates them
     if (alive) {
         if (can && first_q) store_new_child(tm, used + j, prior);
-        const double v = (double)values[(size_t)tt * 2 + pl];
+        const double v = (double)(pl ? v1 : v0);  // value[node.state.player] (search.py:91)
         if (writer) {
             set_first_child(tm, node, used);
             a.used[t] = used + k;
@@ -731,7 +750,11 @@ k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const f
             st[1] += 1u;
             st[3] += (uint32_t)k;
         }
-        backup(tm, a.path + (size_t)tt * PATH_STRIDE, depth, v, false, lit, NL);
+        if (own) {
+            tm.gW[my_idx] = __dadd_rn(w_old, backup_sign(v, depth, lit, false));
+            reinterpret_cast<uint32_t *>(tm.gM + my_idx)[0] = n_old + 1u;
+        }
+        for (int i = lit + NL; i <= depth; i += NL) visit_node(tm, path[i], backup_sign(v, depth, i, false));
     }
 }
 
