@@ -23,6 +23,7 @@
 // so 1/d and sqrt(n) come from tables of correctly rounded values (built once per engine with
 // __drcp_rn / __dsqrt_rn) and x/d is finished with two FMA residual corrections, which yields the
 // correctly rounded quotient (Markstein); tests/test_gpu_search.py checks it against __ddiv_rn.
+#include <assert.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -80,6 +81,9 @@ struct Arena {
 // x / d for an integer 1 <= d < tab_n, correctly rounded: r = RN(1/d) from the table, then two
 // residual corrections (q += (x - d*q) * r).  The first makes q faithful, the second exact-rounded.
 __device__ __forceinline__ double div_tab(double x, uint32_t d, const double *__restrict__ rcp) {
+#ifdef AZ_DEBUG_BOUNDS
+    assert(d < 1u << 20);  // tables hold num_simulations + 8 entries; a wild index shows up here first
+#endif
     const double r = __ldg(rcp + d);
     const double nd = -(double)d;
     double q = __dmul_rn(x, r);
@@ -158,12 +162,23 @@ struct TreeMem {
     double *sW;
     uint4 *sM;
     uint32_t K;
+#ifdef AZ_DEBUG_BOUNDS
+    uint32_t cap;  // debug build (-DAZ_DEBUG_BOUNDS): every node access is checked against the tree's capacity
+#endif
 };
+#ifdef AZ_DEBUG_BOUNDS
+#define AZ_CHECK_NODE(tm, idx) assert((idx) < (tm).cap)
+#define AZ_SET_CAP(tm, c) (tm).cap = (uint32_t)(c)
+#else
+#define AZ_CHECK_NODE(tm, idx) do { } while (0)
+#define AZ_SET_CAP(tm, c) do { } while (0)
+#endif
 
 template <bool LAT>
 __device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx, const double *__restrict__ sqt) {
     Child ch;
     uint4 m;
+    AZ_CHECK_NODE(tm, idx);
     if (idx < tm.K) {
         m = tm.sM[idx];
         ch.w = tm.sW[idx];
@@ -179,6 +194,7 @@ __device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx, con
 }
 
 __device__ __forceinline__ void store_new_child(const TreeMem &tm, uint32_t idx, float prior) {
+    AZ_CHECK_NODE(tm, idx);
     const uint4 m = make_uint4(0u, __float_as_uint(prior), 0u, 0u);
     if (idx < tm.K) {
         tm.sW[idx] = 0.0;
@@ -190,11 +206,13 @@ __device__ __forceinline__ void store_new_child(const TreeMem &tm, uint32_t idx,
 }
 
 __device__ __forceinline__ void set_first_child(const TreeMem &tm, uint32_t idx, uint32_t first) {
+    AZ_CHECK_NODE(tm, idx);
     if (idx < tm.K) reinterpret_cast<uint32_t *>(tm.sM + idx)[2] = first;
     else reinterpret_cast<uint32_t *>(tm.gM + idx)[2] = first;
 }
 
 __device__ __forceinline__ void visit_node(const TreeMem &tm, uint32_t idx, double dv) {
+    AZ_CHECK_NODE(tm, idx);
     if (idx < tm.K) {
         tm.sW[idx] = __dadd_rn(tm.sW[idx], dv);
         reinterpret_cast<uint32_t *>(tm.sM + idx)[0] += 1u;
@@ -369,6 +387,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     tm.sM = reinterpret_cast<uint4 *>(smem_raw) + (size_t)tib * K;
     tm.sW = reinterpret_cast<double *>(smem_raw + (size_t)TREES * K * sizeof(uint4)) + (size_t)tib * K;
     tm.K = (uint32_t)K;
+    AZ_SET_CAP(tm, a.cap);
     uint32_t *path = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TREES * K * (sizeof(uint4) + sizeof(double))) + tib * PATH_STRIDE;
     const uint64_t rb0 = a.root_bb0[tt], rb1 = a.root_bb1[tt];
     const int rpl = a.root_player[tt];
@@ -636,6 +655,7 @@ __global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_p
     tm.sW = nullptr;
     tm.sM = nullptr;
     tm.K = 0;
+    AZ_SET_CAP(tm, a.cap);
     // first round of loads, all independent: error flag, root position, root record
     const int32_t err = a.tree_err[tt];
     const uint64_t rb0 = a.root_bb0[tt], rb1 = a.root_bb1[tt];
@@ -710,6 +730,7 @@ k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const f
     tm.sW = nullptr;
     tm.sM = nullptr;
     tm.K = 0;
+    AZ_SET_CAP(tm, a.cap);
     // second round: W / N of this lane's path node (the leaf itself is visited for the first time: nothing to load)
     const bool own = alive && lit <= depth;
     const bool fresh = lit == depth;
