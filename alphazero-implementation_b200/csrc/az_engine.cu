@@ -84,7 +84,7 @@ __device__ __forceinline__ double div_tab(double x, uint32_t d, const double *__
 #ifdef AZ_DEBUG_BOUNDS
     assert(d < 1u << 20);  // tables hold num_simulations + 8 entries; a wild index shows up here first
 #endif
-    const double r = __ldg(rcp + d);
+    const double r = rcp[d];  // generic load: the tables live in shared memory (fused kernel, small S) or in global memory
     const double nd = -(double)d;
     double q = __dmul_rn(x, r);
     q = __fma_rn(__fma_rn(nd, q, x), r, q);
@@ -189,7 +189,7 @@ __device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx, con
     ch.n = m.x;
     ch.p = __uint_as_float(m.y);
     ch.cb = m.z;
-    ch.sq = LAT ? __ldg(sqt + m.x) : 0.0;
+    ch.sq = LAT ? sqt[m.x] : 0.0;
     return ch;
 }
 
@@ -275,7 +275,7 @@ __device__ __forceinline__ Leaf descend(const TreeMem &tm, const double *__restr
         const int bc = LAT ? argmax_first(masked, c) : argmax_first_ballot(masked, sub);
         const uint32_t cb_sel = __shfl_sync(FULL, ch.cb, sub + bc);
         if (LAT) sq_parent = __shfl_sync(FULL, ch.sq, sub + bc);
-        else sq_parent = __ldg(sqt + __shfl_sync(FULL, ch.n, sub + bc));
+        else sq_parent = sqt[__shfl_sync(FULL, ch.n, sub + bc)];
         const unsigned bcbit = 1u << bc;
         const unsigned lg = legal & ~(fill_mask & bcbit);  // legal mask of the node being entered
         const bool go_next = go && cb_sel != 0;
@@ -361,7 +361,7 @@ struct MoveArgs {
 };
 
 template <int TPW, int EVAL, bool LAT, bool MOVE>
-__global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, double c_puct, int K, MoveArgs mv) {
+__global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, double c_puct, int K, int tabs_in_smem, MoveArgs mv) {
     constexpr int TREES = 2 * TPW;  // per 64-thread block
     constexpr int NL = 32 / TPW;    // lanes per tree
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -372,6 +372,19 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     const int q = lane / (32 / TPW);
     const int tib = warp * TPW + q;
     const int t = blockIdx.x * TREES + tib;
+    // 1/d and sqrt(n) tables: every level's chain goes through them, and in L1 they compete with the node traffic (an L1 miss
+    // costs an L2 round trip on the chain), so the block keeps its own copy in shared memory when they are small enough
+    const double *rcp = a.rcp, *sqt = a.sqt;
+    if (tabs_in_smem) {  // before any warp can leave: both warps of the block take part
+        double *s_tab = reinterpret_cast<double *>(smem_raw + (size_t)TREES * (K * (sizeof(uint4) + sizeof(double)) + PATH_STRIDE * sizeof(uint32_t)));
+        for (int i = threadIdx.x; i < a.tab_n; i += 64) {
+            s_tab[i] = a.rcp[i];
+            s_tab[a.tab_n + i] = a.sqt[i];
+        }
+        rcp = s_tab;
+        sqt = s_tab + a.tab_n;
+        __syncthreads();
+    }
     const bool alive = (t < n_active) && (a.tree_err[t < n_active ? t : 0] == 0);
     const int lit = lane & (NL - 1);
     if (MOVE && t < n_active && lit == 0 && mv.finished) mv.finished[t] = 0;
@@ -423,8 +436,8 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     const int r_j = __popc(r_legal & ((1u << c) - 1u));
     Child rch;
     rch.w = 0.0; rch.sq = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
-    if (alive && root_cb != 0 && r_can) rch = load_child<LAT>(tm, root_cb + r_j, a.sqt);
-    double root_sq = __ldg(a.sqt + root_n);
+    if (alive && root_cb != 0 && r_can) rch = load_child<LAT>(tm, root_cb + r_j, sqt);
+    double root_sq = sqt[root_n];
     if (writer) path[0] = 0;
 
 #ifdef AZ_TRUNK_CLOCKS
@@ -432,7 +445,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
 #endif
     for (int s = 0; s < S; ++s) {
         RCLK(c0);
-        Leaf L = descend<LAT>(tm, a.rcp, a.sqt, rb0, rb1, rpl, c_puct, root_cb, root_sq, r_legal, rch, alive, writer, path, levels,
+        Leaf L = descend<LAT>(tm, rcp, sqt, rb0, rb1, rpl, c_puct, root_cb, root_sq, r_legal, rch, alive, writer, path, levels,
                          scanned);
         RCLK(c1);
         RACC(0, c1, c0);
@@ -490,9 +503,9 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
         RACC(1, c2, c1);
         // Backup, part 2.  Registers: root and the chosen root child; memory: every node on the path.
         root_n += (uint32_t)alive;
-        root_sq = __ldg(a.sqt + root_n);  // next simulation's sqrt(N_root) and sqrt(N_child): loaded behind the backup
+        root_sq = sqt[root_n];  // next simulation's sqrt(N_root) and sqrt(N_child): loaded behind the backup
         rch.n += (uint32_t)(alive && mine);
-        if (LAT) rch.sq = __ldg(a.sqt + rch.n);
+        if (LAT) rch.sq = sqt[rch.n];
         rch.w = (alive && mine) ? __dadd_rn(rch.w, backup_sign(v, L.depth, 1, L.term)) : rch.w;
         if (own) {
             const double w_new = __dadd_rn(w_old, backup_sign(v, L.depth, lit, L.term));
@@ -1663,7 +1676,8 @@ static int32_t run_sims_impl(az_engine *h, int32_t num_sims, int32_t eval_kind, 
         if (cand <= h->a.cap && bytes <= 200u * 1024u && bytes * per_sm <= 200u * 1024u) { K = cand; break; }
     }
     if (h->force_hot_nodes >= 0) K = (h->force_hot_nodes < h->a.cap ? h->force_hot_nodes : h->a.cap) & ~7;
-    const size_t smem = (size_t)trees_per_block * ((size_t)K * 24 + PATH_STRIDE * 4);
+    const int tabs_in_smem = (size_t)h->a.tab_n * 16 <= 4096 ? 1 : 0;
+    const size_t smem = (size_t)trees_per_block * ((size_t)K * 24 + PATH_STRIDE * 4) + (tabs_in_smem ? (size_t)h->a.tab_n * 16 : 0);
     const bool lat = latency_variant(h, blocks);
     MoveArgs mv;
     mv.uniforms = uniforms;
@@ -1675,7 +1689,7 @@ static int32_t run_sims_impl(az_engine *h, int32_t num_sims, int32_t eval_kind, 
 #define AZ_RUN2(TPW_, EV_, LAT_, MOVE_)                                                                                               \
     do {                                                                                                                              \
         AZ_CUDA(h, cudaFuncSetAttribute(k_run_sims<TPW_, EV_, LAT_, MOVE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_run_sims<TPW_, EV_, LAT_, MOVE_><<<blocks, 64, smem, S(stream)>>>(h->a, n, num_sims, c, K, mv);                             \
+        k_run_sims<TPW_, EV_, LAT_, MOVE_><<<blocks, 64, smem, S(stream)>>>(h->a, n, num_sims, c, K, tabs_in_smem, mv);               \
     } while (0)
 #define AZ_RUN1(TPW_, EV_, LAT_)                  \
     do {                                          \
