@@ -156,11 +156,20 @@ struct Child {  // the record of "my" column's child at the current node
 // of a launch (the fused kernel keeps the first, hottest nodes of every tree there: node indices grow
 // in creation order, so the shallow levels every simulation walks through have the smallest indices);
 // nodes >= K are in the HBM arena.  K == 0: everything in HBM.
+// Shared-memory form of a node, 16 bytes = ONE load per child: value_sum, prior, and visit_count / first child as two
+// 16-bit halves (so the lane that counts a visit and the lane that links the children store to different bytes).  Needs
+// 1 + 7 * num_simulations <= 65535; larger searches run without the shared-memory prefix.
+struct HotNode {
+    double w;
+    float p;
+    uint16_t n, cb;
+};
+static_assert(sizeof(HotNode) == 16, "hot node record");
+
 struct TreeMem {
     double *gW;
     uint4 *gM;
-    double *sW;
-    uint4 *sM;
+    HotNode *sH;
     uint32_t K;
 #ifdef AZ_DEBUG_BOUNDS
     uint32_t cap;  // debug build (-DAZ_DEBUG_BOUNDS): every node access is checked against the tree's capacity
@@ -180,16 +189,19 @@ __device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx, con
     uint4 m;
     AZ_CHECK_NODE(tm, idx);
     if (idx < tm.K) {
-        m = tm.sM[idx];
-        ch.w = tm.sW[idx];
+        m = *reinterpret_cast<const uint4 *>(tm.sH + idx);
+        ch.w = __hiloint2double((int)m.y, (int)m.x);
+        ch.p = __uint_as_float(m.z);
+        ch.n = m.w & 0xFFFFu;
+        ch.cb = m.w >> 16;
     } else {
         m = tm.gM[idx];
         ch.w = tm.gW[idx];
+        ch.n = m.x;
+        ch.p = __uint_as_float(m.y);
+        ch.cb = m.z;
     }
-    ch.n = m.x;
-    ch.p = __uint_as_float(m.y);
-    ch.cb = m.z;
-    ch.sq = LAT ? sqt[m.x] : 0.0;
+    ch.sq = LAT ? sqt[ch.n] : 0.0;
     return ch;
 }
 
@@ -197,8 +209,7 @@ __device__ __forceinline__ void store_new_child(const TreeMem &tm, uint32_t idx,
     AZ_CHECK_NODE(tm, idx);
     const uint4 m = make_uint4(0u, __float_as_uint(prior), 0u, 0u);
     if (idx < tm.K) {
-        tm.sW[idx] = 0.0;
-        tm.sM[idx] = m;
+        *reinterpret_cast<uint4 *>(tm.sH + idx) = make_uint4(0u, 0u, __float_as_uint(prior), 0u);
     } else {
         tm.gW[idx] = 0.0;
         tm.gM[idx] = m;
@@ -207,15 +218,15 @@ __device__ __forceinline__ void store_new_child(const TreeMem &tm, uint32_t idx,
 
 __device__ __forceinline__ void set_first_child(const TreeMem &tm, uint32_t idx, uint32_t first) {
     AZ_CHECK_NODE(tm, idx);
-    if (idx < tm.K) reinterpret_cast<uint32_t *>(tm.sM + idx)[2] = first;
+    if (idx < tm.K) tm.sH[idx].cb = (uint16_t)first;
     else reinterpret_cast<uint32_t *>(tm.gM + idx)[2] = first;
 }
 
 __device__ __forceinline__ void visit_node(const TreeMem &tm, uint32_t idx, double dv) {
     AZ_CHECK_NODE(tm, idx);
     if (idx < tm.K) {
-        tm.sW[idx] = __dadd_rn(tm.sW[idx], dv);
-        reinterpret_cast<uint32_t *>(tm.sM + idx)[0] += 1u;
+        tm.sH[idx].w = __dadd_rn(tm.sH[idx].w, dv);
+        tm.sH[idx].n += 1;
     } else {
         tm.gW[idx] = __dadd_rn(tm.gW[idx], dv);
         reinterpret_cast<uint32_t *>(tm.gM + idx)[0] += 1u;
@@ -376,7 +387,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     // costs an L2 round trip on the chain), so the block keeps its own copy in shared memory when they are small enough
     const double *rcp = a.rcp, *sqt = a.sqt;
     if (tabs_in_smem) {  // before any warp can leave: both warps of the block take part
-        double *s_tab = reinterpret_cast<double *>(smem_raw + (size_t)TREES * (K * (sizeof(uint4) + sizeof(double)) + PATH_STRIDE * sizeof(uint32_t)));
+        double *s_tab = reinterpret_cast<double *>(smem_raw + (size_t)TREES * (K * sizeof(HotNode) + PATH_STRIDE * sizeof(uint32_t)));
         for (int i = threadIdx.x; i < a.tab_n; i += 64) {
             s_tab[i] = a.rcp[i];
             s_tab[a.tab_n + i] = a.sqt[i];
@@ -397,11 +408,10 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     TreeMem tm;
     tm.gW = a.W + base;
     tm.gM = a.M + base;
-    tm.sM = reinterpret_cast<uint4 *>(smem_raw) + (size_t)tib * K;
-    tm.sW = reinterpret_cast<double *>(smem_raw + (size_t)TREES * K * sizeof(uint4)) + (size_t)tib * K;
+    tm.sH = reinterpret_cast<HotNode *>(smem_raw) + (size_t)tib * K;
     tm.K = (uint32_t)K;
     AZ_SET_CAP(tm, a.cap);
-    uint32_t *path = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TREES * K * (sizeof(uint4) + sizeof(double))) + tib * PATH_STRIDE;
+    uint32_t *path = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TREES * K * sizeof(HotNode)) + tib * PATH_STRIDE;
     const uint64_t rb0 = a.root_bb0[tt], rb1 = a.root_bb1[tt];
     const int rpl = a.root_player[tt];
     uint32_t used = a.used[tt];
@@ -418,19 +428,28 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     {
         const uint32_t hot = used < tm.K ? used : tm.K;
         for (uint32_t i = lit; i < hot; i += NL) {
-            tm.sM[i] = tm.gM[i];
-            tm.sW[i] = tm.gW[i];
+            const uint4 m = tm.gM[i];
+            HotNode hn;
+            hn.w = tm.gW[i];
+            hn.p = __uint_as_float(m.y);
+            hn.n = (uint16_t)m.x;
+            hn.cb = (uint16_t)m.z;
+            tm.sH[i] = hn;
         }
-        if (hot == 0 && lit == 0 && tm.K > 0) {
-            tm.sM[0] = make_uint4(0u, 0u, 0u, 0u);
-            tm.sW[0] = 0.0;
-        }
+        if (hot == 0 && lit == 0 && tm.K > 0) *reinterpret_cast<uint4 *>(tm.sH) = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncwarp();
 
     // root registers
-    const uint4 rm = (K > 0) ? tm.sM[0] : tm.gM[0];
-    uint32_t root_n = rm.x, root_cb = rm.z;
+    uint32_t root_n, root_cb;
+    if (K > 0) {
+        root_n = tm.sH[0].n;
+        root_cb = tm.sH[0].cb;
+    } else {
+        const uint4 rm = tm.gM[0];
+        root_n = rm.x;
+        root_cb = rm.z;
+    }
     const bool r_can = (c < c4::W) && !(((rb0 | rb1) >> (c4::STRIDE * c + 5)) & 1ull);
     const unsigned r_legal = (__ballot_sync(FULL, r_can) >> sub) & 0x7Fu;
     const int r_j = __popc(r_legal & ((1u << c) - 1u));
@@ -461,8 +480,8 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
         double w_old = 0.0;
         uint32_t n_old = 0u;
         if (own && !fresh) {
-            w_old = my_hot ? tm.sW[my_idx] : tm.gW[my_idx];
-            n_old = my_hot ? reinterpret_cast<const uint32_t *>(tm.sM + my_idx)[0] : reinterpret_cast<const uint32_t *>(tm.gM + my_idx)[0];
+            w_old = my_hot ? tm.sH[my_idx].w : tm.gW[my_idx];
+            n_old = my_hot ? (uint32_t)tm.sH[my_idx].n : reinterpret_cast<const uint32_t *>(tm.gM + my_idx)[0];
         }
         // leaf: evaluate + expand, or terminal value
         const uint64_t occ = L.b0 | L.b1;
@@ -510,8 +529,8 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
         if (own) {
             const double w_new = __dadd_rn(w_old, backup_sign(v, L.depth, lit, L.term));
             if (my_hot) {
-                tm.sW[my_idx] = w_new;
-                reinterpret_cast<uint32_t *>(tm.sM + my_idx)[0] = n_old + 1u;
+                tm.sH[my_idx].w = w_new;
+                tm.sH[my_idx].n = (uint16_t)(n_old + 1u);
             } else {
                 tm.gW[my_idx] = w_new;
                 reinterpret_cast<uint32_t *>(tm.gM + my_idx)[0] = n_old + 1u;
@@ -534,8 +553,9 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
         if (alive) {
             const uint32_t hot = used < tm.K ? used : tm.K;
             for (uint32_t i = lit; i < hot; i += NL) {
-                tm.gM[i] = tm.sM[i];
-                tm.gW[i] = tm.sW[i];
+                const HotNode hn = tm.sH[i];
+                tm.gM[i] = make_uint4(hn.n, __float_as_uint(hn.p), hn.cb, 0u);
+                tm.gW[i] = hn.w;
             }
         }
     } else {
@@ -665,8 +685,7 @@ __global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_p
     TreeMem tm;
     tm.gW = a.W + base;
     tm.gM = a.M + base;
-    tm.sW = nullptr;
-    tm.sM = nullptr;
+    tm.sH = nullptr;
     tm.K = 0;
     AZ_SET_CAP(tm, a.cap);
     // first round of loads, all independent: error flag, root position, root record
@@ -740,8 +759,7 @@ k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const f
     TreeMem tm;
     tm.gW = a.W + base;
     tm.gM = a.M + base;
-    tm.sW = nullptr;
-    tm.sM = nullptr;
+    tm.sH = nullptr;
     tm.K = 0;
     AZ_SET_CAP(tm, a.cap);
     // second round: W / N of this lane's path node (the leaf itself is visited for the first time: nothing to load)
@@ -1670,14 +1688,22 @@ static int32_t run_sims_impl(az_engine *h, int32_t num_sims, int32_t eval_kind, 
     const int blocks = blocks_for(n, trees_per_block);
     int per_sm = (blocks + h->num_sms - 1) / h->num_sms;
     if (per_sm > 14) per_sm = 14;  // register-limited residency of 64-thread blocks (72 registers)
+    const int tabs_in_smem = (size_t)h->a.tab_n * 16 <= 4096 ? 1 : 0;
+    const size_t tab_bytes = tabs_in_smem ? (size_t)h->a.tab_n * 16 : 0;
+    // hot-node count K: the largest multiple of 8 such that every block of the grid stays resident (228 KB of shared memory per SM,
+    // 1 KB of it reserved per resident block; one block may use up to 200 KB) - measured monotonic: more hot nodes, faster
     int K = 0;
-    for (int cand = 512; cand >= 16; cand >>= 1) {
-        const size_t bytes = (size_t)trees_per_block * ((size_t)cand * 24 + PATH_STRIDE * 4);
-        if (cand <= h->a.cap && bytes <= 200u * 1024u && bytes * per_sm <= 200u * 1024u) { K = cand; break; }
+    {
+        const long long per_block = (long long)(228 * 1024) / per_sm - 1024;
+        const long long budget = (per_block < 200 * 1024 ? per_block : 200 * 1024) - (long long)tab_bytes - (long long)trees_per_block * PATH_STRIDE * 4;
+        long long kmax = budget > 0 ? budget / ((long long)trees_per_block * 16) : 0;
+        if (kmax > 1024) kmax = 1024;
+        if (kmax > h->a.cap) kmax = h->a.cap;
+        K = (int)(kmax & ~7ll);
     }
     if (h->force_hot_nodes >= 0) K = (h->force_hot_nodes < h->a.cap ? h->force_hot_nodes : h->a.cap) & ~7;
-    const int tabs_in_smem = (size_t)h->a.tab_n * 16 <= 4096 ? 1 : 0;
-    const size_t smem = (size_t)trees_per_block * ((size_t)K * 24 + PATH_STRIDE * 4) + (tabs_in_smem ? (size_t)h->a.tab_n * 16 : 0);
+    if (h->a.cap > 65535) K = 0;  // the 16-byte shared-memory record holds visit count and child index in 16 bits each
+    const size_t smem = (size_t)trees_per_block * ((size_t)K * 16 + PATH_STRIDE * 4) + tab_bytes;
     const bool lat = latency_variant(h, blocks);
     MoveArgs mv;
     mv.uniforms = uniforms;
