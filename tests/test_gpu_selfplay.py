@@ -119,3 +119,36 @@ def test_fused_move_step_equals_two_calls(kind):
         assert (getattr(da, f) == getattr(db, f)).all(), f
     for e in engs:
         e.close()
+
+
+def test_sharded_selfplay_equals_unsharded():
+    """games never interact, so a rank that owns slots [lo, hi) and is fed those slots' uniforms must play
+    exactly the games the single-GPU run plays in those slots (here: two half-size engines against one full-size engine)."""
+    import alphazero_implementation_b200 as az
+    from alphazero_implementation_b200.distributed import shard_range
+
+    E, S, steps = 1000, 64, 45
+    u = np.random.RandomState(11).random_sample((steps, E))
+
+    def play(lo, hi):
+        eng = az.Engine(num_games=hi - lo, num_simulations=S)
+        eng.reset_games()
+        out = {}
+        for s in range(steps):
+            eng.run_move_step(S, 2, torch.from_numpy(np.ascontiguousarray(u[s, lo:hi])).cuda())
+            if s % 8 == 7 or s == steps - 1:  # the ring holds 2 * num_games + 64 episodes
+                b = eng.drain_episodes()
+                for e in range(len(b)):
+                    o, n = int(b.ep_offset[e]), int(b.ep_len[e])
+                    out[(int(b.ep_step[e]), int(b.ep_slot[e]) + lo)] = (b.ep_outcome[e].tolist(), b.s_bb0[o:o + n].tolist(),
+                                                                       b.s_bb1[o:o + n].tolist(), b.s_counts[o:o + n].tolist())
+        eng.close()
+        return out
+
+    full = play(0, E)
+    merged = {}
+    for r in range(2):
+        merged.update(play(*shard_range(E, r, 2)))
+    assert len(full) > E // 2 and full.keys() == merged.keys()
+    for k in full:
+        assert full[k] == merged[k], k
