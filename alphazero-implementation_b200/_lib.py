@@ -91,6 +91,7 @@ SIGNATURES = {
     "az_select_leaves": (I32, [P, P]),
     "az_gather_leaves": (I32, [P, P, I32, P]),
     "az_expand_backup": (I32, [P, P, P, I32, P]),
+    "az_expand_backup_select": (I32, [P, P, P, I32, P]),
     "az_leaf_info": (I32, [P, P, P, P, P, P, P]),
     "az_root_stats": (I32, [P, P, P, P, P, P, P, P, P]),
     "az_tree_capacity": (I32, [P]),

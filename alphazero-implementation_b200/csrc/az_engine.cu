@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
 // ------------------------------------------------------------------------------------------------
 // split path, step 1: search.py:69-79
 template <int TPW, bool LAT>
-__global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_puct) {
+__device__ __forceinline__ void select_body(const Arena &a, int n_active, double c_puct) {
     constexpr int TREES = 2 * TPW;
     constexpr int NL = 32 / TPW;
     const int lane = threadIdx.x & 31;
@@ -725,10 +725,15 @@ __global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_p
 }
 
 // split path, step 3: search.py:87-91 with the evaluator's outputs
+template <int TPW, bool LAT>
+__global__ void __launch_bounds__(64) k_select(Arena a, int n_active, double c_puct) {
+    select_body<TPW, LAT>(a, n_active, c_puct);
+}
+
+// split path, step 3: search.py:87-91 with the evaluator's outputs
 template <int TPW>
-__global__ void __launch_bounds__(64)
-k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const float *__restrict__ values,
-                int policy_kind) {
+__device__ __forceinline__ void expand_backup_body(const Arena &a, int n_active, const float *__restrict__ policy,
+                                                   const float *__restrict__ values, int policy_kind) {
     constexpr int TREES = 2 * TPW;
     constexpr int NL = 32 / TPW;
     const int lane = threadIdx.x & 31;
@@ -808,6 +813,23 @@ k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const f
         }
         for (int i = lit + NL; i <= depth; i += NL) visit_node(tm, path[i], backup_sign(v, depth, i, false));
     }
+}
+
+template <int TPW>
+__global__ void __launch_bounds__(64)
+k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const float *__restrict__ values, int policy_kind) {
+    expand_backup_body<TPW>(a, n_active, policy, values, policy_kind);
+}
+
+// Steps 3 and 1 of consecutive simulations in one launch: expansion + backup of simulation k, then the selection of simulation
+// k + 1 (same thread -> tree mapping in both, so a tree is only ever touched by its own warp; __syncwarp orders the two halves).
+// One launch less per simulation step of the network-in-the-loop path.
+template <int TPW, bool LAT>
+__global__ void __launch_bounds__(64)
+k_expand_select(Arena a, int n_active, const float *__restrict__ policy, const float *__restrict__ values, int policy_kind, double c_puct) {
+    expand_backup_body<TPW>(a, n_active, policy, values, policy_kind);
+    __syncwarp();
+    select_body<TPW, LAT>(a, n_active, c_puct);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1784,6 +1806,32 @@ int32_t az_expand_backup(az_engine *h, const float *policy, const float *values,
     else if (h->G == 16) k_expand_backup<2><<<blocks_for(n, 4), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind);
     else k_expand_backup<4><<<blocks_for(n, 8), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind);
     AZ_LAUNCH_CHECK(h, "k_expand_backup");
+    return AZ_OK;
+}
+
+/* az_expand_backup followed by az_select_leaves in ONE launch (same results): between two evaluator calls of the
+ * network-in-the-loop simulation loop (search.py:66-91) only this kernel runs. */
+int32_t az_expand_backup_select(az_engine *h, const float *policy, const float *values, int32_t policy_kind, void *stream) {
+    if (!h) return AZ_E_INVALID;
+    if (!policy || !values) return fail(h, AZ_E_INVALID, "%s", "az_expand_backup_select: null evaluator output");
+    if (policy_kind != AZ_POLICY_LOGITS && policy_kind != AZ_POLICY_PRIORS) return fail(h, AZ_E_INVALID, "%s", "az_expand_backup_select: bad policy_kind");
+    if (h->sims_done + 1 > h->cfg.num_simulations)
+        return fail(h, AZ_E_INVALID, "%s", "az_expand_backup_select: more simulations on these roots than the arena holds");
+    if (int rc = set_device(h)) return rc;
+    const int n = h->n_active;
+    const int tpb = 2 * (32 / h->G);
+    const bool lat = latency_variant(h, blocks_for(n, tpb));
+#define AZ_ES(TPW_)                                                                                                                   \
+    do {                                                                                                                              \
+        if (lat) k_expand_select<TPW_, true><<<blocks_for(n, tpb), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind, h->cfg.c_puct);  \
+        else k_expand_select<TPW_, false><<<blocks_for(n, tpb), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind, h->cfg.c_puct);     \
+    } while (0)
+    if (h->G == 32) AZ_ES(1);
+    else if (h->G == 16) AZ_ES(2);
+    else AZ_ES(4);
+#undef AZ_ES
+    AZ_LAUNCH_CHECK(h, "k_expand_select");
+    h->sims_done += 1;
     return AZ_OK;
 }
 

@@ -202,6 +202,13 @@ class Engine:
         self._check(self.lib.az_expand_backup(self.h, _ptr(policy, allow_pinned=True), _ptr(values, allow_pinned=True), policy_kind, _stream()),
                     "az_expand_backup")
 
+    def expand_backup_select(self, policy: torch.Tensor, values: torch.Tensor, policy_kind: int = POLICY_LOGITS):
+        """`expand_backup` of this simulation and `select_leaves` of the next one in one launch."""
+        assert policy.dtype == torch.float32 and values.dtype == torch.float32
+        assert policy.shape[0] >= self.n_active and policy.shape[-1] == 7 and values.shape[-1] == 2
+        self._check(self.lib.az_expand_backup_select(self.h, _ptr(policy, allow_pinned=True), _ptr(values, allow_pinned=True), policy_kind,
+                                                     _stream()), "az_expand_backup_select")
+
     def leaf_info(self):
         n = self.n_active
         out = dict(bb0=self.empty(n, torch.int64), bb1=self.empty(n, torch.int64), player=self.empty(n, torch.uint8),

@@ -76,11 +76,12 @@ class Node:
 
 
 class _GraphedStep:
-    """One simulation step (select -> gather -> net -> expand/backup), optionally replayed as a CUDA graph.
+    """The simulation loop of the network-in-the-loop path, optionally replayed as a CUDA graph.
 
-    The step has fixed shapes (row i of the packed batch = slot i), so one capture serves every
-    simulation of every move.  Capture only records; the two warm-up steps that precede it are real
-    simulations and the caller counts them.
+    n simulations = select, then (evaluate, expand + backup + next select) n - 1 times, then evaluate, expand + backup:
+    between two evaluator calls only `az_expand_backup_select` runs.  The repeated part has fixed shapes (row i of the packed
+    batch = slot i), so one capture serves every simulation of every move.  Capture only records; the warm-up steps that
+    precede it are real simulations.
     """
 
     def __init__(self, engine: Engine, net, layout: int):
@@ -89,26 +90,32 @@ class _GraphedStep:
         self.n = -1
         self.x = None
 
-    def step(self):
+    def evaluate(self):
         e = self.engine
-        e.select_leaves()
         if getattr(self.net, "evaluates_leaves_directly", False):  # tcgen05 kernels with the leaf gather fused in
-            logits, values = self.net.forward_leaves(e)
-        else:
-            e.gather_leaves(self.layout, self.x)
-            logits, values = self.net(self.x)
-        e.expand_backup(logits, values, POLICY_LOGITS)
+            return self.net.forward_leaves(e)
+        e.gather_leaves(self.layout, self.x)
+        return self.net(self.x)
+
+    def middle(self):
+        """evaluate the selected leaves, expand + back up, select the next leaves"""
+        logits, values = self.evaluate()
+        self.engine.expand_backup_select(logits, values, POLICY_LOGITS)
 
     def run(self, num_steps: int, use_graph: bool):
         e = self.engine
+        if num_steps <= 0:
+            return
         if self.n != e.n_active:
             self.n = e.n_active
             self.x = e.gather_leaves(self.layout)  # allocates the packed batch once per batch size
             self.graph = None
+        e.select_leaves()
+        middles = num_steps - 1
         done = 0
-        if use_graph and self.graph is None and num_steps > 2:
+        if use_graph and self.graph is None and middles > 2:
             for _ in range(2):  # cuDNN / cuBLAS pick algorithms and allocate workspaces outside capture
-                self.step()
+                self.middle()
             done = 2
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
@@ -117,14 +124,16 @@ class _GraphedStep:
             with torch.cuda.stream(side):
                 # thread_local: a training thread may allocate while the self-play thread captures (trainer.py overlap)
                 with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
-                    self.step()
+                    self.middle()
             torch.cuda.current_stream().wait_stream(side)
             self.graph = g
-        for _ in range(num_steps - done):
+        for _ in range(middles - done):
             if use_graph and self.graph is not None:
                 self.graph.replay()
             else:
-                self.step()
+                self.middle()
+        logits, values = self.evaluate()
+        e.expand_backup(logits, values, POLICY_LOGITS)
 
 
 class AlphaZeroSearch:

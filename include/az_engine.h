@@ -145,6 +145,9 @@ int32_t az_select_leaves(az_engine *h, void *stream);
 int32_t az_gather_leaves(az_engine *h, void *out, int32_t layout, void *stream);
 int32_t az_expand_backup(az_engine *h, const float *policy /*[E][7]*/, const float *values /*[E][2]*/,
                          int32_t policy_kind, void *stream);
+/* az_expand_backup followed by az_select_leaves in one launch (same results): the only tree kernel between two evaluator
+ * calls of the simulation loop (search.py:66-91). */
+int32_t az_expand_backup_select(az_engine *h, const float *policy, const float *values, int32_t policy_kind, void *stream);
 /* the leaves chosen by the last az_select_leaves (for evaluators that want positions, not planes) */
 int32_t az_leaf_info(az_engine *h, uint64_t *out_bb0, uint64_t *out_bb1, uint8_t *out_player, uint8_t *out_legal,
                      uint8_t *out_status, void *stream);
