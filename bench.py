@@ -99,15 +99,17 @@ class ClockSampler:
         self.t.start()
 
     def _run(self):
-        nv = self.nv
+        nv, i = self.nv, 0
         while not self.stop_flag:
-            try:
+            try:  # clock and throttle reasons every pass, power every fourth (each NVML call costs about a millisecond)
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                if i % 4 == 0:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            time.sleep(0.002)
+            i += 1
+            time.sleep(0.001)
 
     def stop(self) -> dict:
         if not self.ok:
@@ -420,7 +422,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         drained = eng.drain_episodes_device()
-        torch.cuda.synchronize()
+        barrier()  # the collective is timed from a common start, not from the slowest rank's arrival
         a0.record()
         merged = all_gather_episodes(drained)
         a1.record()
