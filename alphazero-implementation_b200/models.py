@@ -407,7 +407,7 @@ class InferenceNet(nn.Module):
             self.input_layout = LAYOUT_PLANES_BF16 if dtype == torch.bfloat16 else LAYOUT_PLANES_F32
             self.trunk = None
             if isinstance(m, ResNet) and m.num_channels == 64 and dtype == torch.bfloat16 and use_tensor_core_kernels:
-                self.trunk = TensorCoreTrunk(m, torch.device(device))  # hand-written tcgen05 trunk; heads stay library GEMMs
+                self.trunk = TensorCoreTrunk(m, torch.device(device))  # hand-written tcgen05 kernel: trunk + heads (csrc/az_conv.cu)
             self.net = self._fold(m).to(dtype).to(memory_format=torch.channels_last)
         else:
             self.input_layout = getattr(model, "input_layout", LAYOUT_PLANES_F32)

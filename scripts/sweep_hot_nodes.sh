@@ -1,4 +1,4 @@
-for k in auto 0 64 128 256 512; do
+for k in auto 0 128 256 320 384 408; do
   if [ $k = auto ]; then a=""; else a="--hot-nodes $k"; fi
   python bench.py --net none --no-cpu-baseline --no-e2e $a > gpurun_out/sw_$k.json 2>gpurun_out/sw_$k.err || tail -3 gpurun_out/sw_$k.err
   python -c "
