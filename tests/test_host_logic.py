@@ -71,3 +71,53 @@ def test_episode_file_round_trip(tmp_path):
     back = load_episodes(str(path))
     assert [e.samples[0].state for e in back] == [e.samples[0].state for e in eps]
     assert back[2].samples[0].value == [-1.0, 1.0]
+
+
+def _fake_batch(rng, n_eps, first_id=0, shuffled=False):
+    """Episodes whose samples carry recognisable values: bb0 = 1000 * episode id + ply."""
+    import torch
+
+    lens = rng.randint(1, 9, size=n_eps)
+    order = rng.permutation(n_eps) if shuffled else np.arange(n_eps)  # storage order of the sample blocks
+    offs = np.zeros(n_eps, np.int64)
+    pos = 0
+    for e in order:
+        offs[e] = pos
+        pos += lens[e]
+    bb0 = np.zeros(pos, np.int64)
+    counts = np.zeros((pos, 7), np.int32)
+    for e in range(n_eps):
+        for q in range(lens[e]):
+            bb0[offs[e] + q] = 1000 * (first_id + e) + q
+            counts[offs[e] + q] = (first_id + e + q) % 5
+    outcome = np.stack([np.where(np.arange(n_eps) % 3 == 0, 1, -1), -np.where(np.arange(n_eps) % 3 == 0, 1, -1)], 1).astype(np.int8)
+    d = dict(ep_len=lens.astype(np.int32), ep_offset=offs, ep_outcome=outcome, s_bb0=bb0, s_bb1=bb0 + 7, s_player=(bb0 % 2).astype(np.uint8),
+             s_counts=counts)
+    return {k: torch.from_numpy(v) for k, v in d.items()}, lens
+
+
+def test_replay_buffer_is_a_deque_of_episodes():
+    """datamodule.py:57 `deque(maxlen=buffer_size)` of episodes, flattened per datamodule.py:114-122 - on flat chunked storage."""
+    from collections import deque
+
+    import torch
+
+    from alphazero_implementation_b200.replay import ReplayBuffer
+
+    rng = np.random.RandomState(0)
+    rb = ReplayBuffer(buffer_size=25, num_simulations=11, device="cpu")
+    ref = deque(maxlen=25)  # (episode id, length, outcome row)
+    next_id = 0
+    for n_eps, shuffled in ((10, False), (7, True), (12, False), (30, True), (1, False), (0, False)):
+        batch, lens = _fake_batch(rng, n_eps, first_id=next_id, shuffled=shuffled)
+        rb.extend(batch)
+        for e in range(n_eps):
+            ref.append((next_id + e, int(lens[e]), batch["ep_outcome"][e].tolist()))
+        next_id += n_eps
+        assert len(rb) == len(ref) and rb.num_samples == sum(l for _, l, _ in ref)
+        bb0, bb1, pl, policy, value = rb.tensors()
+        want_bb0 = [1000 * i + q for i, l, _ in ref for q in range(l)]
+        assert bb0.tolist() == want_bb0 and bb1.tolist() == [v + 7 for v in want_bb0]
+        assert value.tolist() == [[float(o[0]), float(o[1])] for _, l, o in ref for _ in range(l)]
+        want_counts = torch.tensor([[(i + q) % 5] * 7 for i, l, _ in ref for q in range(l)], dtype=torch.float32)
+        assert torch.equal(policy, want_counts / 10.0)  # improved_policy = N_c / (S - 1)
