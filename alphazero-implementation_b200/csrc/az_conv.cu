@@ -301,6 +301,24 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
     // PAIR: two CTAs (one cluster, the two SMs of a TPC) run every MMA together; rank 0 issues them
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
+    // The leaf records of this thread's stem rows are requested first, in one round of independent loads, and consumed after the
+    // set-up below (tensor-memory allocation, barrier init, zero fill): their HBM / L2 latency hides behind it.
+    constexpr int ROWS_PER_THREAD = (TILES * 128 + THREADS - 1) / THREADS;
+    uint64_t in_b0[ROWS_PER_THREAD], in_b1[ROWS_PER_THREAD];
+    uint32_t in_meta[ROWS_PER_THREAD];  // bit 0: row is a live cell of an evaluated leaf, bit 1: side to move, bits 8..: bit index of the cell
+#pragma unroll
+    for (int k = 0; k < ROWS_PER_THREAD; ++k) {
+        const int r = (int)tid + k * THREADS;
+        int pos, y, x;
+        const bool cell = r < TILES * 128 && decode_row(r, pos, y, x);
+        const long long gp = pos0 + pos;
+        const bool in = cell && gp < n;
+        const long long g = in ? gp : 0;
+        const uint8_t st = leaf_status[g];
+        in_b0[k] = leaf_bb0[g];
+        in_b1[k] = leaf_bb1[g];
+        in_meta[k] = ((in && st == AZ_LEAF_EVAL) ? 1u : 0u) | ((uint32_t)(leaf_player[g] & 1) << 1) | ((uint32_t)(x * c4::STRIDE + y) << 8);
+    }
     if (warp == 0) {
         if (PAIR) {
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
@@ -323,15 +341,12 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
         for (uint32_t i = tid; i < NHC; i += THREADS) s_bias[n_conv * C + i] = __ldg(head_b + i);
     __syncthreads();
     // stem input in buf[1]: channels 0..2 = empty / side to move / opponent (cnn.py:93-95), K group 0
-    for (int r = tid; r < TILES * 128; r += THREADS) {
-        int pos, y, x;
-        if (!decode_row(r, pos, y, x)) continue;
-        const long long gp = pos0 + pos;
-        if (gp >= n || leaf_status[gp] != AZ_LEAF_EVAL) continue;
-        const uint64_t b0 = leaf_bb0[gp], b1 = leaf_bb1[gp];
-        const int pl = leaf_player[gp] & 1;
-        const int bit = x * c4::STRIDE + y;
-        const uint32_t s0 = (uint32_t)((b0 >> bit) & 1ull), s1 = (uint32_t)((b1 >> bit) & 1ull);
+#pragma unroll
+    for (int k = 0; k < ROWS_PER_THREAD; ++k) {
+        const int r = (int)tid + k * THREADS;
+        if (!(in_meta[k] & 1u)) continue;
+        const int pl = (in_meta[k] >> 1) & 1, bit = (int)(in_meta[k] >> 8);
+        const uint32_t s0 = (uint32_t)((in_b0[k] >> bit) & 1ull), s1 = (uint32_t)((in_b1[k] >> bit) & 1ull);
         const uint32_t mine = pl ? s1 : s0, theirs = pl ? s0 : s1, emp = 1u - (s0 | s1);
         const uint32_t one = 0x3F80u;
         *reinterpret_cast<uint4 *>(buf[1] + (GUARD + r) * ROWB) = make_uint4(emp * one | (mine * one) << 16, theirs * one, 0u, 0u);
