@@ -27,9 +27,11 @@ class Trainer:
 
     def train(self, *, num_iterations: int, episodes_per_iter: int, simulations_per_episode: int, epochs_per_iter: int,
               initial_state, buffer_size: int, save_every_n_iterations: int = 0, batch_size: int = 32, seed: int = 0,
-              overlap: bool = True, inference_dtype: torch.dtype | None = None):
+              overlap: bool = True, inference_dtype: torch.dtype | None = None, precision: str = "32-true"):
         """`overlap=True` reproduces the reference's pipeline (datamodule.py:89-101): the self-play of iteration k+1 runs on a
-        background thread (own CUDA stream, weights as of the end of iteration k-1's training) while iteration k trains."""
+        background thread (own CUDA stream, weights as of the end of iteration k-1's training) while iteration k trains.
+        `precision`: "32-true" (the reference's Lightning default) or "bf16-mixed" (forward / backward under bf16 autocast,
+        fp32 master weights and optimiser state)."""
         import threading
 
         world = dist.get_world_size() if dist.is_initialized() else 1
@@ -91,7 +93,8 @@ class Trainer:
                 for _ in range(epochs_per_iter):
                     for x, pt, vt in replay.batches(model.input_layout, batch_size, True, g):
                         opt.zero_grad(set_to_none=True)
-                        loss = model.training_step((x, pt, vt), 0)
+                        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=precision == "bf16-mixed"):
+                            loss = model.training_step((x, pt, vt), 0)
                         loss.backward()
                         opt.step()
                         losses.append(loss.detach())
