@@ -2,17 +2,21 @@
 // tensor cores: 42 -> 512 (ReLU) -> 512 (ReLU) -> {7 policy logits, 2 values (tanh)} for a batch of leaf
 // positions, ONE kernel, activations never leave the SM.
 //
-// One CTA (128 threads) owns a tile of 128 positions.  All three layers are tcgen05.mma (kind::f16, bf16 inputs,
-// fp32 accumulation) issued by one thread, with the accumulator in tensor memory (all 512 TMEM columns: a
-// 128 x 512 fp32 tile).  Between layers the four warps read their 32 accumulator lanes back with tcgen05.ld,
-// apply bias + ReLU in fp32, round to bf16 and write the next layer's A operand straight into shared memory in
-// the canonical K-major no-swizzle core-matrix layout the MMA descriptors address (8 rows x 16 bytes per core
-// matrix; LBO = 128 B between K-adjacent core matrices, SBO between 8-row groups).  Weights are packed once per
-// weight update (az_mlp_set_weights) into the same canonical layout, bf16, in 32-wide K chunks, so a chunk is a
-// flat 32 KB region that ONE thread streams into a two-stage shared-memory ring with bulk async copies
-// (cp.async.bulk + mbarrier complete_tx) while the tensor core works on the other stage; tcgen05.commit on a
-// per-stage mbarrier hands the stage back.  Only the GEMM work runs on tensor cores; bias, ReLU and tanh are
-// fp32 epilogues (north_star: "uses tensor cores only for its conv/GEMM layers").
+// One CTA owns a tile of 128 positions.  All three layers are tcgen05.mma (kind::f16, bf16 inputs, fp32 accumulation)
+// with the accumulator in tensor memory (all 512 TMEM columns: a 128 x 512 fp32 tile).  Roles: warp 8 only streams weights
+// - packed once per weight update (az_mlp_set_weights) into the canonical K-major no-swizzle core-matrix layout the MMA
+// descriptors address, bf16, in 16-wide K chunks, so a chunk is a flat 16 KB region - through a five-stage shared-memory
+// ring with bulk async copies (cp.async.bulk + mbarrier complete_tx); warp 0 waits for a stage and issues its MMAs (one
+// elected lane), tcgen05.commit on the stage's mbarrier hands it back to the producer; warps 0..7 are the epilogue: between
+// layers they read their accumulator lanes back with tcgen05.ld (two warps per 32 lanes, half the columns each, the next
+// 32-column block in flight while the current one is processed), apply bias + ReLU in fp32, round to bf16 and write the
+// next layer's A operand straight into shared memory (8 rows x 16 bytes per core matrix; LBO = 128 B between K-adjacent
+// core matrices, SBO between 8-row groups).  Only the GEMM work runs on tensor cores; bias, ReLU and tanh are fp32
+// epilogues (north_star: "uses tensor cores only for its conv/GEMM layers").
+// Measured (scripts/mlp_clocks.py, one CTA, 16384 positions): 25.0 k cycles = set-up 4.6 k, layer 1 1.7 k + epilogue 3.1 k,
+// layer 2 9.8 k (floor: 64 MMAs x 128 cycles = 8.2 k = the time the SM's ~64 B/clk L2 port needs for the layer's 512 KB of
+// weights) + epilogue 3.0 k, heads 1.9 k.  The first version (issuing warp also refilling a two-stage ring, 4 epilogue
+// warps with blocking tensor-memory loads) took 33.6 k; kernel 24.2 -> 18.7 us.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,12 +29,15 @@
 namespace {
 
 constexpr int TILE_M = 128;  // positions per CTA = UMMA M
+constexpr int THREADS = 288;  // warps 0..7: epilogue (w and w + 4 share the accumulator lanes 32 * (w % 4).., half the columns each),
+                              // warp 0 also issues the MMAs; warp 8 only streams weights
+constexpr int ETHREADS = 256;
 constexpr int IN = 42;       // 6 x 7 grid
 constexpr int K1 = 64;       // IN padded to a multiple of the K chunk
 constexpr int HID = 512;
 constexpr int NH = 16;       // 7 logits + 2 values, padded to the smallest UMMA N for M = 128
-constexpr int KC = 32;       // K chunk staged in shared memory (two MMA K steps)
-constexpr int NS = 2;        // stages of the weight ring, filled by bulk async copies (KC = 16 x 4 stages measured slower)
+constexpr int KC = 16;       // K chunk staged in shared memory (one MMA K step): 16 KB per chunk of a 512-row layer
+constexpr int NS = 5;        // stages of the weight ring: 64 KB in flight keep the SM's ~64 B/clk L2 read port busy
 constexpr uint32_t LBO = 128;                       // bytes between K-adjacent core matrices
 constexpr uint32_t SBO_ACT = (HID / 8) * 128;       // 8192: bytes between 8-row groups of the [128][512] activation tile
 constexpr uint32_t SBO_X = (K1 / 8) * 128;          // 1024: same for the [128][64] input tile
@@ -103,6 +110,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the same load without the wait: the caller overlaps it with the arithmetic on the previous block (tmem_ld_wait before use)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+        " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32"
@@ -125,69 +145,83 @@ __device__ long long g_mlp_clk[16];
 #define MCLK(i) do { } while (0)
 #endif
 
-// ---- weight pipeline (warp 0, converged; one elected lane issues): bulk async copies (TMA, 1-D) fill two shared-memory stages; an mbarrier
-// per stage reports the bytes landed ("full"); tcgen05.commit reports when the MMAs that read a stage are done ("empty").
+// ---- weight pipeline.  Warp 8 streams every chunk of every layer, in order, through an NS-stage ring with bulk async copies
+// (TMA, 1-D): an mbarrier per stage reports the bytes landed ("full"); tcgen05.commit reports when the MMAs that read a stage are
+// done ("empty").  Warp 0 only waits for "full" and issues - it never waits for a copy it would have to start itself (the MMA
+// queue is 2-3 instructions deep: a stalled issuer is a stalled tensor core), and 4 chunks stay in flight: a 16 KB chunk takes
+// ~560 cycles to arrive (L2 latency + 64 B/clk), the two MMAs that consume it take 256.
 struct Pipe {
-    uint32_t full[NS], empty[NS], done;  // shared-memory addresses of the mbarriers
-    uint32_t stage[NS];                  // shared-memory addresses of the stages
-    uint32_t g;                          // chunks consumed so far in this kernel (stage = g % NS, use = g / NS)
+    uint32_t full0, empty0, done, stage0;  // shared-memory addresses: full[NS], empty[NS], done barrier, first stage
+    uint32_t g;                            // chunks consumed (issuer) / produced (producer) so far (stage = g % NS, use = g / NS)
 };
 
-__device__ __forceinline__ void pipe_load(const Pipe &p, uint32_t gj, const uint8_t *src, uint32_t bytes) {
-    const uint32_t st = gj % NS;
-    if (gj >= NS) mbar_wait(p.empty[st], ((gj / NS) - 1u) & 1u);  // the MMAs of the previous use have finished reading
-    if (elect_one()) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(p.full[st]), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(p.stage[st]),
-                     "l"(src), "r"(bytes), "r"(p.full[st])
-                     : "memory");
+__device__ __forceinline__ void produce_chunks(Pipe &p, const uint8_t *src, uint32_t nchunks, uint32_t chunk_bytes) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < nchunks; ++i, ++p.g) {
+        const uint32_t st = p.g % NS;
+        if (p.g >= NS) mbar_wait(p.empty0 + st * 8, ((p.g / NS) - 1u) & 1u);  // the MMAs of the previous use have finished reading
+        if (elect_one()) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(p.full0 + st * 8), "r"(chunk_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             p.stage0 + st * STAGE_BYTES),
+                         "l"(src + (size_t)i * chunk_bytes), "r"(chunk_bytes), "r"(p.full0 + st * 8)
+                         : "memory");
+        }
+        __syncwarp();
     }
-    __syncwarp();
 }
 
-// One layer: D[128 x N] (+)= A[128 x K] . W[N x K]^T with W streamed in `nchunks` chunks of `chunk_bytes`.
-// `ksteps` MMAs of K = 16 per chunk and N half.  The first min(NS, nchunks) chunks must already be in flight.
-__device__ __forceinline__ void pipe_layer(Pipe &p, const uint8_t *src, uint32_t nchunks, uint32_t chunk_bytes, uint32_t ksteps,
-                                           uint32_t a_addr, uint32_t a_sbo, uint32_t n_halves, uint32_t idesc, uint32_t tmem_base) {
-    for (uint32_t i = 0; i < nchunks; ++i) {
-        const uint32_t gi = p.g + i, st = gi % NS;
-        mbar_wait(p.full[st], (gi / NS) & 1u);
+// One layer's MMAs (warp 0, converged; one elected lane issues): D[128 x N] (+)= A[128 x K] . W[N x K]^T, W arriving in `nchunks`
+// chunks; `ksteps` MMAs of K = 16 per chunk and N half.
+__device__ __forceinline__ void issue_layer(Pipe &p, uint32_t nchunks, uint32_t ksteps, uint32_t a_addr, uint32_t a_sbo, uint32_t n_halves,
+                                            uint32_t idesc, uint32_t tmem_base) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < nchunks; ++i, ++p.g) {
+        const uint32_t st = p.g % NS, stage = p.stage0 + st * STAGE_BYTES;
+        mbar_wait(p.full0 + st * 8, (p.g / NS) & 1u);
         tc_fence_after();
         if (elect_one()) {
             for (uint32_t ks = 0; ks < ksteps; ++ks)
                 for (uint32_t half = 0; half < n_halves; ++half)
                     umma(tmem_base + half * 256, smem_desc(a_addr + (i * ksteps + ks) * 2 * LBO, a_sbo),
                          // inside a stage: [rows][KC] sub-chunks back to back; K step ks -> sub-chunk ks / (KC/16), part ks % (KC/16)
-                         smem_desc(p.stage[st] + half * (256 / 8) * SBO_CHUNK + (ks / (KC / 16)) * (NH * KC * 2) + (ks % (KC / 16)) * 2 * LBO,
-                                   SBO_CHUNK),
+                         smem_desc(stage + half * (256 / 8) * SBO_CHUNK + (ks / (KC / 16)) * (NH * KC * 2) + (ks % (KC / 16)) * 2 * LBO, SBO_CHUNK),
                          idesc, (i | ks) > 0);
-            umma_commit(p.empty[st]);
+            umma_commit(p.empty0 + st * 8);
         }
         __syncwarp();
-        if (i + NS < nchunks) pipe_load(p, gi + NS, src + (size_t)(i + NS) * chunk_bytes, chunk_bytes);
     }
     if (elect_one()) umma_commit(p.done);
     __syncwarp();
-    p.g += nchunks;
 }
 
-// accumulator (128 x 512 fp32 in TMEM) -> bias + ReLU -> bf16 -> canonical [128][512] A operand in shared memory
+// accumulator (128 x 512 fp32 in TMEM) -> bias + ReLU -> bf16 -> canonical [128][512] A operand in shared memory.
+// 8 warps: thread = (row, column half); the next 32-column block is in flight while the current one is processed.
+__device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], uint8_t *rowp, const float *bias, int cb) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(v[q * 8 + j]) + bias[cb * 32 + q * 8 + j], 0.0f);
+        *reinterpret_cast<uint4 *>(rowp + (cb * 4 + q) * LBO) =
+            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    }
+}
 __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_base, uint8_t *act, const float *bias /* shared memory */) {
-    const uint32_t row = threadIdx.x;                                  // lane of TMEM = row of the tile
+    const uint32_t row = threadIdx.x & 127u;                           // lane of TMEM = row of the tile
+    const int cb0 = (int)(threadIdx.x >> 7) * (HID / 64);              // this warp group's 8 column blocks of 32
     const uint32_t taddr = tmem_base + ((row & ~31u) << 16);          // this warp's 32 lanes
     uint8_t *rowp = act + (row >> 3) * SBO_ACT + (row & 7) * 16;
+    uint32_t va[32], vb[32];
+    tmem_ld32_issue(taddr + cb0 * 32, va);
 #pragma unroll 1
-    for (int cb = 0; cb < HID / 32; ++cb) {
-        uint32_t v[32];
-        tmem_ld32(taddr + cb * 32, v);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(v[q * 8 + j]) + bias[cb * 32 + q * 8 + j], 0.0f);
-            *reinterpret_cast<uint4 *>(rowp + (cb * 4 + q) * LBO) =
-                make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-        }
+    for (int i = 0; i < HID / 64; i += 2) {
+        tmem_ld_wait();
+        tmem_ld32_issue(taddr + (cb0 + i + 1) * 32, vb);
+        epilogue_block(va, rowp, bias, cb0 + i);
+        tmem_ld_wait();
+        if (i + 2 < HID / 64) tmem_ld32_issue(taddr + (cb0 + i + 2) * 32, va);
+        epilogue_block(vb, rowp, bias, cb0 + i + 1);
     }
 }
 
@@ -202,7 +236,7 @@ __device__ __forceinline__ uint64_t row_major42(uint64_t bb) {
 // FROM_LEAVES: the input rows are built in the kernel from the engine's leaf bitboards (the leaf gather fused in);
 // otherwise they are read from an AZ_LAYOUT_GRID_F32 batch.
 template <bool FROM_LEAVES>
-__global__ void __launch_bounds__(TILE_M, 1)
+__global__ void __launch_bounds__(THREADS, 1)
 k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1,
             const uint8_t *__restrict__ leaf_status, long long n, const uint8_t *__restrict__ w1p, const float *__restrict__ b1,
             const uint8_t *__restrict__ w2p, const float *__restrict__ b2, const uint8_t *__restrict__ whp,
@@ -216,122 +250,121 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
     const long long row0 = (long long)blockIdx.x * TILE_M;
     MCLK(0);
     Pipe p;
-#pragma unroll
-    for (int i = 0; i < NS; ++i) {
-        p.full[i] = smem_u32(bars + i);
-        p.empty[i] = smem_u32(bars + NS + i);
-        p.stage[i] = smem_u32(smem + ACT_BYTES) + i * STAGE_BYTES;
-    }
+    p.full0 = smem_u32(bars);
+    p.empty0 = smem_u32(bars + NS);
     p.done = smem_u32(bars + 2 * NS);
+    p.stage0 = smem_u32(smem + ACT_BYTES);
     p.g = 0;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    if (tid == 0) {
+    if (tid == 32) {
 #pragma unroll
         for (int i = 0; i < 2 * NS + 1; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
-    if (warp == 0)
-        for (uint32_t i = 0; i < K1 / KC && i < NS; ++i) pipe_load(p, i, w1p + (size_t)i * STAGE_BYTES, STAGE_BYTES);  // layer-1 weights
-    // input tile: raw grid values (-1 / 0 / 1, exact in bf16) as a [128][64] K-major tile, zero padded
-    for (uint32_t i = tid; i < 2 * HID; i += TILE_M) s_bias[i] = i < HID ? __ldg(b1 + i) : __ldg(b2 + i - HID);
-    if (FROM_LEAVES) {
-        // thread = row: 42 grid values from the leaf's bitboards, written as 8 x 16-byte core-matrix rows
-        const long long row = row0 + tid;
-        uint64_t m0 = 0, m1 = 0;
-        bool live = false;
-        if (row < n) {
-            live = leaf_status[row] == AZ_LEAF_EVAL;
-            m0 = row_major42(leaf_bb0[row]);
-            m1 = row_major42(leaf_bb1[row]);
-        }
-        uint8_t *rowp = act + (tid >> 3) * SBO_X + (tid & 7) * 16;
-#pragma unroll
-        for (int kg = 0; kg < K1 / 8; ++kg) {
-            uint32_t w[4];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                uint32_t pair = 0;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int e = kg * 8 + h * 2 + q;
-                    uint32_t v = 0;
-                    if (e < IN) v = ((m0 >> e) & 1ull) ? 0x0000u : (((m1 >> e) & 1ull) ? 0x3F80u : 0xBF80u);  // 0, +1, -1 in bf16
-                    pair |= v << (16 * q);
-                }
-                w[h] = live ? pair : 0u;
-            }
-            *reinterpret_cast<uint4 *>(rowp + kg * LBO) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-    } else {
-        for (uint32_t i = tid; i < TILE_M * K1 * 2 / 16; i += TILE_M) reinterpret_cast<uint4 *>(act)[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-#pragma unroll 6
-        for (uint32_t e = tid; e < TILE_M * IN; e += TILE_M) {
-            const uint32_t r = e / IN, k = e - r * IN;
-            if (row0 + r < n) *reinterpret_cast<__nv_bfloat16 *>(act + canon(r, k, SBO_X)) = __float2bfloat16_rn(__ldg(grid + (row0 + r) * IN + k));
-        }
-    }
-    fence_async_smem();
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();  // barriers initialised, tensor memory allocated
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t act_addr = smem_u32(act);
 
-    // ---- layer 1: [128 x 64] . [512 x 64]^T
-    MCLK(1);
-    if (warp == 0) {
-        pipe_layer(p, w1p, K1 / KC, STAGE_BYTES, KC / 16, act_addr, SBO_X, 2, instr_desc(128, 256), tmem_base);
-        for (uint32_t i = 0; i < NS; ++i) pipe_load(p, p.g + i, w2p + (size_t)i * STAGE_BYTES, STAGE_BYTES);  // prefetch layer 2 behind the epilogue
-    }
-    MCLK(2);
-    mbar_wait(p.done, 0);
-    tc_fence_after();
-    MCLK(3);
-    epilogue_hidden(tmem_base, act, s_bias);
-    MCLK(4);
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
-    // ---- layer 2: [128 x 512] . [512 x 512]^T, K in chunks of KC
-    MCLK(5);
-    if (warp == 0) {
-        pipe_layer(p, w2p, HID / KC, STAGE_BYTES, KC / 16, act_addr, SBO_ACT, 2, instr_desc(128, 256), tmem_base);
-        pipe_load(p, p.g, whp, WH_ELEMS * 2);  // head weights: one 16 KB "chunk" of [16][KC] sub-chunks
-    }
-    MCLK(6);
-    mbar_wait(p.done, 1);
-    tc_fence_after();
-    MCLK(7);
-    epilogue_hidden(tmem_base, act, s_bias + HID);
-    MCLK(8);
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
-    // ---- heads: [128 x 512] . [16 x 512]^T
-    MCLK(9);
-    if (warp == 0) pipe_layer(p, whp, 1, WH_ELEMS * 2, HID / 16, act_addr, SBO_ACT, 1, instr_desc(128, NH), tmem_base);
-    mbar_wait(p.done, 0);
-    tc_fence_after();
-    MCLK(10);
-    {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((tid & ~31u) << 16), v);
-        const long long row = row0 + tid;
-        if (row < n) {
+    if (warp == 8) {
+        // ===== weight producer: layer 1 (K1 / KC chunks), layer 2 (HID / KC chunks), heads (one 16 KB chunk of [16][KC] sub-chunks) =====
+        produce_chunks(p, w1p, K1 / KC, STAGE_BYTES);
+        produce_chunks(p, w2p, HID / KC, STAGE_BYTES);
+        produce_chunks(p, whp, 1, WH_ELEMS * 2);
+    } else {
+        // input tile: raw grid values (-1 / 0 / 1, exact in bf16) as a [128][64] K-major tile, zero padded
+        for (uint32_t i = tid; i < 2 * HID; i += ETHREADS) s_bias[i] = i < HID ? __ldg(b1 + i) : __ldg(b2 + i - HID);
+        if (FROM_LEAVES) {
+            // thread = (row, half of the 8 K groups): 42 grid values from the leaf's bitboards, written as 16-byte core-matrix rows
+            const uint32_t r = tid & 127u, kg0 = (tid >> 7) * (K1 / 16);
+            const long long row = row0 + r;
+            uint64_t m0 = 0, m1 = 0;
+            bool live = false;
+            if (row < n) {
+                live = leaf_status[row] == AZ_LEAF_EVAL;
+                m0 = row_major42(leaf_bb0[row]);
+                m1 = row_major42(leaf_bb1[row]);
+            }
+            uint8_t *rowp = act + (r >> 3) * SBO_X + (r & 7) * 16;
 #pragma unroll
-            for (int j = 0; j < 7; ++j) logits[row * 7 + j] = __uint_as_float(v[j]) + __ldg(bh + j);
-            values[row * 2 + 0] = tanhf(__uint_as_float(v[7]) + __ldg(bh + 7));
-            values[row * 2 + 1] = tanhf(__uint_as_float(v[8]) + __ldg(bh + 8));
+            for (int kk = 0; kk < K1 / 16; ++kk) {
+                const int kg = (int)kg0 + kk;
+                uint32_t w[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    uint32_t pair = 0;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int e = kg * 8 + h * 2 + q;
+                        uint32_t v = 0;
+                        if (e < IN) v = ((m0 >> e) & 1ull) ? 0x0000u : (((m1 >> e) & 1ull) ? 0x3F80u : 0xBF80u);  // 0, +1, -1 in bf16
+                        pair |= v << (16 * q);
+                    }
+                    w[h] = live ? pair : 0u;
+                }
+                *reinterpret_cast<uint4 *>(rowp + kg * LBO) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else {
+            for (uint32_t i = tid; i < TILE_M * K1 * 2 / 16; i += ETHREADS) reinterpret_cast<uint4 *>(act)[i] = make_uint4(0, 0, 0, 0);
+            asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
+#pragma unroll 6
+            for (uint32_t e = tid; e < TILE_M * IN; e += ETHREADS) {
+                const uint32_t r = e / IN, k = e - r * IN;
+                if (row0 + r < n) *reinterpret_cast<__nv_bfloat16 *>(act + canon(r, k, SBO_X)) = __float2bfloat16_rn(__ldg(grid + (row0 + r) * IN + k));
+            }
+        }
+        fence_async_smem();
+        asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
+
+        // ---- layer 1: [128 x 64] . [512 x 64]^T
+        MCLK(1);
+        if (warp == 0) issue_layer(p, K1 / KC, KC / 16, act_addr, SBO_X, 2, instr_desc(128, 256), tmem_base);
+        MCLK(2);
+        mbar_wait(p.done, 0);
+        tc_fence_after();
+        MCLK(3);
+        epilogue_hidden(tmem_base, act, s_bias);
+        MCLK(4);
+        fence_async_smem();
+        tc_fence_before();
+        asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
+        tc_fence_after();
+
+        // ---- layer 2: [128 x 512] . [512 x 512]^T, K in chunks of KC
+        MCLK(5);
+        if (warp == 0) issue_layer(p, HID / KC, KC / 16, act_addr, SBO_ACT, 2, instr_desc(128, 256), tmem_base);
+        MCLK(6);
+        mbar_wait(p.done, 1);
+        tc_fence_after();
+        MCLK(7);
+        epilogue_hidden(tmem_base, act, s_bias + HID);
+        MCLK(8);
+        fence_async_smem();
+        tc_fence_before();
+        asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
+        tc_fence_after();
+
+        // ---- heads: [128 x 512] . [16 x 512]^T
+        MCLK(9);
+        if (warp == 0) issue_layer(p, 1, HID / 16, act_addr, SBO_ACT, 1, instr_desc(128, NH), tmem_base);
+        mbar_wait(p.done, 0);
+        tc_fence_after();
+        MCLK(10);
+        if (tid < TILE_M) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((tid & ~31u) << 16), v);
+            const long long row = row0 + tid;
+            if (row < n) {
+#pragma unroll
+                for (int j = 0; j < 7; ++j) logits[row * 7 + j] = __uint_as_float(v[j]) + __ldg(bh + j);
+                values[row * 2 + 0] = tanhf(__uint_as_float(v[7]) + __ldg(bh + 7));
+                values[row * 2 + 1] = tanhf(__uint_as_float(v[8]) + __ldg(bh + 8));
+            }
         }
     }
     tc_fence_before();
@@ -442,7 +475,7 @@ int32_t az_mlp_forward(az_mlp *m, const float *grid, int64_t n, float *logits, f
     if (n == 0) return AZ_OK;
     cudaSetDevice(m->device);
     const int blocks = (int)((n + TILE_M - 1) / TILE_M);
-    k_mlp_fused<false><<<blocks, TILE_M, SMEM_BYTES, (cudaStream_t)stream>>>(grid, nullptr, nullptr, nullptr, n, m->w1p, m->b1, m->w2p, m->b2,
+    k_mlp_fused<false><<<blocks, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(grid, nullptr, nullptr, nullptr, n, m->w1p, m->b1, m->w2p, m->b2,
                                                                              m->whp, m->bh, logits, values);
     m->launches++;
     cudaError_t e = cudaGetLastError();
@@ -463,7 +496,7 @@ int32_t az_mlp_forward_leaves(az_mlp *m, az_engine *engine, float *logits, float
     if (az_leaf_arrays(engine, &bb0, &bb1, &status, &n) != AZ_OK || n <= 0) return AZ_E_INVALID;
     cudaSetDevice(m->device);
     const int blocks = (n + TILE_M - 1) / TILE_M;
-    k_mlp_fused<true><<<blocks, TILE_M, SMEM_BYTES, (cudaStream_t)stream>>>(nullptr, bb0, bb1, status, n, m->w1p, m->b1, m->w2p, m->b2, m->whp,
+    k_mlp_fused<true><<<blocks, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(nullptr, bb0, bb1, status, n, m->w1p, m->b1, m->w2p, m->b2, m->whp,
                                                                             m->bh, logits, values);
     m->launches++;
     cudaError_t e = cudaGetLastError();
