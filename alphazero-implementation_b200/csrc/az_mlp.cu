@@ -249,6 +249,17 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const long long row0 = (long long)blockIdx.x * TILE_M;
     MCLK(0);
+    // the leaf record of this thread's row is requested before the CTA set-up and consumed after it
+    uint64_t in_b0 = 0, in_b1 = 0;
+    bool in_live = false;
+    if (FROM_LEAVES && tid < ETHREADS) {
+        const long long row = row0 + (tid & 127u);
+        if (row < n) {
+            in_live = leaf_status[row] == AZ_LEAF_EVAL;
+            in_b0 = leaf_bb0[row];
+            in_b1 = leaf_bb1[row];
+        }
+    }
     Pipe p;
     p.full0 = smem_u32(bars);
     p.empty0 = smem_u32(bars + NS);
@@ -282,14 +293,8 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
         if (FROM_LEAVES) {
             // thread = (row, half of the 8 K groups): 42 grid values from the leaf's bitboards, written as 16-byte core-matrix rows
             const uint32_t r = tid & 127u, kg0 = (tid >> 7) * (K1 / 16);
-            const long long row = row0 + r;
-            uint64_t m0 = 0, m1 = 0;
-            bool live = false;
-            if (row < n) {
-                live = leaf_status[row] == AZ_LEAF_EVAL;
-                m0 = row_major42(leaf_bb0[row]);
-                m1 = row_major42(leaf_bb1[row]);
-            }
+            const bool live = in_live;
+            const uint64_t m0 = row_major42(in_b0), m1 = row_major42(in_b1);
             uint8_t *rowp = act + (r >> 3) * SBO_X + (r & 7) * 16;
 #pragma unroll
             for (int kk = 0; kk < K1 / 16; ++kk) {
