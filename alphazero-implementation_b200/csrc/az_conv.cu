@@ -289,8 +289,8 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *buf[2] = {smem, smem + BUF_BYTES};
     float *s_bias = reinterpret_cast<float *>(smem + OFF_BIAS);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BARS);  // full[9] empty[9] mma_done[2] epi_done[2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + (2 * NS + 4) * 8);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BARS);  // full[9] empty[9] mma_done[2] epi_done[2] pfull[9]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + (3 * NS + 4) * 8);
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const long long pos0 = (long long)blockIdx.x * P;
     if (warp == 0) CLK(0, MAX_LAYERS - 1, 0);
