@@ -25,6 +25,9 @@
 //    layer, used by A and then by B, whose commit releases the stage for the next layer's tap.  The issuer never
 //    waits for a copy it has to start itself: the MMA queue is only 2-3 instructions deep (measured with the
 //    AZ_TRUNK_CLOCKS build, scripts/trunk_clocks.py), so every stall of the issuing warp is a stall of the tensor core.
+//  * Persistent CTAs.  One CTA per SM walks over batches of 8 positions: tensor memory, barriers (their phases just continue),
+//    biases and the zero padding are set up once, the weight producer runs ahead across the batch boundary, and the next
+//    batch's leaf records are requested while the FC tail of the current one runs.
 //  * Heads.  After the last block the policy conv1x1 and the value conv3x3 run as ONE 48-channel conv layer (the 1x1
 //    weights sit in the centre tap); the two small FC layers run on CUDA cores in fp32, each weight read once per CTA.
 // Measured (16384 positions, 4 blocks): 0.70 ms; a group's 72 MMAs take ~3750 cycles = 52 cycles per 128x64x16 MMA
@@ -292,7 +295,6 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BARS);  // full[9] empty[9] mma_done[2] epi_done[2] pfull[9]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + (3 * NS + 4) * 8);
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    const long long pos0 = (long long)blockIdx.x * P;
     if (warp == 0) CLK(0, MAX_LAYERS - 1, 0);
     const int n_conv = 1 + 2 * num_blocks;            // stem + block convs
     const int n_layers = n_conv + (head_w ? 1 : 0);   // + head conv
@@ -301,24 +303,6 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
     // PAIR: two CTAs (one cluster, the two SMs of a TPC) run every MMA together; rank 0 issues them
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
-    // The leaf records of this thread's stem rows are requested first, in one round of independent loads, and consumed after the
-    // set-up below (tensor-memory allocation, barrier init, zero fill): their HBM / L2 latency hides behind it.
-    constexpr int ROWS_PER_THREAD = (TILES * 128 + THREADS - 1) / THREADS;
-    uint64_t in_b0[ROWS_PER_THREAD], in_b1[ROWS_PER_THREAD];
-    uint32_t in_meta[ROWS_PER_THREAD];  // bit 0: row is a live cell of an evaluated leaf, bit 1: side to move, bits 8..: bit index of the cell
-#pragma unroll
-    for (int k = 0; k < ROWS_PER_THREAD; ++k) {
-        const int r = (int)tid + k * THREADS;
-        int pos, y, x;
-        const bool cell = r < TILES * 128 && decode_row(r, pos, y, x);
-        const long long gp = pos0 + pos;
-        const bool in = cell && gp < n;
-        const long long g = in ? gp : 0;
-        const uint8_t st = leaf_status[g];
-        in_b0[k] = leaf_bb0[g];
-        in_b1[k] = leaf_bb1[g];
-        in_meta[k] = ((in && st == AZ_LEAF_EVAL) ? 1u : 0u) | ((uint32_t)(leaf_player[g] & 1) << 1) | ((uint32_t)(x * c4::STRIDE + y) << 8);
-    }
     if (warp == 0) {
         if (PAIR) {
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
@@ -339,26 +323,72 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
     for (uint32_t i = tid; i < (uint32_t)n_conv * C; i += THREADS) s_bias[i] = __ldg(biases + i);
     if (head_w)
         for (uint32_t i = tid; i < NHC; i += THREADS) s_bias[n_conv * C + i] = __ldg(head_b + i);
-    __syncthreads();
-    // stem input in buf[1]: channels 0..2 = empty / side to move / opponent (cnn.py:93-95), K group 0
+    const uint32_t a0 = smem_u32(buf[0]) + GUARD * ROWB, a1 = smem_u32(buf[1]) + GUARD * ROWB;
+    const uint32_t epi_done_lead = PAIR ? mapa(epi_done0, 0u) : epi_done0;  // shared::cluster address in a pair
+    uint32_t tmem_base = 0;
+    constexpr int WTHREADS = THREADS - 32;  // everyone but the weight producer: it free-runs across batches (single-CTA mode)
+    auto batch_sync = [&]() {
+        if (PAIR) __syncthreads();
+        else asm volatile("bar.sync 2, %0;" ::"n"(WTHREADS) : "memory");
+    };
+    __syncthreads();  // barriers initialised, tensor memory allocated, buffers zeroed, biases staged
+
+    // Persistent: the CTA keeps its tensor memory, barriers, biases and zero padding and walks over batches of P positions.  Barrier
+    // phases simply continue: gl counts every layer the CTA has run (full / empty / mma_done / pfull complete once per layer), ge the
+    // conv layers (epi_done is not used by the head layer).  The weight producer runs ahead across the batch boundary.
+    const long long n_batches = (n + P - 1) / P + (PAIR ? ((n + P - 1) / P & 1) : 0);
+    uint32_t it = 0;
+    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
+    const long long pos0 = batch * P;
+    const uint32_t gl0 = it * (uint32_t)n_layers, ge0 = it * (uint32_t)n_conv;
+    // The leaf records of this thread's stem rows are requested first, in one round of independent loads, and consumed after the
+    // set-up below (first batch: tensor-memory allocation, barrier init, zero fill; later: the previous batch's FC tail): their HBM / L2 latency hides behind it.
+    constexpr int ROWS_PER_THREAD = (TILES * 128 + WTHREADS - 1) / WTHREADS;
+    uint64_t in_b0[ROWS_PER_THREAD], in_b1[ROWS_PER_THREAD];
+    uint32_t in_meta[ROWS_PER_THREAD];  // bit 0: cell of an evaluated leaf, bit 1: side to move, bit 2: row is a board cell, bits 8..: bit index of the cell
 #pragma unroll
     for (int k = 0; k < ROWS_PER_THREAD; ++k) {
-        const int r = (int)tid + k * THREADS;
-        if (!(in_meta[k] & 1u)) continue;
+        const int r = (int)tid + k * WTHREADS;
+        int pos, y, x;
+        const bool cell = tid < WTHREADS && r < TILES * 128 && decode_row(r, pos, y, x);
+        const long long gp = pos0 + pos;
+        const bool in = cell && gp < n;
+        const long long g = in ? gp : 0;
+        const uint8_t st = leaf_status[g];
+        in_b0[k] = leaf_bb0[g];
+        in_b1[k] = leaf_bb1[g];
+        in_meta[k] = ((in && st == AZ_LEAF_EVAL) ? 1u : 0u) | (cell ? 4u : 0u) | ((uint32_t)(leaf_player[g] & 1) << 1) | ((uint32_t)(x * c4::STRIDE + y) << 8);
+    }
+    if (PAIR || warp != 9) {
+    batch_sync();  // the previous batch is finished: buffers and tensor memory are this batch's
+    // the FC tail of the previous batch used K groups 2..7 of buf[1] as scratch, guard rows included: those must be zero again
+    if (it > 0)
+        for (uint32_t i = tid; i < 6 * 2 * GUARD; i += WTHREADS) {
+            const uint32_t kg = 2 + i / (2 * GUARD), j = i % (2 * GUARD);
+            const uint32_t row = j < GUARD ? j : (uint32_t)(TILES * 128 + j);  // rows before / after the tiles
+            *reinterpret_cast<uint4 *>(buf[1] + kg * LBO_A + row * ROWB) = make_uint4(0, 0, 0, 0);
+        }
+    // stem input in buf[1]: channels 0..2 = empty / side to move / opponent (cnn.py:93-95), K group 0.  Cells of slots without
+    // an evaluation are written as zeros (the buffer holds the previous batch's activations); K group 1 keeps stale finite
+    // values, which the stem's zero weights for channels 8..15 cancel.
+#pragma unroll
+    for (int k = 0; k < ROWS_PER_THREAD; ++k) {
+        const int r = (int)tid + k * WTHREADS;
+        if (!(in_meta[k] & 4u)) continue;
         const int pl = (in_meta[k] >> 1) & 1, bit = (int)(in_meta[k] >> 8);
+        const uint32_t live = in_meta[k] & 1u;
         const uint32_t s0 = (uint32_t)((in_b0[k] >> bit) & 1ull), s1 = (uint32_t)((in_b1[k] >> bit) & 1ull);
-        const uint32_t mine = pl ? s1 : s0, theirs = pl ? s0 : s1, emp = 1u - (s0 | s1);
+        const uint32_t mine = live * (pl ? s1 : s0), theirs = live * (pl ? s0 : s1), emp = live * (1u - (s0 | s1));
         const uint32_t one = 0x3F80u;
         *reinterpret_cast<uint4 *>(buf[1] + (GUARD + r) * ROWB) = make_uint4(emp * one | (mine * one) << 16, theirs * one, 0u, 0u);
     }
     fence_async_smem();
     tc_fence_before();
-    __syncthreads();
+    batch_sync();
+    }
     if (PAIR) cluster_sync_all();  // the peer's barriers are initialised and its stem input is written before anything remote happens
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t a0 = smem_u32(buf[0]) + GUARD * ROWB, a1 = smem_u32(buf[1]) + GUARD * ROWB;
-    const uint32_t epi_done_lead = PAIR ? mapa(epi_done0, 0u) : epi_done0;  // shared::cluster address in a pair
+    tmem_base = *tmem_slot;
 
     if (warp == 9) {
         // ===== weight producer: tap `tap` of layer l into stage `tap`, once group B of layer l-1 has released it =====
@@ -370,7 +400,7 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
             const uint32_t bytes = PAIR ? tap_bytes / 2 : tap_bytes;
 #pragma unroll 1
             for (uint32_t tap = 0; tap < 9; ++tap) {
-                if (l > 0) mbar_wait_cluster(empty0 + tap * 8, (uint32_t)(l - 1) & 1u);
+                if (gl0 + l > 0) mbar_wait_cluster(empty0 + tap * 8, (gl0 + (uint32_t)l - 1u) & 1u);
                 if (elect_one()) {
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + tap * 8), "r"(bytes) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -387,7 +417,7 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
         for (int l = 0; l < n_layers; ++l)
 #pragma unroll 1
             for (uint32_t tap = 0; tap < 9; ++tap) {
-                mbar_wait(full0 + tap * 8, (uint32_t)l & 1u);
+                mbar_wait(full0 + tap * 8, (gl0 + (uint32_t)l) & 1u);
                 if (elect_one()) mbar_arrive_cluster(pfull_lead + tap * 8);
                 __syncwarp();
             }
@@ -407,16 +437,17 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
                 const uint64_t a_desc = smem_desc(src + g * GROWS * ROWB, LBO_A, SBO_A);
                 const bool last = l + 1 == n_layers;
                 const uint32_t pre_bar = g == 0 ? (l > 0 ? epi_done0 + 8 : 0u) : (last ? 0u : epi_done0);
-                const uint32_t pre_parity = g == 0 ? (uint32_t)(l - 1) & 1u : (uint32_t)l & 1u;
+                const uint32_t pre_parity = g == 0 ? (ge0 + (uint32_t)l - 1u) & 1u : (ge0 + (uint32_t)l) & 1u;
+                const uint32_t par = (gl0 + (uint32_t)l) & 1u;
                 CLK(0, l, g);
                 if (l == 0) {
-                    if (g == 0) issue_group<1, false, PAIR>(full0, pfull0, empty0, 0u, true, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, false);
-                    else issue_group<1, true, PAIR>(full0, pfull0, empty0, 0u, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, !last);
+                    if (g == 0) issue_group<1, false, PAIR>(full0, pfull0, empty0, par, true, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, false);
+                    else issue_group<1, true, PAIR>(full0, pfull0, empty0, par, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, !last);
                 } else {
                     if (g == 0)
-                        issue_group<C / 16, false, PAIR>(full0, pfull0, empty0, (uint32_t)l & 1u, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, false);
+                        issue_group<C / 16, false, PAIR>(full0, pfull0, empty0, par, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, false);
                     else
-                        issue_group<C / 16, true, PAIR>(full0, pfull0, empty0, (uint32_t)l & 1u, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, !last);
+                        issue_group<C / 16, true, PAIR>(full0, pfull0, empty0, par, false, a_desc, b_desc, idesc, tile0, pre_bar, pre_parity, !last);
                 }
                 if (elect_one()) {
                     if (PAIR) umma_commit2(mma_done0 + g * 8);
@@ -434,8 +465,8 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
             const uint8_t *skip = (l > 0 && !(l & 1)) ? buf[0] : nullptr;
 #pragma unroll 1
             for (int g = 0; g < 2; ++g) {
-                if (PAIR) mbar_wait_cluster(mma_done0 + g * 8, (uint32_t)l & 1u);
-                else mbar_wait(mma_done0 + g * 8, (uint32_t)l & 1u);
+                if (PAIR) mbar_wait_cluster(mma_done0 + g * 8, (gl0 + (uint32_t)l) & 1u);
+                else mbar_wait(mma_done0 + g * 8, (gl0 + (uint32_t)l) & 1u);
                 tc_fence_after();
                 if (warp == 0) CLK(2, l, g);
                 conv_epilogue(tmem_base, dst, skip, s_bias + l * C, g * GTILES, (g + 1) * GTILES);
@@ -464,12 +495,13 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
             }
         }
         if (head_w) {
-            float *hact = reinterpret_cast<float *>(buf[1]);  // [P][35][42] fp32, the Flatten() order of NCHW
+            // [P][35][42] fp32, the Flatten() order of NCHW - behind K groups 0 and 1 of buf[1], whose zero padding the next batch's stem needs
+            float *hact = reinterpret_cast<float *>(buf[1] + 2 * LBO_A);
             const float *hb = s_bias + n_conv * C;
 #pragma unroll 1
             for (int g = 0; g < 2; ++g) {
-                if (PAIR) mbar_wait_cluster(mma_done0 + g * 8, (uint32_t)n_conv & 1u);
-                else mbar_wait(mma_done0 + g * 8, (uint32_t)n_conv & 1u);
+                if (PAIR) mbar_wait_cluster(mma_done0 + g * 8, (gl0 + (uint32_t)n_conv) & 1u);
+                else mbar_wait(mma_done0 + g * 8, (gl0 + (uint32_t)n_conv) & 1u);
                 tc_fence_after();
                 if (warp == 0) CLK(2, n_conv, g);
                 // warps 0..3: policy channels 0..31; warps 4..7: value channels 32..34
@@ -535,7 +567,7 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
                     acc[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, h >> 1);
                 }
             }
-            float *red = reinterpret_cast<float *>(buf[1] + 48 * 1024);  // [8 warps][64], behind hact (47040 B)
+            float *red = reinterpret_cast<float *>(buf[1] + 2 * LBO_A + 48 * 1024);  // [8 warps][64], behind hact (47040 B)
             *reinterpret_cast<float2 *>(red + warp * 64 + 2 * lane) = make_float2(acc[0], acc[1]);
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid < P * 8) {
@@ -556,6 +588,7 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
             }
         }
     }
+    }  // batches
     tc_fence_before();
     __syncthreads();
     if (PAIR) cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the pair's MMAs may still touch it
@@ -629,7 +662,10 @@ static int32_t launch_trunk(az_engine *engine, const void *weights, const float 
                                fcv_w, fcv_b, logits, values) != cudaSuccess)
             return AZ_E_CUDA;
     } else {
-        k_resnet_trunk<false><<<(n + P - 1) / P, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(bb0, bb1, player, status, nn, w8, biases, num_blocks, o16,
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return AZ_E_CUDA;
+        const int batches = (n + P - 1) / P;
+        k_resnet_trunk<false><<<batches < sms ? batches : sms, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(bb0, bb1, player, status, nn, w8, biases, num_blocks, o16,
                                                                                              hw8, head_b, fcp_w, fcp_b, fcv_w, fcv_b, logits, values);
     }
     return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;
