@@ -169,7 +169,7 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
 #ifdef AZ_TRUNK_CLOCKS
 // debug build only: per-layer timestamps of one CTA (issue start / issue end / accumulators ready / epilogue end)
 __device__ long long g_clk[4 * 2 * MAX_LAYERS];
-#define CLK(kind, l, g) do { if (blockIdx.x == 300 && (threadIdx.x & 31) == 0) g_clk[((kind) * MAX_LAYERS + (l)) * 2 + (g)] = clock64(); } while (0)
+#define CLK(kind, l, g) do { if (blockIdx.x == 100 && (threadIdx.x & 31) == 0) g_clk[((kind) * MAX_LAYERS + (l)) * 2 + (g)] = clock64(); } while (0)
 #else
 #define CLK(kind, l, g) do { } while (0)
 #endif
