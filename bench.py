@@ -144,8 +144,8 @@ def cpu_arm(E: int, S: int, kind: int, target_s: float = 12.0):
     from oracle import c4oracle
 
     c4oracle.build()
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = c4oracle.set_threads(cores)  # explicit: torchrun exports OMP_NUM_THREADS=1 to its workers
     rng = np.random.RandomState(0)
     c4oracle.selfplay(E, S, rng.random_sample((2, E)), quota=10**9, eval_kind=kind)  # thread pool + page faults
     t0 = time.perf_counter()

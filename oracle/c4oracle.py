@@ -52,6 +52,14 @@ def lib():
     return _lib
 
 
+def set_threads(n: int) -> int:
+    """Use `n` OpenMP threads from now on (overrides OMP_NUM_THREADS); returns the number in effect."""
+    l = lib()
+    l.c4o_set_threads.restype = C.c_int
+    l.c4o_set_threads.argtypes = [C.c_int]
+    return int(l.c4o_set_threads(int(n)))
+
+
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
