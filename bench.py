@@ -422,6 +422,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         drained = eng.drain_episodes_device()
+        all_gather_episodes(drained)  # same payload once untimed: NCCL sizes its buffers for the message on first use
         barrier()  # the collective is timed from a common start, not from the slowest rank's arrival
         a0.record()
         merged = all_gather_episodes(drained)
