@@ -13,11 +13,19 @@
 // warp owns one (TPW = 1; its four 8-lane quarters then compute the same thing).  Lane c (< 7) of each
 // quarter handles column c of the current node: it loads that child's record (coalesced: neighbouring
 // lanes read neighbouring records), scores it in fp64 with the reference's operation order and
-// rounding, and the best child is found with a __shfl_xor butterfly (max) + ballot (lowest column among
-// the maxima = the reference's strict '>' first-maximum rule).  The warp stays converged — quarters
-// whose tree has reached its leaf idle with their loads predicated off — so every shuffle / ballot
-// uses the full mask and no divergence bookkeeping is generated.  A tree is owned by one quarter, so
-// updates need no atomics; __syncwarp orders them between lanes.
+// rounding, and the best child is found with a __shfl_xor butterfly (lowest column among the maxima =
+// the reference's strict '>' first-maximum rule).  The warp stays converged and the level loop and the
+// per-simulation tail are straight-line code: lanes of finished trees compute on stale valid values and
+// every state update is masked, so every shuffle / ballot uses the full mask and no reconvergence
+// barrier sits on the dependent chain.  A tree is owned by one quarter, so updates need no atomics;
+// __syncwarp orders them between lanes.
+//
+// A simulation is one long dependent chain (with thousands, not millions, of trees nothing else hides
+// it), so the kernels are organised around that chain: see descend(), k_run_sims and DESIGN.md section 3.
+// The fused kernel keeps the first ~400 nodes of every tree (16-byte HotNode records) and the 1/d, sqrt
+// tables in shared memory, the root's statistics in registers, and can append the self-play move
+// (az_run_move_step); the split path (k_select / k_expand_backup / k_expand_select) serves external
+// evaluators and issues every independent load in its first round.
 //
 // fp64 without the division subroutine: the divisors of PUCT are small integers (visit counts <= S),
 // so 1/d and sqrt(n) come from tables of correctly rounded values (built once per engine with
