@@ -352,7 +352,8 @@ __device__ __forceinline__ double backup_sign(double v, int depth, int i, bool l
 // fused search: all S simulations of a tree in one launch, built-in evaluator.
 // The root's scalars (N, first child, legal mask) and each lane's root-child record live in registers
 // for the whole launch, the first K nodes of every tree in shared memory (loaded at entry, written back
-// at exit), the rest in HBM.  Dynamic shared memory: [TREES][K] uint4, [TREES][K] f64, [TREES][44] u32.
+// at exit unless the launch also plays the move), the rest in HBM.  Dynamic shared memory: [TREES][K] HotNode (16 B),
+// [TREES][44] u32 path, then the 1/d and sqrt tables (2 x tab_n f64) when they fit.
 #ifdef AZ_TRUNK_CLOCKS
 __device__ long long g_run_clk[8];
 #define RCLK(var) const long long var = clock64()
