@@ -1064,17 +1064,12 @@ k_state_info(const uint64_t *__restrict__ bb0, const uint64_t *__restrict__ bb1,
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_masked_softmax(const float *__restrict__ logits, const uint8_t *__restrict__ legal, long long n, float *out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t lg = legal[i] & 0x7Fu;
-    float x[7], m = -INFINITY;
+// One row of the legal-only softmax (models/games/connect4/model.py:29-35), fp32; x[] in, priors out (0 on illegal columns).
+__device__ __forceinline__ void masked_softmax_row(float (&x)[7], uint32_t lg) {
+    float m = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < 7; ++c) {
-        x[c] = logits[i * 7 + c];
+    for (int c = 0; c < 7; ++c)
         if ((lg >> c) & 1u) m = fmaxf(m, x[c]);
-    }
     float sum = 0.0f;
 #pragma unroll
     for (int c = 0; c < 7; ++c) {
@@ -1082,7 +1077,45 @@ k_masked_softmax(const float *__restrict__ logits, const uint8_t *__restrict__ l
         sum += x[c];
     }
 #pragma unroll
-    for (int c = 0; c < 7; ++c) out[i * 7 + c] = ((lg >> c) & 1u) ? __fdiv_rn(x[c], sum) : 0.0f;
+    for (int c = 0; c < 7; ++c) x[c] = ((lg >> c) & 1u) ? __fdiv_rn(x[c], sum) : 0.0f;
+}
+
+__global__ void __launch_bounds__(256)
+k_masked_softmax(const float *__restrict__ logits, const uint8_t *__restrict__ legal, long long n, float *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t lg = legal[i] & 0x7Fu;
+    float x[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) x[c] = logits[i * 7 + c];
+    masked_softmax_row(x, lg);
+#pragma unroll
+    for (int c = 0; c < 7; ++c) out[i * 7 + c] = x[c];
+}
+
+// Same rows, HBM-coalesced: a row is 28 bytes, so a thread-per-row access pattern touches every 32-byte sector seven times.
+// The block's 256 rows (7168 bytes) go through shared memory with 128-bit accesses; rows are read from shared memory at a
+// stride of 7 words (odd: conflict-free).  Used for the full 256-row blocks when both arrays are 16-byte aligned; the
+// thread-per-row kernel takes the tail.
+__global__ void __launch_bounds__(256)
+k_masked_softmax_tile(const float4 *__restrict__ logits, const uint8_t *__restrict__ legal, float4 *out) {
+    __shared__ float4 tile[448];  // 256 rows x 7 floats
+    const size_t b4 = (size_t)blockIdx.x * 448;
+    const int t = threadIdx.x;
+    tile[t] = logits[b4 + t];
+    if (t < 192) tile[256 + t] = logits[b4 + 256 + t];
+    const uint32_t lg = legal[(size_t)blockIdx.x * 256 + t] & 0x7Fu;
+    __syncthreads();
+    float *row = reinterpret_cast<float *>(tile) + 7 * t;
+    float x[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) x[c] = row[c];
+    masked_softmax_row(x, lg);
+#pragma unroll
+    for (int c = 0; c < 7; ++c) row[c] = x[c];
+    __syncthreads();
+    out[b4 + t] = tile[t];
+    if (t < 192) out[b4 + 256 + t] = tile[256 + t];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1609,8 +1642,17 @@ int32_t az_masked_softmax(az_engine *h, const float *logits, const uint8_t *lega
     if (n < 0 || (n > 0 && (!logits || !legal || !out))) return fail(h, AZ_E_INVALID, "%s", "az_masked_softmax: null argument");
     if (n == 0) return AZ_OK;
     if (int rc = set_device(h)) return rc;
-    k_masked_softmax<<<blocks_for(n, 256), 256, 0, S(stream)>>>(logits, legal, n, out);
-    AZ_LAUNCH_CHECK(h, "k_masked_softmax");
+    int64_t head = 0;
+    if (((uintptr_t)logits | (uintptr_t)out) % 16 == 0 && n >= 256) {
+        head = n & ~(int64_t)255;
+        k_masked_softmax_tile<<<(unsigned)(head / 256), 256, 0, S(stream)>>>(reinterpret_cast<const float4 *>(logits), legal,
+                                                                             reinterpret_cast<float4 *>(out));
+        AZ_LAUNCH_CHECK(h, "k_masked_softmax_tile");
+    }
+    if (head < n) {
+        k_masked_softmax<<<blocks_for(n - head, 256), 256, 0, S(stream)>>>(logits + head * 7, legal + head, n - head, out + head * 7);
+        AZ_LAUNCH_CHECK(h, "k_masked_softmax");
+    }
     return AZ_OK;
 }
 

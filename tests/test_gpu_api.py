@@ -215,6 +215,36 @@ def test_training_iteration_reduces_loss_and_syncs_weights():
                     initial_state=az.Config(6, 7, 4).sample_initial_state(), buffer_size=64)
     assert len(hist) == 3 and hist[0]["episodes"] == 32 and hist[1]["episodes"] == 64
     assert hist[0]["samples"] >= 32 * 7 and hist[2]["loss"] < hist[0]["loss"]
+    assert hist[2]["graph_replays"] > 0 and hist[0]["optimizer_steps"] == 3 * -(-hist[0]["samples"] // 32)
+
+
+def test_graphed_training_steps_equal_eager_steps():
+    """Row (f1): the optimiser steps replayed from a CUDA graph are the eager steps - same minibatches, same weights."""
+    from alphazero_implementation_b200.replay import ReplayBuffer
+    from alphazero_implementation_b200.trainer import _GraphedTraining
+
+    gen = az.EpisodeGenerator(model=az.UniformEvaluator(), num_simulations=24, num_episodes=64,
+                              game_initial_state=az.Config().sample_initial_state())
+    np.random.seed(3)
+    rb = ReplayBuffer(buffer_size=64, num_simulations=24)
+    for batch in gen.generate_batches(quota=64):
+        rb.extend(batch)
+    results = []
+    for use_graph in (False, True):
+        torch.manual_seed(11)
+        model = az.BasicNN().cuda().train()
+        opt = model.configure_optimizers()
+        for group in opt.param_groups:
+            group["capturable"] = True
+        steps = _GraphedTraining(model, opt, batch_size=32, precision="32-true", device=torch.device("cuda", torch.cuda.current_device()))
+        loss_sum, n = steps.run(rb, epochs=2, generator=torch.Generator().manual_seed(5), use_graph=use_graph)
+        assert n == 2 * -(-rb.num_samples // 32)
+        assert (steps.replays > 0) == use_graph
+        results.append((float(loss_sum), [p.detach().clone() for p in model.parameters()]))
+    (l0, w0), (l1, w1) = results
+    assert l0 == pytest.approx(l1, rel=1e-5)
+    for a, b in zip(w0, w1):
+        assert torch.allclose(a, b, atol=1e-6, rtol=1e-5)
 
 
 def test_replay_buffer_targets_match_reference_format(selfplay_goldens):

@@ -103,6 +103,11 @@ def test_masked_softmax_matches_torch(eng):
         assert torch.allclose(got[i, cols], ref, atol=1e-6, rtol=1e-5)
         assert got[i].sum().item() == pytest.approx(1.0, abs=1e-5)
         assert all(got[i, c] == 0 for c in range(7) if c not in cols)
+    # 16-byte-aligned batches take the shared-memory-staged kernel for the full 256-row blocks; a misaligned view of the same
+    # rows takes the thread-per-row kernel.  Same arithmetic: bit-identical.
+    dl, dg = logits.cuda(), legal.cuda()
+    assert dl[1:].data_ptr() % 16 != 0
+    assert torch.equal(eng.masked_softmax(dl[1:], dg[1:]).cpu(), got[1:])
 
 
 def test_env_step_vector_and_scalar_paths_agree(eng, oracle):
