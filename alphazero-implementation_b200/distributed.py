@@ -18,11 +18,28 @@ _EP_FIELDS = ("ep_slot", "ep_step", "ep_len", "ep_offset", "ep_outcome")
 _S_FIELDS = ("s_bb0", "s_bb1", "s_player", "s_counts")
 
 
-def shard_range(total_games: int, rank: int, world: int) -> tuple[int, int]:
-    """Static partition of game slots: rank r owns [lo, hi); sizes differ by at most one."""
-    base, rem = divmod(total_games, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+def shard_range(total_games: int, rank: int, world: int, trainer_share: float | None = None, trainer_rank: int = 0) -> tuple[int, int]:
+    """Static partition of game slots: rank r owns [lo, hi); sizes differ by at most one.
+    `trainer_share` (0 <= share <= 1): the fraction of the games the trainer rank plays - that rank's GPU is time-shared between
+    its self-play and the optimiser steps, so an equal split leaves the other ranks waiting for it; the rest is split evenly
+    over the other ranks.  None (or one rank) = equal shards."""
+    if trainer_share is None or world == 1:
+        base, rem = divmod(total_games, world)
+        lo = rank * base + min(rank, rem)
+        return lo, lo + base + (1 if rank < rem else 0)
+    if not 0.0 <= trainer_share <= 1.0:
+        raise ValueError("trainer_share must be in [0, 1]")
+    mine = min(total_games, int(round(total_games * trainer_share)))
+    base, rem = divmod(total_games - mine, world - 1)
+    sizes, k = [], 0
+    for r in range(world):
+        if r == trainer_rank:
+            sizes.append(mine)
+        else:
+            sizes.append(base + (1 if k < rem else 0))
+            k += 1
+    lo = sum(sizes[:rank])
+    return lo, lo + sizes[rank]
 
 
 @torch.no_grad()

@@ -131,17 +131,20 @@ class Trainer:
     def train(self, *, num_iterations: int, episodes_per_iter: int, simulations_per_episode: int, epochs_per_iter: int,
               initial_state, buffer_size: int, save_every_n_iterations: int = 0, batch_size: int = 32, seed: int = 0,
               overlap: bool = True, inference_dtype: torch.dtype | None = None, precision: str = "32-true",
-              cuda_graph: bool = True):
+              cuda_graph: bool = True, trainer_share: float | None = None):
         """`overlap=True` reproduces the reference's pipeline (datamodule.py:89-101): the self-play of iteration k+1 runs on a
         background thread (own CUDA stream, weights as of the end of iteration k-1's training) while iteration k trains.
         `precision`: "32-true" (the reference's Lightning default) or "bf16-mixed" (forward / backward under bf16 autocast,
         fp32 master weights and optimiser state).  `cuda_graph`: replay the optimiser steps from a CUDA graph (`_GraphedTraining`);
-        False runs the same steps eagerly (same minibatches, same arithmetic)."""
+        False runs the same steps eagerly (same minibatches, same arithmetic).  `trainer_share`: fraction of the games rank 0 plays
+        (`distributed.shard_range`); None = equal shards."""
         import threading
 
         world = dist.get_world_size() if dist.is_initialized() else 1
         rank = dist.get_rank() if dist.is_initialized() else 0
-        lo, hi = shard_range(episodes_per_iter, rank, world)
+        lo, hi = shard_range(episodes_per_iter, rank, world, trainer_share)
+        if hi == lo:
+            raise ValueError("trainer_share leaves a rank without games")
         model = self.model.to(self.device)
         kw = {} if inference_dtype is None else dict(inference_dtype=inference_dtype)
         gen = EpisodeGenerator(model=model, num_simulations=simulations_per_episode, num_episodes=hi - lo,

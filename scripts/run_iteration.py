@@ -25,6 +25,8 @@ ap.add_argument("--epochs", type=int, default=1)
 ap.add_argument("--batch-size", type=int, default=1024)
 ap.add_argument("--net", default="basic")
 ap.add_argument("--precision", default="32-true", choices=["32-true", "bf16-mixed"])
+ap.add_argument("--trainer-share", type=float, default=None, help="fraction of the games played by rank 0, which also trains (default: equal shards)")
+ap.add_argument("--eager", action="store_true", help="optimiser steps as an eager loop instead of CUDA-graph replays")
 args = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -40,7 +42,7 @@ tr = Trainer(model, device=local)
 t0 = time.perf_counter()
 hist = tr.train(num_iterations=args.iterations, episodes_per_iter=args.games, simulations_per_episode=args.sims,
                 epochs_per_iter=args.epochs, initial_state=az.Config(6, 7, 4).sample_initial_state(), buffer_size=args.games * 2,
-                batch_size=args.batch_size, precision=args.precision)
+                batch_size=args.batch_size, precision=args.precision, trainer_share=args.trainer_share, cuda_graph=not args.eager)
 torch.cuda.synchronize()
 wall = time.perf_counter() - t0
 # every rank must end with identical weights (rank 0 trained, everyone received the broadcast)
@@ -55,7 +57,7 @@ else:
     weights_identical = True
 if rank == 0:
     print(json.dumps({"workload": "alphazero_iteration", "n_gpus": world, "net": args.net, "episodes_per_iter": args.games,
-                      "simulations": args.sims, "iterations": args.iterations, "precision": args.precision, "wall_s": wall, "weights_identical_on_all_ranks": weights_identical,
+                      "simulations": args.sims, "iterations": args.iterations, "precision": args.precision, "trainer_share": args.trainer_share, "cuda_graph": not args.eager, "wall_s": wall, "weights_identical_on_all_ranks": weights_identical,
                       "history": hist}))
 if world > 1:
     dist.destroy_process_group()

@@ -92,6 +92,14 @@ def test_shard_range_partitions_all_games():
         sizes = [hi - lo for lo, hi in spans]
         assert max(sizes) - min(sizes) <= 1
     assert shard_range(65536, 3, 8) == (24576, 32768)
+    # weighted split: the trainer rank plays a smaller share, the rest is spread evenly; still a partition
+    for total, world, share in ((65536, 8, 0.08), (100, 4, 0.1), (7, 3, 0.0), (10, 2, 1.0)):
+        spans = [shard_range(total, r, world, share) for r in range(world)]
+        assert spans[0] == (0, min(total, int(round(total * share))))
+        assert all(spans[r][1] == spans[r + 1][0] for r in range(world - 1)) and spans[-1][1] == total
+        others = [hi - lo for lo, hi in spans[1:]]
+        assert max(others) - min(others) <= 1
+    assert shard_range(65536, 0, 8, 0.078125) == (0, 5120) and shard_range(65536, 1, 8, 0.078125) == (5120, 5120 + 8631)
 
 
 @pytest.mark.timeout(180)
