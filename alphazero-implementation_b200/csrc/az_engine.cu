@@ -55,6 +55,7 @@ struct Arena {
     uint4 *M;  // x = N, y = prior bits, z = first child, w = 0
     const double *rcp;  // rcp[d] = RN(1/d), d = 0 .. S+1 (rcp[0] unused)
     const double *sqt;  // sqt[n] = RN(sqrt(n))
+    const double2 *t2;  // t2[n] = {rcp[n + 1], sqt[n]}: what a child with n visits contributes to a level, in one 16-byte load
     uint64_t *root_bb0, *root_bb1;
     uint8_t *root_player;
     uint32_t *used;
@@ -109,6 +110,27 @@ __device__ __forceinline__ double puct_score(uint32_t n, double w, float p, doub
     return __dadd_rn(q, u);
 }
 
+// The tables a kernel reads, in whatever memory they live (shared memory in the fused kernel when they fit, else global).
+struct Tabs {
+    const double *rcp;   // rcp[d]
+    const double2 *t2;   // {rcp[n + 1], sqt[n]}
+};
+
+// x / d with the reciprocal already in a register (same arithmetic as div_tab)
+__device__ __forceinline__ double div_r(double x, uint32_t d, double r) {
+    const double nd = -(double)d;
+    double q = __dmul_rn(x, r);
+    q = __fma_rn(__fma_rn(nd, q, x), r, q);
+    return __fma_rn(__fma_rn(nd, q, x), r, q);
+}
+
+// puct_score with both reciprocals fetched together with the child record (r1 = RN(1/(1+n)), r0 = RN(1/n))
+__device__ __forceinline__ double puct_score_pre(uint32_t n, double w, float p, double sq, double c_puct, double r1, double r0) {
+    const double u = div_r(__dmul_rn(__dmul_rn(c_puct, (double)p), sq), 1u + n, r1);
+    const double q = (w == 0.0) ? 0.0 : div_r(w, n, r0);
+    return __dadd_rn(q, u);
+}
+
 // first maximum over the 7 columns of an 8-lane quarter: a butterfly over (score, column) pairs - the larger score wins,
 // equal scores keep the lower column (the reference's strict `>` scan keeps the first maximum).  Every lane of the
 // quarter ends with the same column.  (Carrying the column costs one extra shuffle per round, issued alongside the
@@ -156,6 +178,7 @@ __device__ __forceinline__ int argmax_first_ballot(double score, int sub) {
 struct Child {  // the record of "my" column's child at the current node
     double w;
     double sq;  // sqrt(n): the sqrt(node.visit_count) of the NEXT level if this child is selected, fetched ahead of the need
+    double r1, r0;  // RN(1/(1+n)), RN(1/n): the two reciprocals of this child's PUCT score (latency variant only)
     uint32_t n, cb;
     float p;
 };
@@ -192,7 +215,7 @@ struct TreeMem {
 #endif
 
 template <bool LAT>
-__device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx, const double *__restrict__ sqt) {
+__device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx, const Tabs &tb) {
     Child ch;
     uint4 m;
     AZ_CHECK_NODE(tm, idx);
@@ -209,7 +232,16 @@ __device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx, con
         ch.p = __uint_as_float(m.y);
         ch.cb = m.z;
     }
-    ch.sq = LAT ? sqt[ch.n] : 0.0;
+    // latency variant: everything the score needs from the tables is requested the moment the visit count is known, in one
+    // round (the reciprocals used to be fetched inside the score, the second behind the first division's dependent chain)
+    if (LAT) {
+        const double2 e = tb.t2[ch.n];
+        ch.r1 = e.x;
+        ch.sq = e.y;
+        ch.r0 = tb.rcp[ch.n];
+    } else {
+        ch.r1 = ch.r0 = ch.sq = 0.0;
+    }
     return ch;
 }
 
@@ -260,7 +292,7 @@ struct Leaf {
 // and nothing else hides it); LAT = false: fewer shuffles and loads per level, for launches that fill the issue slots.
 // Measured on B200 (sims/s, 200 sims/move): 4096 trees 1.97e9 vs 1.81e9; 16384 trees 3.78e9 vs 4.45e9.
 template <bool LAT>
-__device__ __forceinline__ Leaf descend(const TreeMem &tm, const double *__restrict__ rcp, const double *__restrict__ sqt,
+__device__ __forceinline__ Leaf descend(const TreeMem &tm, const Tabs &tb,
                                         uint64_t rb0, uint64_t rb1, int rpl, double c_puct, uint32_t cb,
                                         double sq_parent, unsigned legal, Child ch, bool alive, bool writer,
                                         uint32_t *path, uint32_t &levels, uint32_t &scanned) {
@@ -280,7 +312,7 @@ __device__ __forceinline__ Leaf descend(const TreeMem &tm, const double *__restr
     // The loop body is straight-line code: four trees share a warp and an idle eighth lane sits in every tree, so every
     // `if` here would be a divergent branch with its reconvergence barrier on the dependent chain.  Lanes of finished
     // trees keep computing on stale (valid) values and every update of the leaf is masked by `go`.
-    // Dependent chain of one level: child record -> rcp[n + 1] -> PUCT (6 fp64 operations) -> 3 butterfly rounds ->
+    // Dependent chain of one level: child record -> {rcp[n + 1], sqrt(n)}, rcp[n] -> PUCT (6 fp64 operations) -> 3 butterfly rounds ->
     // shuffle of the winner's first-child index -> next child record.  Everything else hangs off that chain: the
     // winner's sqrt comes with its record, the next node's legal mask is the current one minus the winning column if
     // that column fills up (known before the winner is), and the board update runs in the shadow of the next load.
@@ -289,19 +321,20 @@ __device__ __forceinline__ Leaf descend(const TreeMem &tm, const double *__restr
         // columns with exactly five stones: one more and they leave the legal mask
         const bool fills = ((occ >> (c4::STRIDE * c + 4)) & 3ull) == 1ull;
         const unsigned fill_mask = (__ballot_sync(FULL, fills) >> sub) & 0x7Fu;
-        const double s = puct_score(ch.n, ch.w, ch.p, sq_parent, c_puct, rcp);
+        const double s = LAT ? puct_score_pre(ch.n, ch.w, ch.p, sq_parent, c_puct, ch.r1, ch.r0)
+                             : puct_score(ch.n, ch.w, ch.p, sq_parent, c_puct, tb.rcp);
         const double masked = (go && my_legal) ? s : -INFINITY;
         const int bc = LAT ? argmax_first(masked, c) : argmax_first_ballot(masked, sub);
         const uint32_t cb_sel = __shfl_sync(FULL, ch.cb, sub + bc);
         if (LAT) sq_parent = __shfl_sync(FULL, ch.sq, sub + bc);
-        else sq_parent = sqt[__shfl_sync(FULL, ch.n, sub + bc)];
+        else sq_parent = tb.t2[__shfl_sync(FULL, ch.n, sub + bc)].y;
         const unsigned bcbit = 1u << bc;
         const unsigned lg = legal & ~(fill_mask & bcbit);  // legal mask of the node being entered
         const bool go_next = go && cb_sel != 0;
         const bool can = (lg >> c) & 1u;
-        const Child nxt = load_child<LAT>(tm, (go_next && can) ? cb_sel + __popc(lg & below) : 0u, sqt);
+        const Child nxt = load_child<LAT>(tm, (go_next && can) ? cb_sel + __popc(lg & below) : 0u, tb);
         // Action.sample_next_state(): drop in column bc, flip the side to move
-        const uint64_t bit = go ? c4::drop_bit(occ, bc) : 0ull;
+        const uint64_t bit = c4::drop_bit(occ, bc) & (0ull - (uint64_t)go);  // arithmetic mask: an `if (go)` here became a divergent branch
         const uint64_t bit0 = L.pl == 0 ? bit : 0ull;
         L.b0 |= bit0;
         L.b1 |= bit ^ bit0;
@@ -380,8 +413,9 @@ struct MoveArgs {
     int step, initpl;
 };
 
-template <int TPW, int EVAL, bool LAT, bool MOVE>
-__global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, double c_puct, int K, int tabs_in_smem, MoveArgs mv) {
+// TSM: the tables live in shared memory (a compile-time fact, so that the loads are LDS, not generic loads)
+template <int TPW, int EVAL, bool LAT, bool MOVE, bool TSM>
+__global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, double c_puct, int K, MoveArgs mv) {
     constexpr int TREES = 2 * TPW;  // per 64-thread block
     constexpr int NL = 32 / TPW;    // lanes per tree
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -394,16 +428,20 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     const int t = blockIdx.x * TREES + tib;
     // 1/d and sqrt(n) tables: every level's chain goes through them, and in L1 they compete with the node traffic (an L1 miss
     // costs an L2 round trip on the chain), so the block keeps its own copy in shared memory when they are small enough
-    const double *rcp = a.rcp, *sqt = a.sqt;
-    if (tabs_in_smem) {  // before any warp can leave: both warps of the block take part
-        double *s_tab = reinterpret_cast<double *>(smem_raw + (size_t)TREES * (K * sizeof(HotNode) + PATH_STRIDE * sizeof(uint32_t)));
+    Tabs tb;
+    if (TSM) {  // before any warp can leave: both warps of the block take part
+        double2 *s_t2 = reinterpret_cast<double2 *>(smem_raw + (size_t)TREES * (K * sizeof(HotNode) + PATH_STRIDE * sizeof(uint32_t)));
+        double *s_rcp = reinterpret_cast<double *>(s_t2 + a.tab_n);
         for (int i = threadIdx.x; i < a.tab_n; i += 64) {
-            s_tab[i] = a.rcp[i];
-            s_tab[a.tab_n + i] = a.sqt[i];
+            s_t2[i] = a.t2[i];
+            s_rcp[i] = a.rcp[i];
         }
-        rcp = s_tab;
-        sqt = s_tab + a.tab_n;
+        tb.t2 = s_t2;
+        tb.rcp = s_rcp;
         __syncthreads();
+    } else {
+        tb.t2 = a.t2;
+        tb.rcp = a.rcp;
     }
     const bool alive = (t < n_active) && (a.tree_err[t < n_active ? t : 0] == 0);
     const int lit = lane & (NL - 1);
@@ -463,9 +501,9 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     const unsigned r_legal = (__ballot_sync(FULL, r_can) >> sub) & 0x7Fu;
     const int r_j = __popc(r_legal & ((1u << c) - 1u));
     Child rch;
-    rch.w = 0.0; rch.sq = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
-    if (alive && root_cb != 0 && r_can) rch = load_child<LAT>(tm, root_cb + r_j, sqt);
-    double root_sq = sqt[root_n];
+    rch.w = 0.0; rch.sq = 0.0; rch.r1 = 1.0; rch.r0 = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
+    if (alive && root_cb != 0 && r_can) rch = load_child<LAT>(tm, root_cb + r_j, tb);
+    double root_sq = tb.t2[root_n].y;
     if (writer) path[0] = 0;
 
 #ifdef AZ_TRUNK_CLOCKS
@@ -473,8 +511,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
 #endif
     for (int s = 0; s < S; ++s) {
         RCLK(c0);
-        Leaf L = descend<LAT>(tm, rcp, sqt, rb0, rb1, rpl, c_puct, root_cb, root_sq, r_legal, rch, alive, writer, path, levels,
-                         scanned);
+        Leaf L = descend<LAT>(tm, tb, rb0, rb1, rpl, c_puct, root_cb, root_sq, r_legal, rch, alive, writer, path, levels, scanned);
         RCLK(c1);
         RACC(0, c1, c0);
         // Straight-line from here on as well (the four trees of a warp end in different cases).
@@ -531,9 +568,14 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
         RACC(1, c2, c1);
         // Backup, part 2.  Registers: root and the chosen root child; memory: every node on the path.
         root_n += (uint32_t)alive;
-        root_sq = sqt[root_n];  // next simulation's sqrt(N_root) and sqrt(N_child): loaded behind the backup
+        root_sq = tb.t2[root_n].y;  // next simulation's sqrt(N_root) and the root child's table entries: loaded behind the backup
         rch.n += (uint32_t)(alive && mine);
-        if (LAT) rch.sq = sqt[rch.n];
+        if (LAT) {
+            const double2 e = tb.t2[rch.n];
+            rch.r1 = e.x;
+            rch.sq = e.y;
+            rch.r0 = tb.rcp[rch.n];
+        }
         rch.w = (alive && mine) ? __dadd_rn(rch.w, backup_sign(v, L.depth, 1, L.term)) : rch.w;
         if (own) {
             const double w_new = __dadd_rn(w_old, backup_sign(v, L.depth, lit, L.term));
@@ -711,12 +753,14 @@ __device__ __forceinline__ void select_body(const Arena &a, int n_active, double
     const bool r_can = (c < c4::W) && !(((rb0 | rb1) >> (c4::STRIDE * c + 5)) & 1ull);
     const unsigned r_legal = (__ballot_sync(FULL, r_can) >> sub) & 0x7Fu;
     Child rch;
-    rch.w = 0.0; rch.sq = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
-    if (alive && rm.z != 0 && r_can) rch = load_child<LAT>(tm, rm.z + __popc(r_legal & ((1u << c) - 1u)), a.sqt);
+    rch.w = 0.0; rch.sq = 0.0; rch.r1 = 1.0; rch.r0 = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
+    Tabs tb;
+    tb.rcp = a.rcp;
+    tb.t2 = a.t2;
+    if (alive && rm.z != 0 && r_can) rch = load_child<LAT>(tm, rm.z + __popc(r_legal & ((1u << c) - 1u)), tb);
     if (writer) path[0] = 0;
     uint32_t levels = 0, scanned = 0;
-    Leaf L = descend<LAT>(tm, a.rcp, a.sqt, rb0, rb1, rpl, c_puct, rm.z, __ldg(a.sqt + rm.x), r_legal, rch, alive, writer, path, levels,
-                     scanned);
+    Leaf L = descend<LAT>(tm, tb, rb0, rb1, rpl, c_puct, rm.z, __ldg(a.sqt + rm.x), r_legal, rch, alive, writer, path, levels, scanned);
     if (writer) {
         a.leaf_node[t] = L.node;
         a.leaf_bb0[t] = L.b0;
@@ -1293,11 +1337,12 @@ k_sample_moves(Arena a, int n, const double *__restrict__ uniforms, uint8_t *fin
     }
 }
 
-__global__ void __launch_bounds__(256) k_init_tables(double *rcp, double *sqt, int n) {
+__global__ void __launch_bounds__(256) k_init_tables(double *rcp, double *sqt, double2 *t2, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     rcp[i] = i ? __drcp_rn((double)i) : 0.0;
     sqt[i] = __dsqrt_rn((double)i);
+    t2[i] = make_double2(__drcp_rn((double)(i + 1)), __dsqrt_rn((double)i));
 }
 
 __global__ void __launch_bounds__(256)
@@ -1515,8 +1560,9 @@ int32_t az_create(const az_config *cfg, az_engine **out) {
 #define AL(ptr, count) if (rc == AZ_OK) rc = dev_alloc(h, &(ptr), (size_t)(count))
     AL(a.W, nodes); AL(a.M, nodes);
     double *d_rcp = nullptr, *d_sqt = nullptr;
+    double2 *d_t2 = nullptr;
     a.tab_n = cfg->num_simulations + 8;
-    AL(d_rcp, a.tab_n); AL(d_sqt, a.tab_n);
+    AL(d_rcp, a.tab_n); AL(d_sqt, a.tab_n); AL(d_t2, a.tab_n);
     AL(a.root_bb0, E); AL(a.root_bb1, E); AL(a.root_player, E); AL(a.used, E); AL(a.tree_err, E);
     AL(a.leaf_node, E); AL(a.leaf_bb0, E); AL(a.leaf_bb1, E); AL(a.leaf_player, E); AL(a.leaf_status, E);
     AL(a.leaf_depth, E); AL(a.path, (size_t)E * PATH_STRIDE); AL(a.tstats, (size_t)E * NSTAT);
@@ -1539,7 +1585,8 @@ int32_t az_create(const az_config *cfg, az_engine **out) {
     }
     a.rcp = d_rcp;
     a.sqt = d_sqt;
-    k_init_tables<<<blocks_for(a.tab_n, 256), 256>>>(d_rcp, d_sqt, a.tab_n);
+    a.t2 = d_t2;
+    k_init_tables<<<blocks_for(a.tab_n, 256), 256>>>(d_rcp, d_sqt, d_t2, a.tab_n);
     h->launches++;
     cudaMemset(a.tstats, 0, (size_t)E * NSTAT * sizeof(uint32_t));
     cudaMemset(h->rings[0].ring, 0, 4 * sizeof(unsigned long long));
@@ -1761,8 +1808,8 @@ static int32_t run_sims_impl(az_engine *h, int32_t num_sims, int32_t eval_kind, 
     const int blocks = blocks_for(n, trees_per_block);
     int per_sm = (blocks + h->num_sms - 1) / h->num_sms;
     if (per_sm > 14) per_sm = 14;  // register-limited residency of 64-thread blocks (72 registers)
-    const int tabs_in_smem = (size_t)h->a.tab_n * 16 <= 4096 ? 1 : 0;
-    const size_t tab_bytes = tabs_in_smem ? (size_t)h->a.tab_n * 16 : 0;
+    const int tabs_in_smem = (size_t)h->a.tab_n * 24 <= 6144 ? 1 : 0;  // {1/(n+1), sqrt(n)} pairs + 1/n: 24 bytes per entry
+    const size_t tab_bytes = tabs_in_smem ? (size_t)h->a.tab_n * 24 : 0;
     // hot-node count K: the largest multiple of 8 such that every block of the grid stays resident (228 KB of shared memory per SM,
     // 1 KB of it reserved per resident block; one block may use up to 200 KB) - measured monotonic: more hot nodes, faster
     int K = 0;
@@ -1785,10 +1832,15 @@ static int32_t run_sims_impl(az_engine *h, int32_t num_sims, int32_t eval_kind, 
     mv.init1 = h->init1;
     mv.step = h->step;
     mv.initpl = h->initpl;
-#define AZ_RUN2(TPW_, EV_, LAT_, MOVE_)                                                                                               \
-    do {                                                                                                                              \
-        AZ_CUDA(h, cudaFuncSetAttribute(k_run_sims<TPW_, EV_, LAT_, MOVE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_run_sims<TPW_, EV_, LAT_, MOVE_><<<blocks, 64, smem, S(stream)>>>(h->a, n, num_sims, c, K, tabs_in_smem, mv);               \
+#define AZ_RUN3(TPW_, EV_, LAT_, MOVE_, TSM_)                                                                                               \
+    do {                                                                                                                                    \
+        AZ_CUDA(h, cudaFuncSetAttribute(k_run_sims<TPW_, EV_, LAT_, MOVE_, TSM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_run_sims<TPW_, EV_, LAT_, MOVE_, TSM_><<<blocks, 64, smem, S(stream)>>>(h->a, n, num_sims, c, K, mv);                             \
+    } while (0)
+#define AZ_RUN2(TPW_, EV_, LAT_, MOVE_)                       \
+    do {                                                      \
+        if (tabs_in_smem) AZ_RUN3(TPW_, EV_, LAT_, MOVE_, true); \
+        else AZ_RUN3(TPW_, EV_, LAT_, MOVE_, false);          \
     } while (0)
 #define AZ_RUN1(TPW_, EV_, LAT_)                  \
     do {                                          \
@@ -1810,6 +1862,7 @@ static int32_t run_sims_impl(az_engine *h, int32_t num_sims, int32_t eval_kind, 
 #undef AZ_RUN
 #undef AZ_RUN1
 #undef AZ_RUN2
+#undef AZ_RUN3
     h->last_hot_nodes = K;
     h->sims_done += num_sims;
     AZ_LAUNCH_CHECK(h, "k_run_sims");
