@@ -110,24 +110,35 @@ __device__ __forceinline__ double puct_score(uint32_t n, double w, float p, doub
     return __dadd_rn(q, u);
 }
 
+struct Child {  // the record of "my" column's child at the current node
+    double w;
+    double sq;  // sqrt(n): the sqrt(node.visit_count) of the NEXT level if this child is selected, fetched ahead of the need
+    double r1, r0;  // RN(1/(1+n)), RN(1/n): the two reciprocals of this child's PUCT score (latency variant only)
+    double x;       // (c * prior) * sqrt(N_parent): the numerator of U, computed while the table entries are in flight (latency variant)
+    double d1, d0;  // 1 + n, n as doubles (the divisions' residual steps), converted ahead of the need (latency variant)
+    uint32_t n, cb;
+    float p;
+};
+
 // The tables a kernel reads, in whatever memory they live (shared memory in the fused kernel when they fit, else global).
 struct Tabs {
     const double *rcp;   // rcp[d]
     const double2 *t2;   // {rcp[n + 1], sqt[n]}
 };
 
-// x / d with the reciprocal already in a register (same arithmetic as div_tab)
-__device__ __forceinline__ double div_r(double x, uint32_t d, double r) {
-    const double nd = -(double)d;
+// x / d with the reciprocal r = RN(1/d) and d as a double already in registers (same arithmetic as div_tab)
+__device__ __forceinline__ double div_r(double x, double d, double r) {
+    const double nd = -d;  // folds into the FMA's operand modifier
     double q = __dmul_rn(x, r);
     q = __fma_rn(__fma_rn(nd, q, x), r, q);
     return __fma_rn(__fma_rn(nd, q, x), r, q);
 }
 
-// puct_score with both reciprocals fetched together with the child record (r1 = RN(1/(1+n)), r0 = RN(1/n))
-__device__ __forceinline__ double puct_score_pre(uint32_t n, double w, float p, double sq, double c_puct, double r1, double r0) {
-    const double u = div_r(__dmul_rn(__dmul_rn(c_puct, (double)p), sq), 1u + n, r1);
-    const double q = (w == 0.0) ? 0.0 : div_r(w, n, r0);
+// puct_score with everything but the two divisions done when the child record arrived (load_child): the numerator
+// x = (c * P) * sqrt(N), both reciprocals and both divisors as doubles
+__device__ __forceinline__ double puct_score_pre(const Child &ch) {
+    const double u = div_r(ch.x, ch.d1, ch.r1);
+    const double q = (ch.w == 0.0) ? 0.0 : div_r(ch.w, ch.d0, ch.r0);
     return __dadd_rn(q, u);
 }
 
@@ -175,13 +186,6 @@ __device__ __forceinline__ int argmax_first_ballot(double score, int sub) {
     return __ffs((eq >> sub) & 0xFFu) - 1;
 }
 
-struct Child {  // the record of "my" column's child at the current node
-    double w;
-    double sq;  // sqrt(n): the sqrt(node.visit_count) of the NEXT level if this child is selected, fetched ahead of the need
-    double r1, r0;  // RN(1/(1+n)), RN(1/n): the two reciprocals of this child's PUCT score (latency variant only)
-    uint32_t n, cb;
-    float p;
-};
 
 // One tree's node storage as seen by a kernel: nodes [0, K) may live in shared memory for the duration
 // of a launch (the fused kernel keeps the first, hottest nodes of every tree there: node indices grow
@@ -215,7 +219,7 @@ struct TreeMem {
 #endif
 
 template <bool LAT>
-__device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx, const Tabs &tb) {
+__device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx, const Tabs &tb, double c_puct, double sq_parent) {
     Child ch;
     uint4 m;
     AZ_CHECK_NODE(tm, idx);
@@ -239,8 +243,11 @@ __device__ __forceinline__ Child load_child(const TreeMem &tm, uint32_t idx, con
         ch.r1 = e.x;
         ch.sq = e.y;
         ch.r0 = tb.rcp[ch.n];
+        ch.x = __dmul_rn(__dmul_rn(c_puct, (double)ch.p), sq_parent);
+        ch.d1 = (double)(1u + ch.n);
+        ch.d0 = (double)ch.n;
     } else {
-        ch.r1 = ch.r0 = ch.sq = 0.0;
+        ch.r1 = ch.r0 = ch.sq = ch.x = ch.d1 = ch.d0 = 0.0;
     }
     return ch;
 }
@@ -321,8 +328,7 @@ __device__ __forceinline__ Leaf descend(const TreeMem &tm, const Tabs &tb,
         // columns with exactly five stones: one more and they leave the legal mask
         const bool fills = ((occ >> (c4::STRIDE * c + 4)) & 3ull) == 1ull;
         const unsigned fill_mask = (__ballot_sync(FULL, fills) >> sub) & 0x7Fu;
-        const double s = LAT ? puct_score_pre(ch.n, ch.w, ch.p, sq_parent, c_puct, ch.r1, ch.r0)
-                             : puct_score(ch.n, ch.w, ch.p, sq_parent, c_puct, tb.rcp);
+        const double s = LAT ? puct_score_pre(ch) : puct_score(ch.n, ch.w, ch.p, sq_parent, c_puct, tb.rcp);
         const double masked = (go && my_legal) ? s : -INFINITY;
         const int bc = LAT ? argmax_first(masked, c) : argmax_first_ballot(masked, sub);
         const uint32_t cb_sel = __shfl_sync(FULL, ch.cb, sub + bc);
@@ -332,7 +338,7 @@ __device__ __forceinline__ Leaf descend(const TreeMem &tm, const Tabs &tb,
         const unsigned lg = legal & ~(fill_mask & bcbit);  // legal mask of the node being entered
         const bool go_next = go && cb_sel != 0;
         const bool can = (lg >> c) & 1u;
-        const Child nxt = load_child<LAT>(tm, (go_next && can) ? cb_sel + __popc(lg & below) : 0u, tb);
+        const Child nxt = load_child<LAT>(tm, (go_next && can) ? cb_sel + __popc(lg & below) : 0u, tb, c_puct, sq_parent);
         // Action.sample_next_state(): drop in column bc, flip the side to move
         const uint64_t bit = c4::drop_bit(occ, bc) & (0ull - (uint64_t)go);  // arithmetic mask: an `if (go)` here became a divergent branch
         const uint64_t bit0 = L.pl == 0 ? bit : 0ull;
@@ -501,9 +507,9 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
     const unsigned r_legal = (__ballot_sync(FULL, r_can) >> sub) & 0x7Fu;
     const int r_j = __popc(r_legal & ((1u << c) - 1u));
     Child rch;
-    rch.w = 0.0; rch.sq = 0.0; rch.r1 = 1.0; rch.r0 = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
-    if (alive && root_cb != 0 && r_can) rch = load_child<LAT>(tm, root_cb + r_j, tb);
+    rch.w = 0.0; rch.sq = 0.0; rch.r1 = 1.0; rch.r0 = 0.0; rch.x = 0.0; rch.d1 = 1.0; rch.d0 = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
     double root_sq = tb.t2[root_n].y;
+    if (alive && root_cb != 0 && r_can) rch = load_child<LAT>(tm, root_cb + r_j, tb, c_puct, root_sq);
     if (writer) path[0] = 0;
 
 #ifdef AZ_TRUNK_CLOCKS
@@ -575,6 +581,9 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
             rch.r1 = e.x;
             rch.sq = e.y;
             rch.r0 = tb.rcp[rch.n];
+            rch.x = __dmul_rn(__dmul_rn(c_puct, (double)rch.p), root_sq);  // sqrt(N_root) changes with every simulation
+            rch.d1 = (double)(1u + rch.n);
+            rch.d0 = (double)rch.n;
         }
         rch.w = (alive && mine) ? __dadd_rn(rch.w, backup_sign(v, L.depth, 1, L.term)) : rch.w;
         if (own) {
@@ -753,14 +762,15 @@ __device__ __forceinline__ void select_body(const Arena &a, int n_active, double
     const bool r_can = (c < c4::W) && !(((rb0 | rb1) >> (c4::STRIDE * c + 5)) & 1ull);
     const unsigned r_legal = (__ballot_sync(FULL, r_can) >> sub) & 0x7Fu;
     Child rch;
-    rch.w = 0.0; rch.sq = 0.0; rch.r1 = 1.0; rch.r0 = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
+    rch.w = 0.0; rch.sq = 0.0; rch.r1 = 1.0; rch.r0 = 0.0; rch.x = 0.0; rch.d1 = 1.0; rch.d0 = 0.0; rch.n = 0; rch.cb = 0; rch.p = 0.0f;
     Tabs tb;
     tb.rcp = a.rcp;
     tb.t2 = a.t2;
-    if (alive && rm.z != 0 && r_can) rch = load_child<LAT>(tm, rm.z + __popc(r_legal & ((1u << c) - 1u)), tb);
+    const double root_sq = __ldg(a.sqt + rm.x);
+    if (alive && rm.z != 0 && r_can) rch = load_child<LAT>(tm, rm.z + __popc(r_legal & ((1u << c) - 1u)), tb, c_puct, root_sq);
     if (writer) path[0] = 0;
     uint32_t levels = 0, scanned = 0;
-    Leaf L = descend<LAT>(tm, tb, rb0, rb1, rpl, c_puct, rm.z, __ldg(a.sqt + rm.x), r_legal, rch, alive, writer, path, levels, scanned);
+    Leaf L = descend<LAT>(tm, tb, rb0, rb1, rpl, c_puct, rm.z, root_sq, r_legal, rch, alive, writer, path, levels, scanned);
     if (writer) {
         a.leaf_node[t] = L.node;
         a.leaf_bb0[t] = L.b0;
