@@ -146,6 +146,9 @@ __device__ __forceinline__ double puct_score_pre(const Child &ch) {
 // equal scores keep the lower column (the reference's strict `>` scan keeps the first maximum).  Every lane of the
 // quarter ends with the same column.  (Carrying the column costs one extra shuffle per round, issued alongside the
 // score's two, and saves the equality ballot + find-first-set that would follow a plain max.)
+// The score's own chain is shuffle -> compare -> select per round (on a tie either operand is the same value); the tie-break
+// only steers the column, whose chain is shuffle -> select with the predicates already computed - two chained fp64 compares
+// per round are off the score's path.
 __device__ __forceinline__ int argmax_first(double score, int c) {
     double m = score;
     int mi = c;
@@ -153,21 +156,9 @@ __device__ __forceinline__ int argmax_first(double score, int c) {
     for (int off = 4; off >= 1; off >>= 1) {
         const double o = __shfl_xor_sync(FULL, m, off);
         const int oi = __shfl_xor_sync(FULL, mi, off);
-        // take = (o > m) || (o == m && oi < mi), with the three compares issued side by side (the compiler's own
-        // short-circuit form chains them behind each other on the critical path)
-        int take;
-        asm("{\n\t"
-            ".reg .pred gt, eq, lt;\n\t"
-            "setp.gt.f64 gt, %1, %2;\n\t"
-            "setp.eq.f64 eq, %1, %2;\n\t"
-            "setp.lt.s32 lt, %3, %4;\n\t"
-            "and.pred eq, eq, lt;\n\t"
-            "or.pred gt, gt, eq;\n\t"
-            "selp.s32 %0, 1, 0, gt;\n\t"
-            "}"
-            : "=r"(take)
-            : "d"(o), "d"(m), "r"(oi), "r"(mi));
-        m = take ? o : m;
+        const bool gt = o > m;
+        const bool take = gt || (o == m && oi < mi);
+        m = gt ? o : m;
         mi = take ? oi : mi;
     }
     return mi;
@@ -338,7 +329,12 @@ __device__ __forceinline__ Leaf descend(const TreeMem &tm, const Tabs &tb,
         const unsigned lg = legal & ~(fill_mask & bcbit);  // legal mask of the node being entered
         const bool go_next = go && cb_sel != 0;
         const bool can = (lg >> c) & 1u;
-        const Child nxt = load_child<LAT>(tm, (go_next && can) ? cb_sel + __popc(lg & below) : 0u, tb, c_puct, sq_parent);
+        // The record to fetch: the winner's children start at cb_sel, this lane's is the popc-th of them.  Lanes that are not
+        // legal there, or whose tree has finished, read node 0 (mask known before cb_sel arrives); if the winner turns out to
+        // be unexpanded (cb_sel == 0) the lane reads node popc <= 6 of its own tree - the root or one of the root's children,
+        // all initialised, since a descent only runs below an expanded root - and nothing of it is used (go_next is false).
+        const uint32_t pre = (go && can) ? 0xFFFFFFFFu : 0u;
+        const Child nxt = load_child<LAT>(tm, (cb_sel + (uint32_t)__popc(lg & below)) & pre, tb, c_puct, sq_parent);
         // Action.sample_next_state(): drop in column bc, flip the side to move
         const uint64_t bit = c4::drop_bit(occ, bc) & (0ull - (uint64_t)go);  // arithmetic mask: an `if (go)` here became a divergent branch
         const uint64_t bit0 = L.pl == 0 ? bit : 0ull;
