@@ -356,12 +356,10 @@ __device__ __forceinline__ Leaf descend(const TreeMem &tm, const Tabs &tb,
     }
     // Node.is_terminal of the leaf (node.py:61-63).  Interior nodes are never terminal (a terminal
     // node is never expanded), so only the last mover's stones need the line test.
-    L.win = false;
-    L.term = false;
-    if (L.depth > 0) {
-        L.win = c4::has4_nb(L.pl ? L.b0 : L.b1);  // mover = pl ^ 1
-        L.term = L.win || c4::is_full(L.b0 | L.b1);
-    }
+    // At depth 0 the leaf is the root itself, which has not ended (such trees are not alive): the test is false there as well,
+    // so it runs unconditionally (an `if (depth > 0)` here is a branch with a reconvergence point on every simulation's chain).
+    L.win = c4::has4_nb(L.pl ? L.b0 : L.b1);  // mover = pl ^ 1
+    L.term = L.win || c4::is_full(L.b0 | L.b1);
     return L;
 }
 
@@ -408,6 +406,8 @@ __device__ __forceinline__ void reset_tree(const Arena &a, int t) {
 // MOVE = true: the launch also plays the self-play move of every tree (what k_sample_moves does) - the root's child
 // statistics are still in registers, the step's uniform and the game-log position were fetched at kernel entry, and the
 // tree is discarded anyway (node.py:37-41), so the hot prefix is not written back.
+__constant__ float c_inv_k[8] = {0.0f, 1.0f, 1.0f / 2.0f, 1.0f / 3.0f, 1.0f / 4.0f, 1.0f / 5.0f, 1.0f / 6.0f, 1.0f / 7.0f};
+
 struct MoveArgs {
     const double *uniforms;
     uint8_t *finished;
@@ -539,9 +539,8 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
         const int j = __popc(legal & ((1u << c) - 1u));
         float prior, val;
         if (EVAL == AZ_EVAL_UNIFORM) {
-            // fp32(1) / fp32(k), k = 1..7: compile-time constants picked by a 3-level select tree (no MUFU slow path)
-            prior = (k & 4) ? ((k & 2) ? ((k & 1) ? 1.0f / 7.0f : 1.0f / 6.0f) : ((k & 1) ? 1.0f / 5.0f : 1.0f / 4.0f))
-                            : ((k & 2) ? ((k & 1) ? 1.0f / 3.0f : 1.0f / 2.0f) : 1.0f);
+            // fp32(1) / fp32(k), k = 1..7: compile-time constants from a constant-memory table (no MUFU slow path, no branches)
+            prior = c_inv_k[k & 7];
             val = 0.0f;
         } else {
             const uint64_t h = azeval::board_hash(L.b0, L.b1, L.pl);
@@ -581,7 +580,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
             rch.d1 = (double)(1u + rch.n);
             rch.d0 = (double)rch.n;
         }
-        rch.w = (alive && mine) ? __dadd_rn(rch.w, backup_sign(v, L.depth, 1, L.term)) : rch.w;
+        rch.w = __dadd_rn(rch.w, (alive && mine) ? backup_sign(v, L.depth, 1, L.term) : 0.0);  // + 0.0: value sums are never -0.0
         if (own) {
             const double w_new = __dadd_rn(w_old, backup_sign(v, L.depth, lit, L.term));
             if (my_hot) {
