@@ -386,7 +386,7 @@ __device__ __forceinline__ double backup_sign(double v, int depth, int i, bool l
 // The root's scalars (N, first child, legal mask) and each lane's root-child record live in registers
 // for the whole launch, the first K nodes of every tree in shared memory (loaded at entry, written back
 // at exit unless the launch also plays the move), the rest in HBM.  Dynamic shared memory: [TREES][K] HotNode (16 B),
-// [TREES][44] u32 path, then the 1/d and sqrt tables (2 x tab_n f64) when they fit.
+// [TREES][44] u32 path, then (TSM) the tables: [tab_n] {1/(n+1), sqrt n} pairs (16 B), [tab_n] 1/d (8 B).
 #ifdef AZ_TRUNK_CLOCKS
 __device__ long long g_run_clk[8];
 #define RCLK(var) const long long var = clock64()
