@@ -96,6 +96,24 @@ class ReplayBuffer:
         value = torch.cat([torch.repeat_interleave(c.ep_outcome[c.first:].to(torch.float32), c.ep_len[c.first:], dim=0) for c in cs])
         return bb0, bb1, pl, policy, value
 
+    def to_episode_batch(self) -> EpisodeBatch:
+        """The deque's content, oldest episode first, as flat host arrays (what `DataModule._save_episodes` iterates over,
+        datamodule.py:71-80).  Slots and steps of the episodes are not kept by the buffer: -1 / 0."""
+        cs = list(self.chunks)
+        if not cs:
+            z = np.zeros(0, np.int64)
+            return EpisodeBatch(z.astype(np.int32), z.astype(np.int32), z.astype(np.int32), z, np.zeros((0, 2), np.int8),
+                                z.astype(np.uint64), z.astype(np.uint64), z.astype(np.uint8), np.zeros((0, 7), np.int32))
+        ep_len = torch.cat([c.ep_len[c.first:] for c in cs]).cpu().numpy().astype(np.int32)
+        outcome = torch.cat([c.ep_outcome[c.first:] for c in cs]).cpu().numpy().astype(np.int8)
+        bb0 = torch.cat([c.s_bb0[c.first_sample:] for c in cs]).cpu().numpy().view(np.uint64)
+        bb1 = torch.cat([c.s_bb1[c.first_sample:] for c in cs]).cpu().numpy().view(np.uint64)
+        pl = torch.cat([c.s_player[c.first_sample:] for c in cs]).cpu().numpy().astype(np.uint8)
+        counts = torch.cat([c.s_counts[c.first_sample:] for c in cs]).cpu().numpy().astype(np.int32)
+        off = np.cumsum(ep_len, dtype=np.int64) - ep_len
+        n = ep_len.shape[0]
+        return EpisodeBatch(np.full(n, -1, np.int32), np.zeros(n, np.int32), ep_len, off, outcome, bb0, bb1, pl, counts)
+
     def batches(self, layout: int, batch_size: int = 32, shuffle: bool = True, generator: torch.Generator | None = None):
         """Yield (x, policy_target, value_target) minibatches on the device (DataLoader(batch 32, shuffle), datamodule.py:124-130)."""
         bb0, bb1, pl, policy, value = self.tensors()

@@ -131,13 +131,16 @@ class Trainer:
     def train(self, *, num_iterations: int, episodes_per_iter: int, simulations_per_episode: int, epochs_per_iter: int,
               initial_state, buffer_size: int, save_every_n_iterations: int = 0, batch_size: int = 32, seed: int = 0,
               overlap: bool = True, inference_dtype: torch.dtype | None = None, precision: str = "32-true",
-              cuda_graph: bool = True, trainer_share: float | None = None):
+              cuda_graph: bool = True, trainer_share: float | None = None, save_dir: str | None = None):
         """`overlap=True` reproduces the reference's pipeline (datamodule.py:89-101): the self-play of iteration k+1 runs on a
         background thread (own CUDA stream, weights as of the end of iteration k-1's training) while iteration k trains.
         `precision`: "32-true" (the reference's Lightning default) or "bf16-mixed" (forward / backward under bf16 autocast,
         fp32 master weights and optimiser state).  `cuda_graph`: replay the optimiser steps from a CUDA graph (`_GraphedTraining`);
         False runs the same steps eagerly (same minibatches, same arithmetic).  `trainer_share`: fraction of the games rank 0 plays
-        (`distributed.shard_range`); None = equal shards."""
+        (`distributed.shard_range`); None = equal shards.  `save_every_n_iterations` > 0: after every n-th round of games rank 0
+        writes the replay deque as `<save_dir>/episodes_iter{N}.json` (`DataModule._save_episodes`, datamodule.py:71-80,109-112;
+        default directory "episodes", datamodule.py:63) and, after that iteration's training, the weights as
+        `<save_dir>/model_iter{N}.pt` (the reference's `ModelCheckpoint(every_n_epochs=...)`, trainer.py:66-70)."""
         import threading
 
         world = dist.get_world_size() if dist.is_initialized() else 1
@@ -193,6 +196,15 @@ class Trainer:
             else:
                 replay.extend(local)
             t2 = time.perf_counter()
+            saving = save_every_n_iterations > 0 and rank == 0 and (it + 1) % save_every_n_iterations == 0
+            if saving:
+                import os
+
+                from .episode import episodes_from_batch, save_episodes
+
+                os.makedirs(save_dir or "episodes", exist_ok=True)
+                save_episodes(episodes_from_batch(replay.to_episode_batch(), simulations_per_episode),
+                              os.path.join(save_dir or "episodes", f"episodes_iter{it + 1}.json"))
             # weight sync, then the next iteration's games start and overlap the training below
             nbytes = broadcast_weights(model, src=0) if world > 1 else 0
             gen.update_inference_model(model)
@@ -204,6 +216,8 @@ class Trainer:
                 loss_sum, n_steps = steps.run(replay, epochs_per_iter, g, use_graph=cuda_graph)
                 model.eval()
             torch.cuda.current_stream(self.device).synchronize()
+            if saving:
+                torch.save(model.state_dict(), os.path.join(save_dir or "episodes", f"model_iter{it + 1}.pt"))
             t3 = time.perf_counter()
             self.history.append(dict(iteration=it, episodes=len(replay), samples=replay.num_samples, selfplay_s=selfplay_s,
                                      wait_for_selfplay_s=t1 - t0, gather_s=t2 - t1, train_s=t3 - t2, weight_bytes=nbytes,

@@ -218,6 +218,26 @@ def test_training_iteration_reduces_loss_and_syncs_weights():
     assert hist[2]["graph_replays"] > 0 and hist[0]["optimizer_steps"] == 3 * -(-hist[0]["samples"] // 32)
 
 
+def test_trainer_writes_the_reference_episode_files(tmp_path):
+    """Row (f3): `save_every_n_iterations` -> `episodes_iter{N}.json` holding the replay deque in the reference's format
+    (datamodule.py:71-80,109-112), readable by `load_episodes`, plus the weights of that iteration."""
+    from alphazero_implementation_b200.episode import load_episodes
+    from alphazero_implementation_b200.trainer import Trainer
+
+    torch.manual_seed(0)
+    np.random.seed(0)
+    tr = Trainer(az.BasicNN())
+    hist = tr.train(num_iterations=2, episodes_per_iter=16, simulations_per_episode=16, epochs_per_iter=1,
+                    initial_state=az.Config(6, 7, 4).sample_initial_state(), buffer_size=24, save_every_n_iterations=2,
+                    save_dir=str(tmp_path))
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["episodes_iter2.json", "model_iter2.pt"]
+    eps = load_episodes(str(tmp_path / "episodes_iter2.json"))
+    assert len(eps) == 24 == hist[1]["episodes"] and sum(len(e.samples) for e in eps) == hist[1]["samples"]
+    s = eps[0].samples[0]
+    assert abs(sum(s.policy.values()) - 1.0) < 1e-9 and s.value in ([1.0, -1.0], [-1.0, 1.0], [0.0, 0.0])
+    assert set(torch.load(tmp_path / "model_iter2.pt").keys()) == set(az.BasicNN().state_dict().keys())
+
+
 def test_graphed_training_steps_equal_eager_steps():
     """Row (f1): the optimiser steps replayed from a CUDA graph are the eager steps - same minibatches, same weights."""
     from alphazero_implementation_b200.replay import ReplayBuffer

@@ -121,3 +121,9 @@ def test_replay_buffer_is_a_deque_of_episodes():
         assert value.tolist() == [[float(o[0]), float(o[1])] for _, l, o in ref for _ in range(l)]
         want_counts = torch.tensor([[(i + q) % 5] * 7 for i, l, _ in ref for q in range(l)], dtype=torch.float32)
         assert torch.equal(policy, want_counts / 10.0)  # improved_policy = N_c / (S - 1)
+        # the same content as flat host arrays (what the episodes_iter{N}.json writer iterates over)
+        eb = rb.to_episode_batch()
+        assert len(eb) == len(ref) and eb.ep_len.tolist() == [l for _, l, _ in ref]
+        assert eb.ep_offset.tolist() == [sum(l for _, l, _ in list(ref)[:k]) for k in range(len(ref))]
+        assert eb.s_bb0.tolist() == want_bb0 and eb.ep_outcome.tolist() == [o for _, _, o in ref]
+        assert eb.s_counts.dtype == np.int32 and eb.s_counts.shape == (len(want_bb0), 7)
