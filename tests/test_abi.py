@@ -64,3 +64,45 @@ def test_sass_is_sm100a_only(built_lib):
     out = subprocess.run(["cuobjdump", "--list-elf", path], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     assert not re.search(r"sm_(?!100a)\d+", out), out
+
+
+def _sass_of(path, pattern):
+    """Instructions [(address, text)] of the first kernel whose mangled name matches `pattern`."""
+    import subprocess
+
+    out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    ins, inside = [], False
+    for line in out.splitlines():
+        if "Function :" in line:
+            if inside:
+                break
+            inside = re.search(pattern, line) is not None
+            continue
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?)\s*;", line) if inside else None
+        if m:
+            ins.append((int(m.group(1), 16), m.group(2)))
+    return ins
+
+
+def test_level_loop_of_the_fused_tree_kernel_stays_straight_line(built_lib):
+    """The descent's level loop is a dependent chain the kernel's speed hangs on: it must stay free of
+    reconvergence regions (an `if` that the compiler turns into a divergent branch), read its tables with LDS (tables in
+    shared memory are a compile-time fact) and use the tensor-core-free fp64 path only.  Checked on the SASS of the variant
+    the bench runs (4 trees per warp, uniform evaluator, latency variant, fused move, shared-memory tables)."""
+    path, _ = built_lib
+    ins = _sass_of(path, r"k_run_simsILi4ELi1ELb1ELb1ELb1E")
+    assert len(ins) > 1000
+    loops = []
+    for i, (addr, text) in enumerate(ins):
+        m = re.search(r"\bBRA(?:\.U)?\s+(?:!?U?P\d,\s*)?0x([0-9a-f]+)", text)
+        if m and int(m.group(1), 16) < addr:
+            body = [t for a, t in ins if int(m.group(1), 16) <= a <= addr]
+            if any("SHFL.BFLY" in t for t in body):
+                loops.append(body)
+    level = min(loops, key=len)  # innermost loop with the arg-max butterfly = one tree level
+    assert 100 < len(level) <= 170, len(level)
+    assert not any(t.startswith(("BSSY", "BSYNC")) or " BSSY" in t for t in level)
+    assert sum("SHFL.BFLY" in t for t in level) == 9 and sum("SHFL.IDX" in t for t in level) == 3
+    assert any("LDS.128" in t for t in level) and not any(re.search(r"\bLD\.E", t) for t in level)
+    # two divisions (multiply + 4 FMAs each), their sum, and the next level's numerator (c * P) * sqrt(N): 13 fp64 operations
+    assert sum(t.split()[0 if not t.startswith("@") else 1].startswith(("DFMA", "DMUL", "DADD")) for t in level) <= 13
