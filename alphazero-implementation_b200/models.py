@@ -25,7 +25,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from .engine import LAYOUT_GRID_F32, LAYOUT_PLANES_BF16, LAYOUT_PLANES_F32
-from .game import Action, State, rules_engine
+from .game import State, rules_engine
 
 ActionPolicy = dict
 Value = list

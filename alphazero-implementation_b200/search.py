@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from .engine import (EVAL_HASH, EVAL_UNIFORM, LEAF_EVAL, POLICY_LOGITS, POLICY_PRIORS, TREE_ROOT_ENDED, Engine)
-from .game import DEFAULT_CONFIG, Action, State, states_from_arrays
+from .game import Action, State, states_from_arrays
 
 
 class Node:

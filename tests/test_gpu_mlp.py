@@ -7,7 +7,7 @@ pytestmark = pytest.mark.gpu
 
 import alphazero_implementation_b200 as az  # noqa: E402
 from alphazero_implementation_b200.engine import LAYOUT_GRID_F32  # noqa: E402
-from alphazero_implementation_b200.models import InferenceNet, TensorCoreMLP  # noqa: E402
+from alphazero_implementation_b200.models import TensorCoreMLP  # noqa: E402
 
 
 def _leaf_grids(n, seed=0):

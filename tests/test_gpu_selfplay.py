@@ -10,7 +10,7 @@ from conftest import golden_uniforms  # noqa: E402
 
 
 def _run_engine(E, S, kind, uniforms_2d, init=(0, 0, 0), lanes=0, quota=None, fused=False):
-    from alphazero_implementation_b200.engine import Engine, sort_episode_batch
+    from alphazero_implementation_b200.engine import Engine
 
     quota = E if quota is None else quota
     eng = Engine(num_games=E, num_simulations=S, lanes_per_tree=lanes)
