@@ -69,6 +69,16 @@ class AzStats(C.Structure):
                                            "moves", "episodes", "children_scanned")]
 
 
+class AzResnetDesc(C.Structure):
+    _fields_ = [
+        ("num_blocks", C.c_int32), ("num_channels", C.c_int32), ("operand_format", C.c_int32), ("reserved", C.c_int32),
+        ("trunk_w", C.c_void_p), ("trunk_b", C.c_void_p), ("head_conv_w", C.c_void_p), ("head_conv_b", C.c_void_p),
+        ("fc_policy_w", C.c_void_p), ("fc_policy_b", C.c_void_p), ("fc_value_w", C.c_void_p), ("fc_value_b", C.c_void_p),
+    ]
+
+
+FMT_BF16, FMT_F16 = 0, 1
+
 P = C.c_void_p  # device pointers and streams cross the boundary as plain addresses
 I32, I64 = C.c_int32, C.c_int64
 
@@ -109,6 +119,7 @@ SIGNATURES = {
     "az_mlp_create": (I32, [I32, C.POINTER(P)]),
     "az_mlp_destroy": (I32, [P]),
     "az_mlp_last_error": (C.c_char_p, [P]),
+    "az_mlp_set_operand_format": (I32, [P, I32]),
     "az_mlp_set_weights": (I32, [P, P, P, P, P, P, P, P, P, P]),
     "az_mlp_forward": (I32, [P, P, I64, P, P, P]),
     "az_mlp_forward_leaves": (I32, [P, P, P, P, P]),
@@ -117,6 +128,7 @@ SIGNATURES = {
     "az_trunk_weight_bytes": (I64, [I32]),
     "az_trunk_forward_leaves": (I32, [P, P, P, I32, P, P]),
     "az_resnet_forward_leaves": (I32, [P, P, P, I32, P, P, P, P, P, P, P, P, P]),
+    "az_resnet_forward_leaves_v2": (I32, [P, C.POINTER(AzResnetDesc), P, P, P]),
     "az_trunk_set_cta_pair": (I32, [I32]),
     "az_leaf_arrays": (I32, [P, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(I32)]),
 }

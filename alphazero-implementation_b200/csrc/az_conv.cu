@@ -37,6 +37,7 @@
 // (az_trunk_set_cta_pair).  History: a serial version (one 5-tile group of 8 x 9 padded
 // positions, the issuing warp also refilling the ring) took 1.33 ms - every tap waited for its own stage to drain.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -65,8 +66,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-__host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// D = f32; A and B K-major, both bf16 (format 1) or both fp16 (format 0): same rate, same storage, 8 vs 11 significand bits
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N, bool f16) {
+    return (1u << 4) | (f16 ? 0u : (1u << 7) | (1u << 10)) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -85,11 +87,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
         "{\n\t"
         ".reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
-        "}" ::"r"(bar), "r"(phase)
+        "}" ::"r"(bar), "r"(phase), "r"(0x989680u)  /* suspend-time hint: the warp sleeps in the barrier unit instead of spinning on the issue slots the MMA / producer warps share */
         : "memory");
 }
 // one lane of a converged warp (the caller keeps every operand warp-uniform, so the MMA operands stay in uniform registers)
@@ -137,11 +139,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t phase) 
         "{\n\t"
         ".reg .pred P1;\n\t"
         "WAITC_LOOP:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra WAITC_DONE;\n\t"
         "bra WAITC_LOOP;\n\t"
         "WAITC_DONE:\n\t"
-        "}" ::"r"(bar), "r"(phase)
+        "}" ::"r"(bar), "r"(phase), "r"(0x989680u)  /* suspend-time hint: the warp sleeps in the barrier unit instead of spinning on the issue slots the MMA / producer warps share */
         : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -165,6 +167,21 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+// the 16-bit operand format of a kernel instance: bf16 (north_star's default) or fp16 (same tensor-core rate; 8x smaller rounding
+// error per operand, which is what brings priors / values within 1e-3 of the fp32 reference `predict`, tests/test_gpu_trunk.py)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+    if (F16) {
+        __half2 p = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));  // saturate instead of overflowing to inf
+        return *reinterpret_cast<uint32_t *>(&p);
+    }
+    return pack_bf16(a, b);
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack16(uint32_t w) {
+    if (F16) return __half22float2(*reinterpret_cast<const __half2 *>(&w));
+    return make_float2(bf16_lo(w), bf16_hi(w));
+}
 
 #ifdef AZ_TRUNK_CLOCKS
 // debug build only: per-layer timestamps of one CTA (issue start / issue end / accumulators ready / epilogue end)
@@ -201,6 +218,7 @@ __device__ __forceinline__ bool decode_row(int r, int &pos, int &y, int &x) {
 }
 
 // epilogue of tiles [t0, t1) of one conv layer (8 warps; warp group `half` takes 32 of the 64 channels)
+template <bool F16>
 __device__ __forceinline__ void conv_epilogue(uint32_t tmem_base, uint8_t *dst, const uint8_t *skip, const float *bias, int t0, int t1) {
     const uint32_t lane_row = threadIdx.x & 127u;
     const int half = (threadIdx.x >> 7) & 1;
@@ -222,13 +240,14 @@ __device__ __forceinline__ void conv_epilogue(uint32_t tmem_base, uint8_t *dst, 
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[kg * 8 + j]) + bias[grp * 8 + j];
             if (srow) {
                 const uint4 s = *reinterpret_cast<const uint4 *>(srow + grp * LBO_A);
-                f[0] += bf16_lo(s.x); f[1] += bf16_hi(s.x); f[2] += bf16_lo(s.y); f[3] += bf16_hi(s.y);
-                f[4] += bf16_lo(s.z); f[5] += bf16_hi(s.z); f[6] += bf16_lo(s.w); f[7] += bf16_hi(s.w);
+                const float2 s0 = unpack16<F16>(s.x), s1 = unpack16<F16>(s.y), s2 = unpack16<F16>(s.z), s3 = unpack16<F16>(s.w);
+                f[0] += s0.x; f[1] += s0.y; f[2] += s1.x; f[3] += s1.y;
+                f[4] += s2.x; f[5] += s2.y; f[6] += s3.x; f[7] += s3.y;
             }
             uint4 o = make_uint4(0, 0, 0, 0);
             if (valid)
-                o = make_uint4(pack_bf16(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f)), pack_bf16(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f)),
-                               pack_bf16(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f)), pack_bf16(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f)));
+                o = make_uint4(pack16<F16>(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f)), pack16<F16>(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f)),
+                               pack16<F16>(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f)), pack16<F16>(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f)));
             *reinterpret_cast<uint4 *>(drow + grp * LBO_A) = o;
         }
     }
@@ -281,7 +300,7 @@ __device__ __forceinline__ void issue_group(uint32_t full0, uint32_t pfull0, uin
     }
 }
 
-template <bool PAIR>
+template <bool PAIR, bool F16>
 __global__ void __launch_bounds__(THREADS, 1)
 k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1, const uint8_t *__restrict__ leaf_player,
                    const uint8_t *__restrict__ leaf_status, long long n, const uint8_t *__restrict__ weights,
@@ -379,7 +398,7 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
         const uint32_t live = in_meta[k] & 1u;
         const uint32_t s0 = (uint32_t)((in_b0[k] >> bit) & 1ull), s1 = (uint32_t)((in_b1[k] >> bit) & 1ull);
         const uint32_t mine = live * (pl ? s1 : s0), theirs = live * (pl ? s0 : s1), emp = live * (1u - (s0 | s1));
-        const uint32_t one = 0x3F80u;
+        const uint32_t one = F16 ? 0x3C00u : 0x3F80u;  // 1.0
         *reinterpret_cast<uint4 *>(buf[1] + (GUARD + r) * ROWB) = make_uint4(emp * one | (mine * one) << 16, theirs * one, 0u, 0u);
     }
     fence_async_smem();
@@ -423,7 +442,7 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
             }
     } else if (warp == 8) {
         // ===== MMA issuer (converged; one elected lane issues) =====
-        const uint32_t idesc_c = instr_desc(PAIR ? 256 : 128, C), idesc_h = instr_desc(PAIR ? 256 : 128, NHC);
+        const uint32_t idesc_c = instr_desc(PAIR ? 256 : 128, C, F16), idesc_h = instr_desc(PAIR ? 256 : 128, NHC, F16);
         for (int l = 0; l < n_layers; ++l) {
             const bool is_head = l >= n_conv;
             const uint32_t src = l == 0 ? a1 : (is_head ? a0 : ((l & 1) ? a0 : a1));  // conv1 (odd l) reads x = buf[0]; conv2 reads t = buf[1]
@@ -469,7 +488,7 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
                 else mbar_wait(mma_done0 + g * 8, (gl0 + (uint32_t)l) & 1u);
                 tc_fence_after();
                 if (warp == 0) CLK(2, l, g);
-                conv_epilogue(tmem_base, dst, skip, s_bias + l * C, g * GTILES, (g + 1) * GTILES);
+                conv_epilogue<F16>(tmem_base, dst, skip, s_bias + l * C, g * GTILES, (g + 1) * GTILES);
                 // every thread orders its own rows for the tensor core's reads, the warp syncs, one lane arrives for the warp
                 tc_fence_before();
                 fence_async_smem();
@@ -626,7 +645,8 @@ int32_t az_trunk_set_cta_pair(int32_t on) {
 
 static int32_t launch_trunk(az_engine *engine, const void *weights, const float *biases, int32_t num_blocks, void *out,
                             const void *head_w, const float *head_b, const float *fcp_w, const float *fcp_b, const float *fcv_w,
-                            const float *fcv_b, float *logits, float *values, void *stream) {
+                            const float *fcv_b, float *logits, float *values, void *stream, int32_t fmt = AZ_FMT_BF16) {
+    if (fmt != AZ_FMT_BF16 && fmt != AZ_FMT_F16) return AZ_E_INVALID;
     if (!engine || !weights || !biases || num_blocks < 0 || 1 + 2 * num_blocks + 1 > MAX_LAYERS) return AZ_E_INVALID;
     const uint64_t *bb0 = nullptr, *bb1 = nullptr;
     const uint8_t *status = nullptr, *player = nullptr;
@@ -636,8 +656,10 @@ static int32_t launch_trunk(az_engine *engine, const void *weights, const float 
     const int dev = az_device(engine);
     if (dev < 0 || dev >= 64 || cudaSetDevice(dev) != cudaSuccess) return AZ_E_CUDA;
     if (!attr_set[dev]) {
-        if (cudaFuncSetAttribute(k_resnet_trunk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
-        if (cudaFuncSetAttribute(k_resnet_trunk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
+        if (cudaFuncSetAttribute(k_resnet_trunk<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
+        if (cudaFuncSetAttribute(k_resnet_trunk<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
+        if (cudaFuncSetAttribute(k_resnet_trunk<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
+        if (cudaFuncSetAttribute(k_resnet_trunk<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
         attr_set[dev] = true;
     }
     const int pair = g_trunk_cta_pair;
@@ -658,15 +680,17 @@ static int32_t launch_trunk(az_engine *engine, const void *weights, const float 
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (cudaLaunchKernelEx(&cfg, k_resnet_trunk<true>, bb0, bb1, player, status, nn, w8, biases, (int)num_blocks, o16, hw8, head_b, fcp_w, fcp_b,
+        auto kern = fmt == AZ_FMT_F16 ? k_resnet_trunk<true, true> : k_resnet_trunk<true, false>;
+        if (cudaLaunchKernelEx(&cfg, kern, bb0, bb1, player, status, nn, w8, biases, (int)num_blocks, o16, hw8, head_b, fcp_w, fcp_b,
                                fcv_w, fcv_b, logits, values) != cudaSuccess)
             return AZ_E_CUDA;
     } else {
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return AZ_E_CUDA;
         const int batches = (n + P - 1) / P;
-        k_resnet_trunk<false><<<batches < sms ? batches : sms, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(bb0, bb1, player, status, nn, w8, biases, num_blocks, o16,
-                                                                                             hw8, head_b, fcp_w, fcp_b, fcv_w, fcv_b, logits, values);
+        auto kern = fmt == AZ_FMT_F16 ? k_resnet_trunk<false, true> : k_resnet_trunk<false, false>;
+        kern<<<batches < sms ? batches : sms, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(bb0, bb1, player, status, nn, w8, biases, num_blocks, o16, hw8, head_b,
+                                                                                            fcp_w, fcp_b, fcv_w, fcv_b, logits, values);
     }
     return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;
 }
@@ -689,6 +713,16 @@ int32_t az_resnet_forward_leaves(az_engine *engine, const void *weights, const f
     if (!head_conv_w || !head_conv_b || !fc_policy_w || !fc_policy_b || !fc_value_w || !fc_value_b || !logits || !values) return AZ_E_INVALID;
     return launch_trunk(engine, weights, biases, num_blocks, nullptr, head_conv_w, head_conv_b, fc_policy_w, fc_policy_b, fc_value_w,
                         fc_value_b, logits, values, stream);
+}
+
+/* The same with an explicit descriptor: operand format (bf16 / fp16) and channel count.  Replaces `Connect4Model.predict`'s
+ * forward (models/games/connect4/model.py:19-43) for the ResNet-style net on the leaves of the last az_select_leaves. */
+int32_t az_resnet_forward_leaves_v2(az_engine *engine, const az_resnet_desc *d, float *logits, float *values, void *stream) {
+    if (!d || !logits || !values) return AZ_E_INVALID;
+    if (!d->head_conv_w || !d->head_conv_b || !d->fc_policy_w || !d->fc_policy_b || !d->fc_value_w || !d->fc_value_b) return AZ_E_INVALID;
+    if (d->num_channels != 64) return AZ_E_INVALID;
+    return launch_trunk(engine, d->trunk_w, d->trunk_b, d->num_blocks, nullptr, d->head_conv_w, d->head_conv_b, d->fc_policy_w, d->fc_policy_b,
+                        d->fc_value_w, d->fc_value_b, logits, values, stream, d->operand_format);
 }
 
 }  // extern "C"

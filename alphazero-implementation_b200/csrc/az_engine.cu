@@ -1812,14 +1812,17 @@ static int32_t run_sims_impl(az_engine *h, int32_t num_sims, int32_t eval_kind, 
     const int tpw = 32 / h->G, trees_per_block = 2 * tpw;
     const int blocks = blocks_for(n, trees_per_block);
     int per_sm = (blocks + h->num_sms - 1) / h->num_sms;
-    if (per_sm > 14) per_sm = 14;  // register-limited residency of 64-thread blocks (72 registers)
-    const int tabs_in_smem = (size_t)h->a.tab_n * 24 <= 6144 ? 1 : 0;  // {1/(n+1), sqrt(n)} pairs + 1/n: 24 bytes per entry
-    const size_t tab_bytes = tabs_in_smem ? (size_t)h->a.tab_n * 24 : 0;
+    if (per_sm > 14) per_sm = 14;  // register-limited residency of 64-thread blocks (80 registers, ncu)
     // hot-node count K: the largest multiple of 8 such that every block of the grid stays resident (228 KB of shared memory per SM,
     // 1 KB of it reserved per resident block; one block may use up to 200 KB) - measured monotonic: more hot nodes, faster
+    const long long per_block = (long long)(228 * 1024) / per_sm - 1024;
+    // {1/(n+1), sqrt(n)} pairs + 1/n: 24 bytes per entry (19 KB at 800 simulations per move).  The tables go to shared memory
+    // whenever they leave at least half of the block's share to the hot nodes: always for S <= 248, and for S = 800 up to
+    // 5 resident blocks per SM (<= 5920 trees); denser grids run the throughput variant, where a level's latency matters less.
+    const int tabs_in_smem = (long long)h->a.tab_n * 24 <= (per_block < 200 * 1024 ? per_block : 200 * 1024) / 2 ? 1 : 0;
+    const size_t tab_bytes = tabs_in_smem ? (size_t)h->a.tab_n * 24 : 0;
     int K = 0;
     {
-        const long long per_block = (long long)(228 * 1024) / per_sm - 1024;
         const long long budget = (per_block < 200 * 1024 ? per_block : 200 * 1024) - (long long)tab_bytes - (long long)trees_per_block * PATH_STRIDE * 4;
         long long kmax = budget > 0 ? budget / ((long long)trees_per_block * 16) : 0;
         if (kmax > 1024) kmax = 1024;

@@ -18,6 +18,7 @@
 // weights) + epilogue 3.0 k, heads 1.9 k.  The first version (issuing warp also refilling a two-stage ring, 4 epilogue
 // warps with blocking tensor-memory loads) took 33.6 k; kernel 24.2 -> 18.7 us.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -60,8 +61,9 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t sbo) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = bf16, both K-major, shape M x N
-__host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// operand format: bf16 (1) or fp16 (0) - same rate and storage; fp16's 11 significand bits bring the outputs within 1e-3 of fp32
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N, bool f16) {
+    return (1u << 4) | (f16 ? 0u : (1u << 7) | (1u << 10)) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -81,11 +83,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
         "{\n\t"
         ".reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
-        "}" ::"r"(bar), "r"(phase)
+        "}" ::"r"(bar), "r"(phase), "r"(0x989680u)  /* suspend-time hint: the warp sleeps in the barrier unit instead of spinning on the issue slots the MMA / producer warps share */
         : "memory");
 }
 // one lane of a converged warp (the caller keeps every operand warp-uniform, so the MMA operands stay in uniform registers)
@@ -133,7 +135,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+    if (F16) {
+        __half2 h = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));  // saturate instead of overflowing to inf
+        return *reinterpret_cast<uint32_t *>(&h);
+    }
     __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&p);
 }
@@ -197,6 +204,7 @@ __device__ __forceinline__ void issue_layer(Pipe &p, uint32_t nchunks, uint32_t 
 
 // accumulator (128 x 512 fp32 in TMEM) -> bias + ReLU -> bf16 -> canonical [128][512] A operand in shared memory.
 // 8 warps: thread = (row, column half); the next 32-column block is in flight while the current one is processed.
+template <bool F16>
 __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], uint8_t *rowp, const float *bias, int cb) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -204,9 +212,10 @@ __device__ __forceinline__ void epilogue_block(const uint32_t (&v)[32], uint8_t 
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(v[q * 8 + j]) + bias[cb * 32 + q * 8 + j], 0.0f);
         *reinterpret_cast<uint4 *>(rowp + (cb * 4 + q) * LBO) =
-            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            make_uint4(pack16<F16>(f[0], f[1]), pack16<F16>(f[2], f[3]), pack16<F16>(f[4], f[5]), pack16<F16>(f[6], f[7]));
     }
 }
+template <bool F16>
 __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_base, uint8_t *act, const float *bias /* shared memory */) {
     const uint32_t row = threadIdx.x & 127u;                           // lane of TMEM = row of the tile
     const int cb0 = (int)(threadIdx.x >> 7) * (HID / 64);              // this warp group's 8 column blocks of 32
@@ -218,10 +227,10 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_base, uint8_t *act
     for (int i = 0; i < HID / 64; i += 2) {
         tmem_ld_wait();
         tmem_ld32_issue(taddr + (cb0 + i + 1) * 32, vb);
-        epilogue_block(va, rowp, bias, cb0 + i);
+        epilogue_block<F16>(va, rowp, bias, cb0 + i);
         tmem_ld_wait();
         if (i + 2 < HID / 64) tmem_ld32_issue(taddr + (cb0 + i + 2) * 32, va);
-        epilogue_block(vb, rowp, bias, cb0 + i + 1);
+        epilogue_block<F16>(vb, rowp, bias, cb0 + i + 1);
     }
 }
 
@@ -235,7 +244,7 @@ __device__ __forceinline__ uint64_t row_major42(uint64_t bb) {
 
 // FROM_LEAVES: the input rows are built in the kernel from the engine's leaf bitboards (the leaf gather fused in);
 // otherwise they are read from an AZ_LAYOUT_GRID_F32 batch.
-template <bool FROM_LEAVES>
+template <bool FROM_LEAVES, bool F16>
 __global__ void __launch_bounds__(THREADS, 1)
 k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1,
             const uint8_t *__restrict__ leaf_status, long long n, const uint8_t *__restrict__ w1p, const float *__restrict__ b1,
@@ -307,7 +316,7 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
                     for (int q = 0; q < 2; ++q) {
                         const int e = kg * 8 + h * 2 + q;
                         uint32_t v = 0;
-                        if (e < IN) v = ((m0 >> e) & 1ull) ? 0x0000u : (((m1 >> e) & 1ull) ? 0x3F80u : 0xBF80u);  // 0, +1, -1 in bf16
+                        if (e < IN) v = ((m0 >> e) & 1ull) ? 0x0000u : (((m1 >> e) & 1ull) ? (F16 ? 0x3C00u : 0x3F80u) : (F16 ? 0xBC00u : 0xBF80u));  // 0, +1, -1
                         pair |= v << (16 * q);
                     }
                     w[h] = live ? pair : 0u;
@@ -320,7 +329,11 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
 #pragma unroll 6
             for (uint32_t e = tid; e < TILE_M * IN; e += ETHREADS) {
                 const uint32_t r = e / IN, k = e - r * IN;
-                if (row0 + r < n) *reinterpret_cast<__nv_bfloat16 *>(act + canon(r, k, SBO_X)) = __float2bfloat16_rn(__ldg(grid + (row0 + r) * IN + k));
+                if (row0 + r < n) {
+                    const float xv = __ldg(grid + (row0 + r) * IN + k);
+                    if (F16) *reinterpret_cast<__half *>(act + canon(r, k, SBO_X)) = __float2half_rn(xv);
+                    else *reinterpret_cast<__nv_bfloat16 *>(act + canon(r, k, SBO_X)) = __float2bfloat16_rn(xv);
+                }
             }
         }
         fence_async_smem();
@@ -328,12 +341,12 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
 
         // ---- layer 1: [128 x 64] . [512 x 64]^T
         MCLK(1);
-        if (warp == 0) issue_layer(p, K1 / KC, KC / 16, act_addr, SBO_X, 2, instr_desc(128, 256), tmem_base);
+        if (warp == 0) issue_layer(p, K1 / KC, KC / 16, act_addr, SBO_X, 2, instr_desc(128, 256, F16), tmem_base);
         MCLK(2);
         mbar_wait(p.done, 0);
         tc_fence_after();
         MCLK(3);
-        epilogue_hidden(tmem_base, act, s_bias);
+        epilogue_hidden<F16>(tmem_base, act, s_bias);
         MCLK(4);
         fence_async_smem();
         tc_fence_before();
@@ -342,12 +355,12 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
 
         // ---- layer 2: [128 x 512] . [512 x 512]^T, K in chunks of KC
         MCLK(5);
-        if (warp == 0) issue_layer(p, HID / KC, KC / 16, act_addr, SBO_ACT, 2, instr_desc(128, 256), tmem_base);
+        if (warp == 0) issue_layer(p, HID / KC, KC / 16, act_addr, SBO_ACT, 2, instr_desc(128, 256, F16), tmem_base);
         MCLK(6);
         mbar_wait(p.done, 1);
         tc_fence_after();
         MCLK(7);
-        epilogue_hidden(tmem_base, act, s_bias + HID);
+        epilogue_hidden<F16>(tmem_base, act, s_bias + HID);
         MCLK(8);
         fence_async_smem();
         tc_fence_before();
@@ -356,7 +369,7 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
 
         // ---- heads: [128 x 512] . [16 x 512]^T
         MCLK(9);
-        if (warp == 0) issue_layer(p, 1, HID / 16, act_addr, SBO_ACT, 1, instr_desc(128, NH), tmem_base);
+        if (warp == 0) issue_layer(p, 1, HID / 16, act_addr, SBO_ACT, 1, instr_desc(128, NH, F16), tmem_base);
         mbar_wait(p.done, 0);
         tc_fence_after();
         MCLK(10);
@@ -380,13 +393,14 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
 
 // fp32 [N][K] row-major (nn.Linear.weight) -> bf16, canonical K-major chunks of 64 along K, rows padded to n_pad
 __global__ void __launch_bounds__(256)
-k_pack_weight(const float *__restrict__ w, int N, int K, int n_pad, int k_pad, uint8_t *__restrict__ dst) {
+k_pack_weight(const float *__restrict__ w, int N, int K, int n_pad, int k_pad, uint8_t *__restrict__ dst, int f16) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad * k_pad) return;
     const int nn = i / k_pad, k = i - nn * k_pad;
     const float v = (nn < N && k < K) ? w[(size_t)nn * K + k] : 0.0f;
     const size_t off = (size_t)(k / KC) * ((size_t)n_pad * KC * 2) + canon((uint32_t)nn, (uint32_t)(k % KC), SBO_CHUNK);
-    *reinterpret_cast<__nv_bfloat16 *>(dst + off) = __float2bfloat16_rn(v);
+    if (f16) *reinterpret_cast<__half *>(dst + off) = __float2half_rn(v);
+    else *reinterpret_cast<__nv_bfloat16 *>(dst + off) = __float2bfloat16_rn(v);
 }
 
 __global__ void k_pack_head_rows(const float *__restrict__ wp, const float *__restrict__ wv, float *__restrict__ wh) {
@@ -401,6 +415,7 @@ __global__ void k_pack_head_rows(const float *__restrict__ wp, const float *__re
 
 struct az_mlp {
     int device;
+    int fmt;  // AZ_FMT_*: operand format of the packed weights and of the activations between layers
     uint8_t *w1p, *w2p, *whp;
     float *b1, *b2, *bh, *wh_tmp;
     long long launches;
@@ -428,8 +443,10 @@ int32_t az_mlp_create(int32_t device, az_mlp **out) {
     AL(w1p, W1_ELEMS * 2); AL(w2p, W2_ELEMS * 2); AL(whp, WH_ELEMS * 2);
     AL(b1, HID * 4); AL(b2, HID * 4); AL(bh, NH * 4); AL(wh_tmp, 9 * HID * 4);
 #undef AL
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) {
         cudaGetLastError();
         free(m);
@@ -448,6 +465,13 @@ int32_t az_mlp_destroy(az_mlp *m) {
     return AZ_OK;
 }
 
+/* operand format of the evaluator (AZ_FMT_BF16 default, AZ_FMT_F16); call before az_mlp_set_weights, which packs in that format */
+int32_t az_mlp_set_operand_format(az_mlp *m, int32_t fmt) {
+    if (!m || (fmt != AZ_FMT_BF16 && fmt != AZ_FMT_F16)) return AZ_E_INVALID;
+    m->fmt = fmt;
+    return AZ_OK;
+}
+
 const char *az_mlp_last_error(const az_mlp *m) { return m ? m->err : "az_mlp: null handle"; }
 
 /* fp32 device pointers in nn.Linear layout: w1 [512][42], w2 [512][512], wp [7][512], wv [2][512] and their biases */
@@ -456,10 +480,11 @@ int32_t az_mlp_set_weights(az_mlp *m, const float *w1, const float *b1, const fl
     if (!m || !w1 || !b1 || !w2 || !b2 || !wp || !bp || !wv || !bv) return AZ_E_INVALID;
     cudaSetDevice(m->device);
     cudaStream_t st = (cudaStream_t)stream;
-    k_pack_weight<<<(HID * K1 + 255) / 256, 256, 0, st>>>(w1, HID, IN, HID, K1, m->w1p);
-    k_pack_weight<<<(HID * HID + 255) / 256, 256, 0, st>>>(w2, HID, HID, HID, HID, m->w2p);
+    const int f16 = m->fmt == AZ_FMT_F16;
+    k_pack_weight<<<(HID * K1 + 255) / 256, 256, 0, st>>>(w1, HID, IN, HID, K1, m->w1p, f16);
+    k_pack_weight<<<(HID * HID + 255) / 256, 256, 0, st>>>(w2, HID, HID, HID, HID, m->w2p, f16);
     k_pack_head_rows<<<(9 * HID + 255) / 256, 256, 0, st>>>(wp, wv, m->wh_tmp);
-    k_pack_weight<<<(NH * HID + 255) / 256, 256, 0, st>>>(m->wh_tmp, 9, HID, NH, HID, m->whp);
+    k_pack_weight<<<(NH * HID + 255) / 256, 256, 0, st>>>(m->wh_tmp, 9, HID, NH, HID, m->whp, f16);
     m->launches += 4;
     cudaMemcpyAsync(m->b1, b1, HID * 4, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(m->b2, b2, HID * 4, cudaMemcpyDeviceToDevice, st);
@@ -480,8 +505,8 @@ int32_t az_mlp_forward(az_mlp *m, const float *grid, int64_t n, float *logits, f
     if (n == 0) return AZ_OK;
     cudaSetDevice(m->device);
     const int blocks = (int)((n + TILE_M - 1) / TILE_M);
-    k_mlp_fused<false><<<blocks, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(grid, nullptr, nullptr, nullptr, n, m->w1p, m->b1, m->w2p, m->b2,
-                                                                             m->whp, m->bh, logits, values);
+    auto kern = m->fmt == AZ_FMT_F16 ? k_mlp_fused<false, true> : k_mlp_fused<false, false>;
+    kern<<<blocks, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(grid, nullptr, nullptr, nullptr, n, m->w1p, m->b1, m->w2p, m->b2, m->whp, m->bh, logits, values);
     m->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -501,8 +526,8 @@ int32_t az_mlp_forward_leaves(az_mlp *m, az_engine *engine, float *logits, float
     if (az_leaf_arrays(engine, &bb0, &bb1, &status, &n) != AZ_OK || n <= 0) return AZ_E_INVALID;
     cudaSetDevice(m->device);
     const int blocks = (n + TILE_M - 1) / TILE_M;
-    k_mlp_fused<true><<<blocks, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(nullptr, bb0, bb1, status, n, m->w1p, m->b1, m->w2p, m->b2, m->whp,
-                                                                            m->bh, logits, values);
+    auto kern = m->fmt == AZ_FMT_F16 ? k_mlp_fused<true, true> : k_mlp_fused<true, false>;
+    kern<<<blocks, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(nullptr, bb0, bb1, status, n, m->w1p, m->b1, m->w2p, m->b2, m->whp, m->bh, logits, values);
     m->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -34,23 +34,27 @@ class EpisodeGenerator:
         self.search.update_inference_model(model)
 
     # ------------------------------------------------------------------------------------------
-    def iter_steps(self, initial_state: State | None = None, max_steps: int | None = None):
+    def iter_steps(self, initial_state: State | None = None, max_steps: int | None = None, reset: bool = True):
         """Run the self-play loop; for every move step yield (step, EpisodeBatch-or-None, rng_state_before_draw).
 
         Host buffers in, host buffers out: each step's uniforms are copied from pinned host memory, its finished
         episodes are copied to pinned host memory.  The loop is software-pipelined one step deep: step k+1 is
         enqueued on the compute stream before step k's episodes are read back on a copy stream from the other
         half of the device's double-buffered episode ring, so the readback overlaps the next step's kernels.
-        Consequently a step's tuple is yielded one step late (and the last one after the loop)."""
+        Consequently a step's tuple is yielded one step late (and the last one after the loop) - and step k+1's uniforms are taken
+        from NumPy's global stream before step k's episodes are yielded: a consumer that draws from `np.random` between yields
+        shifts the stream relative to the reference (`generate_episodes` repairs the final position of the stream; pass a
+        `uniform_source` for full control).  `reset=False` continues the games already in the engine's slots."""
         from .engine import PinnedEpisodeBuffers
 
         if initial_state is None:
             initial_state = self.game_initial_state
         E = self.num_episodes
-        eng = self.search.engine_for(E)
-        if eng.num_games != E:
-            raise RuntimeError("engine was sized for a different number of games")
-        eng.reset_games(initial_state.bb0, initial_state.bb1, initial_state.player)
+        eng = self.search.engine_for(E, exact=True)  # the slots are the games: an engine grown by a larger run_simulations call is replaced
+        if reset:
+            eng.reset_games(initial_state.bb0, initial_state.bb1, initial_state.player)
+        elif eng.n_active != E:
+            raise RuntimeError("reset=False needs an engine whose slots hold this generator's games")
         u_host = [torch.empty(E, dtype=torch.float64).pin_memory() for _ in range(2)]
         u_dev = [torch.empty(E, dtype=torch.float64, device=eng.device) for _ in range(2)]
         host_buf = PinnedEpisodeBuffers()

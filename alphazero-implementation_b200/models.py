@@ -84,6 +84,30 @@ class Model(nn.Module):
         clone.eval()
         return clone
 
+    # -- checkpoints in the reference's (Lightning) file shape -----------------------------------------------------------
+    def save_checkpoint(self, path: str, epoch: int = 0, global_step: int = 0) -> None:
+        """What Lightning's `ModelCheckpoint` writes for the reference (core/training/trainer.py:66-70): the weights under
+        `state_dict`, the constructor arguments under `hyper_parameters`."""
+        torch.save({"state_dict": {k: v.detach().cpu() for k, v in self.state_dict().items()}, "hyper_parameters": dict(self.hparams),
+                    "epoch": int(epoch), "global_step": int(global_step), "pytorch-lightning_version": "2.0.0"}, path)
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path: str, map_location=None, strict: bool = True, **kwargs):
+        """`CNNModel.load_from_checkpoint(path)` as scripts/play.py:19-25 calls it: accepts a Lightning checkpoint (weights under
+        `state_dict`, constructor arguments under `hyper_parameters`) or a bare `state_dict` file."""
+        import inspect
+
+        ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+        if isinstance(ckpt, dict) and "state_dict" in ckpt and isinstance(ckpt["state_dict"], dict):
+            sd, hp = ckpt["state_dict"], dict(ckpt.get("hyper_parameters") or {})
+        else:
+            sd, hp = ckpt, {}
+        hp.update(kwargs)
+        accepted = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        model = cls(**{k: v for k, v in hp.items() if k in accepted})
+        model.load_state_dict(sd, strict=strict)
+        return model.eval()
+
 
 def _state_arrays(states: list[State]):
     return (np.array([s.bb0 for s in states], np.uint64), np.array([s.bb1 for s in states], np.uint64),
@@ -194,6 +218,7 @@ class ResNet(Connect4Model):
     def __init__(self, num_res_blocks: int = 9, num_channels: int = 128):
         super().__init__()
         self.num_res_blocks, self.num_channels = num_res_blocks, num_channels
+        self.hparams.update(num_res_blocks=num_res_blocks, num_channels=num_channels)
         rows, cols = self.board_height, self.board_width
         self.input_conv = nn.Sequential(nn.Conv2d(3, num_channels, kernel_size=3, padding=1), nn.BatchNorm2d(num_channels), nn.ReLU())
         self.residual_blocks = nn.ModuleList([ResBlock(num_channels) for _ in range(num_res_blocks)])
@@ -230,18 +255,22 @@ def _fold_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d):
 class TensorCoreMLP:
     """BasicNN.forward as one tcgen05 kernel (csrc/az_mlp.cu): bf16 operands, fp32 accumulation in tensor memory."""
 
-    def __init__(self, model: "BasicNN", device: torch.device):
+    def __init__(self, model: "BasicNN", device: torch.device, dtype: torch.dtype = torch.bfloat16):
         import ctypes as C
 
         from . import _lib
 
         self.lib = _lib.load()
         self.device = torch.device(device)
+        self.dtype = dtype
         h = C.c_void_p()
         rc = self.lib.az_mlp_create(self.device.index or 0, C.byref(h))
         if rc != 0:
             raise RuntimeError(f"az_mlp_create failed ({rc}): needs an sm_100 device")
         self.h = h
+        rc = self.lib.az_mlp_set_operand_format(self.h, _operand_format(dtype))
+        if rc != 0:
+            raise RuntimeError(f"az_mlp_set_operand_format failed ({rc})")
         self._out: dict[int, tuple[Tensor, Tensor]] = {}
         self.set_weights(model)
 
@@ -293,13 +322,24 @@ class TensorCoreMLP:
             pass
 
 
-def _canonical_kmajor(w: Tensor) -> Tensor:
-    """[N][K] -> bf16 in the MMA's K-major no-swizzle core-matrix order: [N/8][K/8][8 rows][8 k]."""
+def _operand_format(dtype: torch.dtype) -> int:
+    """torch dtype -> AZ_FMT_* of the tensor-core evaluators (include/az_engine.h)."""
+    from ._lib import FMT_BF16, FMT_F16
+
+    if dtype == torch.bfloat16:
+        return FMT_BF16
+    if dtype == torch.float16:
+        return FMT_F16
+    raise ValueError(f"the tensor-core evaluators take bf16 or fp16 operands, not {dtype}")
+
+
+def _canonical_kmajor(w: Tensor, dtype: torch.dtype = torch.bfloat16) -> Tensor:
+    """[N][K] -> 16-bit operands in the MMA's K-major no-swizzle core-matrix order: [N/8][K/8][8 rows][8 k]."""
     n, k = w.shape
-    return w.reshape(n // 8, 8, k // 8, 8).permute(0, 2, 1, 3).contiguous().to(torch.bfloat16).reshape(-1)
+    return w.reshape(n // 8, 8, k // 8, 8).permute(0, 2, 1, 3).contiguous().to(dtype).reshape(-1)
 
 
-def pack_trunk_weights(model: "ResNet", device) -> tuple[Tensor, Tensor]:
+def pack_trunk_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloat16) -> tuple[Tensor, Tensor]:
     """BatchNorm-folded stem + residual-block convolutions of a 64-channel ResNet as operands of csrc/az_conv.cu:
     per layer 9 taps (tap = 3*ky + kx) of [64 out][K in] bf16 (K = 16 for the stem, zero padded), and fp32 biases."""
     assert model.num_channels == 64, "the tensor-core trunk kernel is built for 64 channels"
@@ -314,12 +354,12 @@ def pack_trunk_weights(model: "ResNet", device) -> tuple[Tensor, Tensor]:
             w = torch.cat([w, torch.zeros(64, 13, 3, 3, device=w.device)], dim=1)  # 3 -> 16 input channels
         for ky in range(3):
             for kx in range(3):
-                parts.append(_canonical_kmajor(w[:, :, ky, kx]))
+                parts.append(_canonical_kmajor(w[:, :, ky, kx], dtype))
         biases.append(b)
     return torch.cat(parts).contiguous(), torch.stack(biases).contiguous().float()
 
 
-def pack_head_weights(model: "ResNet", device):
+def pack_head_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloat16):
     """Policy conv1x1 (-> 32) and value conv3x3 (-> 3), BatchNorm folded, as ONE 48-output 3x3 conv for csrc/az_conv.cu
     (the 1x1 weights occupy the centre tap), plus the two fully connected layers in fp32."""
     m = copy.deepcopy(model).eval().float().to(device)
@@ -330,7 +370,7 @@ def pack_head_weights(model: "ResNet", device):
     w[32:35] = wv
     b = torch.zeros(48, device=device)
     b[:32], b[32:35] = bp, bv
-    conv = torch.cat([_canonical_kmajor(w[:, :, ky, kx]) for ky in range(3) for kx in range(3)]).contiguous()
+    conv = torch.cat([_canonical_kmajor(w[:, :, ky, kx], dtype) for ky in range(3) for kx in range(3)]).contiguous()
     f = lambda t: t.detach().float().contiguous()
     return conv, b.contiguous(), f(m.policy_head[4].weight), f(m.policy_head[4].bias), f(m.value_head[4].weight).reshape(-1), f(m.value_head[4].bias)
 
@@ -338,18 +378,34 @@ def pack_head_weights(model: "ResNet", device):
 class TensorCoreTrunk:
     """Stem + residual blocks of a 64-channel ResNet as one tcgen05 kernel on the engine's leaves (csrc/az_conv.cu)."""
 
-    def __init__(self, model: "ResNet", device: torch.device):
+    def __init__(self, model: "ResNet", device: torch.device, dtype: torch.dtype = torch.bfloat16):
         from . import _lib
 
         self.lib = _lib.load()
         self.device = torch.device(device)
+        self.dtype = dtype
         self.num_blocks = model.num_res_blocks
-        self.weights, self.biases = pack_trunk_weights(model, self.device)
+        self.weights, self.biases = pack_trunk_weights(model, self.device, dtype)
         assert self.weights.numel() * 2 == self.lib.az_trunk_weight_bytes(self.num_blocks)
-        self.heads = pack_head_weights(model, self.device)
+        self.heads = pack_head_weights(model, self.device, dtype)
+        hw, hb, fpw, fpb, fvw, fvb = self.heads
+        self.desc = _lib.AzResnetDesc(self.num_blocks, model.num_channels, _operand_format(dtype), 0, self.weights.data_ptr(),
+                                      self.biases.data_ptr(), hw.data_ptr(), hb.data_ptr(), fpw.data_ptr(), fpb.data_ptr(),
+                                      fvw.data_ptr(), fvb.data_ptr())
         self._out: dict[int, Tensor] = {}
         self._lv: dict[int, tuple[Tensor, Tensor]] = {}
         self.launches = 0
+
+    def set_weights(self, model: "ResNet") -> bool:
+        """Re-pack `model`'s weights into the existing device buffers (same addresses: captured graphs stay valid)."""
+        if model.num_res_blocks != self.num_blocks or model.num_channels != 64:
+            return False
+        w, b = pack_trunk_weights(model, self.device, self.dtype)
+        self.weights.copy_(w)
+        self.biases.copy_(b)
+        for dst, src in zip(self.heads, pack_head_weights(model, self.device, self.dtype)):
+            dst.copy_(src)
+        return True
 
     def forward_leaves_full(self, engine) -> tuple[Tensor, Tensor]:
         """Trunk AND heads in the one kernel -> (logits [n,7] f32, values [n,2] f32) for the engine's current leaves."""
@@ -357,18 +413,18 @@ class TensorCoreTrunk:
         if n not in self._lv:
             self._lv[n] = (torch.empty((n, 7), device=self.device), torch.empty((n, 2), device=self.device))
         logits, values = self._lv[n]
-        hw, hb, fpw, fpb, fvw, fvb = self.heads
-        rc = self.lib.az_resnet_forward_leaves(engine.h, self.weights.data_ptr(), self.biases.data_ptr(), self.num_blocks,
-                                               hw.data_ptr(), hb.data_ptr(), fpw.data_ptr(), fpb.data_ptr(), fvw.data_ptr(),
-                                               fvb.data_ptr(), logits.data_ptr(), values.data_ptr(),
-                                               torch.cuda.current_stream(self.device).cuda_stream)
+        import ctypes as C
+
+        rc = self.lib.az_resnet_forward_leaves_v2(engine.h, C.byref(self.desc), logits.data_ptr(), values.data_ptr(),
+                                                  torch.cuda.current_stream(self.device).cuda_stream)
         if rc != 0:
-            raise RuntimeError(f"az_resnet_forward_leaves failed ({rc})")
+            raise RuntimeError(f"az_resnet_forward_leaves_v2 failed ({rc})")
         self.launches += 1
         return logits, values
 
     def forward_leaves(self, engine) -> Tensor:
         """-> trunk activations [n, 64, 6, 7] bf16 (channels-last memory) for the leaves of `engine.select_leaves()`."""
+        assert self.dtype == torch.bfloat16, "the trunk-only entry point is bf16 (az_trunk_forward_leaves)"
         n = engine.n_active
         if n not in self._out:
             self._out[n] = torch.empty((n, 6, 7, 64), dtype=torch.bfloat16, device=self.device)
@@ -399,15 +455,15 @@ class InferenceNet(nn.Module):
         if isinstance(m, BasicNN):
             self.input_layout = LAYOUT_GRID_F32
             self.net = m
-            if dtype == torch.bfloat16:  # hand-written tensor-core path
-                self.fused = TensorCoreMLP(m, torch.device(device))
+            if dtype in (torch.bfloat16, torch.float16):  # hand-written tensor-core path
+                self.fused = TensorCoreMLP(m, torch.device(device), dtype)
             else:
                 self.dtype = torch.float32
         elif isinstance(m, (CNNModel, ResNet)):
             self.input_layout = LAYOUT_PLANES_BF16 if dtype == torch.bfloat16 else LAYOUT_PLANES_F32
             self.trunk = None
-            if isinstance(m, ResNet) and m.num_channels == 64 and dtype == torch.bfloat16 and use_tensor_core_kernels:
-                self.trunk = TensorCoreTrunk(m, torch.device(device))  # hand-written tcgen05 kernel: trunk + heads (csrc/az_conv.cu)
+            if isinstance(m, ResNet) and m.num_channels == 64 and dtype in (torch.bfloat16, torch.float16) and use_tensor_core_kernels:
+                self.trunk = TensorCoreTrunk(m, torch.device(device), dtype)  # hand-written tcgen05 kernel: trunk + heads (csrc/az_conv.cu)
             self.net = self._fold(m).to(dtype).to(memory_format=torch.channels_last)
         else:
             self.input_layout = getattr(model, "input_layout", LAYOUT_PLANES_F32)
@@ -447,6 +503,38 @@ class InferenceNet(nn.Module):
             m.policy_head = fold_seq(m.policy_head)
             m.value_head = fold_seq(m.value_head)
         return m
+
+    @torch.no_grad()
+    def refresh(self, model: Model) -> bool:
+        """Take `model`'s weights in place (device addresses unchanged, so the CUDA graph captured around this net stays valid).
+        Returns False when the architecture differs and the caller must rebuild."""
+        if type(model).__name__ != self.kind:
+            return False
+        dev = next(self.net.parameters()).device
+        if self.fused is not None:
+            self.fused.set_weights(model)
+            return True
+        if self.trunk is not None:
+            if not self.trunk.set_weights(model):
+                return False
+        new = copy.deepcopy(model).eval().to(dev)
+        if isinstance(new, (CNNModel, ResNet)):
+            new = self._fold(new)
+        old_t = list(self.net.parameters()) + list(self.net.buffers())
+        new_t = list(new.parameters()) + list(new.buffers())
+        if len(old_t) != len(new_t) or any(a.shape != b.shape for a, b in zip(old_t, new_t)):
+            return False
+        for a, b in zip(old_t, new_t):
+            a.copy_(b.to(a.dtype))
+        return True
+
+    @property
+    def kernel_name(self) -> str:
+        if self.fused is not None:
+            return "k_mlp_fused"
+        if self.trunk is not None:
+            return "k_resnet_trunk"
+        return "k_encode + cuDNN/cuBLAS (torch)"
 
     @torch.no_grad()
     def forward_leaves(self, engine) -> tuple[Tensor, Tensor]:

@@ -102,9 +102,33 @@ class _GraphedStep:
         logits, values = self.evaluate()
         self.engine.expand_backup_select(logits, values, POLICY_LOGITS)
 
-    def run(self, num_steps: int, use_graph: bool):
+    def own_launches(self, num_steps: int) -> int:
+        """Kernels of libaz_engine.so launched (or replayed from the graph) by `run(num_steps)`: the first selection, then per
+        simulation one tree kernel and the evaluator's own kernel (the fused tensor-core kernel, or the leaf gather in front of
+        library GEMMs)."""
+        return 1 + 2 * num_steps
+
+    def run(self, num_steps: int, use_graph: bool, evaluator_events: list | None = None):
+        """`evaluator_events`: run un-graphed and append a (start, end) CUDA-event pair around every evaluator call."""
         e = self.engine
         if num_steps <= 0:
+            return
+        if evaluator_events is not None:
+            if self.n != e.n_active:
+                self.n = e.n_active
+                self.x = e.gather_leaves(self.layout)
+                self.graph = None
+            e.select_leaves()
+            for i in range(num_steps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                logits, values = self.evaluate()
+                b.record()
+                evaluator_events.append((a, b))
+                if i + 1 < num_steps:
+                    e.expand_backup_select(logits, values, POLICY_LOGITS)
+                else:
+                    e.expand_backup(logits, values, POLICY_LOGITS)
             return
         if self.n != e.n_active:
             self.n = e.n_active
@@ -150,6 +174,7 @@ class AlphaZeroSearch:
         self.use_tensor_core_kernels = use_tensor_core_kernels
         self._engine: Engine | None = None
         self._net = None
+        self._mode = None
         self._graphed: _GraphedStep | None = None
         self._refresh_net()
 
@@ -161,22 +186,53 @@ class AlphaZeroSearch:
         self._refresh_net()
 
     def _refresh_net(self):
+        """(Re)build the search-time form of the inference model.  With unchanged architecture the packed weights are rewritten
+        in place (same device addresses), so the captured CUDA graph of the simulation step stays valid.  The weights are
+        produced on the caller's current stream and consumed on whichever stream the search runs on (trainer.py plays on its own
+        stream from another thread): the stream is synchronised before returning, so no search can read half-written weights."""
         from .models import BasicNN, InferenceNet, Model
 
         m = self.inference_model
-        self._graphed = None
         if getattr(m, "az_builtin_eval_kind", 0) in (EVAL_UNIFORM, EVAL_HASH):
-            self._mode, self._net = "builtin", None
+            self._mode, self._net, self._graphed = "builtin", None, None
         elif isinstance(m, Model):
             dtype = self.inference_dtype or (torch.float32 if isinstance(m, BasicNN) else torch.bfloat16)
             dev = torch.device("cuda", torch.cuda.current_device() if self.device_index is None else self.device_index)
-            self._mode, self._net = "net", InferenceNet(m, dtype=dtype, device=dev, use_tensor_core_kernels=self.use_tensor_core_kernels)
+            if self._net is not None and self._mode == "net" and self._net.refresh(m):
+                pass  # in place: graph kept
+            else:
+                self._graphed = None
+                self._mode, self._net = "net", InferenceNet(m, dtype=dtype, device=dev, use_tensor_core_kernels=self.use_tensor_core_kernels)
+            torch.cuda.current_stream(dev).synchronize()
         else:
-            self._mode, self._net = "predict", None
+            self._mode, self._net, self._graphed = "predict", None, None
+
+    @property
+    def evaluator_name(self) -> str:
+        """The kernel that evaluates the leaves (bench.py's roofline names it)."""
+        if self._mode == "builtin":
+            return "k_run_sims (built-in evaluator)"
+        if self._mode == "net":
+            return self._net.kernel_name
+        return "user predict()"
+
+    def launches_per_move_step(self) -> int:
+        """Kernels of libaz_engine.so per self-play move step (`simulate_and_move`)."""
+        if self._mode == "builtin":
+            return 1
+        return 1 + 2 * self.num_simulations + 1  # first select; per simulation evaluator (or gather) + tree kernel; sample_moves
+
+    def close(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+        self._graphed = None
 
     # -- engine ----------------------------------------------------------------------------------
-    def engine_for(self, n: int) -> Engine:
-        if self._engine is None or self._engine.num_games < n:
+    def engine_for(self, n: int, exact: bool = False) -> Engine:
+        """The engine for n trees: grown when too small; `exact` (the self-play loop, whose slots ARE the games) also replaces a
+        larger one left behind by an earlier `run_simulations` call."""
+        if self._engine is None or self._engine.num_games < n or (exact and self._engine.num_games != n):
             if self._engine is not None:
                 self._engine.close()
             self._engine = Engine(num_games=n, num_simulations=self.num_simulations, c_puct=float(self.exploration_weight),
@@ -184,15 +240,16 @@ class AlphaZeroSearch:
             self._graphed = None
         return self._engine
 
-    def simulate(self, engine: Engine, num_simulations: int | None = None):
-        """`num_simulations` simulations on every active tree of `engine` (roots already set)."""
+    def simulate(self, engine: Engine, num_simulations: int | None = None, evaluator_events: list | None = None):
+        """`num_simulations` simulations on every active tree of `engine` (roots already set).  `evaluator_events` (network
+        evaluators only): run the steps un-graphed and collect a CUDA-event pair around every evaluator call."""
         S = self.num_simulations if num_simulations is None else num_simulations
         if self._mode == "builtin":
             engine.run_simulations(S, self.inference_model.az_builtin_eval_kind)
         elif self._mode == "net":
             if self._graphed is None or self._graphed.engine is not engine:
                 self._graphed = _GraphedStep(engine, self._net, self._net.input_layout)
-            self._graphed.run(S, self.use_cuda_graph)
+            self._graphed.run(S, self.use_cuda_graph, evaluator_events)
         else:
             self._simulate_predict(engine, S)
 

@@ -139,15 +139,20 @@ class Trainer:
         False runs the same steps eagerly (same minibatches, same arithmetic).  `trainer_share`: fraction of the games rank 0 plays
         (`distributed.shard_range`); None = equal shards.  `save_every_n_iterations` > 0: after every n-th round of games rank 0
         writes the replay deque as `<save_dir>/episodes_iter{N}.json` (`DataModule._save_episodes`, datamodule.py:71-80,109-112;
-        default directory "episodes", datamodule.py:63) and, after that iteration's training, the weights as
-        `<save_dir>/model_iter{N}.pt` (the reference's `ModelCheckpoint(every_n_epochs=...)`, trainer.py:66-70)."""
+        default directory "episodes", datamodule.py:63) and, after that iteration's training, a Lightning-shaped checkpoint
+        `<save_dir>/model_iter{N}.ckpt` (`{"state_dict", "hyper_parameters", "epoch", "global_step"}`, the reference's
+        `ModelCheckpoint(every_n_epochs=...)`, trainer.py:66-70; read back with `Model.load_from_checkpoint`, scripts/play.py:19)."""
         import threading
 
         world = dist.get_world_size() if dist.is_initialized() else 1
         rank = dist.get_rank() if dist.is_initialized() else 0
-        lo, hi = shard_range(episodes_per_iter, rank, world, trainer_share)
-        if hi == lo:
-            raise ValueError("trainer_share leaves a rank without games")
+        # the whole shard table is checked identically on every rank BEFORE any collective: a rank that raised alone would leave
+        # the others waiting in the all-gather
+        shards = [shard_range(episodes_per_iter, r, world, trainer_share) for r in range(world)]
+        if any(h == l for l, h in shards):
+            raise ValueError(f"every rank needs at least one game: shards {shards} (episodes_per_iter={episodes_per_iter}, "
+                             f"world={world}, trainer_share={trainer_share})")
+        lo, hi = shards[rank]
         model = self.model.to(self.device)
         kw = {} if inference_dtype is None else dict(inference_dtype=inference_dtype)
         gen = EpisodeGenerator(model=model, num_simulations=simulations_per_episode, num_episodes=hi - lo,
@@ -175,6 +180,8 @@ class Trainer:
                 box["error"] = exc
 
         def start():
+            # the inference weights were (re)built on this thread's current stream; the games run on play_stream
+            play_stream.wait_stream(torch.cuda.current_stream(self.device))
             th = threading.Thread(target=play, daemon=True)
             th.start()
             return th
@@ -216,8 +223,10 @@ class Trainer:
                 loss_sum, n_steps = steps.run(replay, epochs_per_iter, g, use_graph=cuda_graph)
                 model.eval()
             torch.cuda.current_stream(self.device).synchronize()
-            if saving:
-                torch.save(model.state_dict(), os.path.join(save_dir or "episodes", f"model_iter{it + 1}.pt"))
+            if saving:  # the reference's ModelCheckpoint file shape (trainer.py:66-70), readable by Model.load_from_checkpoint
+                gstep = sum(h["optimizer_steps"] for h in self.history) + n_steps
+                model.save_checkpoint(os.path.join(save_dir or "episodes", f"model_iter{it + 1}.ckpt"),
+                                      epoch=(it + 1) * epochs_per_iter, global_step=gstep)
             t3 = time.perf_counter()
             self.history.append(dict(iteration=it, episodes=len(replay), samples=replay.num_samples, selfplay_s=selfplay_s,
                                      wait_for_selfplay_s=t1 - t0, gather_s=t2 - t1, train_s=t3 - t2, weight_bytes=nbytes,

@@ -1,24 +1,31 @@
 #!/usr/bin/env python
-"""Headline benchmark: MCTS simulations/s (and self-play games/s) for Connect4 self-play on B200.
+"""Headline benchmark: MCTS simulations/s (and self-play games/s) for Connect4 self-play on B200, network in the loop.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (N=1): BASELINE.json configs[1] — 4096 concurrent games x 200 simulations/move with the
-deterministic uniform-prior evaluator (the bit-exact parity configuration).  One STEP = one move step of
-the self-play loop for every game: `az_run_move_step` = 200 simulations per tree (`az_run_simulations`) and the move
-(`az_sample_moves`: record samples, draw moves, recycle finished games) in ONE launch of `k_run_sims`.  With N > 1 every rank runs its own
-4096 games (weak scaling, no collective on the data path); finished episodes are all-gathered over NCCL
-after the timed region and that time is reported separately.
+Workload.  N = 1: BASELINE.json configs[2] — 16384 concurrent games x 800 simulations/move with a bf16 ResNet-style
+policy/value net (4 residual blocks x 64 channels, random init, 25.3 MFLOP per position) in the loop: every simulation step
+is one evaluator launch over all leaves (`k_resnet_trunk`, hand-written tcgen05, leaf gather + heads fused) and one tree
+launch (`k_expand_select`).  N > 1: configs[3] — 65536 games sharded over the ranks (65536 / N per GPU, "strong" split of the
+fixed total), and the episodes finished in the timed region are all-gathered over NCCL INSIDE the timed region.
+One STEP = one move step of the self-play loop for every game (episode_generator.py:48-78): 800 simulations per tree, then the
+move (`az_sample_moves`: record the samples, draw the moves, recycle finished games).
 
-`value`   device-resident: uniforms already in HBM, CUDA events around each step, L2 flushed between steps.  Both GPU legs
-          run 48 untimed burn-in move steps first, so that what is timed is the stationary mix of a running self-play loop
-          (games at every stage, finishing and restarting) and not the cheaper opening moves all games share after a reset.
-`e2e`     the public API (`EpisodeGenerator.generate_batches`): per step the uniforms come from pinned host
-          memory and finished episodes + counters are read back to the host.
-`--impl reference`  the CPU arm: the reference algorithm (oracle/c4_oracle.c, the C restatement pinned against
-          the reference's own outputs; the reference itself is pure Python that cannot travel to the GPU box)
-          on all host cores via OpenMP, same workload, bounded sample per step.
+`value`   device-resident: the steps' uniforms are already in HBM, one CUDA-event pair around the K timed steps, max over
+          ranks.  `burn-in` untimed move steps come first so that the timed steps see the stationary mix of a running
+          self-play loop (games at every stage, finishing and restarting), not the opening all games share after a reset.
+          No L2 flush: one step streams the 2.2 GB tree arena (16384 trees x 5608 nodes x 24 B) 800 times, far beyond the 126 MB L2.
+`e2e`     the public API (`EpisodeGenerator.iter_steps`) continuing the same games: per step the uniforms come from pinned host
+          memory and the finished episodes + ring counters are read back to pinned host memory (N > 1: plus the all-gather).
+`roofline` of the dominant kernel (`k_resnet_trunk`, tensor-bound): algorithmic FLOPs per launch (evaluated leaves x FLOPs per
+          position) / the kernel's mean duration, CUDA events around every one of its 800 launches in one extra un-graphed move
+          step right after the timed region, against the measured sustained bf16 rate of MEASURED_PEAKS.json.
+`--impl reference`  the CPU arm: the reference algorithm (oracle/c4_oracle.c, the C restatement pinned to the reference's own
+          outputs; OpenMP over trees) with the SAME network evaluated by stock PyTorch CPU kernels, one batched `predict` per
+          simulation step exactly as search.py:82-84 does, on all host cores; each step a bounded sample (fewer games) of the
+          same workload.  When baseline/_ref holds the reference's own Python (scripts/install_reference.py), its
+          `EpisodeGenerator` is timed as well (`reference_python`: BASELINE config 1 exactly, E = 100, and one process per core).
 """
 from __future__ import annotations
 
@@ -38,24 +45,59 @@ NODE_BYTES = 20  # W f64 + N u32 + P f32 + CB u32
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--games", type=int, default=4096)
-    ap.add_argument("--sims", type=int, default=200)
-    ap.add_argument("--evaluator", default="uniform", choices=["uniform", "hash"])
-    ap.add_argument("--lanes", type=int, default=0, help="lanes per tree: 8, 32 or 0 = engine default")
-    ap.add_argument("--hot-nodes", type=int, default=None, help="nodes per tree kept in shared memory by the fused kernel (default: automatic)")
+    ap.add_argument("--games", type=int, default=None, help="total games: default 16384 on one GPU (configs[2]), 65536 sharded over N > 1 (configs[3])")
+    ap.add_argument("--sims", type=int, default=800)
+    ap.add_argument("--net", default="resnet4x64", help="network in the loop: resnetBxC | basic | cnn")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"], help="operand format of the evaluator (fp32 accumulate)")
+    ap.add_argument("--burn-in", type=int, default=36, help="untimed move steps before the warm-up (games reach their stationary mix)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--burn-in", type=int, default=48, help="untimed move steps before the warm-up (games reach their stationary mix)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-tree-scaling", action="store_true")
-    ap.add_argument("--net", default="basic_tc,resnet4x64", help="network-in-the-loop side measurements, comma separated: basic_tc | basic | resnetBxC | none")
-    ap.add_argument("--net-games", type=int, default=16384, help="network-in-the-loop games on one GPU (BASELINE configs[2])")
-    ap.add_argument("--net-games-sharded", type=int, default=65536, help="total games sharded over the ranks when N > 1 (configs[3])")
-    ap.add_argument("--net-sims", type=int, default=800)
-    ap.add_argument("--net-steps", type=int, default=2)
+    ap.add_argument("--extras", default="config2,tree_scaling,basic,resnet9x128,cnn",
+                    help="side measurements on one GPU, comma separated: config2 | tree_scaling | basic | resnetBxC | cnn | none")
+    ap.add_argument("--extra-steps", type=int, default=3)
+    ap.add_argument("--cpu-games", type=int, default=256, help="games of the CPU arm's bounded sample")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
     return ap.parse_args()
+
+
+def total_games(args, world: int) -> int:
+    return args.games if args.games else (16384 if world == 1 else 65536)
+
+
+def net_label(spec: str) -> str:
+    return {"basic": "BasicNN 42-512-512-{7,2}", "cnn": "CNNModel 3-64-128-256 + FC 10752-512"}.get(spec, "ResNet " + spec.replace("resnet", "") + " (blocks x channels)")
+
+
+def workload_config(args, world: int) -> dict:
+    """The workload description both arms print (identical keys and values)."""
+    G = total_games(args, world)
+    return {"workload": f"connect4_selfplay_{args.net}_{args.dtype}_{G}x{args.sims}", "num_games": G, "num_simulations": args.sims,
+            "net": net_label(args.net), "evaluator_dtype": args.dtype, "c_puct": 1.0, "parallelism": f"games sharded x{world}",
+            "l2": "no flush: every step streams a tree arena far larger than the 126 MB L2 (2.2 GB at 16384 x 800)"}
+
+
+def make_model(spec: str, seed: int = 0):
+    import torch
+
+    import alphazero_implementation_b200 as az
+
+    torch.manual_seed(seed)
+    if spec == "basic":
+        return az.BasicNN(), 577_024
+    if spec == "cnn":
+        return az.CNNModel(), 42_122_000
+    b, c = spec.replace("resnet", "").split("x")
+    m = az.ResNet(num_res_blocks=int(b), num_channels=int(c))
+    return m, m.flops_per_position()
+
+
+def torch_dtype(name: str):
+    import torch
+
+    return {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[name]
 
 
 def load_peaks():
@@ -63,28 +105,25 @@ def load_peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))),
-                    source="measured (MEASURED_PEAKS.json)")
+                    source="measured (MEASURED_PEAKS.json; bf16 = the sustained figure: the kernel is timed inside a long step)")
     return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a thread (the timed
-    region of this workload lasts only milliseconds, far below nvidia-smi's own start-up time)."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread."""
 
     REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period_s: float = 0.02):
         import threading
 
         self.samples, self.reason_bits, self.power = [], 0, []
-        self.stop_flag = False
-        self.ok = False
+        self.stop_flag, self.ok, self.period = False, False, period_s
         try:
             import pynvml
 
             pynvml.nvmlInit()
-            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it lists indices
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")  # NVML enumerates physical GPUs
             phys = index
             if vis:
                 ids = [v.strip() for v in vis.split(",") if v.strip()]
@@ -100,17 +139,15 @@ class ClockSampler:
         self.t.start()
 
     def _run(self):
-        nv, i = self.nv, 0
+        nv = self.nv
         while not self.stop_flag:
-            try:  # clock and throttle reasons every pass, power every fourth (each NVML call costs about a millisecond)
+            try:
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                if i % 4 == 0:
-                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            i += 1
-            time.sleep(0.001)
+            time.sleep(self.period)
 
     def stop(self) -> dict:
         if not self.ok:
@@ -120,14 +157,11 @@ class ClockSampler:
         sm = sorted(self.samples)
         reasons = sorted(k for k, bit in self.REASONS.items() if self.reason_bits & bit)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "power_w_max": max(self.power) if self.power else None,
-                "samples": len(sm), "reasons": reasons, "source": "NVML polled every 2 ms during the timed region"}
+                "samples": len(sm), "reasons": reasons, "source": "NVML polled every 20 ms during the timed region"}
 
 
 def algorithmic_bytes(st: dict) -> int:
-    """Bytes the tree kernels must move for the work counted in `st` ('algorithmic bytes'):
-    select reads one 20-byte record per child scanned plus the root's N and CB (8 B) per simulation;
-    expansion writes one 20-byte record per child created plus the leaf's CB (4 B);
-    backup reads and writes W (f64) and N (u32) of every node on the path (24 B)."""
+    """Bytes the tree kernels must move for the work counted in `st` ('algorithmic bytes')."""
     return (st["children_scanned"] * NODE_BYTES + st["simulations"] * 8 + st["children_created"] * NODE_BYTES
             + st["evaluations"] * 4 + st["backup_nodes"] * 24)
 
@@ -136,157 +170,280 @@ def diff(a: dict, b: dict) -> dict:
     return {k: b[k] - a[k] for k in a}
 
 
-# --------------------------------------------------------------------------------------------------
-def cpu_arm(E: int, S: int, kind: int, target_s: float = 12.0):
-    """The reference algorithm on the host cores (C restatement, OpenMP over trees).  A step = one move
-    step of the E-game self-play loop; the sample is however many steps fit in ~target_s."""
+# --------------------------------------------------------------------------------------------------  CPU arm
+def host_cores() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def cpu_model_name() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_arm_net(spec: str, E: int, S: int, target_s: float, max_steps: int = 10**6):
+    """The reference algorithm on the host cores with the network in the loop: C restatement of the tree search (OpenMP over
+    trees) + the same torch module on CPU in fp32, one batched forward per simulation step (search.py:82-84).  A step = one move
+    step of E games x S simulations; as many steps as fit in ~target_s (at least one)."""
+    import numpy as np
+    import torch
+
+    from oracle import c4oracle
+    from oracle.net_eval import TorchNetEvaluator
+
+    c4oracle.build()
+    cores = host_cores()
+    cores = c4oracle.set_threads(cores)  # explicit: torchrun exports OMP_NUM_THREADS=1 to its workers
+    torch.set_num_threads(cores)
+    model, _ = make_model(spec)
+    ev = TorchNetEvaluator(model)
+    rng = np.random.RandomState(0)
+    # probe: a few simulation steps (thread pools, allocator), then size the sample
+    t0 = time.perf_counter()
+    c4oracle.search(np.zeros(E, np.uint64), np.zeros(E, np.uint64), np.zeros(E, np.uint8), 24, py_eval=ev)
+    t_sim = (time.perf_counter() - t0) / 24
+    steps = max(1, min(max_steps, int(target_s / max(t_sim * S, 1e-3))))
+    t0 = time.perf_counter()
+    r = c4oracle.selfplay(E, S, rng.random_sample((steps, E)), quota=10**9, py_eval=ev)
+    dt = time.perf_counter() - t0
+    return dict(sims_per_s=r.n_sims / dt, games_per_s=len(r.ep_slot) / dt, steps=steps, seconds=dt, cores=cores, ms_per_step=dt / steps * 1e3,
+                sims=r.n_sims, evals=r.n_evals, games=E)
+
+
+def cpu_arm_builtin(E: int, S: int, kind: int, target_s: float = 8.0):
+    """Same with a built-in deterministic evaluator (config 2 side measurement)."""
     import numpy as np
 
     from oracle import c4oracle
 
     c4oracle.build()
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    cores = c4oracle.set_threads(cores)  # explicit: torchrun exports OMP_NUM_THREADS=1 to its workers
+    cores = c4oracle.set_threads(host_cores())
     rng = np.random.RandomState(0)
-    c4oracle.selfplay(E, S, rng.random_sample((2, E)), quota=10**9, eval_kind=kind)  # thread pool + page faults
+    c4oracle.selfplay(E, S, rng.random_sample((2, E)), quota=10**9, eval_kind=kind)
     t0 = time.perf_counter()
-    c4oracle.selfplay(E, S, rng.random_sample((5, E)), quota=10**9, eval_kind=kind)
-    t1 = (time.perf_counter() - t0) / 5
+    c4oracle.selfplay(E, S, rng.random_sample((3, E)), quota=10**9, eval_kind=kind)
+    t1 = (time.perf_counter() - t0) / 3
     steps = max(1, min(3000, int(target_s / max(t1, 1e-4))))
     t0 = time.perf_counter()
     r = c4oracle.selfplay(E, S, rng.random_sample((steps, E)), quota=10**9, eval_kind=kind)
     dt = time.perf_counter() - t0
-    return dict(sims_per_s=r.n_sims / dt, games_per_s=len(r.ep_slot) / dt, steps=steps, seconds=dt, cores=cores,
-                ms_per_step=dt / steps * 1e3, sims=r.n_sims)
+    return dict(sims_per_s=r.n_sims / dt, steps=steps, seconds=dt, cores=cores)
+
+
+def reference_python_leg(budget_s: float = 45.0):
+    """The reference's OWN Python (`EpisodeGenerator` -> `AlphaZeroSearch` -> `BasicNN.predict`, imported unchanged from
+    baseline/_ref, populated by scripts/install_reference.py) on this host: BASELINE config 1 exactly (scripts/train.py:12-19 with
+    E = 1: S = 100, BasicNN, seeds 0, one thread), the reference's production batching E = 100, and one process per core.
+    The game under it is the CPU restatement oracle/shims/simulator (the third-party C++ `simulator` 0.0.4 is not available)."""
+    import subprocess
+
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "alphazero_implementation")):
+        return {"unavailable": "baseline/_ref/alphazero_implementation missing (run scripts/install_reference.py where /root/reference exists)"}
+    worker = os.path.join(ROOT, "scripts", "time_reference_python.py")
+    cores = host_cores()
+    out = {"cores": cores, "cpu_model": cpu_model_name(), "game": "oracle/shims/simulator (CPU restatement of simulator 0.0.4)",
+           "torch_threads_per_process": 1}
+
+    def run(E, seed, seconds):
+        return subprocess.Popen([sys.executable, worker, "--episodes", str(E), "--sims", "100", "--seed", str(seed), "--seconds", str(seconds)],
+                                stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1"))
+
+    def collect(procs):
+        res = []
+        for p in procs:
+            so, se = p.communicate(timeout=600)
+            if p.returncode != 0:
+                raise RuntimeError(se[-500:])
+            res.append(json.loads(so.strip().splitlines()[-1]))
+        return res
+
+    try:
+        per = budget_s / 3
+        [c1] = collect([run(1, 0, per)])
+        out["config1_E1_S100_basicnn_1core"] = c1
+        [e100] = collect([run(100, 0, per)])
+        out["E100_S100_basicnn_1process"] = e100
+        allc = collect([run(1, s, per) for s in range(cores)])
+        out["config1_one_process_per_core"] = {"processes": cores, "sims_per_s": sum(r["sims_per_s"] for r in allc),
+                                               "games_per_s": sum(r["games_per_s"] for r in allc)}
+    except Exception as exc:  # the port below remains the arm's value
+        out["error"] = repr(exc)[:300]
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    kind = 1 if args.evaluator == "uniform" else 2
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_arm(args.games, args.sims, kind, target_s=1.0)
-    res = cpu_arm(args.games, args.sims, kind, target_s=max(4.0, min(60.0, 0.5 * args.steps)))
-    sample = f"{res['steps']} move steps of {args.games} games x {args.sims} sims from the initial position ({res['seconds']:.1f} s)"
+    # K steps of the bounded sample, sized to finish within a few minutes: one probe, then at most K move steps in ~3 x cpu-seconds
+    res = cpu_arm_net(args.net, args.cpu_games, args.sims, target_s=max(10.0, 3.0 * args.cpu_seconds), max_steps=max(1, args.steps))
+    sample = (f"{res['steps']} move steps of {res['games']} games x {args.sims} sims from the initial position ({res['seconds']:.1f} s): "
+              f"oracle/c4_oracle.c (OpenMP over trees) + the same {args.net} torch module in fp32 on {res['cores']} host threads, "
+              "one batched forward per simulation step")
     line = {
         "impl": "reference", "metric": "mcts_simulations_per_sec", "value": res["sims_per_s"], "unit": "sims/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "games_per_sec": res["games_per_s"],
-        "config": {"workload": f"connect4_selfplay_{args.evaluator}_{args.games}x{args.sims}", "num_games": args.games,
-                   "num_simulations": args.sims, "evaluator": args.evaluator, "c_puct": 1.0},
-        "cpu_baseline": {"value": res["sims_per_s"], "unit": "sims/s", "cores": res["cores"], "kind": "port", "sample": sample},
+        "steps": res["steps"], "warmup": 1, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "games_per_sec": res["games_per_s"],
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": res["sims_per_s"], "unit": "sims/s", "cores": res["cores"], "kind": "port", "sample": sample,
+                         "cpu_model": cpu_model_name()},
         "e2e": {"value": res["sims_per_s"], "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference algorithm as the C restatement oracle/c4_oracle.c (pinned to the reference's own outputs), OpenMP over trees; "
-                "the reference itself is pure Python (~2e3 sims/s/core, SURVEY.md §6) and its tree is not on the GPU box",
+        "reference_python": reference_python_leg(),
+        "note": "reference algorithm as the C restatement oracle/c4_oracle.c (pinned to the reference's own outputs), network by stock "
+                "PyTorch CPU kernels; `reference_python` = the reference's unmodified Python on this host (its only runnable configs)",
     }
     print(json.dumps(line), flush=True)
 
 
-# --------------------------------------------------------------------------------------------------
-def net_in_loop(args, device_index: int, peaks: dict, world: int = 1, rank: int = 0):
-    """Side measurements with a network in the loop: self-play move steps of E games x S sims, one evaluator call per
-    simulation step.  One GPU: BASELINE configs[2] (16384 games x 800 sims).  N > 1 GPUs: configs[3] — 65536 games sharded
-    over the ranks (65536 / N per GPU), every rank times its own shard between barriers and the job's time is the max over
-    ranks (the episode all-gather is timed in the main section; scripts/run_config4.py plays whole rounds).
-    `resnetBx64`: bf16 ResNet-style net on the hand-written tcgen05 kernel (csrc/az_conv.cu: trunk + heads, leaf gather
-    fused); other widths: conv/linear layers = cuDNN/cuBLAS tensor-core GEMMs.  `basic_tc`: the reference's BasicNN on the
-    hand-written tcgen05 kernel (csrc/az_mlp.cu, leaf gather fused)."""
+# --------------------------------------------------------------------------------------------------  GPU arm
+def concat_device(parts: list[dict]) -> dict:
+    """Drained episode dicts (device tensors) -> one dict, sample offsets rebased."""
     import torch
-    import torch.distributed as dist
+
+    parts = [p for p in parts if p["ep_len"].numel()] or parts[:1]
+    out, base = {}, 0
+    offs = []
+    for p in parts:
+        offs.append(p["ep_offset"] + base)
+        base += int(p["s_bb0"].numel())
+    for k in parts[0]:
+        out[k] = torch.cat(offs) if k == "ep_offset" else torch.cat([p[k] for p in parts])
+    return out
+
+
+def kernel_timing_step(search, eng, u):
+    """One more move step, un-graphed, with a CUDA-event pair around every evaluator launch -> list of ms."""
+    import torch
+
+    pairs: list = []
+    search.simulate(eng, evaluator_events=pairs)
+    eng.sample_moves(u)
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in pairs]
+
+
+def net_extra(args, spec: str, device_index: int, peaks: dict):
+    """Side measurement: another network in the loop at 16384 games x S sims on one GPU.  Burn-in with the fused uniform
+    evaluator (cheap; a random-init net plays a near-uniform game too), then warm-up + timed move steps with the net."""
+    import numpy as np
+    import torch
 
     import alphazero_implementation_b200 as az
+    from alphazero_implementation_b200.engine import EVAL_UNIFORM
 
-    out = []
-    for spec in [s for s in args.net.split(",") if s and s != "none"]:
-        kw = {}
-        if spec == "basic_tc":
-            model, name, flops, kw = az.BasicNN(), "BasicNN (tcgen05 fused MLP, bf16)", 577_024, dict(inference_dtype=torch.bfloat16)
-        elif spec == "basic":
-            model, name, flops = az.BasicNN(), "BasicNN (fp32, cuBLAS)", 577_024
-        else:
-            b, c = spec.replace("resnet", "").split("x")
-            model = az.ResNet(num_res_blocks=int(b), num_channels=int(c))
-            how = "tcgen05 fused kernel" if int(c) == 64 else "cuDNN"
-            name, flops = f"ResNet {b}x{c} (bf16, {how})", model.flops_per_position()
-        total_games = args.net_games if world == 1 else args.net_games_sharded
-        E, S = total_games // world, args.net_sims
-        torch.manual_seed(0)
-        search = az.AlphaZeroSearch(model=model, num_simulations=S, device=device_index, **kw)
-        eng = search.engine_for(E)
-        eng.reset_games()
-        g = torch.Generator(device="cpu").manual_seed(1 + rank)
-        u = torch.rand((args.net_steps + 1, E), dtype=torch.float64, generator=g).to(eng.device)
-        search.simulate(eng)  # warm-up move step (includes graph capture)
-        eng.sample_moves(u[0])
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        st0 = eng.stats()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for i in range(args.net_steps):
-            search.simulate(eng)
-            eng.sample_moves(u[i + 1])
-        ev1.record()
-        torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1)
-        st = diff(st0, eng.stats())
-        sims, evals = float(st["simulations"]), float(st["evaluations"])
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            c = torch.tensor([sims, evals], dtype=torch.float64, device=eng.device)
-            dist.all_reduce(c, op=dist.ReduceOp.SUM)
-            ms, sims, evals = float(t.item()), float(c[0].item()), float(c[1].item())
+    model, flops = make_model(spec)
+    E, S = 16384, args.sims
+    dt = torch.bfloat16 if args.dtype == "fp32" else torch_dtype(args.dtype)
+    search = az.AlphaZeroSearch(model=model, num_simulations=S, device=device_index, inference_dtype=dt)
+    eng = search.engine_for(E)
+    eng.reset_games()
+    n = args.extra_steps
+    u = torch.from_numpy(np.random.RandomState(5).random_sample((32 + 2 + n, E))).to(eng.device)
+    for i in range(32):
+        eng.run_move_step(S, EVAL_UNIFORM, u[i])
+        if i % 8 == 7:
             eng.drain_episodes_device()
-        else:
-            eng.drain_episodes()
-        sims_s = sims / ms * 1e3
-        evals_s = E * world * S * args.net_steps / ms * 1e3  # every slot occupies a batch row each simulation
-        rec = {"workload": f"connect4_selfplay_{spec}_{total_games}x{S}", "net": name, "num_games": total_games, "games_per_gpu": E,
-               "n_gpus": world, "num_simulations": S, "move_steps": args.net_steps, "sims_per_s": sims_s,
-               "us_per_sim_step": ms * 1e3 / (args.net_steps * S), "flops_per_position": flops, "tensor_tflops": evals_s * flops / 1e12,
-               "tensor_pipe_frac_of_measured_bf16": evals_s * flops / 1e12 / (peaks["bf16_tflops"] * world),
-               "leaf_eval_fraction": evals / max(1.0, sims)}
-        out.append(rec)
-        search._engine.close()
-        del search, eng
-        torch.cuda.empty_cache()
-    return out or None
+    search.simulate_and_move(eng, u[32])  # warm-up (graph capture)
+    eng.drain_episodes_device()
+    torch.cuda.synchronize()
+    st0 = eng.stats()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(n):
+        search.simulate_and_move(eng, u[33 + i])
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    st = diff(st0, eng.stats())
+    k_ms = kernel_timing_step(search, eng, u[33 + n])
+    eng.drain_episodes_device()
+    k_mean = float(np.mean(k_ms))
+    evals_per_launch = st["evaluations"] / (n * S)
+    rec = {"workload": f"connect4_selfplay_{spec}_{args.dtype}_{E}x{S}", "net": net_label(spec), "evaluator": search.evaluator_name,
+           "move_steps": n, "sims_per_s": st["simulations"] / ms * 1e3, "us_per_sim_step": ms * 1e3 / (n * S),
+           "flops_per_position": flops, "evaluator_kernel_us": k_mean * 1e3,
+           "tensor_tflops_in_kernel": evals_per_launch * flops / (k_mean * 1e-3) / 1e12,
+           "tensor_frac_of_measured_bf16": evals_per_launch * flops / (k_mean * 1e-3) / 1e12 / peaks["bf16_tflops"],
+           "leaf_eval_fraction": st["evaluations"] / max(1, st["simulations"])}
+    search.close()
+    return rec
 
 
-def tree_scaling(args, device_index: int, peaks: dict, kind: int):
-    """The fused tree kernel at larger tree counts (same S, same evaluator): the kernel is latency-bound, so its fraction
+def config2_extra(args, device_index: int, peaks: dict):
+    """BASELINE configs[1] (last round's headline): 4096 games x 200 sims, uniform evaluator, the fused `k_run_sims` move step."""
+    import numpy as np
+    import torch
+
+    import alphazero_implementation_b200 as az
+    from alphazero_implementation_b200.engine import EVAL_UNIFORM
+
+    E, S, K = 4096, 200, 30
+    eng = az.Engine(num_games=E, num_simulations=S, device=device_index)
+    eng.reset_games()
+    u = torch.from_numpy(np.random.RandomState(1000).random_sample((48 + K, E))).to(eng.device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
+    for i in range(48):
+        eng.run_move_step(S, EVAL_UNIFORM, u[i])
+        if i % 8 == 7:
+            eng.drain_episodes_device()
+    torch.cuda.synchronize()
+    st0 = eng.stats()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+    for i in range(K):
+        flush.zero_()
+        ev[i][0].record()
+        eng.run_move_step(S, EVAL_UNIFORM, u[48 + i])
+        ev[i][1].record()
+        if i % 8 == 7:
+            eng.drain_episodes_device()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    st = diff(st0, eng.stats())
+    gbs = algorithmic_bytes(st) / (ms * 1e-3) / 1e9
+    eng.close()
+    cpu = cpu_arm_builtin(E, S, 1, target_s=6.0)
+    return {"workload": f"connect4_selfplay_uniform_{E}x{S}", "kernel": "k_run_sims (fused search + move, one launch per step)", "steps": K,
+            "sims_per_s": st["simulations"] / ms * 1e3, "ms_per_step": ms / K, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"],
+            "l2": "flushed between steps", "cpu_port_sims_per_s": cpu["sims_per_s"], "cpu_cores": cpu["cores"]}
+
+
+def tree_scaling(args, device_index: int, peaks: dict):
+    """The fused tree kernel (uniform evaluator) at S = 800 and at S = 200 for larger tree counts: latency-bound, so its fraction
     of the HBM roofline grows with the number of independent trees until the issue slots fill."""
     import numpy as np
     import torch
 
     import alphazero_implementation_b200 as az
+    from alphazero_implementation_b200.engine import EVAL_UNIFORM
 
     out = []
-    for E in (16384, 65536):
-        eng = az.Engine(num_games=E, num_simulations=args.sims, device=device_index, lanes_per_tree=args.lanes, hot_nodes=args.hot_nodes)
+    for E, S in ((4096, 800), (16384, 800), (65536, 800), (16384, 200), (65536, 200)):
+        eng = az.Engine(num_games=E, num_simulations=S, device=device_index)
         eng.reset_games()
-        u = torch.from_numpy(np.random.RandomState(5).random_sample((8, E))).to(eng.device)
-        for i in range(3):
-            eng.run_simulations(args.sims, kind)
-            eng.sample_moves(u[i])
+        u = torch.from_numpy(np.random.RandomState(5).random_sample((16, E))).to(eng.device)
+        for i in range(11):
+            eng.run_move_step(S, EVAL_UNIFORM, u[i])
+        eng.drain_episodes_device()
         torch.cuda.synchronize()
         st0 = eng.stats()
         ms = 0.0
         for i in range(5):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            eng.run_simulations(args.sims, kind)
+            eng.run_move_step(S, EVAL_UNIFORM, u[11 + i])
             b.record()
-            eng.sample_moves(u[3 + i])
             torch.cuda.synchronize()
             ms += a.elapsed_time(b)
         st = diff(st0, eng.stats())
         gbs = algorithmic_bytes(st) / (ms * 1e-3) / 1e9
-        out.append({"trees": E, "num_simulations": args.sims, "kernel": "k_run_sims", "kernel_ms": ms / 5, "sims_per_s": st["simulations"] / ms * 1e3,
-                    "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]})
+        out.append({"trees": E, "num_simulations": S, "kernel": "k_run_sims", "kernel_ms": ms / 5, "sims_per_s": st["simulations"] / ms * 1e3,
+                    "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"], "bytes_per_sim": algorithmic_bytes(st) / max(1, st["simulations"])})
         eng.close()
         del eng
         torch.cuda.empty_cache()
@@ -299,112 +456,131 @@ def run_b200(args):
     import torch.distributed as dist
 
     import alphazero_implementation_b200 as az
-    from alphazero_implementation_b200.engine import EVAL_HASH, EVAL_UNIFORM
 
-    os.environ["NCCL_DEBUG"] = "WARN"  # NCCL_DEBUG=VERSION/INFO prints to stdout; stdout carries exactly one JSON line
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # NCCL's communicator lines go to stderr (stdout carries exactly one JSON line); they show the rank count per communicator
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    W, K = max(3, args.warmup), max(1, args.steps)
-    # Untimed burn-in before the warm-up: the games start together from the empty board, and the first ~40 move steps (opening
-    # positions, no game finished yet) are cheaper than the stationary mix of a running self-play loop that the metric is about.
-    # The CPU arm measures hundreds of steps, i.e. the same stationary mix.
-    W += args.burn_in
-    E, S = args.games, args.sims
-    kind = EVAL_UNIFORM if args.evaluator == "uniform" else EVAL_HASH
-    peaks = load_peaks()
+    from alphazero_implementation_b200.distributed import all_gather_episodes, shard_range
 
-    eng = az.Engine(num_games=E, num_simulations=S, device=local, lanes_per_tree=args.lanes, hot_nodes=args.hot_nodes)
+    W, K = max(3, args.warmup), max(1, args.steps)
+    G, S = total_games(args, world), args.sims
+    lo, hi = shard_range(G, rank, world)
+    E = hi - lo
+    peaks = load_peaks()
+    model, flops = make_model(args.net)
+    gen = az.EpisodeGenerator(model=model, num_simulations=S, num_episodes=E, game_initial_state=az.Config(6, 7, 4).sample_initial_state(),
+                              device=local, inference_dtype=torch_dtype(args.dtype))
+    search = gen.search
+    eng = search.engine_for(E)
     eng.reset_games()
     rng = np.random.RandomState(1000 + rank)
-    u_all = torch.from_numpy(rng.random_sample((W + K, E))).to(eng.device)  # inputs resident in HBM
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)  # > 126 MB L2
+    n_pre = args.burn_in + W
+    u_all = torch.from_numpy(rng.random_sample((n_pre + K + 1, E))).to(eng.device)  # inputs resident in HBM
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(W):
-        eng.run_move_step(S, kind, u_all[i])
-        if eng.episode_counts()[0]:
-            eng.drain_episodes_device()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+    warm = []
+    for i in range(n_pre):
+        search.simulate_and_move(eng, u_all[i])
+        d = eng.drain_episodes_device()
+        if i >= args.burn_in:
+            warm.append(d)
+    if world > 1:
+        all_gather_episodes(concat_device(warm), slot_offset=lo)  # NCCL channel set-up and buffer sizing belong to the warm-up
     barrier()
-    st0, l0 = eng.stats(), eng.launch_count
+    st0 = eng.stats()
     sampler = ClockSampler(local)
+    ev0, ev1, ag0 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     t_wall0 = time.perf_counter()
+    ev0.record()
+    drained = []
     for i in range(K):
-        flush.zero_()  # L2 flush between timed iterations (outside the step's event pair)
-        ev[i][0].record()
-        eng.run_move_step(S, kind, u_all[W + i])  # az_run_move_step: 200 simulations per tree + the move, one launch
-        ev[i][1].record()
-        if (i + 1) % 16 == 0:  # keep the device ring from filling; not part of the device-resident step
-            eng.drain_episodes_device()
+        search.simulate_and_move(eng, u_all[n_pre + i])  # 800 x (k_resnet_trunk, k_expand_select) replayed from a CUDA graph + k_sample_moves
+        drained.append(eng.drain_episodes_device())      # device -> device; keeps the episode ring from filling
+    ag0.record()
+    merged = concat_device(drained)
+    if world > 1:
+        merged = all_gather_episodes(merged, slot_offset=lo)  # configs[3]: every rank ends the region holding every finished episode
+    ev1.record()
     barrier()
     wall_s = time.perf_counter() - t_wall0
     clocks = sampler.stop()
-    launches = eng.launch_count - l0 - K // 16 * 0
     st = diff(st0, eng.stats())
-    sim_ms = [a.elapsed_time(b) for a, b in ev]
-    step_ms = sim_ms
-    total_ms = float(sum(step_ms))
+    total_ms, ag_ms = ev0.elapsed_time(ev1), ag0.elapsed_time(ev1)
+    n_eps_job = int(merged["ep_len"].numel())
     if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=eng.device)
+        t = torch.tensor([total_ms, ag_ms], dtype=torch.float64, device=eng.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-        cnt = torch.tensor([st["simulations"], st["episodes"]], dtype=torch.float64, device=eng.device)
+        total_ms, ag_ms = float(t[0].item()), float(t[1].item())
+        cnt = torch.tensor([st["simulations"], st["evaluations"]], dtype=torch.float64, device=eng.device)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        tot_sims, tot_eps = float(cnt[0].item()), float(cnt[1].item())
+        tot_sims, tot_evals = float(cnt[0].item()), float(cnt[1].item())
     else:
-        tot_sims, tot_eps = float(st["simulations"]), float(st["episodes"])
+        tot_sims, tot_evals = float(st["simulations"]), float(st["evaluations"])
     value = tot_sims / total_ms * 1e3
-    eng.drain_episodes_device()
+    launches = K * search.launches_per_move_step()
 
-    # roofline of the dominant kernel (k_run_sims), this rank
-    alg_bytes = algorithmic_bytes(st) / K
-    k_ms = float(np.mean(sim_ms))
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"kernel": "k_run_sims", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (total_ms / K) if world == 1 else None,
-                "bytes_per_sim": alg_bytes * K / max(1, st["simulations"]),
-                "note": "latency-bound pointer chasing: one dependent load round per tree level; see DESIGN.md"}
-    prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    # roofline of the dominant kernel on this rank: CUDA events around each evaluator launch of one more (un-graphed) move step
+    k_ms = kernel_timing_step(search, eng, u_all[n_pre + K])
+    eng.drain_episodes_device()
+    k_mean = float(np.mean(k_ms))
+    evals_per_launch = st["evaluations"] / (K * S)
+    achieved = evals_per_launch * flops / (k_mean * 1e-3) / 1e12
+    roofline = {"kernel": search.evaluator_name, "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                "algorithmic_flops_per_launch": evals_per_launch * flops, "flops_per_position": flops, "positions_per_launch": E,
+                "evaluated_leaves_per_launch": evals_per_launch, "kernel_ms": k_mean, "kernel_launches_timed": len(k_ms),
+                "kernel_share_of_step": k_mean * S / (ev0.elapsed_time(ev1) / K),
+                "how": "CUDA events around each evaluator launch of one extra un-graphed move step right after the timed region",
+                "tree_kernel": {"name": "k_expand_select", "us_per_launch": (ev0.elapsed_time(ev1) / K / S - k_mean) * 1e3,
+                                "algorithmic_gbs": algorithmic_bytes(st) / K / S / max(1e-9, (ev0.elapsed_time(ev1) / K / S - k_mean) * 1e-3) / 1e9,
+                                "note": "step time minus evaluator time; latency-bound pointer chasing, see DESIGN.md"}}
+    prof = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("k_run_sims_dram_bytes_per_launch")
+            roofline["traffic"] = json.load(open(prof)).get(search.evaluator_name + "_dram_bytes_per_launch")
         except Exception:
             pass
 
-    # end to end through the public API with host buffers
+    # end to end through the public API with host buffers, continuing the same games
     e2e = None
     if not args.no_e2e:
-        gen = az.EpisodeGenerator(model=az.UniformEvaluator() if kind == EVAL_UNIFORM else az.HashEvaluator(), num_simulations=S,
-                                  num_episodes=E, game_initial_state=az.Config(6, 7, 4).sample_initial_state(), device=local,
-                                  lanes_per_tree=args.lanes)
         np.random.seed(7 + rank)
-        g_eng = gen.search.engine_for(E)
-        eps, e2e_t0, sims_before, bytes0 = 0, None, None, (0, 0)
-        for step, batch, _ in gen.iter_steps(max_steps=W + K + 1):
-            if step == W - 1:  # warm-up done: open the timed region on a quiet device (step W is already enqueued: it is
-                barrier()      # finished by this barrier and counted as warm-up by the statistics snapshot below)
-                sims_before = g_eng.stats()
+        W2 = 2
+        batches, e2e_t0, sims_before, bytes0 = [], None, None, (0, 0)
+        for step, batch, _ in gen.iter_steps(max_steps=W2 + K + 1, reset=False):
+            if step == W2 - 1:  # warm-up done: open the timed region on a quiet device (step W2 is already enqueued: it is
+                barrier()       # finished by this barrier and counted as warm-up by the statistics snapshot below)
+                sims_before = eng.stats()
                 bytes0 = (gen.h2d_bytes, gen.d2h_bytes)
                 e2e_t0 = time.perf_counter()
                 continue
-            if e2e_t0 is None:
-                continue
-            if batch is not None:
-                eps += len(batch)
+            if e2e_t0 is not None and batch is not None:
+                batches.append(batch)
+        n_eps = sum(len(b) for b in batches)
+        if world > 1:
+            from alphazero_implementation_b200.trainer import _concat, _to_device
+
+            loc = batches[0]
+            for b in batches[1:]:
+                loc = _concat(loc, b)
+            n_eps = int(all_gather_episodes(_to_device(loc, eng.device), slot_offset=lo)["ep_len"].numel())
         barrier()
         e2e_s = time.perf_counter() - e2e_t0
-        d = diff(sims_before, g_eng.stats())
+        d = diff(sims_before, eng.stats())
         n_steps = d["moves"] // E
         h2d, d2h = gen.h2d_bytes - bytes0[0], gen.d2h_bytes - bytes0[1]
         t = torch.tensor([e2e_s], dtype=torch.float64, device=eng.device)
@@ -413,69 +589,53 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(c, op=dist.ReduceOp.SUM)
         e2e = {"value": float(c.item()) / float(t.item()), "unit": "sims/s", "h2d_bytes_per_step": int(h2d / max(1, n_steps)),
-               "d2h_bytes_per_step": int(d2h / max(1, n_steps)), "steps": int(n_steps), "games_per_sec": eps / e2e_s * world,
-               "api": "EpisodeGenerator.iter_steps: pinned-host uniforms in, finished episodes + ring counters out to pinned host memory every step; readback of step k overlaps step k+1"}
-
-    # multi-GPU: all-gather of finished episodes over NCCL (config 4), timed apart from the data path
-    allgather = None
-    if world > 1:
-        from alphazero_implementation_b200.distributed import all_gather_episodes
-
-        all_gather_episodes(eng.drain_episodes_device())  # first call: NCCL channel set-up
-        for _ in range(6):
-            eng.run_move_step(S, kind, u_all[0])
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        drained = eng.drain_episodes_device()
-        all_gather_episodes(drained)  # same payload once untimed: NCCL sizes its buffers for the message on first use
-        barrier()  # the collective is timed from a common start, not from the slowest rank's arrival
-        a0.record()
-        merged = all_gather_episodes(drained)
-        a1.record()
-        torch.cuda.synchronize()
-        allgather = {"ms": a0.elapsed_time(a1), "episodes": int(merged["ep_len"].numel()), "samples": int(merged["s_bb0"].numel())}
+               "d2h_bytes_per_step": int(d2h / max(1, n_steps)), "steps": int(n_steps), "games_per_sec": n_eps / float(t.item()),
+               "api": "EpisodeGenerator.iter_steps: pinned-host uniforms in, finished episodes + ring counters out to pinned host memory every "
+                      "step (readback of step k overlaps step k+1)" + ("; then the NCCL all-gather of the region's episodes" if world > 1 else "")}
 
     arena_bytes = eng.device_bytes
+    details = {"games_per_gpu": E, "burn_in_steps": args.burn_in, "tree_arena_bytes": arena_bytes, "evaluator": search.evaluator_name,
+               "flops_per_position": flops, "leaf_eval_fraction": tot_evals / max(1.0, tot_sims),
+               "us_per_simulation_step": total_ms * 1e3 / (K * S), "cuda_graph": bool(search.use_cuda_graph),
+               "episodes_finished_in_timed_region": n_eps_job}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_arm(E, S, kind)
-        cpu = {"value": r["sims_per_s"], "unit": "sims/s", "cores": r["cores"], "kind": "port",
-               "sample": f"{r['steps']} move steps of {E} games x {S} sims from the initial position ({r['seconds']:.1f} s), "
-                         "oracle/c4_oracle.c with OpenMP over trees"}
-    extra, scaling = None, None
-    eng.close()
-    if rank == 0 and world == 1 and not args.no_tree_scaling:
         try:
-            scaling = tree_scaling(args, local, peaks, kind)
-        except Exception as exc:  # side measurements must not sink the headline
-            scaling = {"error": repr(exc)}
-    if args.net != "none":
-        try:
-            extra = net_in_loop(args, local, peaks, world, rank)
+            r = cpu_arm_net(args.net, args.cpu_games, S, target_s=args.cpu_seconds)
+            cpu = {"value": r["sims_per_s"], "unit": "sims/s", "cores": r["cores"], "kind": "port", "cpu_model": cpu_model_name(),
+                   "sample": f"{r['steps']} move steps of {r['games']} games x {S} sims from the initial position ({r['seconds']:.1f} s): oracle/c4_oracle.c with "
+                             f"OpenMP over trees + the same {args.net} torch module in fp32 on the host cores, one batched forward per simulation step"}
         except Exception as exc:
-            if world > 1:
-                raise  # a rank that skipped the collectives would hang the others
-            extra = {"error": repr(exc)}
+            cpu = {"error": repr(exc)[:300]}
+    search.close()
+    del gen, search, eng
+    torch.cuda.empty_cache()
+
+    extras = {}
+    if rank == 0 and world == 1:
+        for spec in [s for s in args.extras.split(",") if s and s != "none"]:
+            try:  # side measurements must not sink the headline
+                if spec == "config2":
+                    extras["config2"] = config2_extra(args, local, peaks)
+                elif spec == "tree_scaling":
+                    extras["tree_scaling"] = tree_scaling(args, local, peaks)
+                elif spec != args.net:
+                    extras.setdefault("net_in_loop", []).append(net_extra(args, spec, local, peaks))
+            except Exception as exc:
+                extras.setdefault("errors", {})[spec] = repr(exc)[:300]
+            torch.cuda.empty_cache()
 
     if rank == 0:
         line = {
-            "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": K, "warmup": W - args.burn_in,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "games_per_sec": tot_eps / total_ms * 1e3,
-            "config": {"workload": f"connect4_selfplay_{args.evaluator}_{E}x{S}", "num_games_per_gpu": E, "num_simulations": S,
-                       "evaluator": args.evaluator, "c_puct": 1.0, "lanes_per_tree": args.lanes or 8, "parallelism": f"games sharded x{world}",
-                       "burn_in_steps": args.burn_in,
-                       "l2": "flushed between timed steps (256 MiB memset outside the per-step event pair)",
-                       "tree_arena_bytes": arena_bytes},
+            "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic", "games_per_sec": n_eps_job / total_ms * 1e3, "config": workload_config(args, world), "details": details,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "wall_s_timed_region": wall_s, "work": {k: v / K for k, v in st.items()},
+            "wall_s_timed_region": wall_s, "work_per_step": {k: v / K for k, v in st.items()},
         }
-        if allgather:
-            line["episode_allgather"] = allgather
-        if scaling:
-            line["tree_scaling"] = scaling
-        if extra:
-            line["net_in_loop"] = extra
+        if world > 1:
+            line["episode_allgather"] = {"ms": ag_ms, "inside_timed_region": True, "episodes": n_eps_job, "samples": int(merged["s_bb0"].numel())}
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

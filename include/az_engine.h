@@ -54,6 +54,12 @@ extern "C" {
 #define AZ_LAYOUT_PLANES_BF16 2     /* same planes, bf16 NCHW */
 #define AZ_LAYOUT_PLANES_BF16_NHWC 3 /* [E,6,7,8] bf16 channels-last, channels 3..7 zero (tensor-core conv input) */
 
+/* Operand formats of the tensor-core evaluators.  Both are 16-bit operands with fp32 accumulation at the same tcgen05 rate;
+ * fp16 carries 11 significand bits against bf16's 8 and is the mode that meets north_star's 1e-3 tolerance against the fp32
+ * `predict` (models/games/connect4/model.py:19-43); bf16 is the default BASELINE config 3 names. */
+#define AZ_FMT_BF16 0
+#define AZ_FMT_F16 1
+
 /* policy_kind for az_expand_backup */
 #define AZ_POLICY_LOGITS 0 /* raw logits[E,7]; legal-only fp32 softmax applied (model.py:29-38) */
 #define AZ_POLICY_PRIORS 1 /* priors[E,7] already normalised over the legal columns */
@@ -228,6 +234,8 @@ typedef struct az_mlp az_mlp;
 int32_t az_mlp_create(int32_t device, az_mlp **out);
 int32_t az_mlp_destroy(az_mlp *m);
 const char *az_mlp_last_error(const az_mlp *m);
+/* AZ_FMT_BF16 (default) or AZ_FMT_F16 operands; takes effect at the next az_mlp_set_weights */
+int32_t az_mlp_set_operand_format(az_mlp *m, int32_t fmt);
 int32_t az_mlp_set_weights(az_mlp *m, const float *w1 /*[512][42]*/, const float *b1, const float *w2 /*[512][512]*/,
                            const float *b2, const float *w_policy /*[7][512]*/, const float *b_policy,
                            const float *w_value /*[2][512]*/, const float *b_value, void *stream);
@@ -250,7 +258,19 @@ int32_t az_resnet_forward_leaves(az_engine *engine, const void *packed_weights, 
                                  const void *head_conv_w, const float *head_conv_b, const float *fc_policy_w,
                                  const float *fc_policy_b, const float *fc_value_w, const float *fc_value_b, float *logits,
                                  float *values, void *stream);
-/* Tuning switch of the kernel behind the two calls above: 0 (default) = one CTA per 8 positions, 1 = CTA pairs
+typedef struct az_resnet_desc {
+    int32_t num_blocks;      /* residual blocks (resnet.py:51-53) */
+    int32_t num_channels;    /* trunk width: 64 */
+    int32_t operand_format;  /* AZ_FMT_*: format of trunk_w / head_conv_w and of the activations between layers */
+    int32_t reserved;
+    const void *trunk_w;     /* packed 16-bit MMA operands (models.py:pack_trunk_weights) */
+    const float *trunk_b;    /* [1 + 2*num_blocks][num_channels] */
+    const void *head_conv_w; /* 9 taps x [48][num_channels] */
+    const float *head_conv_b;
+    const float *fc_policy_w, *fc_policy_b, *fc_value_w, *fc_value_b; /* fp32, nn.Linear layout */
+} az_resnet_desc;
+int32_t az_resnet_forward_leaves_v2(az_engine *engine, const az_resnet_desc *desc, float *logits, float *values, void *stream);
+/* Tuning switch of the kernel behind the calls above: 0 (default) = one CTA per 8 positions, 1 = CTA pairs
  * (tcgen05 cta_group::2, M = 256).  Same results; returns the previous setting. */
 int32_t az_trunk_set_cta_pair(int32_t on);
 

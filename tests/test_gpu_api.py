@@ -230,12 +230,15 @@ def test_trainer_writes_the_reference_episode_files(tmp_path):
     hist = tr.train(num_iterations=2, episodes_per_iter=16, simulations_per_episode=16, epochs_per_iter=1,
                     initial_state=az.Config(6, 7, 4).sample_initial_state(), buffer_size=24, save_every_n_iterations=2,
                     save_dir=str(tmp_path))
-    assert sorted(p.name for p in tmp_path.iterdir()) == ["episodes_iter2.json", "model_iter2.pt"]
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["episodes_iter2.json", "model_iter2.ckpt"]
     eps = load_episodes(str(tmp_path / "episodes_iter2.json"))
     assert len(eps) == 24 == hist[1]["episodes"] and sum(len(e.samples) for e in eps) == hist[1]["samples"]
     s = eps[0].samples[0]
     assert abs(sum(s.policy.values()) - 1.0) < 1e-9 and s.value in ([1.0, -1.0], [-1.0, 1.0], [0.0, 0.0])
-    assert set(torch.load(tmp_path / "model_iter2.pt").keys()) == set(az.BasicNN().state_dict().keys())
+    ckpt = torch.load(tmp_path / "model_iter2.ckpt", weights_only=False)  # Lightning's file shape (trainer.py:66-70)
+    assert set(ckpt["state_dict"].keys()) == set(az.BasicNN().state_dict().keys()) and "hyper_parameters" in ckpt
+    back = az.BasicNN.load_from_checkpoint(str(tmp_path / "model_iter2.ckpt"))  # scripts/play.py:19
+    assert all(torch.equal(a.cpu(), b.cpu()) for a, b in zip(back.state_dict().values(), tr.model.state_dict().values()))
 
 
 def test_graphed_training_steps_equal_eager_steps():

@@ -127,3 +127,38 @@ def test_replay_buffer_is_a_deque_of_episodes():
         assert eb.ep_offset.tolist() == [sum(l for _, l, _ in list(ref)[:k]) for k in range(len(ref))]
         assert eb.s_bb0.tolist() == want_bb0 and eb.ep_outcome.tolist() == [o for _, _, o in ref]
         assert eb.s_counts.dtype == np.int32 and eb.s_counts.shape == (len(want_bb0), 7)
+
+
+def test_checkpoint_round_trip_in_the_reference_file_shape(tmp_path):
+    """`Model.load_from_checkpoint` (scripts/play.py:19-25) reads a Lightning-shaped checkpoint (`state_dict` +
+    `hyper_parameters`, what the reference's ModelCheckpoint writes, trainer.py:66-70) and a bare state dict; stale keyword
+    arguments of the reference's call site (`height=`, `width=`, ...) that the constructor does not take are ignored."""
+    import torch
+
+    from alphazero_implementation_b200.models import BasicNN, CNNModel, ResNet
+
+    torch.manual_seed(3)
+    for cls, kw in ((BasicNN, {}), (CNNModel, {}), (ResNet, dict(num_res_blocks=2, num_channels=32))):
+        m = cls(**kw)
+        p = tmp_path / f"{cls.__name__}.ckpt"
+        m.save_checkpoint(str(p), epoch=7, global_step=123)
+        ck = torch.load(p, weights_only=False)
+        assert set(ck) >= {"state_dict", "hyper_parameters", "epoch", "global_step"} and ck["hyper_parameters"]["model_name"] == cls.__name__
+        back = cls.load_from_checkpoint(str(p), height=6, width=7, max_actions=7, num_players=2)
+        assert not back.training
+        assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), back.state_dict().values()))
+    # a checkpoint written by the reference's Lightning run: same keys, plus trainer state we do not need
+    ref_shaped = {"state_dict": BasicNN().state_dict(), "hyper_parameters": {"learning_rate": 1e-3, "model_name": "BasicNN"},
+                  "epoch": 249, "global_step": 62820, "optimizer_states": [], "lr_schedulers": [], "loops": {}}
+    torch.save(ref_shaped, tmp_path / "ref.ckpt")
+    assert isinstance(BasicNN.load_from_checkpoint(str(tmp_path / "ref.ckpt")), BasicNN)
+    torch.save(BasicNN().state_dict(), tmp_path / "bare.pt")
+    assert isinstance(BasicNN.load_from_checkpoint(str(tmp_path / "bare.pt")), BasicNN)
+
+
+def test_shard_table_is_validated_before_any_collective():
+    from alphazero_implementation_b200.distributed import shard_range
+
+    assert [shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    shards = [shard_range(8, r, 4, trainer_share=1.0) for r in range(4)]
+    assert shards[0] == (0, 8) and all(lo == hi for lo, hi in shards[1:])  # Trainer.train raises on EVERY rank for such a table
