@@ -125,6 +125,7 @@ SIGNATURES = {
     "az_mlp_forward_leaves": (I32, [P, P, P, P, P]),
     "az_mlp_launch_count": (I64, [P]),
     "az_leaf_players": (I32, [P, C.POINTER(P)]),
+    "az_leaf_compact": (I32, [P, C.POINTER(P), C.POINTER(P)]),
     "az_trunk_weight_bytes": (I64, [I32]),
     "az_trunk_forward_leaves": (I32, [P, P, P, I32, P, P]),
     "az_resnet_forward_leaves": (I32, [P, P, P, I32, P, P, P, P, P, P, P, P, P]),

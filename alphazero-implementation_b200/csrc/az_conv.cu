@@ -303,7 +303,8 @@ __device__ __forceinline__ void issue_group(uint32_t full0, uint32_t pfull0, uin
 template <bool PAIR, bool F16>
 __global__ void __launch_bounds__(THREADS, 1)
 k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1, const uint8_t *__restrict__ leaf_player,
-                   const uint8_t *__restrict__ leaf_status, long long n, const uint8_t *__restrict__ weights,
+                   const uint8_t *__restrict__ leaf_status, const int32_t *__restrict__ eval_list, const int32_t *__restrict__ eval_count,
+                   long long n_slots, const uint8_t *__restrict__ weights,
                    const float *__restrict__ biases, int num_blocks, __nv_bfloat16 *__restrict__ out,
                    const uint8_t *__restrict__ head_w, const float *__restrict__ head_b, const float *__restrict__ fc_policy_w,
                    const float *__restrict__ fc_policy_b, const float *__restrict__ fc_value_w, const float *__restrict__ fc_value_b,
@@ -315,6 +316,9 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + (3 * NS + 4) * 8);
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     if (warp == 0) CLK(0, MAX_LAYERS - 1, 0);
+    // eval_list: position j of the batch is slot eval_list[j], j < *eval_count (only the leaves that wait for an evaluation are
+    // processed, outputs go to the slots' rows); without it position j is slot j and rows of other slots are computed as zeros
+    const long long n = eval_list ? (long long)__ldg(eval_count) : n_slots;
     const int n_conv = 1 + 2 * num_blocks;            // stem + block convs
     const int n_layers = n_conv + (head_w ? 1 : 0);   // + head conv
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS), ring0 = smem_u32(smem + OFF_RING);
@@ -372,7 +376,7 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
         const bool cell = tid < WTHREADS && r < TILES * 128 && decode_row(r, pos, y, x);
         const long long gp = pos0 + pos;
         const bool in = cell && gp < n;
-        const long long g = in ? gp : 0;
+        const long long g = in ? (eval_list ? (long long)__ldg(eval_list + gp) : gp) : 0;
         const uint8_t st = leaf_status[g];
         in_b0[k] = leaf_bb0[g];
         in_b1[k] = leaf_bb1[g];
@@ -507,7 +511,8 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
                 if (!decode_row(r, pos, y, x)) continue;
                 const long long gp = pos0 + pos;
                 if (gp >= n) continue;
-                uint4 *o = reinterpret_cast<uint4 *>(out + ((gp * c4::H + y) * c4::W + x) * C);
+                const long long slot = eval_list ? (long long)__ldg(eval_list + gp) : gp;
+                uint4 *o = reinterpret_cast<uint4 *>(out + ((slot * c4::H + y) * c4::W + x) * C);
                 const uint8_t *row = buf[0] + (GUARD + r) * ROWB;
 #pragma unroll
                 for (int grp = 0; grp < C / 8; ++grp) o[grp] = *reinterpret_cast<const uint4 *>(row + grp * LBO_A);
@@ -596,12 +601,13 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
                 const int p = (int)tid >> 3, j = (int)tid & 7;
                 const long long gp = pos0 + p;
                 if (gp < n) {
+                    const long long slot = eval_list ? (long long)__ldg(eval_list + gp) : gp;
                     if (j < 7) {
-                        logits[gp * 7 + j] = sum + __ldg(fc_policy_b + j);
+                        logits[slot * 7 + j] = sum + __ldg(fc_policy_b + j);
                     } else {
                         const float v = tanhf(sum + __ldg(fc_value_b));
-                        values[gp * 2] = v;
-                        values[gp * 2 + 1] = -v;
+                        values[slot * 2] = v;
+                        values[slot * 2 + 1] = -v;
                     }
                 }
             }
@@ -652,6 +658,10 @@ static int32_t launch_trunk(az_engine *engine, const void *weights, const float 
     const uint8_t *status = nullptr, *player = nullptr;
     int32_t n = 0;
     if (az_leaf_arrays(engine, &bb0, &bb1, &status, &n) != AZ_OK || az_leaf_players(engine, &player) != AZ_OK || n <= 0) return AZ_E_INVALID;
+    // the full net walks the engine's compacted list of leaves that wait for an evaluation; the trunk-only entry point (out != null)
+    // produces activations for every slot
+    const int32_t *elist = nullptr, *ecount = nullptr;
+    if (!out && az_leaf_compact(engine, &elist, &ecount) != AZ_OK) return AZ_E_INVALID;
     static bool attr_set[64] = {false};  // the opt-in to > 48 KB of dynamic shared memory is per device
     const int dev = az_device(engine);
     if (dev < 0 || dev >= 64 || cudaSetDevice(dev) != cudaSuccess) return AZ_E_CUDA;
@@ -681,7 +691,7 @@ static int32_t launch_trunk(az_engine *engine, const void *weights, const float 
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         auto kern = fmt == AZ_FMT_F16 ? k_resnet_trunk<true, true> : k_resnet_trunk<true, false>;
-        if (cudaLaunchKernelEx(&cfg, kern, bb0, bb1, player, status, nn, w8, biases, (int)num_blocks, o16, hw8, head_b, fcp_w, fcp_b,
+        if (cudaLaunchKernelEx(&cfg, kern, bb0, bb1, player, status, elist, ecount, nn, w8, biases, (int)num_blocks, o16, hw8, head_b, fcp_w, fcp_b,
                                fcv_w, fcv_b, logits, values) != cudaSuccess)
             return AZ_E_CUDA;
     } else {
@@ -689,7 +699,7 @@ static int32_t launch_trunk(az_engine *engine, const void *weights, const float 
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return AZ_E_CUDA;
         const int batches = (n + P - 1) / P;
         auto kern = fmt == AZ_FMT_F16 ? k_resnet_trunk<false, true> : k_resnet_trunk<false, false>;
-        kern<<<batches < sms ? batches : sms, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(bb0, bb1, player, status, nn, w8, biases, num_blocks, o16, hw8, head_b,
+        kern<<<batches < sms ? batches : sms, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(bb0, bb1, player, status, elist, ecount, nn, w8, biases, num_blocks, o16, hw8, head_b,
                                                                                             fcp_w, fcp_b, fcv_w, fcv_b, logits, values);
     }
     return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;

@@ -66,6 +66,8 @@ struct Arena {
     uint8_t *leaf_player, *leaf_status, *leaf_depth;
     uint32_t *path;    // [E][PATH_STRIDE]
     uint32_t *tstats;  // [E][NSTAT]
+    int32_t *eval_list;   // [E] slots whose leaf waits for the evaluator, ascending (k_compact_leaves)
+    int32_t *eval_count;  // [4] [0] = entries in eval_list
     // game in progress per slot
     uint64_t *g_bb0, *g_bb1;  // [E][42]
     uint8_t *g_player;        // [E][42]
@@ -890,6 +892,41 @@ k_expand_select(Arena a, int n_active, const float *__restrict__ policy, const f
     select_body<TPW, LAT>(a, n_active, c_puct);
 }
 
+// Ordered compaction of the slots whose leaf waits for the evaluator (status AZ_LEAF_EVAL): eval_list[0 .. count) ascending.
+// ~15 % of the simulations of a running self-play loop end in a terminal leaf (search.py:75-77) and need no evaluation; the
+// tensor-core evaluators walk this list instead of all E rows and scatter their outputs back to the slots' rows.  One block:
+// each thread counts its contiguous stretch of slots, a block-wide exclusive scan gives its offset (deterministic order, no atomics).
+__global__ void __launch_bounds__(1024) k_compact_leaves(const uint8_t *__restrict__ status, int n, int32_t *__restrict__ list, int32_t *__restrict__ count) {
+    __shared__ int warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + 1023) / 1024;
+    const int lo = tid * per, hi = min(n, lo + per);
+    int mine = 0;
+    for (int i = lo; i < hi; ++i) mine += status[i] == AZ_LEAF_EVAL;
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, off);
+        if (lane >= off) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_tot[lane], wi = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(FULL, wi, off);
+            if (lane >= off) wi += v;
+        }
+        warp_tot[lane] = wi - w;  // exclusive
+        if (lane == 31) count[0] = wi;
+    }
+    __syncthreads();
+    int o = warp_tot[warp] + incl - mine;
+    for (int i = lo; i < hi; ++i)
+        if (status[i] == AZ_LEAF_EVAL) list[o++] = i;
+}
+
 // ------------------------------------------------------------------------------------------------
 // plane encoders (the "leaf gather").  One thread per position builds the position's output words from
 // row-major plane masks (a handful of integer ops per word), stages them in shared memory, and the block
@@ -1571,6 +1608,7 @@ int32_t az_create(const az_config *cfg, az_engine **out) {
     AL(a.root_bb0, E); AL(a.root_bb1, E); AL(a.root_player, E); AL(a.used, E); AL(a.tree_err, E);
     AL(a.leaf_node, E); AL(a.leaf_bb0, E); AL(a.leaf_bb1, E); AL(a.leaf_player, E); AL(a.leaf_status, E);
     AL(a.leaf_depth, E); AL(a.path, (size_t)E * PATH_STRIDE); AL(a.tstats, (size_t)E * NSTAT);
+    AL(a.eval_list, E); AL(a.eval_count, 4);
     AL(a.g_bb0, (size_t)E * MAX_PLIES); AL(a.g_bb1, (size_t)E * MAX_PLIES); AL(a.g_player, (size_t)E * MAX_PLIES);
     AL(a.g_counts, (size_t)E * MAX_PLIES * 7); AL(a.g_len, E);
     for (int r = 0; r < 2; ++r) {
@@ -1599,6 +1637,7 @@ int32_t az_create(const az_config *cfg, az_engine **out) {
     use_ring(h, 0);
     cudaMemset(h->d_tot, 0, 8 * sizeof(unsigned long long));
     cudaMemset(a.g_len, 0, (size_t)E * sizeof(int32_t));
+    cudaMemset(a.eval_count, 0, 4 * sizeof(int32_t));
     // every slot starts at the empty board, player 0 (Config.sample_initial_state())
     k_set_roots<<<blocks_for(E, 256), 256>>>(a, nullptr, nullptr, nullptr, 0ull, 0ull, 0, E, 1);
     h->launches++;
@@ -1895,6 +1934,8 @@ int32_t az_select_leaves(az_engine *h, void *stream) {
     else AZ_SEL(4);
 #undef AZ_SEL
     AZ_LAUNCH_CHECK(h, "k_select");
+    k_compact_leaves<<<1, 1024, 0, S(stream)>>>(h->a.leaf_status, n, h->a.eval_list, h->a.eval_count);
+    AZ_LAUNCH_CHECK(h, "k_compact_leaves");
     h->sims_done += 1;
     return AZ_OK;
 }
@@ -1943,6 +1984,8 @@ int32_t az_expand_backup_select(az_engine *h, const float *policy, const float *
     else AZ_ES(4);
 #undef AZ_ES
     AZ_LAUNCH_CHECK(h, "k_expand_select");
+    k_compact_leaves<<<1, 1024, 0, S(stream)>>>(h->a.leaf_status, n, h->a.eval_list, h->a.eval_count);
+    AZ_LAUNCH_CHECK(h, "k_compact_leaves");
     h->sims_done += 1;
     return AZ_OK;
 }
@@ -1963,6 +2006,15 @@ int32_t az_leaf_arrays(az_engine *h, const uint64_t **bb0, const uint64_t **bb1,
     if (bb1) *bb1 = h->a.leaf_bb1;
     if (status) *status = h->a.leaf_status;
     if (n_active) *n_active = h->n_active;
+    return AZ_OK;
+}
+
+/* the slots whose leaf waits for the evaluator after the last az_select_leaves / az_expand_backup_select, ascending, and their
+ * number - both on the device (engine-owned, valid until az_destroy) */
+int32_t az_leaf_compact(az_engine *h, const int32_t **eval_list, const int32_t **eval_count) {
+    if (!h) return AZ_E_INVALID;
+    if (eval_list) *eval_list = h->a.eval_list;
+    if (eval_count) *eval_count = h->a.eval_count;
     return AZ_OK;
 }
 

@@ -247,7 +247,7 @@ __device__ __forceinline__ uint64_t row_major42(uint64_t bb) {
 template <bool FROM_LEAVES, bool F16>
 __global__ void __launch_bounds__(THREADS, 1)
 k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1,
-            const uint8_t *__restrict__ leaf_status, long long n, const uint8_t *__restrict__ w1p, const float *__restrict__ b1,
+            const uint8_t *__restrict__ leaf_status, const int32_t *__restrict__ eval_list, const int32_t *__restrict__ eval_count, long long n_rows, const uint8_t *__restrict__ w1p, const float *__restrict__ b1,
             const uint8_t *__restrict__ w2p, const float *__restrict__ b2, const uint8_t *__restrict__ whp,
             const float *__restrict__ bh, float *__restrict__ logits, float *__restrict__ values) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -257,17 +257,26 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + ACT_BYTES + NS * STAGE_BYTES + BIAS_BYTES + (2 * NS + 1) * 8);
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const long long row0 = (long long)blockIdx.x * TILE_M;
+    // FROM_LEAVES: row j is the leaf of slot eval_list[j], j < *eval_count (only the leaves that wait for an evaluation; the
+    // outputs go to the slots' rows).  A block beyond the list has nothing to do.
+    const long long n = (FROM_LEAVES && eval_list) ? (long long)__ldg(eval_count) : n_rows;
+    if (row0 >= n) return;
     MCLK(0);
     // the leaf record of this thread's row is requested before the CTA set-up and consumed after it
     uint64_t in_b0 = 0, in_b1 = 0;
     bool in_live = false;
+    long long out_row = -1;  // the row of logits / values this thread's row goes to
     if (FROM_LEAVES && tid < ETHREADS) {
         const long long row = row0 + (tid & 127u);
         if (row < n) {
-            in_live = leaf_status[row] == AZ_LEAF_EVAL;
-            in_b0 = leaf_bb0[row];
-            in_b1 = leaf_bb1[row];
+            out_row = eval_list ? (long long)__ldg(eval_list + row) : row;
+            in_live = leaf_status[out_row] == AZ_LEAF_EVAL;
+            in_b0 = leaf_bb0[out_row];
+            in_b1 = leaf_bb1[out_row];
         }
+    } else if (!FROM_LEAVES && tid < ETHREADS) {
+        const long long row = row0 + (tid & 127u);
+        if (row < n) out_row = row;
     }
     Pipe p;
     p.full0 = smem_u32(bars);
@@ -376,8 +385,8 @@ k_mlp_fused(const float *__restrict__ grid, const uint64_t *__restrict__ leaf_bb
         if (tid < TILE_M) {
             uint32_t v[16];
             tmem_ld16(tmem_base + ((tid & ~31u) << 16), v);
-            const long long row = row0 + tid;
-            if (row < n) {
+            const long long row = out_row;
+            if (row >= 0) {
 #pragma unroll
                 for (int j = 0; j < 7; ++j) logits[row * 7 + j] = __uint_as_float(v[j]) + __ldg(bh + j);
                 values[row * 2 + 0] = tanhf(__uint_as_float(v[7]) + __ldg(bh + 7));
@@ -506,7 +515,7 @@ int32_t az_mlp_forward(az_mlp *m, const float *grid, int64_t n, float *logits, f
     cudaSetDevice(m->device);
     const int blocks = (int)((n + TILE_M - 1) / TILE_M);
     auto kern = m->fmt == AZ_FMT_F16 ? k_mlp_fused<false, true> : k_mlp_fused<false, false>;
-    kern<<<blocks, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(grid, nullptr, nullptr, nullptr, n, m->w1p, m->b1, m->w2p, m->b2, m->whp, m->bh, logits, values);
+    kern<<<blocks, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(grid, nullptr, nullptr, nullptr, nullptr, nullptr, n, m->w1p, m->b1, m->w2p, m->b2, m->whp, m->bh, logits, values);
     m->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -524,10 +533,12 @@ int32_t az_mlp_forward_leaves(az_mlp *m, az_engine *engine, float *logits, float
     const uint8_t *status = nullptr;
     int32_t n = 0;
     if (az_leaf_arrays(engine, &bb0, &bb1, &status, &n) != AZ_OK || n <= 0) return AZ_E_INVALID;
+    const int32_t *elist = nullptr, *ecount = nullptr;
+    if (az_leaf_compact(engine, &elist, &ecount) != AZ_OK) return AZ_E_INVALID;
     cudaSetDevice(m->device);
     const int blocks = (n + TILE_M - 1) / TILE_M;
     auto kern = m->fmt == AZ_FMT_F16 ? k_mlp_fused<true, true> : k_mlp_fused<true, false>;
-    kern<<<blocks, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(nullptr, bb0, bb1, status, n, m->w1p, m->b1, m->w2p, m->b2, m->whp, m->bh, logits, values);
+    kern<<<blocks, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(nullptr, bb0, bb1, status, elist, ecount, n, m->w1p, m->b1, m->w2p, m->b2, m->whp, m->bh, logits, values);
     m->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -301,7 +301,7 @@ class TensorCoreMLP:
         fused into the kernel); row i = slot i."""
         n = engine.n_active
         if n not in self._out:
-            self._out[n] = (torch.empty((n, 7), device=self.device), torch.empty((n, 2), device=self.device))
+            self._out[n] = (torch.zeros((n, 7), device=self.device), torch.zeros((n, 2), device=self.device))  # rows of slots without an evaluation stay zero
         logits, values = self._out[n]
         rc = self.lib.az_mlp_forward_leaves(self.h, engine.h, logits.data_ptr(), values.data_ptr(),
                                             torch.cuda.current_stream(self.device).cuda_stream)
@@ -411,7 +411,7 @@ class TensorCoreTrunk:
         """Trunk AND heads in the one kernel -> (logits [n,7] f32, values [n,2] f32) for the engine's current leaves."""
         n = engine.n_active
         if n not in self._lv:
-            self._lv[n] = (torch.empty((n, 7), device=self.device), torch.empty((n, 2), device=self.device))
+            self._lv[n] = (torch.zeros((n, 7), device=self.device), torch.zeros((n, 2), device=self.device))  # rows of slots without an evaluation stay zero
         logits, values = self._lv[n]
         import ctypes as C
 

@@ -102,12 +102,6 @@ class _GraphedStep:
         logits, values = self.evaluate()
         self.engine.expand_backup_select(logits, values, POLICY_LOGITS)
 
-    def own_launches(self, num_steps: int) -> int:
-        """Kernels of libaz_engine.so launched (or replayed from the graph) by `run(num_steps)`: the first selection, then per
-        simulation one tree kernel and the evaluator's own kernel (the fused tensor-core kernel, or the leaf gather in front of
-        library GEMMs)."""
-        return 1 + 2 * num_steps
-
     def run(self, num_steps: int, use_graph: bool, evaluator_events: list | None = None):
         """`evaluator_events`: run un-graphed and append a (start, end) CUDA-event pair around every evaluator call."""
         e = self.engine
@@ -220,7 +214,8 @@ class AlphaZeroSearch:
         """Kernels of libaz_engine.so per self-play move step (`simulate_and_move`)."""
         if self._mode == "builtin":
             return 1
-        return 1 + 2 * self.num_simulations + 1  # first select; per simulation evaluator (or gather) + tree kernel; sample_moves
+        # k_select + k_compact_leaves; S - 1 x (evaluator or gather, k_expand_select, k_compact_leaves); evaluator, k_expand_backup; k_sample_moves
+        return 3 * self.num_simulations + 2
 
     def close(self):
         if self._engine is not None:

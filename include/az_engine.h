@@ -162,6 +162,10 @@ int32_t az_leaf_info(az_engine *h, uint64_t *out_bb0, uint64_t *out_bb1, uint8_t
  * lets another kernel consume the leaves without a gather launch (see az_mlp_forward_leaves) */
 int32_t az_leaf_arrays(az_engine *h, const uint64_t **bb0, const uint64_t **bb1, const uint8_t **status, int32_t *n_active);
 int32_t az_leaf_players(az_engine *h, const uint8_t **player);
+/* Ordered list of the slots whose leaf waits for the evaluator (status AZ_LEAF_EVAL) and its length, both DEVICE pointers, rebuilt
+ * by every az_select_leaves / az_expand_backup_select: terminal leaves (search.py:75-77, ~15 % of the simulations of a running
+ * self-play loop) need no evaluation, so the tensor-core evaluators walk this list and scatter their outputs to the slots' rows. */
+int32_t az_leaf_compact(az_engine *h, const int32_t **eval_list, const int32_t **eval_count);
 
 /* ---- results ---- */
 /* root statistics of every active tree, per column (0 on illegal columns):

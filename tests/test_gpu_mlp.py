@@ -80,7 +80,8 @@ def test_fused_mlp_in_the_search_loop():
 
 def test_fused_leaf_gather_equals_separate_gather():
     """az_mlp_forward_leaves (rows built from the leaf bitboards inside the kernel) == az_gather_leaves + az_mlp_forward,
-    and rows of terminal / idle slots behave like all-zero inputs."""
+    on the rows of the slots whose leaf waits for an evaluation (the fused kernel walks the engine's compacted list of those
+    slots and leaves the other rows alone)."""
     torch.manual_seed(5)
     m = az.BasicNN().cuda().eval()
     n = 3000
@@ -98,5 +99,7 @@ def test_fused_leaf_gather_equals_separate_gather():
     a_l, a_v = [t.clone() for t in mlp(eng.gather_leaves(LAYOUT_GRID_F32))]
     b_l, b_v = mlp.forward_leaves(eng)
     torch.cuda.synchronize()
-    assert torch.equal(a_l, b_l) and torch.equal(a_v, b_v)
+    live = status == 0
+    assert torch.equal(a_l[live], b_l[live]) and torch.equal(a_v[live], b_v[live])
+    assert (b_l[~live] == 0).all() and (b_v[~live] == 0).all()
     eng.close()
