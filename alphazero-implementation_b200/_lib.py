@@ -12,8 +12,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("AZ_ENGINE_LIB") or os.path.join(PKG_DIR, "libaz_engine.so")  # override: A/B builds of the library
-SOURCES = ["az_engine.cu", "az_mlp.cu", "az_conv.cu"]
-HEADERS = ["az_eval.cuh", "c4_bitboard.cuh", os.path.join("..", "..", "include", "az_engine.h")]
+SOURCES = ["az_engine.cu", "az_mlp.cu", "az_conv.cu", "az_conv128.cu"]
+HEADERS = ["az_eval.cuh", "c4_bitboard.cuh", "tcgen05.cuh", os.path.join("..", "..", "include", "az_engine.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -41,14 +41,29 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> alphazero-implementation_b200/libaz_engine.so"""
     if not force and not _stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    # one nvcc -c per source, in parallel (each takes 10-30 s), then one link
+    objdir = os.path.join(PKG_DIR, "build")
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    jobs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [_nvcc(), *compile_flags, "-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        jobs.append((cmd, obj, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    objs = []
+    for cmd, obj, proc in jobs:
+        out, err = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed ({' '.join(cmd)}):\n{out}\n{err}")
+        if verbose:
+            print(err)
+        objs.append(obj)
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH, *objs]
+    proc = subprocess.run(link, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({' '.join(cmd)}):\n{proc.stdout}\n{proc.stderr}")
-    if verbose:
-        print(proc.stderr)
+        raise RuntimeError(f"link failed ({' '.join(link)}):\n{proc.stdout}\n{proc.stderr}")
     return LIB_PATH
 
 
@@ -127,6 +142,7 @@ SIGNATURES = {
     "az_leaf_players": (I32, [P, C.POINTER(P)]),
     "az_leaf_compact": (I32, [P, C.POINTER(P), C.POINTER(P)]),
     "az_trunk_weight_bytes": (I64, [I32]),
+    "az_resnet128_weight_bytes": (I64, [I32]),
     "az_trunk_forward_leaves": (I32, [P, P, P, I32, P, P]),
     "az_resnet_forward_leaves": (I32, [P, P, P, I32, P, P, P, P, P, P, P, P, P]),
     "az_resnet_forward_leaves_v2": (I32, [P, C.POINTER(AzResnetDesc), P, P, P]),

@@ -1,0 +1,383 @@
+// The reference's own ResNet(board, 7, num_res_blocks, 128) (src/alphazero_simple/resnet.py:30-103, instantiated 9 x 128 in
+// src/alphazero_less_simple/main.py:13) behind the main package's Model API, BatchNorm folded, as ONE tcgen05 kernel for the
+// leaves of the search: stem conv3x3 (3 -> 128), residual blocks (2 x conv3x3 128 -> 128, skip, ReLU), the policy / value head
+// convolutions and the two small FC layers.  223.9 MFLOP per position at 9 blocks; activations never leave the SM.
+//
+// Same implicit-GEMM formulation as csrc/az_conv.cu (pixel = GEMM row, channels = K, activation buffer K-group-major so that a
+// filter tap is the same buffer with the MMA descriptor moved by 8*dy + dx rows; compact padding: a position is 7 x 8 pixel rows),
+// but a different schedule, because with 128 channels nothing that kernel relies on fits: the 9 taps of a layer are 288 KB.
+//  * A CTA works on 4 positions = 2 accumulator tiles of 128 rows x 128 fp32 columns.  Both tiles use every weight piece, so a
+//    layer's weights are streamed ONCE per CTA: pieces of [128 out][16 in] (4 KB), ordered K-chunk-major (ks, tap), through a
+//    16-stage ring of bulk async copies - 4 KB per 2 MMAs of 64 cycles = 32 B/clk, half of the SM's L2 port.
+//  * Layers are pipelined through tensor memory instead of ping-ponging two groups: the accumulators are double-buffered
+//    (2 sets x 2 tiles x 128 columns = all 512 columns).  While the eight epilogue warps drain layer l (tcgen05.ld, bias (+ skip),
+//    ReLU, round to 16 bits, write the next layer's A operand), the tensor core already runs layer l + 1 into the other set:
+//    its MMAs are ordered by K chunk, and chunk ks needs only input channels 16 ks .. 16 ks + 15, so it waits for an mbarrier
+//    that the epilogue warps arrive on after writing exactly those channels (`chunk[ks]`).  The epilogue of a layer takes
+//    ~1.5 k cycles against 9.2 k cycles of MMAs (144 x 64), so after the first chunk the tensor core never waits; the only
+//    bubble is the hand-over at the start of a layer (last MMA done -> first chunk written).
+//  * The residual sum is formed in place: conv2's epilogue reads the skip value of its row and overwrites it, which no MMA reads
+//    any more (conv1 of the same block is complete) - two activation buffers (x, t) of 72 KB are enough.
+//  * Shared-memory operand traffic: A 4 KB + B 4 KB per 64-cycle MMA = 128 B/clk, the crossbar's rate; N = 128 is therefore
+//    balanced where the 64-channel kernel (6 KB per 32 cycles) is operand-bound.
+// Roles: warps 0..7 epilogue (thread = one pixel row of one tile), warp 8 issues MMAs (one elected lane), warp 9 streams weights.
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/az_engine.h"
+#include "c4_bitboard.cuh"
+#include "tcgen05.cuh"
+
+namespace {
+
+using namespace tc05;
+
+constexpr int C = 128;                 // trunk channels
+constexpr int KG = C / 8;              // K groups of 8 channels (16 bytes per row)
+constexpr int KS = C / 16;             // K steps per tap
+constexpr int GUARD = 16;              // zero rows before / after the tiles (a tap moves the window by up to 9 rows)
+constexpr uint32_t ROWB = 16;
+constexpr int PW = 8, PIX = 56, LEAD = 8;  // pixel-row stride, rows per position, leading zero rows of a tile
+constexpr int TPOS = 2, TILES = 2, POS = TPOS * TILES;  // positions per tile / tiles per CTA / positions per CTA
+constexpr int ROWS = TILES * 128;
+constexpr int RTOT = ROWS + 2 * GUARD;           // 288 rows per K group
+constexpr uint32_t LBO_A = RTOT * ROWB;          // 4608: next K group
+constexpr uint32_t SBO_A = 128;                  // next 8-row group
+constexpr uint32_t BUF_BYTES = KG * LBO_A;       // 73728
+constexpr uint32_t PIECE_BYTES = C * 16 * 2;     // 4096: [128 out][16 in]
+constexpr uint32_t LBO_W = 128, SBO_W = 256;     // canonical K-major [N][16]
+constexpr int NHC = 48, NHU = 35;                // head conv channels: 32 policy (1x1, centre tap) + 3 value (3x3) + padding
+constexpr uint32_t HEAD_PIECE_BYTES = NHC * 16 * 2;  // 1536
+constexpr int NS = 16;                           // ring stages
+constexpr int MAX_LAYERS = 24;
+constexpr int THREADS = 320, WTHREADS = 288;
+constexpr uint32_t OFF_RING = 2 * BUF_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_RING + NS * PIECE_BYTES;
+constexpr uint32_t OFF_BARS = OFF_BIAS + MAX_LAYERS * C * 4;
+constexpr int NBARS = 2 * NS + 1 + KS;           // full[NS] empty[NS] mma_done chunk[KS]
+constexpr uint32_t SMEM_BYTES = OFF_BARS + NBARS * 8 + 16;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(LEAD + TPOS * PIX <= 128, "a tile's positions must fit its 128 rows");
+// FC-tail scratch inside t's K groups 2..7 (K groups 0 / 1 take the next batch's stem input): head activations, then the per-warp sums
+constexpr uint32_t OFF_HACT = 2 * LBO_A;
+constexpr uint32_t HACT_BYTES = POS * NHU * 42 * 4;
+constexpr uint32_t OFF_RED = OFF_HACT + 24 * 1024;
+static_assert(HACT_BYTES <= 24 * 1024 && OFF_RED + 8 * 32 * 4 <= 8 * LBO_A, "FC scratch must stay inside K groups 2..7");
+
+__device__ __forceinline__ bool decode_row(int r, int &pos, int &y, int &x) {
+    const int tile = r >> 7;
+    const int rr = (r & 127) - LEAD;
+    const int p = rr >= 0 ? rr / PIX : 0;
+    const int q = rr - p * PIX;
+    y = q >> 3;
+    x = q & 7;
+    pos = tile * TPOS + p;
+    return rr >= 0 && p < TPOS && y < c4::H && x < c4::W;
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(THREADS, 1)
+k_resnet128(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1, const uint8_t *__restrict__ leaf_player,
+            const uint8_t *__restrict__ leaf_status, const int32_t *__restrict__ eval_list, const int32_t *__restrict__ eval_count,
+            long long n_slots, const uint8_t *__restrict__ weights, const float *__restrict__ biases, int num_blocks,
+            const uint8_t *__restrict__ head_w, const float *__restrict__ head_b, const float *__restrict__ fc_policy_w,
+            const float *__restrict__ fc_policy_b, const float *__restrict__ fc_value_w, const float *__restrict__ fc_value_b,
+            float *__restrict__ logits, float *__restrict__ values) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *bufX = smem, *bufT = smem + BUF_BYTES;
+    float *s_bias = reinterpret_cast<float *>(smem + OFF_BIAS);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BARS);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + NBARS * 8);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    // position j of a batch is slot eval_list[j], j < *eval_count: only the leaves that wait for an evaluation are processed
+    const long long n = eval_list ? (long long)__ldg(eval_count) : n_slots;
+    const int n_conv = 1 + 2 * num_blocks, n_layers = n_conv + 1;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS), mma_done = smem_u32(bars + 2 * NS), chunk0 = smem_u32(bars + 2 * NS + 1);
+    const uint32_t ring0 = smem_u32(smem + OFF_RING);
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512u);
+    if (tid == 32) {
+        for (int i = 0; i < 2 * NS + 1; ++i) mbar_init(smem_u32(bars + i), 1u);
+        for (int i = 0; i < KS; ++i) mbar_init(chunk0 + i * 8, 8u);  // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (uint32_t i = tid; i < 2 * BUF_BYTES / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < (uint32_t)n_conv * C; i += THREADS) s_bias[i] = __ldg(biases + i);
+    for (uint32_t i = tid; i < NHC; i += THREADS) s_bias[n_conv * C + i] = __ldg(head_b + i);
+    const uint32_t aX = smem_u32(bufX) + GUARD * ROWB, aT = smem_u32(bufT) + GUARD * ROWB;
+    fence_before();
+    __syncthreads();  // barriers initialised, tensor memory allocated, buffers zeroed, biases staged
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    auto batch_sync = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(WTHREADS) : "memory"); };  // everyone but the weight producer
+
+    const long long n_batches = (n + POS - 1) / POS;
+    uint32_t it = 0;
+    uint32_t g = 0;  // pieces produced (warp 9) / consumed (warp 8) so far: stage = g % NS, use = g / NS
+    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
+        const long long pos0 = batch * POS;
+        const uint32_t gl0 = it * (uint32_t)n_layers, ge0 = it * (uint32_t)n_conv;
+        // this thread's stem row: the leaf record is requested now and consumed after the batch barrier
+        uint64_t in_b0 = 0, in_b1 = 0;
+        uint32_t in_meta = 0;  // bit 0: row of a position that exists, bit 1: side to move, bit 2: row is a board cell, bits 8..: bit index
+        if (tid < ROWS) {
+            int pos, y, x;
+            const bool cell = decode_row((int)tid, pos, y, x);
+            const long long gp = pos0 + pos;
+            const bool in = cell && gp < n;
+            const long long slot = in ? (eval_list ? (long long)__ldg(eval_list + gp) : gp) : 0;
+            const bool live = in && leaf_status[slot] == AZ_LEAF_EVAL;
+            in_b0 = leaf_bb0[slot];
+            in_b1 = leaf_bb1[slot];
+            in_meta = (live ? 1u : 0u) | ((uint32_t)(leaf_player[slot] & 1) << 1) | (cell ? 4u : 0u) | ((uint32_t)(x * c4::STRIDE + y) << 8);
+        }
+        if (warp != 9) {
+            batch_sync();  // the previous batch is finished: buffers and tensor memory are this batch's
+            // the FC tail of the previous batch used K groups 2..7 of t as scratch, guard rows included: those must be zero again
+            if (it > 0)
+                for (uint32_t i = tid; i < 6 * 2 * GUARD; i += WTHREADS) {
+                    const uint32_t kg = 2 + i / (2 * GUARD), j = i % (2 * GUARD);
+                    const uint32_t row = j < GUARD ? j : (uint32_t)(ROWS + j);
+                    *reinterpret_cast<uint4 *>(bufT + kg * LBO_A + row * ROWB) = make_uint4(0, 0, 0, 0);
+                }
+            // stem input in t, K group 0: channels 0..2 = empty / side to move / opponent (cnn.py:93-95).  K group 1 keeps stale
+            // finite activations, which the stem's zero weights for channels 8..15 cancel.
+            if (in_meta & 4u) {
+                const int pl = (in_meta >> 1) & 1, bit = (int)(in_meta >> 8);
+                const uint32_t live = in_meta & 1u;
+                const uint32_t s0 = (uint32_t)((in_b0 >> bit) & 1ull), s1 = (uint32_t)((in_b1 >> bit) & 1ull);
+                const uint32_t mine = live * (pl ? s1 : s0), theirs = live * (pl ? s0 : s1), emp = live * (1u - (s0 | s1));
+                const uint32_t one = F16 ? 0x3C00u : 0x3F80u;
+                *reinterpret_cast<uint4 *>(bufT + (GUARD + tid) * ROWB) = make_uint4(emp * one | (mine * one) << 16, theirs * one, 0u, 0u);
+            }
+            fence_async_smem();
+            fence_before();
+            batch_sync();
+            fence_after();
+        }
+
+        if (warp == 9) {
+            // ===== weight producer: every piece of every layer, in the order the issuer consumes them =====
+            for (int l = 0; l < n_layers; ++l) {
+                const bool head = l >= n_conv;
+                const uint8_t *src = l == 0 ? weights : (head ? head_w : weights + 9 * PIECE_BYTES + (size_t)(l - 1) * 9 * KS * PIECE_BYTES);
+                const uint32_t bytes = head ? HEAD_PIECE_BYTES : PIECE_BYTES;
+                const int pieces = l == 0 ? 9 : 9 * KS;
+#pragma unroll 1
+                for (int i = 0; i < pieces; ++i, ++g) {
+                    const uint32_t st = g % NS;
+                    if (g >= NS) mbar_wait(empty0 + st * 8, ((g / NS) - 1u) & 1u);  // the MMAs of the previous use have read the stage
+                    if (elect_one()) bulk_load(ring0 + st * PIECE_BYTES, src + (size_t)i * bytes, bytes, full0 + st * 8);
+                    __syncwarp();
+                }
+            }
+        } else if (warp == 8) {
+            // ===== MMA issuer (converged; one elected lane issues) =====
+            for (int l = 0; l < n_layers; ++l) {
+                const bool head = l >= n_conv;
+                const uint32_t src = l == 0 ? aT : ((head || (l & 1)) ? aX : aT);  // conv1 (odd l) and the heads read x; conv2 reads t
+                const uint32_t idesc = head ? instr_desc(128, NHC, F16) : instr_desc(128, C, F16);
+                const uint32_t acc = tmem_base + (uint32_t)(l & 1) * 256u;
+                const uint64_t a_desc = smem_desc(src, LBO_A, SBO_A);
+                const int ksteps = l == 0 ? 1 : KS;
+#pragma unroll 1
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    // input channels 16 ks .. 16 ks + 15 of every row are written once all eight epilogue warps have passed them
+                    if (l > 0) {
+                        mbar_wait(chunk0 + ks * 8, (ge0 + (uint32_t)l - 1u) & 1u);
+                        fence_after();
+                    }
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap, ++g) {
+                        const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);  // rows; one row = 16 B = one descriptor address unit
+                        const uint32_t st = g % NS;
+                        mbar_wait(full0 + st * 8, (g / NS) & 1u);
+                        fence_after();
+                        if (elect_one()) {
+                            const uint64_t bd = smem_desc(ring0 + st * PIECE_BYTES, LBO_W, SBO_W);
+#pragma unroll
+                            for (int t = 0; t < TILES; ++t)
+                                umma(acc + t * C, a_desc + (uint64_t)(int64_t)(shift + t * 128 + ks * (int)(2 * LBO_A >> 4)), bd, idesc, (ks | tap) > 0);
+                            umma_commit(empty0 + st * 8);
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (elect_one()) umma_commit(mma_done);
+                __syncwarp();
+            }
+        } else {
+            // ===== epilogue warps: thread = (tile, row) =====
+            const int tile = (int)(warp >> 2);
+            const int r = tile * 128 + (int)((warp & 3u) * 32u + lane);
+            int pos, y, x;
+            const bool valid = decode_row(r, pos, y, x);
+            const uint32_t lane_addr = tmem_base + (((warp & 3u) * 32u) << 16) + (uint32_t)tile * C;
+            const uint32_t row_off = (GUARD + r) * ROWB;
+            for (int l = 0; l < n_conv; ++l) {
+                uint8_t *dst = (l & 1) ? bufT : bufX;          // stem and conv2 write x, conv1 writes t
+                const bool skip = l > 0 && !(l & 1);            // conv2: + x, in place
+                const float *bias = s_bias + l * C;
+                const uint32_t acc = lane_addr + (uint32_t)(l & 1) * 256u;
+                mbar_wait(mma_done, (gl0 + (uint32_t)l) & 1u);
+                fence_after();
+                uint32_t va[16], vb[16];
+                auto chunk = [&](const uint32_t (&v)[16], int c) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint8_t *p = dst + (2 * c + h) * LBO_A + row_off;
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[h * 8 + j]) + bias[c * 16 + h * 8 + j];
+                        if (skip) {
+                            const uint4 s = *reinterpret_cast<const uint4 *>(p);
+                            const float2 s0 = unpack16<F16>(s.x), s1 = unpack16<F16>(s.y), s2 = unpack16<F16>(s.z), s3 = unpack16<F16>(s.w);
+                            f[0] += s0.x; f[1] += s0.y; f[2] += s1.x; f[3] += s1.y;
+                            f[4] += s2.x; f[5] += s2.y; f[6] += s3.x; f[7] += s3.y;
+                        }
+                        uint4 o = make_uint4(0, 0, 0, 0);
+                        if (valid)
+                            o = make_uint4(pack16<F16>(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f)), pack16<F16>(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f)),
+                                           pack16<F16>(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f)), pack16<F16>(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f)));
+                        *reinterpret_cast<uint4 *>(p) = o;
+                    }
+                    // this warp's rows of channels 16 c .. 16 c + 15 are in place for the tensor core (and its reads of the
+                    // accumulator columns are complete): one arrival per warp
+                    fence_before();
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(chunk0 + c * 8);
+                };
+                tmem_ld16_issue(acc, va);
+#pragma unroll 1
+                for (int c = 0; c < KS; c += 2) {
+                    tmem_ld_wait();
+                    tmem_ld16_issue(acc + (c + 1) * 16, vb);
+                    chunk(va, c);
+                    tmem_ld_wait();
+                    if (c + 2 < KS) tmem_ld16_issue(acc + (c + 2) * 16, va);
+                    chunk(vb, c + 1);
+                }
+            }
+            // ---- heads: [POS][35][42] fp32 in the Flatten() order of NCHW, then both FC layers on CUDA cores
+            float *hact = reinterpret_cast<float *>(bufT + OFF_HACT);
+            const float *hb = s_bias + n_conv * C;
+            {
+                mbar_wait(mma_done, (gl0 + (uint32_t)n_conv) & 1u);
+                fence_after();
+                const uint32_t acc = lane_addr + (uint32_t)(n_conv & 1) * 256u;
+                uint32_t v[32], w[16];
+                tmem_ld32_issue(acc, v);
+                tmem_ld16_issue(acc + 32, w);
+                tmem_ld_wait();
+                if (valid) {
+                    float *o = hact + pos * NHU * 42 + y * c4::W + x;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) o[c * 42] = fmaxf(__uint_as_float(v[c]) + hb[c], 0.f);
+#pragma unroll
+                    for (int c = 32; c < NHU; ++c) o[c * 42] = fmaxf(__uint_as_float(w[c - 32]) + hb[c], 0.f);
+                }
+            }
+            fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // thread t takes inputs k = t, t + 256, ...: every FC weight is read once per CTA (coalesced) and used for POS positions;
+            // acc[p][j], j = 7 is the value head
+            float acc[POS * 8];
+#pragma unroll
+            for (int i = 0; i < POS * 8; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int k0 = 0; k0 < 32 * 42; k0 += 256) {
+                const int k = k0 + (int)tid;
+                const bool in = k < 32 * 42;
+                const int kk = in ? k : 0;
+                float wj[7];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) wj[j] = in ? __ldg(fc_policy_w + j * (32 * 42) + kk) : 0.f;
+#pragma unroll
+                for (int p = 0; p < POS; ++p) {
+                    const float xv = hact[p * NHU * 42 + kk];
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) acc[p * 8 + j] = fmaf(wj[j], xv, acc[p * 8 + j]);
+                }
+            }
+            {
+                const bool in = tid < 3 * 42;
+                const int kk = in ? (int)tid : 0;
+                const float wv = in ? __ldg(fc_value_w + kk) : 0.f;
+#pragma unroll
+                for (int p = 0; p < POS; ++p) acc[p * 8 + 7] = fmaf(wv, hact[p * NHU * 42 + 32 * 42 + kk], acc[p * 8 + 7]);
+            }
+            // warp reduction by recursive halving: lane L ends with the total of index L
+#pragma unroll
+            for (int h = POS * 4; h >= 1; h >>= 1) {
+                const bool up = (lane & (uint32_t)h) != 0;
+#pragma unroll
+                for (int i = 0; i < h; ++i) {
+                    const float send = up ? acc[i] : acc[i + h];
+                    const float keep = up ? acc[i + h] : acc[i];
+                    acc[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, h);
+                }
+            }
+            float *red = reinterpret_cast<float *>(bufT + OFF_RED);  // [8 warps][32]
+            red[warp * 32 + lane] = acc[0];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid < POS * 8) {
+                float sum = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) sum += red[w8 * 32 + tid];
+                const int p = (int)tid >> 3, j = (int)tid & 7;
+                const long long gp = pos0 + p;
+                if (gp < n) {
+                    const long long slot = eval_list ? (long long)__ldg(eval_list + gp) : gp;
+                    if (j < 7) {
+                        logits[slot * 7 + j] = sum + __ldg(fc_policy_b + j);
+                    } else {
+                        const float v = tanhf(sum + __ldg(fc_value_b));
+                        values[slot * 2] = v;
+                        values[slot * 2 + 1] = -v;
+                    }
+                }
+            }
+        }
+    }  // batches
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512u);
+}
+
+}  // namespace
+
+extern "C" {
+
+/* bytes of packed trunk weights for `num_blocks` residual blocks of 128 channels: stem 9 pieces + 72 pieces per convolution, 4 KB each */
+int64_t az_resnet128_weight_bytes(int32_t num_blocks) { return 9ll * PIECE_BYTES + (int64_t)num_blocks * 2 * 9 * KS * PIECE_BYTES; }
+
+/* internal: called by az_resnet_forward_leaves_v2 (csrc/az_conv.cu) for num_channels == 128 */
+int32_t az_resnet128_launch(az_engine *engine, const az_resnet_desc *d, float *logits, float *values, void *stream) {
+    if (!engine || !d || !d->trunk_w || !d->trunk_b || d->num_blocks < 0 || 1 + 2 * d->num_blocks + 1 > MAX_LAYERS) return AZ_E_INVALID;
+    if (d->operand_format != AZ_FMT_BF16 && d->operand_format != AZ_FMT_F16) return AZ_E_INVALID;
+    const uint64_t *bb0 = nullptr, *bb1 = nullptr;
+    const uint8_t *status = nullptr, *player = nullptr;
+    const int32_t *elist = nullptr, *ecount = nullptr;
+    int32_t n = 0;
+    if (az_leaf_arrays(engine, &bb0, &bb1, &status, &n) != AZ_OK || az_leaf_players(engine, &player) != AZ_OK ||
+        az_leaf_compact(engine, &elist, &ecount) != AZ_OK || n <= 0)
+        return AZ_E_INVALID;
+    static bool attr_set[64] = {false};
+    const int dev = az_device(engine);
+    if (dev < 0 || dev >= 64 || cudaSetDevice(dev) != cudaSuccess) return AZ_E_CUDA;
+    if (!attr_set[dev]) {
+        if (cudaFuncSetAttribute(k_resnet128<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
+        if (cudaFuncSetAttribute(k_resnet128<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
+        attr_set[dev] = true;
+    }
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return AZ_E_CUDA;
+    const int batches = (n + POS - 1) / POS;
+    auto kern = d->operand_format == AZ_FMT_F16 ? k_resnet128<true> : k_resnet128<false>;
+    kern<<<batches < sms ? batches : sms, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
+        bb0, bb1, player, status, elist, ecount, (long long)n, (const uint8_t *)d->trunk_w, d->trunk_b, d->num_blocks, (const uint8_t *)d->head_conv_w,
+        d->head_conv_b, d->fc_policy_w, d->fc_policy_b, d->fc_value_w, d->fc_value_b, logits, values);
+    return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;
+}
+
+}  // extern "C"

@@ -359,24 +359,48 @@ def pack_trunk_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloa
     return torch.cat(parts).contiguous(), torch.stack(biases).contiguous().float()
 
 
+def pack_trunk_weights128(model: "ResNet", device, dtype: torch.dtype = torch.bfloat16) -> tuple[Tensor, Tensor]:
+    """The same convolutions for the 128-channel kernel (csrc/az_conv128.cu): per layer the pieces [128 out][16 in] in the order
+    the kernel consumes them, K-chunk-major: for ks (16 input channels) for tap (3*ky + kx); the stem has one K chunk (3 -> 16)."""
+    assert model.num_channels == 128
+    m = copy.deepcopy(model).eval().float().to(device)
+    convs = [_fold_bn(m.input_conv[0], m.input_conv[1])]
+    for blk in m.residual_blocks:
+        convs.append(_fold_bn(blk.conv1, blk.bn1))
+        convs.append(_fold_bn(blk.conv2, blk.bn2))
+    parts, biases = [], []
+    for li, (w, b) in enumerate(convs):
+        if li == 0:
+            w = torch.cat([w, torch.zeros(128, 13, 3, 3, device=w.device)], dim=1)
+        for ks in range(w.shape[1] // 16):
+            for ky in range(3):
+                for kx in range(3):
+                    parts.append(_canonical_kmajor(w[:, 16 * ks:16 * ks + 16, ky, kx], dtype))
+        biases.append(b)
+    return torch.cat(parts).contiguous(), torch.stack(biases).contiguous().float()
+
+
 def pack_head_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloat16):
     """Policy conv1x1 (-> 32) and value conv3x3 (-> 3), BatchNorm folded, as ONE 48-output 3x3 conv for csrc/az_conv.cu
     (the 1x1 weights occupy the centre tap), plus the two fully connected layers in fp32."""
     m = copy.deepcopy(model).eval().float().to(device)
-    wp, bp = _fold_bn(m.policy_head[0], m.policy_head[1])  # [32, 64, 1, 1]
-    wv, bv = _fold_bn(m.value_head[0], m.value_head[1])    # [3, 64, 3, 3]
-    w = torch.zeros(48, 64, 3, 3, device=device)
+    wp, bp = _fold_bn(m.policy_head[0], m.policy_head[1])  # [32, C, 1, 1]
+    wv, bv = _fold_bn(m.value_head[0], m.value_head[1])    # [3, C, 3, 3]
+    w = torch.zeros(48, model.num_channels, 3, 3, device=device)
     w[:32, :, 1, 1] = wp[:, :, 0, 0]
     w[32:35] = wv
     b = torch.zeros(48, device=device)
     b[:32], b[32:35] = bp, bv
-    conv = torch.cat([_canonical_kmajor(w[:, :, ky, kx], dtype) for ky in range(3) for kx in range(3)]).contiguous()
+    if model.num_channels == 128:  # pieces [48][16] in (ks, tap) order, like the trunk's
+        conv = torch.cat([_canonical_kmajor(w[:, 16 * ks:16 * ks + 16, ky, kx], dtype) for ks in range(8) for ky in range(3) for kx in range(3)]).contiguous()
+    else:
+        conv = torch.cat([_canonical_kmajor(w[:, :, ky, kx], dtype) for ky in range(3) for kx in range(3)]).contiguous()
     f = lambda t: t.detach().float().contiguous()
     return conv, b.contiguous(), f(m.policy_head[4].weight), f(m.policy_head[4].bias), f(m.value_head[4].weight).reshape(-1), f(m.value_head[4].bias)
 
 
 class TensorCoreTrunk:
-    """Stem + residual blocks of a 64-channel ResNet as one tcgen05 kernel on the engine's leaves (csrc/az_conv.cu)."""
+    """A ResNet (64 or 128 channels) as one tcgen05 kernel on the engine's leaves (csrc/az_conv.cu, csrc/az_conv128.cu)."""
 
     def __init__(self, model: "ResNet", device: torch.device, dtype: torch.dtype = torch.bfloat16):
         from . import _lib
@@ -385,8 +409,10 @@ class TensorCoreTrunk:
         self.device = torch.device(device)
         self.dtype = dtype
         self.num_blocks = model.num_res_blocks
-        self.weights, self.biases = pack_trunk_weights(model, self.device, dtype)
-        assert self.weights.numel() * 2 == self.lib.az_trunk_weight_bytes(self.num_blocks)
+        self.num_channels = model.num_channels
+        self._pack = pack_trunk_weights128 if self.num_channels == 128 else pack_trunk_weights
+        self.weights, self.biases = self._pack(model, self.device, dtype)
+        assert self.weights.numel() * 2 == (self.lib.az_resnet128_weight_bytes if self.num_channels == 128 else self.lib.az_trunk_weight_bytes)(self.num_blocks)
         self.heads = pack_head_weights(model, self.device, dtype)
         hw, hb, fpw, fpb, fvw, fvb = self.heads
         self.desc = _lib.AzResnetDesc(self.num_blocks, model.num_channels, _operand_format(dtype), 0, self.weights.data_ptr(),
@@ -398,9 +424,9 @@ class TensorCoreTrunk:
 
     def set_weights(self, model: "ResNet") -> bool:
         """Re-pack `model`'s weights into the existing device buffers (same addresses: captured graphs stay valid)."""
-        if model.num_res_blocks != self.num_blocks or model.num_channels != 64:
+        if model.num_res_blocks != self.num_blocks or model.num_channels != self.num_channels:
             return False
-        w, b = pack_trunk_weights(model, self.device, self.dtype)
+        w, b = self._pack(model, self.device, self.dtype)
         self.weights.copy_(w)
         self.biases.copy_(b)
         for dst, src in zip(self.heads, pack_head_weights(model, self.device, self.dtype)):
@@ -424,7 +450,7 @@ class TensorCoreTrunk:
 
     def forward_leaves(self, engine) -> Tensor:
         """-> trunk activations [n, 64, 6, 7] bf16 (channels-last memory) for the leaves of `engine.select_leaves()`."""
-        assert self.dtype == torch.bfloat16, "the trunk-only entry point is bf16 (az_trunk_forward_leaves)"
+        assert self.dtype == torch.bfloat16 and self.num_channels == 64, "the trunk-only entry point is bf16, 64 channels (az_trunk_forward_leaves)"
         n = engine.n_active
         if n not in self._out:
             self._out[n] = torch.empty((n, 6, 7, 64), dtype=torch.bfloat16, device=self.device)
@@ -462,7 +488,7 @@ class InferenceNet(nn.Module):
         elif isinstance(m, (CNNModel, ResNet)):
             self.input_layout = LAYOUT_PLANES_BF16 if dtype == torch.bfloat16 else LAYOUT_PLANES_F32
             self.trunk = None
-            if isinstance(m, ResNet) and m.num_channels == 64 and dtype in (torch.bfloat16, torch.float16) and use_tensor_core_kernels:
+            if isinstance(m, ResNet) and m.num_channels in (64, 128) and m.num_res_blocks <= 11 and dtype in (torch.bfloat16, torch.float16) and use_tensor_core_kernels:
                 self.trunk = TensorCoreTrunk(m, torch.device(device), dtype)  # hand-written tcgen05 kernel: trunk + heads (csrc/az_conv.cu)
             self.net = self._fold(m).to(dtype).to(memory_format=torch.channels_last)
         else:
@@ -533,7 +559,7 @@ class InferenceNet(nn.Module):
         if self.fused is not None:
             return "k_mlp_fused"
         if self.trunk is not None:
-            return "k_resnet_trunk"
+            return "k_resnet128" if self.trunk.num_channels == 128 else "k_resnet_trunk"
         return "k_encode + cuDNN/cuBLAS (torch)"
 
     @torch.no_grad()

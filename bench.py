@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--burn-in", type=int, default=36, help="untimed move steps before the warm-up (games reach their stationary mix)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--extras", default="config2,tree_scaling,basic,resnet9x128,cnn",
+    ap.add_argument("--extras", default="config2,tree_scaling,resnet4x64:fp16,basic,resnet9x128,cnn",
                     help="side measurements on one GPU, comma separated: config2 | tree_scaling | basic | resnetBxC | cnn | none")
     ap.add_argument("--extra-steps", type=int, default=3)
     ap.add_argument("--cpu-games", type=int, default=256, help="games of the CPU arm's bounded sample")
@@ -337,9 +337,11 @@ def net_extra(args, spec: str, device_index: int, peaks: dict):
     import alphazero_implementation_b200 as az
     from alphazero_implementation_b200.engine import EVAL_UNIFORM
 
+    spec, _, dname = spec.partition(":")  # "resnet4x64:fp16" = the same net with fp16 operands
+    dname = dname or ("bf16" if args.dtype == "fp32" else args.dtype)
     model, flops = make_model(spec)
     E, S = 16384, args.sims
-    dt = torch.bfloat16 if args.dtype == "fp32" else torch_dtype(args.dtype)
+    dt = torch_dtype(dname)
     search = az.AlphaZeroSearch(model=model, num_simulations=S, device=device_index, inference_dtype=dt)
     eng = search.engine_for(E)
     eng.reset_games()
@@ -365,7 +367,7 @@ def net_extra(args, spec: str, device_index: int, peaks: dict):
     eng.drain_episodes_device()
     k_mean = float(np.mean(k_ms))
     evals_per_launch = st["evaluations"] / (n * S)
-    rec = {"workload": f"connect4_selfplay_{spec}_{args.dtype}_{E}x{S}", "net": net_label(spec), "evaluator": search.evaluator_name,
+    rec = {"workload": f"connect4_selfplay_{spec}_{dname}_{E}x{S}", "net": net_label(spec), "evaluator": search.evaluator_name,
            "move_steps": n, "sims_per_s": st["simulations"] / ms * 1e3, "us_per_sim_step": ms * 1e3 / (n * S),
            "flops_per_position": flops, "evaluator_kernel_us": k_mean * 1e3,
            "tensor_tflops_in_kernel": evals_per_launch * flops / (k_mean * 1e-3) / 1e12,
@@ -619,7 +621,7 @@ def run_b200(args):
                     extras["config2"] = config2_extra(args, local, peaks)
                 elif spec == "tree_scaling":
                     extras["tree_scaling"] = tree_scaling(args, local, peaks)
-                elif spec != args.net:
+                elif spec != args.net + ":" + args.dtype and spec != args.net:
                     extras.setdefault("net_in_loop", []).append(net_extra(args, spec, local, peaks))
             except Exception as exc:
                 extras.setdefault("errors", {})[spec] = repr(exc)[:300]

@@ -1,0 +1,91 @@
+"""GPU: the hand-written tcgen05 kernel for the reference's own ResNet(board, 7, B, 128) (csrc/az_conv128.cu; architecture:
+src/alphazero_simple/resnet.py:30-103, instantiated 9 x 128 in src/alphazero_less_simple/main.py:13) against plain PyTorch:
+(a) the same arithmetic emulated in PyTorch (BatchNorm folded, 16-bit-rounded weights and inter-layer activations, fp32
+accumulation) within accumulation-order noise, (b) the fp32 module within north_star's 1e-3 on priors / values in fp16 mode."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import alphazero_implementation_b200 as az  # noqa: E402
+from alphazero_implementation_b200.engine import LAYOUT_PLANES_F32  # noqa: E402
+from alphazero_implementation_b200.models import InferenceNet, _fold_bn  # noqa: E402
+from test_gpu_trunk import _engine_with_leaves, _randomise_bn  # noqa: E402
+
+
+def _emulated(model, x, dtype):
+    r = lambda t: t.to(dtype).to(torch.float32)
+    w, b = _fold_bn(model.input_conv[0], model.input_conv[1])
+    h = r(torch.relu(F.conv2d(r(x), r(w), b, padding=1)))
+    for blk in model.residual_blocks:
+        w1, b1 = _fold_bn(blk.conv1, blk.bn1)
+        w2, b2 = _fold_bn(blk.conv2, blk.bn2)
+        t = r(torch.relu(F.conv2d(h, r(w1), b1, padding=1)))
+        h = r(torch.relu(F.conv2d(t, r(w2), b2, padding=1) + h))
+    wp, bp = _fold_bn(model.policy_head[0], model.policy_head[1])
+    wv, bv = _fold_bn(model.value_head[0], model.value_head[1])
+    pa = torch.relu(F.conv2d(h, r(wp), bp))
+    va = torch.relu(F.conv2d(h, r(wv), bv, padding=1))
+    return model.policy_head[4](pa.flatten(1)), torch.tanh(model.value_head[4](va.flatten(1)))
+
+
+@pytest.mark.parametrize("blocks,n,dtype", [(0, 4, torch.bfloat16), (1, 3, torch.bfloat16), (1, 64, torch.float16), (2, 1000, torch.bfloat16),
+                                            (9, 700, torch.float16), (3, 2501, torch.bfloat16)])
+def test_resnet128_kernel_matches_pytorch(blocks, n, dtype):
+    torch.manual_seed(13 * blocks + n)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = az.ResNet(num_res_blocks=blocks, num_channels=128).cuda().eval()
+    _randomise_bn(model)
+    eng = _engine_with_leaves(n, seed=n + 2)
+    live = eng.leaf_info()["status"] == 0
+    assert live.any()
+    x = eng.gather_leaves(LAYOUT_PLANES_F32)
+    net = InferenceNet(model, dtype=dtype)
+    assert net.kernel_name == "k_resnet128"
+    logits, values = net.forward_leaves(eng)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        l_emu, v_emu = _emulated(model, x, dtype)
+        l_32, v_32 = model(x)
+    assert torch.isfinite(logits).all() and torch.isfinite(values).all()
+    assert (logits[~live] == 0).all() and (values[~live] == 0).all()  # slots without an evaluation are left alone
+    tol = 4e-3 if dtype == torch.float16 else 3e-2  # accumulation order differs (taps outer vs K chunks outer); one rounding flip per activation
+    assert torch.allclose(logits[live], l_emu[live], atol=tol, rtol=2e-2), float((logits[live] - l_emu[live]).abs().max())
+    assert torch.allclose(values[live, :1], v_emu[live], atol=tol), float((values[live, :1] - v_emu[live]).abs().max())
+    assert torch.equal(values[:, 1], -values[:, 0])
+    dp = float((torch.softmax(logits[live], 1) - torch.softmax(l_32[live], 1)).abs().max())
+    dv = float((values[live] - v_32[live]).abs().max())
+    if dtype == torch.float16:
+        assert dp <= 1e-3 and dv <= 1e-3, (dp, dv)  # north_star tolerance against the fp32 `predict`
+    else:
+        assert dp <= 2e-2 and dv <= 5e-2, (dp, dv)
+    eng.close()
+
+
+def test_resnet128_in_the_search_loop_and_weight_refresh():
+    """9 x 128 through AlphaZeroSearch (CUDA-graphed steps); `update_inference_model` rewrites the packed weights in place and the
+    captured graph keeps working."""
+    torch.manual_seed(3)
+    model = az.ResNet(num_res_blocks=9, num_channels=128)
+    search = az.AlphaZeroSearch(model=model, num_simulations=40, inference_dtype=torch.bfloat16)
+    assert search.evaluator_name == "k_resnet128"
+    nodes = [az.Node(az.Config().sample_initial_state()) for _ in range(6)]
+    search.run_simulations(nodes)
+    a = [[ch.visit_count for ch in nd.children.values()] for nd in nodes]
+    assert all(sum(v) == 39 for v in a) and all(v == a[0] for v in a)  # same root, same evaluator: same tree
+    graph = search._graphed.graph
+    model2 = az.ResNet(num_res_blocks=9, num_channels=128)
+    search.update_inference_model(model2)
+    assert search._graphed is not None and search._graphed.graph is graph  # refreshed in place
+    nodes = [az.Node(az.Config().sample_initial_state()) for _ in range(6)]
+    search.run_simulations(nodes)
+    b = [[ch.visit_count for ch in nd.children.values()] for nd in nodes]
+    fresh = az.AlphaZeroSearch(model=model2, num_simulations=40, inference_dtype=torch.bfloat16)
+    nodes = [az.Node(az.Config().sample_initial_state()) for _ in range(6)]
+    fresh.run_simulations(nodes)
+    assert b == [[ch.visit_count for ch in nd.children.values()] for nd in nodes]
+    search.close()
+    fresh.close()
