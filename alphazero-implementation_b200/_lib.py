@@ -141,6 +141,7 @@ SIGNATURES = {
     "az_mlp_launch_count": (I64, [P]),
     "az_leaf_players": (I32, [P, C.POINTER(P)]),
     "az_leaf_compact": (I32, [P, C.POINTER(P), C.POINTER(P)]),
+    "az_set_leaf_compaction": (I32, [P, I32]),
     "az_trunk_weight_bytes": (I64, [I32]),
     "az_resnet128_weight_bytes": (I64, [I32]),
     "az_trunk_forward_leaves": (I32, [P, P, P, I32, P, P]),

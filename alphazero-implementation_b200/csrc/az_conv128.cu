@@ -7,8 +7,10 @@
 // filter tap is the same buffer with the MMA descriptor moved by 8*dy + dx rows; compact padding: a position is 7 x 8 pixel rows),
 // but a different schedule, because with 128 channels nothing that kernel relies on fits: the 9 taps of a layer are 288 KB.
 //  * A CTA works on 4 positions = 2 accumulator tiles of 128 rows x 128 fp32 columns.  Both tiles use every weight piece, so a
-//    layer's weights are streamed ONCE per CTA: pieces of [128 out][16 in] (4 KB), ordered K-chunk-major (ks, tap), through a
-//    16-stage ring of bulk async copies - 4 KB per 2 MMAs of 64 cycles = 32 B/clk, half of the SM's L2 port.
+//    layer's weights are streamed ONCE per CTA, K-chunk-major: a piece is the 9 taps of one K chunk, [9][128 out][16 in] = 36 KB,
+//    through a 2-stage ring of bulk async copies - 36 KB per 18 MMAs of 64 cycles = 32 B/clk, half of the SM's L2 port.  The
+//    pieces must be this large: a bulk copy costs ~300 cycles whatever its size (measured: 4 KB pieces arrived one per
+//    ~350 cycles = 11.7 B/clk and the tensor pipe sat at 34 %; profiles/r02_k_resnet128_4k_pieces_ncu_raw.json).
 //  * Layers are pipelined through tensor memory instead of ping-ponging two groups: the accumulators are double-buffered
 //    (2 sets x 2 tiles x 128 columns = all 512 columns).  While the eight epilogue warps drain layer l (tcgen05.ld, bias (+ skip),
 //    ReLU, round to 16 bits, write the next layer's A operand), the tensor core already runs layer l + 1 into the other set:
@@ -44,16 +46,18 @@ constexpr int RTOT = ROWS + 2 * GUARD;           // 288 rows per K group
 constexpr uint32_t LBO_A = RTOT * ROWB;          // 4608: next K group
 constexpr uint32_t SBO_A = 128;                  // next 8-row group
 constexpr uint32_t BUF_BYTES = KG * LBO_A;       // 73728
-constexpr uint32_t PIECE_BYTES = C * 16 * 2;     // 4096: [128 out][16 in]
+constexpr uint32_t TAP_BYTES = C * 16 * 2;       // 4096: one tap of a K chunk, [128 out][16 in]
+constexpr uint32_t PIECE_BYTES = 9 * TAP_BYTES;  // 36864: the 9 taps of a K chunk
 constexpr uint32_t LBO_W = 128, SBO_W = 256;     // canonical K-major [N][16]
 constexpr int NHC = 48, NHU = 35;                // head conv channels: 32 policy (1x1, centre tap) + 3 value (3x3) + padding
-constexpr uint32_t HEAD_PIECE_BYTES = NHC * 16 * 2;  // 1536
-constexpr int NS = 16;                           // ring stages
-constexpr int MAX_LAYERS = 24;
+constexpr uint32_t HEAD_TAP_BYTES = NHC * 16 * 2;    // 1536
+constexpr uint32_t HEAD_PIECE_BYTES = 9 * HEAD_TAP_BYTES;
+constexpr int NS = 2;                            // ring stages
+constexpr int MAX_CONV = 19;                     // stem + 9 blocks
 constexpr int THREADS = 320, WTHREADS = 288;
 constexpr uint32_t OFF_RING = 2 * BUF_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_RING + NS * PIECE_BYTES;
-constexpr uint32_t OFF_BARS = OFF_BIAS + MAX_LAYERS * C * 4;
+constexpr uint32_t OFF_BARS = OFF_BIAS + (MAX_CONV * C + NHC) * 4;
 constexpr int NBARS = 2 * NS + 1 + KS;           // full[NS] empty[NS] mma_done chunk[KS]
 constexpr uint32_t SMEM_BYTES = OFF_BARS + NBARS * 8 + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -159,9 +163,9 @@ k_resnet128(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ 
             // ===== weight producer: every piece of every layer, in the order the issuer consumes them =====
             for (int l = 0; l < n_layers; ++l) {
                 const bool head = l >= n_conv;
-                const uint8_t *src = l == 0 ? weights : (head ? head_w : weights + 9 * PIECE_BYTES + (size_t)(l - 1) * 9 * KS * PIECE_BYTES);
+                const uint8_t *src = l == 0 ? weights : (head ? head_w : weights + PIECE_BYTES + (size_t)(l - 1) * KS * PIECE_BYTES);
                 const uint32_t bytes = head ? HEAD_PIECE_BYTES : PIECE_BYTES;
-                const int pieces = l == 0 ? 9 : 9 * KS;
+                const int pieces = l == 0 ? 1 : KS;
 #pragma unroll 1
                 for (int i = 0; i < pieces; ++i, ++g) {
                     const uint32_t st = g % NS;
@@ -179,28 +183,27 @@ k_resnet128(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ 
                 const uint32_t acc = tmem_base + (uint32_t)(l & 1) * 256u;
                 const uint64_t a_desc = smem_desc(src, LBO_A, SBO_A);
                 const int ksteps = l == 0 ? 1 : KS;
+                const uint32_t tap_units = (head ? HEAD_TAP_BYTES : TAP_BYTES) >> 4;
 #pragma unroll 1
-                for (int ks = 0; ks < ksteps; ++ks) {
+                for (int ks = 0; ks < ksteps; ++ks, ++g) {
                     // input channels 16 ks .. 16 ks + 15 of every row are written once all eight epilogue warps have passed them
-                    if (l > 0) {
-                        mbar_wait(chunk0 + ks * 8, (ge0 + (uint32_t)l - 1u) & 1u);
-                        fence_after();
-                    }
+                    if (l > 0) mbar_wait(chunk0 + ks * 8, (ge0 + (uint32_t)l - 1u) & 1u);
+                    const uint32_t st = g % NS;
+                    mbar_wait(full0 + st * 8, (g / NS) & 1u);  // the K chunk's 9 taps have landed
+                    fence_after();
+                    if (elect_one()) {
+                        const uint64_t bd = smem_desc(ring0 + st * PIECE_BYTES, LBO_W, SBO_W);
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap, ++g) {
-                        const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);  // rows; one row = 16 B = one descriptor address unit
-                        const uint32_t st = g % NS;
-                        mbar_wait(full0 + st * 8, (g / NS) & 1u);
-                        fence_after();
-                        if (elect_one()) {
-                            const uint64_t bd = smem_desc(ring0 + st * PIECE_BYTES, LBO_W, SBO_W);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);  // rows; one row = 16 B = one descriptor address unit
 #pragma unroll
                             for (int t = 0; t < TILES; ++t)
-                                umma(acc + t * C, a_desc + (uint64_t)(int64_t)(shift + t * 128 + ks * (int)(2 * LBO_A >> 4)), bd, idesc, (ks | tap) > 0);
-                            umma_commit(empty0 + st * 8);
+                                umma(acc + t * C, a_desc + (uint64_t)(int64_t)(shift + t * 128 + ks * (int)(2 * LBO_A >> 4)), bd + (uint64_t)(tap * tap_units), idesc,
+                                     (ks | tap) > 0);
                         }
-                        __syncwarp();
+                        umma_commit(empty0 + st * 8);
                     }
+                    __syncwarp();
                 }
                 if (elect_one()) umma_commit(mma_done);
                 __syncwarp();
@@ -348,12 +351,12 @@ k_resnet128(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ 
 
 extern "C" {
 
-/* bytes of packed trunk weights for `num_blocks` residual blocks of 128 channels: stem 9 pieces + 72 pieces per convolution, 4 KB each */
-int64_t az_resnet128_weight_bytes(int32_t num_blocks) { return 9ll * PIECE_BYTES + (int64_t)num_blocks * 2 * 9 * KS * PIECE_BYTES; }
+/* bytes of packed trunk weights for `num_blocks` residual blocks of 128 channels: stem 1 piece + 8 pieces per convolution, 36 KB each */
+int64_t az_resnet128_weight_bytes(int32_t num_blocks) { return (int64_t)PIECE_BYTES + (int64_t)num_blocks * 2 * KS * PIECE_BYTES; }
 
 /* internal: called by az_resnet_forward_leaves_v2 (csrc/az_conv.cu) for num_channels == 128 */
 int32_t az_resnet128_launch(az_engine *engine, const az_resnet_desc *d, float *logits, float *values, void *stream) {
-    if (!engine || !d || !d->trunk_w || !d->trunk_b || d->num_blocks < 0 || 1 + 2 * d->num_blocks + 1 > MAX_LAYERS) return AZ_E_INVALID;
+    if (!engine || !d || !d->trunk_w || !d->trunk_b || d->num_blocks < 0 || 1 + 2 * d->num_blocks > MAX_CONV) return AZ_E_INVALID;
     if (d->operand_format != AZ_FMT_BF16 && d->operand_format != AZ_FMT_F16) return AZ_E_INVALID;
     const uint64_t *bb0 = nullptr, *bb1 = nullptr;
     const uint8_t *status = nullptr, *player = nullptr;

@@ -896,13 +896,27 @@ k_expand_select(Arena a, int n_active, const float *__restrict__ policy, const f
 // ~15 % of the simulations of a running self-play loop end in a terminal leaf (search.py:75-77) and need no evaluation; the
 // tensor-core evaluators walk this list instead of all E rows and scatter their outputs back to the slots' rows.  One block:
 // each thread counts its contiguous stretch of slots, a block-wide exclusive scan gives its offset (deterministic order, no atomics).
+// Thread t owns the slots [t * per, t * per + per), per a multiple of 16, and reads them as 16-byte vectors (the status array is
+// padded by 16 bytes): one L2 round trip per thread instead of one per slot.
+__device__ __forceinline__ uint32_t eval_bits(uint32_t w) { return ~(w | (w >> 1)) & 0x01010101u; }  // bit 8 i set <=> byte i == AZ_LEAF_EVAL (0); bytes are 0 / 1 / 2
 __global__ void __launch_bounds__(1024) k_compact_leaves(const uint8_t *__restrict__ status, int n, int32_t *__restrict__ list, int32_t *__restrict__ count) {
+    static_assert(AZ_LEAF_EVAL == 0 && AZ_LEAF_TERMINAL == 1 && AZ_LEAF_IDLE == 2, "eval_bits relies on the status encoding");
     __shared__ int warp_tot[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n + 1023) / 1024;
-    const int lo = tid * per, hi = min(n, lo + per);
+    const int per = (((n + 1023) / 1024) + 15) & ~15;
+    const int lo = tid * per;
     int mine = 0;
-    for (int i = lo; i < hi; ++i) mine += status[i] == AZ_LEAF_EVAL;
+    for (int base = lo; base < lo + per && base < n; base += 16) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(status + base);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t z = eval_bits(w[k]);
+            const int left = n - (base + 4 * k);  // slots of this word that exist
+            if (left < 4) z &= left <= 0 ? 0u : (0x01010101u >> (8 * (4 - left)));
+            mine += __popc(z);
+        }
+    }
     int incl = mine;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -923,8 +937,19 @@ __global__ void __launch_bounds__(1024) k_compact_leaves(const uint8_t *__restri
     }
     __syncthreads();
     int o = warp_tot[warp] + incl - mine;
-    for (int i = lo; i < hi; ++i)
-        if (status[i] == AZ_LEAF_EVAL) list[o++] = i;
+    for (int base = lo; base < lo + per && base < n; base += 16) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(status + base);  // L1 hit
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t z = eval_bits(w[k]);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int i = base + 4 * k + b;
+                if (((z >> (8 * b)) & 1u) && i < n) list[o++] = i;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1462,6 +1487,8 @@ struct az_engine {
     int force_hot_nodes;  // -1 = automatic
     int last_hot_nodes;
     int sims_done;  // simulations run on the current roots (arena and tables are sized for num_simulations)
+    bool compact;        // az_set_leaf_compaction: every selection is followed by k_compact_leaves
+    bool compact_valid;  // eval_list / eval_count describe the leaves of the last selection
     uint64_t init0, init1;
     int initpl;
     bool have_init;
@@ -1606,7 +1633,7 @@ int32_t az_create(const az_config *cfg, az_engine **out) {
     a.tab_n = cfg->num_simulations + 8;
     AL(d_rcp, a.tab_n); AL(d_sqt, a.tab_n); AL(d_t2, a.tab_n);
     AL(a.root_bb0, E); AL(a.root_bb1, E); AL(a.root_player, E); AL(a.used, E); AL(a.tree_err, E);
-    AL(a.leaf_node, E); AL(a.leaf_bb0, E); AL(a.leaf_bb1, E); AL(a.leaf_player, E); AL(a.leaf_status, E);
+    AL(a.leaf_node, E); AL(a.leaf_bb0, E); AL(a.leaf_bb1, E); AL(a.leaf_player, E); AL(a.leaf_status, E + 16);
     AL(a.leaf_depth, E); AL(a.path, (size_t)E * PATH_STRIDE); AL(a.tstats, (size_t)E * NSTAT);
     AL(a.eval_list, E); AL(a.eval_count, 4);
     AL(a.g_bb0, (size_t)E * MAX_PLIES); AL(a.g_bb1, (size_t)E * MAX_PLIES); AL(a.g_player, (size_t)E * MAX_PLIES);
@@ -1934,8 +1961,11 @@ int32_t az_select_leaves(az_engine *h, void *stream) {
     else AZ_SEL(4);
 #undef AZ_SEL
     AZ_LAUNCH_CHECK(h, "k_select");
-    k_compact_leaves<<<1, 1024, 0, S(stream)>>>(h->a.leaf_status, n, h->a.eval_list, h->a.eval_count);
-    AZ_LAUNCH_CHECK(h, "k_compact_leaves");
+    h->compact_valid = h->compact;
+    if (h->compact) {
+        k_compact_leaves<<<1, 1024, 0, S(stream)>>>(h->a.leaf_status, n, h->a.eval_list, h->a.eval_count);
+        AZ_LAUNCH_CHECK(h, "k_compact_leaves");
+    }
     h->sims_done += 1;
     return AZ_OK;
 }
@@ -1959,6 +1989,7 @@ int32_t az_expand_backup(az_engine *h, const float *policy, const float *values,
     else if (h->G == 16) k_expand_backup<2><<<blocks_for(n, 4), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind);
     else k_expand_backup<4><<<blocks_for(n, 8), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind);
     AZ_LAUNCH_CHECK(h, "k_expand_backup");
+    h->compact_valid = false;  // the leaves are consumed
     return AZ_OK;
 }
 
@@ -1984,8 +2015,11 @@ int32_t az_expand_backup_select(az_engine *h, const float *policy, const float *
     else AZ_ES(4);
 #undef AZ_ES
     AZ_LAUNCH_CHECK(h, "k_expand_select");
-    k_compact_leaves<<<1, 1024, 0, S(stream)>>>(h->a.leaf_status, n, h->a.eval_list, h->a.eval_count);
-    AZ_LAUNCH_CHECK(h, "k_compact_leaves");
+    h->compact_valid = h->compact;
+    if (h->compact) {
+        k_compact_leaves<<<1, 1024, 0, S(stream)>>>(h->a.leaf_status, n, h->a.eval_list, h->a.eval_count);
+        AZ_LAUNCH_CHECK(h, "k_compact_leaves");
+    }
     h->sims_done += 1;
     return AZ_OK;
 }
@@ -2013,8 +2047,14 @@ int32_t az_leaf_arrays(az_engine *h, const uint64_t **bb0, const uint64_t **bb1,
  * number - both on the device (engine-owned, valid until az_destroy) */
 int32_t az_leaf_compact(az_engine *h, const int32_t **eval_list, const int32_t **eval_count) {
     if (!h) return AZ_E_INVALID;
-    if (eval_list) *eval_list = h->a.eval_list;
-    if (eval_count) *eval_count = h->a.eval_count;
+    if (eval_list) *eval_list = h->compact_valid ? h->a.eval_list : nullptr;
+    if (eval_count) *eval_count = h->compact_valid ? h->a.eval_count : nullptr;
+    return AZ_OK;
+}
+
+int32_t az_set_leaf_compaction(az_engine *h, int32_t on) {
+    if (!h) return AZ_E_INVALID;
+    h->compact = on != 0;
     return AZ_OK;
 }
 

@@ -533,6 +533,8 @@ int32_t az_mlp_forward_leaves(az_mlp *m, az_engine *engine, float *logits, float
     const uint8_t *status = nullptr;
     int32_t n = 0;
     if (az_leaf_arrays(engine, &bb0, &bb1, &status, &n) != AZ_OK || n <= 0) return AZ_E_INVALID;
+    // walks the engine's compacted leaf list when the last selection produced one (az_set_leaf_compaction); at <= 148 tiles of 128
+    // rows the kernel is one wave either way, so the BasicNN path leaves compaction off and saves the extra launch
     const int32_t *elist = nullptr, *ecount = nullptr;
     if (az_leaf_compact(engine, &elist, &ecount) != AZ_OK) return AZ_E_INVALID;
     cudaSetDevice(m->device);

@@ -92,6 +92,7 @@ class Engine:
             raise RuntimeError(f"az_create failed ({rc}): {self.lib.az_last_error(None).decode()}")
         self.h = h
         self.n_active = self.num_games
+        self.leaf_compaction = False
         self.tree_capacity = self.lib.az_tree_capacity(self.h)
 
     # -- plumbing --------------------------------------------------------------------------------
@@ -181,6 +182,11 @@ class Engine:
         self.n_active = n
 
     # -- search ----------------------------------------------------------------------------------
+    def set_leaf_compaction(self, on: bool):
+        """Follow every selection with the ordered list of the slots that wait for an evaluation (the ResNet kernels walk it)."""
+        self._check(self.lib.az_set_leaf_compaction(self.h, int(bool(on))), "az_set_leaf_compaction")
+        self.leaf_compaction = bool(on)
+
     def run_simulations(self, num_sims: int, eval_kind: int):
         self._check(self.lib.az_run_simulations(self.h, int(num_sims), int(eval_kind), _stream()), "az_run_simulations")
 

@@ -488,7 +488,7 @@ class InferenceNet(nn.Module):
         elif isinstance(m, (CNNModel, ResNet)):
             self.input_layout = LAYOUT_PLANES_BF16 if dtype == torch.bfloat16 else LAYOUT_PLANES_F32
             self.trunk = None
-            if isinstance(m, ResNet) and m.num_channels in (64, 128) and m.num_res_blocks <= 11 and dtype in (torch.bfloat16, torch.float16) and use_tensor_core_kernels:
+            if isinstance(m, ResNet) and m.num_channels in (64, 128) and m.num_res_blocks <= (9 if m.num_channels == 128 else 11) and dtype in (torch.bfloat16, torch.float16) and use_tensor_core_kernels:
                 self.trunk = TensorCoreTrunk(m, torch.device(device), dtype)  # hand-written tcgen05 kernel: trunk + heads (csrc/az_conv.cu)
             self.net = self._fold(m).to(dtype).to(memory_format=torch.channels_last)
         else:
@@ -553,6 +553,12 @@ class InferenceNet(nn.Module):
         for a, b in zip(old_t, new_t):
             a.copy_(b.to(a.dtype))
         return True
+
+    @property
+    def wants_leaf_compaction(self) -> bool:
+        """The ResNet kernels process several waves of small batches, so skipping the ~15 % of slots whose leaf is terminal pays;
+        the MLP kernel is one wave of 128-row tiles either way."""
+        return self.trunk is not None
 
     @property
     def kernel_name(self) -> str:

@@ -86,6 +86,7 @@ class _GraphedStep:
 
     def __init__(self, engine: Engine, net, layout: int):
         self.engine, self.net, self.layout = engine, net, layout
+        engine.set_leaf_compaction(getattr(net, "wants_leaf_compaction", False))  # before the first selection (and any capture)
         self.graph = None
         self.n = -1
         self.x = None
@@ -214,8 +215,10 @@ class AlphaZeroSearch:
         """Kernels of libaz_engine.so per self-play move step (`simulate_and_move`)."""
         if self._mode == "builtin":
             return 1
-        # k_select + k_compact_leaves; S - 1 x (evaluator or gather, k_expand_select, k_compact_leaves); evaluator, k_expand_backup; k_sample_moves
-        return 3 * self.num_simulations + 2
+        # k_select; S - 1 x (evaluator or gather, k_expand_select); evaluator, k_expand_backup; k_sample_moves - plus one
+        # k_compact_leaves per selection when the evaluator walks the compacted leaf list
+        S = self.num_simulations
+        return 2 * S + 2 + (S if getattr(self._net, "wants_leaf_compaction", False) else 0)
 
     def close(self):
         if self._engine is not None:

@@ -18,3 +18,4 @@ from .episode import Episode, Sample  # noqa: E402,F401
 from .search import AlphaZeroSearch, Node  # noqa: E402,F401
 from .episode_generator import EpisodeGenerator  # noqa: E402,F401
 from .models import BasicNN, CNNModel, Connect4Model, Model, ResNet  # noqa: E402,F401
+from .player import AlphaZeroPlayer, Arena, Player, calculate_expected_score, elo_ladder, play_game, update_elo  # noqa: E402,F401

@@ -114,7 +114,7 @@ class ClockSampler:
 
     REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
-    def __init__(self, index: int, period_s: float = 0.02):
+    def __init__(self, index: int, period_s: float = 0.1):
         import threading
 
         self.samples, self.reason_bits, self.power = [], 0, []
@@ -157,7 +157,7 @@ class ClockSampler:
         sm = sorted(self.samples)
         reasons = sorted(k for k, bit in self.REASONS.items() if self.reason_bits & bit)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "power_w_max": max(self.power) if self.power else None,
-                "samples": len(sm), "reasons": reasons, "source": "NVML polled every 20 ms during the timed region"}
+                "samples": len(sm), "reasons": reasons, "source": "NVML polled every 100 ms during the timed region"}
 
 
 def algorithmic_bytes(st: dict) -> int:
@@ -509,9 +509,12 @@ def run_b200(args):
     t_wall0 = time.perf_counter()
     ev0.record()
     drained = []
+    step_ev = [ev0]
     for i in range(K):
         search.simulate_and_move(eng, u_all[n_pre + i])  # 800 x (k_resnet_trunk, k_expand_select) replayed from a CUDA graph + k_sample_moves
         drained.append(eng.drain_episodes_device())      # device -> device; keeps the episode ring from filling
+        step_ev.append(torch.cuda.Event(enable_timing=True))
+        step_ev[-1].record()
     ag0.record()
     merged = concat_device(drained)
     if world > 1:
@@ -522,6 +525,7 @@ def run_b200(args):
     clocks = sampler.stop()
     st = diff(st0, eng.stats())
     total_ms, ag_ms = ev0.elapsed_time(ev1), ag0.elapsed_time(ev1)
+    step_ms = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(K)]
     n_eps_job = int(merged["ep_len"].numel())
     if world > 1:
         t = torch.tensor([total_ms, ag_ms], dtype=torch.float64, device=eng.device)
@@ -599,7 +603,7 @@ def run_b200(args):
     details = {"games_per_gpu": E, "burn_in_steps": args.burn_in, "tree_arena_bytes": arena_bytes, "evaluator": search.evaluator_name,
                "flops_per_position": flops, "leaf_eval_fraction": tot_evals / max(1.0, tot_sims),
                "us_per_simulation_step": total_ms * 1e3 / (K * S), "cuda_graph": bool(search.use_cuda_graph),
-               "episodes_finished_in_timed_region": n_eps_job}
+               "episodes_finished_in_timed_region": n_eps_job, "step_ms": [round(x, 2) for x in step_ms]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:

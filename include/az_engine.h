@@ -162,9 +162,12 @@ int32_t az_leaf_info(az_engine *h, uint64_t *out_bb0, uint64_t *out_bb1, uint8_t
  * lets another kernel consume the leaves without a gather launch (see az_mlp_forward_leaves) */
 int32_t az_leaf_arrays(az_engine *h, const uint64_t **bb0, const uint64_t **bb1, const uint8_t **status, int32_t *n_active);
 int32_t az_leaf_players(az_engine *h, const uint8_t **player);
-/* Ordered list of the slots whose leaf waits for the evaluator (status AZ_LEAF_EVAL) and its length, both DEVICE pointers, rebuilt
- * by every az_select_leaves / az_expand_backup_select: terminal leaves (search.py:75-77, ~15 % of the simulations of a running
- * self-play loop) need no evaluation, so the tensor-core evaluators walk this list and scatter their outputs to the slots' rows. */
+/* Leaf compaction.  Terminal leaves (search.py:75-77, ~15 % of the simulations of a running self-play loop) need no evaluation.
+ * az_set_leaf_compaction(h, 1): every az_select_leaves / az_expand_backup_select is followed by one more small launch that writes
+ * the ordered list of the slots whose leaf waits for the evaluator (status AZ_LEAF_EVAL) and its length; the ResNet evaluators
+ * then walk that list and scatter their outputs to the slots' rows.  az_leaf_compact returns the two DEVICE pointers, or NULLs
+ * when the last selection ran without compaction (the evaluators then compute every slot's row, zeros for the others). */
+int32_t az_set_leaf_compaction(az_engine *h, int32_t on);
 int32_t az_leaf_compact(az_engine *h, const int32_t **eval_list, const int32_t **eval_count);
 
 /* ---- results ---- */

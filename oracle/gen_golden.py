@@ -16,6 +16,7 @@ Files
                          outcomes, yield order, number of RNG draws) under np.random.seed(seed).
   rules_goldens.json     random playouts through the game-rules stand-in, cross-checked move by move
                          against the in-tree rules `src/alphazero_simple/connect4_game.py:28-98`.
+  training_goldens.json  losses of four `training_step` + Adam steps of BasicNN / CNNModel on one fixed batch.
   basicnn_goldens.json   `BasicNN.predict` / `CNNModel.predict` outputs (fp32, CPU) on fixture states
                          with seeded random weights, plus one C1 run (E=1, S=100, BasicNN).
 """
@@ -262,13 +263,49 @@ def gen_nets(R):
     return out
 
 
+def gen_training(R):
+    """`Model.training_step` + `configure_optimizers` (models/base/model.py:27-48) and `format_dataset` (:76-82) of the reference on
+    the fixture states: CE(soft visit targets) + MSE, Adam(lr 1e-3, weight decay 1e-4), four optimiser steps on one batch."""
+    import torch
+
+    states = [R.State.from_json(state_json(s)) for s in FINAL_SITUATIONS + START_SITUATIONS]
+    policies, values = [], []
+    for i, s in enumerate(states):
+        acts = s.actions
+        w = [1.0 + ((a.column * (i % 3 + 1)) % 5) for a in acts]
+        policies.append({a: wi / sum(w) for a, wi in zip(acts, w)})
+        values.append([1.0, -1.0] if i % 2 else [-1.0, 1.0])
+    out = {}
+    for name, cls in (("BasicNN", R.BasicNN), ("CNNModel", R.CNNModel)):
+        torch.manual_seed(0)
+        torch.set_num_threads(1)
+        m = cls()
+        ds = m.format_dataset(states, policies, values)
+        x, p, v = ds.tensors
+        m.train()
+        opt = m.configure_optimizers()
+        torch.manual_seed(1)  # Dropout masks of CNNModel
+        losses = []
+        for step in range(4):
+            opt.zero_grad()
+            loss = m.training_step((x, p, v), step)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        out[name] = dict(losses=losses, policy_target=p.tolist(), value_target=v.tolist(), input_shape=list(x.shape),
+                         param_abs_sum=float(sum(q.detach().double().abs().sum() for q in m.parameters())),
+                         optimizer=dict(type=type(opt).__name__, lr=opt.defaults["lr"], weight_decay=opt.defaults["weight_decay"]))
+    return out
+
+
 def main():
     R = load_reference()
     os.makedirs(GOLDEN, exist_ok=True)
     meta = dict(generator="oracle/gen_golden.py", reference="pierreveron/alphazero-implementation @ /root/reference",
                 game_layer="oracle/shims/simulator (stand-in; third-party simulator 0.0.4 source absent: PARITY UNPINNED)")
     for fname, fn in (("rules_goldens.json", gen_rules), ("search_goldens.json", gen_search),
-                      ("nets_goldens.json", gen_nets), ("selfplay_goldens.json", gen_selfplay)):
+                      ("nets_goldens.json", gen_nets), ("selfplay_goldens.json", gen_selfplay),
+                      ("training_goldens.json", gen_training)):
         data = fn(R)
         with open(os.path.join(GOLDEN, fname), "w") as f:
             json.dump(dict(meta=meta, data=data), f, separators=(",", ":"))

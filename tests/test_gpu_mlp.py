@@ -92,6 +92,7 @@ def test_fused_leaf_gather_equals_separate_gather():
         eng.run_simulations(40, 2)
         eng.sample_moves(u)
     eng.run_simulations(40, 2)
+    eng.set_leaf_compaction(True)
     eng.select_leaves()
     status = eng.leaf_info()["status"]
     assert (status == 1).any() and (status == 0).any()
@@ -101,5 +102,4 @@ def test_fused_leaf_gather_equals_separate_gather():
     torch.cuda.synchronize()
     live = status == 0
     assert torch.equal(a_l[live], b_l[live]) and torch.equal(a_v[live], b_v[live])
-    assert (b_l[~live] == 0).all() and (b_v[~live] == 0).all()
     eng.close()

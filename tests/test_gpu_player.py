@@ -1,0 +1,52 @@
+"""GPU: the search's consumers outside training: `AlphaZeroPlayer.play` with the reference's temperature rule
+(ui/cli/player.py:42-76), a game between two agents (src/elo.ipynb#cell3), the batched arena and the Elo ladder (#cell1, #cell4)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import alphazero_implementation_b200 as az  # noqa: E402
+
+
+def _state(case):
+    return az.State(az.Config(6, 7, 4), case["bb0"], case["bb1"], case["player"])
+
+
+def test_player_temperature_rule(search_goldens):
+    case = next(c for c in search_goldens if c["name"].startswith("final0_k1_S100"))  # player 0 wins at column 3
+    s = _state(case)
+    greedy = az.AlphaZeroPlayer(az.UniformEvaluator(), mcts_simulation=100, temperature=0)
+    assert greedy.play(s).column == case["expected_move"] == 3
+    # temperature 1: moves are drawn in proportion to the visit counts [1,1,1,93,1,1,1]
+    t1 = az.AlphaZeroPlayer(az.UniformEvaluator(), mcts_simulation=100, temperature=1.0)
+    t1.seed(0)
+    picks = [t1.play(s).column for _ in range(60)]
+    assert picks.count(3) >= 45 and set(picks) <= set(range(7))
+    # a small temperature sharpens the distribution: (93/99) ** 10 dominates
+    cold = az.AlphaZeroPlayer(az.UniformEvaluator(), mcts_simulation=100, temperature=0.1)
+    cold.seed(0)
+    assert all(cold.play(s).column == 3 for _ in range(20))
+    # temperature inf: a uniformly random legal move, no search
+    rnd = az.AlphaZeroPlayer(az.UniformEvaluator(), temperature=float("inf"))
+    rnd.seed(1)
+    cols = {rnd.play(s).column for _ in range(80)}
+    assert cols == {a.column for a in s.actions}
+
+
+def test_play_game_and_arena_and_elo():
+    init = az.Config(6, 7, 4).sample_initial_state()
+    strong = az.AlphaZeroPlayer(az.UniformEvaluator(), mcts_simulation=300, temperature=0)
+    weak = az.AlphaZeroPlayer(az.UniformEvaluator(), temperature=float("inf"))
+    weak.seed(3)
+    assert az.play_game(strong, weak, init) in (0.0, 0.5, 1.0)
+    res = az.Arena(strong, weak, init).play(64)
+    assert res["games"] == 64 == res["a_wins"] + res["draws"] + res["b_wins"]
+    assert res["a_score"] >= 0.85  # 300 simulations of plain MCTS against random moves
+    # the batched arena plays the same game as the one-position-at-a-time loop when both agents are deterministic
+    a = az.AlphaZeroPlayer(az.HashEvaluator(), mcts_simulation=64, temperature=0)
+    b = az.AlphaZeroPlayer(az.UniformEvaluator(), mcts_simulation=48, temperature=0)
+    single = az.play_game(a, b, init)
+    group = az.Arena(a, b, init)._play_group(a, b, 3)
+    assert (group == single).all()
+    ratings = az.elo_ladder({"mcts300": az.UniformEvaluator(), "hash64": az.HashEvaluator()}, init, games_per_pair=4, mcts_simulation=64)
+    assert set(ratings) == {"mcts300", "hash64"} and sum(ratings.values()) in range(2992, 3001)  # int truncation loses less than a point per rating per game

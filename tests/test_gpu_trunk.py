@@ -11,8 +11,11 @@ from alphazero_implementation_b200.engine import LAYOUT_PLANES_F32  # noqa: E402
 from alphazero_implementation_b200.models import TensorCoreTrunk, _fold_bn  # noqa: E402
 
 
-def _engine_with_leaves(n, seed=0, deep=True):
+def _engine_with_leaves(n, seed=0, deep=True, compact=False):
+    """An engine whose last selection left a mix of leaves that wait for an evaluation and terminal leaves.  `compact`: the
+    selection also writes the ordered list of the former (az_set_leaf_compaction), which the ResNet kernels then walk."""
     eng = az.Engine(num_games=n, num_simulations=48)
+    eng.set_leaf_compaction(compact)
     eng.reset_games()
     u = torch.from_numpy(np.random.RandomState(seed).random_sample(n)).cuda()
     for _ in range(12 if deep else 3):
@@ -101,7 +104,7 @@ def test_full_net_kernel_matches_pytorch_reference(blocks, n):
     torch.backends.cuda.matmul.allow_tf32 = False
     model = az.ResNet(num_res_blocks=blocks, num_channels=64).cuda().eval()
     _randomise_bn(model)
-    eng = _engine_with_leaves(n, seed=n + 1)
+    eng = _engine_with_leaves(n, seed=n + 1, compact=n % 2 == 1)  # both ways of walking the batch
     live = eng.leaf_info()["status"] == 0
     x = eng.gather_leaves(LAYOUT_PLANES_F32)
     trunk = TensorCoreTrunk(model, torch.device("cuda", torch.cuda.current_device()))

@@ -39,7 +39,8 @@ def test_resnet128_kernel_matches_pytorch(blocks, n, dtype):
     torch.backends.cuda.matmul.allow_tf32 = False
     model = az.ResNet(num_res_blocks=blocks, num_channels=128).cuda().eval()
     _randomise_bn(model)
-    eng = _engine_with_leaves(n, seed=n + 2)
+    compact = n != 64  # one case computes every slot's row, the others walk the compacted leaf list
+    eng = _engine_with_leaves(n, seed=n + 2, compact=compact)
     live = eng.leaf_info()["status"] == 0
     assert live.any()
     x = eng.gather_leaves(LAYOUT_PLANES_F32)
@@ -51,7 +52,8 @@ def test_resnet128_kernel_matches_pytorch(blocks, n, dtype):
         l_emu, v_emu = _emulated(model, x, dtype)
         l_32, v_32 = model(x)
     assert torch.isfinite(logits).all() and torch.isfinite(values).all()
-    assert (logits[~live] == 0).all() and (values[~live] == 0).all()  # slots without an evaluation are left alone
+    if compact:
+        assert (logits[~live] == 0).all() and (values[~live] == 0).all()  # slots without an evaluation are left alone
     tol = 4e-3 if dtype == torch.float16 else 3e-2  # accumulation order differs (taps outer vs K chunks outer); one rounding flip per activation
     assert torch.allclose(logits[live], l_emu[live], atol=tol, rtol=2e-2), float((logits[live] - l_emu[live]).abs().max())
     assert torch.allclose(values[live, :1], v_emu[live], atol=tol), float((values[live, :1] - v_emu[live]).abs().max())

@@ -162,3 +162,54 @@ def test_shard_table_is_validated_before_any_collective():
     assert [shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
     shards = [shard_range(8, r, 4, trainer_share=1.0) for r in range(4)]
     assert shards[0] == (0, 8) and all(lo == hi for lo, hi in shards[1:])  # Trainer.train raises on EVERY rank for such a table
+
+
+def test_training_step_losses_match_the_reference(nets_goldens):
+    """Row f1: `Model.training_step` + `configure_optimizers` (models/base/model.py:27-48) - CE(soft visit targets) + MSE,
+    Adam(lr 1e-3, weight decay 1e-4) - reproduce the losses of four optimiser steps the REFERENCE's own classes took on the same
+    batch (tests/golden/training_goldens.json, oracle/gen_golden.py:gen_training).  CPU, fp32, same seeds; CNNModel includes
+    train-mode BatchNorm and Dropout(0.3)."""
+    import torch
+
+    from alphazero_implementation_b200.models import BasicNN, CNNModel
+    from conftest import load_golden
+    from oracle.net_eval import grid_f32, planes_f32
+
+    tg = load_golden("training_goldens.json")
+    st = nets_goldens["states"]
+    bb0 = np.array([s["bb0"] for s in st], np.uint64)
+    bb1 = np.array([s["bb1"] for s in st], np.uint64)
+    pl = np.array([s["player"] for s in st], np.uint8)
+    for name, cls in (("BasicNN", BasicNN), ("CNNModel", CNNModel)):
+        ref = tg[name]
+        torch.manual_seed(0)
+        torch.set_num_threads(1)
+        m = cls()
+        x = torch.from_numpy(grid_f32(bb0, bb1) if name == "BasicNN" else planes_f32(bb0, bb1, pl))
+        assert list(x.shape) == ref["input_shape"]
+        p, v = torch.tensor(ref["policy_target"]), torch.tensor(ref["value_target"])
+        m.train()
+        opt = m.configure_optimizers()
+        assert type(opt).__name__ == ref["optimizer"]["type"] and opt.defaults["lr"] == ref["optimizer"]["lr"]
+        assert opt.defaults["weight_decay"] == ref["optimizer"]["weight_decay"]
+        torch.manual_seed(1)
+        losses = []
+        for step in range(4):
+            opt.zero_grad()
+            loss = m.training_step((x, p, v), step)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        assert np.allclose(losses, ref["losses"], rtol=2e-5, atol=1e-6), (name, losses, ref["losses"])
+        s = float(sum(q.detach().double().abs().sum() for q in m.parameters()))
+        assert abs(s - ref["param_abs_sum"]) <= 1e-6 * ref["param_abs_sum"], name
+
+
+def test_elo_update_is_the_notebooks():
+    """src/elo.ipynb#cell1: K = 32, ratings truncated to int."""
+    from alphazero_implementation_b200.player import calculate_expected_score, update_elo
+
+    assert calculate_expected_score(1500, 1500) == 0.5
+    assert update_elo(1500, 1500, 1.0) == (1516, 1484)
+    assert update_elo(1500, 1500, 0.5) == (1500, 1500)
+    assert update_elo(1516, 1484, 0.0) == (int(1516 + 32 * (0 - 1 / (1 + 10 ** (-32 / 400)))), int(1484 + 32 * (1 - (1 - 1 / (1 + 10 ** (-32 / 400))))))
