@@ -512,8 +512,9 @@ def run_b200(args):
     step_ev = [ev0]
     for i in range(K):
         search.simulate_and_move(eng, u_all[n_pre + i])  # 800 x (k_resnet_trunk, k_expand_select) replayed from a CUDA graph + k_sample_moves
-        drained.append(eng.drain_episodes_device())      # device -> device; keeps the episode ring from filling
-        step_ev.append(torch.cuda.Event(enable_timing=True))
+        if (i + 1) % 16 == 0 or i + 1 == K:  # device -> device; the ring holds 2 E + 64 episodes, ~E / 20 finish per step.  Draining
+            drained.append(eng.drain_episodes_device())  # (a host synchronisation) every step left the GPU queue empty at every
+        step_ev.append(torch.cuda.Event(enable_timing=True))  # step boundary: any host hiccup there showed up as a 10 % slower step
         step_ev[-1].record()
     ag0.record()
     merged = concat_device(drained)
