@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("AZ_ENGINE_LIB") or os.path.join(PKG_DIR, "libaz_engine.so")  # override: A/B builds of the library
-SOURCES = ["az_engine.cu", "az_mlp.cu", "az_conv.cu", "az_conv128.cu"]
+SOURCES = ["az_engine.cu", "az_mlp.cu", "az_conv.cu", "az_resnet_pipe.cu"]
 HEADERS = ["az_eval.cuh", "c4_bitboard.cuh", "tcgen05.cuh", os.path.join("..", "..", "include", "az_engine.h")]
 
 NVCC_FLAGS = [
@@ -86,7 +86,7 @@ class AzStats(C.Structure):
 
 class AzResnetDesc(C.Structure):
     _fields_ = [
-        ("num_blocks", C.c_int32), ("num_channels", C.c_int32), ("operand_format", C.c_int32), ("reserved", C.c_int32),
+        ("num_blocks", C.c_int32), ("num_channels", C.c_int32), ("operand_format", C.c_int32), ("variant", C.c_int32),
         ("trunk_w", C.c_void_p), ("trunk_b", C.c_void_p), ("head_conv_w", C.c_void_p), ("head_conv_b", C.c_void_p),
         ("fc_policy_w", C.c_void_p), ("fc_policy_b", C.c_void_p), ("fc_value_w", C.c_void_p), ("fc_value_b", C.c_void_p),
     ]
@@ -143,7 +143,7 @@ SIGNATURES = {
     "az_leaf_compact": (I32, [P, C.POINTER(P), C.POINTER(P)]),
     "az_set_leaf_compaction": (I32, [P, I32]),
     "az_trunk_weight_bytes": (I64, [I32]),
-    "az_resnet128_weight_bytes": (I64, [I32]),
+    "az_resnet_pipe_weight_bytes": (I64, [I32, I32]),
     "az_trunk_forward_leaves": (I32, [P, P, P, I32, P, P]),
     "az_resnet_forward_leaves": (I32, [P, P, P, I32, P, P, P, P, P, P, P, P, P]),
     "az_resnet_forward_leaves_v2": (I32, [P, C.POINTER(AzResnetDesc), P, P, P]),

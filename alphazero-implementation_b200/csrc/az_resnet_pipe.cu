@@ -1,7 +1,9 @@
-// The reference's own ResNet(board, 7, num_res_blocks, 128) (src/alphazero_simple/resnet.py:30-103, instantiated 9 x 128 in
+// ResNet(board, 7, num_res_blocks, C) (src/alphazero_simple/resnet.py:30-103; the reference's own instance is 9 x 128,
 // src/alphazero_less_simple/main.py:13) behind the main package's Model API, BatchNorm folded, as ONE tcgen05 kernel for the
-// leaves of the search: stem conv3x3 (3 -> 128), residual blocks (2 x conv3x3 128 -> 128, skip, ReLU), the policy / value head
-// convolutions and the two small FC layers.  223.9 MFLOP per position at 9 blocks; activations never leave the SM.
+// leaves of the search: stem conv3x3 (3 -> C), residual blocks (2 x conv3x3 C -> C, skip, ReLU), the policy / value head
+// convolutions and the two small FC layers; activations never leave the SM.  Two instances: C = 128 with 2 accumulator tiles
+// (4 positions) per CTA - 223.9 MFLOP per position at 9 blocks - and C = 64 with 4 tiles (8 positions), the headline net 4 x 64.
+// The comments below give the numbers of the 128-channel instance.
 //
 // Same implicit-GEMM formulation as csrc/az_conv.cu (pixel = GEMM row, channels = K, activation buffer K-group-major so that a
 // filter tap is the same buffer with the MMA descriptor moved by 8*dy + dx rows; compact padding: a position is 7 x 8 pixel rows),
@@ -22,7 +24,9 @@
 //    any more (conv1 of the same block is complete) - two activation buffers (x, t) of 72 KB are enough.
 //  * Shared-memory operand traffic: A 4 KB + B 4 KB per 64-cycle MMA = 128 B/clk, the crossbar's rate; N = 128 is therefore
 //    balanced where the 64-channel kernel (6 KB per 32 cycles) is operand-bound.
-// Roles: warps 0..7 epilogue (thread = one pixel row of one tile), warp 8 issues MMAs (one elected lane), warp 9 streams weights.
+//    With 64 channels the same MMAs are operand-bound as in csrc/az_conv.cu (6 KB per 32 cycles -> ~48 cycles each); what this
+//    schedule saves there is everything around them: no per-group hand-overs, weights once per layer for all four tiles.
+// Roles: warps 0..7 epilogue (thread = one pixel row of each pair of tiles), warp 8 issues MMAs (one elected lane), warp 9 streams weights.
 #include <stdint.h>
 #include <stdio.h>
 
@@ -34,39 +38,48 @@ namespace {
 
 using namespace tc05;
 
-constexpr int C = 128;                 // trunk channels
-constexpr int KG = C / 8;              // K groups of 8 channels (16 bytes per row)
-constexpr int KS = C / 16;             // K steps per tap
 constexpr int GUARD = 16;              // zero rows before / after the tiles (a tap moves the window by up to 9 rows)
 constexpr uint32_t ROWB = 16;
 constexpr int PW = 8, PIX = 56, LEAD = 8;  // pixel-row stride, rows per position, leading zero rows of a tile
-constexpr int TPOS = 2, TILES = 2, POS = TPOS * TILES;  // positions per tile / tiles per CTA / positions per CTA
-constexpr int ROWS = TILES * 128;
-constexpr int RTOT = ROWS + 2 * GUARD;           // 288 rows per K group
-constexpr uint32_t LBO_A = RTOT * ROWB;          // 4608: next K group
-constexpr uint32_t SBO_A = 128;                  // next 8-row group
-constexpr uint32_t BUF_BYTES = KG * LBO_A;       // 73728
-constexpr uint32_t TAP_BYTES = C * 16 * 2;       // 4096: one tap of a K chunk, [128 out][16 in]
-constexpr uint32_t PIECE_BYTES = 9 * TAP_BYTES;  // 36864: the 9 taps of a K chunk
+constexpr int TPOS = 2;                // positions per 128-row tile
+constexpr uint32_t SBO_A = 128;        // next 8-row group
 constexpr uint32_t LBO_W = 128, SBO_W = 256;     // canonical K-major [N][16]
-constexpr int NHC = 48, NHU = 35;                // head conv channels: 32 policy (1x1, centre tap) + 3 value (3x3) + padding
+constexpr int NHC = 48, NHU = 35;      // head conv channels: 32 policy (1x1, centre tap) + 3 value (3x3) + padding
 constexpr uint32_t HEAD_TAP_BYTES = NHC * 16 * 2;    // 1536
 constexpr uint32_t HEAD_PIECE_BYTES = 9 * HEAD_TAP_BYTES;
-constexpr int NS = 2;                            // ring stages
-constexpr int MAX_CONV = 19;                     // stem + 9 blocks
 constexpr int THREADS = 320, WTHREADS = 288;
-constexpr uint32_t OFF_RING = 2 * BUF_BYTES;
-constexpr uint32_t OFF_BIAS = OFF_RING + NS * PIECE_BYTES;
-constexpr uint32_t OFF_BARS = OFF_BIAS + (MAX_CONV * C + NHC) * 4;
-constexpr int NBARS = 2 * NS + 1 + KS;           // full[NS] empty[NS] mma_done chunk[KS]
-constexpr uint32_t SMEM_BYTES = OFF_BARS + NBARS * 8 + 16;
-static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(LEAD + TPOS * PIX <= 128, "a tile's positions must fit its 128 rows");
-// FC-tail scratch inside t's K groups 2..7 (K groups 0 / 1 take the next batch's stem input): head activations, then the per-warp sums
-constexpr uint32_t OFF_HACT = 2 * LBO_A;
-constexpr uint32_t HACT_BYTES = POS * NHU * 42 * 4;
-constexpr uint32_t OFF_RED = OFF_HACT + 24 * 1024;
-static_assert(HACT_BYTES <= 24 * 1024 && OFF_RED + 8 * 32 * 4 <= 8 * LBO_A, "FC scratch must stay inside K groups 2..7");
+
+// C channels, TILES accumulator tiles per CTA (TILES * C = 256 tensor-memory columns per accumulator set), NS ring stages
+template <int C_, int TILES_, int NS_, int MAX_CONV_>
+struct Cfg {
+    static constexpr int C = C_, TILES = TILES_, NS = NS_, MAX_CONV = MAX_CONV_;
+    static constexpr int KG = C / 8;              // K groups of 8 channels (16 bytes per row)
+    static constexpr int KS = C / 16;             // K steps per tap = pieces per layer = chunks of an epilogue
+    static constexpr int POS = TPOS * TILES;      // positions per CTA
+    static constexpr int ROWS = TILES * 128;
+    static constexpr int RTOT = ROWS + 2 * GUARD; // rows per K group
+    static constexpr int RPT = TILES / 2;         // rows per epilogue thread (tiles w/4, w/4 + 2, ...)
+    static constexpr uint32_t LBO_A = RTOT * ROWB;          // next K group
+    static constexpr uint32_t BUF_BYTES = KG * LBO_A;
+    static constexpr uint32_t TAP_BYTES = C * 16 * 2;       // one tap of a K chunk, [C out][16 in]
+    static constexpr uint32_t PIECE_BYTES = 9 * TAP_BYTES;  // the 9 taps of a K chunk
+    static constexpr uint32_t OFF_RING = 2 * BUF_BYTES;
+    static constexpr uint32_t OFF_BIAS = OFF_RING + NS * PIECE_BYTES;
+    static constexpr uint32_t OFF_BARS = OFF_BIAS + (MAX_CONV * C + NHC) * 4;
+    static constexpr int NBARS = 2 * NS + 1 + KS;           // full[NS] empty[NS] mma_done chunk[KS]
+    static constexpr uint32_t SMEM_BYTES = OFF_BARS + NBARS * 8 + 16;
+    // FC-tail scratch inside t's K groups 2..7 (K groups 0 / 1 take the next batch's stem input): head activations, per-warp sums
+    static constexpr uint32_t OFF_HACT = 2 * LBO_A;
+    static constexpr uint32_t HACT_BYTES = POS * NHU * 42 * 4;
+    static constexpr uint32_t OFF_RED = OFF_HACT + ((HACT_BYTES + 1023) / 1024) * 1024;
+    static_assert(TILES * C == 256 && (TILES == 2 || TILES == 4), "an accumulator set is 256 columns");
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+    static_assert(HEAD_PIECE_BYTES <= PIECE_BYTES, "head pieces use the same ring");
+    static_assert(OFF_RED + 8 * POS * 8 * 4 <= 8 * LBO_A, "FC scratch must stay inside K groups 2..7");
+};
+using Cfg128 = Cfg<128, 2, 2, 19>;  // 9 blocks; 36 KB pieces
+using Cfg64 = Cfg<64, 4, 4, 23>;    // 11 blocks; 18 KB pieces
 
 __device__ __forceinline__ bool decode_row(int r, int &pos, int &y, int &x) {
     const int tile = r >> 7;
@@ -79,14 +92,17 @@ __device__ __forceinline__ bool decode_row(int r, int &pos, int &y, int &x) {
     return rr >= 0 && p < TPOS && y < c4::H && x < c4::W;
 }
 
-template <bool F16>
+template <typename K, bool F16>
 __global__ void __launch_bounds__(THREADS, 1)
-k_resnet128(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1, const uint8_t *__restrict__ leaf_player,
+k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1, const uint8_t *__restrict__ leaf_player,
             const uint8_t *__restrict__ leaf_status, const int32_t *__restrict__ eval_list, const int32_t *__restrict__ eval_count,
             long long n_slots, const uint8_t *__restrict__ weights, const float *__restrict__ biases, int num_blocks,
             const uint8_t *__restrict__ head_w, const float *__restrict__ head_b, const float *__restrict__ fc_policy_w,
             const float *__restrict__ fc_policy_b, const float *__restrict__ fc_value_w, const float *__restrict__ fc_value_b,
             float *__restrict__ logits, float *__restrict__ values) {
+    constexpr int C = K::C, TILES = K::TILES, NS = K::NS, KS = K::KS, POS = K::POS, ROWS = K::ROWS, RPT = K::RPT, NBARS = K::NBARS;
+    constexpr uint32_t LBO_A = K::LBO_A, BUF_BYTES = K::BUF_BYTES, TAP_BYTES = K::TAP_BYTES, PIECE_BYTES = K::PIECE_BYTES;
+    constexpr uint32_t OFF_RING = K::OFF_RING, OFF_BIAS = K::OFF_BIAS, OFF_BARS = K::OFF_BARS, OFF_HACT = K::OFF_HACT, OFF_RED = K::OFF_RED;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *bufX = smem, *bufT = smem + BUF_BYTES;
     float *s_bias = reinterpret_cast<float *>(smem + OFF_BIAS);
@@ -120,19 +136,22 @@ k_resnet128(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ 
     for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
         const long long pos0 = batch * POS;
         const uint32_t gl0 = it * (uint32_t)n_layers, ge0 = it * (uint32_t)n_conv;
-        // this thread's stem row: the leaf record is requested now and consumed after the batch barrier
-        uint64_t in_b0 = 0, in_b1 = 0;
-        uint32_t in_meta = 0;  // bit 0: row of a position that exists, bit 1: side to move, bit 2: row is a board cell, bits 8..: bit index
-        if (tid < ROWS) {
+        // this thread's stem rows: the leaf records are requested now and consumed after the batch barrier
+        constexpr int SROWS = (ROWS + WTHREADS - 1) / WTHREADS;
+        uint64_t in_b0[SROWS], in_b1[SROWS];
+        uint32_t in_meta[SROWS];  // bit 0: row of a position that exists, bit 1: side to move, bit 2: row is a board cell, bits 8..: bit index
+#pragma unroll
+        for (int k = 0; k < SROWS; ++k) {
+            const int r = (int)tid + k * WTHREADS;
             int pos, y, x;
-            const bool cell = decode_row((int)tid, pos, y, x);
+            const bool cell = tid < WTHREADS && r < ROWS && decode_row(r, pos, y, x);
             const long long gp = pos0 + pos;
             const bool in = cell && gp < n;
             const long long slot = in ? (eval_list ? (long long)__ldg(eval_list + gp) : gp) : 0;
             const bool live = in && leaf_status[slot] == AZ_LEAF_EVAL;
-            in_b0 = leaf_bb0[slot];
-            in_b1 = leaf_bb1[slot];
-            in_meta = (live ? 1u : 0u) | ((uint32_t)(leaf_player[slot] & 1) << 1) | (cell ? 4u : 0u) | ((uint32_t)(x * c4::STRIDE + y) << 8);
+            in_b0[k] = leaf_bb0[slot];
+            in_b1[k] = leaf_bb1[slot];
+            in_meta[k] = (live ? 1u : 0u) | ((uint32_t)(leaf_player[slot] & 1) << 1) | (cell ? 4u : 0u) | ((uint32_t)(x * c4::STRIDE + y) << 8);
         }
         if (warp != 9) {
             batch_sync();  // the previous batch is finished: buffers and tensor memory are this batch's
@@ -145,13 +164,16 @@ k_resnet128(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ 
                 }
             // stem input in t, K group 0: channels 0..2 = empty / side to move / opponent (cnn.py:93-95).  K group 1 keeps stale
             // finite activations, which the stem's zero weights for channels 8..15 cancel.
-            if (in_meta & 4u) {
-                const int pl = (in_meta >> 1) & 1, bit = (int)(in_meta >> 8);
-                const uint32_t live = in_meta & 1u;
-                const uint32_t s0 = (uint32_t)((in_b0 >> bit) & 1ull), s1 = (uint32_t)((in_b1 >> bit) & 1ull);
+#pragma unroll
+            for (int k = 0; k < SROWS; ++k) {
+                if (!(in_meta[k] & 4u)) continue;
+                const int r = (int)tid + k * WTHREADS;
+                const int pl = (in_meta[k] >> 1) & 1, bit = (int)(in_meta[k] >> 8);
+                const uint32_t live = in_meta[k] & 1u;
+                const uint32_t s0 = (uint32_t)((in_b0[k] >> bit) & 1ull), s1 = (uint32_t)((in_b1[k] >> bit) & 1ull);
                 const uint32_t mine = live * (pl ? s1 : s0), theirs = live * (pl ? s0 : s1), emp = live * (1u - (s0 | s1));
                 const uint32_t one = F16 ? 0x3C00u : 0x3F80u;
-                *reinterpret_cast<uint4 *>(bufT + (GUARD + tid) * ROWB) = make_uint4(emp * one | (mine * one) << 16, theirs * one, 0u, 0u);
+                *reinterpret_cast<uint4 *>(bufT + (GUARD + r) * ROWB) = make_uint4(emp * one | (mine * one) << 16, theirs * one, 0u, 0u);
             }
             fence_async_smem();
             fence_before();
@@ -209,13 +231,21 @@ k_resnet128(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ 
                 __syncwarp();
             }
         } else {
-            // ===== epilogue warps: thread = (tile, row) =====
-            const int tile = (int)(warp >> 2);
-            const int r = tile * 128 + (int)((warp & 3u) * 32u + lane);
-            int pos, y, x;
-            const bool valid = decode_row(r, pos, y, x);
-            const uint32_t lane_addr = tmem_base + (((warp & 3u) * 32u) << 16) + (uint32_t)tile * C;
-            const uint32_t row_off = (GUARD + r) * ROWB;
+            // ===== epilogue warps: thread = one row of the tiles w/4, w/4 + 2, ... (RPT rows) =====
+            const int tile0 = (int)(warp >> 2);
+            const int row_in_tile = (int)((warp & 3u) * 32u + lane);
+            int pos[RPT], yy[RPT], xx[RPT];
+            bool valid[RPT];
+            uint32_t row_off[RPT];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                const int r = (tile0 + 2 * j) * 128 + row_in_tile;
+                valid[j] = decode_row(r, pos[j], yy[j], xx[j]);
+                row_off[j] = (GUARD + r) * ROWB;
+            }
+            const uint32_t lane_addr = tmem_base + (((warp & 3u) * 32u) << 16);
+            constexpr int NQ = KS * RPT;  // (chunk, row) pairs of a layer, chunk-major
+            static_assert(NQ % 2 == 0, "the double-buffered loop handles pairs");
             for (int l = 0; l < n_conv; ++l) {
                 uint8_t *dst = (l & 1) ? bufT : bufX;          // stem and conv2 write x, conv1 writes t
                 const bool skip = l > 0 && !(l & 1);            // conv2: + x, in place
@@ -224,13 +254,15 @@ k_resnet128(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ 
                 mbar_wait(mma_done, (gl0 + (uint32_t)l) & 1u);
                 fence_after();
                 uint32_t va[16], vb[16];
-                auto chunk = [&](const uint32_t (&v)[16], int c) {
+                auto load = [&](int q, uint32_t (&v)[16]) { tmem_ld16_issue(acc + (uint32_t)((tile0 + 2 * (q % RPT)) * C + (q / RPT) * 16), v); };
+                auto chunk = [&](const uint32_t (&v)[16], int q) {
+                    const int c = q / RPT, j = q % RPT;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        uint8_t *p = dst + (2 * c + h) * LBO_A + row_off;
+                        uint8_t *p = dst + (2 * c + h) * LBO_A + row_off[j];
                         float f[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[h * 8 + j]) + bias[c * 16 + h * 8 + j];
+                        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[h * 8 + i]) + bias[c * 16 + h * 8 + i];
                         if (skip) {
                             const uint4 s = *reinterpret_cast<const uint4 *>(p);
                             const float2 s0 = unpack16<F16>(s.x), s1 = unpack16<F16>(s.y), s2 = unpack16<F16>(s.z), s3 = unpack16<F16>(s.w);
@@ -238,27 +270,29 @@ k_resnet128(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ 
                             f[4] += s2.x; f[5] += s2.y; f[6] += s3.x; f[7] += s3.y;
                         }
                         uint4 o = make_uint4(0, 0, 0, 0);
-                        if (valid)
+                        if (valid[j])
                             o = make_uint4(pack16<F16>(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f)), pack16<F16>(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f)),
                                            pack16<F16>(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f)), pack16<F16>(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f)));
                         *reinterpret_cast<uint4 *>(p) = o;
                     }
-                    // this warp's rows of channels 16 c .. 16 c + 15 are in place for the tensor core (and its reads of the
-                    // accumulator columns are complete): one arrival per warp
-                    fence_before();
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(chunk0 + c * 8);
+                    if (j == RPT - 1) {
+                        // this warp's rows of channels 16 c .. 16 c + 15 are in place for the tensor core (and its reads of those
+                        // accumulator columns are complete): one arrival per warp
+                        fence_before();
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(chunk0 + c * 8);
+                    }
                 };
-                tmem_ld16_issue(acc, va);
-#pragma unroll 1
-                for (int c = 0; c < KS; c += 2) {
+                load(0, va);
+#pragma unroll
+                for (int q = 0; q < NQ; q += 2) {
                     tmem_ld_wait();
-                    tmem_ld16_issue(acc + (c + 1) * 16, vb);
-                    chunk(va, c);
+                    load(q + 1, vb);
+                    chunk(va, q);
                     tmem_ld_wait();
-                    if (c + 2 < KS) tmem_ld16_issue(acc + (c + 2) * 16, va);
-                    chunk(vb, c + 1);
+                    if (q + 2 < NQ) load(q + 2, va);
+                    chunk(vb, q + 1);
                 }
             }
             // ---- heads: [POS][35][42] fp32 in the Flatten() order of NCHW, then both FC layers on CUDA cores
@@ -267,17 +301,20 @@ k_resnet128(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ 
             {
                 mbar_wait(mma_done, (gl0 + (uint32_t)n_conv) & 1u);
                 fence_after();
-                const uint32_t acc = lane_addr + (uint32_t)(n_conv & 1) * 256u;
-                uint32_t v[32], w[16];
-                tmem_ld32_issue(acc, v);
-                tmem_ld16_issue(acc + 32, w);
-                tmem_ld_wait();
-                if (valid) {
-                    float *o = hact + pos * NHU * 42 + y * c4::W + x;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) o[c * 42] = fmaxf(__uint_as_float(v[c]) + hb[c], 0.f);
+                for (int j = 0; j < RPT; ++j) {
+                    const uint32_t acc = lane_addr + (uint32_t)(n_conv & 1) * 256u + (uint32_t)((tile0 + 2 * j) * C);
+                    uint32_t v[32], w[16];
+                    tmem_ld32_issue(acc, v);
+                    tmem_ld16_issue(acc + 32, w);
+                    tmem_ld_wait();
+                    if (valid[j]) {
+                        float *o = hact + pos[j] * NHU * 42 + yy[j] * c4::W + xx[j];
 #pragma unroll
-                    for (int c = 32; c < NHU; ++c) o[c * 42] = fmaxf(__uint_as_float(w[c - 32]) + hb[c], 0.f);
+                        for (int c = 0; c < 32; ++c) o[c * 42] = fmaxf(__uint_as_float(v[c]) + hb[c], 0.f);
+#pragma unroll
+                        for (int c = 32; c < NHU; ++c) o[c * 42] = fmaxf(__uint_as_float(w[c - 32]) + hb[c], 0.f);
+                    }
                 }
             }
             fence_before();
@@ -309,24 +346,27 @@ k_resnet128(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ 
 #pragma unroll
                 for (int p = 0; p < POS; ++p) acc[p * 8 + 7] = fmaf(wv, hact[p * NHU * 42 + 32 * 42 + kk], acc[p * 8 + 7]);
             }
-            // warp reduction by recursive halving: lane L ends with the total of index L
+            // warp reduction by recursive halving: each step exchanges half of the values; with V = POS * 8 values lane L ends
+            // with the totals of the V / 32 indices L * V / 32 ...
+            constexpr int V = POS * 8, VL = V / 32;
 #pragma unroll
-            for (int h = POS * 4; h >= 1; h >>= 1) {
-                const bool up = (lane & (uint32_t)h) != 0;
+            for (int h = V / 2; h >= VL; h >>= 1) {
+                const bool up = (lane & (uint32_t)(h / VL)) != 0;
 #pragma unroll
                 for (int i = 0; i < h; ++i) {
                     const float send = up ? acc[i] : acc[i + h];
                     const float keep = up ? acc[i + h] : acc[i];
-                    acc[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, h);
+                    acc[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, h / VL);
                 }
             }
-            float *red = reinterpret_cast<float *>(bufT + OFF_RED);  // [8 warps][32]
-            red[warp * 32 + lane] = acc[0];
+            float *red = reinterpret_cast<float *>(bufT + OFF_RED);  // [8 warps][V]
+#pragma unroll
+            for (int i = 0; i < VL; ++i) red[warp * V + VL * lane + i] = acc[i];
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (tid < POS * 8) {
+            if (tid < V) {
                 float sum = 0.f;
 #pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) sum += red[w8 * 32 + tid];
+                for (int w8 = 0; w8 < 8; ++w8) sum += red[w8 * V + tid];
                 const int p = (int)tid >> 3, j = (int)tid & 7;
                 const long long gp = pos0 + p;
                 if (gp < n) {
@@ -349,15 +389,9 @@ k_resnet128(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ 
 
 }  // namespace
 
-extern "C" {
-
-/* bytes of packed trunk weights for `num_blocks` residual blocks of 128 channels: stem 1 piece + 8 pieces per convolution, 36 KB each */
-int64_t az_resnet128_weight_bytes(int32_t num_blocks) { return (int64_t)PIECE_BYTES + (int64_t)num_blocks * 2 * KS * PIECE_BYTES; }
-
-/* internal: called by az_resnet_forward_leaves_v2 (csrc/az_conv.cu) for num_channels == 128 */
-int32_t az_resnet128_launch(az_engine *engine, const az_resnet_desc *d, float *logits, float *values, void *stream) {
-    if (!engine || !d || !d->trunk_w || !d->trunk_b || d->num_blocks < 0 || 1 + 2 * d->num_blocks > MAX_CONV) return AZ_E_INVALID;
-    if (d->operand_format != AZ_FMT_BF16 && d->operand_format != AZ_FMT_F16) return AZ_E_INVALID;
+template <typename K>
+static int32_t launch_pipe(az_engine *engine, const az_resnet_desc *d, float *logits, float *values, void *stream) {
+    if (d->num_blocks < 0 || 1 + 2 * d->num_blocks > K::MAX_CONV) return AZ_E_INVALID;
     const uint64_t *bb0 = nullptr, *bb1 = nullptr;
     const uint8_t *status = nullptr, *player = nullptr;
     const int32_t *elist = nullptr, *ecount = nullptr;
@@ -369,18 +403,37 @@ int32_t az_resnet128_launch(az_engine *engine, const az_resnet_desc *d, float *l
     const int dev = az_device(engine);
     if (dev < 0 || dev >= 64 || cudaSetDevice(dev) != cudaSuccess) return AZ_E_CUDA;
     if (!attr_set[dev]) {
-        if (cudaFuncSetAttribute(k_resnet128<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
-        if (cudaFuncSetAttribute(k_resnet128<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
+        if (cudaFuncSetAttribute(k_resnet_pipe<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
+        if (cudaFuncSetAttribute(k_resnet_pipe<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
         attr_set[dev] = true;
     }
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return AZ_E_CUDA;
-    const int batches = (n + POS - 1) / POS;
-    auto kern = d->operand_format == AZ_FMT_F16 ? k_resnet128<true> : k_resnet128<false>;
-    kern<<<batches < sms ? batches : sms, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
+    const int batches = (n + K::POS - 1) / K::POS;
+    auto kern = d->operand_format == AZ_FMT_F16 ? k_resnet_pipe<K, true> : k_resnet_pipe<K, false>;
+    kern<<<batches < sms ? batches : sms, THREADS, K::SMEM_BYTES, (cudaStream_t)stream>>>(
         bb0, bb1, player, status, elist, ecount, (long long)n, (const uint8_t *)d->trunk_w, d->trunk_b, d->num_blocks, (const uint8_t *)d->head_conv_w,
         d->head_conv_b, d->fc_policy_w, d->fc_policy_b, d->fc_value_w, d->fc_value_b, logits, values);
     return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;
+}
+
+extern "C" {
+
+/* bytes of packed trunk weights for `num_blocks` residual blocks of 64 / 128 channels (models.py:pack_trunk_weights_pipe):
+ * one piece [9 taps][C out][16 in] for the stem, C / 16 pieces per block convolution */
+int64_t az_resnet_pipe_weight_bytes(int32_t num_blocks, int32_t num_channels) {
+    if (num_channels == 128) return (int64_t)Cfg128::PIECE_BYTES * (1 + (int64_t)num_blocks * 2 * Cfg128::KS);
+    if (num_channels == 64) return (int64_t)Cfg64::PIECE_BYTES * (1 + (int64_t)num_blocks * 2 * Cfg64::KS);
+    return -1;
+}
+
+/* internal: called by az_resnet_forward_leaves_v2 (csrc/az_conv.cu) */
+int32_t az_resnet_pipe_launch(az_engine *engine, const az_resnet_desc *d, float *logits, float *values, void *stream) {
+    if (!engine || !d || !d->trunk_w || !d->trunk_b) return AZ_E_INVALID;
+    if (d->operand_format != AZ_FMT_BF16 && d->operand_format != AZ_FMT_F16) return AZ_E_INVALID;
+    if (d->num_channels == 128) return launch_pipe<Cfg128>(engine, d, logits, values, stream);
+    if (d->num_channels == 64) return launch_pipe<Cfg64>(engine, d, logits, values, stream);
+    return AZ_E_INVALID;
 }
 
 }  // extern "C"

@@ -359,10 +359,12 @@ def pack_trunk_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloa
     return torch.cat(parts).contiguous(), torch.stack(biases).contiguous().float()
 
 
-def pack_trunk_weights128(model: "ResNet", device, dtype: torch.dtype = torch.bfloat16) -> tuple[Tensor, Tensor]:
-    """The same convolutions for the 128-channel kernel (csrc/az_conv128.cu): per layer the pieces [128 out][16 in] in the order
-    the kernel consumes them, K-chunk-major: for ks (16 input channels) for tap (3*ky + kx); the stem has one K chunk (3 -> 16)."""
-    assert model.num_channels == 128
+def pack_trunk_weights_pipe(model: "ResNet", device, dtype: torch.dtype = torch.bfloat16) -> tuple[Tensor, Tensor]:
+    """The same convolutions for the layer-pipelined kernel (csrc/az_resnet_pipe.cu): per layer the pieces [9 taps][C out][16 in]
+    in the order the kernel consumes them, K-chunk-major: for ks (16 input channels) for tap (3*ky + kx); the stem has one
+    K chunk (3 -> 16)."""
+    C = model.num_channels
+    assert C in (64, 128)
     m = copy.deepcopy(model).eval().float().to(device)
     convs = [_fold_bn(m.input_conv[0], m.input_conv[1])]
     for blk in m.residual_blocks:
@@ -371,7 +373,7 @@ def pack_trunk_weights128(model: "ResNet", device, dtype: torch.dtype = torch.bf
     parts, biases = [], []
     for li, (w, b) in enumerate(convs):
         if li == 0:
-            w = torch.cat([w, torch.zeros(128, 13, 3, 3, device=w.device)], dim=1)
+            w = torch.cat([w, torch.zeros(C, 13, 3, 3, device=w.device)], dim=1)
         for ks in range(w.shape[1] // 16):
             for ky in range(3):
                 for kx in range(3):
@@ -380,7 +382,7 @@ def pack_trunk_weights128(model: "ResNet", device, dtype: torch.dtype = torch.bf
     return torch.cat(parts).contiguous(), torch.stack(biases).contiguous().float()
 
 
-def pack_head_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloat16):
+def pack_head_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloat16, pipe: bool = True):
     """Policy conv1x1 (-> 32) and value conv3x3 (-> 3), BatchNorm folded, as ONE 48-output 3x3 conv for csrc/az_conv.cu
     (the 1x1 weights occupy the centre tap), plus the two fully connected layers in fp32."""
     m = copy.deepcopy(model).eval().float().to(device)
@@ -391,8 +393,9 @@ def pack_head_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloat
     w[32:35] = wv
     b = torch.zeros(48, device=device)
     b[:32], b[32:35] = bp, bv
-    if model.num_channels == 128:  # pieces [48][16] in (ks, tap) order, like the trunk's
-        conv = torch.cat([_canonical_kmajor(w[:, 16 * ks:16 * ks + 16, ky, kx], dtype) for ks in range(8) for ky in range(3) for kx in range(3)]).contiguous()
+    if pipe:  # pieces [48][16] in (ks, tap) order, like the trunk's
+        conv = torch.cat([_canonical_kmajor(w[:, 16 * ks:16 * ks + 16, ky, kx], dtype) for ks in range(model.num_channels // 16)
+                          for ky in range(3) for kx in range(3)]).contiguous()
     else:
         conv = torch.cat([_canonical_kmajor(w[:, :, ky, kx], dtype) for ky in range(3) for kx in range(3)]).contiguous()
     f = lambda t: t.detach().float().contiguous()
@@ -402,20 +405,24 @@ def pack_head_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloat
 class TensorCoreTrunk:
     """A ResNet (64 or 128 channels) as one tcgen05 kernel on the engine's leaves (csrc/az_conv.cu, csrc/az_conv128.cu)."""
 
-    def __init__(self, model: "ResNet", device: torch.device, dtype: torch.dtype = torch.bfloat16):
+    def __init__(self, model: "ResNet", device: torch.device, dtype: torch.dtype = torch.bfloat16, variant: int = 0):
+        """variant 0: the layer-pipelined kernel (64 or 128 channels); 1: the ping-pong kernel of csrc/az_conv.cu (64 channels)."""
         from . import _lib
 
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.dtype = dtype
+        self.variant = variant
         self.num_blocks = model.num_res_blocks
         self.num_channels = model.num_channels
-        self._pack = pack_trunk_weights128 if self.num_channels == 128 else pack_trunk_weights
+        assert variant == 0 or self.num_channels == 64
+        self._pack = pack_trunk_weights_pipe if variant == 0 else pack_trunk_weights
         self.weights, self.biases = self._pack(model, self.device, dtype)
-        assert self.weights.numel() * 2 == (self.lib.az_resnet128_weight_bytes if self.num_channels == 128 else self.lib.az_trunk_weight_bytes)(self.num_blocks)
-        self.heads = pack_head_weights(model, self.device, dtype)
+        expect = self.lib.az_resnet_pipe_weight_bytes(self.num_blocks, self.num_channels) if variant == 0 else self.lib.az_trunk_weight_bytes(self.num_blocks)
+        assert self.weights.numel() * 2 == expect
+        self.heads = pack_head_weights(model, self.device, dtype, pipe=variant == 0)
         hw, hb, fpw, fpb, fvw, fvb = self.heads
-        self.desc = _lib.AzResnetDesc(self.num_blocks, model.num_channels, _operand_format(dtype), 0, self.weights.data_ptr(),
+        self.desc = _lib.AzResnetDesc(self.num_blocks, model.num_channels, _operand_format(dtype), variant, self.weights.data_ptr(),
                                       self.biases.data_ptr(), hw.data_ptr(), hb.data_ptr(), fpw.data_ptr(), fpb.data_ptr(),
                                       fvw.data_ptr(), fvb.data_ptr())
         self._out: dict[int, Tensor] = {}
@@ -429,7 +436,7 @@ class TensorCoreTrunk:
         w, b = self._pack(model, self.device, self.dtype)
         self.weights.copy_(w)
         self.biases.copy_(b)
-        for dst, src in zip(self.heads, pack_head_weights(model, self.device, self.dtype)):
+        for dst, src in zip(self.heads, pack_head_weights(model, self.device, self.dtype, pipe=self.variant == 0)):
             dst.copy_(src)
         return True
 
@@ -450,7 +457,7 @@ class TensorCoreTrunk:
 
     def forward_leaves(self, engine) -> Tensor:
         """-> trunk activations [n, 64, 6, 7] bf16 (channels-last memory) for the leaves of `engine.select_leaves()`."""
-        assert self.dtype == torch.bfloat16 and self.num_channels == 64, "the trunk-only entry point is bf16, 64 channels (az_trunk_forward_leaves)"
+        assert self.dtype == torch.bfloat16 and self.variant == 1, "the trunk-only entry point belongs to the ping-pong kernel (bf16, 64 channels)"
         n = engine.n_active
         if n not in self._out:
             self._out[n] = torch.empty((n, 6, 7, 64), dtype=torch.bfloat16, device=self.device)
@@ -470,7 +477,7 @@ class InferenceNet(nn.Module):
     `az_expand_backup`.  BasicNN stays fp32 (config 1 parity is quoted in fp32)."""
 
     def __init__(self, model: Model, dtype: torch.dtype = torch.bfloat16, device: torch.device | str = "cuda",
-                 use_tensor_core_kernels: bool = True):
+                 use_tensor_core_kernels: bool = True, trunk_variant: int = 0):
         super().__init__()
         self.trunk = None
         m = copy.deepcopy(model).eval().to(device)
@@ -489,7 +496,8 @@ class InferenceNet(nn.Module):
             self.input_layout = LAYOUT_PLANES_BF16 if dtype == torch.bfloat16 else LAYOUT_PLANES_F32
             self.trunk = None
             if isinstance(m, ResNet) and m.num_channels in (64, 128) and m.num_res_blocks <= (9 if m.num_channels == 128 else 11) and dtype in (torch.bfloat16, torch.float16) and use_tensor_core_kernels:
-                self.trunk = TensorCoreTrunk(m, torch.device(device), dtype)  # hand-written tcgen05 kernel: trunk + heads (csrc/az_conv.cu)
+                # hand-written tcgen05 kernel, trunk + heads: csrc/az_resnet_pipe.cu (variant 0) or csrc/az_conv.cu (variant 1, 64 channels)
+                self.trunk = TensorCoreTrunk(m, torch.device(device), dtype, variant=trunk_variant if m.num_channels == 64 else 0)
             self.net = self._fold(m).to(dtype).to(memory_format=torch.channels_last)
         else:
             self.input_layout = getattr(model, "input_layout", LAYOUT_PLANES_F32)
@@ -565,7 +573,7 @@ class InferenceNet(nn.Module):
         if self.fused is not None:
             return "k_mlp_fused"
         if self.trunk is not None:
-            return "k_resnet128" if self.trunk.num_channels == 128 else "k_resnet_trunk"
+            return "k_resnet_pipe" if self.trunk.variant == 0 else "k_resnet_trunk"
         return "k_encode + cuDNN/cuBLAS (torch)"
 
     @torch.no_grad()

@@ -158,7 +158,7 @@ class _GraphedStep:
 class AlphaZeroSearch:
     def __init__(self, *, model, num_simulations: int, exploration_weight: float = 1.0, device: int | None = None,
                  lanes_per_tree: int = 0, inference_dtype: torch.dtype | None = None, use_cuda_graph: bool = True,
-                 use_tensor_core_kernels: bool = True):
+                 use_tensor_core_kernels: bool = True, trunk_variant: int = 0):
         self.inference_model = model.get_inference_clone()
         self.num_simulations = int(num_simulations)
         self.exploration_weight = exploration_weight
@@ -167,6 +167,7 @@ class AlphaZeroSearch:
         self.inference_dtype = inference_dtype
         self.use_cuda_graph = use_cuda_graph
         self.use_tensor_core_kernels = use_tensor_core_kernels
+        self.trunk_variant = trunk_variant
         self._engine: Engine | None = None
         self._net = None
         self._mode = None
@@ -197,7 +198,8 @@ class AlphaZeroSearch:
                 pass  # in place: graph kept
             else:
                 self._graphed = None
-                self._mode, self._net = "net", InferenceNet(m, dtype=dtype, device=dev, use_tensor_core_kernels=self.use_tensor_core_kernels)
+                self._mode, self._net = "net", InferenceNet(m, dtype=dtype, device=dev, use_tensor_core_kernels=self.use_tensor_core_kernels,
+                                                              trunk_variant=self.trunk_variant)
             torch.cuda.current_stream(dev).synchronize()
         else:
             self._mode, self._net, self._graphed = "predict", None, None

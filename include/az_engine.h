@@ -267,18 +267,19 @@ int32_t az_resnet_forward_leaves(az_engine *engine, const void *packed_weights, 
                                  float *values, void *stream);
 typedef struct az_resnet_desc {
     int32_t num_blocks;      /* residual blocks (resnet.py:51-53) */
-    int32_t num_channels;    /* trunk width: 64 (csrc/az_conv.cu) or 128, the reference's own instance (csrc/az_conv128.cu) */
+    int32_t num_channels;    /* trunk width: 64, or 128 = the reference's own instance */
     int32_t operand_format;  /* AZ_FMT_*: format of trunk_w / head_conv_w and of the activations between layers */
-    int32_t reserved;
-    const void *trunk_w;     /* packed 16-bit MMA operands (models.py:pack_trunk_weights) */
+    int32_t variant;         /* 0: layer-pipelined kernel (csrc/az_resnet_pipe.cu; weights: models.py:pack_trunk_weights_pipe);
+                                1: ping-pong kernel, 64 channels only (csrc/az_conv.cu; weights: models.py:pack_trunk_weights) */
+    const void *trunk_w;     /* packed 16-bit MMA operands */
     const float *trunk_b;    /* [1 + 2*num_blocks][num_channels] */
-    const void *head_conv_w; /* 9 taps x [48][num_channels] */
+    const void *head_conv_w; /* [48 out] x num_channels x 9 taps, packed like trunk_w (models.py:pack_head_weights) */
     const float *head_conv_b;
     const float *fc_policy_w, *fc_policy_b, *fc_value_w, *fc_value_b; /* fp32, nn.Linear layout */
 } az_resnet_desc;
 int32_t az_resnet_forward_leaves_v2(az_engine *engine, const az_resnet_desc *desc, float *logits, float *values, void *stream);
-/* bytes of packed trunk weights the 128-channel kernel expects (models.py:pack_trunk_weights128) */
-int64_t az_resnet128_weight_bytes(int32_t num_blocks);
+/* bytes of packed trunk weights the layer-pipelined kernel expects (models.py:pack_trunk_weights_pipe); -1 for an unsupported width */
+int64_t az_resnet_pipe_weight_bytes(int32_t num_blocks, int32_t num_channels);
 /* Tuning switch of the kernel behind the calls above: 0 (default) = one CTA per 8 positions, 1 = CTA pairs
  * (tcgen05 cta_group::2, M = 256).  Same results; returns the previous setting. */
 int32_t az_trunk_set_cta_pair(int32_t on);

@@ -1,5 +1,6 @@
-"""GPU: the hand-written tcgen05 kernel for the reference's own ResNet(board, 7, B, 128) (csrc/az_conv128.cu; architecture:
-src/alphazero_simple/resnet.py:30-103, instantiated 9 x 128 in src/alphazero_less_simple/main.py:13) against plain PyTorch:
+"""GPU: the layer-pipelined tcgen05 ResNet kernel (csrc/az_resnet_pipe.cu) - 128 channels, the reference's own
+ResNet(board, 7, 9, 128) (src/alphazero_simple/resnet.py:30-103, src/alphazero_less_simple/main.py:13), and 64 channels, the
+headline net - against plain PyTorch:
 (a) the same arithmetic emulated in PyTorch (BatchNorm folded, 16-bit-rounded weights and inter-layer activations, fp32
 accumulation) within accumulation-order noise, (b) the fp32 module within north_star's 1e-3 on priors / values in fp16 mode."""
 import numpy as np
@@ -31,13 +32,15 @@ def _emulated(model, x, dtype):
     return model.policy_head[4](pa.flatten(1)), torch.tanh(model.value_head[4](va.flatten(1)))
 
 
-@pytest.mark.parametrize("blocks,n,dtype", [(0, 4, torch.bfloat16), (1, 3, torch.bfloat16), (1, 64, torch.float16), (2, 1000, torch.bfloat16),
-                                            (9, 700, torch.float16), (3, 2501, torch.bfloat16)])
-def test_resnet128_kernel_matches_pytorch(blocks, n, dtype):
+@pytest.mark.parametrize("channels,blocks,n,dtype", [
+    (128, 0, 4, torch.bfloat16), (128, 1, 3, torch.bfloat16), (128, 1, 64, torch.float16), (128, 2, 1000, torch.bfloat16),
+    (128, 9, 700, torch.float16), (128, 3, 2501, torch.bfloat16),
+    (64, 0, 8, torch.bfloat16), (64, 1, 5, torch.float16), (64, 4, 64, torch.float16), (64, 4, 3001, torch.bfloat16), (64, 11, 1190, torch.float16)])
+def test_resnet_pipe_kernel_matches_pytorch(channels, blocks, n, dtype):
     torch.manual_seed(13 * blocks + n)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    model = az.ResNet(num_res_blocks=blocks, num_channels=128).cuda().eval()
+    model = az.ResNet(num_res_blocks=blocks, num_channels=channels).cuda().eval()
     _randomise_bn(model)
     compact = n != 64  # one case computes every slot's row, the others walk the compacted leaf list
     eng = _engine_with_leaves(n, seed=n + 2, compact=compact)
@@ -45,7 +48,7 @@ def test_resnet128_kernel_matches_pytorch(blocks, n, dtype):
     assert live.any()
     x = eng.gather_leaves(LAYOUT_PLANES_F32)
     net = InferenceNet(model, dtype=dtype)
-    assert net.kernel_name == "k_resnet128"
+    assert net.kernel_name == "k_resnet_pipe"
     logits, values = net.forward_leaves(eng)
     torch.cuda.synchronize()
     with torch.no_grad():
@@ -73,7 +76,7 @@ def test_resnet128_in_the_search_loop_and_weight_refresh():
     torch.manual_seed(3)
     model = az.ResNet(num_res_blocks=9, num_channels=128)
     search = az.AlphaZeroSearch(model=model, num_simulations=40, inference_dtype=torch.bfloat16)
-    assert search.evaluator_name == "k_resnet128"
+    assert search.evaluator_name == "k_resnet_pipe"
     nodes = [az.Node(az.Config().sample_initial_state()) for _ in range(6)]
     search.run_simulations(nodes)
     a = [[ch.visit_count for ch in nd.children.values()] for nd in nodes]

@@ -59,7 +59,7 @@ def test_trunk_matches_pytorch_reference(blocks, n):
     eng = _engine_with_leaves(n, seed=n)
     status = eng.leaf_info()["status"]
     x = eng.gather_leaves(LAYOUT_PLANES_F32)
-    trunk = TensorCoreTrunk(model, torch.device("cuda", torch.cuda.current_device()))
+    trunk = TensorCoreTrunk(model, torch.device("cuda", torch.cuda.current_device()), variant=1)
     got = trunk.forward_leaves(eng).float()
     torch.cuda.synchronize()
     with torch.no_grad():
@@ -95,8 +95,9 @@ def test_resnet_in_the_search_loop_matches_library_path():
         assert max(abs(x - y) for x, y in zip(a, b)) <= 10
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("blocks,n", [(0, 8), (2, 77), (4, 1000), (2, 4999)])
-def test_full_net_kernel_matches_pytorch_reference(blocks, n):
+def test_full_net_kernel_matches_pytorch_reference(blocks, n, variant):
     """Trunk + fused heads (policy conv1x1 + FC, value conv3x3 + FC + tanh) vs the fp32 PyTorch module evaluated on the
     bf16-emulated trunk: logits / values within bf16 noise, and vs the plain fp32 module within the bf16 budget."""
     torch.manual_seed(7 * blocks + n)
@@ -107,7 +108,7 @@ def test_full_net_kernel_matches_pytorch_reference(blocks, n):
     eng = _engine_with_leaves(n, seed=n + 1, compact=n % 2 == 1)  # both ways of walking the batch
     live = eng.leaf_info()["status"] == 0
     x = eng.gather_leaves(LAYOUT_PLANES_F32)
-    trunk = TensorCoreTrunk(model, torch.device("cuda", torch.cuda.current_device()))
+    trunk = TensorCoreTrunk(model, torch.device("cuda", torch.cuda.current_device()), variant=variant)  # both 64-channel kernels
     logits, values = trunk.forward_leaves_full(eng)
     torch.cuda.synchronize()
     r = lambda t: t.to(torch.bfloat16).to(torch.float32)
@@ -142,8 +143,8 @@ def test_cta_pair_variant_is_bit_identical(blocks, n):
     model = az.ResNet(num_res_blocks=blocks, num_channels=64).cuda().eval()
     _randomise_bn(model)
     eng = _engine_with_leaves(n, seed=n)
-    net = InferenceNet(model, dtype=torch.bfloat16)
-    assert net.evaluates_leaves_directly
+    net = InferenceNet(model, dtype=torch.bfloat16, trunk_variant=1)
+    assert net.evaluates_leaves_directly and net.kernel_name == "k_resnet_trunk"
     outs = []
     try:
         for pair in (0, 1):
