@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("AZ_ENGINE_LIB") or os.path.join(PKG_DIR, "libaz_engine.so")  # override: A/B builds of the library
-SOURCES = ["az_engine.cu", "az_mlp.cu", "az_conv.cu", "az_resnet_pipe.cu"]
+SOURCES = ["az_engine.cu", "az_mlp.cu", "az_conv.cu", "az_resnet_pipe.cu", "az_cnn.cu"]
 HEADERS = ["az_eval.cuh", "c4_bitboard.cuh", "tcgen05.cuh", os.path.join("..", "..", "include", "az_engine.h")]
 
 NVCC_FLAGS = [
@@ -92,6 +92,13 @@ class AzResnetDesc(C.Structure):
     ]
 
 
+class AzCnnDesc(C.Structure):
+    _fields_ = [
+        ("operand_format", C.c_int32), ("reserved", C.c_int32), ("conv_w", C.c_void_p), ("conv_b", C.c_void_p), ("fc_w", C.c_void_p),
+        ("fc_b", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
 FMT_BF16, FMT_F16 = 0, 1
 
 P = C.c_void_p  # device pointers and streams cross the boundary as plain addresses
@@ -148,6 +155,10 @@ SIGNATURES = {
     "az_resnet_forward_leaves": (I32, [P, P, P, I32, P, P, P, P, P, P, P, P, P]),
     "az_resnet_forward_leaves_v2": (I32, [P, C.POINTER(AzResnetDesc), P, P, P]),
     "az_trunk_set_cta_pair": (I32, [I32]),
+    "az_cnn_conv_weight_bytes": (I64, []),
+    "az_cnn_fc_weight_bytes": (I64, []),
+    "az_cnn_workspace_bytes": (I64, [I64]),
+    "az_cnn_forward_leaves": (I32, [P, C.POINTER(AzCnnDesc), P, P, P]),
     "az_leaf_arrays": (I32, [P, C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(I32)]),
 }
 

@@ -470,6 +470,87 @@ class TensorCoreTrunk:
         return out.permute(0, 3, 1, 2)  # NCHW view of NHWC memory == channels_last
 
 
+def pack_cnn_weights(model: "CNNModel", device, dtype: torch.dtype = torch.bfloat16):
+    """CNNModel's weights as operands of csrc/az_cnn.cu.  Convolutions (BatchNorm folded): pieces [9 taps][out][16 in] per K chunk -
+    conv1 one piece [9][64][16] (3 -> 16 input channels), conv2 four pieces [9][128][16], conv3 eight pieces for output channels
+    0..127 and eight for 128..255.  Linear 10752 -> 512: input index c * 42 + pixel (NCHW Flatten) reordered to pixel * 256 + c,
+    then per chunk of 32 inputs a tile [512][32] in the MMA's canonical order.  Heads: [8][512] fp32 (7 policy rows, 1 value row)."""
+    m = copy.deepcopy(model).eval().float().to(device)
+    convs = [_fold_bn(m.conv_layers[0], m.conv_layers[1]), _fold_bn(m.conv_layers[3], m.conv_layers[4]), _fold_bn(m.conv_layers[6], m.conv_layers[7])]
+    w0, w1, w2 = (w for w, _ in convs)
+    w0 = torch.cat([w0, torch.zeros(64, 13, 3, 3, device=w0.device)], dim=1)
+    parts = []
+
+    def pieces(w):
+        for ks in range(w.shape[1] // 16):
+            for ky in range(3):
+                for kx in range(3):
+                    parts.append(_canonical_kmajor(w[:, 16 * ks:16 * ks + 16, ky, kx], dtype))
+
+    pieces(w0)
+    pieces(w1)
+    pieces(w2[:128])
+    pieces(w2[128:])
+    conv_w = torch.cat(parts).contiguous()
+    conv_b = torch.cat([b for _, b in convs]).contiguous().float()
+    fc = m.shared_layers[0]
+    wf = fc.weight.detach().float().reshape(512, 256, 42).permute(0, 2, 1).reshape(512, 42 * 256)  # [out][pixel * 256 + c]
+    fc_w = torch.cat([_canonical_kmajor(wf[:, 32 * k:32 * k + 32], dtype) for k in range(42 * 256 // 32)]).contiguous()
+    head_w = torch.cat([m.policy_head.weight.detach().float(), m.value_head[0].weight.detach().float()]).contiguous()
+    head_b = torch.cat([m.policy_head.bias.detach().float(), m.value_head[0].bias.detach().float()]).contiguous()
+    return conv_w, conv_b, fc_w, fc.bias.detach().float().contiguous(), head_w, head_b
+
+
+class TensorCoreCNN:
+    """CNNModel.forward as two tcgen05 kernels on the engine's leaves (csrc/az_cnn.cu)."""
+
+    num_channels = 0
+    variant = 0
+
+    def __init__(self, model: "CNNModel", device: torch.device, dtype: torch.dtype = torch.bfloat16):
+        from . import _lib
+
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.w = list(pack_cnn_weights(model, self.device, dtype))
+        assert self.w[0].numel() * 2 == self.lib.az_cnn_conv_weight_bytes() and self.w[2].numel() * 2 == self.lib.az_cnn_fc_weight_bytes()
+        self.workspace = None
+        self._lv: dict[int, tuple[Tensor, Tensor]] = {}
+        self.desc = None
+        self.launches = 0
+
+    def set_weights(self, model: "CNNModel") -> bool:
+        for dst, src in zip(self.w, pack_cnn_weights(model, self.device, self.dtype)):
+            dst.copy_(src)
+        return True
+
+    def _descriptor(self, n: int):
+        from . import _lib
+
+        need = int(self.lib.az_cnn_workspace_bytes(n))
+        if self.workspace is None or self.workspace.numel() < need:
+            self.workspace = torch.zeros(need, dtype=torch.uint8, device=self.device)  # conv3 activations of the evaluated leaves (21.5 KB each)
+            cw, cb, fw, fb, hw, hb = self.w
+            self.desc = _lib.AzCnnDesc(_operand_format(self.dtype), 0, cw.data_ptr(), cb.data_ptr(), fw.data_ptr(), fb.data_ptr(), hw.data_ptr(),
+                                       hb.data_ptr(), self.workspace.data_ptr(), self.workspace.numel())
+        return self.desc
+
+    def forward_leaves_full(self, engine) -> tuple[Tensor, Tensor]:
+        import ctypes as C
+
+        n = engine.n_active
+        if n not in self._lv:
+            self._lv[n] = (torch.zeros((n, 7), device=self.device), torch.zeros((n, 2), device=self.device))
+        logits, values = self._lv[n]
+        rc = self.lib.az_cnn_forward_leaves(engine.h, C.byref(self._descriptor(n)), logits.data_ptr(), values.data_ptr(),
+                                            torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"az_cnn_forward_leaves failed ({rc})")
+        self.launches += 2
+        return logits, values
+
+
 class InferenceNet(nn.Module):
     """Search-time form of a `Model` (the role of `get_inference_clone()`, models/base/model.py:92-96):
     eval-mode, BatchNorm folded, conv/linear weights in `dtype` (bf16 on the hot path), activations
@@ -477,7 +558,7 @@ class InferenceNet(nn.Module):
     `az_expand_backup`.  BasicNN stays fp32 (config 1 parity is quoted in fp32)."""
 
     def __init__(self, model: Model, dtype: torch.dtype = torch.bfloat16, device: torch.device | str = "cuda",
-                 use_tensor_core_kernels: bool = True, trunk_variant: int = 0):
+                 use_tensor_core_kernels: bool = True, trunk_variant: int | None = None):
         super().__init__()
         self.trunk = None
         m = copy.deepcopy(model).eval().to(device)
@@ -495,9 +576,14 @@ class InferenceNet(nn.Module):
         elif isinstance(m, (CNNModel, ResNet)):
             self.input_layout = LAYOUT_PLANES_BF16 if dtype == torch.bfloat16 else LAYOUT_PLANES_F32
             self.trunk = None
+            if isinstance(m, CNNModel) and dtype in (torch.bfloat16, torch.float16) and use_tensor_core_kernels:
+                self.trunk = TensorCoreCNN(m, torch.device(device), dtype)  # hand-written tcgen05 kernels (csrc/az_cnn.cu)
             if isinstance(m, ResNet) and m.num_channels in (64, 128) and m.num_res_blocks <= (9 if m.num_channels == 128 else 11) and dtype in (torch.bfloat16, torch.float16) and use_tensor_core_kernels:
                 # hand-written tcgen05 kernel, trunk + heads: csrc/az_resnet_pipe.cu (variant 0) or csrc/az_conv.cu (variant 1, 64 channels)
-                self.trunk = TensorCoreTrunk(m, torch.device(device), dtype, variant=trunk_variant if m.num_channels == 64 else 0)
+                # measured at 16384 x 800 (profiles/r02_*): 64 channels 0.595 ms ping-pong vs 0.623 ms layer-pipelined (its layers are too
+                # short for the hand-over bubble at each layer start); 128 channels only fit the layer-pipelined schedule
+                variant = 0 if m.num_channels == 128 else (1 if trunk_variant is None else trunk_variant)
+                self.trunk = TensorCoreTrunk(m, torch.device(device), dtype, variant=variant)
             self.net = self._fold(m).to(dtype).to(memory_format=torch.channels_last)
         else:
             self.input_layout = getattr(model, "input_layout", LAYOUT_PLANES_F32)
@@ -573,6 +659,8 @@ class InferenceNet(nn.Module):
         if self.fused is not None:
             return "k_mlp_fused"
         if self.trunk is not None:
+            if isinstance(self.trunk, TensorCoreCNN):
+                return "k_cnn_conv + k_cnn_fc"
             return "k_resnet_pipe" if self.trunk.variant == 0 else "k_resnet_trunk"
         return "k_encode + cuDNN/cuBLAS (torch)"
 

@@ -158,7 +158,7 @@ class _GraphedStep:
 class AlphaZeroSearch:
     def __init__(self, *, model, num_simulations: int, exploration_weight: float = 1.0, device: int | None = None,
                  lanes_per_tree: int = 0, inference_dtype: torch.dtype | None = None, use_cuda_graph: bool = True,
-                 use_tensor_core_kernels: bool = True, trunk_variant: int = 0):
+                 use_tensor_core_kernels: bool = True, trunk_variant: int | None = None):
         self.inference_model = model.get_inference_clone()
         self.num_simulations = int(num_simulations)
         self.exploration_weight = exploration_weight

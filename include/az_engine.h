@@ -280,6 +280,27 @@ typedef struct az_resnet_desc {
 int32_t az_resnet_forward_leaves_v2(az_engine *engine, const az_resnet_desc *desc, float *logits, float *values, void *stream);
 /* bytes of packed trunk weights the layer-pipelined kernel expects (models.py:pack_trunk_weights_pipe); -1 for an unsupported width */
 int64_t az_resnet_pipe_weight_bytes(int32_t num_blocks, int32_t num_channels);
+/* ---- CNNModel (models/games/connect4/cnn.py:8-75) on the tensor cores: csrc/az_cnn.cu ----
+ * conv3x3 3 -> 64 -> 128 -> 256 (BatchNorm folded, ReLU) in one kernel, Linear 10752 -> 512 + ReLU and both heads in a second;
+ * logits [E][7], values [E][2] = [v, -v] (cnn.py:73) for the leaves of the last selection.  Weights are packed by
+ * alphazero-implementation_b200/models.py:pack_cnn_weights; `workspace` holds the conv output between the kernels. */
+typedef struct az_cnn_desc {
+    int32_t operand_format;  /* AZ_FMT_* */
+    int32_t reserved;
+    const void *conv_w;      /* az_cnn_conv_weight_bytes() bytes */
+    const float *conv_b;     /* [64 + 128 + 256] */
+    const void *fc_w;        /* az_cnn_fc_weight_bytes() bytes: [336 K chunks][512][32], k = pixel * 256 + channel */
+    const float *fc_b;       /* [512] */
+    const float *head_w;     /* [8][512] fp32: policy_head.weight rows 0..6, value_head[0].weight row 7 */
+    const float *head_b;     /* [8] */
+    void *workspace;         /* >= az_cnn_workspace_bytes(num_games) bytes */
+    int64_t workspace_bytes;
+} az_cnn_desc;
+int64_t az_cnn_conv_weight_bytes(void);
+int64_t az_cnn_fc_weight_bytes(void);
+int64_t az_cnn_workspace_bytes(int64_t n);
+int32_t az_cnn_forward_leaves(az_engine *engine, const az_cnn_desc *desc, float *logits, float *values, void *stream);
+
 /* Tuning switch of the kernel behind the calls above: 0 (default) = one CTA per 8 positions, 1 = CTA pairs
  * (tcgen05 cta_group::2, M = 256).  Same results; returns the previous setting. */
 int32_t az_trunk_set_cta_pair(int32_t on);

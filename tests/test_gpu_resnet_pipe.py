@@ -47,7 +47,7 @@ def test_resnet_pipe_kernel_matches_pytorch(channels, blocks, n, dtype):
     live = eng.leaf_info()["status"] == 0
     assert live.any()
     x = eng.gather_leaves(LAYOUT_PLANES_F32)
-    net = InferenceNet(model, dtype=dtype)
+    net = InferenceNet(model, dtype=dtype, trunk_variant=0)
     assert net.kernel_name == "k_resnet_pipe"
     logits, values = net.forward_leaves(eng)
     torch.cuda.synchronize()
