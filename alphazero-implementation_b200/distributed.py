@@ -63,46 +63,25 @@ def broadcast_weights(model: torch.nn.Module, src: int = 0, group=None) -> int:
     return nbytes
 
 
-def all_gather_episodes(local: dict, group=None, slot_offset: int | None = None) -> dict:
-    """Merge every rank's drained episodes (dict of tensors as returned by `Engine.drain_episodes_device`)
-    into one dict present on all ranks.  Two collectives: an all-gather of the (episodes, samples, slot offset)
-    triples, then ONE all-gather of a byte buffer into which every field is packed (padded to the largest rank).
-    Episode slots are made global by adding the owning rank's slot offset; sample offsets are rebased.
-    Merge order: rank, then the rank's own order."""
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return local
-    world = dist.get_world_size(group)
-    dev = local["ep_len"].device
-    counts = torch.tensor([local["ep_len"].numel(), local["s_bb0"].numel(), slot_offset or 0], dtype=torch.int64, device=dev)
-    all_counts = torch.empty(world * 3, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(all_counts, counts, group=group)
-    all_counts = all_counts.view(world, 3).cpu()
-    ne, ns, offs = (all_counts[:, i].tolist() for i in range(3))
-    max_e, max_s = max(ne + [1]), max(ns + [1])
-    # layout of one rank's packed buffer: every field padded to the largest rank, regions 16-byte aligned
-    layout, total = [], 0
-    for fields, mx in ((_EP_FIELDS, max_e), (_S_FIELDS, max_s)):
+_ROW_BYTES = {"ep_slot": 4, "ep_step": 4, "ep_len": 4, "ep_offset": 8, "ep_outcome": 2, "s_bb0": 8, "s_bb1": 8, "s_player": 1, "s_counts": 28}
+_HEADER = 32  # int64 [episodes, samples, slot offset, 0]
+
+
+def _slab_layout(cap_e: int, cap_s: int):
+    """Fixed layout of one rank's slab for given capacities: 32-byte header, then every field, regions 16-byte aligned."""
+    layout, total = {}, _HEADER
+    for fields, cap in ((_EP_FIELDS, cap_e), (_S_FIELDS, cap_s)):
         for f in fields:
-            x = local[f]
-            row = x.element_size() * math.prod(x.shape[1:])
-            layout.append((f, total, mx, row, x.dtype, tuple(x.shape[1:])))
-            total += (mx * row + 15) // 16 * 16
-    buf = torch.zeros(total, dtype=torch.uint8, device=dev)
-    for f, off, mx, row, dtype, tail in layout:
-        x = local[f].contiguous()
-        if x.shape[0]:
-            buf[off:off + x.shape[0] * row] = x.view(-1).view(torch.uint8)
-    gathered = torch.empty(world * total, dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(gathered, buf, group=group)
-    gathered = gathered.view(world, total)
-    out = {}
-    for f, off, mx, row, dtype, tail in layout:
-        cnt = ne if f in _EP_FIELDS else ns
-        parts = [gathered[r, off:off + cnt[r] * row].view(dtype).view(cnt[r], *tail) for r in range(world)]
-        out[f] = torch.cat(parts)
-    # rebase sample offsets; make slots global
+            layout[f] = total
+            total += (cap * _ROW_BYTES[f] + 15) // 16 * 16
+    return layout, total
+
+
+def _merge(parts: dict, ne: list, ns: list, offs: list, slot_offset, dev) -> dict:
+    """Per-rank field tensors -> one dict: sample offsets rebased, slots made global.  Merge order: rank, then the rank's own order."""
+    out = {f: torch.cat(ps) for f, ps in parts.items()}
     s_base, e_pos = 0, 0
-    for r in range(world):
+    for r in range(len(ne)):
         sl = slice(e_pos, e_pos + ne[r])
         out["ep_offset"][sl] += s_base
         if slot_offset is not None:
@@ -111,3 +90,61 @@ def all_gather_episodes(local: dict, group=None, slot_offset: int | None = None)
         e_pos += ne[r]
     out["ep_rank"] = torch.cat([torch.full((c,), r, dtype=torch.int32, device=dev) for r, c in enumerate(ne)])
     return out
+
+
+def all_gather_episodes(local: dict, group=None, slot_offset: int | None = None, capacity: tuple[int, int] | None = None) -> dict:
+    """Merge every rank's drained episodes (dict of tensors as returned by `Engine.drain_episodes_device`) into one dict present
+    on all ranks (the analogue of `buffer.append(episode)` into the shared replay deque, datamodule.py:29-30,57).
+
+    `capacity = (episodes, samples)` - the same on every rank, known before the call (e.g. the shard's episode quota and a bound on
+    the samples) - selects the ONE-collective path: every rank packs its fields into a fixed-size slab whose 32-byte header carries
+    its true counts, one all-gather moves the slabs, and the host reads the headers once, after the collective.  Should a rank
+    exceed the capacity (seen by all ranks in the headers), or without `capacity`, the exact two-collective path runs: an all-gather
+    of the counts, then one all-gather of slabs padded to the largest rank.
+    Episode slots are made global by adding the owning rank's slot offset; sample offsets are rebased."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    dev = local["ep_len"].device
+    my_e, my_s = int(local["ep_len"].numel()), int(local["s_bb0"].numel())
+
+    def pack(cap_e: int, cap_s: int, header: bool):
+        layout, total = _slab_layout(cap_e, cap_s)
+        buf = torch.zeros(total, dtype=torch.uint8, device=dev)
+        if header:
+            buf[:_HEADER].view(torch.int64).copy_(torch.tensor([my_e, my_s, slot_offset or 0, 0], dtype=torch.int64))
+        for f, off in layout.items():
+            x = local[f].contiguous()
+            if x.shape[0]:
+                buf[off:off + x.shape[0] * _ROW_BYTES[f]] = x.view(-1).view(torch.uint8)
+        gathered = torch.empty(world * total, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered, buf, group=group)
+        return layout, gathered.view(world, total)
+
+    def unpack(layout, gathered, ne, ns):
+        parts = {}
+        for f, off in layout.items():
+            cnt, x = (ne if f in _EP_FIELDS else ns), local[f]
+            parts[f] = [gathered[r, off:off + cnt[r] * _ROW_BYTES[f]].view(x.dtype).view(cnt[r], *x.shape[1:]) for r in range(world)]
+        return parts
+
+    if capacity is not None:
+        cap_e, cap_s = int(capacity[0]), int(capacity[1])
+        fits = my_e <= cap_e and my_s <= cap_s
+        if not fits:  # send the header only; every rank will see the overflow and take the exact path
+            local_keep, local = local, {f: local[f][:0] for f in local}
+            my_payload = (my_e, my_s)
+        layout, gathered = pack(cap_e, cap_s, header=True)
+        if not fits:
+            local = local_keep
+        heads = gathered[:, :_HEADER].contiguous().view(torch.int64).view(world, 4).cpu()  # the one host read, after the collective
+        ne, ns, offs = (heads[:, i].tolist() for i in range(3))
+        if all(e <= cap_e for e in ne) and all(x <= cap_s for x in ns):
+            return _merge(unpack(layout, gathered, ne, ns), ne, ns, offs, slot_offset, dev)
+    counts = torch.tensor([my_e, my_s, slot_offset or 0], dtype=torch.int64, device=dev)
+    all_counts = torch.empty(world * 3, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_counts, counts, group=group)
+    all_counts = all_counts.view(world, 3).cpu()
+    ne, ns, offs = (all_counts[:, i].tolist() for i in range(3))
+    layout, gathered = pack(max(ne + [1]), max(ns + [1]), header=False)
+    return _merge(unpack(layout, gathered, ne, ns), ne, ns, offs, slot_offset, dev)

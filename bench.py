@@ -502,8 +502,11 @@ def run_b200(args):
         d = eng.drain_episodes_device()
         if i >= args.burn_in:
             warm.append(d)
+    # the all-gather's slab capacity, known to every rank before the call (one collective, counts in the slab header): games finish at
+    # ~E / 20 per step and leave ~1 sample per slot per step; a rank that exceeded it would be seen by all and the exact path taken
+    ag_cap = (E * K // 8 + 64, int(1.5 * E * K) + 64 * 42)
     if world > 1:
-        all_gather_episodes(concat_device(warm), slot_offset=lo)  # NCCL channel set-up and buffer sizing belong to the warm-up
+        all_gather_episodes(concat_device(warm), slot_offset=lo, capacity=ag_cap)  # NCCL channel set-up and buffer sizing belong to the warm-up
     barrier()
     st0 = eng.stats()
     sampler = ClockSampler(local)
@@ -521,7 +524,7 @@ def run_b200(args):
     ag0.record()
     merged = concat_device(drained)
     if world > 1:
-        merged = all_gather_episodes(merged, slot_offset=lo)  # configs[3]: every rank ends the region holding every finished episode
+        merged = all_gather_episodes(merged, slot_offset=lo, capacity=ag_cap)  # configs[3]: every rank ends the region holding every finished episode
     ev1.record()
     barrier()
     wall_s = time.perf_counter() - t_wall0

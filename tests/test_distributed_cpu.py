@@ -54,9 +54,10 @@ def _worker(rank, world, port, out):
             assert torch.equal(v, expect[k]), k
         # 2. episode all-gather with different counts per rank (rank 1 has none in the second round)
         lo, hi = shard_range(10, rank, world)
-        for rnd, n_ep in enumerate([(3, 5), (4, 0)]):
+        # exact two-collective path, one-collective path with a capacity that fits, and one that a rank overflows (falls back)
+        for rnd, (n_ep, cap) in enumerate([((3, 5), None), ((4, 0), None), ((3, 5), (8, 8 * 42)), ((4, 0), (4, 4 * 42)), ((3, 5), (4, 4 * 42))]):
             local = _fake_episodes(rank, n_ep[rank])
-            merged = all_gather_episodes(local, slot_offset=lo)
+            merged = all_gather_episodes(local, slot_offset=lo, capacity=cap)
             tot_e = sum(n_ep)
             assert merged["ep_len"].numel() == tot_e
             mine = slice(0, n_ep[0]) if rank == 0 else slice(n_ep[0], tot_e)
