@@ -464,11 +464,14 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        # NCCL's communicator lines go to stderr (stdout carries exactly one JSON line); they show the rank count per communicator
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+    # stdout carries exactly one JSON line: everything a library prints there (NCCL's version and communicator lines at the
+    # NCCL_DEBUG level the launcher chose, cuDNN notices) is sent to stderr by pointing fd 1 at fd 2; the JSON line goes to the saved fd
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1 and "NCCL_DEBUG" not in os.environ:
+        os.environ["NCCL_DEBUG"] = "INFO"  # communicator lines (rank count per communicator) on stderr
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -544,6 +547,18 @@ def run_b200(args):
         tot_sims, tot_evals = float(st["simulations"]), float(st["evaluations"])
     value = tot_sims / total_ms * 1e3
     launches = K * search.launches_per_move_step()
+    ag_iso_ms = None
+    if world > 1:  # the same collective once more from a common start: inside the region its time is mostly the ranks' skew
+        local_again = concat_device(drained)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        all_gather_episodes(local_again, slot_offset=lo, capacity=ag_cap)
+        b1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ag_iso_ms = float(t.item())
 
     # roofline of the dominant kernel on this rank: CUDA events around each evaluator launch of one more (un-graphed) move step
     k_ms = kernel_timing_step(search, eng, u_all[n_pre + K])
@@ -646,9 +661,10 @@ def run_b200(args):
             "wall_s_timed_region": wall_s, "work_per_step": {k: v / K for k, v in st.items()},
         }
         if world > 1:
-            line["episode_allgather"] = {"ms": ag_ms, "inside_timed_region": True, "episodes": n_eps_job, "samples": int(merged["s_bb0"].numel())}
+            line["episode_allgather"] = {"ms_in_region_incl_rank_skew": ag_ms, "ms_isolated": ag_iso_ms, "inside_timed_region": True, "collectives": 1,
+                                         "episodes": n_eps_job, "samples": int(merged["s_bb0"].numel()), "slab_capacity": list(ag_cap)}
         line.update(extras)
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
