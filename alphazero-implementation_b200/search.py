@@ -192,7 +192,10 @@ class AlphaZeroSearch:
         if getattr(m, "az_builtin_eval_kind", 0) in (EVAL_UNIFORM, EVAL_HASH):
             self._mode, self._net, self._graphed = "builtin", None, None
         elif isinstance(m, Model):
-            dtype = self.inference_dtype or (torch.float32 if isinstance(m, BasicNN) else torch.bfloat16)
+            # Defaults: BasicNN in fp32 (the reference's arithmetic: BASELINE config 1 reproduces the reference's episodes); the conv
+            # nets on the hand-written tensor-core kernels with fp16 operands, which stay within 1e-3 of the fp32 `predict`
+            # (tests/test_gpu_config3.py) at the speed of bf16.  bf16 (BASELINE config 3's format) and fp32 are one argument away.
+            dtype = self.inference_dtype or (torch.float32 if isinstance(m, BasicNN) else torch.float16)
             dev = torch.device("cuda", torch.cuda.current_device() if self.device_index is None else self.device_index)
             if self._net is not None and self._mode == "net" and self._net.refresh(m):
                 pass  # in place: graph kept
@@ -289,6 +292,24 @@ class AlphaZeroSearch:
     def run_simulations(self, current_nodes: list[Node], materialize: str = "root") -> None:
         if not current_nodes:
             return
+        # A terminal node WITH a parent is a leaf the reference visits num_simulations times (search.py:75-77): the reward of the
+        # player who moved into it is backed up along the parent chain (no sign flip at the terminal node itself, :55-56).
+        # Host arithmetic, exact (rewards are -1 / 0 / +1).  A terminal node without a parent raises below, as in the reference.
+        done = [nd for nd in current_nodes if nd.parent is not None and nd.state.has_ended]
+        for nd in done:
+            for _ in range(self.num_simulations):
+                v = float(nd.state.reward[nd.parent.state.player])
+                walk = nd
+                while walk is not None:
+                    walk.value_sum += v
+                    walk.visit_count += 1
+                    if not walk.is_terminal:
+                        v = -v
+                    walk = walk.parent
+        if done:
+            current_nodes = [nd for nd in current_nodes if not (nd.parent is not None and nd.state.has_ended)]
+            if not current_nodes:
+                return
         for nd in current_nodes:
             if nd.children or nd.visit_count:
                 raise ValueError("run_simulations expects fresh roots (the reference always passes Node(state)); "

@@ -337,3 +337,19 @@ def test_leaf_gather_into_pinned_host_batch_and_host_evaluator():
     assert torch.equal(px, engs[1].gather_leaves(LAYOUT_PLANES_F32).cpu())
     for e in engs:
         e.close()
+
+
+def test_terminal_node_with_a_parent_is_visited_like_the_reference():
+    """`run_simulations` on a node whose state has ended and that HAS a parent: the reference backs up the reward of the player
+    who moved into it num_simulations times along the parent chain, without a sign flip at the terminal node (search.py:75-77,
+    :48-57); a terminal node without a parent raises AttributeError."""
+    st = az.State(az.Config(), (1 << 0) | (1 << 7) | (1 << 14), (1 << 1) | (1 << 8) | (1 << 15), 0)  # player 0 wins at column 3
+    parent = az.Node(st)
+    win = az.Node(az.Action(st, 3).sample_next_state(), parent=parent, prior=0.5)
+    assert win.is_terminal and win.utility_values == [1.0, -1.0]
+    fresh = az.Node(az.Config().sample_initial_state())
+    search = az.AlphaZeroSearch(model=az.UniformEvaluator(), num_simulations=10)
+    search.run_simulations([win, fresh])
+    assert (win.visit_count, win.value_sum) == (10, 10.0)        # + reward[parent.player] per simulation
+    assert (parent.visit_count, parent.value_sum) == (10, 10.0)  # no flip at the terminal node: the parent receives +v too
+    assert fresh.visit_count == 10 and sum(c.visit_count for c in fresh.children.values()) == 9
