@@ -47,19 +47,22 @@ constexpr uint32_t LBO_W = 128, SBO_W = 256;     // canonical K-major [N][16]
 constexpr int NHC = 48, NHU = 35;      // head conv channels: 32 policy (1x1, centre tap) + 3 value (3x3) + padding
 constexpr uint32_t HEAD_TAP_BYTES = NHC * 16 * 2;    // 1536
 constexpr uint32_t HEAD_PIECE_BYTES = 9 * HEAD_TAP_BYTES;
-constexpr int THREADS = 320, WTHREADS = 288;
 static_assert(LEAD + TPOS * PIX <= 128, "a tile's positions must fit its 128 rows");
 
-// C channels, TILES accumulator tiles per CTA (TILES * C = 256 tensor-memory columns per accumulator set), NS ring stages
-template <int C_, int TILES_, int NS_, int MAX_CONV_>
+// C channels, TILES accumulator tiles per CTA (TILES * C tensor-memory columns per accumulator set), NS ring stages, EW epilogue
+// warps (warp EW issues the MMAs, warp EW + 1 streams the weights), CTAS resident CTAs per SM
+template <int C_, int TILES_, int NS_, int MAX_CONV_, int EW_ = 8, int CTAS_ = 1>
 struct Cfg {
-    static constexpr int C = C_, TILES = TILES_, NS = NS_, MAX_CONV = MAX_CONV_;
+    static constexpr int C = C_, TILES = TILES_, NS = NS_, MAX_CONV = MAX_CONV_, EW = EW_, CTAS = CTAS_;
+    static constexpr int THREADS = (EW + 2) * 32, WTHREADS = (EW + 1) * 32, ETHREADS = EW * 32;
+    static constexpr int TSTEP = EW / 4;          // an epilogue thread owns one row of the tiles w / 4, w / 4 + TSTEP, ...
+    static constexpr int SETCOLS = TILES * C;     // tensor-memory columns of one accumulator set
     static constexpr int KG = C / 8;              // K groups of 8 channels (16 bytes per row)
     static constexpr int KS = C / 16;             // K steps per tap = pieces per layer = chunks of an epilogue
     static constexpr int POS = TPOS * TILES;      // positions per CTA
     static constexpr int ROWS = TILES * 128;
     static constexpr int RTOT = ROWS + 2 * GUARD; // rows per K group
-    static constexpr int RPT = TILES / 2;         // rows per epilogue thread (tiles w/4, w/4 + 2, ...)
+    static constexpr int RPT = TILES / TSTEP;     // rows per epilogue thread
     static constexpr uint32_t LBO_A = RTOT * ROWB;          // next K group
     static constexpr uint32_t BUF_BYTES = KG * LBO_A;
     static constexpr uint32_t TAP_BYTES = C * 16 * 2;       // one tap of a K chunk, [C out][16 in]
@@ -73,13 +76,18 @@ struct Cfg {
     static constexpr uint32_t OFF_HACT = 2 * LBO_A;
     static constexpr uint32_t HACT_BYTES = POS * NHU * 42 * 4;
     static constexpr uint32_t OFF_RED = OFF_HACT + ((HACT_BYTES + 1023) / 1024) * 1024;
-    static_assert(TILES * C == 256 && (TILES == 2 || TILES == 4), "an accumulator set is 256 columns");
-    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+    static_assert(SETCOLS == 128 || SETCOLS == 256, "two accumulator sets: 256 or 512 tensor-memory columns");
+    static_assert((EW == 4 || EW == 8) && TILES % TSTEP == 0, "epilogue warps come in groups of four (one per 32 accumulator lanes)");
+    static_assert(CTAS * (SMEM_BYTES + 1024) <= 233472 && SMEM_BYTES <= 232448, "shared memory budget");
     static_assert(HEAD_PIECE_BYTES <= PIECE_BYTES, "head pieces use the same ring");
-    static_assert(OFF_RED + 8 * POS * 8 * 4 <= 8 * LBO_A, "FC scratch must stay inside K groups 2..7");
+    static_assert(OFF_RED + EW * POS * 8 * 4 <= 8 * LBO_A, "FC scratch must stay inside K groups 2..7");
 };
-using Cfg128 = Cfg<128, 2, 2, 19>;  // 9 blocks; 36 KB pieces
-using Cfg64 = Cfg<64, 4, 4, 23>;    // 11 blocks; 18 KB pieces
+using Cfg128 = Cfg<128, 2, 2, 19>;       // 9 blocks; 36 KB pieces
+using Cfg64 = Cfg<64, 4, 4, 23>;         // 11 blocks; 18 KB pieces; 8 positions per CTA
+// 64 channels, TWO CTAs per SM of 4 positions each (4 epilogue warps, 6 warps in all): while one CTA is in an epilogue, a layer
+// hand-over, its FC tail or its prologue, the other one's MMAs keep the tensor core busy - the overlap the ping-pong kernel builds
+// by hand inside one CTA, here between two independent instruction streams.  5 blocks at most (bias table).
+using Cfg64x2 = Cfg<64, 2, 2, 11, 4, 2>;
 
 __device__ __forceinline__ bool decode_row(int r, int &pos, int &y, int &x) {
     const int tile = r >> 7;
@@ -93,7 +101,7 @@ __device__ __forceinline__ bool decode_row(int r, int &pos, int &y, int &x) {
 }
 
 template <typename K, bool F16>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(K::THREADS, K::CTAS)
 k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1, const uint8_t *__restrict__ leaf_player,
             const uint8_t *__restrict__ leaf_status, const int32_t *__restrict__ eval_list, const int32_t *__restrict__ eval_count,
             long long n_slots, const uint8_t *__restrict__ weights, const float *__restrict__ biases, int num_blocks,
@@ -101,6 +109,8 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
             const float *__restrict__ fc_policy_b, const float *__restrict__ fc_value_w, const float *__restrict__ fc_value_b,
             float *__restrict__ logits, float *__restrict__ values) {
     constexpr int C = K::C, TILES = K::TILES, NS = K::NS, KS = K::KS, POS = K::POS, ROWS = K::ROWS, RPT = K::RPT, NBARS = K::NBARS;
+    constexpr int EW = K::EW, THREADS = K::THREADS, WTHREADS = K::WTHREADS, ETHREADS = K::ETHREADS, TSTEP = K::TSTEP;
+    constexpr uint32_t SETCOLS = K::SETCOLS;
     constexpr uint32_t LBO_A = K::LBO_A, BUF_BYTES = K::BUF_BYTES, TAP_BYTES = K::TAP_BYTES, PIECE_BYTES = K::PIECE_BYTES;
     constexpr uint32_t OFF_RING = K::OFF_RING, OFF_BIAS = K::OFF_BIAS, OFF_BARS = K::OFF_BARS, OFF_HACT = K::OFF_HACT, OFF_RED = K::OFF_RED;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -114,10 +124,10 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
     const int n_conv = 1 + 2 * num_blocks, n_layers = n_conv + 1;
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS), mma_done = smem_u32(bars + 2 * NS), chunk0 = smem_u32(bars + 2 * NS + 1);
     const uint32_t ring0 = smem_u32(smem + OFF_RING);
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512u);
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 2 * SETCOLS);
     if (tid == 32) {
         for (int i = 0; i < 2 * NS + 1; ++i) mbar_init(smem_u32(bars + i), 1u);
-        for (int i = 0; i < KS; ++i) mbar_init(chunk0 + i * 8, 8u);  // one arrival per epilogue warp
+        for (int i = 0; i < KS; ++i) mbar_init(chunk0 + i * 8, (uint32_t)EW);  // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t i = tid; i < 2 * BUF_BYTES / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -153,7 +163,7 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
             in_b1[k] = leaf_bb1[slot];
             in_meta[k] = (live ? 1u : 0u) | ((uint32_t)(leaf_player[slot] & 1) << 1) | (cell ? 4u : 0u) | ((uint32_t)(x * c4::STRIDE + y) << 8);
         }
-        if (warp != 9) {
+        if (warp != EW + 1) {
             batch_sync();  // the previous batch is finished: buffers and tensor memory are this batch's
             // the FC tail of the previous batch used K groups 2..7 of t as scratch, guard rows included: those must be zero again
             if (it > 0)
@@ -181,7 +191,7 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
             fence_after();
         }
 
-        if (warp == 9) {
+        if (warp == EW + 1) {
             // ===== weight producer: every piece of every layer, in the order the issuer consumes them =====
             for (int l = 0; l < n_layers; ++l) {
                 const bool head = l >= n_conv;
@@ -196,13 +206,13 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                     __syncwarp();
                 }
             }
-        } else if (warp == 8) {
+        } else if (warp == EW) {
             // ===== MMA issuer (converged; one elected lane issues) =====
             for (int l = 0; l < n_layers; ++l) {
                 const bool head = l >= n_conv;
                 const uint32_t src = l == 0 ? aT : ((head || (l & 1)) ? aX : aT);  // conv1 (odd l) and the heads read x; conv2 reads t
                 const uint32_t idesc = head ? instr_desc(128, NHC, F16) : instr_desc(128, C, F16);
-                const uint32_t acc = tmem_base + (uint32_t)(l & 1) * 256u;
+                const uint32_t acc = tmem_base + (uint32_t)(l & 1) * SETCOLS;
                 const uint64_t a_desc = smem_desc(src, LBO_A, SBO_A);
                 const int ksteps = l == 0 ? 1 : KS;
                 const uint32_t tap_units = (head ? HEAD_TAP_BYTES : TAP_BYTES) >> 4;
@@ -231,7 +241,7 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                 __syncwarp();
             }
         } else {
-            // ===== epilogue warps: thread = one row of the tiles w/4, w/4 + 2, ... (RPT rows) =====
+            // ===== epilogue warps: thread = one row of the tiles w/4, w/4 + TSTEP, ... (RPT rows) =====
             const int tile0 = (int)(warp >> 2);
             const int row_in_tile = (int)((warp & 3u) * 32u + lane);
             int pos[RPT], yy[RPT], xx[RPT];
@@ -239,7 +249,7 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
             uint32_t row_off[RPT];
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
-                const int r = (tile0 + 2 * j) * 128 + row_in_tile;
+                const int r = (tile0 + TSTEP * j) * 128 + row_in_tile;
                 valid[j] = decode_row(r, pos[j], yy[j], xx[j]);
                 row_off[j] = (GUARD + r) * ROWB;
             }
@@ -250,11 +260,11 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                 uint8_t *dst = (l & 1) ? bufT : bufX;          // stem and conv2 write x, conv1 writes t
                 const bool skip = l > 0 && !(l & 1);            // conv2: + x, in place
                 const float *bias = s_bias + l * C;
-                const uint32_t acc = lane_addr + (uint32_t)(l & 1) * 256u;
+                const uint32_t acc = lane_addr + (uint32_t)(l & 1) * SETCOLS;
                 mbar_wait(mma_done, (gl0 + (uint32_t)l) & 1u);
                 fence_after();
                 uint32_t va[16], vb[16];
-                auto load = [&](int q, uint32_t (&v)[16]) { tmem_ld16_issue(acc + (uint32_t)((tile0 + 2 * (q % RPT)) * C + (q / RPT) * 16), v); };
+                auto load = [&](int q, uint32_t (&v)[16]) { tmem_ld16_issue(acc + (uint32_t)((tile0 + TSTEP * (q % RPT)) * C + (q / RPT) * 16), v); };
                 auto chunk = [&](const uint32_t (&v)[16], int q) {
                     const int c = q / RPT, j = q % RPT;
 #pragma unroll
@@ -303,7 +313,7 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                 fence_after();
 #pragma unroll
                 for (int j = 0; j < RPT; ++j) {
-                    const uint32_t acc = lane_addr + (uint32_t)(n_conv & 1) * 256u + (uint32_t)((tile0 + 2 * j) * C);
+                    const uint32_t acc = lane_addr + (uint32_t)(n_conv & 1) * SETCOLS + (uint32_t)((tile0 + TSTEP * j) * C);
                     uint32_t v[32], w[16];
                     tmem_ld32_issue(acc, v);
                     tmem_ld16_issue(acc + 32, w);
@@ -318,14 +328,14 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                 }
             }
             fence_before();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            // thread t takes inputs k = t, t + 256, ...: every FC weight is read once per CTA (coalesced) and used for POS positions;
+            asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
+            // thread t takes inputs k = t, t + ETHREADS, ...: every FC weight is read once per CTA (coalesced) and used for POS positions;
             // acc[p][j], j = 7 is the value head
             float acc[POS * 8];
 #pragma unroll
             for (int i = 0; i < POS * 8; ++i) acc[i] = 0.f;
 #pragma unroll
-            for (int k0 = 0; k0 < 32 * 42; k0 += 256) {
+            for (int k0 = 0; k0 < 32 * 42; k0 += ETHREADS) {
                 const int k = k0 + (int)tid;
                 const bool in = k < 32 * 42;
                 const int kk = in ? k : 0;
@@ -359,14 +369,14 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                     acc[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, h / VL);
                 }
             }
-            float *red = reinterpret_cast<float *>(bufT + OFF_RED);  // [8 warps][V]
+            float *red = reinterpret_cast<float *>(bufT + OFF_RED);  // [EW warps][V]
 #pragma unroll
             for (int i = 0; i < VL; ++i) red[warp * V + VL * lane + i] = acc[i];
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
             if (tid < V) {
                 float sum = 0.f;
 #pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) sum += red[w8 * V + tid];
+                for (int w8 = 0; w8 < EW; ++w8) sum += red[w8 * V + tid];
                 const int p = (int)tid >> 3, j = (int)tid & 7;
                 const long long gp = pos0 + p;
                 if (gp < n) {
@@ -384,7 +394,7 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
     }  // batches
     fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 512u);
+    if (warp == 0) tmem_dealloc(tmem_base, 2 * SETCOLS);
 }
 
 }  // namespace
@@ -411,7 +421,8 @@ static int32_t launch_pipe(az_engine *engine, const az_resnet_desc *d, float *lo
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return AZ_E_CUDA;
     const int batches = (n + K::POS - 1) / K::POS;
     auto kern = d->operand_format == AZ_FMT_F16 ? k_resnet_pipe<K, true> : k_resnet_pipe<K, false>;
-    kern<<<batches < sms ? batches : sms, THREADS, K::SMEM_BYTES, (cudaStream_t)stream>>>(
+    const int resident = sms * K::CTAS;
+    kern<<<batches < resident ? batches : resident, K::THREADS, K::SMEM_BYTES, (cudaStream_t)stream>>>(
         bb0, bb1, player, status, elist, ecount, (long long)n, (const uint8_t *)d->trunk_w, d->trunk_b, d->num_blocks, (const uint8_t *)d->head_conv_w,
         d->head_conv_b, d->fc_policy_w, d->fc_policy_b, d->fc_value_w, d->fc_value_b, logits, values);
     return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;
@@ -432,6 +443,7 @@ int32_t az_resnet_pipe_launch(az_engine *engine, const az_resnet_desc *d, float 
     if (!engine || !d || !d->trunk_w || !d->trunk_b) return AZ_E_INVALID;
     if (d->operand_format != AZ_FMT_BF16 && d->operand_format != AZ_FMT_F16) return AZ_E_INVALID;
     if (d->num_channels == 128) return launch_pipe<Cfg128>(engine, d, logits, values, stream);
+    if (d->num_channels == 64 && d->variant == 2) return launch_pipe<Cfg64x2>(engine, d, logits, values, stream);
     if (d->num_channels == 64) return launch_pipe<Cfg64>(engine, d, logits, values, stream);
     return AZ_E_INVALID;
 }

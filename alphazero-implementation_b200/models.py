@@ -406,7 +406,8 @@ class TensorCoreTrunk:
     """A ResNet (64 or 128 channels) as one tcgen05 kernel on the engine's leaves (csrc/az_conv.cu, csrc/az_conv128.cu)."""
 
     def __init__(self, model: "ResNet", device: torch.device, dtype: torch.dtype = torch.bfloat16, variant: int = 0):
-        """variant 0: the layer-pipelined kernel (64 or 128 channels); 1: the ping-pong kernel of csrc/az_conv.cu (64 channels)."""
+        """variant 0: the layer-pipelined kernel (64 or 128 channels); 1: the ping-pong kernel of csrc/az_conv.cu (64 channels);
+        2: the layer-pipelined kernel with two 4-position CTAs per SM (64 channels, at most 5 blocks)."""
         from . import _lib
 
         self.lib = _lib.load()
@@ -416,11 +417,12 @@ class TensorCoreTrunk:
         self.num_blocks = model.num_res_blocks
         self.num_channels = model.num_channels
         assert variant == 0 or self.num_channels == 64
-        self._pack = pack_trunk_weights_pipe if variant == 0 else pack_trunk_weights
+        assert variant != 2 or self.num_blocks <= 5
+        self._pack = pack_trunk_weights_pipe if variant != 1 else pack_trunk_weights
         self.weights, self.biases = self._pack(model, self.device, dtype)
-        expect = self.lib.az_resnet_pipe_weight_bytes(self.num_blocks, self.num_channels) if variant == 0 else self.lib.az_trunk_weight_bytes(self.num_blocks)
+        expect = self.lib.az_resnet_pipe_weight_bytes(self.num_blocks, self.num_channels) if variant != 1 else self.lib.az_trunk_weight_bytes(self.num_blocks)
         assert self.weights.numel() * 2 == expect
-        self.heads = pack_head_weights(model, self.device, dtype, pipe=variant == 0)
+        self.heads = pack_head_weights(model, self.device, dtype, pipe=variant != 1)
         hw, hb, fpw, fpb, fvw, fvb = self.heads
         self.desc = _lib.AzResnetDesc(self.num_blocks, model.num_channels, _operand_format(dtype), variant, self.weights.data_ptr(),
                                       self.biases.data_ptr(), hw.data_ptr(), hb.data_ptr(), fpw.data_ptr(), fpb.data_ptr(),
@@ -436,7 +438,7 @@ class TensorCoreTrunk:
         w, b = self._pack(model, self.device, self.dtype)
         self.weights.copy_(w)
         self.biases.copy_(b)
-        for dst, src in zip(self.heads, pack_head_weights(model, self.device, self.dtype, pipe=self.variant == 0)):
+        for dst, src in zip(self.heads, pack_head_weights(model, self.device, self.dtype, pipe=self.variant != 1)):
             dst.copy_(src)
         return True
 
@@ -661,7 +663,7 @@ class InferenceNet(nn.Module):
         if self.trunk is not None:
             if isinstance(self.trunk, TensorCoreCNN):
                 return "k_cnn_conv + k_cnn_fc"
-            return "k_resnet_pipe" if self.trunk.variant == 0 else "k_resnet_trunk"
+            return "k_resnet_pipe" if self.trunk.variant != 1 else "k_resnet_trunk"
         return "k_encode + cuDNN/cuBLAS (torch)"
 
     @torch.no_grad()

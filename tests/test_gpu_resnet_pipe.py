@@ -35,8 +35,11 @@ def _emulated(model, x, dtype):
 @pytest.mark.parametrize("channels,blocks,n,dtype", [
     (128, 0, 4, torch.bfloat16), (128, 1, 3, torch.bfloat16), (128, 1, 64, torch.float16), (128, 2, 1000, torch.bfloat16),
     (128, 9, 700, torch.float16), (128, 3, 2501, torch.bfloat16),
-    (64, 0, 8, torch.bfloat16), (64, 1, 5, torch.float16), (64, 4, 64, torch.float16), (64, 4, 3001, torch.bfloat16), (64, 11, 1190, torch.float16)])
+    (64, 0, 8, torch.bfloat16), (64, 1, 5, torch.float16), (64, 4, 64, torch.float16), (64, 4, 3001, torch.bfloat16), (64, 11, 1190, torch.float16),
+    (-64, 0, 4, torch.bfloat16), (-64, 1, 7, torch.float16), (-64, 4, 64, torch.float16), (-64, 4, 3001, torch.bfloat16), (-64, 5, 2381, torch.float16)])
 def test_resnet_pipe_kernel_matches_pytorch(channels, blocks, n, dtype):
+    variant = 2 if channels < 0 else 0  # -64: the two-CTAs-per-SM instance
+    channels = abs(channels)
     torch.manual_seed(13 * blocks + n)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -47,7 +50,7 @@ def test_resnet_pipe_kernel_matches_pytorch(channels, blocks, n, dtype):
     live = eng.leaf_info()["status"] == 0
     assert live.any()
     x = eng.gather_leaves(LAYOUT_PLANES_F32)
-    net = InferenceNet(model, dtype=dtype, trunk_variant=0)
+    net = InferenceNet(model, dtype=dtype, trunk_variant=variant)
     assert net.kernel_name == "k_resnet_pipe"
     logits, values = net.forward_leaves(eng)
     torch.cuda.synchronize()
