@@ -582,9 +582,11 @@ class InferenceNet(nn.Module):
                 self.trunk = TensorCoreCNN(m, torch.device(device), dtype)  # hand-written tcgen05 kernels (csrc/az_cnn.cu)
             if isinstance(m, ResNet) and m.num_channels in (64, 128) and m.num_res_blocks <= (9 if m.num_channels == 128 else 11) and dtype in (torch.bfloat16, torch.float16) and use_tensor_core_kernels:
                 # hand-written tcgen05 kernel, trunk + heads: csrc/az_resnet_pipe.cu (variant 0) or csrc/az_conv.cu (variant 1, 64 channels)
-                # measured at 16384 x 800 (profiles/r02_*): 64 channels 0.595 ms ping-pong vs 0.623 ms layer-pipelined (its layers are too
-                # short for the hand-over bubble at each layer start); 128 channels only fit the layer-pipelined schedule
-                variant = 0 if m.num_channels == 128 else (1 if trunk_variant is None else trunk_variant)
+                # measured at 16384 x 800 (profiles/r02_*), 64 channels: layer-pipelined with two 4-position CTAs per SM 0.542 ms (up to
+                # 5 blocks), ping-pong 0.592 ms, layer-pipelined with one 8-position CTA 0.630 ms (the hand-over bubble at each layer
+                # start has nothing to hide behind); 128 channels only fit the layer-pipelined schedule
+                auto = 2 if m.num_res_blocks <= 5 else 1
+                variant = 0 if m.num_channels == 128 else (auto if trunk_variant is None else trunk_variant)
                 self.trunk = TensorCoreTrunk(m, torch.device(device), dtype, variant=variant)
             self.net = self._fold(m).to(dtype).to(memory_format=torch.channels_last)
         else:

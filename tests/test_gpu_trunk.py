@@ -85,7 +85,7 @@ def test_resnet_in_the_search_loop_matches_library_path():
     roots = [az.Config().sample_initial_state() for _ in range(4)]
     out = []
     for tc in (True, False):
-        s = az.AlphaZeroSearch(model=model, num_simulations=96, use_tensor_core_kernels=tc)
+        s = az.AlphaZeroSearch(model=model, num_simulations=96, use_tensor_core_kernels=tc, inference_dtype=torch.bfloat16)
         assert (s._net.trunk is not None) == tc
         nodes = [az.Node(r) for r in roots]
         s.run_simulations(nodes)
