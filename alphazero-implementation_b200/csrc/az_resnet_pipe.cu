@@ -29,6 +29,7 @@
 // Roles: warps 0..7 epilogue (thread = one pixel row of each pair of tiles), warp 8 issues MMAs (one elected lane), warp 9 streams weights.
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/az_engine.h"
 #include "c4_bitboard.cuh"
@@ -107,7 +108,7 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
             long long n_slots, const uint8_t *__restrict__ weights, const float *__restrict__ biases, int num_blocks,
             const uint8_t *__restrict__ head_w, const float *__restrict__ head_b, const float *__restrict__ fc_policy_w,
             const float *__restrict__ fc_policy_b, const float *__restrict__ fc_value_w, const float *__restrict__ fc_value_b,
-            float *__restrict__ logits, float *__restrict__ values) {
+            float *__restrict__ logits, float *__restrict__ values, uint32_t stagger_ns) {
     constexpr int C = K::C, TILES = K::TILES, NS = K::NS, KS = K::KS, POS = K::POS, ROWS = K::ROWS, RPT = K::RPT, NBARS = K::NBARS;
     constexpr int EW = K::EW, THREADS = K::THREADS, WTHREADS = K::WTHREADS, ETHREADS = K::ETHREADS, TSTEP = K::TSTEP;
     constexpr uint32_t SETCOLS = K::SETCOLS;
@@ -162,6 +163,12 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
             in_b0[k] = leaf_bb0[slot];
             in_b1[k] = leaf_bb1[slot];
             in_meta[k] = (live ? 1u : 0u) | ((uint32_t)(leaf_player[slot] & 1) << 1) | (cell ? 4u : 0u) | ((uint32_t)(x * c4::STRIDE + y) << 8);
+        }
+        if (K::CTAS == 2 && it == 0 && warp == EW && blockIdx.x >= gridDim.x / 2) {
+            // Two co-resident CTAs run identical batches; started together they stay in lock step and sit in their prologues
+            // and FC tails at the same time.  The second wave of CTAs (blockIdx >= gridDim / 2 fills the second slot of each SM)
+            // starts about half a batch late, so that one CTA's non-MMA phases fall into the other's MMA phases.
+            for (int d = 0; d < n_layers; ++d) __nanosleep(stagger_ns);
         }
         if (warp != EW + 1) {
             batch_sync();  // the previous batch is finished: buffers and tensor memory are this batch's
@@ -399,6 +406,16 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
 
 }  // namespace
 
+// start offset of the second wave of co-resident CTAs, per layer of the net (AZ_PIPE_STAGGER_NS overrides; 0 = none)
+static uint32_t stagger_ns() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("AZ_PIPE_STAGGER_NS");
+        v = e ? atoi(e) : 1100;
+    }
+    return (uint32_t)v;
+}
+
 template <typename K>
 static int32_t launch_pipe(az_engine *engine, const az_resnet_desc *d, float *logits, float *values, void *stream) {
     if (d->num_blocks < 0 || 1 + 2 * d->num_blocks > K::MAX_CONV) return AZ_E_INVALID;
@@ -424,7 +441,7 @@ static int32_t launch_pipe(az_engine *engine, const az_resnet_desc *d, float *lo
     const int resident = sms * K::CTAS;
     kern<<<batches < resident ? batches : resident, K::THREADS, K::SMEM_BYTES, (cudaStream_t)stream>>>(
         bb0, bb1, player, status, elist, ecount, (long long)n, (const uint8_t *)d->trunk_w, d->trunk_b, d->num_blocks, (const uint8_t *)d->head_conv_w,
-        d->head_conv_b, d->fc_policy_w, d->fc_policy_b, d->fc_value_w, d->fc_value_b, logits, values);
+        d->head_conv_b, d->fc_policy_w, d->fc_policy_b, d->fc_value_w, d->fc_value_b, logits, values, stagger_ns());
     return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;
 }
 
