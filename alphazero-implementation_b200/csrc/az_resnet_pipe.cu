@@ -164,10 +164,10 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
             in_b1[k] = leaf_bb1[slot];
             in_meta[k] = (live ? 1u : 0u) | ((uint32_t)(leaf_player[slot] & 1) << 1) | (cell ? 4u : 0u) | ((uint32_t)(x * c4::STRIDE + y) << 8);
         }
-        if (K::CTAS == 2 && it == 0 && warp == EW && blockIdx.x >= gridDim.x / 2) {
-            // Two co-resident CTAs run identical batches; started together they stay in lock step and sit in their prologues
-            // and FC tails at the same time.  The second wave of CTAs (blockIdx >= gridDim / 2 fills the second slot of each SM)
-            // starts about half a batch late, so that one CTA's non-MMA phases fall into the other's MMA phases.
+        if (K::CTAS == 2 && stagger_ns && it == 0 && warp == EW && blockIdx.x >= gridDim.x / 2) {
+            // Experiment kept as a switch (default off): two co-resident CTAs run identical batches, and a start offset for the
+            // second wave of CTAs (blockIdx >= gridDim / 2 fills the second slot of each SM) was meant to keep them out of lock
+            // step.  They drift apart on their own (contention for the tensor core); any offset only costs its own length.
             for (int d = 0; d < n_layers; ++d) __nanosleep(stagger_ns);
         }
         if (warp != EW + 1) {
@@ -411,7 +411,7 @@ static uint32_t stagger_ns() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("AZ_PIPE_STAGGER_NS");
-        v = e ? atoi(e) : 1100;
+        v = e ? atoi(e) : 0;  // measured (scripts/gpu/run9.sh): 0 / 600 / 1100 / 1600 / 2200 ns -> 0.536 / 0.543 / 0.550 / 0.548 / 0.563 ms per launch
     }
     return (uint32_t)v;
 }

@@ -198,7 +198,9 @@ class Trainer:
             local, selfplay_s = box["episodes"], box["selfplay_s"]
             t1 = time.perf_counter()
             if world > 1:
-                merged = all_gather_episodes(_to_device(local, self.device), slot_offset=lo)
+                # one collective: every rank contributes exactly its shard's quota of episodes, of at most 42 samples each
+                cap_e = max(h - l for l, h in shards)
+                merged = all_gather_episodes(_to_device(local, self.device), slot_offset=lo, capacity=(cap_e, 42 * cap_e))
                 replay.extend({k: merged[k] for k in ("ep_len", "ep_offset", "ep_outcome", "s_bb0", "s_bb1", "s_player", "s_counts")})
             else:
                 replay.extend(local)
