@@ -469,8 +469,8 @@ def run_b200(args):
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
-    if world > 1 and "NCCL_DEBUG" not in os.environ:
-        os.environ["NCCL_DEBUG"] = "INFO"  # communicator lines (rank count per communicator) on stderr
+    if world > 1 and os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "INFO"  # communicator lines (rank count per communicator) - on stderr, see above
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the engine has no CPU path (use --impl reference for the CPU arm)")
