@@ -9,7 +9,6 @@ Works on any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests)
 """
 from __future__ import annotations
 
-import math
 
 import torch
 import torch.distributed as dist

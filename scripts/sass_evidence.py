@@ -9,7 +9,6 @@ import collections
 import os
 import re
 import subprocess
-import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "alphazero-implementation_b200", "libaz_engine.so")

@@ -1,6 +1,5 @@
 """GPU: the search's consumers outside training: `AlphaZeroPlayer.play` with the reference's temperature rule
 (ui/cli/player.py:42-76), a game between two agents (src/elo.ipynb#cell3), the batched arena and the Elo ladder (#cell1, #cell4)."""
-import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu

@@ -3,7 +3,6 @@ ResNet(board, 7, 9, 128) (src/alphazero_simple/resnet.py:30-103, src/alphazero_l
 headline net - against plain PyTorch:
 (a) the same arithmetic emulated in PyTorch (BatchNorm folded, 16-bit-rounded weights and inter-layer activations, fp32
 accumulation) within accumulation-order noise, (b) the fp32 module within north_star's 1e-3 on priors / values in fp16 mode."""
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
