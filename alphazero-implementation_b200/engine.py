@@ -260,13 +260,27 @@ class Engine:
         self._check(self.lib.az_episode_counts(self.h, C.byref(ne), C.byref(ns), _stream()), "az_episode_counts")
         return ne.value, ns.value
 
-    def drain_episodes_device(self):
-        """Ring -> fresh device tensors (ring order, unsorted).  Used by the NCCL all-gather."""
+    def alloc_drain_buffers(self) -> dict:
+        """Device buffers that hold a full ring (2 E + 64 episodes of at most 42 samples): pass them to `drain_episodes_device`
+        to drain without allocating (the caching allocator's occasional cudaMalloc is a host-side stall of tens of ms)."""
+        ce = 2 * self.num_games + 64
+        cs = ce * 42
+        return dict(ep_slot=self.empty(ce, torch.int32), ep_step=self.empty(ce, torch.int32), ep_len=self.empty(ce, torch.int32),
+                    ep_offset=self.empty(ce, torch.int64), ep_outcome=self.empty((ce, 2), torch.int8),
+                    s_bb0=self.empty(cs, torch.int64), s_bb1=self.empty(cs, torch.int64), s_player=self.empty(cs, torch.uint8),
+                    s_counts=self.empty((cs, 7), torch.int32))
+
+    def drain_episodes_device(self, buffers: dict | None = None):
+        """Ring -> device tensors (ring order, unsorted): fresh ones, or views of `buffers` (`alloc_drain_buffers`).  Used by the
+        NCCL all-gather."""
         ne, ns = self.episode_counts()
-        d = dict(ep_slot=self.empty(ne, torch.int32), ep_step=self.empty(ne, torch.int32), ep_len=self.empty(ne, torch.int32),
-                 ep_offset=self.empty(ne, torch.int64), ep_outcome=self.empty((ne, 2), torch.int8),
-                 s_bb0=self.empty(ns, torch.int64), s_bb1=self.empty(ns, torch.int64), s_player=self.empty(ns, torch.uint8),
-                 s_counts=self.empty((ns, 7), torch.int32))
+        if buffers is not None:
+            d = {k: (v[:ne] if k.startswith("ep_") else v[:ns]) for k, v in buffers.items()}
+        else:
+            d = dict(ep_slot=self.empty(ne, torch.int32), ep_step=self.empty(ne, torch.int32), ep_len=self.empty(ne, torch.int32),
+                     ep_offset=self.empty(ne, torch.int64), ep_outcome=self.empty((ne, 2), torch.int8),
+                     s_bb0=self.empty(ns, torch.int64), s_bb1=self.empty(ns, torch.int64), s_player=self.empty(ns, torch.uint8),
+                     s_counts=self.empty((ns, 7), torch.int32))
         one, ons = C.c_int64(0), C.c_int64(0)
         self._check(self.lib.az_drain_episodes(self.h, ne, ns, _ptr(d["ep_slot"]), _ptr(d["ep_step"]), _ptr(d["ep_len"]),
                                                _ptr(d["ep_offset"]), _ptr(d["ep_outcome"]), _ptr(d["s_bb0"]), _ptr(d["s_bb1"]),

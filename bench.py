@@ -510,6 +510,7 @@ def run_b200(args):
     ag_cap = (E * K // 8 + 64, int(1.5 * E * K) + 64 * 42)
     if world > 1:
         all_gather_episodes(concat_device(warm), slot_offset=lo, capacity=ag_cap)  # NCCL channel set-up and buffer sizing belong to the warm-up
+    drain_bufs = [eng.alloc_drain_buffers() for _ in range((K + 15) // 16)]  # no allocation inside the timed region
     barrier()
     st0 = eng.stats()
     sampler = ClockSampler(local)
@@ -521,7 +522,7 @@ def run_b200(args):
     for i in range(K):
         search.simulate_and_move(eng, u_all[n_pre + i])  # 800 x (k_resnet_pipe, k_expand_select, k_compact_leaves) replayed from a CUDA graph + k_sample_moves
         if (i + 1) % 16 == 0 or i + 1 == K:  # device -> device; the ring holds 2 E + 64 episodes, ~E / 20 finish per step.  Draining
-            drained.append(eng.drain_episodes_device())  # (a host synchronisation) every step left the GPU queue empty at every
+            drained.append(eng.drain_episodes_device(drain_bufs[i // 16]))  # (a host synchronisation) every step left the GPU queue empty at every
         step_ev.append(torch.cuda.Event(enable_timing=True))  # step boundary: any host hiccup there showed up as a 10 % slower step
         step_ev[-1].record()
     ag0.record()
