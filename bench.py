@@ -626,6 +626,13 @@ def run_b200(args):
                "flops_per_position": flops, "leaf_eval_fraction": tot_evals / max(1.0, tot_sims),
                "us_per_simulation_step": total_ms * 1e3 / (K * S), "cuda_graph": bool(search.use_cuda_graph),
                "episodes_finished_in_timed_region": n_eps_job, "step_ms": [round(x, 2) for x in step_ms]}
+    dev_file = os.path.join(ROOT, "profiles", "r02_evaluator_deviation.json")  # written by tests/test_gpu_config3.py on 16384 positions
+    if os.path.exists(dev_file):
+        try:
+            dev = json.load(open(dev_file))
+            details["evaluator_max_abs_dev_vs_fp32_predict"] = {k: dev[k] for k in (f"{args.net}_{args.dtype}", f"{args.net}_fp16") if k in dev}
+        except Exception:
+            pass
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
