@@ -43,7 +43,7 @@ constexpr uint32_t OFF_B1 = BUF_IN, OFF_B2 = OFF_B1 + BUF_1, OFF_RING = OFF_B2 +
 constexpr uint32_t OFF_BIAS = OFF_RING + NS * PIECE;
 constexpr int NBIAS = 64 + 128 + 256;
 constexpr uint32_t OFF_BARS = OFF_BIAS + NBIAS * 4;
-constexpr int NBARS = 2 * NS + 1 + 8;                     // full[NS] empty[NS] mma_done chunk[8]
+constexpr int NBARS = 2 * NS + NL + 8 + 1;                // full[NS] empty[NS] mma_done[NL] chunk[8] drain0
 constexpr uint32_t CONV_SMEM = OFF_BARS + NBARS * 8 + 16;
 static_assert(CONV_SMEM <= 232448, "shared memory budget");
 constexpr int64_t CONV_W_BYTES = (int64_t)PIECE0 + 4 * PIECE + 16 * PIECE;
@@ -92,12 +92,16 @@ k_cnn_conv(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ l
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + NBARS * 8);
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const long long n = eval_list ? (long long)__ldg(eval_count) : n_slots;
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS), mma_done = smem_u32(bars + 2 * NS), chunk0 = smem_u32(bars + 2 * NS + 1);
+    // mma_done: one barrier PER LAYER (each completes once per batch).  With a single one the issuer, which needs nothing from the
+    // epilogue warps to run L0 of the next batch, could complete two layers (L2b, next L0) before a late epilogue warp looks - and a
+    // parity wait that misses two phase flips waits forever.
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS), mma_done = smem_u32(bars + 2 * NS), chunk0 = smem_u32(bars + 2 * NS + NL);
+    const uint32_t drain0 = chunk0 + 8 * 8;  // accumulator set 0 is free again: L2a's epilogue is complete (one arrival per epilogue warp)
     const uint32_t ring0 = smem_u32(smem + OFF_RING);
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512u);
     if (tid == 32) {
-        for (int i = 0; i < 2 * NS + 1; ++i) mbar_init(smem_u32(bars + i), 1u);
-        for (int i = 0; i < 8; ++i) mbar_init(chunk0 + i * 8, 8u);  // one arrival per epilogue warp
+        for (int i = 0; i < 2 * NS + NL; ++i) mbar_init(smem_u32(bars + i), 1u);
+        for (int i = 0; i < 9; ++i) mbar_init(chunk0 + i * 8, 8u);  // chunk[8] and drain0: one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t i = tid; i < OFF_RING / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -107,42 +111,48 @@ k_cnn_conv(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ l
     __syncthreads();
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    auto batch_sync = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(WTHREADS) : "memory"); };
+    // The batches of a CTA form ONE pipeline without CTA-wide barriers: the issuer warp stages the next batch's input planes itself
+    // (its own buffer) while it waits, the first layers of the next batch run while the epilogue warps still write the previous
+    // batch's conv3 output to HBM; the only extra hand-over is `drain0` (accumulator set 0 free again).
+    auto stage_input = [&](long long first_pos) {  // issuer warp: 8 rows per lane
+        uint64_t b0[POS], b1[POS];
+        uint32_t meta[POS];  // bit 0: leaf waits for an evaluation, bit 1: side to move
+#pragma unroll
+        for (int p = 0; p < POS; ++p) {
+            const long long gp = first_pos + p;
+            const bool in = gp < n;
+            const long long slot = in ? (eval_list ? (long long)__ldg(eval_list + gp) : gp) : 0;
+            b0[p] = leaf_bb0[slot];
+            b1[p] = leaf_bb1[slot];
+            meta[p] = ((in && leaf_status[slot] == AZ_LEAF_EVAL) ? 1u : 0u) | ((uint32_t)(leaf_player[slot] & 1) << 1);
+        }
+        const uint32_t one = F16 ? 0x3C00u : 0x3F80u;
+#pragma unroll
+        for (int k = 0; k < ROWS / 32; ++k) {
+            const int r = (int)lane + 32 * k;
+            int pos, y, x;
+            if (!decode_row(r, pos, y, x)) continue;
+            uint64_t c0 = b0[0], c1 = b1[0];
+            uint32_t m = meta[0];
+#pragma unroll
+            for (int p = 1; p < POS; ++p)
+                if (pos == p) { c0 = b0[p]; c1 = b1[p]; m = meta[p]; }
+            const int bit = x * c4::STRIDE + y, pl = (int)(m >> 1) & 1;
+            const uint32_t live = m & 1u;
+            const uint32_t s0 = (uint32_t)((c0 >> bit) & 1ull), s1 = (uint32_t)((c1 >> bit) & 1ull);
+            const uint32_t mine = live * (pl ? s1 : s0), theirs = live * (pl ? s0 : s1), emp = live * (1u - (s0 | s1));
+            // channels 0..2 = empty / side to move / opponent (cnn.py:93-95); the buffer's second K group stays zero
+            *reinterpret_cast<uint4 *>(bufIn + (GUARD + r) * ROWB) = make_uint4(emp * one | (mine * one) << 16, theirs * one, 0u, 0u);
+        }
+        fence_async_smem();
+        __syncwarp();
+    };
+    if (warp == 8 && (long long)blockIdx.x < (n + POS - 1) / POS) stage_input((long long)blockIdx.x * POS);
 
     const long long n_batches = (n + POS - 1) / POS;
     uint32_t it = 0, g = 0;  // g: weight pieces produced / consumed so far
     for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
         const long long pos0 = batch * POS;
-        uint64_t in_b0 = 0, in_b1 = 0;
-        uint32_t in_meta = 0;
-        if (tid < ROWS) {
-            int pos, y, x;
-            const bool cell = decode_row((int)tid, pos, y, x);
-            const long long gp = pos0 + pos;
-            const bool in = cell && gp < n;
-            const long long slot = in ? (eval_list ? (long long)__ldg(eval_list + gp) : gp) : 0;
-            const bool live = in && leaf_status[slot] == AZ_LEAF_EVAL;
-            in_b0 = leaf_bb0[slot];
-            in_b1 = leaf_bb1[slot];
-            in_meta = (live ? 1u : 0u) | ((uint32_t)(leaf_player[slot] & 1) << 1) | (cell ? 4u : 0u) | ((uint32_t)(x * c4::STRIDE + y) << 8);
-        }
-        if (warp != 9) {
-            batch_sync();  // the previous batch's last epilogue has drained tensor memory
-            // input planes: channels 0..2 = empty / side to move / opponent (cnn.py:93-95); the buffer's second K group stays zero
-            if (in_meta & 4u) {
-                const int pl = (in_meta >> 1) & 1, bit = (int)(in_meta >> 8);
-                const uint32_t live = in_meta & 1u;
-                const uint32_t s0 = (uint32_t)((in_b0 >> bit) & 1ull), s1 = (uint32_t)((in_b1 >> bit) & 1ull);
-                const uint32_t mine = live * (pl ? s1 : s0), theirs = live * (pl ? s0 : s1), emp = live * (1u - (s0 | s1));
-                const uint32_t one = F16 ? 0x3C00u : 0x3F80u;
-                *reinterpret_cast<uint4 *>(bufIn + (GUARD + tid) * ROWB) = make_uint4(emp * one | (mine * one) << 16, theirs * one, 0u, 0u);
-            }
-            fence_async_smem();
-            fence_before();
-            batch_sync();
-            fence_after();
-        }
-
         if (warp == 9) {
             // ===== weight producer =====
             const uint8_t *src = weights;
@@ -157,6 +167,10 @@ k_cnn_conv(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ l
             }
         } else if (warp == 8) {
             // ===== MMA issuer =====
+            if (it > 0) {  // set 0 (L0's accumulators) was L2a's in the previous batch: its epilogue must have drained it
+                mbar_wait(drain0, (it - 1u) & 1u);
+                fence_after();
+            }
 #pragma unroll 1
             for (int l = 0; l < NL; ++l) {
                 const uint32_t src = l == 0 ? aIn : (l == 1 ? a1 : a2);
@@ -187,9 +201,11 @@ k_cnn_conv(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ l
                     }
                     __syncwarp();
                 }
-                if (elect_one()) umma_commit(mma_done);
+                if (elect_one()) umma_commit(mma_done + l * 8);
                 __syncwarp();
             }
+            // the next batch's input: L0 of this batch (the only reader of the input buffer) completed long ago
+            if (batch + gridDim.x < n_batches) stage_input((batch + gridDim.x) * POS);
         } else {
             // ===== epilogue warps: thread = (tile, row) =====
             const int tile = (int)(warp >> 2);
@@ -206,7 +222,7 @@ k_cnn_conv(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ l
                 const float *bias = s_bias + (l == 0 ? 0 : (l == 1 ? 64 : (l == 2 ? 192 : 320)));
                 const uint32_t acc = lane_addr + (uint32_t)(l & 1) * 256u + (uint32_t)(tile * N);
                 uint8_t *dst = l == 0 ? buf1 : buf2;
-                mbar_wait(mma_done, (uint32_t)l & 1u);  // four completions per batch: the parity is the layer's
+                mbar_wait(mma_done + l * 8, it & 1u);
                 fence_after();
                 uint32_t va[16], vb[16];
                 auto chunk = [&](const uint32_t (&v)[16], int c) {
@@ -243,8 +259,12 @@ k_cnn_conv(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ l
                     if (c + 2 < chunks) tmem_ld16_issue(acc + (c + 2) * 16, va);
                     chunk(vb, c + 1);
                 }
+                if (l == 2) {  // set 0 is drained: the next batch's L0 may overwrite it
+                    fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(drain0);
+                }
             }
-            fence_before();  // the accumulator reads of L2b are complete before the next batch's barrier lets L1 overwrite set 1
         }
     }
     fence_before();
