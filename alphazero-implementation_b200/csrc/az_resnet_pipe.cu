@@ -52,9 +52,10 @@ static_assert(LEAD + TPOS * PIX <= 128, "a tile's positions must fit its 128 row
 
 // C channels, TILES accumulator tiles per CTA (TILES * C tensor-memory columns per accumulator set), NS ring stages, EW epilogue
 // warps (warp EW issues the MMAs, warp EW + 1 streams the weights), CTAS resident CTAs per SM
-template <int C_, int TILES_, int NS_, int MAX_CONV_, int EW_ = 8, int CTAS_ = 1>
+template <int C_, int TILES_, int NS_, int MAX_CONV_, int EW_ = 8, int CTAS_ = 1, bool PAIR_ = false>
 struct Cfg {
     static constexpr int C = C_, TILES = TILES_, NS = NS_, MAX_CONV = MAX_CONV_, EW = EW_, CTAS = CTAS_;
+    static constexpr bool PAIR = PAIR_;           // clusters of two CTAs on two SMs share every MMA (cta_group::2, M = 256)
     static constexpr int THREADS = (EW + 2) * 32, WTHREADS = (EW + 1) * 32, ETHREADS = EW * 32;
     static constexpr int TSTEP = EW / 4;          // an epilogue thread owns one row of the tiles w / 4, w / 4 + TSTEP, ...
     static constexpr int SETCOLS = TILES * C;     // tensor-memory columns of one accumulator set
@@ -71,7 +72,7 @@ struct Cfg {
     static constexpr uint32_t OFF_RING = 2 * BUF_BYTES;
     static constexpr uint32_t OFF_BIAS = OFF_RING + NS * PIECE_BYTES;
     static constexpr uint32_t OFF_BARS = OFF_BIAS + (MAX_CONV * C + NHC) * 4;
-    static constexpr int NBARS = 2 * NS + 1 + KS;           // full[NS] empty[NS] mma_done chunk[KS]
+    static constexpr int NBARS = 2 * NS + 1 + KS + NS + 1;  // full[NS] empty[NS] mma_done chunk[KS] | pair: pfull[NS] batch_ready
     static constexpr uint32_t SMEM_BYTES = OFF_BARS + NBARS * 8 + 16;
     // FC-tail scratch inside t's K groups 2..7 (K groups 0 / 1 take the next batch's stem input): head activations, per-warp sums
     static constexpr uint32_t OFF_HACT = 2 * LBO_A;
@@ -89,6 +90,10 @@ using Cfg64 = Cfg<64, 4, 4, 23>;         // 11 blocks; 18 KB pieces; 8 positions
 // hand-over, its FC tail or its prologue, the other one's MMAs keep the tensor core busy - the overlap the ping-pong kernel builds
 // by hand inside one CTA, here between two independent instruction streams.  5 blocks at most (bias table).
 using Cfg64x2 = Cfg<64, 2, 2, 11, 4, 2>;
+// The same with CTA pairs: cta_group::2 MMAs (M = 256: this CTA's tile and the peer's), each CTA stages HALF of every weight piece
+// and the tensor cores fetch B once per pair: 5 KB instead of 6 KB of shared-memory operands per MMA per SM - measured 43 against 48
+// cycles per 128x64x16 MMA (scripts/ubench/mma_pair.cu) - and half the weight traffic into each SM.
+using Cfg64x2p = Cfg<64, 2, 2, 11, 4, 2, true>;
 
 __device__ __forceinline__ bool decode_row(int r, int &pos, int &y, int &x) {
     const int tile = r >> 7;
@@ -112,6 +117,7 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
     constexpr int C = K::C, TILES = K::TILES, NS = K::NS, KS = K::KS, POS = K::POS, ROWS = K::ROWS, RPT = K::RPT, NBARS = K::NBARS;
     constexpr int EW = K::EW, THREADS = K::THREADS, WTHREADS = K::WTHREADS, ETHREADS = K::ETHREADS, TSTEP = K::TSTEP;
     constexpr uint32_t SETCOLS = K::SETCOLS;
+    constexpr bool PAIR = K::PAIR;
     constexpr uint32_t LBO_A = K::LBO_A, BUF_BYTES = K::BUF_BYTES, TAP_BYTES = K::TAP_BYTES, PIECE_BYTES = K::PIECE_BYTES;
     constexpr uint32_t OFF_RING = K::OFF_RING, OFF_BIAS = K::OFF_BIAS, OFF_BARS = K::OFF_BARS, OFF_HACT = K::OFF_HACT, OFF_RED = K::OFF_RED;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -124,27 +130,45 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
     const long long n = eval_list ? (long long)__ldg(eval_count) : n_slots;
     const int n_conv = 1 + 2 * num_blocks, n_layers = n_conv + 1;
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS), mma_done = smem_u32(bars + 2 * NS), chunk0 = smem_u32(bars + 2 * NS + 1);
+    const uint32_t pfull0 = chunk0 + KS * 8, batch_ready = pfull0 + NS * 8;
     const uint32_t ring0 = smem_u32(smem + OFF_RING);
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 2 * SETCOLS);
+    // PAIR: the two CTAs of a cluster (two SMs) run every MMA together; rank 0 issues them.  Barriers that gate the MMAs live in
+    // the leader: chunk[] and batch_ready collect arrivals from both CTAs, pfull[] is the peer's "my half of the weights has landed".
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    if (warp == 0) {
+        if (PAIR) tmem_alloc2(smem_u32(tmem_slot), 2 * SETCOLS);
+        else tmem_alloc(smem_u32(tmem_slot), 2 * SETCOLS);
+    }
     if (tid == 32) {
         for (int i = 0; i < 2 * NS + 1; ++i) mbar_init(smem_u32(bars + i), 1u);
-        for (int i = 0; i < KS; ++i) mbar_init(chunk0 + i * 8, (uint32_t)EW);  // one arrival per epilogue warp
+        for (int i = 0; i < KS; ++i) mbar_init(chunk0 + i * 8, (uint32_t)(PAIR ? 2 * EW : EW));  // one arrival per epilogue warp (of both CTAs)
+        for (int i = 0; i < NS; ++i) mbar_init(pfull0 + i * 8, 1u);
+        mbar_init(batch_ready, 2u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    const uint32_t chunk_lead = PAIR ? mapa(chunk0, 0u) : chunk0;  // shared::cluster addresses of the leader's barriers
+    const uint32_t pfull_lead = PAIR ? mapa(pfull0, 0u) : pfull0, ready_lead = PAIR ? mapa(batch_ready, 0u) : batch_ready;
     for (uint32_t i = tid; i < 2 * BUF_BYTES / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     for (uint32_t i = tid; i < (uint32_t)n_conv * C; i += THREADS) s_bias[i] = __ldg(biases + i);
     for (uint32_t i = tid; i < NHC; i += THREADS) s_bias[n_conv * C + i] = __ldg(head_b + i);
     const uint32_t aX = smem_u32(bufX) + GUARD * ROWB, aT = smem_u32(bufT) + GUARD * ROWB;
     fence_before();
     __syncthreads();  // barriers initialised, tensor memory allocated, buffers zeroed, biases staged
+    if (PAIR) cluster_sync_all();  // ... in the peer as well, before anything remote happens
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
     auto batch_sync = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(WTHREADS) : "memory"); };  // everyone but the weight producer
 
     const long long n_batches = (n + POS - 1) / POS;
+    // PAIR: cluster c walks over pairs of batches (2 pb, 2 pb + 1), one per CTA; both CTAs run the same number of iterations (a
+    // batch beyond the last one is empty: zero rows, no outputs)
+    const long long first = PAIR ? (long long)cluster_id_x() : (long long)blockIdx.x, stride = PAIR ? (long long)cluster_count_x() : (long long)gridDim.x;
+    const long long n_units = PAIR ? (n_batches + 1) / 2 : n_batches;
     uint32_t it = 0;
     uint32_t g = 0;  // pieces produced (warp 9) / consumed (warp 8) so far: stage = g % NS, use = g / NS
-    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
+    for (long long unit = first; unit < n_units; unit += stride, ++it) {
+        const long long batch = PAIR ? 2 * unit + rank : unit;
         const long long pos0 = batch * POS;
         const uint32_t gl0 = it * (uint32_t)n_layers, ge0 = it * (uint32_t)n_conv;
         // this thread's stem rows: the leaf records are requested now and consumed after the batch barrier
@@ -196,6 +220,7 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
             fence_before();
             batch_sync();
             fence_after();
+            if (PAIR && tid == 0) mbar_arrive_cluster(ready_lead);  // this CTA's stem input is in place (the leader's issuer waits for both)
         }
 
         if (warp == EW + 1) {
@@ -204,31 +229,55 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                 const bool head = l >= n_conv;
                 const uint8_t *src = l == 0 ? weights : (head ? head_w : weights + PIECE_BYTES + (size_t)(l - 1) * KS * PIECE_BYTES);
                 const uint32_t bytes = head ? HEAD_PIECE_BYTES : PIECE_BYTES;
+                // a pair splits B by output channel: this CTA stages rows [rank * N / 2, (rank + 1) * N / 2) of every tap - packed as the
+                // first / second half of the piece (models.py:pack_trunk_weights_pipe(pair=True))
+                const uint32_t mine = PAIR ? bytes / 2 : bytes;
                 const int pieces = l == 0 ? 1 : KS;
 #pragma unroll 1
                 for (int i = 0; i < pieces; ++i, ++g) {
                     const uint32_t st = g % NS;
-                    if (g >= NS) mbar_wait(empty0 + st * 8, ((g / NS) - 1u) & 1u);  // the MMAs of the previous use have read the stage
-                    if (elect_one()) bulk_load(ring0 + st * PIECE_BYTES, src + (size_t)i * bytes, bytes, full0 + st * 8);
+                    if (g >= NS) {  // the MMAs of the previous use have read the stage
+                        if (PAIR) mbar_wait_cluster(empty0 + st * 8, ((g / NS) - 1u) & 1u);
+                        else mbar_wait(empty0 + st * 8, ((g / NS) - 1u) & 1u);
+                    }
+                    if (elect_one()) bulk_load(ring0 + st * PIECE_BYTES, src + (size_t)i * bytes + (size_t)rank * mine, mine, full0 + st * 8);
+                    __syncwarp();
+                }
+            }
+        } else if (warp == EW && !leader) {
+            // ===== peer CTA of a pair: tell the leader when this CTA's half of a weight piece has landed =====
+            for (int l = 0; l < n_layers; ++l) {
+                const int pieces = l == 0 ? 1 : KS;
+#pragma unroll 1
+                for (int i = 0; i < pieces; ++i, ++g) {
+                    const uint32_t st = g % NS;
+                    mbar_wait(full0 + st * 8, (g / NS) & 1u);
+                    if (elect_one()) mbar_arrive_cluster(pfull_lead + st * 8);
                     __syncwarp();
                 }
             }
         } else if (warp == EW) {
             // ===== MMA issuer (converged; one elected lane issues) =====
+            if (PAIR) mbar_wait_cluster(batch_ready, it & 1u);  // the peer's stem input is in place as well
             for (int l = 0; l < n_layers; ++l) {
                 const bool head = l >= n_conv;
                 const uint32_t src = l == 0 ? aT : ((head || (l & 1)) ? aX : aT);  // conv1 (odd l) and the heads read x; conv2 reads t
-                const uint32_t idesc = head ? instr_desc(128, NHC, F16) : instr_desc(128, C, F16);
+                const uint32_t idesc = head ? instr_desc(PAIR ? 256 : 128, NHC, F16) : instr_desc(PAIR ? 256 : 128, C, F16);
                 const uint32_t acc = tmem_base + (uint32_t)(l & 1) * SETCOLS;
                 const uint64_t a_desc = smem_desc(src, LBO_A, SBO_A);
                 const int ksteps = l == 0 ? 1 : KS;
-                const uint32_t tap_units = (head ? HEAD_TAP_BYTES : TAP_BYTES) >> 4;
+                // bytes of one tap inside a staged piece: a pair holds half of the output channels per CTA
+                const uint32_t tap_units = ((head ? HEAD_TAP_BYTES : TAP_BYTES) >> 4) / (PAIR ? 2u : 1u);
 #pragma unroll 1
                 for (int ks = 0; ks < ksteps; ++ks, ++g) {
-                    // input channels 16 ks .. 16 ks + 15 of every row are written once all eight epilogue warps have passed them
-                    if (l > 0) mbar_wait(chunk0 + ks * 8, (ge0 + (uint32_t)l - 1u) & 1u);
+                    // input channels 16 ks .. 16 ks + 15 of every row are written once all epilogue warps (of both CTAs) have passed them
+                    if (l > 0) {
+                        if (PAIR) mbar_wait_cluster(chunk0 + ks * 8, (ge0 + (uint32_t)l - 1u) & 1u);
+                        else mbar_wait(chunk0 + ks * 8, (ge0 + (uint32_t)l - 1u) & 1u);
+                    }
                     const uint32_t st = g % NS;
                     mbar_wait(full0 + st * 8, (g / NS) & 1u);  // the K chunk's 9 taps have landed
+                    if (PAIR) mbar_wait_cluster(pfull0 + st * 8, (g / NS) & 1u);  // ... in the peer too
                     fence_after();
                     if (elect_one()) {
                         const uint64_t bd = smem_desc(ring0 + st * PIECE_BYTES, LBO_W, SBO_W);
@@ -236,15 +285,21 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                         for (int tap = 0; tap < 9; ++tap) {
                             const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);  // rows; one row = 16 B = one descriptor address unit
 #pragma unroll
-                            for (int t = 0; t < TILES; ++t)
-                                umma(acc + t * C, a_desc + (uint64_t)(int64_t)(shift + t * 128 + ks * (int)(2 * LBO_A >> 4)), bd + (uint64_t)(tap * tap_units), idesc,
-                                     (ks | tap) > 0);
+                            for (int t = 0; t < TILES; ++t) {
+                                const uint64_t ad = a_desc + (uint64_t)(int64_t)(shift + t * 128 + ks * (int)(2 * LBO_A >> 4));
+                                if (PAIR) umma2(acc + t * C, ad, bd + (uint64_t)(tap * tap_units), idesc, (ks | tap) > 0);
+                                else umma(acc + t * C, ad, bd + (uint64_t)(tap * tap_units), idesc, (ks | tap) > 0);
+                            }
                         }
-                        umma_commit(empty0 + st * 8);
+                        if (PAIR) umma_commit2(empty0 + st * 8);
+                        else umma_commit(empty0 + st * 8);
                     }
                     __syncwarp();
                 }
-                if (elect_one()) umma_commit(mma_done);
+                if (elect_one()) {
+                    if (PAIR) umma_commit2(mma_done);
+                    else umma_commit(mma_done);
+                }
                 __syncwarp();
             }
         } else {
@@ -268,7 +323,8 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                 const bool skip = l > 0 && !(l & 1);            // conv2: + x, in place
                 const float *bias = s_bias + l * C;
                 const uint32_t acc = lane_addr + (uint32_t)(l & 1) * SETCOLS;
-                mbar_wait(mma_done, (gl0 + (uint32_t)l) & 1u);
+                if (PAIR) mbar_wait_cluster(mma_done, (gl0 + (uint32_t)l) & 1u);
+                else mbar_wait(mma_done, (gl0 + (uint32_t)l) & 1u);
                 fence_after();
                 uint32_t va[16], vb[16];
                 auto load = [&](int q, uint32_t (&v)[16]) { tmem_ld16_issue(acc + (uint32_t)((tile0 + TSTEP * (q % RPT)) * C + (q / RPT) * 16), v); };
@@ -298,7 +354,10 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                         fence_before();
                         fence_async_smem();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(chunk0 + c * 8);
+                        if (lane == 0) {
+                            if (PAIR) mbar_arrive_cluster(chunk_lead + c * 8);
+                            else mbar_arrive(chunk0 + c * 8);
+                        }
                     }
                 };
                 load(0, va);
@@ -316,7 +375,8 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
             float *hact = reinterpret_cast<float *>(bufT + OFF_HACT);
             const float *hb = s_bias + n_conv * C;
             {
-                mbar_wait(mma_done, (gl0 + (uint32_t)n_conv) & 1u);
+                if (PAIR) mbar_wait_cluster(mma_done, (gl0 + (uint32_t)n_conv) & 1u);
+                else mbar_wait(mma_done, (gl0 + (uint32_t)n_conv) & 1u);
                 fence_after();
 #pragma unroll
                 for (int j = 0; j < RPT; ++j) {
@@ -401,7 +461,11 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
     }  // batches
     fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 2 * SETCOLS);
+    if (PAIR) cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the pair's MMAs may still touch it
+    if (warp == 0) {
+        if (PAIR) tmem_dealloc2(tmem_base, 2 * SETCOLS);
+        else tmem_dealloc(tmem_base, 2 * SETCOLS);
+    }
 }
 
 }  // namespace
@@ -439,6 +503,27 @@ static int32_t launch_pipe(az_engine *engine, const az_resnet_desc *d, float *lo
     const int batches = (n + K::POS - 1) / K::POS;
     auto kern = d->operand_format == AZ_FMT_F16 ? k_resnet_pipe<K, true> : k_resnet_pipe<K, false>;
     const int resident = sms * K::CTAS;
+    if (K::PAIR) {
+        // clusters of two CTAs = the two SMs of a TPC; an odd tail gets an empty partner
+        cudaLaunchConfig_t cfg = {};
+        const int want = (batches + 1) / 2 * 2;
+        cfg.gridDim = dim3((unsigned)(want < resident ? want : resident / 2 * 2));
+        cfg.blockDim = dim3(K::THREADS);
+        cfg.dynamicSmemBytes = K::SMEM_BYTES;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, kern, bb0, bb1, player, status, elist, ecount, (long long)n, (const uint8_t *)d->trunk_w, d->trunk_b, (int)d->num_blocks,
+                               (const uint8_t *)d->head_conv_w, d->head_conv_b, d->fc_policy_w, d->fc_policy_b, d->fc_value_w, d->fc_value_b, logits, values,
+                               stagger_ns()) != cudaSuccess)
+            return AZ_E_CUDA;
+        return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;
+    }
     kern<<<batches < resident ? batches : resident, K::THREADS, K::SMEM_BYTES, (cudaStream_t)stream>>>(
         bb0, bb1, player, status, elist, ecount, (long long)n, (const uint8_t *)d->trunk_w, d->trunk_b, d->num_blocks, (const uint8_t *)d->head_conv_w,
         d->head_conv_b, d->fc_policy_w, d->fc_policy_b, d->fc_value_w, d->fc_value_b, logits, values, stagger_ns());
@@ -461,6 +546,7 @@ int32_t az_resnet_pipe_launch(az_engine *engine, const az_resnet_desc *d, float 
     if (d->operand_format != AZ_FMT_BF16 && d->operand_format != AZ_FMT_F16) return AZ_E_INVALID;
     if (d->num_channels == 128) return launch_pipe<Cfg128>(engine, d, logits, values, stream);
     if (d->num_channels == 64 && d->variant == 2) return launch_pipe<Cfg64x2>(engine, d, logits, values, stream);
+    if (d->num_channels == 64 && d->variant == 3) return launch_pipe<Cfg64x2p>(engine, d, logits, values, stream);
     if (d->num_channels == 64) return launch_pipe<Cfg64>(engine, d, logits, values, stream);
     return AZ_E_INVALID;
 }

@@ -359,10 +359,10 @@ def pack_trunk_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloa
     return torch.cat(parts).contiguous(), torch.stack(biases).contiguous().float()
 
 
-def pack_trunk_weights_pipe(model: "ResNet", device, dtype: torch.dtype = torch.bfloat16) -> tuple[Tensor, Tensor]:
+def pack_trunk_weights_pipe(model: "ResNet", device, dtype: torch.dtype = torch.bfloat16, pair: bool = False) -> tuple[Tensor, Tensor]:
     """The same convolutions for the layer-pipelined kernel (csrc/az_resnet_pipe.cu): per layer the pieces [9 taps][C out][16 in]
     in the order the kernel consumes them, K-chunk-major: for ks (16 input channels) for tap (3*ky + kx); the stem has one
-    K chunk (3 -> 16)."""
+    K chunk (3 -> 16).  `pair`: every piece as two halves [half][9 taps][C/2 out][16 in] - what each CTA of a pair stages."""
     C = model.num_channels
     assert C in (64, 128)
     m = copy.deepcopy(model).eval().float().to(device)
@@ -374,15 +374,24 @@ def pack_trunk_weights_pipe(model: "ResNet", device, dtype: torch.dtype = torch.
     for li, (w, b) in enumerate(convs):
         if li == 0:
             w = torch.cat([w, torch.zeros(C, 13, 3, 3, device=w.device)], dim=1)
-        for ks in range(w.shape[1] // 16):
-            for ky in range(3):
-                for kx in range(3):
-                    parts.append(_canonical_kmajor(w[:, 16 * ks:16 * ks + 16, ky, kx], dtype))
+        parts += _pieces(w, dtype, pair)
         biases.append(b)
     return torch.cat(parts).contiguous(), torch.stack(biases).contiguous().float()
 
 
-def pack_head_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloat16, pipe: bool = True):
+def _pieces(w: Tensor, dtype: torch.dtype, pair: bool) -> list[Tensor]:
+    """[out][in][3][3] -> the (K chunk, [half,] tap) pieces of the layer-pipelined kernels, each [rows][16] in canonical order."""
+    n, out = w.shape[0], []
+    halves = [(0, n // 2), (n // 2, n)] if pair else [(0, n)]
+    for ks in range(w.shape[1] // 16):
+        for lo, hi in halves:
+            for ky in range(3):
+                for kx in range(3):
+                    out.append(_canonical_kmajor(w[lo:hi, 16 * ks:16 * ks + 16, ky, kx], dtype))
+    return out
+
+
+def pack_head_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloat16, pipe: bool = True, pair: bool = False):
     """Policy conv1x1 (-> 32) and value conv3x3 (-> 3), BatchNorm folded, as ONE 48-output 3x3 conv for csrc/az_conv.cu
     (the 1x1 weights occupy the centre tap), plus the two fully connected layers in fp32."""
     m = copy.deepcopy(model).eval().float().to(device)
@@ -394,8 +403,7 @@ def pack_head_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloat
     b = torch.zeros(48, device=device)
     b[:32], b[32:35] = bp, bv
     if pipe:  # pieces [48][16] in (ks, tap) order, like the trunk's
-        conv = torch.cat([_canonical_kmajor(w[:, 16 * ks:16 * ks + 16, ky, kx], dtype) for ks in range(model.num_channels // 16)
-                          for ky in range(3) for kx in range(3)]).contiguous()
+        conv = torch.cat(_pieces(w, dtype, pair)).contiguous()
     else:
         conv = torch.cat([_canonical_kmajor(w[:, :, ky, kx], dtype) for ky in range(3) for kx in range(3)]).contiguous()
     f = lambda t: t.detach().float().contiguous()
@@ -407,7 +415,8 @@ class TensorCoreTrunk:
 
     def __init__(self, model: "ResNet", device: torch.device, dtype: torch.dtype = torch.bfloat16, variant: int = 0):
         """variant 0: the layer-pipelined kernel (64 or 128 channels); 1: the ping-pong kernel of csrc/az_conv.cu (64 channels);
-        2: the layer-pipelined kernel with two 4-position CTAs per SM (64 channels, at most 5 blocks)."""
+        2: the layer-pipelined kernel with two 4-position CTAs per SM (64 channels, at most 5 blocks); 3: variant 2 with CTA pairs
+        (cta_group::2 MMAs over two SMs, each CTA staging half of the weights)."""
         from . import _lib
 
         self.lib = _lib.load()
@@ -417,12 +426,13 @@ class TensorCoreTrunk:
         self.num_blocks = model.num_res_blocks
         self.num_channels = model.num_channels
         assert variant == 0 or self.num_channels == 64
-        assert variant != 2 or self.num_blocks <= 5
-        self._pack = pack_trunk_weights_pipe if variant != 1 else pack_trunk_weights
+        assert variant not in (2, 3) or self.num_blocks <= 5
+        pair = variant == 3
+        self._pack = (lambda m, dev, dt: pack_trunk_weights_pipe(m, dev, dt, pair)) if variant != 1 else pack_trunk_weights
         self.weights, self.biases = self._pack(model, self.device, dtype)
         expect = self.lib.az_resnet_pipe_weight_bytes(self.num_blocks, self.num_channels) if variant != 1 else self.lib.az_trunk_weight_bytes(self.num_blocks)
         assert self.weights.numel() * 2 == expect
-        self.heads = pack_head_weights(model, self.device, dtype, pipe=variant != 1)
+        self.heads = pack_head_weights(model, self.device, dtype, pipe=variant != 1, pair=pair)
         hw, hb, fpw, fpb, fvw, fvb = self.heads
         self.desc = _lib.AzResnetDesc(self.num_blocks, model.num_channels, _operand_format(dtype), variant, self.weights.data_ptr(),
                                       self.biases.data_ptr(), hw.data_ptr(), hb.data_ptr(), fpw.data_ptr(), fpb.data_ptr(),
@@ -438,7 +448,7 @@ class TensorCoreTrunk:
         w, b = self._pack(model, self.device, self.dtype)
         self.weights.copy_(w)
         self.biases.copy_(b)
-        for dst, src in zip(self.heads, pack_head_weights(model, self.device, self.dtype, pipe=self.variant != 1)):
+        for dst, src in zip(self.heads, pack_head_weights(model, self.device, self.dtype, pipe=self.variant != 1, pair=self.variant == 3)):
             dst.copy_(src)
         return True
 

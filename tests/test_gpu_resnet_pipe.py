@@ -35,10 +35,12 @@ def _emulated(model, x, dtype):
     (128, 0, 4, torch.bfloat16), (128, 1, 3, torch.bfloat16), (128, 1, 64, torch.float16), (128, 2, 1000, torch.bfloat16),
     (128, 9, 700, torch.float16), (128, 3, 2501, torch.bfloat16),
     (64, 0, 8, torch.bfloat16), (64, 1, 5, torch.float16), (64, 4, 64, torch.float16), (64, 4, 3001, torch.bfloat16), (64, 11, 1190, torch.float16),
-    (-64, 0, 4, torch.bfloat16), (-64, 1, 7, torch.float16), (-64, 4, 64, torch.float16), (-64, 4, 3001, torch.bfloat16), (-64, 5, 2381, torch.float16)])
+    (-64, 0, 4, torch.bfloat16), (-64, 1, 7, torch.float16), (-64, 4, 64, torch.float16), (-64, 4, 3001, torch.bfloat16), (-64, 5, 2381, torch.float16),
+    (-640, 0, 4, torch.bfloat16), (-640, 1, 7, torch.float16), (-640, 1, 8, torch.float16), (-640, 4, 64, torch.float16), (-640, 4, 3001, torch.bfloat16),
+    (-640, 5, 2381, torch.float16)])
 def test_resnet_pipe_kernel_matches_pytorch(channels, blocks, n, dtype):
-    variant = 2 if channels < 0 else 0  # -64: the two-CTAs-per-SM instance
-    channels = abs(channels)
+    variant = {64: 0, 128: 0, -64: 2, -640: 3}[channels]  # -64: the two-CTAs-per-SM instance; -640: the same with CTA pairs
+    channels = 128 if channels == 128 else 64
     torch.manual_seed(13 * blocks + n)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
