@@ -213,3 +213,22 @@ def test_elo_update_is_the_notebooks():
     assert update_elo(1500, 1500, 1.0) == (1516, 1484)
     assert update_elo(1500, 1500, 0.5) == (1500, 1500)
     assert update_elo(1516, 1484, 0.0) == (int(1516 + 32 * (0 - 1 / (1 + 10 ** (-32 / 400)))), int(1484 + 32 * (1 - (1 - 1 / (1 + 10 ** (-32 / 400))))))
+
+
+def test_player_move_rule_on_visit_counts():
+    """ui/cli/player.py:66-74 on root child visit counts: temperature 0 = first maximum of the visit policy, t = p ** (1 / t)
+    renormalised and sampled, inf = a uniformly random legal column (host logic of `AlphaZeroPlayer` / `Arena`)."""
+    import random
+
+    from alphazero_implementation_b200.player import _pick
+
+    counts = np.array([10, 40, 0, 40, 5, 0, 4])
+    legal = 0b1011011  # columns 0, 1, 3, 4, 6
+    rng = random.Random(0)
+    assert _pick(counts, legal, 0, rng) == 1  # first of the two maxima, like max() over the policy dict in action order
+    assert {_pick(counts, legal, float("inf"), rng) for _ in range(200)} == {0, 1, 3, 4, 6}
+    picks = [_pick(counts, legal, 1.0, rng) for _ in range(4000)]
+    freq = np.bincount(picks, minlength=7) / 4000
+    assert np.allclose(freq, counts / counts.sum(), atol=0.03) and freq[2] == 0 and freq[5] == 0
+    cold = [_pick(counts, legal, 0.05, rng) for _ in range(200)]
+    assert set(cold) <= {1, 3}  # (40 / 99) ** 20 against (10 / 99) ** 20: the maxima take everything
