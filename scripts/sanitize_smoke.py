@@ -2,7 +2,7 @@
 available, otherwise the library compiled with -DAZ_DEBUG_BOUNDS (device asserts on every tree-node index):
   (cd alphazero-implementation_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -fmad=false -shared \
      -Xcompiler -fPIC -DAZ_DEBUG_BOUNDS -o ../libaz_engine.so az_engine.cu az_mlp.cu az_conv.cu az_resnet_pipe.cu az_cnn.cu)
-  compute-sanitizer --tool memcheck python scripts/sanitize_smoke.py"""
+  compute-sanitizer --tool memcheck python scripts/sanitize_smoke.py      (compute-sanitizer is closed on the round-2 GPU pool)"""
 import sys
 import numpy as np
 import torch
