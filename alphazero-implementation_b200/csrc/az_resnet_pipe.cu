@@ -94,6 +94,7 @@ using Cfg64x2 = Cfg<64, 2, 2, 11, 4, 2>;
 // and the tensor cores fetch B once per pair: 5 KB instead of 6 KB of shared-memory operands per MMA per SM - measured 43 against 48
 // cycles per 128x64x16 MMA (scripts/ubench/mma_pair.cu) - and half the weight traffic into each SM.
 using Cfg64x2p = Cfg<64, 2, 2, 11, 4, 2, true>;
+using Cfg128p = Cfg<128, 2, 2, 19, 8, 1, true>;  // 128 channels with CTA pairs: B 2 KB instead of 4 KB per MMA per SM, 18 KB half-pieces
 
 __device__ __forceinline__ bool decode_row(int r, int &pos, int &y, int &x) {
     const int tile = r >> 7;
@@ -544,6 +545,7 @@ int64_t az_resnet_pipe_weight_bytes(int32_t num_blocks, int32_t num_channels) {
 int32_t az_resnet_pipe_launch(az_engine *engine, const az_resnet_desc *d, float *logits, float *values, void *stream) {
     if (!engine || !d || !d->trunk_w || !d->trunk_b) return AZ_E_INVALID;
     if (d->operand_format != AZ_FMT_BF16 && d->operand_format != AZ_FMT_F16) return AZ_E_INVALID;
+    if (d->num_channels == 128 && d->variant == 3) return launch_pipe<Cfg128p>(engine, d, logits, values, stream);
     if (d->num_channels == 128) return launch_pipe<Cfg128>(engine, d, logits, values, stream);
     if (d->num_channels == 64 && d->variant == 2) return launch_pipe<Cfg64x2>(engine, d, logits, values, stream);
     if (d->num_channels == 64 && d->variant == 3) return launch_pipe<Cfg64x2p>(engine, d, logits, values, stream);

@@ -425,8 +425,8 @@ class TensorCoreTrunk:
         self.variant = variant
         self.num_blocks = model.num_res_blocks
         self.num_channels = model.num_channels
-        assert variant == 0 or self.num_channels == 64
-        assert variant not in (2, 3) or self.num_blocks <= 5
+        assert variant in (0, 3) or self.num_channels == 64
+        assert variant not in (2, 3) or self.num_blocks <= 5 or self.num_channels == 128
         pair = variant == 3
         self._pack = (lambda m, dev, dt: pack_trunk_weights_pipe(m, dev, dt, pair)) if variant != 1 else pack_trunk_weights
         self.weights, self.biases = self._pack(model, self.device, dtype)
@@ -596,7 +596,10 @@ class InferenceNet(nn.Module):
                 # 5 blocks), ping-pong 0.592 ms, layer-pipelined with one 8-position CTA 0.630 ms (the hand-over bubble at each layer
                 # start has nothing to hide behind); 128 channels only fit the layer-pipelined schedule
                 auto = 2 if m.num_res_blocks <= 5 else 1
-                variant = 0 if m.num_channels == 128 else (auto if trunk_variant is None else trunk_variant)
+                if m.num_channels == 128:
+                    variant = 3 if trunk_variant == 3 else 0
+                else:
+                    variant = auto if trunk_variant is None else trunk_variant
                 self.trunk = TensorCoreTrunk(m, torch.device(device), dtype, variant=variant)
             self.net = self._fold(m).to(dtype).to(memory_format=torch.channels_last)
         else:

@@ -37,10 +37,11 @@ def _emulated(model, x, dtype):
     (64, 0, 8, torch.bfloat16), (64, 1, 5, torch.float16), (64, 4, 64, torch.float16), (64, 4, 3001, torch.bfloat16), (64, 11, 1190, torch.float16),
     (-64, 0, 4, torch.bfloat16), (-64, 1, 7, torch.float16), (-64, 4, 64, torch.float16), (-64, 4, 3001, torch.bfloat16), (-64, 5, 2381, torch.float16),
     (-640, 0, 4, torch.bfloat16), (-640, 1, 7, torch.float16), (-640, 1, 8, torch.float16), (-640, 4, 64, torch.float16), (-640, 4, 3001, torch.bfloat16),
-    (-640, 5, 2381, torch.float16)])
+    (-640, 5, 2381, torch.float16),
+    (-1280, 0, 4, torch.bfloat16), (-1280, 1, 5, torch.float16), (-1280, 2, 1000, torch.bfloat16), (-1280, 9, 701, torch.float16)])
 def test_resnet_pipe_kernel_matches_pytorch(channels, blocks, n, dtype):
-    variant = {64: 0, 128: 0, -64: 2, -640: 3}[channels]  # -64: the two-CTAs-per-SM instance; -640: the same with CTA pairs
-    channels = 128 if channels == 128 else 64
+    variant = {64: 0, 128: 0, -64: 2, -640: 3, -1280: 3}[channels]  # -64: two CTAs per SM; -640 / -1280: CTA pairs (64 / 128 channels)
+    channels = 128 if channels in (128, -1280) else 64
     torch.manual_seed(13 * blocks + n)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
