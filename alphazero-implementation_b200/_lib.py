@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("AZ_ENGINE_LIB") or os.path.join(PKG_DIR, "libaz_engine.so")  # override: A/B builds of the library
-SOURCES = ["az_engine.cu", "az_mlp.cu", "az_conv.cu", "az_resnet_pipe.cu", "az_cnn.cu"]
+SOURCES = ["az_engine.cu", "az_mlp.cu", "az_conv.cu", "az_resnet_pipe.cu", "az_resnet_wide.cu", "az_cnn.cu"]
 HEADERS = ["az_eval.cuh", "c4_bitboard.cuh", "tcgen05.cuh", os.path.join("..", "..", "include", "az_engine.h")]
 
 NVCC_FLAGS = [

@@ -630,6 +630,7 @@ k_resnet_trunk(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict
 extern "C" {
 
 int32_t az_resnet_pipe_launch(az_engine *engine, const az_resnet_desc *d, float *logits, float *values, void *stream);  // csrc/az_resnet_pipe.cu
+int32_t az_resnet_wide_launch(az_engine *engine, const az_resnet_desc *d, float *logits, float *values, void *stream);  // csrc/az_resnet_wide.cu
 
 #ifdef AZ_TRUNK_CLOCKS
 int32_t az_debug_trunk_clocks(long long *out) {
@@ -733,6 +734,7 @@ int32_t az_resnet_forward_leaves_v2(az_engine *engine, const az_resnet_desc *d, 
     if (!d || !logits || !values) return AZ_E_INVALID;
     if (!d->head_conv_w || !d->head_conv_b || !d->fc_policy_w || !d->fc_policy_b || !d->fc_value_w || !d->fc_value_b) return AZ_E_INVALID;
     // default: the layer-pipelined kernel (csrc/az_resnet_pipe.cu) for 64 and 128 channels; variant 1 = this file's ping-pong kernel
+    if (d->num_channels == 64 && d->variant == 4) return az_resnet_wide_launch(engine, d, logits, values, stream);  // filter rows fused (N = 192)
     if (d->num_channels == 128 || (d->num_channels == 64 && d->variant != 1)) return az_resnet_pipe_launch(engine, d, logits, values, stream);  // variants 0, 2, 3
     if (d->num_channels != 64 || d->variant != 1) return AZ_E_INVALID;
     return launch_trunk(engine, d->trunk_w, d->trunk_b, d->num_blocks, nullptr, d->head_conv_w, d->head_conv_b, d->fc_policy_w, d->fc_policy_b,

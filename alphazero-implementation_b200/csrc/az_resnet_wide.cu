@@ -1,0 +1,453 @@
+// ResNet(board, 7, num_res_blocks, 64) (src/alphazero_simple/resnet.py:30-103) behind the main package's Model API, BatchNorm
+// folded, as ONE tcgen05 kernel for the leaves of the search - the 64-channel net with the three taps of a filter row fused
+// into one MMA (N = 3 x 64 = 192).
+//
+// Why: in the implicit-GEMM formulation of csrc/az_conv.cu / az_resnet_pipe.cu (pixel = GEMM row, channels = K, a filter tap =
+// the activation buffer with the MMA descriptor moved by 8*dy + dx rows) a 64-channel layer issues 128x64x16 MMAs: 4 KB of A +
+// 2 KB of B from shared memory for 32 cycles of math.  The operand crossbar moves 128 B/clk, so each takes 48 cycles
+// (scripts/ubench/mma_pair.cu) and the whole kernel runs at the speed of shared memory.  The A tile of a tap is
+// used for 64 output columns only.  Here the three taps (dy, -1), (dy, 0), (dy, +1) of a filter row share ONE A tile - the
+// activations moved by 8*dy rows only:
+//     D[p][(dx, co)] = sum_dy sum_ci X[p + 8 dy][ci] * W[dy][dx][ci][co]                      (128 x 192 x 16 MMAs)
+//     out[q][co]     = D[q - 1][(-1, co)] + D[q][(0, co)] + D[q + 1][(+1, co)]                (epilogue)
+// A 128x192x16 MMA is 96 cycles of math for 4 KB + 6 KB of operands (80 cycles of crossbar): math-bound, and a layer is 12
+// MMAs per tile instead of 36 - 120 KB instead of 216 KB of operand reads.  The row shift of the epilogue is a warp shuffle: a
+// 128-row tile is 2 positions x 7 x 8 pixel rows, pixel column = row & 7, and column 7 is the shared zero column - its
+// accumulator rows are exact zeros - so lane 0 of a warp (column 0) takes its left neighbour from lane 31 of the same warp
+// (column 7 of another row: zero, as the true neighbour), and lane 31 itself is never a board cell.
+//
+// Schedule: one CTA per SM, 2 tiles (4 positions); an accumulator tile is 192 fp32 columns, two of them = 384 of the 512
+// columns, so the tiles ping-pong: while the eight epilogue warps drain tile 0 of layer l (tcgen05.ld, shuffles, bias (+ skip),
+// ReLU, round to 16 bits, write the next layer's A operand), the tensor core runs tile 1 of layer l, then tile 0 of layer
+// l + 1, ...  Both tiles use every weight piece, so a layer's weights are streamed once per CTA: a piece = one K chunk =
+// [3 dy][192 = (dx, co)][16 ci] = 18 KB - byte for byte the [9 taps][64][16] piece of the layer-pipelined kernel
+// (models.py:pack_trunk_weights_pipe), so both kernels take the same packed weights - through a 6-stage ring (1.5 layers ahead).
+// At a batch boundary the next batch's stem input of a tile is staged by that tile's last trunk epilogue (the t buffer is free
+// by then), so the stem MMAs follow the head MMAs without a CTA-wide barrier.
+// Roles: warps 0..7 epilogue (thread = one pixel row of a tile; warps 0..3 take output channels 0..31, warps 4..7 32..63),
+// warp 8 issues the MMAs (one elected lane), warp 9 streams the weights.
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "../../include/az_engine.h"
+#include "c4_bitboard.cuh"
+#include "tcgen05.cuh"
+
+namespace {
+
+using namespace tc05;
+
+constexpr int C = 64, KS = C / 16, KG = C / 8;
+constexpr int GUARD = 16;              // zero rows before / after the tiles (a filter row moves the window by 8 rows)
+constexpr uint32_t ROWB = 16;
+constexpr int PW = 8, PIX = 56, LEAD = 8;  // pixel-row stride, rows per position, leading zero rows of a tile
+constexpr int TPOS = 2, TILES = 2, POS = TPOS * TILES, ROWS = TILES * 128;
+constexpr int RTOT = ROWS + 2 * GUARD;
+constexpr uint32_t SBO_A = 128, LBO_A = RTOT * ROWB;   // next 8-row group, next K group
+constexpr uint32_t BUF_BYTES = KG * LBO_A;
+constexpr uint32_t LBO_W = 128, SBO_W = 256;           // canonical K-major [N][16]
+constexpr int NHC = 48, NHU = 35;      // head conv channels per dx block: 32 policy (1x1, centre tap) + 3 value (3x3) + padding
+constexpr uint32_t DY_BYTES = 3 * C * 16 * 2, PIECE_BYTES = 3 * DY_BYTES;              // [192][16], three filter rows
+constexpr uint32_t HEAD_DY_BYTES = 3 * NHC * 16 * 2, HEAD_PIECE_BYTES = 3 * HEAD_DY_BYTES;
+constexpr int NS = 6;                  // ring stages
+constexpr int EW = 8, THREADS = (EW + 2) * 32, ETHREADS = EW * 32;
+constexpr int MAX_CONV = 23;           // 11 blocks
+constexpr uint32_t TILE_COLS = 256;    // tensor-memory columns between the two accumulator tiles (192 used)
+constexpr uint32_t OFF_RING = 2 * BUF_BYTES;
+constexpr uint32_t OFF_HACT = OFF_RING + NS * PIECE_BYTES;
+constexpr uint32_t HACT_BYTES = POS * NHU * 42 * 4;
+constexpr uint32_t OFF_RED = OFF_HACT + HACT_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_RED + EW * POS * 8 * 4;
+constexpr uint32_t OFF_BARS = OFF_BIAS + (MAX_CONV * C + NHC) * 4;
+constexpr int NBARS = 2 * NS + 4;      // full[NS] empty[NS] mma_done[2] epi_done[2]
+constexpr uint32_t SMEM_BYTES = OFF_BARS + NBARS * 8 + 16;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(LEAD + TPOS * PIX <= 128, "a tile's positions must fit its 128 rows");
+static_assert(OFF_HACT % 16 == 0 && OFF_BIAS % 16 == 0 && OFF_BARS % 8 == 0, "alignment");
+
+__device__ __forceinline__ bool decode_row(int r, int &pos, int &y, int &x) {
+    const int tile = r >> 7;
+    const int rr = (r & 127) - LEAD;
+    const int p = rr >= 0 ? rr / PIX : 0;
+    const int q = rr - p * PIX;
+    y = q >> 3;
+    x = q & 7;
+    pos = tile * TPOS + p;
+    return rr >= 0 && p < TPOS && y < c4::H && x < c4::W;
+}
+
+// the leaf record behind one pixel row of a batch (requested early, consumed when the stem input is staged)
+struct RowRec {
+    uint64_t b0, b1;
+    uint32_t meta;  // bit 0: row of a position that exists and waits for an evaluation, bit 1: side to move, bit 2: board cell, bits 8..: bit index
+};
+
+template <bool F16>
+__global__ void __launch_bounds__(THREADS, 1)
+k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1, const uint8_t *__restrict__ leaf_player,
+              const uint8_t *__restrict__ leaf_status, const int32_t *__restrict__ eval_list, const int32_t *__restrict__ eval_count,
+              long long n_slots, const uint8_t *__restrict__ weights, const float *__restrict__ biases, int num_blocks,
+              const uint8_t *__restrict__ head_w, const float *__restrict__ head_b, const float *__restrict__ fc_policy_w,
+              const float *__restrict__ fc_policy_b, const float *__restrict__ fc_value_w, const float *__restrict__ fc_value_b,
+              float *__restrict__ logits, float *__restrict__ values) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *bufX = smem, *bufT = smem + BUF_BYTES;
+    float *hact = reinterpret_cast<float *>(smem + OFF_HACT);
+    float *red = reinterpret_cast<float *>(smem + OFF_RED);
+    float *s_bias = reinterpret_cast<float *>(smem + OFF_BIAS);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BARS);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + NBARS * 8);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    // position j of a batch is slot eval_list[j], j < *eval_count: only the leaves that wait for an evaluation are processed
+    const long long n = eval_list ? (long long)__ldg(eval_count) : n_slots;
+    const int n_conv = 1 + 2 * num_blocks, n_layers = n_conv + 1;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS), mma_done0 = smem_u32(bars + 2 * NS), epi_done0 = smem_u32(bars + 2 * NS + 2);
+    const uint32_t ring0 = smem_u32(smem + OFF_RING);
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (tid == 32) {
+        for (int i = 0; i < 2 * NS + 2; ++i) mbar_init(smem_u32(bars + i), 1u);
+        for (int i = 0; i < 2; ++i) mbar_init(epi_done0 + i * 8, (uint32_t)EW);  // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (uint32_t i = tid; i < 2 * BUF_BYTES / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < (uint32_t)n_conv * C; i += THREADS) s_bias[i] = __ldg(biases + i);
+    for (uint32_t i = tid; i < NHC; i += THREADS) s_bias[n_conv * C + i] = __ldg(head_b + i);
+    const uint32_t aX = smem_u32(bufX) + GUARD * ROWB, aT = smem_u32(bufT) + GUARD * ROWB;
+    const long long n_batches = (n + POS - 1) / POS;
+
+    // the leaf record of pixel row r (0..255) of batch `batch`
+    auto load_rec = [&](long long batch, int r) {
+        RowRec rec;
+        int pos, y, x;
+        const bool cell = decode_row(r, pos, y, x);
+        const long long gp = batch * POS + pos;
+        const bool in = cell && gp < n;
+        const long long slot = in ? (eval_list ? (long long)__ldg(eval_list + gp) : gp) : 0;
+        const bool live = in && leaf_status[slot] == AZ_LEAF_EVAL;
+        rec.b0 = leaf_bb0[slot];
+        rec.b1 = leaf_bb1[slot];
+        rec.meta = (live ? 1u : 0u) | ((uint32_t)(leaf_player[slot] & 1) << 1) | (cell ? 4u : 0u) | ((uint32_t)(x * c4::STRIDE + y) << 8);
+        return rec;
+    };
+    // stem input in t, K group 0: channels 0..2 = empty / side to move / opponent (cnn.py:93-95).  K group 1 keeps stale finite
+    // activations, which the stem's zero weights for channels 8..15 cancel.
+    auto stage_row = [&](const RowRec &rec, int r) {
+        if (!(rec.meta & 4u)) return;
+        const int pl = (rec.meta >> 1) & 1, bit = (int)(rec.meta >> 8);
+        const uint32_t live = rec.meta & 1u;
+        const uint32_t s0 = (uint32_t)((rec.b0 >> bit) & 1ull), s1 = (uint32_t)((rec.b1 >> bit) & 1ull);
+        const uint32_t mine = live * (pl ? s1 : s0), theirs = live * (pl ? s0 : s1), emp = live * (1u - (s0 | s1));
+        const uint32_t one = F16 ? 0x3C00u : 0x3F80u;
+        *reinterpret_cast<uint4 *>(bufT + (GUARD + r) * ROWB) = make_uint4(emp * one | (mine * one) << 16, theirs * one, 0u, 0u);
+    };
+    __syncthreads();  // buffers zeroed before the first batch's stem input goes in
+    if (tid < 128 && (long long)blockIdx.x < n_batches) {
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) stage_row(load_rec((long long)blockIdx.x, t * 128 + (int)tid), t * 128 + (int)tid);
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();  // barriers initialised, tensor memory allocated, biases and the first stem input staged
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == EW + 1) {
+        // ===== weight producer: every piece of every layer of every batch, in the order the issuer consumes them =====
+        uint32_t g = 0;
+        for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+            for (int l = 0; l < n_layers; ++l) {
+                const bool head = l >= n_conv;
+                const uint8_t *src = l == 0 ? weights : (head ? head_w : weights + PIECE_BYTES + (size_t)(l - 1) * KS * PIECE_BYTES);
+                const uint32_t bytes = head ? HEAD_PIECE_BYTES : PIECE_BYTES;
+                const int pieces = l == 0 ? 1 : KS;
+#pragma unroll 1
+                for (int i = 0; i < pieces; ++i, ++g) {
+                    const uint32_t st = g % NS;
+                    if (g >= NS) mbar_wait(empty0 + st * 8, ((g / NS) - 1u) & 1u);  // both tiles' MMAs of the previous use have read the stage
+                    if (elect_one()) bulk_load(ring0 + st * PIECE_BYTES, src + (size_t)i * bytes, bytes, full0 + st * 8);
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == EW) {
+        // ===== MMA issuer (converged; one elected lane issues).  Order: layer by layer, tile 0 then tile 1 =====
+        uint32_t g = 0, idx = 0;  // pieces consumed; tile-layers issued per tile
+        for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+            for (int l = 0; l < n_layers; ++l, ++idx) {
+                const bool head = l >= n_conv;
+                const uint32_t src = l == 0 ? aT : ((head || (l & 1)) ? aX : aT);  // conv1 (odd l) and the heads read x; conv2 reads t
+                const uint32_t idesc = head ? instr_desc(128, 3 * NHC, F16) : instr_desc(128, 3 * C, F16);
+                const uint64_t a_desc = smem_desc(src, LBO_A, SBO_A);
+                const int ksteps = l == 0 ? 1 : KS;
+                const uint32_t dy_units = (head ? HEAD_DY_BYTES : DY_BYTES) >> 4;
+#pragma unroll
+                for (int t = 0; t < TILES; ++t) {
+                    // the tile's previous epilogue is through: its accumulator columns are read, this layer's input rows are written
+                    // (after a batch's last trunk layer: the next batch's stem input as well)
+                    if (idx > 0) mbar_wait(epi_done0 + t * 8, (idx - 1u) & 1u);
+                    fence_after();
+#pragma unroll 1
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t gg = g + (uint32_t)ks, st = gg % NS;
+                        if (t == 0) {
+                            mbar_wait(full0 + st * 8, (gg / NS) & 1u);  // the K chunk's three filter rows have landed
+                            fence_after();
+                        }
+                        if (elect_one()) {
+                            const uint64_t bd = smem_desc(ring0 + st * PIECE_BYTES, LBO_W, SBO_W);
+#pragma unroll
+                            for (int dy = 0; dy < 3; ++dy) {
+                                const uint64_t ad = a_desc + (uint64_t)(int64_t)((dy - 1) * PW + t * 128 + ks * (int)(2 * LBO_A >> 4));
+                                umma(tmem_base + (uint32_t)t * TILE_COLS, ad, bd + (uint64_t)(dy * dy_units), idesc, (ks | dy) > 0);
+                            }
+                            if (t == TILES - 1) umma_commit(empty0 + st * 8);
+                        }
+                        __syncwarp();
+                    }
+                    if (elect_one()) umma_commit(mma_done0 + t * 8);
+                    __syncwarp();
+                }
+                g += (uint32_t)ksteps;
+            }
+        }
+    } else {
+        // ===== epilogue warps: thread = one pixel row of a tile, 32 of the 64 output channels =====
+        const int half = (int)(warp >> 2);
+        const int row_in_tile = (int)((warp & 3u) * 32u + lane);
+        int pos[TILES], yy[TILES], xx[TILES];
+        bool valid[TILES];
+        uint32_t row_off[TILES];
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) {
+            const int r = t * 128 + row_in_tile;
+            valid[t] = decode_row(r, pos[t], yy[t], xx[t]);
+            row_off[t] = (GUARD + r) * ROWB;
+        }
+        const uint32_t lane_addr = tmem_base + (((warp & 3u) * 32u) << 16);
+        const int lm = (int)((lane + 31u) & 31u), lp = (int)((lane + 1u) & 31u);  // left / right neighbour row (see the header)
+        uint32_t idx = 0;
+        for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+            const long long next = batch + gridDim.x;
+            const bool stage_next = half == 0 && next < n_batches;
+            RowRec rec[TILES];
+            if (stage_next) {
+#pragma unroll
+                for (int t = 0; t < TILES; ++t) rec[t] = load_rec(next, t * 128 + row_in_tile);
+            }
+            for (int l = 0; l < n_conv; ++l, ++idx) {
+                uint8_t *dst = (l & 1) ? bufT : bufX;          // stem and conv2 write x, conv1 writes t
+                const bool skip = l > 0 && !(l & 1);            // conv2: + x, in place
+                float2 bias2[16];  // this warp's 32 output channels
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(s_bias + l * C + half * 32 + 4 * i);
+                    bias2[2 * i] = make_float2(b4.x, b4.y);
+                    bias2[2 * i + 1] = make_float2(b4.z, b4.w);
+                }
+#pragma unroll
+                for (int t = 0; t < TILES; ++t) {
+                    const uint32_t acc = lane_addr + (uint32_t)t * TILE_COLS + (uint32_t)half * 32u;
+                    mbar_wait(mma_done0 + t * 8, idx & 1u);
+                    fence_after();
+                    uint32_t vm[2][16], v0[2][16], vp[2][16];
+#if defined(WIDE_EXP) && (WIDE_EXP & 2)
+                    tmem_ld16_issue(acc + C, v0[0]);
+                    tmem_ld16_issue(acc + C + 16, v0[1]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { vm[0][i] = v0[0][i] + 1; vp[0][i] = v0[0][i] + 2; vm[1][i] = v0[1][i] + 1; vp[1][i] = v0[1][i] + 2; }
+#else
+                    tmem_ld16_issue(acc, vm[0]);
+                    tmem_ld16_issue(acc + C, v0[0]);
+                    tmem_ld16_issue(acc + 2 * C, vp[0]);
+                    tmem_ld16_issue(acc + 16, vm[1]);
+                    tmem_ld16_issue(acc + C + 16, v0[1]);
+                    tmem_ld16_issue(acc + 2 * C + 16, vp[1]);
+                    tmem_ld_wait();
+#endif
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint8_t *p = dst + (uint32_t)(half * 4 + cc * 2 + h) * LBO_A + row_off[t];
+                            float2 f[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int j = h * 8 + 2 * i;
+#if defined(WIDE_EXP) && (WIDE_EXP & 1)
+                                const float2 m = make_float2(__uint_as_float(vm[cc][j]), __uint_as_float(vm[cc][j + 1]));
+                                const float2 q = make_float2(__uint_as_float(vp[cc][j]), __uint_as_float(vp[cc][j + 1]));
+#else
+                                const float2 m = make_float2(__shfl_sync(0xFFFFFFFFu, __uint_as_float(vm[cc][j]), lm),
+                                                             __shfl_sync(0xFFFFFFFFu, __uint_as_float(vm[cc][j + 1]), lm));
+                                const float2 q = make_float2(__shfl_sync(0xFFFFFFFFu, __uint_as_float(vp[cc][j]), lp),
+                                                             __shfl_sync(0xFFFFFFFFu, __uint_as_float(vp[cc][j + 1]), lp));
+#endif
+                                const float2 c0 = make_float2(__uint_as_float(v0[cc][j]), __uint_as_float(v0[cc][j + 1]));
+                                f[i] = fadd2(fadd2(fadd2(c0, m), q), bias2[cc * 8 + h * 4 + i]);
+                            }
+                            if (skip) {
+                                const uint4 s = *reinterpret_cast<const uint4 *>(p);
+                                f[0] = fadd2(f[0], unpack16<F16>(s.x));
+                                f[1] = fadd2(f[1], unpack16<F16>(s.y));
+                                f[2] = fadd2(f[2], unpack16<F16>(s.z));
+                                f[3] = fadd2(f[3], unpack16<F16>(s.w));
+                            }
+                            uint4 o = make_uint4(0, 0, 0, 0);
+                            if (valid[t]) o = make_uint4(pack16_relu<F16>(f[0]), pack16_relu<F16>(f[1]), pack16_relu<F16>(f[2]), pack16_relu<F16>(f[3]));
+                            *reinterpret_cast<uint4 *>(p) = o;
+                        }
+                    }
+                    // a batch's last trunk layer: t is free (its last reader, this layer's MMAs, is complete) - the tile's rows of
+                    // the next batch's stem input go in now
+                    if (l == n_conv - 1 && stage_next) stage_row(rec[t], t * 128 + row_in_tile);
+                    // this warp's part of the tile is in place for the tensor core and its accumulator reads are complete
+                    fence_before();
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(epi_done0 + t * 8);
+                }
+            }
+            // ---- heads: [POS][35][42] fp32 in the Flatten() order of NCHW.  Policy channels (1x1 conv) have weights in the centre
+            // tap only: their dx = -1 / +1 blocks are zero.  Warps 0..3: policy 0..15 and the 3 value channels; warps 4..7: policy 16..31.
+            const float *hb = s_bias + n_conv * C;
+#pragma unroll
+            for (int t = 0; t < TILES; ++t) {
+                const uint32_t acc = lane_addr + (uint32_t)t * TILE_COLS;
+                mbar_wait(mma_done0 + t * 8, idx & 1u);
+                fence_after();
+                uint32_t v[16], wm[16], w0[16], wp[16];
+                tmem_ld16_issue(acc + NHC + (uint32_t)half * 16u, v);
+                if (half == 0) {
+                    tmem_ld16_issue(acc + 32, wm);
+                    tmem_ld16_issue(acc + NHC + 32, w0);
+                    tmem_ld16_issue(acc + 2 * NHC + 32, wp);
+                }
+                tmem_ld_wait();
+                float val[3] = {0.f, 0.f, 0.f};
+                if (half == 0) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float m = __shfl_sync(0xFFFFFFFFu, __uint_as_float(wm[c]), lm);
+                        const float q = __shfl_sync(0xFFFFFFFFu, __uint_as_float(wp[c]), lp);
+                        val[c] = ((__uint_as_float(w0[c]) + m) + q) + hb[32 + c];
+                    }
+                }
+                if (valid[t]) {
+                    float *o = hact + pos[t] * NHU * 42 + yy[t] * c4::W + xx[t];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) o[(half * 16 + c) * 42] = fmaxf(__uint_as_float(v[c]) + hb[half * 16 + c], 0.f);
+                    if (half == 0) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) o[(32 + c) * 42] = fmaxf(val[c], 0.f);
+                    }
+                }
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(epi_done0 + t * 8);
+            }
+            ++idx;
+            asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
+            // ---- both FC layers on CUDA cores: thread t takes inputs k = t, t + ETHREADS, ...: every FC weight is read once per
+            // CTA (coalesced) and used for POS positions; acc[p][j], j = 7 is the value head
+            float acc[POS * 8];
+#pragma unroll
+            for (int i = 0; i < POS * 8; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int k0 = 0; k0 < 32 * 42; k0 += ETHREADS) {
+                const int k = k0 + (int)tid;
+                const bool in = k < 32 * 42;
+                const int kk = in ? k : 0;
+                float wj[7];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) wj[j] = in ? __ldg(fc_policy_w + j * (32 * 42) + kk) : 0.f;
+#pragma unroll
+                for (int p = 0; p < POS; ++p) {
+                    const float xv = hact[p * NHU * 42 + kk];
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) acc[p * 8 + j] = fmaf(wj[j], xv, acc[p * 8 + j]);
+                }
+            }
+            {
+                const bool in = tid < 3 * 42;
+                const int kk = in ? (int)tid : 0;
+                const float wv = in ? __ldg(fc_value_w + kk) : 0.f;
+#pragma unroll
+                for (int p = 0; p < POS; ++p) acc[p * 8 + 7] = fmaf(wv, hact[p * NHU * 42 + 32 * 42 + kk], acc[p * 8 + 7]);
+            }
+            // warp reduction by recursive halving: each step exchanges half of the values; lane L ends with the total of index L
+            constexpr int V = POS * 8;
+            static_assert(V == 32, "one value per lane after the halving");
+#pragma unroll
+            for (int h = V / 2; h >= 1; h >>= 1) {
+                const bool up = (lane & (uint32_t)h) != 0;
+#pragma unroll
+                for (int i = 0; i < h; ++i) {
+                    const float send = up ? acc[i] : acc[i + h];
+                    const float keep = up ? acc[i + h] : acc[i];
+                    acc[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, h);
+                }
+            }
+            red[warp * V + lane] = acc[0];
+            asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
+            if (tid < V) {
+                float sum = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < EW; ++w8) sum += red[w8 * V + tid];
+                const int p = (int)tid >> 3, j = (int)tid & 7;
+                const long long gp = batch * POS + p;
+                if (gp < n) {
+                    const long long slot = eval_list ? (long long)__ldg(eval_list + gp) : gp;
+                    if (j < 7) {
+                        logits[slot * 7 + j] = sum + __ldg(fc_policy_b + j);
+                    } else {
+                        const float v = tanhf(sum + __ldg(fc_value_b));
+                        values[slot * 2] = v;
+                        values[slot * 2 + 1] = -v;
+                    }
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+extern "C" {
+
+/* internal: called by az_resnet_forward_leaves_v2 (csrc/az_conv.cu), variant 4.  Takes the packed weights of the layer-pipelined
+ * kernel (az_resnet_pipe_weight_bytes(num_blocks, 64) bytes, models.py:pack_trunk_weights_pipe). */
+int32_t az_resnet_wide_launch(az_engine *engine, const az_resnet_desc *d, float *logits, float *values, void *stream) {
+    if (!engine || !d || !d->trunk_w || !d->trunk_b || d->num_channels != 64) return AZ_E_INVALID;
+    if (d->operand_format != AZ_FMT_BF16 && d->operand_format != AZ_FMT_F16) return AZ_E_INVALID;
+    if (d->num_blocks < 0 || 1 + 2 * d->num_blocks > MAX_CONV) return AZ_E_INVALID;
+    const uint64_t *bb0 = nullptr, *bb1 = nullptr;
+    const uint8_t *status = nullptr, *player = nullptr;
+    const int32_t *elist = nullptr, *ecount = nullptr;
+    int32_t n = 0;
+    if (az_leaf_arrays(engine, &bb0, &bb1, &status, &n) != AZ_OK || az_leaf_players(engine, &player) != AZ_OK ||
+        az_leaf_compact(engine, &elist, &ecount) != AZ_OK || n <= 0)
+        return AZ_E_INVALID;
+    static bool attr_set[64] = {false};
+    const int dev = az_device(engine);
+    if (dev < 0 || dev >= 64 || cudaSetDevice(dev) != cudaSuccess) return AZ_E_CUDA;
+    if (!attr_set[dev]) {
+        if (cudaFuncSetAttribute(k_resnet_wide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
+        if (cudaFuncSetAttribute(k_resnet_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
+        attr_set[dev] = true;
+    }
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return AZ_E_CUDA;
+    const int batches = (n + POS - 1) / POS;
+    auto kern = d->operand_format == AZ_FMT_F16 ? k_resnet_wide<true> : k_resnet_wide<false>;
+    kern<<<batches < sms ? batches : sms, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
+        bb0, bb1, player, status, elist, ecount, (long long)n, (const uint8_t *)d->trunk_w, d->trunk_b, d->num_blocks, (const uint8_t *)d->head_conv_w,
+        d->head_conv_b, d->fc_policy_w, d->fc_policy_b, d->fc_value_w, d->fc_value_b, logits, values);
+    return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;
+}
+
+}  // extern "C"

@@ -171,4 +171,21 @@ __device__ __forceinline__ float2 unpack16(uint32_t w) {
     return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
 }
 
+// packed fp32 pair arithmetic (FADD2) and ReLU + round-to-16-bit in one instruction (F2FP.RELU): the epilogues are issue-bound
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 r;
+    asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tadd.rn.f32x2 c, a, b;\n\tmov.b64 {%0, %1}, c;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+// max(v, 0) rounded to the operand format, v.x in the low half; fp16 saturates to the largest finite value instead of overflowing
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16_relu(float2 v) {
+    uint32_t r;
+    if (F16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v.y), "f"(v.x));
+    else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v.y), "f"(v.x));
+    return r;
+}
+
 }  // namespace tc05

@@ -416,7 +416,8 @@ class TensorCoreTrunk:
     def __init__(self, model: "ResNet", device: torch.device, dtype: torch.dtype = torch.bfloat16, variant: int = 0):
         """variant 0: the layer-pipelined kernel (64 or 128 channels); 1: the ping-pong kernel of csrc/az_conv.cu (64 channels);
         2: the layer-pipelined kernel with two 4-position CTAs per SM (64 channels, at most 5 blocks); 3: variant 2 with CTA pairs
-        (cta_group::2 MMAs over two SMs, each CTA staging half of the weights)."""
+        (cta_group::2 MMAs over two SMs, each CTA staging half of the weights); 4: 64 channels with the three taps of a filter row
+        fused into one MMA (N = 192; csrc/az_resnet_wide.cu - takes variant 0's packed weights)."""
         from . import _lib
 
         self.lib = _lib.load()
@@ -425,6 +426,7 @@ class TensorCoreTrunk:
         self.variant = variant
         self.num_blocks = model.num_res_blocks
         self.num_channels = model.num_channels
+        assert variant in (0, 1, 2, 3, 4)
         assert variant in (0, 3) or self.num_channels == 64
         assert variant not in (2, 3) or self.num_blocks <= 5 or self.num_channels == 128
         pair = variant == 3
@@ -678,7 +680,7 @@ class InferenceNet(nn.Module):
         if self.trunk is not None:
             if isinstance(self.trunk, TensorCoreCNN):
                 return "k_cnn_conv + k_cnn_fc"
-            return "k_resnet_pipe" if self.trunk.variant != 1 else "k_resnet_trunk"
+            return {1: "k_resnet_trunk", 4: "k_resnet_wide"}.get(self.trunk.variant, "k_resnet_pipe")
         return "k_encode + cuDNN/cuBLAS (torch)"
 
     @torch.no_grad()

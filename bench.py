@@ -344,7 +344,7 @@ def net_extra(args, spec: str, device_index: int, peaks: dict):
     E, S = 16384, args.sims
     dt = torch_dtype(dname)
     search = az.AlphaZeroSearch(model=model, num_simulations=S, device=device_index, inference_dtype=dt,
-                                trunk_variant={"pingpong": 1, "pipe": 0, "pipe2": 2, "pair": 3}.get(variant))
+                                trunk_variant={"pingpong": 1, "pipe": 0, "pipe2": 2, "pair": 3, "wide": 4}.get(variant))
     eng = search.engine_for(E)
     eng.reset_games()
     n = args.extra_steps

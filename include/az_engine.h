@@ -272,7 +272,9 @@ typedef struct az_resnet_desc {
     int32_t variant;         /* 0: layer-pipelined kernel (csrc/az_resnet_pipe.cu; weights: models.py:pack_trunk_weights_pipe);
                                 1: ping-pong kernel, 64 channels only (csrc/az_conv.cu; weights: models.py:pack_trunk_weights);
                                 2: variant 0 with two 4-position CTAs per SM, 64 channels, at most 5 blocks;
-                                3: variant 2 with CTA pairs (cta_group::2; weights packed as halves, pack_trunk_weights_pipe(pair=True)) */
+                                3: variant 2 with CTA pairs (cta_group::2; weights packed as halves, pack_trunk_weights_pipe(pair=True));
+                                4: 64 channels, the three taps of a filter row fused into one MMA (N = 192), two tiles ping-pong
+                                   (csrc/az_resnet_wide.cu; same packed weights as variant 0) */
     const void *trunk_w;     /* packed 16-bit MMA operands */
     const float *trunk_b;    /* [1 + 2*num_blocks][num_channels] */
     const void *head_conv_w; /* [48 out] x num_channels x 9 taps, packed like trunk_w (models.py:pack_head_weights) */

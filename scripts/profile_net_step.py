@@ -22,8 +22,11 @@ for name in nets:
     elif name == "cnn":
         model = az.CNNModel()
     else:
-        b, c = name.replace("resnet", "").split("x")
+        base, _, v = name.partition(":v")  # "resnet4x64:v4" = trunk_variant 4
+        b, c = base.replace("resnet", "").split("x")
         model = az.ResNet(int(b), int(c))
+        if v:
+            kw = dict(trunk_variant=int(v))
     search = az.AlphaZeroSearch(model=model, num_simulations=64, use_cuda_graph=False, **kw)
     eng = search.engine_for(E)
     eng.reset_games()

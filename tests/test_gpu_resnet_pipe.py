@@ -38,9 +38,12 @@ def _emulated(model, x, dtype):
     (-64, 0, 4, torch.bfloat16), (-64, 1, 7, torch.float16), (-64, 4, 64, torch.float16), (-64, 4, 3001, torch.bfloat16), (-64, 5, 2381, torch.float16),
     (-640, 0, 4, torch.bfloat16), (-640, 1, 7, torch.float16), (-640, 1, 8, torch.float16), (-640, 4, 64, torch.float16), (-640, 4, 3001, torch.bfloat16),
     (-640, 5, 2381, torch.float16),
-    (-1280, 0, 4, torch.bfloat16), (-1280, 1, 5, torch.float16), (-1280, 2, 1000, torch.bfloat16), (-1280, 9, 701, torch.float16)])
+    (-1280, 0, 4, torch.bfloat16), (-1280, 1, 5, torch.float16), (-1280, 2, 1000, torch.bfloat16), (-1280, 9, 701, torch.float16),
+    (-192, 0, 4, torch.bfloat16), (-192, 0, 9, torch.float16), (-192, 1, 7, torch.float16), (-192, 1, 8, torch.bfloat16), (-192, 4, 64, torch.float16),
+    (-192, 4, 3001, torch.bfloat16), (-192, 4, 2381, torch.float16), (-192, 11, 1190, torch.float16), (-192, 2, 593, torch.float16)])
 def test_resnet_pipe_kernel_matches_pytorch(channels, blocks, n, dtype):
-    variant = {64: 0, 128: 0, -64: 2, -640: 3, -1280: 3}[channels]  # -64: two CTAs per SM; -640 / -1280: CTA pairs (64 / 128 channels)
+    # -64: two CTAs per SM; -640 / -1280: CTA pairs (64 / 128 channels); -192: filter rows fused, N = 192 (csrc/az_resnet_wide.cu)
+    variant = {64: 0, 128: 0, -64: 2, -640: 3, -1280: 3, -192: 4}[channels]
     channels = 128 if channels in (128, -1280) else 64
     torch.manual_seed(13 * blocks + n)
     torch.backends.cudnn.allow_tf32 = False
@@ -53,7 +56,7 @@ def test_resnet_pipe_kernel_matches_pytorch(channels, blocks, n, dtype):
     assert live.any()
     x = eng.gather_leaves(LAYOUT_PLANES_F32)
     net = InferenceNet(model, dtype=dtype, trunk_variant=variant)
-    assert net.kernel_name == "k_resnet_pipe"
+    assert net.kernel_name == ("k_resnet_wide" if variant == 4 else "k_resnet_pipe")
     logits, values = net.forward_leaves(eng)
     torch.cuda.synchronize()
     with torch.no_grad():
