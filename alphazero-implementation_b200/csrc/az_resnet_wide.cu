@@ -25,7 +25,8 @@
 // At a batch boundary the next batch's stem input of a tile is staged by that tile's last trunk epilogue (the t buffer is free
 // by then), so the stem MMAs follow the head MMAs without a CTA-wide barrier.
 // Roles: warps 0..7 epilogue (thread = one pixel row of a tile; warps 0..3 take output channels 0..31, warps 4..7 32..63),
-// warp 8 issues the MMAs (one elected lane), warp 9 streams the weights.
+// warp 8 issues the MMAs (one elected lane), warp 9 streams the weights, warp 10 stages the stem inputs, warp 11 runs the two
+// fully connected layers of the heads - the last two keep batch boundaries off the epilogue warps, which bound this kernel.
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -50,18 +51,35 @@ constexpr uint32_t LBO_W = 128, SBO_W = 256;           // canonical K-major [N][
 constexpr int NHC = 48, NHU = 35;      // head conv channels per dx block: 32 policy (1x1, centre tap) + 3 value (3x3) + padding
 constexpr uint32_t DY_BYTES = 3 * C * 16 * 2, PIECE_BYTES = 3 * DY_BYTES;              // [192][16], three filter rows
 constexpr uint32_t HEAD_DY_BYTES = 3 * NHC * 16 * 2, HEAD_PIECE_BYTES = 3 * HEAD_DY_BYTES;
+#ifndef WIDE_TMEM_A
+#define WIDE_TMEM_A false
+#endif
 constexpr int NS = 6;                  // ring stages
-constexpr int EW = 8, THREADS = (EW + 2) * 32, ETHREADS = EW * 32;
+constexpr bool TMEM_A = WIDE_TMEM_A;        // centre filter row's A operand from tensor memory: measured slower (608 vs 581 us), kept as a switch
+#ifndef WIDE_EW
+#define WIDE_EW 8
+#endif
+constexpr int EW = WIDE_EW, THREADS = (EW + 4) * 32;   // + issuer, weight producer, stager, FC warp
+constexpr int CPW = C / (EW / 4), NCC = CPW / 16;   // output channels per epilogue warp (4 warps cover the 128 rows), 16-channel chunks of them
+static_assert(EW == 8 || EW == 16, "epilogue warps: 2 or 4 per 32 accumulator lanes");
 constexpr int MAX_CONV = 23;           // 11 blocks
-constexpr uint32_t TILE_COLS = 256;    // tensor-memory columns between the two accumulator tiles (192 used)
+constexpr uint32_t TILE_COLS = 192;    // tensor-memory columns of an accumulator tile: columns 0..383 = the two tiles
+// columns 384..511: the activations once more, 16-bit pairs, [tile][x | t][32 columns] - the A operand of the centre filter row
+// (no row shift: it can come from tensor memory, which takes 8 of its 14 KB per MMA off the shared-memory crossbar)
+constexpr uint32_t ACT_COLS = 384, ACT_BUF = 32;
 constexpr uint32_t OFF_RING = 2 * BUF_BYTES;
 constexpr uint32_t OFF_HACT = OFF_RING + NS * PIECE_BYTES;
 constexpr uint32_t HACT_BYTES = POS * NHU * 42 * 4;
 constexpr uint32_t OFF_RED = OFF_HACT + HACT_BYTES;
-constexpr uint32_t OFF_BIAS = OFF_RED + EW * POS * 8 * 4;
+constexpr uint32_t OFF_BIAS = OFF_RED;
 constexpr uint32_t OFF_BARS = OFF_BIAS + (MAX_CONV * C + NHC) * 4;
-constexpr int NBARS = 2 * NS + 4;      // full[NS] empty[NS] mma_done[2] epi_done[2]
+constexpr int NBARS = 2 * NS + 10;     // full[NS] empty[NS] mma_done[2] epi_done[2] stage_go[2] stem_ready[2] hact_ready hact_free
 constexpr uint32_t SMEM_BYTES = OFF_BARS + NBARS * 8 + 16;
+#ifdef WIDE_TRACE
+constexpr uint32_t SMEM_LAUNCH = SMEM_BYTES + 3 * 340 * 8;
+#else
+constexpr uint32_t SMEM_LAUNCH = SMEM_BYTES;
+#endif
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(LEAD + TPOS * PIX <= 128, "a tile's positions must fit its 128 rows");
 static_assert(OFF_HACT % 16 == 0 && OFF_BIAS % 16 == 0 && OFF_BARS % 8 == 0, "alignment");
@@ -83,7 +101,24 @@ struct RowRec {
     uint32_t meta;  // bit 0: row of a position that exists and waits for an evaluation, bit 1: side to move, bit 2: board cell, bits 8..: bit index
 };
 
-template <bool F16>
+#ifdef WIDE_TRACE
+// timeline of CTA 0 (timing study only): each traced warp keeps (code, clock) pairs in shared memory (a store and a clock read
+// per event - nothing that waits), copied out when the kernel ends.  code = layer * 100 + tile * 10 + phase
+constexpr int TRACE_WARPS = 3, TRACE_CAP = 340;
+__device__ unsigned int g_trace[TRACE_WARPS * TRACE_CAP * 2];
+#define TRACE(slot, l, t, phase)                                                                 \
+    do {                                                                                          \
+        if (blockIdx.x == 0 && lane == 0 && tr_n < TRACE_CAP) {                                   \
+            s_trace[((slot) * TRACE_CAP + tr_n) * 2] = (unsigned int)((l) * 100 + (t) * 10 + (phase)); \
+            s_trace[((slot) * TRACE_CAP + tr_n) * 2 + 1] = (unsigned int)clock64();               \
+            ++tr_n;                                                                               \
+        }                                                                                         \
+    } while (0)
+#else
+#define TRACE(slot, l, t, phase)
+#endif
+
+template <bool F16, bool S16>
 __global__ void __launch_bounds__(THREADS, 1)
 k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ leaf_bb1, const uint8_t *__restrict__ leaf_player,
               const uint8_t *__restrict__ leaf_status, const int32_t *__restrict__ eval_list, const int32_t *__restrict__ eval_count,
@@ -94,20 +129,27 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *bufX = smem, *bufT = smem + BUF_BYTES;
     float *hact = reinterpret_cast<float *>(smem + OFF_HACT);
-    float *red = reinterpret_cast<float *>(smem + OFF_RED);
     float *s_bias = reinterpret_cast<float *>(smem + OFF_BIAS);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BARS);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BARS + NBARS * 8);
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+#ifdef WIDE_TRACE
+    unsigned int *s_trace = reinterpret_cast<unsigned int *>(smem + SMEM_BYTES);
+    int tr_n = 0;
+#endif
     // position j of a batch is slot eval_list[j], j < *eval_count: only the leaves that wait for an evaluation are processed
     const long long n = eval_list ? (long long)__ldg(eval_count) : n_slots;
     const int n_conv = 1 + 2 * num_blocks, n_layers = n_conv + 1;
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS), mma_done0 = smem_u32(bars + 2 * NS), epi_done0 = smem_u32(bars + 2 * NS + 2);
+    const uint32_t stage_go0 = epi_done0 + 16, stem_ready0 = stage_go0 + 16, hact_ready = stem_ready0 + 16, hact_free = hact_ready + 8;
     const uint32_t ring0 = smem_u32(smem + OFF_RING);
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
     if (tid == 32) {
         for (int i = 0; i < 2 * NS + 2; ++i) mbar_init(smem_u32(bars + i), 1u);
         for (int i = 0; i < 2; ++i) mbar_init(epi_done0 + i * 8, (uint32_t)EW);  // one arrival per epilogue warp
+        for (int i = 0; i < 4; ++i) mbar_init(stage_go0 + i * 8, 1u);            // stage_go[2] (tensor core), stem_ready[2] (stager warp)
+        mbar_init(hact_ready, (uint32_t)EW);
+        mbar_init(hact_free, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t i = tid; i < 2 * BUF_BYTES / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -141,14 +183,9 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
         const uint32_t one = F16 ? 0x3C00u : 0x3F80u;
         *reinterpret_cast<uint4 *>(bufT + (GUARD + r) * ROWB) = make_uint4(emp * one | (mine * one) << 16, theirs * one, 0u, 0u);
     };
-    __syncthreads();  // buffers zeroed before the first batch's stem input goes in
-    if (tid < 128 && (long long)blockIdx.x < n_batches) {
-#pragma unroll
-        for (int t = 0; t < TILES; ++t) stage_row(load_rec((long long)blockIdx.x, t * 128 + (int)tid), t * 128 + (int)tid);
-    }
     fence_async_smem();
     fence_before();
-    __syncthreads();  // barriers initialised, tensor memory allocated, biases and the first stem input staged
+    __syncthreads();  // barriers initialised, tensor memory allocated, buffers zeroed, biases staged
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -165,18 +202,23 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                 for (int i = 0; i < pieces; ++i, ++g) {
                     const uint32_t st = g % NS;
                     if (g >= NS) mbar_wait(empty0 + st * 8, ((g / NS) - 1u) & 1u);  // both tiles' MMAs of the previous use have read the stage
+#if defined(WIDE_EXP) && (WIDE_EXP & 4)
+                    if (elect_one()) { if (g < NS) bulk_load(ring0 + st * PIECE_BYTES, src + (size_t)i * bytes, bytes, full0 + st * 8); else mbar_arrive(full0 + st * 8); }
+#else
                     if (elect_one()) bulk_load(ring0 + st * PIECE_BYTES, src + (size_t)i * bytes, bytes, full0 + st * 8);
+#endif
                     __syncwarp();
                 }
             }
         }
     } else if (warp == EW) {
         // ===== MMA issuer (converged; one elected lane issues).  Order: layer by layer, tile 0 then tile 1 =====
-        uint32_t g = 0, idx = 0;  // pieces consumed; tile-layers issued per tile
-        for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+        uint32_t g = 0, idx = 0, it = 0;  // pieces consumed; tile-layers issued per tile; batches
+        for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
             for (int l = 0; l < n_layers; ++l, ++idx) {
                 const bool head = l >= n_conv;
-                const uint32_t src = l == 0 ? aT : ((head || (l & 1)) ? aX : aT);  // conv1 (odd l) and the heads read x; conv2 reads t
+                const int src_t = (l == 0 || !(head || (l & 1))) ? 1 : 0;           // conv1 (odd l) and the heads read x; stem and conv2 read t
+                const uint32_t src = src_t ? aT : aX;
                 const uint32_t idesc = head ? instr_desc(128, 3 * NHC, F16) : instr_desc(128, 3 * C, F16);
                 const uint64_t a_desc = smem_desc(src, LBO_A, SBO_A);
                 const int ksteps = l == 0 ? 1 : KS;
@@ -185,8 +227,11 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                 for (int t = 0; t < TILES; ++t) {
                     // the tile's previous epilogue is through: its accumulator columns are read, this layer's input rows are written
                     // (after a batch's last trunk layer: the next batch's stem input as well)
+                    TRACE(0, l, t, 0);  // issuer: about to wait for the tile's previous epilogue
+                    if (l == 0) mbar_wait(stem_ready0 + t * 8, it & 1u);  // the stager warp has written this batch's stem input
                     if (idx > 0) mbar_wait(epi_done0 + t * 8, (idx - 1u) & 1u);
                     fence_after();
+                    TRACE(0, l, t, 1);  // issuer: epilogue seen
 #pragma unroll 1
                     for (int ks = 0; ks < ksteps; ++ks) {
                         const uint32_t gg = g + (uint32_t)ks, st = gg % NS;
@@ -199,21 +244,31 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
 #pragma unroll
                             for (int dy = 0; dy < 3; ++dy) {
                                 const uint64_t ad = a_desc + (uint64_t)(int64_t)((dy - 1) * PW + t * 128 + ks * (int)(2 * LBO_A >> 4));
-                                umma(tmem_base + (uint32_t)t * TILE_COLS, ad, bd + (uint64_t)(dy * dy_units), idesc, (ks | dy) > 0);
+                                if (TMEM_A && dy == 1 && l > 0)
+                                    umma_ts(tmem_base + (uint32_t)t * TILE_COLS, tmem_base + ACT_COLS + (uint32_t)(2 * t + src_t) * ACT_BUF + (uint32_t)ks * 8u,
+                                            bd + (uint64_t)(dy * dy_units), idesc, (ks | dy) > 0);
+                                else
+                                    umma(tmem_base + (uint32_t)t * TILE_COLS, ad, bd + (uint64_t)(dy * dy_units), idesc, (ks | dy) > 0);
                             }
                             if (t == TILES - 1) umma_commit(empty0 + st * 8);
                         }
                         __syncwarp();
                     }
-                    if (elect_one()) umma_commit(mma_done0 + t * 8);
+                    if (elect_one()) {
+                        umma_commit(mma_done0 + t * 8);
+                        // a batch's last trunk layer: when it is complete nothing reads the tile's rows of t any more - the stager
+                        // warp may write the next batch's stem input there
+                        if (l == n_conv - 1) umma_commit(stage_go0 + t * 8);
+                    }
                     __syncwarp();
+                    TRACE(0, l, t, 2);  // issuer: tile-layer issued and committed
                 }
                 g += (uint32_t)ksteps;
             }
         }
-    } else {
-        // ===== epilogue warps: thread = one pixel row of a tile, 32 of the 64 output channels =====
-        const int half = (int)(warp >> 2);
+    } else if (warp < EW) {
+        // ===== epilogue warps: thread = one pixel row of a tile, CPW of the 64 output channels =====
+        const int half = (int)(warp >> 2);  // which CPW channels
         const int row_in_tile = (int)((warp & 3u) * 32u + lane);
         int pos[TILES], yy[TILES], xx[TILES];
         bool valid[TILES];
@@ -226,64 +281,59 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
         }
         const uint32_t lane_addr = tmem_base + (((warp & 3u) * 32u) << 16);
         const int lm = (int)((lane + 31u) & 31u), lp = (int)((lane + 1u) & 31u);  // left / right neighbour row (see the header)
-        uint32_t idx = 0;
-        for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-            const long long next = batch + gridDim.x;
-            const bool stage_next = half == 0 && next < n_batches;
-            RowRec rec[TILES];
-            if (stage_next) {
-#pragma unroll
-                for (int t = 0; t < TILES; ++t) rec[t] = load_rec(next, t * 128 + row_in_tile);
-            }
+        uint32_t idx = 0, it = 0;
+        for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
             for (int l = 0; l < n_conv; ++l, ++idx) {
                 uint8_t *dst = (l & 1) ? bufT : bufX;          // stem and conv2 write x, conv1 writes t
                 const bool skip = l > 0 && !(l & 1);            // conv2: + x, in place
-                float2 bias2[16];  // this warp's 32 output channels
+                float2 bias2[CPW / 2];  // this warp's output channels
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 b4 = *reinterpret_cast<const float4 *>(s_bias + l * C + half * 32 + 4 * i);
+                for (int i = 0; i < CPW / 4; ++i) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(s_bias + l * C + half * CPW + 4 * i);
                     bias2[2 * i] = make_float2(b4.x, b4.y);
                     bias2[2 * i + 1] = make_float2(b4.z, b4.w);
                 }
 #pragma unroll
                 for (int t = 0; t < TILES; ++t) {
-                    const uint32_t acc = lane_addr + (uint32_t)t * TILE_COLS + (uint32_t)half * 32u;
+                    const uint32_t acc = lane_addr + (uint32_t)t * TILE_COLS + (uint32_t)(half * CPW);
+                    if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 0);  // epilogue: about to wait for the MMAs
                     mbar_wait(mma_done0 + t * 8, idx & 1u);
                     fence_after();
-                    uint32_t vm[2][16], v0[2][16], vp[2][16];
-#if defined(WIDE_EXP) && (WIDE_EXP & 2)
-                    tmem_ld16_issue(acc + C, v0[0]);
-                    tmem_ld16_issue(acc + C + 16, v0[1]);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { vm[0][i] = v0[0][i] + 1; vp[0][i] = v0[0][i] + 2; vm[1][i] = v0[1][i] + 1; vp[1][i] = v0[1][i] + 2; }
-#else
-                    tmem_ld16_issue(acc, vm[0]);
-                    tmem_ld16_issue(acc + C, v0[0]);
-                    tmem_ld16_issue(acc + 2 * C, vp[0]);
-                    tmem_ld16_issue(acc + 16, vm[1]);
-                    tmem_ld16_issue(acc + C + 16, v0[1]);
-                    tmem_ld16_issue(acc + 2 * C + 16, vp[1]);
-                    tmem_ld_wait();
+                    if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 1);  // MMAs complete
+#if defined(WIDE_EXP) && (WIDE_EXP & 8)
+                    if (true) { fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(epi_done0 + t * 8); continue; }
 #endif
+                    uint32_t vm[NCC][16], v0[NCC][16], vp[NCC][16], pk[16];
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
+                    for (int cc = 0; cc < NCC; ++cc) {
+                        tmem_ld16_issue(acc + 16 * cc, vm[cc]);
+                        tmem_ld16_issue(acc + C + 16 * cc, v0[cc]);
+                        tmem_ld16_issue(acc + 2 * C + 16 * cc, vp[cc]);
+                    }
+                    tmem_ld_wait();
+                    if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 2);  // accumulators in registers
+#pragma unroll
+                    for (int cc = 0; cc < NCC; ++cc) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            uint8_t *p = dst + (uint32_t)(half * 4 + cc * 2 + h) * LBO_A + row_off[t];
+                            uint8_t *p = dst + (uint32_t)(half * (CPW / 8) + cc * 2 + h) * LBO_A + row_off[t];
                             float2 f[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int j = h * 8 + 2 * i;
-#if defined(WIDE_EXP) && (WIDE_EXP & 1)
-                                const float2 m = make_float2(__uint_as_float(vm[cc][j]), __uint_as_float(vm[cc][j + 1]));
-                                const float2 q = make_float2(__uint_as_float(vp[cc][j]), __uint_as_float(vp[cc][j + 1]));
-#else
-                                const float2 m = make_float2(__shfl_sync(0xFFFFFFFFu, __uint_as_float(vm[cc][j]), lm),
-                                                             __shfl_sync(0xFFFFFFFFu, __uint_as_float(vm[cc][j + 1]), lm));
-                                const float2 q = make_float2(__shfl_sync(0xFFFFFFFFu, __uint_as_float(vp[cc][j]), lp),
-                                                             __shfl_sync(0xFFFFFFFFu, __uint_as_float(vp[cc][j + 1]), lp));
-#endif
+                                float2 m, q;
+                                if (S16) {
+                                    // the neighbours' partial sums travel as fp16 pairs: one shuffle per direction for two channels
+                                    // (the crossbar, not the tensor core, bounds this kernel); 11 significand bits against the 8 / 11 the
+                                    // sum is rounded to anyway
+                                    m = unpack16<true>(__shfl_sync(0xFFFFFFFFu, pack16_sat(__uint_as_float(vm[cc][j]), __uint_as_float(vm[cc][j + 1])), lm));
+                                    q = unpack16<true>(__shfl_sync(0xFFFFFFFFu, pack16_sat(__uint_as_float(vp[cc][j]), __uint_as_float(vp[cc][j + 1])), lp));
+                                } else {
+                                    m = make_float2(__shfl_sync(0xFFFFFFFFu, __uint_as_float(vm[cc][j]), lm),
+                                                    __shfl_sync(0xFFFFFFFFu, __uint_as_float(vm[cc][j + 1]), lm));
+                                    q = make_float2(__shfl_sync(0xFFFFFFFFu, __uint_as_float(vp[cc][j]), lp),
+                                                    __shfl_sync(0xFFFFFFFFu, __uint_as_float(vp[cc][j + 1]), lp));
+                                }
                                 const float2 c0 = make_float2(__uint_as_float(v0[cc][j]), __uint_as_float(v0[cc][j + 1]));
                                 f[i] = fadd2(fadd2(fadd2(c0, m), q), bias2[cc * 8 + h * 4 + i]);
                             }
@@ -297,28 +347,33 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                             uint4 o = make_uint4(0, 0, 0, 0);
                             if (valid[t]) o = make_uint4(pack16_relu<F16>(f[0]), pack16_relu<F16>(f[1]), pack16_relu<F16>(f[2]), pack16_relu<F16>(f[3]));
                             *reinterpret_cast<uint4 *>(p) = o;
+                            pk[cc * 8 + h * 4] = o.x; pk[cc * 8 + h * 4 + 1] = o.y; pk[cc * 8 + h * 4 + 2] = o.z; pk[cc * 8 + h * 4 + 3] = o.w;
                         }
                     }
-                    // a batch's last trunk layer: t is free (its last reader, this layer's MMAs, is complete) - the tile's rows of
-                    // the next batch's stem input go in now
-                    if (l == n_conv - 1 && stage_next) stage_row(rec[t], t * 128 + row_in_tile);
+                    if (TMEM_A && EW == 8) {
+                        tmem_st16(lane_addr + ACT_COLS + (uint32_t)(2 * t + (l & 1)) * ACT_BUF + (uint32_t)half * 16u, pk);
+                        tmem_st_wait();
+                    }
                     // this warp's part of the tile is in place for the tensor core and its accumulator reads are complete
+                    if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 3);  // outputs computed and stored
                     fence_before();
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(epi_done0 + t * 8);
+                    if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 4);  // arrived
                 }
             }
             // ---- heads: [POS][35][42] fp32 in the Flatten() order of NCHW.  Policy channels (1x1 conv) have weights in the centre
             // tap only: their dx = -1 / +1 blocks are zero.  Warps 0..3: policy 0..15 and the 3 value channels; warps 4..7: policy 16..31.
             const float *hb = s_bias + n_conv * C;
+            if (it > 0) mbar_wait(hact_free, (it - 1u) & 1u);  // the FC warp is through with the previous batch's head activations
 #pragma unroll
             for (int t = 0; t < TILES; ++t) {
                 const uint32_t acc = lane_addr + (uint32_t)t * TILE_COLS;
                 mbar_wait(mma_done0 + t * 8, idx & 1u);
                 fence_after();
                 uint32_t v[16], wm[16], w0[16], wp[16];
-                tmem_ld16_issue(acc + NHC + (uint32_t)half * 16u, v);
+                if (half < 2) tmem_ld16_issue(acc + NHC + (uint32_t)half * 16u, v);
                 if (half == 0) {
                     tmem_ld16_issue(acc + 32, wm);
                     tmem_ld16_issue(acc + NHC + 32, w0);
@@ -334,7 +389,7 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                         val[c] = ((__uint_as_float(w0[c]) + m) + q) + hb[32 + c];
                     }
                 }
-                if (valid[t]) {
+                if (valid[t] && half < 2) {
                     float *o = hact + pos[t] * NHU * 42 + yy[t] * c4::W + xx[t];
 #pragma unroll
                     for (int c = 0; c < 16; ++c) o[(half * 16 + c) * 42] = fmaxf(__uint_as_float(v[c]) + hb[half * 16 + c], 0.f);
@@ -348,34 +403,59 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                 if (lane == 0) mbar_arrive(epi_done0 + t * 8);
             }
             ++idx;
-            asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
-            // ---- both FC layers on CUDA cores: thread t takes inputs k = t, t + ETHREADS, ...: every FC weight is read once per
-            // CTA (coalesced) and used for POS positions; acc[p][j], j = 7 is the value head
+            // both tiles' head activations are in place for the FC warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(hact_ready);
+        }
+    } else if (warp == EW + 2) {
+        // ===== stager warp: the stem input of every batch (lane = 4 pixel rows of a tile).  The first batch's goes in at once, the
+        // next batch's when the tensor core reports the tile's last trunk layer complete (stage_go) =====
+        uint32_t it = 0;
+        for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
+            RowRec rec[TILES][4];
+#pragma unroll
+            for (int t = 0; t < TILES; ++t)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rec[t][j] = load_rec(batch, t * 128 + j * 32 + (int)lane);
+#pragma unroll
+            for (int t = 0; t < TILES; ++t) {
+                if (it > 0) mbar_wait(stage_go0 + t * 8, (it - 1u) & 1u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) stage_row(rec[t][j], t * 128 + j * 32 + (int)lane);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(stem_ready0 + t * 8);
+            }
+        }
+    } else if (warp == EW + 3) {
+        // ===== FC warp: both fully connected layers on CUDA cores, off the epilogue warps' critical path.  Lane L takes inputs
+        // k = L, L + 32, ...: every FC weight is read once per CTA (coalesced) and used for POS positions; acc[p][j], j = 7 = value head
+        uint32_t it = 0;
+        for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
+            mbar_wait(hact_ready, it & 1u);
             float acc[POS * 8];
 #pragma unroll
             for (int i = 0; i < POS * 8; ++i) acc[i] = 0.f;
-#pragma unroll
-            for (int k0 = 0; k0 < 32 * 42; k0 += ETHREADS) {
-                const int k = k0 + (int)tid;
-                const bool in = k < 32 * 42;
-                const int kk = in ? k : 0;
+#pragma unroll 6
+            for (int k = (int)lane; k < 32 * 42; k += 32) {
                 float wj[7];
 #pragma unroll
-                for (int j = 0; j < 7; ++j) wj[j] = in ? __ldg(fc_policy_w + j * (32 * 42) + kk) : 0.f;
+                for (int j = 0; j < 7; ++j) wj[j] = __ldg(fc_policy_w + j * (32 * 42) + k);
 #pragma unroll
                 for (int p = 0; p < POS; ++p) {
-                    const float xv = hact[p * NHU * 42 + kk];
+                    const float xv = hact[p * NHU * 42 + k];
 #pragma unroll
                     for (int j = 0; j < 7; ++j) acc[p * 8 + j] = fmaf(wj[j], xv, acc[p * 8 + j]);
                 }
             }
-            {
-                const bool in = tid < 3 * 42;
-                const int kk = in ? (int)tid : 0;
-                const float wv = in ? __ldg(fc_value_w + kk) : 0.f;
+#pragma unroll 1
+            for (int k = (int)lane; k < 3 * 42; k += 32) {
+                const float wv = __ldg(fc_value_w + k);
 #pragma unroll
-                for (int p = 0; p < POS; ++p) acc[p * 8 + 7] = fmaf(wv, hact[p * NHU * 42 + 32 * 42 + kk], acc[p * 8 + 7]);
+                for (int p = 0; p < POS; ++p) acc[p * 8 + 7] = fmaf(wv, hact[p * NHU * 42 + 32 * 42 + k], acc[p * 8 + 7]);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(hact_free);  // the head activations are consumed
             // warp reduction by recursive halving: each step exchanges half of the values; lane L ends with the total of index L
             constexpr int V = POS * 8;
             static_assert(V == 32, "one value per lane after the halving");
@@ -389,35 +469,50 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                     acc[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, h);
                 }
             }
-            red[warp * V + lane] = acc[0];
-            asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
-            if (tid < V) {
-                float sum = 0.f;
-#pragma unroll
-                for (int w8 = 0; w8 < EW; ++w8) sum += red[w8 * V + tid];
-                const int p = (int)tid >> 3, j = (int)tid & 7;
-                const long long gp = batch * POS + p;
-                if (gp < n) {
-                    const long long slot = eval_list ? (long long)__ldg(eval_list + gp) : gp;
-                    if (j < 7) {
-                        logits[slot * 7 + j] = sum + __ldg(fc_policy_b + j);
-                    } else {
-                        const float v = tanhf(sum + __ldg(fc_value_b));
-                        values[slot * 2] = v;
-                        values[slot * 2 + 1] = -v;
-                    }
+            const float sum = acc[0];
+            const int p = (int)lane >> 3, j = (int)lane & 7;
+            const long long gp = batch * POS + p;
+            if (gp < n) {
+                const long long slot = eval_list ? (long long)__ldg(eval_list + gp) : gp;
+                if (j < 7) {
+                    logits[slot * 7 + j] = sum + __ldg(fc_policy_b + j);
+                } else {
+                    const float v = tanhf(sum + __ldg(fc_value_b));
+                    values[slot * 2] = v;
+                    values[slot * 2 + 1] = -v;
                 }
             }
         }
     }
     fence_before();
     __syncthreads();
+#ifdef WIDE_TRACE
+    if (blockIdx.x == 0) {
+        if (lane == 0 && (warp == EW || warp == 0 || warp == EW - 1)) {
+            const int slot = warp == EW ? 0 : (warp == 0 ? 1 : 2);
+            for (int i = tr_n; i < TRACE_CAP; ++i) s_trace[(slot * TRACE_CAP + i) * 2] = 0xFFFFFFFFu;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < TRACE_WARPS * TRACE_CAP * 2; i += THREADS) g_trace[i] = s_trace[i];
+    }
+#endif
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
 
 extern "C" {
+
+#ifdef WIDE_TRACE
+/* timing study: copy out the timeline of CTA 0 of the last launch: [3 warps][TRACE_CAP][code, clock] */
+int32_t az_resnet_wide_trace(unsigned int *out, int32_t cap) {
+    cudaDeviceSynchronize();
+    const int32_t n = TRACE_WARPS * TRACE_CAP * 2;
+    if (cap < n) return -1;
+    cudaMemcpyFromSymbol(out, g_trace, (size_t)n * 4);
+    return n;
+}
+#endif
 
 /* internal: called by az_resnet_forward_leaves_v2 (csrc/az_conv.cu), variant 4.  Takes the packed weights of the layer-pipelined
  * kernel (az_resnet_pipe_weight_bytes(num_blocks, 64) bytes, models.py:pack_trunk_weights_pipe). */
@@ -436,15 +531,23 @@ int32_t az_resnet_wide_launch(az_engine *engine, const az_resnet_desc *d, float 
     const int dev = az_device(engine);
     if (dev < 0 || dev >= 64 || cudaSetDevice(dev) != cudaSuccess) return AZ_E_CUDA;
     if (!attr_set[dev]) {
-        if (cudaFuncSetAttribute(k_resnet_wide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
-        if (cudaFuncSetAttribute(k_resnet_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return AZ_E_CUDA;
+        if (cudaFuncSetAttribute(k_resnet_wide<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LAUNCH) != cudaSuccess) return AZ_E_CUDA;
+        if (cudaFuncSetAttribute(k_resnet_wide<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LAUNCH) != cudaSuccess) return AZ_E_CUDA;
+        if (cudaFuncSetAttribute(k_resnet_wide<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LAUNCH) != cudaSuccess) return AZ_E_CUDA;
+        if (cudaFuncSetAttribute(k_resnet_wide<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LAUNCH) != cudaSuccess) return AZ_E_CUDA;
         attr_set[dev] = true;
     }
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return AZ_E_CUDA;
     const int batches = (n + POS - 1) / POS;
-    auto kern = d->operand_format == AZ_FMT_F16 ? k_resnet_wide<true> : k_resnet_wide<false>;
-    kern<<<batches < sms ? batches : sms, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(
+    static int s16 = -1;
+    if (s16 < 0) {
+        const char *e = getenv("AZ_WIDE_SHFL16");
+        s16 = e ? atoi(e) : 0;
+    }
+    auto kern = d->operand_format == AZ_FMT_F16 ? (s16 ? k_resnet_wide<true, true> : k_resnet_wide<true, false>)
+                                                : (s16 ? k_resnet_wide<false, true> : k_resnet_wide<false, false>);
+    kern<<<batches < sms ? batches : sms, THREADS, SMEM_LAUNCH, (cudaStream_t)stream>>>(
         bb0, bb1, player, status, elist, ecount, (long long)n, (const uint8_t *)d->trunk_w, d->trunk_b, d->num_blocks, (const uint8_t *)d->head_conv_w,
         d->head_conv_b, d->fc_policy_w, d->fc_policy_b, d->fc_value_w, d->fc_value_b, logits, values);
     return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;

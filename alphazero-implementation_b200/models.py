@@ -593,11 +593,11 @@ class InferenceNet(nn.Module):
             if isinstance(m, CNNModel) and dtype in (torch.bfloat16, torch.float16) and use_tensor_core_kernels:
                 self.trunk = TensorCoreCNN(m, torch.device(device), dtype)  # hand-written tcgen05 kernels (csrc/az_cnn.cu)
             if isinstance(m, ResNet) and m.num_channels in (64, 128) and m.num_res_blocks <= (9 if m.num_channels == 128 else 11) and dtype in (torch.bfloat16, torch.float16) and use_tensor_core_kernels:
-                # hand-written tcgen05 kernel, trunk + heads: csrc/az_resnet_pipe.cu (variant 0) or csrc/az_conv.cu (variant 1, 64 channels)
-                # measured at 16384 x 800 (profiles/r02_*), 64 channels: layer-pipelined with two 4-position CTAs per SM 0.542 ms (up to
-                # 5 blocks), ping-pong 0.592 ms, layer-pipelined with one 8-position CTA 0.630 ms (the hand-over bubble at each layer
-                # start has nothing to hide behind); 128 channels only fit the layer-pipelined schedule
-                auto = 2 if m.num_res_blocks <= 5 else 1
+                # hand-written tcgen05 kernel, trunk + heads.  64 channels, measured at 16384 positions x 4 blocks (profiles/r02_*):
+                # filter rows fused into N = 192 MMAs, csrc/az_resnet_wide.cu (variant 4) 0.51 ms; layer-pipelined with two 4-position
+                # CTAs per SM, csrc/az_resnet_pipe.cu (variant 2, up to 5 blocks) 0.64 ms; ping-pong, csrc/az_conv.cu (variant 1)
+                # 0.70 ms; layer-pipelined with one 8-position CTA (variant 0) 0.75 ms.  128 channels only fit the layer-pipelined schedule
+                auto = 4 if m.num_res_blocks >= 1 else 2
                 if m.num_channels == 128:
                     variant = 3 if trunk_variant == 3 else 0
                 else:

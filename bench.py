@@ -6,7 +6,7 @@
 
 Workload.  N = 1: BASELINE.json configs[2] — 16384 concurrent games x 800 simulations/move with a bf16 ResNet-style
 policy/value net (4 residual blocks x 64 channels, random init, 25.3 MFLOP per position) in the loop: every simulation step
-is one evaluator launch over the leaves that wait for an evaluation (`k_resnet_pipe`, hand-written tcgen05, leaf gather + heads
+is one evaluator launch over the leaves that wait for an evaluation (`k_resnet_wide`, hand-written tcgen05, leaf gather + heads
 fused) and two tree launches (`k_expand_select`, `k_compact_leaves`).  N > 1: configs[3] — 65536 games sharded over the ranks (65536 / N per GPU, "strong" split of the
 fixed total), and the episodes finished in the timed region are all-gathered over NCCL INSIDE the timed region.
 One STEP = one move step of the self-play loop for every game (episode_generator.py:48-78): 800 simulations per tree, then the
@@ -18,7 +18,7 @@ move (`az_sample_moves`: record the samples, draw the moves, recycle finished ga
           No L2 flush: one step streams the 2.2 GB tree arena (16384 trees x 5608 nodes x 24 B) 800 times, far beyond the 126 MB L2.
 `e2e`     the public API (`EpisodeGenerator.iter_steps`) continuing the same games: per step the uniforms come from pinned host
           memory and the finished episodes + ring counters are read back to pinned host memory (N > 1: plus the all-gather).
-`roofline` of the dominant kernel (`k_resnet_pipe`, tensor-bound): algorithmic FLOPs per launch (evaluated leaves x FLOPs per
+`roofline` of the dominant kernel (`k_resnet_wide`, tensor-bound): algorithmic FLOPs per launch (evaluated leaves x FLOPs per
           position) / the kernel's mean duration, CUDA events around every one of its 800 launches in one extra un-graphed move
           step right after the timed region, against the measured sustained bf16 rate of MEASURED_PEAKS.json.
 `--impl reference`  the CPU arm: the reference algorithm (oracle/c4_oracle.c, the C restatement pinned to the reference's own
@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--extra-steps", type=int, default=3)
     ap.add_argument("--cpu-games", type=int, default=256, help="games of the CPU arm's bounded sample")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
-    ap.add_argument("--trunk-variant", type=int, default=None, help="64-channel ResNet kernel: 2 = layer-pipelined, two CTAs per SM (csrc/az_resnet_pipe.cu, default), 0 = one CTA per SM, 1 = ping-pong (csrc/az_conv.cu)")
+    ap.add_argument("--trunk-variant", type=int, default=None, help="64-channel ResNet kernel: 4 = filter rows fused, N = 192 (csrc/az_resnet_wide.cu, default), 2 = layer-pipelined, two CTAs per SM (csrc/az_resnet_pipe.cu), 0 = one CTA per SM, 1 = ping-pong (csrc/az_conv.cu)")
     return ap.parse_args()
 
 
@@ -520,7 +520,7 @@ def run_b200(args):
     drained = []
     step_ev = [ev0]
     for i in range(K):
-        search.simulate_and_move(eng, u_all[n_pre + i])  # 800 x (k_resnet_pipe, k_expand_select, k_compact_leaves) replayed from a CUDA graph + k_sample_moves
+        search.simulate_and_move(eng, u_all[n_pre + i])  # 800 x (k_resnet_wide, k_expand_select, k_compact_leaves) replayed from a CUDA graph + k_sample_moves
         if (i + 1) % 16 == 0 or i + 1 == K:  # device -> device; the ring holds 2 E + 64 episodes, ~E / 20 finish per step.  Draining
             drained.append(eng.drain_episodes_device(drain_bufs[i // 16]))  # (a host synchronisation) every step left the GPU queue empty at every
         step_ev.append(torch.cuda.Event(enable_timing=True))  # step boundary: any host hiccup there showed up as a 10 % slower step

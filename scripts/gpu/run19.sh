@@ -1,4 +1,3 @@
 #!/bin/bash
-# GPU session: what the epilogue of k_resnet_wide pays for (timing-only builds: results are wrong by construction)
-# exp bit 0: no shuffles; bit 1: one third of the tensor-memory loads
-for e in 1 2 3; do echo "exp $e"; AZ_ENGINE_LIB=$PWD/_ab/libaz_exp$e.so python scripts/profile_net_step.py 16384 resnet4x64:v4 2>&1 | tail -1; done
+# GPU session: tensor core alone (no trunk epilogue), centre row's A operand from shared memory / from tensor memory
+for e in 8_false 8_true; do echo "exp $e"; AZ_ENGINE_LIB=$PWD/_ab/libaz_exp$e.so python scripts/profile_net_step.py 16384 resnet4x64:v4 resnet8x64:v4 2>&1 | grep "E="; done
