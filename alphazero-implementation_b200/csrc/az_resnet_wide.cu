@@ -48,14 +48,11 @@ constexpr int RTOT = ROWS + 2 * GUARD;
 constexpr uint32_t SBO_A = 128, LBO_A = RTOT * ROWB;   // next 8-row group, next K group
 constexpr uint32_t BUF_BYTES = KG * LBO_A;
 constexpr uint32_t LBO_W = 128, SBO_W = 256;           // canonical K-major [N][16]
-constexpr int NHC = 48, NHU = 35;      // head conv channels per dx block: 32 policy (1x1, centre tap) + 3 value (3x3) + padding
+constexpr int NHC = 48, NHU = 35;      // head biases: 32 policy (1x1, centre tap) + 3 value (3x3) + padding
+constexpr int NH = 64;                 // head MMA columns: 32 policy + 3 filter columns x 8 (3 value channels + padding) + 8 padding
 constexpr uint32_t DY_BYTES = 3 * C * 16 * 2, PIECE_BYTES = 3 * DY_BYTES;              // [192][16], three filter rows
-constexpr uint32_t HEAD_DY_BYTES = 3 * NHC * 16 * 2, HEAD_PIECE_BYTES = 3 * HEAD_DY_BYTES;
-#ifndef WIDE_TMEM_A
-#define WIDE_TMEM_A false
-#endif
+constexpr uint32_t HEAD_DY_BYTES = NH * 16 * 2, HEAD_PIECE_BYTES = 3 * HEAD_DY_BYTES;  // [64][16], three filter rows
 constexpr int NS = 6;                  // ring stages
-constexpr bool TMEM_A = WIDE_TMEM_A;        // centre filter row's A operand from tensor memory: measured slower (608 vs 581 us), kept as a switch
 #ifndef WIDE_EW
 #define WIDE_EW 8
 #endif
@@ -63,17 +60,15 @@ constexpr int EW = WIDE_EW, THREADS = (EW + 4) * 32;   // + issuer, weight produ
 constexpr int CPW = C / (EW / 4), NCC = CPW / 16;   // output channels per epilogue warp (4 warps cover the 128 rows), 16-channel chunks of them
 static_assert(EW == 8 || EW == 16, "epilogue warps: 2 or 4 per 32 accumulator lanes");
 constexpr int MAX_CONV = 23;           // 11 blocks
-constexpr uint32_t TILE_COLS = 192;    // tensor-memory columns of an accumulator tile: columns 0..383 = the two tiles
-// columns 384..511: the activations once more, 16-bit pairs, [tile][x | t][32 columns] - the A operand of the centre filter row
-// (no row shift: it can come from tensor memory, which takes 8 of its 14 KB per MMA off the shared-memory crossbar)
-constexpr uint32_t ACT_COLS = 384, ACT_BUF = 32;
+constexpr uint32_t TILE_COLS = 192;    // tensor-memory columns of an accumulator tile: columns 0..383 = the two tiles,
+constexpr uint32_t HEAD_COLS = 384;    // 384..511 = the two tiles' head accumulators (64 columns each)
 constexpr uint32_t OFF_RING = 2 * BUF_BYTES;
 constexpr uint32_t OFF_HACT = OFF_RING + NS * PIECE_BYTES;
 constexpr uint32_t HACT_BYTES = POS * NHU * 42 * 4;
 constexpr uint32_t OFF_RED = OFF_HACT + HACT_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_RED;
 constexpr uint32_t OFF_BARS = OFF_BIAS + (MAX_CONV * C + NHC) * 4;
-constexpr int NBARS = 2 * NS + 10;     // full[NS] empty[NS] mma_done[2] epi_done[2] stage_go[2] stem_ready[2] hact_ready hact_free
+constexpr int NBARS = 2 * NS + 14;     // full[NS] empty[NS] mma_done[2] epi_done[2] stage_go[2] stem_ready[2] hact_ready hact_free head_mma[2] head_epi[2]
 constexpr uint32_t SMEM_BYTES = OFF_BARS + NBARS * 8 + 16;
 #ifdef WIDE_TRACE
 constexpr uint32_t SMEM_LAUNCH = SMEM_BYTES + 3 * 340 * 8;
@@ -139,9 +134,10 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
 #endif
     // position j of a batch is slot eval_list[j], j < *eval_count: only the leaves that wait for an evaluation are processed
     const long long n = eval_list ? (long long)__ldg(eval_count) : n_slots;
-    const int n_conv = 1 + 2 * num_blocks, n_layers = n_conv + 1;
+    const int n_conv = 1 + 2 * num_blocks;
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS), mma_done0 = smem_u32(bars + 2 * NS), epi_done0 = smem_u32(bars + 2 * NS + 2);
     const uint32_t stage_go0 = epi_done0 + 16, stem_ready0 = stage_go0 + 16, hact_ready = stem_ready0 + 16, hact_free = hact_ready + 8;
+    const uint32_t head_mma0 = hact_free + 8, head_epi0 = head_mma0 + 16;
     const uint32_t ring0 = smem_u32(smem + OFF_RING);
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
     if (tid == 32) {
@@ -150,6 +146,8 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
         for (int i = 0; i < 4; ++i) mbar_init(stage_go0 + i * 8, 1u);            // stage_go[2] (tensor core), stem_ready[2] (stager warp)
         mbar_init(hact_ready, (uint32_t)EW);
         mbar_init(hact_free, 1u);
+        for (int i = 0; i < 2; ++i) mbar_init(head_mma0 + i * 8, 1u);
+        for (int i = 0; i < 2; ++i) mbar_init(head_epi0 + i * 8, (uint32_t)EW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t i = tid; i < 2 * BUF_BYTES / 16; i += THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -189,82 +187,99 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Order of the work at a batch boundary (per tile t): ... last trunk layer of batch k, heads of batch k, stem of batch k + 1,
+    // conv1 of batch k + 1 ...  The heads accumulate in their own tensor-memory columns, so the next stem's MMAs do not wait for the
+    // head epilogue, and the epilogue warps take the next stem BEFORE the heads: the tensor core gets conv1 of the next batch as
+    // early as possible.  Trunk tile-layers (stem included) of a tile are counted by idx = batch * n_conv + l.
     if (warp == EW + 1) {
-        // ===== weight producer: every piece of every layer of every batch, in the order the issuer consumes them =====
+        // ===== weight producer: every piece in the order the issuer consumes them: stem (first batch), then per batch the trunk
+        // pieces, the 4 head pieces and the next batch's stem piece =====
         uint32_t g = 0;
+        auto piece = [&](const uint8_t *src, uint32_t bytes) {
+            const uint32_t st = g % NS;
+            if (g >= NS) mbar_wait(empty0 + st * 8, ((g / NS) - 1u) & 1u);  // both tiles' MMAs of the previous use have read the stage
+            if (elect_one()) bulk_load(ring0 + st * PIECE_BYTES, src, bytes, full0 + st * 8);
+            __syncwarp();
+            ++g;
+        };
+        if ((long long)blockIdx.x < n_batches) piece(weights, PIECE_BYTES);
         for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-            for (int l = 0; l < n_layers; ++l) {
-                const bool head = l >= n_conv;
-                const uint8_t *src = l == 0 ? weights : (head ? head_w : weights + PIECE_BYTES + (size_t)(l - 1) * KS * PIECE_BYTES);
-                const uint32_t bytes = head ? HEAD_PIECE_BYTES : PIECE_BYTES;
-                const int pieces = l == 0 ? 1 : KS;
+            for (int l = 1; l < n_conv; ++l)
 #pragma unroll 1
-                for (int i = 0; i < pieces; ++i, ++g) {
-                    const uint32_t st = g % NS;
-                    if (g >= NS) mbar_wait(empty0 + st * 8, ((g / NS) - 1u) & 1u);  // both tiles' MMAs of the previous use have read the stage
-#if defined(WIDE_EXP) && (WIDE_EXP & 4)
-                    if (elect_one()) { if (g < NS) bulk_load(ring0 + st * PIECE_BYTES, src + (size_t)i * bytes, bytes, full0 + st * 8); else mbar_arrive(full0 + st * 8); }
-#else
-                    if (elect_one()) bulk_load(ring0 + st * PIECE_BYTES, src + (size_t)i * bytes, bytes, full0 + st * 8);
-#endif
-                    __syncwarp();
-                }
-            }
+                for (int i = 0; i < KS; ++i) piece(weights + PIECE_BYTES + ((size_t)(l - 1) * KS + i) * PIECE_BYTES, PIECE_BYTES);
+#pragma unroll 1
+            for (int i = 0; i < KS; ++i) piece(head_w + (size_t)i * HEAD_PIECE_BYTES, HEAD_PIECE_BYTES);
+            if (batch + gridDim.x < n_batches) piece(weights, PIECE_BYTES);
         }
     } else if (warp == EW) {
-        // ===== MMA issuer (converged; one elected lane issues).  Order: layer by layer, tile 0 then tile 1 =====
-        uint32_t g = 0, idx = 0, it = 0;  // pieces consumed; tile-layers issued per tile; batches
-        for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
-            for (int l = 0; l < n_layers; ++l, ++idx) {
-                const bool head = l >= n_conv;
-                const int src_t = (l == 0 || !(head || (l & 1))) ? 1 : 0;           // conv1 (odd l) and the heads read x; stem and conv2 read t
-                const uint32_t src = src_t ? aT : aX;
-                const uint32_t idesc = head ? instr_desc(128, 3 * NHC, F16) : instr_desc(128, 3 * C, F16);
-                const uint64_t a_desc = smem_desc(src, LBO_A, SBO_A);
-                const int ksteps = l == 0 ? 1 : KS;
-                const uint32_t dy_units = (head ? HEAD_DY_BYTES : DY_BYTES) >> 4;
-#pragma unroll
-                for (int t = 0; t < TILES; ++t) {
-                    // the tile's previous epilogue is through: its accumulator columns are read, this layer's input rows are written
-                    // (after a batch's last trunk layer: the next batch's stem input as well)
-                    TRACE(0, l, t, 0);  // issuer: about to wait for the tile's previous epilogue
-                    if (l == 0) mbar_wait(stem_ready0 + t * 8, it & 1u);  // the stager warp has written this batch's stem input
-                    if (idx > 0) mbar_wait(epi_done0 + t * 8, (idx - 1u) & 1u);
-                    fence_after();
-                    TRACE(0, l, t, 1);  // issuer: epilogue seen
+        // ===== MMA issuer (converged; one elected lane issues) =====
+        uint32_t g = 0, it = 0;  // pieces consumed; batches
+        // the MMAs of one tile over `ksteps` ring stages starting at piece g: three filter rows per K chunk
+        auto mmas = [&](int t, uint32_t src, uint32_t acc, uint32_t idesc, int ksteps, uint32_t dy_units) {
+            const uint64_t a_desc = smem_desc(src, LBO_A, SBO_A);
 #pragma unroll 1
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint32_t gg = g + (uint32_t)ks, st = gg % NS;
-                        if (t == 0) {
-                            mbar_wait(full0 + st * 8, (gg / NS) & 1u);  // the K chunk's three filter rows have landed
-                            fence_after();
-                        }
-                        if (elect_one()) {
-                            const uint64_t bd = smem_desc(ring0 + st * PIECE_BYTES, LBO_W, SBO_W);
-#pragma unroll
-                            for (int dy = 0; dy < 3; ++dy) {
-                                const uint64_t ad = a_desc + (uint64_t)(int64_t)((dy - 1) * PW + t * 128 + ks * (int)(2 * LBO_A >> 4));
-                                if (TMEM_A && dy == 1 && l > 0)
-                                    umma_ts(tmem_base + (uint32_t)t * TILE_COLS, tmem_base + ACT_COLS + (uint32_t)(2 * t + src_t) * ACT_BUF + (uint32_t)ks * 8u,
-                                            bd + (uint64_t)(dy * dy_units), idesc, (ks | dy) > 0);
-                                else
-                                    umma(tmem_base + (uint32_t)t * TILE_COLS, ad, bd + (uint64_t)(dy * dy_units), idesc, (ks | dy) > 0);
-                            }
-                            if (t == TILES - 1) umma_commit(empty0 + st * 8);
-                        }
-                        __syncwarp();
-                    }
-                    if (elect_one()) {
-                        umma_commit(mma_done0 + t * 8);
-                        // a batch's last trunk layer: when it is complete nothing reads the tile's rows of t any more - the stager
-                        // warp may write the next batch's stem input there
-                        if (l == n_conv - 1) umma_commit(stage_go0 + t * 8);
-                    }
-                    __syncwarp();
-                    TRACE(0, l, t, 2);  // issuer: tile-layer issued and committed
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t gg = g + (uint32_t)ks, st = gg % NS;
+                if (t == 0) {
+                    mbar_wait(full0 + st * 8, (gg / NS) & 1u);  // the K chunk's three filter rows have landed
+                    fence_after();
                 }
-                g += (uint32_t)ksteps;
+                if (elect_one()) {
+                    const uint64_t bd = smem_desc(ring0 + st * PIECE_BYTES, LBO_W, SBO_W);
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const uint64_t ad = a_desc + (uint64_t)(int64_t)((dy - 1) * PW + t * 128 + ks * (int)(2 * LBO_A >> 4));
+                        umma(acc, ad, bd + (uint64_t)(dy * dy_units), idesc, (ks | dy) > 0);
+                    }
+                    if (t == TILES - 1) umma_commit(empty0 + st * 8);  // both tiles have used the stage
+                }
+                __syncwarp();
             }
+        };
+        // one stem / trunk layer of one tile; idx = its number in the tile's sequence
+        auto trunk = [&](int l, int t, uint32_t idx, uint32_t batch_no) {
+            TRACE(0, l, t, 0);  // issuer: about to wait for the tile's previous epilogue
+            if (l == 0) mbar_wait(stem_ready0 + t * 8, batch_no & 1u);  // the stager warp has written this batch's stem input
+            // the tile's previous epilogue is through: its accumulator columns are read, this layer's input rows are written
+            if (idx > 0) mbar_wait(epi_done0 + t * 8, (idx - 1u) & 1u);
+            fence_after();
+            TRACE(0, l, t, 1);  // issuer: epilogue seen
+            mmas(t, (l == 0 || !(l & 1)) ? aT : aX, tmem_base + (uint32_t)t * TILE_COLS, instr_desc(128, 3 * C, F16), l == 0 ? 1 : KS, DY_BYTES >> 4);
+            if (elect_one()) {
+                umma_commit(mma_done0 + t * 8);
+                // a batch's last trunk layer: when it is complete nothing reads the tile's rows of t any more - the stager warp may
+                // write the next batch's stem input there
+                if (l == n_conv - 1) umma_commit(stage_go0 + t * 8);
+            }
+            __syncwarp();
+            TRACE(0, l, t, 2);  // issuer: tile-layer issued and committed
+        };
+        if ((long long)blockIdx.x < n_batches) {
+            for (int t = 0; t < TILES; ++t) trunk(0, t, 0u, 0u);
+            g += 1;
+        }
+        for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
+            const bool has_next = batch + gridDim.x < n_batches;
+            for (int l = 1; l < n_conv; ++l) {
+                for (int t = 0; t < TILES; ++t) trunk(l, t, it * (uint32_t)n_conv + (uint32_t)l, it);
+                g += KS;
+            }
+            for (int t = 0; t < TILES; ++t) {
+                // heads of this batch (read x: the last trunk epilogue of the tile; their own accumulator columns: the previous
+                // batch's head epilogue), then the next batch's stem - the head pieces are ring stages g .. g + 3, the stem piece g + 4
+                mbar_wait(epi_done0 + t * 8, (it * (uint32_t)n_conv + (uint32_t)n_conv - 1u) & 1u);
+                if (it > 0) mbar_wait(head_epi0 + t * 8, (it - 1u) & 1u);
+                fence_after();
+                mmas(t, aX, tmem_base + HEAD_COLS + (uint32_t)t * NH, instr_desc(128, NH, F16), KS, HEAD_DY_BYTES >> 4);
+                if (elect_one()) umma_commit(head_mma0 + t * 8);
+                __syncwarp();
+                if (has_next) {
+                    g += KS;
+                    trunk(0, t, (it + 1u) * (uint32_t)n_conv, it + 1u);
+                    g -= KS;
+                }
+            }
+            g += KS + (has_next ? 1u : 0u);
         }
     } else if (warp < EW) {
         // ===== epilogue warps: thread = one pixel row of a tile, CPW of the 64 output channels =====
@@ -281,118 +296,124 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
         }
         const uint32_t lane_addr = tmem_base + (((warp & 3u) * 32u) << 16);
         const int lm = (int)((lane + 31u) & 31u), lp = (int)((lane + 1u) & 31u);  // left / right neighbour row (see the header)
-        uint32_t idx = 0, it = 0;
-        for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
-            for (int l = 0; l < n_conv; ++l, ++idx) {
-                uint8_t *dst = (l & 1) ? bufT : bufX;          // stem and conv2 write x, conv1 writes t
-                const bool skip = l > 0 && !(l & 1);            // conv2: + x, in place
-                float2 bias2[CPW / 2];  // this warp's output channels
+        // stem / trunk layer l of both tiles; idx = its number in a tile's sequence
+        auto trunk = [&](int l, uint32_t idx) {
+            uint8_t *dst = (l & 1) ? bufT : bufX;          // stem and conv2 write x, conv1 writes t
+            const bool skip = l > 0 && !(l & 1);            // conv2: + x, in place
+            float2 bias2[CPW / 2];  // this warp's output channels
 #pragma unroll
-                for (int i = 0; i < CPW / 4; ++i) {
-                    const float4 b4 = *reinterpret_cast<const float4 *>(s_bias + l * C + half * CPW + 4 * i);
-                    bias2[2 * i] = make_float2(b4.x, b4.y);
-                    bias2[2 * i + 1] = make_float2(b4.z, b4.w);
-                }
-#pragma unroll
-                for (int t = 0; t < TILES; ++t) {
-                    const uint32_t acc = lane_addr + (uint32_t)t * TILE_COLS + (uint32_t)(half * CPW);
-                    if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 0);  // epilogue: about to wait for the MMAs
-                    mbar_wait(mma_done0 + t * 8, idx & 1u);
-                    fence_after();
-                    if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 1);  // MMAs complete
-#if defined(WIDE_EXP) && (WIDE_EXP & 8)
-                    if (true) { fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(epi_done0 + t * 8); continue; }
-#endif
-                    uint32_t vm[NCC][16], v0[NCC][16], vp[NCC][16], pk[16];
-#pragma unroll
-                    for (int cc = 0; cc < NCC; ++cc) {
-                        tmem_ld16_issue(acc + 16 * cc, vm[cc]);
-                        tmem_ld16_issue(acc + C + 16 * cc, v0[cc]);
-                        tmem_ld16_issue(acc + 2 * C + 16 * cc, vp[cc]);
-                    }
-                    tmem_ld_wait();
-                    if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 2);  // accumulators in registers
-#pragma unroll
-                    for (int cc = 0; cc < NCC; ++cc) {
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint8_t *p = dst + (uint32_t)(half * (CPW / 8) + cc * 2 + h) * LBO_A + row_off[t];
-                            float2 f[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int j = h * 8 + 2 * i;
-                                float2 m, q;
-                                if (S16) {
-                                    // the neighbours' partial sums travel as fp16 pairs: one shuffle per direction for two channels
-                                    // (the crossbar, not the tensor core, bounds this kernel); 11 significand bits against the 8 / 11 the
-                                    // sum is rounded to anyway
-                                    m = unpack16<true>(__shfl_sync(0xFFFFFFFFu, pack16_sat(__uint_as_float(vm[cc][j]), __uint_as_float(vm[cc][j + 1])), lm));
-                                    q = unpack16<true>(__shfl_sync(0xFFFFFFFFu, pack16_sat(__uint_as_float(vp[cc][j]), __uint_as_float(vp[cc][j + 1])), lp));
-                                } else {
-                                    m = make_float2(__shfl_sync(0xFFFFFFFFu, __uint_as_float(vm[cc][j]), lm),
-                                                    __shfl_sync(0xFFFFFFFFu, __uint_as_float(vm[cc][j + 1]), lm));
-                                    q = make_float2(__shfl_sync(0xFFFFFFFFu, __uint_as_float(vp[cc][j]), lp),
-                                                    __shfl_sync(0xFFFFFFFFu, __uint_as_float(vp[cc][j + 1]), lp));
-                                }
-                                const float2 c0 = make_float2(__uint_as_float(v0[cc][j]), __uint_as_float(v0[cc][j + 1]));
-                                f[i] = fadd2(fadd2(fadd2(c0, m), q), bias2[cc * 8 + h * 4 + i]);
-                            }
-                            if (skip) {
-                                const uint4 s = *reinterpret_cast<const uint4 *>(p);
-                                f[0] = fadd2(f[0], unpack16<F16>(s.x));
-                                f[1] = fadd2(f[1], unpack16<F16>(s.y));
-                                f[2] = fadd2(f[2], unpack16<F16>(s.z));
-                                f[3] = fadd2(f[3], unpack16<F16>(s.w));
-                            }
-                            uint4 o = make_uint4(0, 0, 0, 0);
-                            if (valid[t]) o = make_uint4(pack16_relu<F16>(f[0]), pack16_relu<F16>(f[1]), pack16_relu<F16>(f[2]), pack16_relu<F16>(f[3]));
-                            *reinterpret_cast<uint4 *>(p) = o;
-                            pk[cc * 8 + h * 4] = o.x; pk[cc * 8 + h * 4 + 1] = o.y; pk[cc * 8 + h * 4 + 2] = o.z; pk[cc * 8 + h * 4 + 3] = o.w;
-                        }
-                    }
-                    if (TMEM_A && EW == 8) {
-                        tmem_st16(lane_addr + ACT_COLS + (uint32_t)(2 * t + (l & 1)) * ACT_BUF + (uint32_t)half * 16u, pk);
-                        tmem_st_wait();
-                    }
-                    // this warp's part of the tile is in place for the tensor core and its accumulator reads are complete
-                    if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 3);  // outputs computed and stored
-                    fence_before();
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(epi_done0 + t * 8);
-                    if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 4);  // arrived
-                }
+            for (int i = 0; i < CPW / 4; ++i) {
+                const float4 b4 = *reinterpret_cast<const float4 *>(s_bias + l * C + half * CPW + 4 * i);
+                bias2[2 * i] = make_float2(b4.x, b4.y);
+                bias2[2 * i + 1] = make_float2(b4.z, b4.w);
             }
-            // ---- heads: [POS][35][42] fp32 in the Flatten() order of NCHW.  Policy channels (1x1 conv) have weights in the centre
-            // tap only: their dx = -1 / +1 blocks are zero.  Warps 0..3: policy 0..15 and the 3 value channels; warps 4..7: policy 16..31.
-            const float *hb = s_bias + n_conv * C;
-            if (it > 0) mbar_wait(hact_free, (it - 1u) & 1u);  // the FC warp is through with the previous batch's head activations
 #pragma unroll
             for (int t = 0; t < TILES; ++t) {
-                const uint32_t acc = lane_addr + (uint32_t)t * TILE_COLS;
+                const uint32_t acc = lane_addr + (uint32_t)t * TILE_COLS + (uint32_t)(half * CPW);
+                if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 0);  // epilogue: about to wait for the MMAs
                 mbar_wait(mma_done0 + t * 8, idx & 1u);
                 fence_after();
-                uint32_t v[16], wm[16], w0[16], wp[16];
-                if (half < 2) tmem_ld16_issue(acc + NHC + (uint32_t)half * 16u, v);
+                if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 1);  // MMAs complete
+                uint32_t vm[NCC][16], v0[NCC][16], vp[NCC][16];
+#pragma unroll
+                for (int cc = 0; cc < NCC; ++cc) {
+                    tmem_ld16_issue(acc + 16 * cc, vm[cc]);
+                    tmem_ld16_issue(acc + C + 16 * cc, v0[cc]);
+                    tmem_ld16_issue(acc + 2 * C + 16 * cc, vp[cc]);
+                }
+                tmem_ld_wait();
+                if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 2);  // accumulators in registers
+#pragma unroll
+                for (int cc = 0; cc < NCC; ++cc) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint8_t *p = dst + (uint32_t)(half * (CPW / 8) + cc * 2 + h) * LBO_A + row_off[t];
+                        float2 f[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int j = h * 8 + 2 * i;
+                            float2 m, q;
+                            if (S16) {
+                                // the neighbours' partial sums travel as fp16 pairs: one shuffle per direction for two channels;
+                                // 11 significand bits against the 8 / 11 the sum is rounded to anyway
+                                m = unpack16<true>(__shfl_sync(0xFFFFFFFFu, pack16_sat(__uint_as_float(vm[cc][j]), __uint_as_float(vm[cc][j + 1])), lm));
+                                q = unpack16<true>(__shfl_sync(0xFFFFFFFFu, pack16_sat(__uint_as_float(vp[cc][j]), __uint_as_float(vp[cc][j + 1])), lp));
+                            } else {
+                                m = make_float2(__shfl_sync(0xFFFFFFFFu, __uint_as_float(vm[cc][j]), lm),
+                                                __shfl_sync(0xFFFFFFFFu, __uint_as_float(vm[cc][j + 1]), lm));
+                                q = make_float2(__shfl_sync(0xFFFFFFFFu, __uint_as_float(vp[cc][j]), lp),
+                                                __shfl_sync(0xFFFFFFFFu, __uint_as_float(vp[cc][j + 1]), lp));
+                            }
+                            const float2 c0 = make_float2(__uint_as_float(v0[cc][j]), __uint_as_float(v0[cc][j + 1]));
+                            f[i] = fadd2(fadd2(fadd2(c0, m), q), bias2[cc * 8 + h * 4 + i]);
+                        }
+                        if (skip) {
+                            const uint4 s = *reinterpret_cast<const uint4 *>(p);
+                            f[0] = fadd2(f[0], unpack16<F16>(s.x));
+                            f[1] = fadd2(f[1], unpack16<F16>(s.y));
+                            f[2] = fadd2(f[2], unpack16<F16>(s.z));
+                            f[3] = fadd2(f[3], unpack16<F16>(s.w));
+                        }
+                        uint4 o = make_uint4(0, 0, 0, 0);
+                        if (valid[t]) o = make_uint4(pack16_relu<F16>(f[0]), pack16_relu<F16>(f[1]), pack16_relu<F16>(f[2]), pack16_relu<F16>(f[3]));
+                        *reinterpret_cast<uint4 *>(p) = o;
+                    }
+                }
+                // this warp's part of the tile is in place for the tensor core and its accumulator reads are complete
+                if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 3);  // outputs computed and stored
+                fence_before();
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(epi_done0 + t * 8);
+                if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, l, t, 4);  // arrived
+            }
+        };
+        uint32_t it = 0;
+        if ((long long)blockIdx.x < n_batches) trunk(0, 0u);
+        for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
+            for (int l = 1; l < n_conv; ++l) trunk(l, it * (uint32_t)n_conv + (uint32_t)l);
+            // the next batch's stem first (its MMAs were issued right behind this batch's heads): conv1 of the next batch can start
+            if (batch + gridDim.x < n_batches) trunk(0, (it + 1u) * (uint32_t)n_conv);
+            // ---- heads: [POS][35][42] fp32 in the Flatten() order of NCHW.  Accumulator columns of a tile: 0..31 policy channels
+            // (1x1 conv: centre tap only, no neighbour terms), 32 + 8 dx + v = value channel v, filter column dx (models.py:
+            // pack_head_weights(wide=True)).  Warps 0..3: policy 0..15 and the 3 value channels; warps 4..7: policy 16..31.
+            const float *hb = s_bias + n_conv * C;
+            if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, 50, 0, 0);
+            if (it > 0) mbar_wait(hact_free, (it - 1u) & 1u);  // the FC warp is through with the previous batch's head activations
+            if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, 50, 0, 1);
+#pragma unroll
+            for (int t = 0; t < TILES; ++t) {
+                const uint32_t acc = lane_addr + HEAD_COLS + (uint32_t)t * NH;
+                float hbr[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(hb + (half & 1) * 16 + 4 * i);
+                    hbr[4 * i] = b4.x; hbr[4 * i + 1] = b4.y; hbr[4 * i + 2] = b4.z; hbr[4 * i + 3] = b4.w;
+                }
+                const float4 hbv = *reinterpret_cast<const float4 *>(hb + 32);
+                mbar_wait(head_mma0 + t * 8, it & 1u);
+                fence_after();
+                if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, 50, t, 2);
+                uint32_t v[16], wa[16], wb[16];
+                if (half < 2) tmem_ld16_issue(acc + (uint32_t)half * 16u, v);
                 if (half == 0) {
-                    tmem_ld16_issue(acc + 32, wm);
-                    tmem_ld16_issue(acc + NHC + 32, w0);
-                    tmem_ld16_issue(acc + 2 * NHC + 32, wp);
+                    tmem_ld16_issue(acc + 32, wa);  // value channels: filter columns -1 (0..7) and 0 (8..15)
+                    tmem_ld16_issue(acc + 48, wb);  // filter column +1 (0..7)
                 }
                 tmem_ld_wait();
                 float val[3] = {0.f, 0.f, 0.f};
                 if (half == 0) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const float m = __shfl_sync(0xFFFFFFFFu, __uint_as_float(wm[c]), lm);
-                        const float q = __shfl_sync(0xFFFFFFFFu, __uint_as_float(wp[c]), lp);
-                        val[c] = ((__uint_as_float(w0[c]) + m) + q) + hb[32 + c];
+                        const float m = __shfl_sync(0xFFFFFFFFu, __uint_as_float(wa[c]), lm);
+                        const float q = __shfl_sync(0xFFFFFFFFu, __uint_as_float(wb[c]), lp);
+                        val[c] = ((__uint_as_float(wa[8 + c]) + m) + q) + (c == 0 ? hbv.x : (c == 1 ? hbv.y : hbv.z));
                     }
                 }
                 if (valid[t] && half < 2) {
                     float *o = hact + pos[t] * NHU * 42 + yy[t] * c4::W + xx[t];
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) o[(half * 16 + c) * 42] = fmaxf(__uint_as_float(v[c]) + hb[half * 16 + c], 0.f);
+                    for (int c = 0; c < 16; ++c) o[(half * 16 + c) * 42] = fmaxf(__uint_as_float(v[c]) + hbr[c], 0.f);
                     if (half == 0) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c) o[(32 + c) * 42] = fmaxf(val[c], 0.f);
@@ -400,11 +421,10 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
                 }
                 fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(epi_done0 + t * 8);
+                if (lane == 0) mbar_arrive(head_epi0 + t * 8);
+                if (warp == 0 || warp == EW - 1) TRACE(warp == 0 ? 1 : 2, 50, t, 3);
             }
-            ++idx;
             // both tiles' head activations are in place for the FC warp
-            __syncwarp();
             if (lane == 0) mbar_arrive(hact_ready);
         }
     } else if (warp == EW + 2) {
@@ -540,13 +560,16 @@ int32_t az_resnet_wide_launch(az_engine *engine, const az_resnet_desc *d, float 
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return AZ_E_CUDA;
     const int batches = (n + POS - 1) / POS;
-    static int s16 = -1;
-    if (s16 < 0) {
+    // neighbour shuffles as fp16 pairs: default for bf16 operands (the pair's 11 significand bits against the 8 the sum is rounded
+    // to: no measurable change of the outputs, 2-3 % of the kernel), fp32 shuffles for fp16 operands; AZ_WIDE_SHFL16 = 0 / 1 overrides
+    static int s16_env = -2;
+    if (s16_env == -2) {
         const char *e = getenv("AZ_WIDE_SHFL16");
-        s16 = e ? atoi(e) : 0;
+        s16_env = e ? atoi(e) : -1;
     }
-    auto kern = d->operand_format == AZ_FMT_F16 ? (s16 ? k_resnet_wide<true, true> : k_resnet_wide<true, false>)
-                                                : (s16 ? k_resnet_wide<false, true> : k_resnet_wide<false, false>);
+    const bool f16 = d->operand_format == AZ_FMT_F16;
+    const bool s16 = s16_env >= 0 ? s16_env != 0 : !f16;
+    auto kern = f16 ? (s16 ? k_resnet_wide<true, true> : k_resnet_wide<true, false>) : (s16 ? k_resnet_wide<false, true> : k_resnet_wide<false, false>);
     kern<<<batches < sms ? batches : sms, THREADS, SMEM_LAUNCH, (cudaStream_t)stream>>>(
         bb0, bb1, player, status, elist, ecount, (long long)n, (const uint8_t *)d->trunk_w, d->trunk_b, d->num_blocks, (const uint8_t *)d->head_conv_w,
         d->head_conv_b, d->fc_policy_w, d->fc_policy_b, d->fc_value_w, d->fc_value_b, logits, values);

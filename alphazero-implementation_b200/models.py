@@ -391,9 +391,11 @@ def _pieces(w: Tensor, dtype: torch.dtype, pair: bool) -> list[Tensor]:
     return out
 
 
-def pack_head_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloat16, pipe: bool = True, pair: bool = False):
+def pack_head_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloat16, pipe: bool = True, pair: bool = False, wide: bool = False):
     """Policy conv1x1 (-> 32) and value conv3x3 (-> 3), BatchNorm folded, as ONE 48-output 3x3 conv for csrc/az_conv.cu
-    (the 1x1 weights occupy the centre tap), plus the two fully connected layers in fp32."""
+    (the 1x1 weights occupy the centre tap), plus the two fully connected layers in fp32.
+    `wide` (csrc/az_resnet_wide.cu): per K chunk the pieces [3 filter rows][64][16] - rows 0..31 the policy channels (centre row
+    only), row 32 + 8 kx + v = value channel v, filter column kx; the kernel adds the three columns of a value channel."""
     m = copy.deepcopy(model).eval().float().to(device)
     wp, bp = _fold_bn(m.policy_head[0], m.policy_head[1])  # [32, C, 1, 1]
     wv, bv = _fold_bn(m.value_head[0], m.value_head[1])    # [3, C, 3, 3]
@@ -402,7 +404,14 @@ def pack_head_weights(model: "ResNet", device, dtype: torch.dtype = torch.bfloat
     w[32:35] = wv
     b = torch.zeros(48, device=device)
     b[:32], b[32:35] = bp, bv
-    if pipe:  # pieces [48][16] in (ks, tap) order, like the trunk's
+    if wide:
+        rows = torch.zeros(3, 64, model.num_channels, device=device)  # [ky][row][in]
+        rows[1, :32] = wp[:, :, 0, 0]
+        for kx in range(3):
+            rows[:, 32 + 8 * kx:35 + 8 * kx] = wv[:, :, :, kx].permute(2, 0, 1)
+        conv = torch.cat([_canonical_kmajor(rows[ky, :, 16 * ks:16 * ks + 16], dtype)
+                          for ks in range(model.num_channels // 16) for ky in range(3)]).contiguous()
+    elif pipe:  # pieces [48][16] in (ks, tap) order, like the trunk's
         conv = torch.cat(_pieces(w, dtype, pair)).contiguous()
     else:
         conv = torch.cat([_canonical_kmajor(w[:, :, ky, kx], dtype) for ky in range(3) for kx in range(3)]).contiguous()
@@ -434,7 +443,7 @@ class TensorCoreTrunk:
         self.weights, self.biases = self._pack(model, self.device, dtype)
         expect = self.lib.az_resnet_pipe_weight_bytes(self.num_blocks, self.num_channels) if variant != 1 else self.lib.az_trunk_weight_bytes(self.num_blocks)
         assert self.weights.numel() * 2 == expect
-        self.heads = pack_head_weights(model, self.device, dtype, pipe=variant != 1, pair=pair)
+        self.heads = pack_head_weights(model, self.device, dtype, pipe=variant != 1, pair=pair, wide=variant == 4)
         hw, hb, fpw, fpb, fvw, fvb = self.heads
         self.desc = _lib.AzResnetDesc(self.num_blocks, model.num_channels, _operand_format(dtype), variant, self.weights.data_ptr(),
                                       self.biases.data_ptr(), hw.data_ptr(), hb.data_ptr(), fpw.data_ptr(), fpb.data_ptr(),
@@ -450,7 +459,7 @@ class TensorCoreTrunk:
         w, b = self._pack(model, self.device, self.dtype)
         self.weights.copy_(w)
         self.biases.copy_(b)
-        for dst, src in zip(self.heads, pack_head_weights(model, self.device, self.dtype, pipe=self.variant != 1, pair=self.variant == 3)):
+        for dst, src in zip(self.heads, pack_head_weights(model, self.device, self.dtype, pipe=self.variant != 1, pair=self.variant == 3, wide=self.variant == 4)):
             dst.copy_(src)
         return True
 

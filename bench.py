@@ -573,9 +573,14 @@ def run_b200(args):
                 "evaluated_leaves_per_launch": evals_per_launch, "kernel_ms": k_mean, "kernel_launches_timed": len(k_ms),
                 "kernel_share_of_step": k_mean * S / (ev0.elapsed_time(ev1) / K),
                 "how": "CUDA events around each evaluator launch of one extra un-graphed move step right after the timed region",
-                "note": "tensor-bound by classification; at 64 output channels every 128x64x16 MMA fetches 6 KB of shared-memory operands = 48 cycles at "
-                        "128 B/clk against 32 cycles of math (measured 48.0, profiles/r02_ubench_mma_pair.txt): the kernel's ceiling is the "
-                        "shared-memory operand path, ~0.6 of the tensor peak; the 128-channel instance of the same kernel reaches 0.65",
+                # the events of the extra step see the kernel between launch gaps (GPU below its power cap, higher clock); the whole
+                # timed step divided by S bounds the in-region duration from above
+                "frac_lower_bound_whole_step": evals_per_launch * flops / (ev0.elapsed_time(ev1) / K / S * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                "note": "tensor-bound by classification.  k_resnet_wide fuses the three taps of a filter row into one 128x192x16 MMA (96 cycles "
+                        "of math; measured 112-115: the A tile is fetched once per 128 output columns, 14 KB of shared-memory operands at 128 "
+                        "B/clk) - 12 MMAs per tile-layer instead of 36 of 48 cycles; the epilogue's shuffles / stores share that crossbar, so the "
+                        "kernel runs at ~1700 cycles per tile-layer against 1152 of math (ncu: tensor pipe 65.9 %, profiles/"
+                        "r02_k_resnet_wide_steady_ncu_raw.json); the previous 64-channel kernel (k_resnet_pipe, N = 64) measured 0.47",
                 "tree_kernel": {"name": "k_expand_select", "us_per_launch": (ev0.elapsed_time(ev1) / K / S - k_mean) * 1e3,
                                 "algorithmic_gbs": algorithmic_bytes(st) / K / S / max(1e-9, (ev0.elapsed_time(ev1) / K / S - k_mean) * 1e-3) / 1e9,
                                 "note": "step time minus evaluator time; latency-bound pointer chasing, see DESIGN.md"}}
