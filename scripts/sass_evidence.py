@@ -12,7 +12,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "alphazero-implementation_b200", "libaz_engine.so")
-OPS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UBLKCP", "UTCBAR", "SYNCS", "UTCATOMSWS", "NANOSLEEP", "HMMA", "DFMA", "SHFL", "LDS", "STS", "LDG", "STG"]
+OPS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UBLKCP", "UTCBAR", "SYNCS", "UTCATOMSWS", "NANOSLEEP", "HMMA", "DFMA", "SHFL", "FADD2", "F2FP", "LDS", "STS", "LDG", "STG"]
 
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 kernels, name = collections.OrderedDict(), None

@@ -102,3 +102,29 @@ def test_resnet128_in_the_search_loop_and_weight_refresh():
     assert b == [[ch.visit_count for ch in nd.children.values()] for nd in nodes]
     search.close()
     fresh.close()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_wide_kernel_is_deterministic_and_independent_of_the_batch_composition(dtype):
+    """k_resnet_wide hands tiles back and forth between the tensor core, eight epilogue warps, a stager warp and an FC warp through
+    mbarriers: (a) two launches on the same leaves give bit-identical outputs (no race decides anything); (b) a position's outputs do
+    not depend on where it sits - with leaf compaction (position j = the j-th leaf that waits for an evaluation) and without (position
+    = slot, terminal leaves as empty rows) every evaluated slot gets the same bits, because its neighbours in a tile only ever
+    contribute exact zeros (the shared zero row / column of the compact padding)."""
+    torch.manual_seed(5)
+    model = az.ResNet(num_res_blocks=3, num_channels=64).cuda().eval()
+    _randomise_bn(model)
+    outs = []
+    for compact in (True, False):
+        eng = _engine_with_leaves(2999, seed=11, compact=compact)
+        live = eng.leaf_info()["status"] == 0
+        net = InferenceNet(model, dtype=dtype, trunk_variant=4)
+        assert net.kernel_name == "k_resnet_wide"
+        l1, v1 = (t.clone() for t in net.forward_leaves(eng))
+        l2, v2 = (t.clone() for t in net.forward_leaves(eng))
+        torch.cuda.synchronize()
+        assert torch.equal(l1, l2) and torch.equal(v1, v2)
+        outs.append((l1[live], v1[live]))
+        eng.close()
+    assert outs[0][0].shape[0] > 2000
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
