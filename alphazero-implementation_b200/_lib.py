@@ -155,6 +155,7 @@ SIGNATURES = {
     "az_resnet_forward_leaves": (I32, [P, P, P, I32, P, P, P, P, P, P, P, P, P]),
     "az_resnet_forward_leaves_v2": (I32, [P, C.POINTER(AzResnetDesc), P, P, P]),
     "az_trunk_set_cta_pair": (I32, [I32]),
+    "az_resnet_wide_set_timing": (I32, [P, I32]),
     "az_cnn_conv_weight_bytes": (I64, []),
     "az_cnn_fc_weight_bytes": (I64, []),
     "az_cnn_workspace_bytes": (I64, [I64]),

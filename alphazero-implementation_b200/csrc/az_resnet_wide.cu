@@ -120,7 +120,7 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
               long long n_slots, const uint8_t *__restrict__ weights, const float *__restrict__ biases, int num_blocks,
               const uint8_t *__restrict__ head_w, const float *__restrict__ head_b, const float *__restrict__ fc_policy_w,
               const float *__restrict__ fc_policy_b, const float *__restrict__ fc_value_w, const float *__restrict__ fc_value_b,
-              float *__restrict__ logits, float *__restrict__ values) {
+              float *__restrict__ logits, float *__restrict__ values, unsigned long long *__restrict__ timing, int timing_cap) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *bufX = smem, *bufT = smem + BUF_BYTES;
     float *hact = reinterpret_cast<float *>(smem + OFF_HACT);
@@ -155,6 +155,14 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
     for (uint32_t i = tid; i < NHC; i += THREADS) s_bias[n_conv * C + i] = __ldg(head_b + i);
     const uint32_t aX = smem_u32(bufX) + GUARD * ROWB, aT = smem_u32(bufT) + GUARD * ROWB;
     const long long n_batches = (n + POS - 1) / POS;
+    // measurement hook (az_resnet_wide_set_timing): first start / last end of every launch on the device's global timer
+    unsigned long long t_slot = 0;
+    if (timing && tid == 0) {
+        t_slot = 4 + 2 * (*reinterpret_cast<volatile unsigned long long *>(timing) % (unsigned long long)timing_cap);
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMin(timing + t_slot, now);
+    }
 
     // the leaf record of pixel row r (0..255) of batch `batch`
     auto load_rec = [&](long long batch, int r) {
@@ -517,11 +525,34 @@ k_resnet_wide(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
     }
 #endif
     if (warp == 0) tmem_dealloc(tmem_base, 512);
+    if (timing && tid == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMax(timing + t_slot + 1, now);
+        __threadfence();
+        if (atomicAdd(timing + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {  // the launch's last CTA: next launch, next slot
+            timing[1] = 0;
+            __threadfence();
+            atomicAdd(timing, 1ull);
+        }
+    }
 }
 
 }  // namespace
 
+static unsigned long long *g_timing = nullptr;
+static int g_timing_cap = 0;
+
 extern "C" {
+
+/* Measurement hook: `buf` = device array of 4 + 2 * cap uint64, [0] = launches so far, [1] = scratch, then per launch (slot =
+ * launch % cap) {first CTA start, last CTA end} on %globaltimer (ns); the caller initialises the pairs to {~0, 0}.  The pointer is
+ * baked into launches (and captured graphs) made after this call; NULL switches the hook off. */
+int32_t az_resnet_wide_set_timing(void *buf, int32_t cap) {
+    g_timing = (unsigned long long *)buf;
+    g_timing_cap = buf ? cap : 0;
+    return AZ_OK;
+}
 
 #ifdef WIDE_TRACE
 /* timing study: copy out the timeline of CTA 0 of the last launch: [3 warps][TRACE_CAP][code, clock] */
@@ -572,7 +603,7 @@ int32_t az_resnet_wide_launch(az_engine *engine, const az_resnet_desc *d, float 
     auto kern = f16 ? (s16 ? k_resnet_wide<true, true> : k_resnet_wide<true, false>) : (s16 ? k_resnet_wide<false, true> : k_resnet_wide<false, false>);
     kern<<<batches < sms ? batches : sms, THREADS, SMEM_LAUNCH, (cudaStream_t)stream>>>(
         bb0, bb1, player, status, elist, ecount, (long long)n, (const uint8_t *)d->trunk_w, d->trunk_b, d->num_blocks, (const uint8_t *)d->head_conv_w,
-        d->head_conv_b, d->fc_policy_w, d->fc_policy_b, d->fc_value_w, d->fc_value_b, logits, values);
+        d->head_conv_b, d->fc_policy_w, d->fc_policy_b, d->fc_value_w, d->fc_value_b, logits, values, g_timing, g_timing_cap);
     return cudaGetLastError() == cudaSuccess ? AZ_OK : AZ_E_CUDA;
 }
 

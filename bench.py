@@ -329,36 +329,6 @@ def kernel_timing_step(search, eng, u):
     return [a.elapsed_time(b) for a, b in pairs]
 
 
-def kernel_sustained_ms(search, eng, launches: int = 32, reps: int = 12):
-    """The evaluator kernel alone, back to back on the leaves of the last selection (one CUDA graph of `launches` launches replayed
-    `reps` times after two warm-up replays) -> mean ms per launch.  No launch gaps: the GPU sits at its power cap as in the timed
-    region, where the un-graphed step of `kernel_timing_step` lets it boost between launches."""
-    import torch
-
-    net = search._net
-    if not getattr(net, "evaluates_leaves_directly", False):
-        return None
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream(device=eng.device)
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        net.forward_leaves(eng)
-        with torch.cuda.graph(g, stream=side):
-            for _ in range(launches):
-                net.forward_leaves(eng)
-    torch.cuda.current_stream().wait_stream(side)
-    for _ in range(2):
-        g.replay()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(reps):
-        g.replay()
-    b.record()
-    torch.cuda.synchronize()
-    return a.elapsed_time(b) / (reps * launches)
-
-
 def net_extra(args, spec: str, device_index: int, peaks: dict):
     """Side measurement: another network in the loop at 16384 games x S sims on one GPU.  Burn-in with the fused uniform
     evaluator (cheap; a random-init net plays a near-uniform game too), then warm-up + timed move steps with the net."""
@@ -397,8 +367,7 @@ def net_extra(args, spec: str, device_index: int, peaks: dict):
     st = diff(st0, eng.stats())
     k_ms = kernel_timing_step(search, eng, u[33 + n])
     eng.drain_episodes_device()
-    k_sus = kernel_sustained_ms(search, eng)
-    k_mean = max(float(np.mean(k_ms)), k_sus or 0.0)  # as in the headline's roofline: events of an un-graphed step / back to back
+    k_mean = float(np.mean(k_ms))
     evals_per_launch = st["evaluations"] / (n * S)
     rec = {"workload": f"connect4_selfplay_{spec}_{dname}_{E}x{S}", "net": net_label(spec), "evaluator": search.evaluator_name,
            "move_steps": n, "sims_per_s": st["simulations"] / ms * 1e3, "us_per_sim_step": ms * 1e3 / (n * S),
@@ -516,6 +485,13 @@ def run_b200(args):
     E = hi - lo
     peaks = load_peaks()
     model, flops = make_model(args.net)
+    # k_resnet_wide's measurement hook: first-CTA start / last-CTA end of every launch on the device's global timer -> the kernel's
+    # duration INSIDE the timed region (set before the first launch: the pointer is baked into the captured graph)
+    from alphazero_implementation_b200 import _lib as az_lib
+    T_CAP = 1 << 15
+    timing = torch.zeros(4 + 2 * T_CAP, dtype=torch.int64, device=torch.device("cuda", local))
+    timing[4::2] = -1  # ~0 as uint64: atomicMin target
+    az_lib.load().az_resnet_wide_set_timing(timing.data_ptr(), T_CAP)
     gen = az.EpisodeGenerator(model=model, num_simulations=S, num_episodes=E, game_initial_state=az.Config(6, 7, 4).sample_initial_state(),
                               device=local, inference_dtype=torch_dtype(args.dtype), trunk_variant=args.trunk_variant)
     search = gen.search
@@ -544,6 +520,10 @@ def run_b200(args):
     drain_bufs = [eng.alloc_drain_buffers() for _ in range((K + 15) // 16)]  # no allocation inside the timed region
     barrier()
     st0 = eng.stats()
+    launch0 = int(timing[0].item())
+    timing[4::2] = -1  # fresh slots for the region's launches (at most T_CAP of them)
+    timing[5::2] = 0
+    torch.cuda.synchronize()
     sampler = ClockSampler(local)
     ev0, ev1, ag0 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     t_wall0 = time.perf_counter()
@@ -564,6 +544,13 @@ def run_b200(args):
     barrier()
     wall_s = time.perf_counter() - t_wall0
     clocks = sampler.stop()
+    launch1 = int(timing[0].item())
+    k_region = None
+    if 0 < launch1 - launch0 <= T_CAP:
+        slots = torch.arange(launch0, launch1, device=timing.device) % T_CAP
+        dur = (timing[5::2][slots] - timing[4::2][slots]).double() * 1e-6  # ns -> ms
+        k_region = {"launches": launch1 - launch0, "mean_ms": float(dur.mean().item()), "min_ms": float(dur.min().item()), "max_ms": float(dur.max().item())}
+    az_lib.load().az_resnet_wide_set_timing(None, 0)  # off for everything that follows (extras build their own graphs)
     st = diff(st0, eng.stats())
     total_ms, ag_ms = ev0.elapsed_time(ev1), ag0.elapsed_time(ev1)
     step_ms = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(K)]
@@ -596,20 +583,20 @@ def run_b200(args):
     k_ms = kernel_timing_step(search, eng, u_all[n_pre + K])
     eng.drain_episodes_device()
     k_events = float(np.mean(k_ms))
-    k_sus = kernel_sustained_ms(search, eng)
-    # the duration the roofline uses: the larger of the two (back to back the GPU runs at its power cap, as in the timed region)
-    k_mean = max(k_events, k_sus) if k_sus else k_events
+    # the duration the roofline uses: the kernel's own device-timer stamps inside the timed region (k_resnet_wide), else the events
+    # of the extra un-graphed step (between launch gaps the GPU boosts above its power-capped clock: a slight underestimate)
+    k_mean = k_region["mean_ms"] if k_region else k_events
     evals_per_launch = st["evaluations"] / (K * S)
     achieved = evals_per_launch * flops / (k_mean * 1e-3) / 1e12
     roofline = {"kernel": search.evaluator_name, "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
                 "algorithmic_flops_per_launch": evals_per_launch * flops, "flops_per_position": flops, "positions_per_launch": E,
                 "evaluated_leaves_per_launch": evals_per_launch, "kernel_ms": k_mean, "kernel_launches_timed": len(k_ms),
-                "kernel_ms_events_ungraphed_step": k_events, "kernel_ms_back_to_back": k_sus,
+                "kernel_ms_events_ungraphed_step": k_events, "kernel_in_timed_region": k_region,
                 "kernel_share_of_step": k_mean * S / (ev0.elapsed_time(ev1) / K),
-                "how": "max of (a) CUDA events around each evaluator launch of one extra un-graphed move step right after the timed region and "
-                       "(b) the same kernel replayed back to back from a CUDA graph on the last selection's leaves (no launch gaps: power-capped "
-                       "clocks, as in the timed region)",
+                "how": "k_resnet_wide stamps the device's global timer at its first CTA's start and its last CTA's end (az_resnet_wide_set_timing): "
+                       "mean over every launch INSIDE the timed region; other evaluators: CUDA events around each launch of one extra un-graphed "
+                       "move step right after the timed region (kernel_ms_events_ungraphed_step, reported for both)",
                 # the events of the extra step see the kernel between launch gaps (GPU below its power cap, higher clock); the whole
                 # timed step divided by S bounds the in-region duration from above
                 "frac_lower_bound_whole_step": evals_per_launch * flops / (ev0.elapsed_time(ev1) / K / S * 1e-3) / 1e12 / peaks["bf16_tflops"],

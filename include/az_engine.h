@@ -305,6 +305,12 @@ int64_t az_cnn_fc_weight_bytes(void);
 int64_t az_cnn_workspace_bytes(int64_t n);
 int32_t az_cnn_forward_leaves(az_engine *engine, const az_cnn_desc *desc, float *logits, float *values, void *stream);
 
+/* Measurement hook of k_resnet_wide (az_resnet_desc.variant 4): `buf` = device array of 4 + 2 * cap uint64 - [0] launches so far,
+ * [1] scratch, then per launch (slot = launch % cap) {first CTA start, last CTA end} on the device's global timer in ns; the caller
+ * initialises the pairs to {~0, 0}.  The pointer is baked into launches (and captured graphs) made after the call; NULL = off.
+ * bench.py uses it to time the kernel INSIDE the timed region (no reference counterpart). */
+int32_t az_resnet_wide_set_timing(void *buf, int32_t cap);
+
 /* Tuning switch of the kernel behind the calls above: 0 (default) = one CTA per 8 positions, 1 = CTA pairs
  * (tcgen05 cta_group::2, M = 256).  Same results; returns the previous setting. */
 int32_t az_trunk_set_cta_pair(int32_t on);
