@@ -150,7 +150,9 @@ class _GraphedStep:
                 with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
                     self.middle()
                 # ... and UNROLL of them in a second graph: fewer graph launches (and gaps between them) per move step
-                if self.UNROLL > 1:
+                # (only for long searches: the engine's host-side guard counts every call, recorded ones included, against the
+                # arena's num_simulations)
+                if self.UNROLL > 1 and middles >= 4 * self.UNROLL:
                     gu = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(gu, stream=side, capture_error_mode="thread_local"):
                         for _ in range(self.UNROLL):
