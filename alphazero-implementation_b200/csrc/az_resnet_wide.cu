@@ -594,6 +594,11 @@ int32_t az_resnet_wide_launch(az_engine *engine, const az_resnet_desc *d, float 
     // neighbour shuffles as fp16 pairs (default; AZ_WIDE_SHFL16=0 = fp32 shuffles): 2-3 % of the kernel, and no measurable change of the
     // outputs - max deviation from the fp32 `predict` over 16384 positions 3.8e-5 / 1.6e-4 (priors / values) with fp16 operands either
     // way, 3.0e-4 / 1.19e-3 against 3.0e-4 / 1.13e-3 with bf16 operands (profiles/r02_evaluator_deviation.json)
+    static int s16_env = -2;
+    if (s16_env == -2) {
+        const char *e = getenv("AZ_WIDE_SHFL16");
+        s16_env = e ? atoi(e) : 1;
+    }
     const bool f16 = d->operand_format == AZ_FMT_F16;
     const bool s16 = s16_env != 0;
     auto kern = f16 ? (s16 ? k_resnet_wide<true, true> : k_resnet_wide<true, false>) : (s16 ? k_resnet_wide<false, true> : k_resnet_wide<false, false>);
