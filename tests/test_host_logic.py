@@ -232,3 +232,41 @@ def test_player_move_rule_on_visit_counts():
     assert np.allclose(freq, counts / counts.sum(), atol=0.03) and freq[2] == 0 and freq[5] == 0
     cold = [_pick(counts, legal, 0.05, rng) for _ in range(200)]
     assert set(cold) <= {1, 3}  # (40 / 99) ** 20 against (10 / 99) ** 20: the maxima take everything
+
+
+def test_packed_weights_of_the_fused_filter_row_kernel():
+    """csrc/az_resnet_wide.cu reads (a) the layer-pipelined kernel's trunk pieces [9 taps][64 out][16 in] as [3 filter rows][192 =
+    (filter column, out)][16 in] - the canonical K-major order is row-group-major, so the two views are the same bytes - and (b) head
+    pieces [3 filter rows][64][16]: rows 0..31 = policy conv1x1 (centre tap only), row 32 + 8 kx + v = value channel v, filter column kx.
+    Unpack both and compare with the BatchNorm-folded convolution weights."""
+    import torch
+
+    import alphazero_implementation_b200 as az
+    from alphazero_implementation_b200.models import _fold_bn, pack_head_weights, pack_trunk_weights_pipe
+
+    torch.manual_seed(0)
+    m = az.ResNet(num_res_blocks=1, num_channels=64).eval()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.2)
+            mod.running_var.uniform_(0.5, 1.5)
+    w, b = pack_trunk_weights_pipe(m, "cpu", torch.float32)
+    piece = 9 * 64 * 16
+    assert w.numel() == piece * (1 + 2 * 4) and b.shape == (3, 64)
+    w1, _ = _fold_bn(m.residual_blocks[0].conv1, m.residual_blocks[0].bn1)
+    for ks in range(4):  # piece 1 + ks = K chunk ks of conv1, viewed as [3 dy][192][16]: [N/8][K/8][8][8] per filter row
+        p = w[piece * (1 + ks):piece * (2 + ks)].reshape(3, 24, 2, 8, 8).permute(0, 1, 3, 2, 4).reshape(3, 192, 16)
+        for ky in range(3):
+            for kx in range(3):
+                assert torch.equal(p[ky, 64 * kx:64 * kx + 64], w1[:, 16 * ks:16 * ks + 16, ky, kx])
+    conv, hb, *_ = pack_head_weights(m, "cpu", torch.float32, wide=True)
+    assert conv.numel() == 4 * 3 * 64 * 16 and hb.shape == (48,)
+    rows = conv.reshape(4, 3, 8, 2, 8, 8).permute(1, 2, 4, 0, 3, 5).reshape(3, 64, 64)  # [ky][row][in]
+    wp, bp = _fold_bn(m.policy_head[0], m.policy_head[1])
+    wv, bv = _fold_bn(m.value_head[0], m.value_head[1])
+    assert torch.equal(rows[1, :32], wp[:, :, 0, 0]) and not rows[0, :32].any() and not rows[2, :32].any()
+    for ky in range(3):
+        for kx in range(3):
+            assert torch.equal(rows[ky, 32 + 8 * kx:35 + 8 * kx], wv[:, :, ky, kx])
+            assert not rows[ky, 35 + 8 * kx:40 + 8 * kx].any()
+    assert not rows[:, 56:].any() and torch.equal(hb[:32], bp) and torch.equal(hb[32:35], bv)
