@@ -229,10 +229,13 @@ k_cnn_conv(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict__ l
                     uint4 o[2];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        float f[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = fmaxf(__uint_as_float(v[h * 8 + i]) + bias[c * 16 + h * 8 + i], 0.f);
-                        o[h] = make_uint4(pack16<F16>(f[0], f[1]), pack16<F16>(f[2], f[3]), pack16<F16>(f[4], f[5]), pack16<F16>(f[6], f[7]));
+                        // packed pair adds (FADD2), ReLU + rounding in one F2FP.RELU
+                        const float4 b0 = *reinterpret_cast<const float4 *>(bias + c * 16 + h * 8), b1 = *reinterpret_cast<const float4 *>(bias + c * 16 + h * 8 + 4);
+                        o[h] = make_uint4(
+                            pack16_relu<F16>(fadd2(make_float2(__uint_as_float(v[h * 8]), __uint_as_float(v[h * 8 + 1])), make_float2(b0.x, b0.y))),
+                            pack16_relu<F16>(fadd2(make_float2(__uint_as_float(v[h * 8 + 2]), __uint_as_float(v[h * 8 + 3])), make_float2(b0.z, b0.w))),
+                            pack16_relu<F16>(fadd2(make_float2(__uint_as_float(v[h * 8 + 4]), __uint_as_float(v[h * 8 + 5])), make_float2(b1.x, b1.y))),
+                            pack16_relu<F16>(fadd2(make_float2(__uint_as_float(v[h * 8 + 6]), __uint_as_float(v[h * 8 + 7])), make_float2(b1.z, b1.w))));
                     }
                     if (l < 2) {
 #pragma unroll

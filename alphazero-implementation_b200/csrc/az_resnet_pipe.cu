@@ -334,19 +334,22 @@ k_resnet_pipe(const uint64_t *__restrict__ leaf_bb0, const uint64_t *__restrict_
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         uint8_t *p = dst + (2 * c + h) * LBO_A + row_off[j];
-                        float f[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[h * 8 + i]) + bias[c * 16 + h * 8 + i];
+                        // packed pair adds (FADD2), ReLU + rounding in one F2FP.RELU: a third of the scalar version's instructions
+                        const float4 b0 = *reinterpret_cast<const float4 *>(bias + c * 16 + h * 8), b1 = *reinterpret_cast<const float4 *>(bias + c * 16 + h * 8 + 4);
+                        float2 f[4];
+                        f[0] = fadd2(make_float2(__uint_as_float(v[h * 8]), __uint_as_float(v[h * 8 + 1])), make_float2(b0.x, b0.y));
+                        f[1] = fadd2(make_float2(__uint_as_float(v[h * 8 + 2]), __uint_as_float(v[h * 8 + 3])), make_float2(b0.z, b0.w));
+                        f[2] = fadd2(make_float2(__uint_as_float(v[h * 8 + 4]), __uint_as_float(v[h * 8 + 5])), make_float2(b1.x, b1.y));
+                        f[3] = fadd2(make_float2(__uint_as_float(v[h * 8 + 6]), __uint_as_float(v[h * 8 + 7])), make_float2(b1.z, b1.w));
                         if (skip) {
                             const uint4 s = *reinterpret_cast<const uint4 *>(p);
-                            const float2 s0 = unpack16<F16>(s.x), s1 = unpack16<F16>(s.y), s2 = unpack16<F16>(s.z), s3 = unpack16<F16>(s.w);
-                            f[0] += s0.x; f[1] += s0.y; f[2] += s1.x; f[3] += s1.y;
-                            f[4] += s2.x; f[5] += s2.y; f[6] += s3.x; f[7] += s3.y;
+                            f[0] = fadd2(f[0], unpack16<F16>(s.x));
+                            f[1] = fadd2(f[1], unpack16<F16>(s.y));
+                            f[2] = fadd2(f[2], unpack16<F16>(s.z));
+                            f[3] = fadd2(f[3], unpack16<F16>(s.w));
                         }
                         uint4 o = make_uint4(0, 0, 0, 0);
-                        if (valid[j])
-                            o = make_uint4(pack16<F16>(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f)), pack16<F16>(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f)),
-                                           pack16<F16>(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f)), pack16<F16>(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f)));
+                        if (valid[j]) o = make_uint4(pack16_relu<F16>(f[0]), pack16_relu<F16>(f[1]), pack16_relu<F16>(f[2]), pack16_relu<F16>(f[3]));
                         *reinterpret_cast<uint4 *>(p) = o;
                     }
                     if (j == RPT - 1) {
