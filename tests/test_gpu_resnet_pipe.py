@@ -128,3 +128,33 @@ def test_wide_kernel_is_deterministic_and_independent_of_the_batch_composition(d
         eng.close()
     assert outs[0][0].shape[0] > 2000
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_wide_kernel_timing_hook_counts_launches_and_stamps_durations():
+    """`az_resnet_wide_set_timing` (what bench.py times the headline kernel with inside its timed region): the device buffer counts the
+    launches and holds {first CTA start, last CTA end} of each on the global timer; switching the hook off stops the counting."""
+    from alphazero_implementation_b200 import _lib
+
+    lib = _lib.load()
+    cap = 8
+    buf = torch.zeros(4 + 2 * cap, dtype=torch.int64, device="cuda")
+    buf[4::2] = -1
+    torch.manual_seed(1)
+    model = az.ResNet(num_res_blocks=2, num_channels=64).cuda().eval()
+    eng = _engine_with_leaves(500, seed=3, compact=True)
+    net = InferenceNet(model, dtype=torch.bfloat16, trunk_variant=4)
+    try:
+        assert lib.az_resnet_wide_set_timing(buf.data_ptr(), cap) == 0
+        for _ in range(3):
+            net.forward_leaves(eng)
+        torch.cuda.synchronize()
+        assert int(buf[0]) == 3 and int(buf[1]) == 0
+        dur = (buf[5:5 + 6:2] - buf[4:4 + 6:2]).cpu()
+        assert (dur > 1_000).all() and (dur < 50_000_000).all(), dur  # ns: a launch of 500 positions takes tens of microseconds
+        assert int(buf[4 + 2 * 3]) == -1 and int(buf[5 + 2 * 3]) == 0  # untouched slot
+    finally:
+        lib.az_resnet_wide_set_timing(None, 0)
+    net.forward_leaves(eng)
+    torch.cuda.synchronize()
+    assert int(buf[0]) == 3
+    eng.close()
