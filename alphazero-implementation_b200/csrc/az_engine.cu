@@ -66,8 +66,8 @@ struct Arena {
     uint8_t *leaf_player, *leaf_status, *leaf_depth;
     uint32_t *path;    // [E][PATH_STRIDE]
     uint32_t *tstats;  // [E][NSTAT]
-    int32_t *eval_list;   // [E] slots whose leaf waits for the evaluator, ascending (k_compact_leaves)
-    int32_t *eval_count;  // [4] [0] = entries in eval_list
+    int32_t *eval_list;   // [E] slots whose leaf waits for the evaluator: ascending (k_compact_leaves) or in ticket order (k_expand_select<COMPACT>)
+    int32_t *eval_count;  // [4] [0] = entries in eval_list; [2..3] one 64-bit word: tickets | warps through << 32 (k_expand_select<COMPACT>; zero between launches)
     // game in progress per slot
     uint64_t *g_bb0, *g_bb1;  // [E][42]
     uint8_t *g_player;        // [E][42]
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(64) k_run_sims(Arena a, int n_active, int S, d
 // ------------------------------------------------------------------------------------------------
 // split path, step 1: search.py:69-79
 template <int TPW, bool LAT>
-__device__ __forceinline__ void select_body(const Arena &a, int n_active, double c_puct) {
+__device__ __forceinline__ bool select_body(const Arena &a, int n_active, double c_puct) {
     constexpr int TREES = 2 * TPW;
     constexpr int NL = 32 / TPW;
     const int lane = threadIdx.x & 31;
@@ -753,7 +753,7 @@ __device__ __forceinline__ void select_body(const Arena &a, int n_active, double
     const bool alive = in_range && err == 0;
     const int lit = lane & (NL - 1);
     if (in_range && !alive && lit == 0) a.leaf_status[t] = AZ_LEAF_IDLE;
-    if (!__any_sync(FULL, alive)) return;
+    if (!__any_sync(FULL, alive)) return false;
     const bool writer = alive && lit == 0;
     uint32_t *path = a.path + (size_t)tt * PATH_STRIDE;
     const bool r_can = (c < c4::W) && !(((rb0 | rb1) >> (c4::STRIDE * c + 5)) & 1ull);
@@ -782,6 +782,7 @@ __device__ __forceinline__ void select_body(const Arena &a, int n_active, double
     }
     __syncwarp();
     if (alive && L.term) backup(tm, path, L.depth, L.win ? 1.0 : 0.0, true, lit, NL);
+    return writer && !L.term;  // this lane wrote AZ_LEAF_EVAL for its tree
 }
 
 // split path, step 3: search.py:87-91 with the evaluator's outputs
@@ -884,12 +885,33 @@ k_expand_backup(Arena a, int n_active, const float *__restrict__ policy, const f
 // Steps 3 and 1 of consecutive simulations in one launch: expansion + backup of simulation k, then the selection of simulation
 // k + 1 (same thread -> tree mapping in both, so a tree is only ever touched by its own warp; __syncwarp orders the two halves).
 // One launch less per simulation step of the network-in-the-loop path.
-template <int TPW, bool LAT>
+// COMPACT: the list of the slots whose new leaf waits for the evaluator (what k_compact_leaves writes in one more launch) is built
+// here.  One 64-bit atomic per warp on the word at eval_count[2..3]: the low half hands out list positions for the warp's up-to-TPW
+// slots, the high half counts the warps that are through - the warp that finds every other warp's ticket taken publishes the total
+// in eval_count[0] and zeroes the word for the next launch.  No fences: the next kernel on the stream is the first reader.  The
+// list is a permutation of k_compact_leaves' ascending one (the order is the order of the tickets); the evaluators scatter their
+// outputs to the slots' rows and a position's outputs do not depend on the batch it falls into, so the search is unchanged.
+template <int TPW, bool LAT, bool COMPACT>
 __global__ void __launch_bounds__(64)
 k_expand_select(Arena a, int n_active, const float *__restrict__ policy, const float *__restrict__ values, int policy_kind, double c_puct) {
     expand_backup_body<TPW>(a, n_active, policy, values, policy_kind);
     __syncwarp();
-    select_body<TPW, LAT>(a, n_active, c_puct);
+    const bool wants = select_body<TPW, LAT>(a, n_active, c_puct);
+    if (COMPACT) {
+        const int lane = threadIdx.x & 31;
+        const unsigned m = __ballot_sync(FULL, wants);
+        unsigned long long *word = reinterpret_cast<unsigned long long *>(a.eval_count + 2);
+        unsigned long long old = 0ull;
+        if (lane == 0) {
+            old = atomicAdd(word, (1ull << 32) | (unsigned long long)__popc(m));
+            if ((unsigned)(old >> 32) == gridDim.x * 2u - 1u) {  // every other warp of the launch has its ticket
+                a.eval_count[0] = (int32_t)((unsigned)old + (unsigned)__popc(m));
+                *word = 0ull;
+            }
+        }
+        const int at = (int)__shfl_sync(FULL, (unsigned)old, 0);
+        if (wants) a.eval_list[at + __popc(m & ((1u << lane) - 1u))] = blockIdx.x * (2 * TPW) + (threadIdx.x >> 5) * TPW + lane / (32 / TPW);
+    }
 }
 
 // Ordered compaction of the slots whose leaf waits for the evaluator (status AZ_LEAF_EVAL): eval_list[0 .. count) ascending.
@@ -1513,7 +1535,7 @@ struct az_engine {
     int force_hot_nodes;  // -1 = automatic
     int last_hot_nodes;
     int sims_done;  // simulations run on the current roots (arena and tables are sized for num_simulations)
-    bool compact;        // az_set_leaf_compaction: every selection is followed by k_compact_leaves
+    int compact;         // az_set_leaf_compaction: 1 = every selection is followed by k_compact_leaves, 2 = az_expand_backup_select builds the list itself
     bool compact_valid;  // eval_list / eval_count describe the leaves of the last selection
     uint64_t init0, init1;
     int initpl;
@@ -1992,7 +2014,7 @@ int32_t az_select_leaves(az_engine *h, void *stream) {
     else AZ_SEL(4);
 #undef AZ_SEL
     AZ_LAUNCH_CHECK(h, "k_select");
-    h->compact_valid = h->compact;
+    h->compact_valid = h->compact != 0;
     if (h->compact) {
         k_compact_leaves<<<1, 1024, 0, S(stream)>>>(h->a.leaf_status, n, h->a.eval_list, h->a.eval_count, env_int("AZ_COMPACT_STAGE", 1));
         AZ_LAUNCH_CHECK(h, "k_compact_leaves");
@@ -2036,18 +2058,24 @@ int32_t az_expand_backup_select(az_engine *h, const float *policy, const float *
     const int n = h->n_active;
     const int tpb = 2 * (32 / h->G);
     const bool lat = latency_variant(h, blocks_for(n, tpb));
+    const bool fused = h->compact == 2;
 #define AZ_ES(TPW_)                                                                                                                   \
     do {                                                                                                                              \
-        if (lat) k_expand_select<TPW_, true><<<blocks_for(n, tpb), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind, h->cfg.c_puct);  \
-        else k_expand_select<TPW_, false><<<blocks_for(n, tpb), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind, h->cfg.c_puct);     \
+        if (fused) {                                                                                                                  \
+            if (lat) k_expand_select<TPW_, true, true><<<blocks_for(n, tpb), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind, h->cfg.c_puct);  \
+            else k_expand_select<TPW_, false, true><<<blocks_for(n, tpb), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind, h->cfg.c_puct);     \
+        } else {                                                                                                                      \
+            if (lat) k_expand_select<TPW_, true, false><<<blocks_for(n, tpb), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind, h->cfg.c_puct); \
+            else k_expand_select<TPW_, false, false><<<blocks_for(n, tpb), 64, 0, S(stream)>>>(h->a, n, policy, values, policy_kind, h->cfg.c_puct);    \
+        }                                                                                                                             \
     } while (0)
     if (h->G == 32) AZ_ES(1);
     else if (h->G == 16) AZ_ES(2);
     else AZ_ES(4);
 #undef AZ_ES
     AZ_LAUNCH_CHECK(h, "k_expand_select");
-    h->compact_valid = h->compact;
-    if (h->compact) {
+    h->compact_valid = h->compact != 0;
+    if (h->compact == 1) {
         k_compact_leaves<<<1, 1024, 0, S(stream)>>>(h->a.leaf_status, n, h->a.eval_list, h->a.eval_count, env_int("AZ_COMPACT_STAGE", 1));
         AZ_LAUNCH_CHECK(h, "k_compact_leaves");
     }
@@ -2085,7 +2113,8 @@ int32_t az_leaf_compact(az_engine *h, const int32_t **eval_list, const int32_t *
 
 int32_t az_set_leaf_compaction(az_engine *h, int32_t on) {
     if (!h) return AZ_E_INVALID;
-    h->compact = on != 0;
+    if (on < 0 || on > 2) return fail(h, AZ_E_INVALID, "%s", "az_set_leaf_compaction: 0 (off), 1 (one more launch, ascending list) or 2 (fused into az_expand_backup_select)");
+    h->compact = on;
     return AZ_OK;
 }
 

@@ -93,6 +93,7 @@ class Engine:
         self.h = h
         self.n_active = self.num_games
         self.leaf_compaction = False
+        self.leaf_compaction_fused = False
         self.tree_capacity = self.lib.az_tree_capacity(self.h)
 
     # -- plumbing --------------------------------------------------------------------------------
@@ -182,10 +183,13 @@ class Engine:
         self.n_active = n
 
     # -- search ----------------------------------------------------------------------------------
-    def set_leaf_compaction(self, on: bool):
-        """Follow every selection with the ordered list of the slots that wait for an evaluation (the ResNet kernels walk it)."""
-        self._check(self.lib.az_set_leaf_compaction(self.h, int(bool(on))), "az_set_leaf_compaction")
+    def set_leaf_compaction(self, on: bool, fused: bool = False):
+        """Every selection also writes the list of the slots that wait for an evaluation (the ResNet / CNN kernels walk it): in one
+        more launch, ascending - or, `fused`, inside `expand_backup_select` itself, in the order the warps finished."""
+        mode = (2 if fused else 1) if on else 0
+        self._check(self.lib.az_set_leaf_compaction(self.h, mode), "az_set_leaf_compaction")
         self.leaf_compaction = bool(on)
+        self.leaf_compaction_fused = mode == 2
 
     def run_simulations(self, num_sims: int, eval_kind: int):
         self._check(self.lib.az_run_simulations(self.h, int(num_sims), int(eval_kind), _stream()), "az_run_simulations")
@@ -214,6 +218,20 @@ class Engine:
         assert policy.shape[0] >= self.n_active and policy.shape[-1] == 7 and values.shape[-1] == 2
         self._check(self.lib.az_expand_backup_select(self.h, _ptr(policy, allow_pinned=True), _ptr(values, allow_pinned=True), policy_kind,
                                                      _stream()), "az_expand_backup_select")
+
+    def leaf_compact(self):
+        """The engine's list of the slots whose leaf waits for an evaluation and its length (`az_leaf_compact`), as views of the
+        device arrays - `None` when the last selection ran without compaction."""
+        lst, cnt = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.az_leaf_compact(self.h, C.byref(lst), C.byref(cnt)), "az_leaf_compact")
+        if not lst.value or not cnt.value:
+            return None
+
+        class _Raw:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = dict(shape=(n,), typestr="<i4", data=(ptr, False), version=2)
+
+        return torch.as_tensor(_Raw(lst.value, self.num_games), device=self.device), torch.as_tensor(_Raw(cnt.value, 4), device=self.device)
 
     def leaf_info(self):
         n = self.n_active

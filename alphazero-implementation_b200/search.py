@@ -90,7 +90,9 @@ class _GraphedStep:
 
     def __init__(self, engine: Engine, net, layout: int):
         self.engine, self.net, self.layout = engine, net, layout
-        engine.set_leaf_compaction(getattr(net, "wants_leaf_compaction", False))  # before the first selection (and any capture)
+        # before the first selection (and any capture).  AZ_COMPACT_FUSED=0: the list of the leaves to evaluate comes from one more
+        # launch per simulation (k_compact_leaves) instead of from k_expand_select itself
+        engine.set_leaf_compaction(getattr(net, "wants_leaf_compaction", False), fused=os.environ.get("AZ_COMPACT_FUSED", "1") != "0")
         self.graph = None
         self.graph_unrolled = None
         self.n = -1
@@ -240,10 +242,13 @@ class AlphaZeroSearch:
         """Kernels of libaz_engine.so per self-play move step (`simulate_and_move`)."""
         if self._mode == "builtin":
             return 1
-        # k_select; S - 1 x (evaluator or gather, k_expand_select); evaluator, k_expand_backup; k_sample_moves - plus one
-        # k_compact_leaves per selection when the evaluator walks the compacted leaf list
+        # k_select; S - 1 x (evaluator or gather, k_expand_select); evaluator, k_expand_backup; k_sample_moves - plus, when the
+        # evaluator walks the compacted leaf list, one k_compact_leaves after k_select (the later lists come out of k_expand_select)
+        # or, AZ_COMPACT_FUSED=0, one per selection
         S = self.num_simulations
-        return 2 * S + 2 + (S if getattr(self._net, "wants_leaf_compaction", False) else 0)
+        if not getattr(self._net, "wants_leaf_compaction", False):
+            return 2 * S + 2
+        return 2 * S + 2 + (1 if os.environ.get("AZ_COMPACT_FUSED", "1") != "0" else S)
 
     def close(self):
         if self._engine is not None:

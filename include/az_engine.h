@@ -166,7 +166,10 @@ int32_t az_leaf_players(az_engine *h, const uint8_t **player);
  * az_set_leaf_compaction(h, 1): every az_select_leaves / az_expand_backup_select is followed by one more small launch that writes
  * the ordered list of the slots whose leaf waits for the evaluator (status AZ_LEAF_EVAL) and its length; the ResNet evaluators
  * then walk that list and scatter their outputs to the slots' rows.  az_leaf_compact returns the two DEVICE pointers, or NULLs
- * when the last selection ran without compaction (the evaluators then compute every slot's row, zeros for the others). */
+ * when the last selection ran without compaction (the evaluators then compute every slot's row, zeros for the others).
+ * az_set_leaf_compaction(h, 2): az_expand_backup_select builds the list itself (no extra launch): the same slots in the order the
+ * warps finished their selections, not ascending - for consumers that scatter per slot, as all evaluators of this library do;
+ * az_select_leaves (once per search) still takes the extra launch. */
 int32_t az_set_leaf_compaction(az_engine *h, int32_t on);
 int32_t az_leaf_compact(az_engine *h, const int32_t **eval_list, const int32_t **eval_count);
 
