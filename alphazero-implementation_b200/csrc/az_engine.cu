@@ -1130,82 +1130,54 @@ k_env_step(const uint64_t *__restrict__ bb0, const uint64_t *__restrict__ bb1, c
     if (ostatus) ostatus[i] = status;
 }
 
-// 4 positions per thread: 128-bit loads/stores of the bitboards, 32-bit loads/stores of the byte arrays.
-// Used when every pointer is present and 16-byte aligned (the normal case); the scalar kernel covers the rest.
-__device__ __forceinline__ void env_step_one(uint64_t &b0, uint64_t &b1, int &pl, int cc, uint8_t &legal, uint8_t &ended,
-                                             int8_t &r0, uint8_t &status) {
-    c4::Terminal T = c4::terminal_of(b0, b1);
-    status = 1;
-    if (!T.ended && cc < c4::W && !(((b0 | b1) >> (c4::STRIDE * cc + 5)) & 1ull)) {
-        const uint64_t bit = c4::drop_bit(b0 | b1, cc);
-        if (pl == 0) b0 |= bit; else b1 |= bit;
-        const bool win = c4::has4_nb(pl ? b1 : b0);
-        T.ended = win || c4::is_full(b0 | b1);
-        T.reward0 = win ? (pl == 0 ? 1 : -1) : 0;
-        pl ^= 1;
-        status = 0;
-    }
-    legal = T.ended ? 0 : (uint8_t)c4::legal_mask(b0 | b1);
-    ended = T.ended ? 1 : 0;
-    r0 = T.reward0;
-}
-
+// 4 positions per thread: 128-bit loads / stores of the bitboards, 32-bit loads / stores of the byte arrays; used when every
+// pointer is present and 16-byte aligned (the normal case), the scalar kernels cover the rest.  The rules run on the 32-bit halves
+// of the boards (c4::h32): the 64-bit formulation compiles to ALU-pipe instructions only (697 per 4 positions in the first version
+// of the step kernel) and that pipe bounded the kernels at 59 % / 53 % of HBM; with the low-word shifts, the byte packing and the
+// column arithmetic on the FMA pipe it is 498 ALU + 133 FMA (75 % / 71 %, profiles/r02_rules_kernels.json).
+template <int MODE>
 __global__ void __launch_bounds__(256)
-k_env_step_v4(const ulonglong2 *__restrict__ bb0, const ulonglong2 *__restrict__ bb1, const uint32_t *__restrict__ player,
-              const uint32_t *__restrict__ col, long long quads, ulonglong2 *o0, ulonglong2 *o1, uint32_t *opl, uint32_t *olegal,
-              uint32_t *oended, uint2 *oreward, uint32_t *ostatus) {
+k_env_step_h(const uint4 *__restrict__ bb0, const uint4 *__restrict__ bb1, const uint32_t *__restrict__ player,
+             const uint32_t *__restrict__ col, long long quads, uint4 *o0, uint4 *o1, uint32_t *opl, uint32_t *olegal,
+             uint32_t *oended, uint2 *oreward, uint32_t *ostatus) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= quads) return;
-    const ulonglong2 a0 = bb0[2 * i], a1 = bb0[2 * i + 1], c0 = bb1[2 * i], c1 = bb1[2 * i + 1];
-    uint64_t x0[4] = {a0.x, a0.y, a1.x, a1.y}, x1[4] = {c0.x, c0.y, c1.x, c1.y};
-    const uint32_t pw = player[i], cw = col[i];
-    uint32_t plw = 0, lgw = 0, enw = 0, stw = 0;
-    uint32_t rw[2] = {0, 0};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        int pl = (pw >> (8 * k)) & 1;
-        uint8_t lg, en, st;
-        int8_t r0;
-        env_step_one(x0[k], x1[k], pl, (cw >> (8 * k)) & 0xFF, lg, en, r0, st);
-        plw |= (uint32_t)pl << (8 * k);
-        lgw |= (uint32_t)lg << (8 * k);
-        enw |= (uint32_t)en << (8 * k);
-        stw |= (uint32_t)st << (8 * k);
-        const uint32_t pair = (uint32_t)(uint8_t)r0 | ((uint32_t)(uint8_t)(int8_t)-r0 << 8);
-        rw[k >> 1] |= pair << (16 * (k & 1));
-    }
-    o0[2 * i] = make_ulonglong2(x0[0], x0[1]);
-    o0[2 * i + 1] = make_ulonglong2(x0[2], x0[3]);
-    o1[2 * i] = make_ulonglong2(x1[0], x1[1]);
-    o1[2 * i + 1] = make_ulonglong2(x1[2], x1[3]);
-    opl[i] = plw;
-    olegal[i] = lgw;
-    oended[i] = enw;
-    oreward[i] = make_uint2(rw[0], rw[1]);
+    const uint4 a0 = bb0[2 * i], a1 = bb0[2 * i + 1], c0 = bb1[2 * i], c1 = bb1[2 * i + 1];
+    const uint32_t pw = player[i] & 0x01010101u, cw = col[i];
+    using namespace c4::h32;
+    const uint32_t px = mad_u32(pw, 0x80u, 0u);
+    const Step s0 = env_step<MODE>(a0.x, a0.y, c0.x, c0.y, player_mask(px, 0), byte_of(cw, 0));
+    const Step s1 = env_step<MODE>(a0.z, a0.w, c0.z, c0.w, player_mask(px, 1), byte_of(cw, 1));
+    const Step s2 = env_step<MODE>(a1.x, a1.y, c1.x, c1.y, player_mask(px, 2), byte_of(cw, 2));
+    const Step s3 = env_step<MODE>(a1.z, a1.w, c1.z, c1.w, player_mask(px, 3), byte_of(cw, 3));
+    o0[2 * i] = make_uint4(s0.lo0, s0.hi0, s1.lo0, s1.hi0);
+    o0[2 * i + 1] = make_uint4(s2.lo0, s2.hi0, s3.lo0, s3.hi0);
+    o1[2 * i] = make_uint4(s0.lo1, s0.hi1, s1.lo1, s1.hi1);
+    o1[2 * i + 1] = make_uint4(s2.lo1, s2.hi1, s3.lo1, s3.hi1);
+    // four bytes to a word: a * 2^k + b on the FMA pipe (the fields do not overlap)
+    const uint32_t stw = mad_u32(s3.status, 1u << 24, mad_u32(s2.status, 1u << 16, mad_u32(s1.status, 1u << 8, s0.status)));
+    opl[i] = pw ^ stw ^ 0x01010101u;  // the side to move changes where the move was made
+    olegal[i] = mad_u32(s3.info.legal, 1u << 24, mad_u32(s2.info.legal, 1u << 16, mad_u32(s1.info.legal, 1u << 8, s0.info.legal)));
+    oended[i] = mad_u32(s3.info.ended, 1u << 24, mad_u32(s2.info.ended, 1u << 16, mad_u32(s1.info.ended, 1u << 8, s0.info.ended)));
+    oreward[i] = make_uint2(mad_u32(s1.info.pair, 1u << 16, s0.info.pair), mad_u32(s3.info.pair, 1u << 16, s2.info.pair));
     ostatus[i] = stw;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(256)
-k_state_info_v4(const ulonglong2 *__restrict__ bb0, const ulonglong2 *__restrict__ bb1, long long quads, uint32_t *olegal,
-                uint32_t *oended, uint2 *oreward) {
+k_state_info_h(const uint4 *__restrict__ bb0, const uint4 *__restrict__ bb1, long long quads, uint32_t *olegal, uint32_t *oended,
+               uint2 *oreward) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= quads) return;
-    const ulonglong2 a0 = bb0[2 * i], a1 = bb0[2 * i + 1], c0 = bb1[2 * i], c1 = bb1[2 * i + 1];
-    const uint64_t x0[4] = {a0.x, a0.y, a1.x, a1.y}, x1[4] = {c0.x, c0.y, c1.x, c1.y};
-    uint32_t lgw = 0, enw = 0, rw[2] = {0, 0};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const bool w0 = c4::has4_nb(x0[k]), w1 = c4::has4_nb(x1[k]);
-        const bool ended = w0 || w1 || c4::is_full(x0[k] | x1[k]);
-        const int8_t r0 = w0 ? 1 : (w1 ? -1 : 0);
-        lgw |= (ended ? 0u : c4::legal_mask(x0[k] | x1[k])) << (8 * k);
-        enw |= (ended ? 1u : 0u) << (8 * k);
-        const uint32_t pair = (uint32_t)(uint8_t)r0 | ((uint32_t)(uint8_t)(int8_t)-r0 << 8);
-        rw[k >> 1] |= pair << (16 * (k & 1));
-    }
-    olegal[i] = lgw;
-    oended[i] = enw;
-    oreward[i] = make_uint2(rw[0], rw[1]);
+    const uint4 a0 = bb0[2 * i], a1 = bb0[2 * i + 1], c0 = bb1[2 * i], c1 = bb1[2 * i + 1];
+    const c4::h32::Info s0 = c4::h32::state_info<MODE>(a0.x, a0.y, c0.x, c0.y);
+    const c4::h32::Info s1 = c4::h32::state_info<MODE>(a0.z, a0.w, c0.z, c0.w);
+    const c4::h32::Info s2 = c4::h32::state_info<MODE>(a1.x, a1.y, c1.x, c1.y);
+    const c4::h32::Info s3 = c4::h32::state_info<MODE>(a1.z, a1.w, c1.z, c1.w);
+    using c4::h32::mad_u32;
+    olegal[i] = mad_u32(s3.legal, 1u << 24, mad_u32(s2.legal, 1u << 16, mad_u32(s1.legal, 1u << 8, s0.legal)));
+    oended[i] = mad_u32(s3.ended, 1u << 24, mad_u32(s2.ended, 1u << 16, mad_u32(s1.ended, 1u << 8, s0.ended)));
+    oreward[i] = make_uint2(mad_u32(s1.pair, 1u << 16, s0.pair), mad_u32(s3.pair, 1u << 16, s2.pair));
 }
 
 __global__ void __launch_bounds__(256)
@@ -1750,6 +1722,14 @@ int32_t az_device(const az_engine *h) { return h ? h->cfg.device : -1; }
 int64_t az_launch_count(const az_engine *h) { return h ? h->launches : 0; }
 int32_t az_tree_capacity(const az_engine *h) { return h ? h->a.cap : 0; }
 
+// AZ_RULES_MODE: the 4-in-line test of the vector rules kernels - 1 (the default) = left shifts, low words on the FMA pipe; 0 =
+// right shifts on the ALU pipe (for the A/B).  Identical results
+static int rules_mode() {
+    static int mode = -2;
+    if (mode == -2) mode = env_int("AZ_RULES_MODE", 1);
+    return mode;
+}
+
 int32_t az_env_step(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, const uint8_t *player, const uint8_t *col,
                     int64_t n, uint64_t *o0, uint64_t *o1, uint8_t *opl, uint8_t *olegal, uint8_t *oended,
                     int8_t *oreward, uint8_t *ostatus, void *stream) {
@@ -1762,12 +1742,17 @@ int32_t az_env_step(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, cons
     for (const void *p : ptrs) vec = vec && p && (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
     const long long quads = vec ? n / 4 : 0, head = quads * 4;
     if (quads) {
-        k_env_step_v4<<<blocks_for(quads, 256), 256, 0, S(stream)>>>(
-            reinterpret_cast<const ulonglong2 *>(bb0), reinterpret_cast<const ulonglong2 *>(bb1), reinterpret_cast<const uint32_t *>(player),
-            reinterpret_cast<const uint32_t *>(col), quads, reinterpret_cast<ulonglong2 *>(o0), reinterpret_cast<ulonglong2 *>(o1),
-            reinterpret_cast<uint32_t *>(opl), reinterpret_cast<uint32_t *>(olegal), reinterpret_cast<uint32_t *>(oended),
-            reinterpret_cast<uint2 *>(oreward), reinterpret_cast<uint32_t *>(ostatus));
-        AZ_LAUNCH_CHECK(h, "k_env_step_v4");
+        const int mode = rules_mode();
+#define AZ_ENV_H(M_)                                                                                                                \
+    k_env_step_h<M_><<<blocks_for(quads, 256), 256, 0, S(stream)>>>(                                                                \
+        reinterpret_cast<const uint4 *>(bb0), reinterpret_cast<const uint4 *>(bb1), reinterpret_cast<const uint32_t *>(player),     \
+        reinterpret_cast<const uint32_t *>(col), quads, reinterpret_cast<uint4 *>(o0), reinterpret_cast<uint4 *>(o1),                \
+        reinterpret_cast<uint32_t *>(opl), reinterpret_cast<uint32_t *>(olegal), reinterpret_cast<uint32_t *>(oended),              \
+        reinterpret_cast<uint2 *>(oreward), reinterpret_cast<uint32_t *>(ostatus))
+        if (mode == 0) AZ_ENV_H(0);
+        else AZ_ENV_H(1);
+#undef AZ_ENV_H
+        AZ_LAUNCH_CHECK(h, "k_env_step_h");
     }
     if (head < n) {
 #define OFF(p, k) ((p) ? (p) + (k) : (p))
@@ -1792,11 +1777,15 @@ int32_t az_state_info(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, co
     for (const void *p : ptrs) vec = vec && p && (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
     const long long quads = vec ? n / 4 : 0, head = quads * 4;
     if (quads) {
-        k_state_info_v4<<<blocks_for(quads, 256), 256, 0, S(stream)>>>(reinterpret_cast<const ulonglong2 *>(bb0),
-                                                                  reinterpret_cast<const ulonglong2 *>(bb1), quads,
-                                                                  reinterpret_cast<uint32_t *>(olegal), reinterpret_cast<uint32_t *>(oended),
-                                                                  reinterpret_cast<uint2 *>(oreward));
-        AZ_LAUNCH_CHECK(h, "k_state_info_v4");
+        const int mode = rules_mode();
+#define AZ_INFO_H(M_)                                                                                                                      \
+    k_state_info_h<M_><<<blocks_for(quads, 256), 256, 0, S(stream)>>>(reinterpret_cast<const uint4 *>(bb0), reinterpret_cast<const uint4 *>(bb1), \
+                                                                      quads, reinterpret_cast<uint32_t *>(olegal),                         \
+                                                                      reinterpret_cast<uint32_t *>(oended), reinterpret_cast<uint2 *>(oreward))
+        if (mode == 0) AZ_INFO_H(0);
+        else AZ_INFO_H(1);
+#undef AZ_INFO_H
+        AZ_LAUNCH_CHECK(h, "k_state_info_h");
     }
     if (head < n) {
 #define OFF(p, k) ((p) ? (p) + (k) : (p))

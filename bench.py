@@ -7,7 +7,7 @@
 Workload.  N = 1: BASELINE.json configs[2] — 16384 concurrent games x 800 simulations/move with a bf16 ResNet-style
 policy/value net (4 residual blocks x 64 channels, random init, 25.3 MFLOP per position) in the loop: every simulation step
 is one evaluator launch over the leaves that wait for an evaluation (`k_resnet_wide`, hand-written tcgen05, leaf gather + heads
-fused) and two tree launches (`k_expand_select`, `k_compact_leaves`).  N > 1: configs[3] — 65536 games sharded over the ranks (65536 / N per GPU, "strong" split of the
+fused) and one tree launch (`k_expand_select`: expansion + backup, the next selection, and the list of the leaves to evaluate).  N > 1: configs[3] — 65536 games sharded over the ranks (65536 / N per GPU, "strong" split of the
 fixed total), and the episodes finished in the timed region are all-gathered over NCCL INSIDE the timed region.
 One STEP = one move step of the self-play loop for every game (episode_generator.py:48-78): 800 simulations per tree, then the
 move (`az_sample_moves`: record the samples, draw the moves, recycle finished games).
@@ -531,7 +531,7 @@ def run_b200(args):
     drained = []
     step_ev = [ev0]
     for i in range(K):
-        search.simulate_and_move(eng, u_all[n_pre + i])  # 800 x (k_resnet_wide, k_expand_select, k_compact_leaves) replayed from a CUDA graph + k_sample_moves
+        search.simulate_and_move(eng, u_all[n_pre + i])  # 800 x (k_resnet_wide, k_expand_select) replayed from a CUDA graph + k_sample_moves
         if (i + 1) % 16 == 0 or i + 1 == K:  # device -> device; the ring holds 2 E + 64 episodes, ~E / 20 finish per step.  Draining
             drained.append(eng.drain_episodes_device(drain_bufs[i // 16]))  # (a host synchronisation) every step left the GPU queue empty at every
         step_ev.append(torch.cuda.Event(enable_timing=True))  # step boundary: any host hiccup there showed up as a 10 % slower step

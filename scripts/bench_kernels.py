@@ -58,6 +58,12 @@ def sinfo():
 ms = timeit(sinfo)
 b = N * (16 + 4)
 res["k_state_info"] = dict(items=N, bytes_per_item=20, ms=ms, gbs=b / ms / 1e6, frac=b / ms / 1e6 / peak)
+if "rules" in sys.argv[1:]:  # only the two rules kernels (AZ_RULES_MODE selects the formulation)
+    import os
+    res["rules_mode"] = os.environ.get("AZ_RULES_MODE", "default")
+    print(json.dumps(res))
+    eng.close()
+    sys.exit(0)
 M = 1 << 22
 for name, layout, per in (("grid_f32", LAYOUT_GRID_F32, 168), ("planes_f32", LAYOUT_PLANES_F32, 504), ("planes_bf16", LAYOUT_PLANES_BF16, 252),
                           ("planes_bf16_nhwc8", LAYOUT_PLANES_BF16_NHWC, 672)):
