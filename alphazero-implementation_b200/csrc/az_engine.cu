@@ -1133,8 +1133,8 @@ k_env_step(const uint64_t *__restrict__ bb0, const uint64_t *__restrict__ bb1, c
 // 4 positions per thread: 128-bit loads / stores of the bitboards, 32-bit loads / stores of the byte arrays; used when every
 // pointer is present and 16-byte aligned (the normal case), the scalar kernels cover the rest.  The rules run on the 32-bit halves
 // of the boards (c4::h32): the 64-bit formulation compiles to ALU-pipe instructions only (697 per 4 positions in the first version
-// of the step kernel) and that pipe bounded the kernels at 59 % / 53 % of HBM; with the low-word shifts, the byte packing and the
-// column arithmetic on the FMA pipe it is 498 ALU + 133 FMA (75 % / 71 %, profiles/r02_rules_kernels.json).
+// of the step kernel) and that pipe bounded the kernels at 59 % / 53 % of HBM; with the low-word shifts, three directions' high-word
+// shifts, the byte packing and the column arithmetic on the FMA pipe it is 424 ALU + 280 FMA (76 % / 76 %, profiles/r02_rules_kernels.json).
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_env_step_h(const uint4 *__restrict__ bb0, const uint4 *__restrict__ bb1, const uint32_t *__restrict__ player,
@@ -1722,11 +1722,11 @@ int32_t az_device(const az_engine *h) { return h ? h->cfg.device : -1; }
 int64_t az_launch_count(const az_engine *h) { return h ? h->launches : 0; }
 int32_t az_tree_capacity(const az_engine *h) { return h ? h->a.cap : 0; }
 
-// AZ_RULES_MODE: the 4-in-line test of the vector rules kernels - 1 (the default) = left shifts, low words on the FMA pipe; 0 =
-// right shifts on the ALU pipe (for the A/B).  Identical results
+// AZ_RULES_MODE: the 4-in-line test of the vector rules kernels - 0 = right shifts on the ALU pipe; 1 = left shifts, low words on the
+// FMA pipe; 2 / 3 / 4 (the default) = also the high words of 1 / 2 / 3 of the four directions (for the A/B).  Identical results
 static int rules_mode() {
     static int mode = -2;
-    if (mode == -2) mode = env_int("AZ_RULES_MODE", 1);
+    if (mode == -2) mode = env_int("AZ_RULES_MODE", 4);
     return mode;
 }
 
@@ -1750,7 +1750,10 @@ int32_t az_env_step(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, cons
         reinterpret_cast<uint32_t *>(opl), reinterpret_cast<uint32_t *>(olegal), reinterpret_cast<uint32_t *>(oended),              \
         reinterpret_cast<uint2 *>(oreward), reinterpret_cast<uint32_t *>(ostatus))
         if (mode == 0) AZ_ENV_H(0);
-        else AZ_ENV_H(1);
+        else if (mode == 2) AZ_ENV_H(2);
+        else if (mode == 3) AZ_ENV_H(3);
+        else if (mode == 1) AZ_ENV_H(1);
+        else AZ_ENV_H(4);
 #undef AZ_ENV_H
         AZ_LAUNCH_CHECK(h, "k_env_step_h");
     }
@@ -1783,7 +1786,10 @@ int32_t az_state_info(az_engine *h, const uint64_t *bb0, const uint64_t *bb1, co
                                                                       quads, reinterpret_cast<uint32_t *>(olegal),                         \
                                                                       reinterpret_cast<uint32_t *>(oended), reinterpret_cast<uint2 *>(oreward))
         if (mode == 0) AZ_INFO_H(0);
-        else AZ_INFO_H(1);
+        else if (mode == 2) AZ_INFO_H(2);
+        else if (mode == 3) AZ_INFO_H(3);
+        else if (mode == 1) AZ_INFO_H(1);
+        else AZ_INFO_H(4);
 #undef AZ_INFO_H
         AZ_LAUNCH_CHECK(h, "k_state_info_h");
     }

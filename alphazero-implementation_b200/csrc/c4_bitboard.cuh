@@ -135,23 +135,28 @@ C4_HD void shr64(uint32_t lo, uint32_t hi, uint32_t &olo, uint32_t &ohi) {
     ohi = hi >> S;
 }
 
-// (hi:lo) << S for a constant 1 <= S <= 31: the low word as a multiplication (FMA pipe), the high word as one funnel shift
-template <int S>
+// (hi:lo) << S for a constant 1 <= S <= 31: the low word as a multiplication (FMA pipe); the high word as one funnel shift (ALU
+// pipe) or, HM, as hi * 2^S + mulhi(lo, 2^S) (FMA pipe, the mulhi at about a third of a multiply-add's rate)
+template <int S, bool HM>
 C4_HD void shl64(uint32_t lo, uint32_t hi, uint32_t &olo, uint32_t &ohi) {
     olo = mad_u32(lo, 1u << S, 0u);
+    if (HM) {
+        ohi = mad_u32(hi, 1u << S, mulhi_u32(lo, 1u << S));
+    } else {
 #if defined(__CUDA_ARCH__)
-    ohi = __funnelshift_l(lo, hi, S);
+        ohi = __funnelshift_l(lo, hi, S);
 #else
-    ohi = (hi << S) | (lo >> (32 - S));
+        ohi = (hi << S) | (lo >> (32 - S));
 #endif
+    }
 }
 // the same test with left shifts: stones at p, p - S, p - 2 S, p - 3 S (bits shifted out of the 64 belong to no cell)
-template <int S>
+template <int S, bool HM>
 C4_HD void line4_l(uint32_t lo, uint32_t hi, uint32_t &rlo, uint32_t &rhi) {
     uint32_t al, ah, bl, bh;
-    shl64<S>(lo, hi, al, ah);
+    shl64<S, HM>(lo, hi, al, ah);
     const uint32_t ml = lo & al, mh = hi & ah;
-    shl64<2 * S>(ml, mh, bl, bh);
+    shl64<2 * S, HM>(ml, mh, bl, bh);
     rlo |= ml & bl;
     rhi |= mh & bh;
 }
@@ -176,17 +181,18 @@ C4_HD void line4(uint32_t lo, uint32_t hi, uint32_t &rlo, uint32_t &rhi) {
     rhi |= mh & bh;
 }
 
-// has4 of a board given as halves.  MODE 1 (what the kernels run): left shifts - low words on the FMA pipe, high words on the ALU
-// pipe: 24 ALU + 8 FMA instructions; MODE 0: right shifts, everything on the ALU pipe (32), kept for the A/B.  (Right shifts as
-// mulhi were measured too: IMAD.HI issues at about a quarter of IMAD's rate and the kernels got no faster.)
+// has4 of a board given as halves.  MODE >= 1: left shifts - low words on the FMA pipe, high words on the ALU pipe (MODE 1: 24 ALU
+// + 8 FMA instructions) or, for MODE - 1 of the four directions, on the FMA pipe too (MODE 4, what the kernels run: 18 ALU + 20
+// FMA); MODE 0: right shifts, everything on the ALU pipe (32), kept for the A/B.  (Right shifts as mulhi everywhere were
+// measured too: IMAD.HI issues at about a third of IMAD's rate and the kernels got no faster.)
 template <int MODE>
 C4_HD bool has4(uint32_t lo, uint32_t hi) {
     uint32_t rlo = 0u, rhi = 0u;
-    if (MODE == 1) {
-        line4_l<1>(lo, hi, rlo, rhi);
-        line4_l<7>(lo, hi, rlo, rhi);
-        line4_l<6>(lo, hi, rlo, rhi);
-        line4_l<8>(lo, hi, rlo, rhi);
+    if (MODE >= 1) {  // MODE - 1 = directions whose high-word shifts run on the FMA pipe as well
+        line4_l<1, (MODE >= 2)>(lo, hi, rlo, rhi);
+        line4_l<7, (MODE >= 3)>(lo, hi, rlo, rhi);
+        line4_l<6, (MODE >= 4)>(lo, hi, rlo, rhi);
+        line4_l<8, (MODE >= 5)>(lo, hi, rlo, rhi);
     } else {
         line4<1>(lo, hi, rlo, rhi);
         line4<7>(lo, hi, rlo, rhi);

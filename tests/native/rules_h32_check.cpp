@@ -73,7 +73,7 @@ int main(int argc, char **argv) {
         for (int ply = 0; ply < 60; ++ply) {  // keeps stepping after the end: finished positions are inputs too
             const uint32_t r = rnd();
             const uint32_t cc = (r & 15u) == 0 ? (r >> 8) & 255u : (r >> 8) % 7u;  // 1 in 16: any byte
-            if (check<0>(b0, b1, pl, cc) || check<1>(b0, b1, pl, cc)) return 1;
+            if (check<0>(b0, b1, pl, cc) || check<1>(b0, b1, pl, cc) || check<2>(b0, b1, pl, cc) || check<3>(b0, b1, pl, cc) || check<4>(b0, b1, pl, cc)) return 1;
             // every other column byte on this position now and then
             if ((r & 0xFF0000u) == 0)
                 for (uint32_t c = 0; c < 256; ++c)
