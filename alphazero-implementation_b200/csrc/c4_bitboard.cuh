@@ -92,8 +92,8 @@ C4_HD Terminal terminal_of(uint64_t b0, uint64_t b1) {
 // On sm_100 the integer work of a kernel is split over two issue pipes of 64 lanes / clk / SM each: shifts and logic ops (SHF,
 // LOP3, IADD3, SEL) on the ALU pipe, integer multiply-adds (IMAD, IMAD.HI) on the FMA pipe.  The 64-bit formulation above
 // compiles to ALU-pipe instructions only and that pipe, not HBM, bounds the kernels.  Here the 4-in-line test
-// shifts LEFT, the low word by a multiplication with a power of two (FMA pipe), the high word by one funnel shift, and the
-// byte packing / unpacking around it uses multiply-adds and byte permutes.
+// shifts LEFT, the low word by a multiplication with a power of two (FMA pipe), the high word by one funnel shift (ALU pipe) or
+// by a multiply-add on a mulhi (FMA pipe), and the byte packing / unpacking around it uses multiply-adds and byte permutes.
 namespace h32 {
 
 constexpr uint32_t TOP_LO = 0x04081020u, TOP_HI = 0x8102u;          // TOP_ROW
