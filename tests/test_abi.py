@@ -106,3 +106,19 @@ def test_level_loop_of_the_fused_tree_kernel_stays_straight_line(built_lib):
     assert any("LDS.128" in t for t in level) and not any(re.search(r"\bLD\.E", t) for t in level)
     # two divisions (multiply + 4 FMAs each), their sum, and the next level's numerator (c * P) * sqrt(N): 13 fp64 operations
     assert sum(t.split()[0 if not t.startswith("@") else 1].startswith(("DFMA", "DMUL", "DADD")) for t in level) <= 13
+
+
+def test_rules_kernels_split_their_integer_work_over_both_issue_pipes(built_lib):
+    """The streaming rules kernels are bound by integer issue, not by HBM: what made them faster is the split
+    of that work over the ALU pipe (logic ops, funnel shifts, selects) and the FMA pipe (shifts written as multiplications).  Checked
+    on the SASS of the variants the library runs by default: straight-line code, and per 4 positions at most 440 / 215 ALU-pipe
+    instructions (the 64-bit kernels of round 1: 697 / 379) beside at least 250 / 170 integer multiply-adds."""
+    path, _ = built_lib
+    alu = ("LOP3", "SHF", "IADD3", "ISETP", "SEL", "PRMT", "PLOP3", "LEA", "VIADD", "P2R", "R2P")
+    for pattern, max_alu, min_fma in ((r"k_env_step_hILi4E", 440, 250), (r"k_state_info_hILi4E", 215, 170)):
+        ins = [t.split()[1] if t.startswith("@") else t.split()[0] for _, t in _sass_of(path, pattern)]
+        assert len(ins) > 300, pattern
+        assert not any(op.startswith(("BSSY", "BSYNC", "CALL")) for op in ins)
+        n_alu = sum(op.startswith(alu) for op in ins)
+        n_fma = sum(op.startswith("IMAD") for op in ins)
+        assert n_alu <= max_alu and n_fma >= min_fma, (pattern, n_alu, n_fma)
